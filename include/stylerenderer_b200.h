@@ -1,0 +1,120 @@
+/* stylerenderer_b200 -- C ABI of the B200-native (sm_100a) StyleRenderer hot path.
+ *
+ * This is the drop-in boundary: every entry point replaces one C/C++ symbol that sits under the
+ * reference's pybind shims.  Plain pointers and sizes only, no torch types.
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers owned by the caller (outputs pre-allocated, inputs
+ *     never modified); `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every function is asynchronous w.r.t. the host and returns 0 on success, a negative
+ *     SR_ERR_* code for argument errors, or a positive cudaError_t for launch errors;
+ *     sr_last_error() returns a thread-local human readable message for the last failure;
+ *   - functions are stateless and re-entrant (the reference ops are called from the forward
+ *     thread and from autograd's backward thread).
+ */
+#ifndef STYLERENDERER_B200_H_
+#define STYLERENDERER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SR_OK 0
+#define SR_ERR_INVALID_ARGUMENT (-1)
+#define SR_ERR_UNSUPPORTED (-2)
+#define SR_ERR_DRIVER (-3)
+
+/* ABI version (bumped on any signature change) and last error text. */
+int sr_abi_version(void);
+const char *sr_last_error(void);
+/* Number of kernel launches issued by this library in this process (bench.py's gpu_launches). */
+int64_t sr_launch_count(void);
+
+/* ------------------------------------------------------------------ fused bias + leaky-ReLU ----
+ * Replaces `bool fused_bias_act_op(float*,const float*,const float*,const float*,int,int,float,
+ * float,int,int,int,int,int,int)` (reference op/fused_bias_act.cpp:3-4, kernel
+ * op/fused_bias_act_kernel.cu:14-42).
+ *   t = x[i] + (bias ? bias[(i / step_b) % size_b] : 0);  r = ref ? ref[i] : 0
+ *   act*10+grad: 30 -> t>0 ? t : alpha*t;  31 -> r>0 ? t : alpha*t;  32 -> 0;  10/11 -> t;  12 -> 0
+ *   y[i] = that * scale
+ * bias / ref may be NULL (the reference's "empty tensor").  NCHW: step_b = H*W, size_b = C.
+ * channels-last or [B,C]: step_b = 1, size_b = C.  size_x is 64-bit (the reference caps at 2^31). */
+int sr_fused_bias_act_f32(float *y, const float *x, const float *bias, const float *ref,
+                          int act, int grad, float alpha, float scale,
+                          int64_t size_x, int64_t step_b, int64_t size_b, void *stream);
+
+/* Backward of the leaky-ReLU with the bias gradient fused into the same pass (the reference makes a
+ * second full pass: op/fused_act.py:27-38):
+ *   dx[i] = scale * (y[i] > 0 ? gy[i] : alpha*gy[i]);   dbias[c] = sum_{i in channel c} dx[i]
+ * dbias (size_b floats) is zeroed by the call; pass dbias = NULL to skip the reduction. */
+int sr_fused_lrelu_backward_f32(float *dx, float *dbias, const float *gy, const float *y,
+                                float alpha, float scale,
+                                int64_t size_x, int64_t step_b, int64_t size_b, void *stream);
+
+/* ------------------------------------------------------------------ upfirdn2d ------------------
+ * Replaces `bool upfirdn2d_op(float*, const float*, const float*, UpFirDn2DKernelParams&, int, int)`
+ * (reference op/upfirdn2d.cpp:2-23, kernels op/upfirdn2d_kernel.cu:79-257): zero-stuff by `up`, pad
+ * (negative pads crop), TRUE convolution with taps[kh][kw], keep every `down`-th sample.
+ *   x:   [major, in_h, in_w, minor]  (NCHW planes: major = N*C, minor = 1)
+ *   out: [major, out_h, out_w, minor], out = (in*up + pad0 + pad1 - k) / down + 1 (floor)
+ * Any up/down >= 1 and any tap count are accepted (specialised kernels cover the model's
+ * 4x4 up1/down1, up2, down2 cases; everything else takes the generic kernel). */
+int sr_upfirdn2d_f32(float *out, const float *x, const float *taps,
+                     int64_t major, int64_t in_h, int64_t in_w, int64_t minor,
+                     int kernel_h, int kernel_w, int up_x, int up_y, int down_x, int down_y,
+                     int pad_x0, int pad_x1, int pad_y0, int pad_y1, void *stream);
+
+/* ------------------------------------------------------------------ rasterizer -----------------
+ * Replace `rasterize_gpu<scalar,int64_t>` / `rasterize_gpu_backward<scalar,int64_t>` (reference
+ * op/rasterize.cpp:14-19, kernels op/rasterize.cu:40-138, math op/rasterize.h:9-228).
+ *
+ * Forward: z-buffer rasterisation of `nf` triangles over `nv` vertices into h x w (h == w required:
+ * the reference swaps the two).
+ *   verts [b,nv,3] (or [nv,3] when shared_v), tris int64 [nf,3] when shared_f else [b,nf,3]
+ *   ids   int64 [b,h,w,3]  = winning triangle's vertex ids (+ nv*batch unless shared_v), 0 = background
+ *   bary  [b,h,w,3]        = normalised barycentric coefficients, 0 = background
+ *   keys  uint64 [b,h,w]   workspace (depth/triangle keys), contents undefined on return
+ * Deterministic: among equal depths the first triangle in list order wins, like the reference's
+ * CPU loop (the reference CUDA kernel is racy).  Bit-exact with that CPU loop for ids and bary.
+ * Optional fused attribute interpolation (reference op/rasterize.py:29-37): when tex != NULL,
+ *   out[b,y,x,:] = sum_k bary_k * tex[ids_k, :],  tex [b*nv, c] (row index = ids), out [b,h,w,c]. */
+int sr_rasterize_forward_f32(int64_t b, int64_t nv, int64_t nf, int64_t h, int64_t w,
+                             int shared_v, int shared_f, int perspective,
+                             const float *verts, const int64_t *tris,
+                             int64_t *ids, float *bary, uint64_t *keys, float eps,
+                             const float *tex, int64_t c, float *out, void *stream);
+int sr_rasterize_forward_f64(int64_t b, int64_t nv, int64_t nf, int64_t h, int64_t w,
+                             int shared_v, int shared_f, int perspective,
+                             const double *verts, const int64_t *tris,
+                             int64_t *ids, double *bary, uint64_t *keys, double eps,
+                             const double *tex, int64_t c, double *out, void *stream);
+/* size in bytes of the `keys` workspace for a given problem */
+int64_t sr_rasterize_workspace_bytes(int64_t b, int64_t h, int64_t w, int is_f64);
+
+/* Reference-shaped backward (`rasterize.backward`, op/rasterize.cpp:179-241): dcoeff [b,h,w,3,9]
+ * = d bary_i / d vertex_k.{x,y,z}; pixels whose three ids are not distinct are left untouched
+ * (the caller zero-fills, like the reference). n = vertices per image. */
+int sr_rasterize_dcoeff_f32(int64_t b, int64_t n, int64_t h, int64_t w, int perspective,
+                            const float *verts, const int64_t *ids, float *dcoeff, float eps, void *stream);
+int sr_rasterize_dcoeff_f64(int64_t b, int64_t n, int64_t h, int64_t w, int perspective,
+                            const double *verts, const int64_t *ids, double *dcoeff, double eps, void *stream);
+
+/* Fused backward of the whole `Rasterize` autograd function (reference op/rasterize.py:39-80, which
+ * materialises dcoeff and scatter-adds through a host-built sparse matrix):
+ *   grad_verts[ids_k,:] += sum_i (sum_c gout_c * tex[ids_i,c]) * dcoeff[i][k][:]
+ *   grad_tex[ids_k,c]   += gout_c * bary_k
+ * by atomic accumulation; grad_verts [b*n,3] / grad_tex [b*n,c] must be zero-filled by the caller;
+ * either may be NULL.  Summation order is not deterministic (float atomics). */
+int sr_rasterize_backward_f32(int64_t b, int64_t n, int64_t h, int64_t w, int64_t c, int perspective,
+                              const float *verts, const float *tex, const int64_t *ids, const float *bary,
+                              const float *gout, float *grad_verts, float *grad_tex, float eps, void *stream);
+int sr_rasterize_backward_f64(int64_t b, int64_t n, int64_t h, int64_t w, int64_t c, int perspective,
+                              const double *verts, const double *tex, const int64_t *ids, const double *bary,
+                              const double *gout, double *grad_verts, double *grad_tex, double eps, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STYLERENDERER_B200_H_ */
