@@ -1,0 +1,552 @@
+// Z-buffer mesh rasteriser (forward, reference-shaped dcoeff, fused backward) for sm_100a.
+//
+// Replaces rasterize_gpu / rasterize_gpu_backward and their kernels (reference op/rasterize.cu:40-138,
+// math op/rasterize.h:9-228) and the sparse-matrix scatter of op/rasterize.py:39-80.
+//
+// Determinism and bit-exactness: the reference CUDA kernel races (z test and payload write are not
+// one atomic) and its CPU loop is the only well-defined behaviour: strict `zbuf < z`, so among equal
+// depths the FIRST triangle in list order wins.  Here every (pixel, triangle) candidate is folded into
+// one 64-bit key  [ order-preserving(z) : 32 | ~triangle_id : 32 ]  with a single atomicMax, which is
+// order independent and reproduces exactly that rule; a resolve pass then recomputes the winner's
+// coefficients with the same device function.  All geometry arithmetic uses round-to-nearest
+// intrinsics (__fmul_rn / __fadd_rn / __fdiv_rn ...) which the compiler never contracts into FMAs,
+// mirroring the FMA-free host build of the reference, so ids AND coefficients are bit-exact with
+// `rasterize_cpu` (oracle/raster_body.inc).  float64 uses a three-pass variant (max z, min id, resolve).
+//
+// Work decomposition (BFM-size meshes have < 1 covered pixel per triangle): one lane per triangle for
+// set-up and small boxes; triangles whose clamped box exceeds 32 pixels are re-distributed over the
+// warp (ballot + shuffle broadcast, 32 pixels per step) so a few big triangles cannot serialise a lane.
+#include "common.cuh"
+#include <float.h>
+
+namespace sr {
+namespace {
+
+constexpr int kThreads = 256;
+
+// ---- strictly rounded arithmetic ----------------------------------------------------------------
+template <typename T> struct RN;
+template <> struct RN<float> {
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float lowest() { return -FLT_MAX; }
+};
+template <> struct RN<double> {
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double lowest() { return -DBL_MAX; }
+};
+
+__device__ __forceinline__ uint32_t order_bits(float z) {
+    uint32_t u = __float_as_uint(z);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ uint64_t order_bits(double z) {
+    uint64_t u = (uint64_t)__double_as_longlong(z);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+template <typename T>
+struct Tri {
+    T p[9];        // projected corners: x, y in pixel units, z untouched
+    T E[9];        // edge-function matrix, rows: constant, d/dx, d/dy
+    T det;
+    int x_lo, x_hi, y_lo, y_hi;
+};
+
+__device__ __forceinline__ int clamp_lo(double v) { return v <= 0.0 ? 0 : (v > 1.0e9 ? 1000000000 : (int)ceil(v)); }
+__device__ __forceinline__ int clamp_hi(double v, int span) {
+    return v >= (double)(span - 1) ? span - 1 : (v < -1.0 ? -1 : (int)floor(v));
+}
+
+// reference op/rasterize.h:9-75 (`barycentric` with det_ != NULL); mirrors oracle sr_tri_setup.
+template <typename T>
+__device__ __forceinline__ bool tri_setup(Tri<T> &t, int span_x, int span_y, bool perspective, T eps)
+{
+    using R = RN<T>;
+    T xmin = 0, xmax = 0, ymin = 0, ymax = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        T *q = t.p + 3 * c;
+        if (perspective) {
+            if (q[2] >= -eps) return false;
+            q[0] = R::div(q[0], -q[2]);
+            q[1] = R::div(q[1], -q[2]);
+        }
+        // ((1 + x) * W / 2) - .5 : the reference subtracts a double .5 and rounds back, which for
+        // +,-,*,/ equals the single-precision operation (innocuous double rounding)
+        q[0] = R::sub(R::div(R::mul(R::add((T)1, q[0]), (T)span_x), (T)2), (T)0.5);
+        q[1] = R::sub(R::div(R::mul(R::sub((T)1, q[1]), (T)span_y), (T)2), (T)0.5);
+        if (c == 0) { xmin = xmax = q[0]; ymin = ymax = q[1]; }
+        else {
+            if (xmin > q[0]) xmin = q[0]; else if (xmax < q[0]) xmax = q[0];
+            if (ymin > q[1]) ymin = q[1]; else if (ymax < q[1]) ymax = q[1];
+        }
+    }
+    t.x_lo = clamp_lo((double)xmin); t.x_hi = clamp_hi((double)xmax, span_x);
+    t.y_lo = clamp_lo((double)ymin); t.y_hi = clamp_hi((double)ymax, span_y);
+    if (t.x_hi < t.x_lo || t.y_hi < t.y_lo) return false;
+    const T *p = t.p;
+    T *E = t.E;
+    E[0] = R::sub(R::mul(p[3], p[7]), R::mul(p[4], p[6]));
+    E[1] = R::sub(R::mul(p[1], p[6]), R::mul(p[0], p[7]));
+    E[2] = R::sub(R::mul(p[0], p[4]), R::mul(p[1], p[3]));
+    T det = R::add(R::add(E[0], E[1]), E[2]);
+    if (det > eps) return false;
+    E[3] = R::sub(p[4], p[7]); E[4] = R::sub(p[7], p[1]); E[5] = R::sub(p[1], p[4]);
+    E[6] = R::sub(p[6], p[3]); E[7] = R::sub(p[0], p[6]); E[8] = R::sub(p[3], p[0]);
+    if (det < 0) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) E[c] = -E[c];
+        det = -det;
+    }
+    t.det = det;
+    return true;
+}
+
+// longest edge I of a zero-area triangle: project onto it (segment) or test the point (rasterize.h:105-120)
+template <typename T, int I>
+__device__ __forceinline__ bool degenerate_case(const Tri<T> &t, T px, T py, T len_i, T eps, T w[3])
+{
+    using R = RN<T>;
+    constexpr int J = (I + 1) % 3, K = (J + 1) % 3;
+    const T *E = t.E, *p = t.p;
+    if (len_i > eps) {
+        const T lj = R::add(R::mul(-R::sub(px, p[3 * K]), E[6 + I]), R::mul(R::sub(py, p[3 * K + 1]), E[3 + I]));
+        const T lk = R::sub(R::mul(R::sub(px, p[3 * J]), E[6 + I]), R::mul(R::sub(py, p[3 * J + 1]), E[3 + I]));
+        const T li = R::add(lj, lk);
+        w[I] = 0; w[J] = R::div(lj, li); w[K] = R::div(lk, li);
+        return w[J] >= -eps && w[K] >= -eps;
+    }
+    w[J] = 0; w[K] = 0; w[I] = 1;
+    const T dx = R::sub(px, p[3 * I]), dy = R::sub(py, p[3 * I + 1]);
+    const T d2 = R::add(R::mul(dx, dx), R::mul(dy, dy));
+    return d2 < eps;
+}
+
+// reference op/rasterize.h:76-142 (`normalize_coeff` + depth of `assign_buffer`); mirrors sr_tri_sample.
+template <typename T>
+__device__ __forceinline__ bool tri_sample(const Tri<T> &t, T px, T py, bool perspective, T eps, T w[3], T &z)
+{
+    using R = RN<T>;
+    const T *E = t.E, *p = t.p;
+    w[0] = R::add(R::add(E[0], R::mul(E[3], px)), R::mul(E[6], py));
+    w[1] = R::add(R::add(E[1], R::mul(E[4], px)), R::mul(E[7], py));
+    w[2] = R::add(R::add(E[2], R::mul(E[5], px)), R::mul(E[8], py));
+    if (w[0] < -eps || w[1] < -eps || w[2] < -eps) return false;
+    if (t.det > eps) {
+        T s = R::add(R::add(w[0], w[1]), w[2]);
+        w[0] = R::div(w[0], s); w[1] = R::div(w[1], s); w[2] = R::div(w[2], s);
+    } else {                                           // degenerate triangle (rasterize.h:87-120)
+        const T l0 = R::add(R::mul(E[3], E[3]), R::mul(E[6], E[6]));
+        const T l1 = R::add(R::mul(E[4], E[4]), R::mul(E[7], E[7]));
+        const T l2 = R::add(R::mul(E[5], E[5]), R::mul(E[8], E[8]));
+        int i = (l0 > l1) ? 0 : 1;
+        i = (((i == 0) ? l0 : l1) > l2) ? i : 2;
+        // compile-time indices only (dynamic indexing would push the whole Tri into local memory)
+        bool ok;
+        if (i == 0) ok = degenerate_case<T, 0>(t, px, py, l0, eps, w);
+        else if (i == 1) ok = degenerate_case<T, 1>(t, px, py, l1, eps, w);
+        else ok = degenerate_case<T, 2>(t, px, py, l2, eps, w);
+        if (!ok) return false;
+    }
+    if (perspective) {
+        w[0] = R::div(w[0], p[2]); w[1] = R::div(w[1], p[5]); w[2] = R::div(w[2], p[8]);
+        T s = R::add(R::add(w[0], w[1]), w[2]);
+        if (s >= -eps) return false;
+        w[0] = R::mul(w[0], s); w[1] = R::mul(w[1], s); w[2] = R::mul(w[2], s);
+        z = s;
+    } else {
+        z = R::add(R::add(R::mul(w[0], p[2]), R::mul(w[1], p[5])), R::mul(w[2], p[8]));
+    }
+    return true;
+}
+
+struct RasterGeom {
+    int64_t b, nv, nf;
+    int h, w;
+    int shared_v, shared_f, perspective;
+};
+
+template <typename T>
+__device__ __forceinline__ bool load_tri(Tri<T> &t, const T *__restrict__ V, const int64_t *__restrict__ F,
+                                         int64_t f, int64_t nv, int64_t ids[3])
+{
+    ids[0] = __ldg(F + 3 * f); ids[1] = __ldg(F + 3 * f + 1); ids[2] = __ldg(F + 3 * f + 2);
+    if (ids[0] < 0 || ids[1] < 0 || ids[2] < 0 || ids[0] >= nv || ids[1] >= nv || ids[2] >= nv) return false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const T *s = V + 3 * ids[k];
+        t.p[3 * k] = __ldg(s); t.p[3 * k + 1] = __ldg(s + 1); t.p[3 * k + 2] = __ldg(s + 2);
+    }
+    return true;
+}
+
+// PASS 0: float, packed (z, ~id) key.  PASS 1: double, max ordered z.  PASS 2: double, min id among z == zmax.
+template <typename T, int PASS>
+__device__ __forceinline__ void emit(const Tri<T> &t, int x, int y, uint32_t f, const RasterGeom &g, T eps,
+                                     uint64_t *__restrict__ zkeys, uint32_t *__restrict__ idkeys, int64_t img)
+{
+    T w[3], z;
+    if (!tri_sample<T>(t, (T)x, (T)y, g.perspective != 0, eps, w, z)) return;
+    if (!(z > RN<T>::lowest())) return;            // the buffer starts at -MAX and the test is strict; drops NaN
+    z = z + (T)0;                                  // -0 -> +0: they compare equal on the host
+    // reference pixel index is x + y*w (op/rasterize.cpp:42) with x spanning h and y spanning w (quirk 6)
+    const int64_t pix = (img * g.h * (int64_t)g.w) + (int64_t)y * g.w + x;
+    if (PASS == 0) {
+        const uint64_t key = ((uint64_t)order_bits((float)z) << 32) | (uint64_t)(0xffffffffu - f);
+        atomicMax(reinterpret_cast<unsigned long long *>(zkeys + pix), (unsigned long long)key);
+    } else if (PASS == 1) {
+        atomicMax(reinterpret_cast<unsigned long long *>(zkeys + pix), (unsigned long long)order_bits((double)z));
+    } else {
+        if (zkeys[pix] == order_bits((double)z)) atomicMin(idkeys + pix, f);
+    }
+}
+
+template <typename T, int PASS>
+__global__ void __launch_bounds__(kThreads)
+raster_tri_kernel(const RasterGeom g, const T *__restrict__ verts, const int64_t *__restrict__ tris,
+                  uint64_t *__restrict__ zkeys, uint32_t *__restrict__ idkeys, T eps)
+{
+    const int64_t total = g.b * g.nf;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    const uint32_t lane = threadIdx.x & 31u;
+    // warp-uniform trip count: every lane of a warp runs the same number of iterations
+    for (int64_t base = (int64_t)blockIdx.x * kThreads + (threadIdx.x & ~31u); base < total; base += stride) {
+        const int64_t item = base + lane;
+        Tri<T> t;
+        bool live = item < total;
+        int64_t img = 0;
+        uint32_t f = 0;
+        if (live) {
+            img = item / g.nf;
+            f = (uint32_t)(item - img * g.nf);
+            const T *V = verts + (g.shared_v ? 0 : img * g.nv * 3);
+            const int64_t *F = tris + (g.shared_f ? 0 : img * g.nf * 3);
+            int64_t ids[3];
+            live = load_tri<T>(t, V, F, f, g.nv, ids);
+            // reference passes (h, w) for (w, h): x spans h, y spans w (op/rasterize.cpp:38)
+            if (live) live = tri_setup<T>(t, g.h, g.w, g.perspective != 0, eps);
+        }
+        int bw = 0, area = 0;
+        if (live) { bw = t.x_hi - t.x_lo + 1; area = bw * (t.y_hi - t.y_lo + 1); }
+        const bool big = live && area > 32;
+        if (live && !big) {
+            for (int y = t.y_lo; y <= t.y_hi; ++y)
+                for (int x = t.x_lo; x <= t.x_hi; ++x) emit<T, PASS>(t, x, y, f, g, eps, zkeys, idkeys, img);
+        }
+        // big boxes: the whole warp walks the box of one lane at a time, 32 pixels per step
+        uint32_t pending = __ballot_sync(0xffffffffu, big);
+        while (pending) {
+            const int src = __ffs(pending) - 1;
+            pending &= pending - 1;
+            Tri<T> s;
+#pragma unroll
+            for (int c = 0; c < 9; ++c) { s.p[c] = __shfl_sync(0xffffffffu, t.p[c], src); s.E[c] = __shfl_sync(0xffffffffu, t.E[c], src); }
+            s.det = __shfl_sync(0xffffffffu, t.det, src);
+            s.x_lo = __shfl_sync(0xffffffffu, t.x_lo, src); s.y_lo = __shfl_sync(0xffffffffu, t.y_lo, src);
+            const int sbw = __shfl_sync(0xffffffffu, bw, src), sarea = __shfl_sync(0xffffffffu, area, src);
+            const uint32_t sf = __shfl_sync(0xffffffffu, f, src);
+            const int64_t simg = __shfl_sync(0xffffffffu, img, src);
+            for (int k = lane; k < sarea; k += 32) {
+                const int yy = k / sbw, xx = k - yy * sbw;
+                emit<T, PASS>(s, s.x_lo + xx, s.y_lo + yy, sf, g, eps, zkeys, idkeys, simg);
+            }
+        }
+    }
+}
+
+// One thread per pixel: decode the winner, recompute its coefficients, write ids / bary (/ interpolated tex).
+template <typename T, bool PACKED>
+__global__ void __launch_bounds__(kThreads)
+raster_resolve_kernel(const RasterGeom g, const T *__restrict__ verts, const int64_t *__restrict__ tris,
+                      const uint64_t *__restrict__ zkeys, const uint32_t *__restrict__ idkeys, T eps,
+                      int64_t *__restrict__ ids_out, T *__restrict__ bary_out,
+                      const T *__restrict__ tex, int c, T *__restrict__ out)
+{
+    const int64_t npix = g.b * g.h * (int64_t)g.w;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t pix = (int64_t)blockIdx.x * kThreads + threadIdx.x; pix < npix; pix += stride) {
+        const uint64_t key = zkeys[pix];
+        int64_t ids[3] = {0, 0, 0};
+        T w[3] = {0, 0, 0};
+        bool hit = key != 0;
+        if (hit) {
+            const uint32_t f = PACKED ? (0xffffffffu - (uint32_t)key) : idkeys[pix];
+            const int64_t img = pix / (g.h * (int64_t)g.w);
+            const int rem = (int)(pix - img * g.h * (int64_t)g.w);
+            const int y = rem / g.w, x = rem - y * g.w;
+            const T *V = verts + (g.shared_v ? 0 : img * g.nv * 3);
+            const int64_t *F = tris + (g.shared_f ? 0 : img * g.nf * 3);
+            Tri<T> t;
+            T z;
+            hit = load_tri<T>(t, V, F, f, g.nv, ids) && tri_setup<T>(t, g.h, g.w, g.perspective != 0, eps) &&
+                  tri_sample<T>(t, (T)x, (T)y, g.perspective != 0, eps, w, z);
+            if (hit && !g.shared_v) { ids[0] += g.nv * img; ids[1] += g.nv * img; ids[2] += g.nv * img; }
+            if (!hit) { ids[0] = ids[1] = ids[2] = 0; w[0] = w[1] = w[2] = 0; }
+        }
+        ids_out[3 * pix] = ids[0]; ids_out[3 * pix + 1] = ids[1]; ids_out[3 * pix + 2] = ids[2];
+        bary_out[3 * pix] = w[0]; bary_out[3 * pix + 1] = w[1]; bary_out[3 * pix + 2] = w[2];
+        if (tex) {
+            // op/rasterize.py:29-37: sum_k tex[ids_k] * bary_k  (background: row 0 times 0 = 0)
+            for (int ch = 0; ch < c; ++ch) {
+                T v = 0;
+                if (hit) v = tex[ids[0] * c + ch] * w[0] + tex[ids[1] * c + ch] * w[1] + tex[ids[2] * c + ch] * w[2];
+                out[pix * c + ch] = v;
+            }
+        }
+    }
+}
+
+// reference op/rasterize.h:168-228 (`barycentric_grad`); mirrors oracle sr_bary_grad.
+template <typename T>
+__device__ __forceinline__ bool bary_grad(const T q[9], T px, T py, T axis_x, T axis_y, bool perspective, T eps,
+                                          T out[27])
+{
+    using R = RN<T>;
+    const T u = R::div(R::add(R::sub(R::mul(px, (T)2), axis_x), (T)1), axis_x);
+    const T v = R::div(R::sub(R::add(R::mul(py, (T)-2), axis_y), (T)1), axis_y);
+    T E[9], det, cf[3];
+    E[0] = R::sub(R::mul(q[3], q[7]), R::mul(q[4], q[6]));
+    E[1] = R::sub(R::mul(q[1], q[6]), R::mul(q[0], q[7]));
+    E[2] = R::sub(R::mul(q[0], q[4]), R::mul(q[1], q[3]));
+    if (perspective) {
+        if (q[2] >= -eps || q[5] >= -eps || q[8] >= -eps) return false;
+        det = R::add(R::add(R::mul(E[0], q[2]), R::mul(E[1], q[5])), R::mul(E[2], q[8]));
+        if ((det >= -eps) & (det <= eps)) return false;
+        E[0] = -E[0]; E[1] = -E[1]; E[2] = -E[2];
+        E[3] = R::sub(R::mul(q[4], q[8]), R::mul(q[5], q[7]));
+        E[4] = R::sub(R::mul(q[2], q[7]), R::mul(q[1], q[8]));
+        E[5] = R::sub(R::mul(q[1], q[5]), R::mul(q[2], q[4]));
+        E[6] = R::sub(R::mul(q[5], q[6]), R::mul(q[3], q[8]));
+        E[7] = R::sub(R::mul(q[0], q[8]), R::mul(q[2], q[6]));
+        E[8] = R::sub(R::mul(q[2], q[3]), R::mul(q[0], q[5]));
+    } else {
+        det = R::add(R::add(E[0], E[1]), E[2]);
+        E[3] = R::sub(q[4], q[7]); E[4] = R::sub(q[7], q[1]); E[5] = R::sub(q[1], q[4]);
+        E[6] = R::sub(q[6], q[3]); E[7] = R::sub(q[0], q[6]); E[8] = R::sub(q[3], q[0]);
+    }
+    if (!(det < -eps || det > eps)) return false;
+#pragma unroll
+    for (int l = 0; l < 9; ++l) E[l] = R::div(E[l], det);
+    cf[0] = R::add(R::add(E[0], R::mul(E[3], u)), R::mul(E[6], v));
+    cf[1] = R::add(R::add(E[1], R::mul(E[4], u)), R::mul(E[7], v));
+    cf[2] = R::add(R::add(E[2], R::mul(E[5], u)), R::mul(E[8], v));
+#pragma unroll
+    for (int l = 0; l < 27; ++l) {
+        const int i = l / 9, j = (l + 1) % 3, k = (l / 3) % 3;
+        out[l] = R::mul(-cf[k], E[i + j * 3]);
+    }
+    if (perspective) {
+        const T tot = R::add(R::add(cf[0], cf[1]), cf[2]);
+#pragma unroll
+        for (int l = 0; l < 9; ++l) {
+            const T dsum = R::add(R::add(out[l], out[l + 9]), out[l + 18]);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const T corr = R::div(R::mul(cf[i], dsum), tot);
+                out[l + i * 9] = (l % 3 == 2) ? R::div(R::sub(-out[l + i * 9], corr), tot)
+                                              : R::div(R::sub(out[l + i * 9], corr), tot);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int l = 0; l < 9; ++l) out[2 + l * 3] = 0;
+    }
+    return true;
+}
+
+template <typename T>
+__device__ __forceinline__ bool gather_pixel_tri(const T *__restrict__ verts, const int64_t *__restrict__ I,
+                                                 int64_t limit, T q[9])
+{
+    const int64_t a = I[0], b = I[1], c = I[2];
+    if (a == b || a == c || b == c) return false;                       // op/rasterize.cpp:74
+    if (a < 0 || b < 0 || c < 0 || a >= limit || b >= limit || c >= limit) return false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        q[k] = __ldg(verts + 3 * a + k); q[3 + k] = __ldg(verts + 3 * b + k); q[6 + k] = __ldg(verts + 3 * c + k);
+    }
+    return true;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+raster_dcoeff_kernel(int64_t b, int64_t n, int h, int w, int perspective, const T *__restrict__ verts,
+                     const int64_t *__restrict__ ids, T *__restrict__ dcoeff, T eps)
+{
+    const int64_t npix = b * h * (int64_t)w;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t pix = (int64_t)blockIdx.x * kThreads + threadIdx.x; pix < npix; pix += stride) {
+        T q[9], d[27];
+        if (!gather_pixel_tri<T>(verts, ids + 3 * pix, n * b, q)) continue;
+        const int rem = (int)(pix % (h * (int64_t)w));
+        // reference passes ((scalar)h, (scalar)w) for (w, h) (op/rasterize.cpp:87)
+        if (!bary_grad<T>(q, (T)(rem % w), (T)(rem / w), (T)h, (T)w, perspective != 0, eps, d)) continue;
+#pragma unroll
+        for (int l = 0; l < 27; ++l) dcoeff[pix * 27 + l] = d[l];
+    }
+}
+
+// Fused backward: no dcoeff tensor, no sparse matrix -- contract in registers, scatter with atomics.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+raster_backward_kernel(int64_t b, int64_t n, int h, int w, int c, int perspective, const T *__restrict__ verts,
+                       const T *__restrict__ tex, const int64_t *__restrict__ ids, const T *__restrict__ bary,
+                       const T *__restrict__ gout, T *__restrict__ grad_v, T *__restrict__ grad_tex, T eps)
+{
+    const int64_t npix = b * h * (int64_t)w;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t pix = (int64_t)blockIdx.x * kThreads + threadIdx.x; pix < npix; pix += stride) {
+        const T w0 = bary[3 * pix], w1 = bary[3 * pix + 1], w2 = bary[3 * pix + 2];
+        if (w0 == (T)0 && w1 == (T)0 && w2 == (T)0) continue;           // background
+        const int64_t I[3] = {ids[3 * pix], ids[3 * pix + 1], ids[3 * pix + 2]};
+        const T wk[3] = {w0, w1, w2};
+        T diff[3] = {0, 0, 0};
+        for (int ch = 0; ch < c; ++ch) {
+            const T gc = gout[pix * c + ch];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                diff[k] += gc * __ldg(tex + I[k] * c + ch);
+                if (grad_tex) atomicAdd(grad_tex + I[k] * c + ch, gc * wk[k]);
+            }
+        }
+        if (!grad_v) continue;
+        T q[9], d[27];
+        if (!gather_pixel_tri<T>(verts, I, n * b, q)) continue;
+        const int rem = (int)(pix % (h * (int64_t)w));
+        if (!bary_grad<T>(q, (T)(rem % w), (T)(rem / w), (T)h, (T)w, perspective != 0, eps, d)) continue;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                if (a == 2 && !perspective) continue;                   // d/dz is exactly 0 in orthographic mode
+                const T s = diff[0] * d[k * 3 + a] + diff[1] * d[9 + k * 3 + a] + diff[2] * d[18 + k * 3 + a];
+                atomicAdd(grad_v + I[k] * 3 + a, s);
+            }
+    }
+}
+
+int grid_for(int64_t items, int per_sm) {
+    int64_t blocks = (items + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)kNumSMs * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+template <typename T>
+int rasterize_forward(int64_t b, int64_t nv, int64_t nf, int64_t h, int64_t w, int shared_v, int shared_f,
+                      int perspective, const T *verts, const int64_t *tris, int64_t *ids, T *bary,
+                      uint64_t *keys, T eps, const T *tex, int64_t c, T *out, void *stream)
+{
+    constexpr bool kF32 = sizeof(T) == 4;
+    SR_REQUIRE(b >= 0 && nv >= 0 && nf >= 0 && h >= 1 && w >= 1, "rasterize: bad sizes");
+    SR_REQUIRE(h == w, "rasterize: only square targets (the reference swaps h and w; non-square renders wrongly)");
+    SR_REQUIRE(h <= 32768, "rasterize: target too large");
+    SR_REQUIRE(nf < 0xffffffffll, "rasterize: too many triangles");
+    if (b == 0) return SR_OK;
+    SR_REQUIRE(ids && bary && keys, "rasterize: null output/workspace");
+    SR_REQUIRE(!tex || (out && c >= 1), "rasterize: tex given without out / channels");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t npix = b * h * w;
+    RasterGeom g;
+    g.b = b; g.nv = nv; g.nf = nf; g.h = (int)h; g.w = (int)w;
+    g.shared_v = shared_v; g.shared_f = shared_f; g.perspective = perspective;
+    if (eps < 0) eps = -eps;
+    uint32_t *idkeys = reinterpret_cast<uint32_t *>(keys + npix);
+    cudaError_t e = cudaMemsetAsync(keys, 0, sizeof(uint64_t) * (size_t)npix, st);
+    if (e == cudaSuccess && !kF32) e = cudaMemsetAsync(idkeys, 0xff, sizeof(uint32_t) * (size_t)npix, st);
+    if (e != cudaSuccess) { set_error("rasterize: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    if (nf > 0 && verts && tris) {
+        const int grid = grid_for(b * nf, 16);
+        if constexpr (kF32) {
+            raster_tri_kernel<T, 0><<<grid, kThreads, 0, st>>>(g, verts, tris, keys, idkeys, eps);
+            count_launch();
+        } else {
+            raster_tri_kernel<T, 1><<<grid, kThreads, 0, st>>>(g, verts, tris, keys, idkeys, eps);
+            raster_tri_kernel<T, 2><<<grid, kThreads, 0, st>>>(g, verts, tris, keys, idkeys, eps);
+            count_launch(2);
+        }
+    }
+    raster_resolve_kernel<T, kF32><<<grid_for(npix, 16), kThreads, 0, st>>>(g, verts, tris, keys, idkeys, eps, ids, bary,
+                                                                           tex, (int)c, out);
+    count_launch();
+    return check_launch("sr_rasterize_forward");
+}
+
+template <typename T>
+int rasterize_dcoeff(int64_t b, int64_t n, int64_t h, int64_t w, int perspective, const T *verts,
+                     const int64_t *ids, T *dcoeff, T eps, void *stream)
+{
+    SR_REQUIRE(b >= 0 && n >= 0 && h >= 1 && w >= 1, "rasterize_dcoeff: bad sizes");
+    if (b == 0) return SR_OK;
+    SR_REQUIRE(verts && ids && dcoeff, "rasterize_dcoeff: null pointer");
+    if (eps < 0) eps = -eps;
+    raster_dcoeff_kernel<T><<<grid_for(b * h * w, 16), kThreads, 0, (cudaStream_t)stream>>>(
+        b, n, (int)h, (int)w, perspective, verts, ids, dcoeff, eps);
+    count_launch();
+    return check_launch("sr_rasterize_dcoeff");
+}
+
+template <typename T>
+int rasterize_backward(int64_t b, int64_t n, int64_t h, int64_t w, int64_t c, int perspective, const T *verts,
+                       const T *tex, const int64_t *ids, const T *bary, const T *gout, T *grad_v, T *grad_tex,
+                       T eps, void *stream)
+{
+    SR_REQUIRE(b >= 0 && n >= 0 && h >= 1 && w >= 1 && c >= 1, "rasterize_backward: bad sizes");
+    if (b == 0 || (!grad_v && !grad_tex)) return SR_OK;
+    SR_REQUIRE(verts && tex && ids && bary && gout, "rasterize_backward: null pointer");
+    if (eps < 0) eps = -eps;
+    raster_backward_kernel<T><<<grid_for(b * h * w, 16), kThreads, 0, (cudaStream_t)stream>>>(
+        b, n, (int)h, (int)w, (int)c, perspective, verts, tex, ids, bary, gout, grad_v, grad_tex, eps);
+    count_launch();
+    return check_launch("sr_rasterize_backward");
+}
+
+}  // namespace
+}  // namespace sr
+
+using namespace sr;
+
+extern "C" int64_t sr_rasterize_workspace_bytes(int64_t b, int64_t h, int64_t w, int is_f64) {
+    const int64_t npix = b * h * w;
+    return npix * 8 + (is_f64 ? npix * 4 : 0) + 16;
+}
+
+extern "C" int sr_rasterize_forward_f32(int64_t b, int64_t nv, int64_t nf, int64_t h, int64_t w, int shared_v,
+                                        int shared_f, int perspective, const float *verts, const int64_t *tris,
+                                        int64_t *ids, float *bary, uint64_t *keys, float eps, const float *tex,
+                                        int64_t c, float *out, void *stream) {
+    return rasterize_forward<float>(b, nv, nf, h, w, shared_v, shared_f, perspective, verts, tris, ids, bary, keys,
+                                    eps, tex, c, out, stream);
+}
+extern "C" int sr_rasterize_forward_f64(int64_t b, int64_t nv, int64_t nf, int64_t h, int64_t w, int shared_v,
+                                        int shared_f, int perspective, const double *verts, const int64_t *tris,
+                                        int64_t *ids, double *bary, uint64_t *keys, double eps, const double *tex,
+                                        int64_t c, double *out, void *stream) {
+    return rasterize_forward<double>(b, nv, nf, h, w, shared_v, shared_f, perspective, verts, tris, ids, bary, keys,
+                                     eps, tex, c, out, stream);
+}
+extern "C" int sr_rasterize_dcoeff_f32(int64_t b, int64_t n, int64_t h, int64_t w, int perspective,
+                                       const float *verts, const int64_t *ids, float *dcoeff, float eps, void *stream) {
+    return rasterize_dcoeff<float>(b, n, h, w, perspective, verts, ids, dcoeff, eps, stream);
+}
+extern "C" int sr_rasterize_dcoeff_f64(int64_t b, int64_t n, int64_t h, int64_t w, int perspective,
+                                       const double *verts, const int64_t *ids, double *dcoeff, double eps, void *stream) {
+    return rasterize_dcoeff<double>(b, n, h, w, perspective, verts, ids, dcoeff, eps, stream);
+}
+extern "C" int sr_rasterize_backward_f32(int64_t b, int64_t n, int64_t h, int64_t w, int64_t c, int perspective,
+                                         const float *verts, const float *tex, const int64_t *ids, const float *bary,
+                                         const float *gout, float *grad_verts, float *grad_tex, float eps, void *stream) {
+    return rasterize_backward<float>(b, n, h, w, c, perspective, verts, tex, ids, bary, gout, grad_verts, grad_tex, eps, stream);
+}
+extern "C" int sr_rasterize_backward_f64(int64_t b, int64_t n, int64_t h, int64_t w, int64_t c, int perspective,
+                                         const double *verts, const double *tex, const int64_t *ids, const double *bary,
+                                         const double *gout, double *grad_verts, double *grad_tex, double eps, void *stream) {
+    return rasterize_backward<double>(b, n, h, w, c, perspective, verts, tex, ids, bary, gout, grad_verts, grad_tex, eps, stream);
+}

@@ -1,0 +1,288 @@
+// upfirdn2d (zero-stuff -> pad -> FIR -> decimate) for sm_100a.
+//
+// Replaces the reference's upfirdn2d_op / upfirdn2d_kernel / upfirdn2d_kernel_large
+// (reference op/upfirdn2d.cpp:2-83, op/upfirdn2d_kernel.cu:79-257).  Semantics are those of
+// `upfirdn2d_native` (reference op/upfirdn2d.py:159-200), restated in oracle/sr_oracle.c:
+//   out[o] = sum_k taps[K-1-k] * U[o*down + k - pad0],  U = input zero-stuffed by `up`.
+//
+// HBM-bound (algorithmic bytes 4*major*(in_h*in_w + out_h*out_w)); the kernels are
+// organised so that the FIR costs ~1.3 shared-memory loads and K*K/up^2 FMAs per output:
+//   * poly-phase form: for output o only taps k = k0 + j*up contribute, k0 = (pad0 - o*down) mod up,
+//     reading input ib + j with ib = (o*down + k0 - pad0) / up -- no multiplies by stuffed zeros;
+//   * a CTA stages a zero-padded input tile (several whole planes at low resolution, so 4x4..32x32
+//     planes still fill the CTA) in shared memory, each thread then produces a 4 x VY register patch
+//     from a register window filled with 128/64-bit shared loads; all phase/tap indices are
+//     compile-time (the pad phase is a template parameter);
+//   * 128-bit output stores when rows are 16-byte aligned.
+// Everything that is not one of the specialised (up, down, taps, phase) combinations, or has
+// minor > 1, takes the generic one-thread-per-output kernel.
+#include "common.cuh"
+
+namespace sr {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int VX = 4;                 // outputs per thread along x
+
+// ---- compile-time poly-phase index helpers (one axis) -----------------------------------------
+__host__ __device__ constexpr int cmod(int a, int b) { return ((a % b) + b) % b; }
+// first contributing tap of output (base + v), base*down = 0 (mod up), pad phase PH = pad0 mod up
+__host__ __device__ constexpr int tap0(int v, int UP, int DOWN, int PH) { return cmod(PH - v * DOWN, UP); }
+// input offset of output (base + v) relative to output `base`'s first input sample
+__host__ __device__ constexpr int in_off(int v, int UP, int DOWN, int PH) {
+    return (v * DOWN + tap0(v, UP, DOWN, PH) - PH) / UP;
+}
+
+struct TileGeom {
+    int in_h, in_w, out_h, out_w;
+    int pqx, pqy;                     // floor(pad0 / up) per axis
+    int txs_log2, tys_log2;           // threads per tile along x / y (powers of two), planes/tile = 256 >> (sum)
+    int tin_h, tin_w, tin_stride;     // staged input tile (per plane) and its padded row stride
+    int tiles_x, tiles_y;             // tiles per plane
+    int64_t major;
+    FastDiv div_tiles_x, div_tiles_y;
+    int vec_store;                    // out rows 16-byte aligned
+};
+
+template <int UP, int DOWN, int KH, int KW, int PHX, int PHY, int VY>
+__global__ void __launch_bounds__(kThreads)
+upfirdn2d_tile_kernel(float *__restrict__ out, const float *__restrict__ x, const float *__restrict__ taps,
+                      const TileGeom g)
+{
+    static_assert(KH % UP == 0 && KW % UP == 0, "tap count must be a multiple of up");
+    static_assert((VX * DOWN) % UP == 0 && (VY * DOWN) % UP == 0, "patch must cover whole phases");
+    constexpr int JX = KW / UP, JY = KH / UP;                           // taps per output per axis
+    constexpr int NWX = in_off(VX - 1, UP, DOWN, PHX) + JX;             // register window
+    constexpr int NWY = in_off(VY - 1, UP, DOWN, PHY) + JY;
+    constexpr int SX = VX * DOWN / UP, SY = VY * DOWN / UP;             // window step between patches
+    constexpr int LDW = (SX % 4 == 0) ? 4 : ((SX % 2 == 0) ? 2 : 1);    // shared load width
+    constexpr int NWXP = (NWX + LDW - 1) / LDW * LDW;
+
+    extern __shared__ __align__(16) float s_in[];
+
+    const int txs = 1 << g.txs_log2, tys = 1 << g.tys_log2;
+    const int planes_per_tile = kThreads >> (g.txs_log2 + g.tys_log2);
+    const int tow = txs * VX, toh = tys * VY;
+
+    // tile decode: blockIdx.x = ((plane_group * tiles_y) + ty) * tiles_x + tx
+    uint32_t t = blockIdx.x, tile_x, tile_y, pg;
+    g.div_tiles_x.divmod(t, t, tile_x);
+    g.div_tiles_y.divmod(t, pg, tile_y);
+    const int64_t plane0 = (int64_t)pg * planes_per_tile;
+    const int ox0 = tile_x * tow, oy0 = tile_y * toh;
+    const int ix0 = ox0 * DOWN / UP - g.pqx, iy0 = oy0 * DOWN / UP - g.pqy;   // tile origin in the input
+
+    // ---- taps -> registers, already flipped: tk[a][b] multiplies window sample with tap index (a, b)
+    float tk[KH][KW];
+#pragma unroll
+    for (int a = 0; a < KH; ++a)
+#pragma unroll
+        for (int b = 0; b < KW; ++b) tk[a][b] = __ldg(taps + (KH - 1 - a) * KW + (KW - 1 - b));
+
+    // ---- stage the zero-padded input tile: rows are distributed over sub-warps of `lpr` lanes
+    {
+        int lpr = 32;
+        while (lpr > 1 && (lpr >> 1) >= g.tin_w) lpr >>= 1;
+        const int rows_per_pass = kThreads / lpr;
+        const int sub = threadIdx.x / lpr, l = threadIdx.x % lpr;
+        const int total_rows = planes_per_tile * g.tin_h;
+        for (int r = sub; r < total_rows; r += rows_per_pass) {
+            const int p = r / g.tin_h, ry = r - p * g.tin_h;
+            const int iy = iy0 + ry;
+            const int64_t plane = plane0 + p;
+            const bool row_ok = (iy >= 0) && (iy < g.in_h) && (plane < g.major);
+            const float *src = x + (plane * g.in_h + iy) * (int64_t)g.in_w;
+            float *dst = s_in + (size_t)r * g.tin_stride;
+            for (int cx = l; cx < g.tin_stride; cx += lpr) {
+                const int ix = ix0 + cx;
+                float v = 0.0f;
+                if (row_ok && ix >= 0 && ix < g.in_w) v = __ldg(src + ix);
+                dst[cx] = v;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- thread -> (plane, patch) and its register window
+    const int sx = threadIdx.x & (txs - 1);
+    const int sy = (threadIdx.x >> g.txs_log2) & (tys - 1);
+    const int p = threadIdx.x >> (g.txs_log2 + g.tys_log2);
+    const int64_t plane = plane0 + p;
+    const float *wbase = s_in + ((size_t)p * g.tin_h + sy * SY) * g.tin_stride + sx * SX;
+
+    float win[NWY][NWXP];
+#pragma unroll
+    for (int a = 0; a < NWY; ++a) {
+        const float *row = wbase + a * g.tin_stride;
+#pragma unroll
+        for (int b = 0; b < NWXP; b += LDW) {
+            if (LDW == 4) {
+                float4 v = *reinterpret_cast<const float4 *>(row + b);
+                win[a][b] = v.x; win[a][b + 1] = v.y; win[a][b + 2] = v.z; win[a][b + 3] = v.w;
+            } else if (LDW == 2) {
+                float2 v = *reinterpret_cast<const float2 *>(row + b);
+                win[a][b] = v.x; win[a][b + 1] = v.y;
+            } else {
+                win[a][b] = row[b];
+            }
+        }
+    }
+
+    const int ox = ox0 + sx * VX, oyb = oy0 + sy * VY;
+    if (plane >= g.major || ox >= g.out_w) return;
+#pragma unroll
+    for (int vy = 0; vy < VY; ++vy) {
+        const int oy = oyb + vy;
+        if (oy >= g.out_h) break;
+        float acc[VX];
+#pragma unroll
+        for (int vx = 0; vx < VX; ++vx) {
+            float s = 0.0f;
+#pragma unroll
+            for (int jy = 0; jy < JY; ++jy)
+#pragma unroll
+                for (int jx = 0; jx < JX; ++jx)
+                    s = fmaf(win[in_off(vy, UP, DOWN, PHY) + jy][in_off(vx, UP, DOWN, PHX) + jx],
+                             tk[tap0(vy, UP, DOWN, PHY) + jy * UP][tap0(vx, UP, DOWN, PHX) + jx * UP], s);
+            acc[vx] = s;
+        }
+        float *dst = out + (plane * g.out_h + oy) * (int64_t)g.out_w + ox;
+        if (g.vec_store && ox + VX <= g.out_w) {
+            *reinterpret_cast<float4 *>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        } else {
+#pragma unroll
+            for (int vx = 0; vx < VX; ++vx)
+                if (ox + vx < g.out_w) dst[vx] = acc[vx];
+        }
+    }
+}
+
+// ---- generic: one thread per output element, any geometry ---------------------------------------
+struct GenericGeom {
+    int64_t major, minor, total;
+    int in_h, in_w, out_h, out_w, kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_y0;
+};
+
+__global__ void __launch_bounds__(kThreads)
+upfirdn2d_generic_kernel(float *__restrict__ out, const float *__restrict__ x, const float *__restrict__ taps,
+                         const GenericGeom g)
+{
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x; idx < g.total; idx += stride) {
+        int64_t r = idx;
+        const int c = (int)(r % g.minor); r /= g.minor;
+        const int ox = (int)(r % g.out_w); r /= g.out_w;
+        const int oy = (int)(r % g.out_h);
+        const int64_t m = r / g.out_h;
+        // poly-phase walk in the same (ky, kx) row-major order as the oracle
+        const int ky0 = pos_mod_i(g.pad_y0 - oy * g.down_y, g.up_y);
+        const int kx0 = pos_mod_i(g.pad_x0 - ox * g.down_x, g.up_x);
+        float acc = 0.0f;
+        for (int ky = ky0; ky < g.kh; ky += g.up_y) {
+            const int iy = (oy * g.down_y + ky - g.pad_y0) / g.up_y;       // exact division
+            if (iy < 0 || iy >= g.in_h) continue;
+            for (int kx = kx0; kx < g.kw; kx += g.up_x) {
+                const int ix = (ox * g.down_x + kx - g.pad_x0) / g.up_x;
+                if (ix < 0 || ix >= g.in_w) continue;
+                acc = fmaf(__ldg(x + ((m * g.in_h + iy) * g.in_w + ix) * g.minor + c),
+                           __ldg(taps + (g.kh - 1 - ky) * g.kw + (g.kw - 1 - kx)), acc);
+            }
+        }
+        out[idx] = acc;
+    }
+}
+
+int ilog2_ceil(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+template <int UP, int DOWN, int KH, int KW, int PHX, int PHY, int VY>
+int launch_tile(float *out, const float *x, const float *taps, int64_t major, int in_h, int in_w,
+                int out_h, int out_w, int pad_x0, int pad_y0, cudaStream_t st)
+{
+    constexpr int JX = KW / UP, JY = KH / UP;
+    constexpr int NWX = in_off(VX - 1, UP, DOWN, PHX) + JX, NWY = in_off(VY - 1, UP, DOWN, PHY) + JY;
+    constexpr int SX = VX * DOWN / UP, SY = VY * DOWN / UP;
+    constexpr int LDW = (SX % 4 == 0) ? 4 : ((SX % 2 == 0) ? 2 : 1);
+    constexpr int NWXP = (NWX + LDW - 1) / LDW * LDW;
+    TileGeom g;
+    g.in_h = in_h; g.in_w = in_w; g.out_h = out_h; g.out_w = out_w; g.major = major;
+    g.pqx = floor_div_i(pad_x0, UP); g.pqy = floor_div_i(pad_y0, UP);
+    int tx = ilog2_ceil((out_w + VX - 1) / VX); if (tx > 4) tx = 4;         // <= 16 strips = 64 outputs wide
+    int ty = ilog2_ceil((out_h + VY - 1) / VY); if (ty > 8 - tx) ty = 8 - tx;
+    g.txs_log2 = tx; g.tys_log2 = ty;
+    const int txs = 1 << tx, tys = 1 << ty, ppt = kThreads >> (tx + ty);
+    g.tin_w = (txs - 1) * SX + NWX;
+    g.tin_h = (tys - 1) * SY + NWY;
+    g.tin_stride = ((txs - 1) * SX + NWXP + 3) / 4 * 4;
+    g.tiles_x = (out_w + txs * VX - 1) / (txs * VX);
+    g.tiles_y = (out_h + tys * VY - 1) / (tys * VY);
+    g.div_tiles_x = FastDiv((uint32_t)g.tiles_x);
+    g.div_tiles_y = FastDiv((uint32_t)g.tiles_y);
+    g.vec_store = (out_w % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+    const int64_t groups = (major + ppt - 1) / ppt;
+    const int64_t blocks = groups * g.tiles_x * g.tiles_y;
+    if (blocks >= 0x7fffffffll) return SR_ERR_UNSUPPORTED;
+    // +4 floats of slack: the widest vector read of the last row may run past the staged columns
+    const size_t smem = sizeof(float) * ((size_t)ppt * g.tin_h * g.tin_stride + 4);
+    auto kern = upfirdn2d_tile_kernel<UP, DOWN, KH, KW, PHX, PHY, VY>;
+    if (smem > 48 * 1024) {
+        if (smem > 200 * 1024) return SR_ERR_UNSUPPORTED;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    kern<<<(unsigned)blocks, kThreads, smem, st>>>(out, x, taps, g);
+    return SR_OK;
+}
+
+}  // namespace
+}  // namespace sr
+
+using namespace sr;
+
+extern "C" int sr_upfirdn2d_f32(float *out, const float *x, const float *taps,
+                                int64_t major, int64_t in_h, int64_t in_w, int64_t minor,
+                                int kernel_h, int kernel_w, int up_x, int up_y, int down_x, int down_y,
+                                int pad_x0, int pad_x1, int pad_y0, int pad_y1, void *stream)
+{
+    SR_REQUIRE(up_x >= 1 && up_y >= 1 && down_x >= 1 && down_y >= 1, "upfirdn2d: up/down must be >= 1");
+    SR_REQUIRE(kernel_h >= 1 && kernel_w >= 1, "upfirdn2d: empty FIR");
+    SR_REQUIRE(major >= 0 && in_h >= 0 && in_w >= 0 && minor >= 0, "upfirdn2d: negative size");
+    SR_REQUIRE(in_h < (1 << 24) && in_w < (1 << 24), "upfirdn2d: plane too large");
+    const int64_t oh = (in_h * up_y + pad_y0 + pad_y1 - kernel_h) / down_y + 1;
+    const int64_t ow = (in_w * up_x + pad_x0 + pad_x1 - kernel_w) / down_x + 1;
+    SR_REQUIRE(in_h * up_y + pad_y0 + pad_y1 >= kernel_h && in_w * up_x + pad_x0 + pad_x1 >= kernel_w,
+               "upfirdn2d: FIR larger than the padded input");
+    if (major == 0 || minor == 0 || oh <= 0 || ow <= 0) return SR_OK;
+    SR_REQUIRE(out && x && taps, "upfirdn2d: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+
+    int rc = SR_ERR_UNSUPPORTED;
+    if (minor == 1 && up_x == up_y && down_x == down_y && kernel_h == 4 && kernel_w == 4) {
+#define SR_TILE(UP, DOWN, PHX, PHY, VY) \
+    rc = launch_tile<UP, DOWN, 4, 4, PHX, PHY, VY>(out, x, taps, major, (int)in_h, (int)in_w, (int)oh, (int)ow, \
+                                                   pad_x0, pad_y0, st)
+        if (up_x == 1 && down_x == 1) SR_TILE(1, 1, 0, 0, 2);
+        else if (up_x == 1 && down_x == 2) SR_TILE(1, 2, 0, 0, 2);
+        else if (up_x == 2 && down_x == 1) {
+            const int phx = pos_mod_i(pad_x0, 2), phy = pos_mod_i(pad_y0, 2);
+            if (phx == 0 && phy == 0) SR_TILE(2, 1, 0, 0, 2);
+            else if (phx == 1 && phy == 1) SR_TILE(2, 1, 1, 1, 2);
+            else if (phx == 0 && phy == 1) SR_TILE(2, 1, 0, 1, 2);
+            else SR_TILE(2, 1, 1, 0, 2);
+        }
+#undef SR_TILE
+    }
+    if (rc == SR_ERR_UNSUPPORTED) {
+        GenericGeom g;
+        g.major = major; g.minor = minor; g.total = major * oh * ow * minor;
+        g.in_h = (int)in_h; g.in_w = (int)in_w; g.out_h = (int)oh; g.out_w = (int)ow;
+        g.kh = kernel_h; g.kw = kernel_w; g.up_x = up_x; g.up_y = up_y; g.down_x = down_x; g.down_y = down_y;
+        g.pad_x0 = pad_x0; g.pad_y0 = pad_y0;
+        int64_t blocks = (g.total + kThreads - 1) / kThreads;
+        const int64_t cap = (int64_t)kNumSMs * 32;
+        if (blocks > cap) blocks = cap;
+        upfirdn2d_generic_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
+        rc = SR_OK;
+    }
+    if (rc != SR_OK) return rc;
+    count_launch();
+    return check_launch("sr_upfirdn2d_f32");
+}
