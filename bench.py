@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the StyleRenderer hot path on B200 (contract: see DESIGN.md section "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload generator|rasterize]
+
+One "step" = one forward+backward pass of the hot path over one batch of synthetic input:
+  generator (default; BASELINE.json configs[1]): Generator(256, 512, 8), batch 32 per GPU, random z, fp32 storage,
+      loss = <image, fixed random cotangent>, gradients w.r.t. every parameter and z;
+  rasterize (BASELINE.json configs[2]): BFM-size mesh (35 721 verts / 70 688 tris) -> 256x256, batch 64, fwd+bwd.
+Prints ONE JSON line on rank 0.  `value` is device-resident throughput, `e2e` goes through the public module API from
+pinned HOST buffers (H2D + D2H inside the timed region), `roofline` describes the dominant stylerenderer_b200 kernel of
+the step (timed live with CUDA events on the launching stream), `cpu_baseline` is the oracle's native-PyTorch CPU
+restatement of the reference timed on this host on a bounded sample.
+`--impl reference` times that CPU restatement alone (the reference itself cannot travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "generator fwd+bwd images/sec @256px"
+UNIT = "images/s"
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        p["_source"] = "measured"
+        return p
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md "clocks" line)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.samples, self._stop = index, [], threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [s.strip() for s in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        mhz = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": statistics.median(mhz) if mhz else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+class KernelTimer:
+    """Times every call of selected C-ABI entry points with CUDA events on the launching (current) stream."""
+
+    def __init__(self, lib_mod, names):
+        self.lib_mod, self.names, self.records, self._orig = lib_mod, names, [], {}
+
+    def __enter__(self):
+        handle = self.lib_mod.lib()
+        for n in self.names:
+            fn = getattr(handle, n)
+            self._orig[n] = fn
+
+            def wrapped(*a, _fn=fn, _n=n):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                rc = _fn(*a)
+                e.record()
+                self.records.append((_n, a, s, e))
+                return rc
+            setattr(handle, n, wrapped)
+        return self
+
+    def __exit__(self, *a):
+        handle = self.lib_mod.lib()
+        for n, fn in self._orig.items():
+            setattr(handle, n, fn)
+
+    def stats(self):
+        """-> {name: [(args, ms), ...]} (call after torch.cuda.synchronize())."""
+        out = {}
+        for n, a, s, e in self.records:
+            out.setdefault(n, []).append((a, s.elapsed_time(e)))
+        return out
+
+
+def algorithmic_bytes(name, a):
+    """bytes one launch must move."""
+    if name == "sr_fused_bias_act_f32":
+        return 8 * a[8] + 4 * a[10]
+    if name == "sr_fused_lrelu_backward_f32":
+        return 12 * a[6] + 4 * a[8]
+    if name == "sr_upfirdn2d_f32":
+        major, ih, iw, minor, kh, kw, ux, uy, dx, dy, px0, px1, py0, py1 = a[3:17]
+        oh = (ih * uy + py0 + py1 - kh) // dy + 1
+        ow = (iw * ux + px0 + px1 - kw) // dx + 1
+        return 4 * major * minor * (ih * iw + oh * ow) + 4 * kh * kw
+    return 0
+
+
+def dominant_kernel_roofline(stats, peaks, total_ms, steps):
+    if not stats:
+        return None
+    tot = {n: sum(ms for _, ms in calls) for n, calls in stats.items()}
+    name = max(tot, key=tot.get)
+    calls = stats[name]
+    by = sum(algorithmic_bytes(name, a) for a, _ in calls)
+    ms = tot[name]
+    ach = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    peak = peaks["hbm_gbs"]
+    return {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(ach / peak, 4), "traffic": None, "peak_source": peaks["_source"],
+            "launches_per_step": len(calls) / steps, "avg_launch_ms": round(ms / len(calls), 5),
+            "share_of_step": round(ms / total_ms, 4) if total_ms else None,
+            "algorithmic_bytes_per_step": by // steps,
+            "all_kernels_ms_per_step": {n: round(v / steps, 4) for n, v in tot.items()}}
+
+
+# ----------------------------------------------------------------------------------------------- workloads
+def build_generator(device, dtype=torch.float32):
+    from stylerenderer_b200 import model as M
+    torch.manual_seed(0)
+    g = M.Generator(256, 512, 8, channel_multiplier=2)
+    with torch.no_grad():                               # zeros would hide the noise / bias paths
+        for n, p in g.named_parameters():
+            if n.endswith("noise.weight") or n.endswith("activate.bias"):
+                p.normal_(0, 0.1)
+    return g.to(device)
+
+
+def generator_step(G, z, cot):
+    for p in G.parameters():
+        p.grad = None
+    z = z.detach().requires_grad_(True)
+    img, _ = G([z])
+    loss = (img * cot).sum()
+    loss.backward()
+    return loss.detach(), z.grad
+
+
+def cpu_reference_generator_rate(batch, iters, threads=None):
+    """Native-PyTorch CPU restatement of the reference (oracle/torch_ref.py) -- the checker, timed as a baseline."""
+    from oracle import torch_ref as T
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    G = T.Generator(256, 512, 8, channel_multiplier=2)
+    z = torch.randn(batch, 512)
+    cot = torch.randn(batch, 3, 256, 256)
+    times = []
+    for it in range(iters + 1):
+        t0 = time.perf_counter()
+        for p in G.parameters():
+            p.grad = None
+        zz = z.clone().requires_grad_(True)
+        img, _ = G([zz])
+        (img * cot).sum().backward()
+        if it:                                          # first pass = warm-up
+            times.append(time.perf_counter() - t0)
+    return batch * len(times) / sum(times), torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 2
+    per_step = []
+    from oracle import torch_ref as T
+    torch.manual_seed(0)
+    G = T.Generator(256, 512, 8, channel_multiplier=2)
+    z = torch.randn(batch, 512)
+    cot = torch.randn(batch, 3, 256, 256)
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        for p in G.parameters():
+            p.grad = None
+        zz = z.clone().requires_grad_(True)
+        img, _ = G([zz])
+        (img * cot).sum().backward()
+        if it >= args.warmup:
+            per_step.append(time.perf_counter() - t0)
+    value = batch * len(per_step) / sum(per_step)
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * sum(per_step) / len(per_step), 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "StyleGAN2 generator 256x256 fwd+bwd (BASELINE.json configs[1])",
+                       "note": "bounded sample: batch 2 per step on host cores (reference CPU path restated in "
+                               "oracle/torch_ref.py; the reference tree cannot travel to the GPU box)"},
+            "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"Generator(256) fwd+bwd, batch {batch}, {args.steps} steps"},
+            "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step (BASELINE config: 32)")
+    ap.add_argument("--conv-backend", default=None, choices=[None, "cudnn", "tcgen05"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (--impl b200) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
+
+    from stylerenderer_b200 import _lib, layers
+    if args.conv_backend:
+        layers.set_conv_backend(args.conv_backend)
+    elif getattr(layers, "HAVE_TCGEN05", False):
+        layers.set_conv_backend("tcgen05")
+    peaks = measured_peaks()
+
+    # ---- CPU baseline (rank 0, bounded sample, before the GPU timing)
+    cpu_base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        rate, cores = cpu_reference_generator_rate(batch=2, iters=2)
+        cpu_base = {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": "oracle/torch_ref.Generator(256) fwd+bwd, batch 2, 2 timed iterations after 1 warm-up "
+                              f"({time.perf_counter() - t0:.0f} s of CPU work)"}
+
+    torch.manual_seed(1234 + rank)                      # per-rank RNG offset (reference distributed.py:93-95)
+    G = build_generator(dev)
+    B = args.batch
+    z_dev = torch.randn(B, 512, device=dev)
+    cot = torch.randn(B, 3, 256, 256, device=dev)
+    z_host = torch.randn(B, 512).pin_memory()
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    gz_host = torch.empty(B, 512).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def step_resident():
+        generator_step(G, z_dev, cot)
+
+    def step_e2e():
+        z = z_host.to(dev, non_blocking=True)
+        loss, gz = generator_step(G, z, cot)
+        loss_host.copy_(loss, non_blocking=True)
+        gz_host.copy_(gz, non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # the caller reads the result every step
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    n0 = _lib.launch_count()
+    with ClockSampler(local) as clocks:
+        ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - n0
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # ---- live per-kernel timing of the stylerenderer_b200 launches inside a timed region (rank 0)
+    roof = None
+    if rank == 0:
+        names = ["sr_fused_bias_act_f32", "sr_fused_lrelu_backward_f32", "sr_upfirdn2d_f32"]
+        names += [n for n in getattr(_lib, "CONV_EXPORTS", ())]
+        with KernelTimer(_lib, names) as kt:
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(min(args.steps, 5)):
+                step_resident()
+            e.record()
+            torch.cuda.synchronize()
+            region_ms = s.elapsed_time(e)
+        roof = dominant_kernel_roofline(kt.stats(), peaks, region_ms, min(args.steps, 5))
+
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if layers.get_conv_backend() == "cudnn" else "tf32",
+                "data": "synthetic",
+                "config": {"workload": "StyleGAN2 generator 256x256, batch 32/GPU, random z, fwd+bwd (BASELINE.json configs[1])",
+                           "global_batch": world * B, "parallelism": f"dp{world} (image-sharded, no collective)",
+                           "conv_backend": layers.get_conv_backend(),
+                           "l2": "activations per step (several GB) exceed the 126 MB L2; no explicit flush",
+                           "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32)},
+                "clocks": clocks.summary(),
+                "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": z_host.numel() * 4,
+                        "d2h_bytes_per_step": 4 + gz_host.numel() * 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
+                "gpu_launches": int(launches),
+                "roofline": roof, "cpu_baseline": cpu_base}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,1 +1,259 @@
-"""placeholder -- replaced below in this round"""
+"""StyleGAN2 building blocks behind the reference's class names, constructor signatures and state_dict keys
+(reference layers.py).  Host code stays PyTorch; every operator the reference implements in op/ is a
+hand-written sm_100a kernel reached through stylerenderer_b200.op.
+
+ModulatedConv2d is re-formulated B200-first ("Hard parts"): instead of materialising one
+modulated+demodulated weight tensor per sample and running a grouped conv with B groups (reference
+layers.py:296-322; 302 MB of weights per 512x512 layer at B=32), the per-sample style scales the
+*activations* and the demodulation scales the *outputs*:
+
+    y[b,o] = d[b,o] * conv( x[b,i] * s[b,i],  scale * W[o,i] ),   d = rsqrt( (s^2) @ (scale^2 * sum_k W^2)^T + eps )
+
+so all samples share one weight matrix and the contraction becomes ONE dense implicit GEMM
+(M = B*H*W, N = Cout, K = k*k*Cin).  `conv_backend` selects who runs that GEMM:
+    "tcgen05" -- the hand-written sm_100a kernel (csrc/modconv.cu), where available for the shape;
+    "cudnn"   -- stock F.conv2d / F.conv_transpose2d (library baseline; never counted in gpu_launches).
+"""
+import math
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
+
+_CONFIG = {"conv_backend": "cudnn"}
+
+
+def set_conv_backend(name):
+    assert name in ("cudnn", "tcgen05")
+    _CONFIG["conv_backend"] = name
+
+
+def get_conv_backend():
+    return _CONFIG["conv_backend"]
+
+
+def make_kernel(k):                                   # reference layers.py:7-12
+    k = torch.tensor(k, dtype=torch.float32)
+    if k.dim() == 1:
+        k = k[None, :] * k[:, None]
+    k /= k.sum()
+    return k
+
+
+class PixelNorm(nn.Module):                           # reference layers.py:100-105
+    def __init__(self, eps=1e-8):
+        super().__init__()
+        self.eps = abs(eps)
+
+    def forward(self, input):
+        return input * torch.rsqrt(torch.mean(input * input, -1, keepdim=True) + self.eps)
+
+
+class Upsample(nn.Module):                            # reference layers.py:170-181
+    def __init__(self, kernel, factor=2):
+        super().__init__()
+        self.factor = factor
+        kernel = make_kernel(kernel) * (factor ** 2)
+        self.register_buffer("kernel", kernel)
+        p = kernel.shape[0] - factor
+        self.pad = ((p + 1) // 2 + factor - 1, p // 2)
+
+    def forward(self, input):
+        return upfirdn2d(input, self.kernel, up=self.factor, down=1, pad=self.pad)
+
+
+class Downsample(nn.Module):                          # reference layers.py:182-193
+    def __init__(self, kernel, factor=2):
+        super().__init__()
+        self.factor = factor
+        kernel = make_kernel(kernel)
+        self.register_buffer("kernel", kernel)
+        p = kernel.shape[0] - factor
+        self.pad = ((p + 1) // 2, p // 2)
+
+    def forward(self, input):
+        return upfirdn2d(input, self.kernel, up=1, down=self.factor, pad=self.pad)
+
+
+class Blur(nn.Module):                                # reference layers.py:194-203
+    def __init__(self, kernel, pad, upsample_factor=1):
+        super().__init__()
+        kernel = make_kernel(kernel)
+        if upsample_factor > 1:
+            kernel = kernel * (upsample_factor ** 2)
+        self.register_buffer("kernel", kernel)
+        self.pad = pad
+
+    def forward(self, input):
+        return upfirdn2d(input, self.kernel, pad=self.pad)
+
+
+class EqualConv2d(nn.Module):                         # reference layers.py:204-221
+    def __init__(self, in_channel, out_channel, kernel_size, stride=1, padding=0, bias=True):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(out_channel, in_channel, kernel_size, kernel_size))
+        self.scale = 1 / math.sqrt(in_channel * kernel_size ** 2)
+        self.stride = stride
+        self.padding = padding
+        self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
+
+    def forward(self, input):
+        return F.conv2d(input, self.weight * self.scale, bias=self.bias, stride=self.stride, padding=self.padding)
+
+    def __repr__(self):
+        return "%s(%d, %d, %d, stride=%d, padding=%d)" % (self.__class__.__name__, self.weight.shape[1],
+                                                          self.weight.shape[0], self.weight.shape[2], self.stride,
+                                                          self.padding)
+
+
+class EqualLinear(nn.Module):                         # reference layers.py:222-251
+    def __init__(self, in_dim, out_dim, bias=True, bias_init=0, lr_mul=1, activation=None):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(out_dim, in_dim).div_(lr_mul))
+        self.bias = nn.Parameter(torch.zeros(out_dim).fill_(bias_init)) if bias else None
+        self.activation = activation
+        self.scale = (1 / math.sqrt(in_dim)) * lr_mul
+        self.lr_mul = lr_mul
+
+    def forward(self, input):
+        if self.activation == "fused_lrelu":
+            out = F.linear(input, self.weight * self.scale)
+            return fused_leaky_relu(out, self.bias * self.lr_mul)
+        out = F.linear(input, self.weight * self.scale, bias=self.bias * self.lr_mul)
+        if self.activation == "relu":
+            out = F.relu(out)
+        elif self.activation == "lrelu":
+            out = F.leaky_relu(out, negative_slope=0.2)
+        elif self.activation == "selu":
+            out = F.selu(out)
+        elif self.activation == "tanh":
+            out = torch.tanh(out)
+        return out
+
+    def __repr__(self):
+        return "%s(%d, %d)" % (self.__class__.__name__, self.weight.shape[1], self.weight.shape[0])
+
+
+class ScaledLeakyReLU(nn.Module):                     # reference layers.py:252-258
+    def __init__(self, negative_slope=0.2):
+        super().__init__()
+        self.negative_slope = negative_slope
+
+    def forward(self, input):
+        return F.leaky_relu(input, negative_slope=self.negative_slope) * math.sqrt(2)
+
+
+class ModulatedConv2d(nn.Module):                     # reference layers.py:259-323
+    def __init__(self, in_channel, out_channel, kernel_size, style_dim, demodulate=True, upsample=False,
+                 downsample=False, blur_kernel=[1, 3, 3, 1]):
+        super().__init__()
+        self.eps = 1e-8
+        self.kernel_size = kernel_size
+        self.in_channel = in_channel
+        self.out_channel = out_channel
+        self.upsample = upsample
+        self.downsample = downsample
+        if upsample:
+            factor = 2
+            p = (len(blur_kernel) - factor) - (kernel_size - 1)
+            self.blur = Blur(blur_kernel, pad=((p + 1) // 2 + factor - 1, p // 2 + 1), upsample_factor=factor)
+        if downsample:
+            factor = 2
+            p = (len(blur_kernel) - factor) + (kernel_size - 1)
+            self.blur = Blur(blur_kernel, pad=((p + 1) // 2, p // 2))
+        fan_in = in_channel * kernel_size ** 2
+        self.scale = 1 / math.sqrt(fan_in)
+        self.padding = kernel_size // 2
+        self.weight = nn.Parameter(torch.randn(1, out_channel, in_channel, kernel_size, kernel_size))
+        self.modulation = EqualLinear(style_dim, in_channel, bias_init=1)
+        self.demodulate = demodulate
+
+    def __repr__(self):
+        return "%s(%d, %d, %d, upsample=%s, downsample=%s)" % (self.__class__.__name__, self.in_channel,
+                                                               self.out_channel, self.kernel_size, self.upsample,
+                                                               self.downsample)
+
+    def style_scales(self, style):
+        """(s [B,Cin], d [B,Cout] or None): per-sample input modulation and output demodulation."""
+        s = self.modulation(style)
+        d = None
+        if self.demodulate:
+            wsq = (self.weight[0] * self.scale).pow(2).sum([2, 3])               # [Cout, Cin]
+            d = torch.rsqrt(F.linear(s * s, wsq) + self.eps)                       # reference layers.py:297
+        return s, d
+
+    def contract(self, x_mod):
+        """The shared-weight contraction of the already modulated input (no demodulation)."""
+        w = self.weight[0] * self.scale
+        if self.upsample:                                                          # reference layers.py:301-310
+            out = F.conv_transpose2d(x_mod, w.transpose(0, 1), padding=0, stride=2)
+            return self.blur(out)
+        if self.downsample:                                                        # reference layers.py:311-317
+            return F.conv2d(self.blur(x_mod), w, padding=0, stride=2)
+        return F.conv2d(x_mod, w, padding=self.padding)                            # reference layers.py:318-322
+
+    def forward(self, input, style):
+        batch, in_channel = input.shape[:2]
+        s, d = self.style_scales(style)
+        out = self.contract(input * s.view(batch, in_channel, 1, 1))
+        if d is not None:
+            out = out * d.view(batch, self.out_channel, 1, 1)
+        return out
+
+
+class NoiseInjection(nn.Module):                      # reference layers.py:324-332
+    def __init__(self):
+        super().__init__()
+        self.weight = nn.Parameter(torch.zeros(1))
+
+    def forward(self, image, noise=None):
+        if noise is None:
+            batch, _, height, width = image.shape
+            noise = image.new_empty(batch, 1, height, width).normal_()
+        return image + self.weight * noise
+
+
+class ConstantInput(nn.Module):                       # reference layers.py:333-340
+    def __init__(self, channel, size=4):
+        super().__init__()
+        self.input = nn.Parameter(torch.randn(1, channel, size, size))
+
+    def forward(self, input):
+        return self.input.repeat(input.shape[0], 1, 1, 1)
+
+
+class ConvLayer(nn.Sequential):                       # reference layers.py:341-378
+    def __init__(self, in_channel, out_channel, kernel_size, downsample=False, blur_kernel=[1, 3, 3, 1], bias=True,
+                 activate="lrelu"):
+        layers = []
+        if downsample:
+            factor = 2
+            p = (len(blur_kernel) - factor) + (kernel_size - 1)
+            layers.append(Blur(blur_kernel, pad=((p + 1) // 2, p // 2)))
+            stride = 2
+            self.padding = 0
+        else:
+            stride = 1
+            self.padding = kernel_size // 2
+        if activate is False or activate is None:        # reference ResBlock passes activate=False (quirk #2):
+            activate = "none"                            # upstream semantics = no activation
+        if "sp" in activate.lower():
+            raise NotImplementedError("SpectralNorm conv layers are outside the hot path (SURVEY.md section 2 row 4)")
+        layers.append(EqualConv2d(in_channel, out_channel, kernel_size, padding=self.padding, stride=stride, bias=bias))
+        if activate == "lrelu":
+            layers.append(FusedLeakyReLU(out_channel) if bias else ScaledLeakyReLU(0.2))
+        super().__init__(*layers)
+
+
+class ResBlock(nn.Module):                            # reference layers.py:379-391
+    def __init__(self, in_channel, out_channel, blur_kernel=[1, 3, 3, 1], downsample=True):
+        super().__init__()
+        self.conv1 = ConvLayer(in_channel, in_channel, 3)
+        self.conv2 = ConvLayer(in_channel, out_channel, 3, downsample=downsample)
+        self.skip = ConvLayer(in_channel, out_channel, 1, downsample=downsample, activate=False, bias=False)
+
+    def forward(self, input):
+        out = self.conv2(self.conv1(input))
+        return (out + self.skip(input)) / math.sqrt(2)

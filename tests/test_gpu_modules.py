@@ -1,0 +1,114 @@
+"""GPU parity of the module layer (stylerenderer_b200.layers / .model) against fixtures produced by the unmodified
+reference on CPU (tests/golden/make_golden.py) -- bar: 1e-3 relative in fp32 (BASELINE.json north_star)."""
+import pytest
+import torch
+
+from make_golden import det_fill, grid_mesh
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-3
+
+
+def close(got, want, what=""):
+    scale = float(want.abs().max())
+    torch.testing.assert_close(got.cpu(), want, rtol=REL, atol=REL * max(scale, 1e-6) * 0.1, msg=lambda m: what + ": " + m)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def fp32_math():
+    """Parity runs pin true-fp32 library math; the tcgen05 path states its own precision."""
+    assert torch.cuda.is_available()
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def grads(mod, args, wrt, gy):
+    y = mod(*args)
+    names = [n for n, _ in sorted(mod.named_parameters())]
+    params = [p for _, p in sorted(mod.named_parameters())]
+    gr = torch.autograd.grad(y, wrt + params, gy.to(y.device), allow_unused=True)
+    return y.detach(), gr[:len(wrt)], dict(zip(names, gr[len(wrt):]))
+
+
+def check_param_grads(got, want):
+    assert set(got) == set(want)
+    for k, w in want.items():
+        if w is None:
+            assert got[k] is None or float(got[k].abs().max()) == 0, k
+        else:
+            close(got[k], w, k)
+
+
+@pytest.mark.parametrize("backend", ["cudnn", "tcgen05"])
+@pytest.mark.parametrize("name", ["modconv_plain", "modconv_up", "modconv_1x1_nodemod"])
+def test_modulated_conv(golden, name, backend):
+    from stylerenderer_b200 import layers as L
+    if backend == "tcgen05" and not getattr(L, "HAVE_TCGEN05", False):
+        pytest.skip("tcgen05 modulated conv not built yet")
+    L.set_conv_backend(backend)
+    try:
+        g = golden["modules"][name]
+        m = det_fill(L.ModulatedConv2d(**g["kw"]), 500).cuda()
+        x = g["x"].cuda().requires_grad_(True)
+        s = g["style"].cuda().requires_grad_(True)
+        y, (gx, gs), gp = grads(m, (x, s), [x, s], g["gy"])
+        close(y, g["y"], "y"); close(gx, g["gx"], "gx"); close(gs, g["gs"], "gs")
+        check_param_grads(gp, g["gp"])
+    finally:
+        L.set_conv_backend("cudnn")
+
+
+def test_styled_blocks(golden):
+    from stylerenderer_b200 import model as M
+    mods = golden["modules"]
+    for name, up in [("styledconv_plain", False), ("styledconv_up", True)]:
+        g = mods[name]
+        m = det_fill(M.StyledConv(8, 12, 3, 32, upsample=up), 501).cuda()
+        x = g["x"].cuda().requires_grad_(True); s = g["style"].cuda().requires_grad_(True)
+        y, (gx, gs), gp = grads(m, (x, s, g["noise"].cuda()), [x, s], g["gy"])
+        close(y, g["y"], name); close(gx, g["gx"], name); close(gs, g["gs"], name)
+        check_param_grads(gp, g["gp"])
+    g = mods["styledmapconv"]
+    m = det_fill(M.StyledMapConv(8, 12, 3, 32), 502).cuda()
+    x = g["x"].cuda().requires_grad_(True); s = g["style"].cuda().requires_grad_(True)
+    sm = g["stylemap"].cuda().requires_grad_(True)
+    y, (gx, gs, gm), gp = grads(m, (x, s, sm, g["noise"].cuda()), [x, s, sm], g["gy"])
+    close(y, g["y"]); close(gx, g["gx"]); close(gm, g["gm"])
+    check_param_grads(gp, g["gp"])
+    g = mods["torgb"]
+    m = det_fill(M.ToRGB(8, 32), 503).cuda()
+    x = g["x"].cuda().requires_grad_(True); s = g["style"].cuda().requires_grad_(True)
+    sk = g["skip"].cuda().requires_grad_(True)
+    y, (gx, gs, gk), gp = grads(m, (x, s, sk), [x, s, sk], g["gy"])
+    close(y, g["y"]); close(gx, g["gx"]); close(gk, g["gk"])
+    check_param_grads(gp, g["gp"])
+
+
+def test_networks(golden):
+    from stylerenderer_b200 import model as M
+    nets = golden["networks"]
+    g = nets["generator32"]
+    G = det_fill(M.Generator(32, 64, 2), 600).cuda().eval()
+    assert len(G.state_dict()) == g["n_keys"]
+    z = g["z"].cuda().requires_grad_(True)
+    img, _ = G([z], randomize_noise=False)
+    close(img, g["img"], "generator image")
+    gz, gw = torch.autograd.grad(img, (z, G.convs[3].conv.weight), g["gimg"].cuda())
+    close(gz, g["gz"], "dz")
+    close(gw[0, :4, :4], g["gw_convs3_slice"], "dW slice")
+    assert abs(float(gw.norm()) - float(g["gw_convs3_norm"])) <= REL * float(g["gw_convs3_norm"])
+    g = nets["generatorwithmap16"]
+    v, tri = grid_mesh(24, 2, 611)
+    GM = det_fill(M.GeneratorWithMap(16, 64, 2), 610).cuda().eval()
+    assert len(GM.state_dict()) == g["n_keys"]
+    img, _, normals = GM([g["z"].cuda()], (v.cuda(), g["tex"].cuda(), tri.cuda()), return_normals=True,
+                         randomize_noise=False)
+    close(normals[-1], g["normal16"], "rasterized normals")
+    close(img, g["img"], "GAR image")
+    g = nets["discriminator16"]
+    D = det_fill(M.Discriminator(16), 620).cuda().eval()
+    close(D(g["x"].cuda()), g["y"], "discriminator logits")

@@ -73,7 +73,7 @@ def test_fused_leaky_relu_backward(op, shape, channels_last):
     out = op.fused_leaky_relu(xin, bc)
     gx, gb = torch.autograd.grad(out, (xc, bc), cuda(gy))
     assert torch.equal(gx.cpu(), gx_want)                           # dx is elementwise: bit exact
-    torch.testing.assert_close(gb.cpu().double(), gb_want, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(gb.cpu().double(), gb_want, rtol=1e-4, atol=1e-4)   # fp32 sum of up to 4096 terms
 
 
 def test_fused_leaky_relu_double_backward(op):
