@@ -114,6 +114,52 @@ int sr_rasterize_backward_f64(int64_t b, int64_t n, int64_t h, int64_t w, int64_
                               const double *verts, const double *tex, const int64_t *ids, const double *bary,
                               const double *gout, double *grad_verts, double *grad_tex, double eps, void *stream);
 
+/* ------------------------------------------------------------------ modulated convolution ------
+ * Replaces the dense contraction inside ModulatedConv2d.forward (reference layers.py:293-323: cuDNN grouped
+ * conv2d / conv_transpose2d over B per-sample weight copies) with ONE shared-weight implicit GEMM on the
+ * tcgen05 tensor cores (tf32 x tf32 -> fp32):
+ *   D[n, gy, gx, co] = sum_{t < num_taps} sum_{ci} in[n, gy*in_stride + tap_dy[t], gx*in_stride + tap_dx[t], ci]
+ *                                                   * weight[co, tap_w[t], ci]            (zero outside the input)
+ * for every point (gy, gx) of a grid_h x grid_w lattice; D is written to
+ *   out[n, out_y0 + gy*out_stride, out_x0 + gx*out_stride, co]      (NHWC, [batch, out_h, out_w, cout]).
+ * Layouts: in [batch, in_h, in_w, cin] NHWC fp32; weight [cout][taps_total][cin] fp32 (see
+ * sr_conv_weight_prep_tf32).  cin % 32 == 0, cout % 128 == 0, all tensors 16-byte aligned.
+ * Epilogues:
+ *   0: out = D * rowscale[n, co]                                  (rowscale may be NULL)
+ *   1: t = D * rowscale[n,co] (* stylemap[n,0,y,x] + stylemap[n,1,y,x]) + noise_weight[0]*noise[n,y,x] + bias[co]
+ *      out = (t > 0 ? t : alpha*t) * gain          -- the StyledConv / StyledMapConv tail (reference model.py:26-32,48-55)
+ *   in both cases, if out2 != NULL: out2 = tf32_round(out * scale2[n, co]) (next layer's modulated input).
+ * noise is planar [*, out_h, out_w] with batch stride noise_batch_stride (0 broadcasts one plane);
+ * stylemap is planar with two planes of out_h*out_w per image and batch stride stylemap_batch_stride. */
+typedef struct sr_conv_args {
+    const float *in;
+    int64_t batch, in_h, in_w, cin;
+    const float *weight;
+    int64_t cout, taps_total;
+    int32_t num_taps;
+    int32_t tap_dy[9], tap_dx[9], tap_w[9];
+    int32_t in_stride;
+    int64_t grid_h, grid_w, out_h, out_w;
+    int32_t out_stride, out_y0, out_x0;
+    float *out;
+    float *out2;
+    int32_t epilogue;
+    const float *rowscale, *scale2, *bias, *noise, *noise_weight, *stylemap;
+    int64_t noise_batch_stride, stylemap_batch_stride;
+    float alpha, gain;
+} sr_conv_args;
+int sr_conv_igemm_tf32(const sr_conv_args *args, void *stream);
+
+/* xs[n,p,c] = tf32_round(x[n,p,c] * style[n,c]) for an NHWC tensor (style == NULL: rounding only). */
+int sr_modulate_tf32(float *xs, const float *x, const float *style, int64_t batch, int64_t pixels, int64_t channels,
+                     void *stream);
+
+/* Re-layout + scale + tf32-round a reference-layout weight [cout, cin, kh, kw] into a GEMM B operand
+ * [rows][kh*kw][cols]:  transpose 0/3: rows = cout, cols = cin, tap = ky*kw+kx;  1: rows = cin, cols = cout,
+ * taps flipped (dgrad of the plain conv);  2: rows = cin, cols = cout, taps as is (transposed-conv forward). */
+int sr_conv_weight_prep_tf32(float *dst, const float *w, float scale, int64_t cout, int64_t cin, int kh, int kw,
+                             int transpose, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

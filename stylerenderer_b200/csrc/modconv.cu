@@ -1,0 +1,478 @@
+// Modulated convolution on 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+// Replaces the dense contraction of ModulatedConv2d (reference layers.py:293-323): cuDNN grouped
+// conv / grouped transposed conv over per-sample weight copies.  Here all samples share ONE weight
+// matrix (the style scales the activations, the demodulation scales the outputs, see layers.py of this
+// package), so every variant is an implicit GEMM   D[pixel, cout] = sum_{tap, cin} A[pixel+tap, cin] * W[cout, tap, cin]
+//   M = batch * grid_h * grid_w pixels, N = cout, K = taps * cin
+// and one kernel covers all of them through a tap list + an input stride + an output lattice:
+//   plain 3x3 conv / its dgrad      9 taps, stride 1, dense output
+//   transposed stride-2 conv        4 phase launches (4/2/2/1 taps), output lattice stride 2
+//   dgrad of the transposed conv    9 taps, input stride 2 (TMA element strides)
+//
+// Data path per CTA (one 128-pixel x BLOCK_N tile of D, fp32 accumulator in TMEM):
+//   warp 0   TMA producer: per (tap, 32-channel K block) one 4-D box {32 ch, TW, TH, TN} of the NHWC
+//            activations -- the tap shift and the zero padding are done by the TMA unit (signed box
+//            coordinates, out-of-bound fill) -- plus one 2-D box {32, BLOCK_N} of the weights, both
+//            128-byte swizzled, into a STAGES-deep ring guarded by full/empty mbarriers;
+//   warp 1   MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M128 x N x K8, 4 per
+//            K block) on shared-memory descriptors, tcgen05.commit releases ring slots / publishes TMEM;
+//   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns, fused StyledConv epilogue
+//            (demodulate, style-map affine, noise, bias, leaky-ReLU * sqrt2, optional second output
+//            pre-multiplied by the NEXT layer's style and rounded to tf32), 128-byte row stores.
+// fp32 storage, TF32 multiplicands (both operands are rounded to tf32 with cvt.rna by the kernels that
+// produce them), fp32 accumulation: the same arithmetic class as the reference's cuDNN path under
+// torch's default cudnn.allow_tf32 = True.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace sr {
+namespace {
+
+constexpr int kConvThreads = 192;
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;                         // fp32 elements = one 128-byte swizzle row
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor:
+// start >> 4 at [0,14), LBO >> 4 at [16,30) (unused for swizzled K-major, 1), SBO >> 4 at [32,46),
+// version 1 at [46,48), layout SWIZZLE_128B = 2 at [61,64)).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ float round_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------ kernel
+struct ConvKParams {
+    int tw_log2, th_log2, tn_log2;          // tile = 2^tn images x 2^th rows x 2^tw columns = 128 pixels
+    int tiles_x, tiles_y;
+    int batch, grid_h, grid_w;
+    int kblocks_per_tap;                    // cin / 32
+    int num_taps;
+    int tap_dy[9], tap_dx[9], tap_k0[9];    // input offset of a tap and its first K column in the weight matrix
+    int in_stride;
+    int cout;
+    long long out_img_stride, out_row_stride, out_pix_stride;   // in floats
+    long long out_offset;                   // lattice origin (y0 * row + x0 * pix), in floats
+    float *out, *out2;
+    int epilogue;                           // 0: acc * rowscale   1: styled
+    const float *rowscale, *scale2, *bias, *noise, *noise_weight, *stylemap;
+    long long noise_img_stride, noise_row_stride, noise_pix_stride, noise_offset;
+    long long map_img_stride;               // stylemap [batch, 2, out_h, out_w] planar: plane stride = out_h*out_w
+    long long map_plane_stride;
+    float alpha, gain;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                       const ConvKParams p)
+{
+    constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
+    constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                                ((uint32_t)(BLOCK_M >> 4) << 24);            // f32 accum, tf32 x tf32, K-major A and B
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + STAGES * A_BYTES;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * (A_BYTES + B_BYTES));
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tmem_full_bar = empty_bar + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x, n_tile = blockIdx.y;
+    const int tile_x = tile % p.tiles_x, tile_y = (tile / p.tiles_x) % p.tiles_y, tile_n = tile / (p.tiles_x * p.tiles_y);
+    const int gx0 = tile_x << p.tw_log2, gy0 = tile_y << p.th_log2, n0 = tile_n << p.tn_log2;
+    const int num_kb = p.num_taps * p.kblocks_per_tap;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_b) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {                                   // TMEM: BLOCK_N fp32 columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)BLOCK_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                               // ===== TMA producer
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                const int t = kb / p.kblocks_per_tap, kc = kb - t * p.kblocks_per_tap;
+                mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+                tma_load_4d(sA + s * A_BYTES, &tmap_a, &full_bar[s], kc * BLOCK_K,
+                            gx0 * p.in_stride + p.tap_dx[t], gy0 * p.in_stride + p.tap_dy[t], n0);
+                tma_load_2d(sB + s * B_BYTES, &tmap_b, &full_bar[s], p.tap_k0[t] + kc * BLOCK_K, n_tile * BLOCK_N);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                               // ===== MMA issuer
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tcgen05_fence_after();
+                const uint64_t da = make_kmajor_sw128_desc(smem_u32(sA + s * A_BYTES));
+                const uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + s * B_BYTES));
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / 8; ++k)  // K = 8 per instruction = 32 bytes along the swizzled row
+                    umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
+                tcgen05_commit(&empty_bar[s]);         // frees the ring slot once these MMAs have read it
+            }
+            tcgen05_commit(tmem_full_bar);             // accumulator complete
+        }
+    } else {                                           // ===== epilogue: warp w reads TMEM lanes 32*(w%4)..+31
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int tx = row & ((1 << p.tw_log2) - 1);
+        const int ty = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
+        const int tn = row >> (p.tw_log2 + p.th_log2);
+        const int gx = gx0 + tx, gy = gy0 + ty, n = n0 + tn;
+        const bool valid = gx < p.grid_w && gy < p.grid_h && n < p.batch;
+        const long long opix = (long long)n * p.out_img_stride + (long long)gy * p.out_row_stride +
+                               (long long)gx * p.out_pix_stride + p.out_offset;
+        float pre_add = 0.0f, map_mul = 1.0f;
+        if (p.epilogue == 1 && valid) {
+            if (p.noise)
+                pre_add = __ldg(p.noise_weight) * __ldg(p.noise + (long long)n * p.noise_img_stride +
+                                                        (long long)gy * p.noise_row_stride +
+                                                        (long long)gx * p.noise_pix_stride + p.noise_offset);
+            if (p.stylemap) {
+                const float *m = p.stylemap + (long long)n * p.map_img_stride + (long long)gy * p.noise_row_stride +
+                                 (long long)gx * p.noise_pix_stride + p.noise_offset;
+                map_mul = __ldg(m);
+                pre_add += __ldg(m + p.map_plane_stride);
+            }
+        }
+        mbar_wait(tmem_full_bar, 0);
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+            if (valid) {
+                const int ch0 = n_tile * BLOCK_N + c * 32;
+                const float4 *rs = p.rowscale ? reinterpret_cast<const float4 *>(p.rowscale + (long long)n * p.cout + ch0) : nullptr;
+                const float4 *s2 = p.out2 ? reinterpret_cast<const float4 *>(p.scale2 + (long long)n * p.cout + ch0) : nullptr;
+                const float4 *bs = (p.epilogue == 1 && p.bias) ? reinterpret_cast<const float4 *>(p.bias + ch0) : nullptr;
+                float4 *o1 = reinterpret_cast<float4 *>(p.out + opix * 1 + ch0);
+                float4 *o2 = p.out2 ? reinterpret_cast<float4 *>(p.out2 + opix + ch0) : nullptr;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float v[4] = {__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                  __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])};
+                    if (rs) { const float4 s = __ldg(rs + j); v[0] *= s.x; v[1] *= s.y; v[2] *= s.z; v[3] *= s.w; }
+                    if (p.epilogue == 1) {
+                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (bs) b = __ldg(bs + j);
+                        const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float t = v[e] * map_mul + pre_add + bb[e];
+                            v[e] = ((t > 0.0f) ? t : t * p.alpha) * p.gain;
+                        }
+                    }
+                    o1[j] = make_float4(v[0], v[1], v[2], v[3]);
+                    if (o2) {
+                        const float4 s = __ldg(s2 + j);
+                        o2[j] = make_float4(round_tf32(v[0] * s.x), round_tf32(v[1] * s.y), round_tf32(v[2] * s.z),
+                                            round_tf32(v[3] * s.w));
+                    }
+                }
+            }
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)BLOCK_N) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------ small helper kernels
+// xs[b,p,c] = tf32(x[b,p,c] * s[b,c])  -- the modulated, tensor-core-ready copy of an NHWC activation
+__global__ void __launch_bounds__(256)
+modulate_tf32_kernel(float *__restrict__ xs, const float *__restrict__ x, const float *__restrict__ s,
+                     uint32_t n4, FastDiv c4_div, FastDiv img4_div, int c4)
+{
+    const uint32_t stride = gridDim.x * 256;
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n4; i += stride) {
+        uint32_t q, cq, b, rem;
+        c4_div.divmod(i, q, cq);                      // channel quad inside the pixel
+        img4_div.divmod(i, b, rem);                   // image index
+        const float4 v = ld_stream4(x + 4ull * i);
+        const float4 m = s ? __ldg(reinterpret_cast<const float4 *>(s) + (size_t)b * c4 + cq) : make_float4(1.f, 1.f, 1.f, 1.f);
+        float4 o = make_float4(round_tf32(v.x * m.x), round_tf32(v.y * m.y), round_tf32(v.z * m.z), round_tf32(v.w * m.w));
+        *reinterpret_cast<float4 *>(xs + 4ull * i) = o;
+    }
+}
+
+// Weight re-layout: reference [cout, cin, kh, kw] -> GEMM B operand [rows][taps][cols], scaled and rounded to tf32.
+//   transpose = 0: rows = cout, cols = cin, tap t = ky*kw + kx                         (forward)
+//   transpose = 1: rows = cin, cols = cout, tap t = (kh-1-ky)*kw + (kw-1-kx)           (dgrad of the plain conv)
+//   transpose = 2: rows = cin, cols = cout, tap t = ky*kw + kx                         (transposed conv forward)
+//   transpose = 3: rows = cout, cols = cin, tap t = ky*kw + kx (same as 0)             (dgrad of the transposed conv)
+__global__ void __launch_bounds__(256)
+weight_prep_kernel(float *__restrict__ dst, const float *__restrict__ w, float scale, int cout, int cin, int kh, int kw,
+                   int transpose)
+{
+    const int taps = kh * kw;
+    const int64_t total = (int64_t)cout * cin * taps;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        int64_t r = i;
+        const int kx = (int)(r % kw); r /= kw;
+        const int ky = (int)(r % kh); r /= kh;
+        const int ci = (int)(r % cin);
+        const int co = (int)(r / cin);
+        const float v = round_tf32(w[i] * scale);
+        int64_t o;
+        if (transpose == 1) o = ((int64_t)ci * taps + ((kh - 1 - ky) * kw + (kw - 1 - kx))) * cout + co;
+        else if (transpose == 2) o = ((int64_t)ci * taps + (ky * kw + kx)) * cout + co;
+        else o = ((int64_t)co * taps + (ky * kw + kx)) * cin + ci;
+        dst[o] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int ilog2_exact(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+template <int BLOCK_N, int STAGES>
+int launch_conv(const CUtensorMap &ta, const CUtensorMap &tb, const ConvKParams &p, int m_tiles, int n_tiles, cudaStream_t st)
+{
+    constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
+    const size_t smem = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 256;
+    auto kern = conv_igemm_tf32_kernel<BLOCK_N, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    kern<<<dim3((unsigned)m_tiles, (unsigned)n_tiles), kConvThreads, smem, st>>>(ta, tb, p);
+    return SR_OK;
+}
+
+}  // namespace
+}  // namespace sr
+
+using namespace sr;
+
+extern "C" int sr_conv_igemm_tf32(const sr_conv_args *a, void *stream)
+{
+    SR_REQUIRE(a, "conv: null args");
+    SR_REQUIRE(a->in && a->weight && a->out, "conv: null tensor");
+    SR_REQUIRE(a->cin >= 32 && a->cin % 32 == 0, "conv: cin must be a multiple of 32 (got %lld)", (long long)a->cin);
+    SR_REQUIRE(a->cout >= 128 && a->cout % 128 == 0, "conv: cout must be a multiple of 128 (got %lld)", (long long)a->cout);
+    SR_REQUIRE(a->num_taps >= 1 && a->num_taps <= 9, "conv: 1..9 taps");
+    SR_REQUIRE(a->in_stride >= 1 && a->in_stride <= 8 && a->out_stride >= 1, "conv: bad strides");
+    SR_REQUIRE(a->batch >= 1 && a->grid_h >= 1 && a->grid_w >= 1, "conv: empty problem");
+    SR_REQUIRE((reinterpret_cast<uintptr_t>(a->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->weight) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "conv: tensors must be 16-byte aligned");
+    SR_REQUIRE(a->epilogue == 0 || a->epilogue == 1, "conv: unknown epilogue");
+    SR_REQUIRE(!a->out2 || a->scale2, "conv: out2 needs scale2");
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) { set_error("conv: cuTensorMapEncodeTiled not available from the driver"); return SR_ERR_DRIVER; }
+    cudaStream_t st = (cudaStream_t)stream;
+
+    // tile shape: 16x8 pixels of one image, or several whole small images
+    int tw, th, tn;
+    if (a->grid_w > 8) { tw = 16; th = 8; tn = 1; }
+    else if (a->grid_w > 4) { tw = 8; th = (a->grid_h > 4) ? 8 : 4; tn = 128 / (tw * th); }
+    else { tw = 4; th = 4; tn = 8; }
+    const int block_n = (a->cout % 256 == 0) ? 256 : 128;
+
+    CUtensorMap ta, tb;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)a->cin, (cuuint64_t)a->in_w, (cuuint64_t)a->in_h, (cuuint64_t)a->batch};
+        cuuint64_t strides[3] = {(cuuint64_t)a->cin * 4, (cuuint64_t)a->in_w * a->cin * 4,
+                                 (cuuint64_t)a->in_h * a->in_w * a->cin * 4};
+        const cuuint32_t s = (cuuint32_t)a->in_stride;
+        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)tw * s, (cuuint32_t)th * s, (cuuint32_t)tn};
+        cuuint32_t estr[4] = {1, s, s, 1};
+        CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(a->in), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv: cuTensorMapEncodeTiled(A) failed with %d", (int)r); return SR_ERR_DRIVER; }
+    }
+    {
+        const cuuint64_t ktot = (cuuint64_t)a->taps_total * a->cin;
+        cuuint64_t dims[2] = {ktot, (cuuint64_t)a->cout};
+        cuuint64_t strides[1] = {ktot * 4};
+        cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)block_n};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(a->weight), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv: cuTensorMapEncodeTiled(B) failed with %d", (int)r); return SR_ERR_DRIVER; }
+    }
+
+    ConvKParams p;
+    p.tw_log2 = ilog2_exact(tw); p.th_log2 = ilog2_exact(th); p.tn_log2 = ilog2_exact(tn);
+    p.tiles_x = (int)((a->grid_w + tw - 1) / tw);
+    p.tiles_y = (int)((a->grid_h + th - 1) / th);
+    const int tiles_n = (int)((a->batch + tn - 1) / tn);
+    p.batch = (int)a->batch; p.grid_h = (int)a->grid_h; p.grid_w = (int)a->grid_w;
+    p.kblocks_per_tap = (int)(a->cin / BLOCK_K);
+    p.num_taps = a->num_taps;
+    for (int t = 0; t < 9; ++t) {
+        p.tap_dy[t] = a->tap_dy[t]; p.tap_dx[t] = a->tap_dx[t];
+        p.tap_k0[t] = (int)(a->tap_w[t] * a->cin);
+    }
+    p.in_stride = a->in_stride;
+    p.cout = (int)a->cout;
+    p.out_pix_stride = (long long)a->out_stride * a->cout;
+    p.out_row_stride = (long long)a->out_stride * a->out_w * a->cout;
+    p.out_img_stride = (long long)a->out_h * a->out_w * a->cout;
+    p.out_offset = ((long long)a->out_y0 * a->out_w + a->out_x0) * a->cout;
+    p.out = a->out; p.out2 = a->out2;
+    p.epilogue = a->epilogue;
+    p.rowscale = a->rowscale; p.scale2 = a->scale2; p.bias = a->bias;
+    p.noise = a->noise; p.noise_weight = a->noise_weight; p.stylemap = a->stylemap;
+    SR_REQUIRE(!p.noise || p.noise_weight, "conv: noise needs noise_weight");
+    // noise / stylemap are planar [*, out_h, out_w] and are addressed on the same output lattice
+    p.noise_pix_stride = a->out_stride;
+    p.noise_row_stride = (long long)a->out_stride * a->out_w;
+    p.noise_img_stride = a->noise_batch_stride;
+    p.noise_offset = (long long)a->out_y0 * a->out_w + a->out_x0;
+    p.map_plane_stride = (long long)a->out_h * a->out_w;
+    p.map_img_stride = a->stylemap_batch_stride;
+    p.alpha = a->alpha; p.gain = a->gain;
+
+    const long long m_tiles = (long long)p.tiles_x * p.tiles_y * tiles_n;
+    SR_REQUIRE(m_tiles < 0x7fffffffll, "conv: too many tiles");
+    int rc;
+    if (block_n == 256) rc = launch_conv<256, 4>(ta, tb, p, (int)m_tiles, (int)(a->cout / 256), st);
+    else rc = launch_conv<128, 6>(ta, tb, p, (int)m_tiles, (int)(a->cout / 128), st);
+    if (rc != SR_OK) return rc;
+    count_launch();
+    return check_launch("sr_conv_igemm_tf32");
+}
+
+extern "C" int sr_modulate_tf32(float *xs, const float *x, const float *style, int64_t batch, int64_t pixels,
+                                int64_t channels, void *stream)
+{
+    SR_REQUIRE(xs && x, "modulate: null pointer");
+    SR_REQUIRE(channels % 4 == 0, "modulate: channels must be a multiple of 4");
+    SR_REQUIRE((reinterpret_cast<uintptr_t>(xs) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+               (!style || (reinterpret_cast<uintptr_t>(style) & 15) == 0), "modulate: 16-byte alignment required");
+    const int64_t n4 = batch * pixels * channels / 4;
+    if (n4 == 0) return SR_OK;
+    SR_REQUIRE(n4 < 0x7fffffffll, "modulate: tensor too large");
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    modulate_tf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        xs, x, style, (uint32_t)n4, FastDiv((uint32_t)(channels / 4)), FastDiv((uint32_t)(pixels * channels / 4)),
+        (int)(channels / 4));
+    count_launch();
+    return check_launch("sr_modulate_tf32");
+}
+
+extern "C" int sr_conv_weight_prep_tf32(float *dst, const float *w, float scale, int64_t cout, int64_t cin, int kh, int kw,
+                                        int transpose, void *stream)
+{
+    SR_REQUIRE(dst && w && cout > 0 && cin > 0 && kh > 0 && kw > 0, "weight_prep: bad arguments");
+    SR_REQUIRE(transpose >= 0 && transpose <= 3, "weight_prep: transpose mode 0..3");
+    const int64_t total = cout * cin * kh * kw;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    weight_prep_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, w, scale, (int)cout, (int)cin, kh, kw, transpose);
+    count_launch();
+    return check_launch("sr_conv_weight_prep_tf32");
+}

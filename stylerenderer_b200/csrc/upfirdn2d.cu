@@ -79,27 +79,35 @@ upfirdn2d_tile_kernel(float *__restrict__ out, const float *__restrict__ x, cons
 #pragma unroll
         for (int b = 0; b < KW; ++b) tk[a][b] = __ldg(taps + (KH - 1 - a) * KW + (KW - 1 - b));
 
-    // ---- stage the zero-padded input tile: rows are distributed over sub-warps of `lpr` lanes
+    // ---- stage the zero-padded input tile with 4-byte cp.async (zero-fill for the padding): every lane
+    //      issues all of its copies back to back, so the whole tile is in flight at once (the rows of a
+    //      (2H+1)-wide plane are not 16-byte aligned, which rules out TMA / 16-byte copies in this layout).
+    //      Rows are distributed over sub-warps of `lpr` lanes.
     {
         int lpr = 32;
-        while (lpr > 1 && (lpr >> 1) >= g.tin_w) lpr >>= 1;
+        while (lpr > 1 && (lpr >> 1) >= g.tin_stride) lpr >>= 1;
         const int rows_per_pass = kThreads / lpr;
         const int sub = threadIdx.x / lpr, l = threadIdx.x % lpr;
         const int total_rows = planes_per_tile * g.tin_h;
+        int p = sub / g.tin_h, ry = sub - p * g.tin_h;               // one division, then incremental
+        const int dp = rows_per_pass / g.tin_h, dr = rows_per_pass - dp * g.tin_h;
         for (int r = sub; r < total_rows; r += rows_per_pass) {
-            const int p = r / g.tin_h, ry = r - p * g.tin_h;
             const int iy = iy0 + ry;
             const int64_t plane = plane0 + p;
             const bool row_ok = (iy >= 0) && (iy < g.in_h) && (plane < g.major);
             const float *src = x + (plane * g.in_h + iy) * (int64_t)g.in_w;
-            float *dst = s_in + (size_t)r * g.tin_stride;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_in + (size_t)r * g.tin_stride);
             for (int cx = l; cx < g.tin_stride; cx += lpr) {
                 const int ix = ix0 + cx;
-                float v = 0.0f;
-                if (row_ok && ix >= 0 && ix < g.in_w) v = __ldg(src + ix);
-                dst[cx] = v;
+                const bool ok = row_ok && ix >= 0 && ix < g.in_w;
+                const float *gp = ok ? src + ix : x;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n"
+                             :: "r"(dst + 4u * cx), "l"(gp), "r"(ok ? 4 : 0) : "memory");
             }
+            p += dp; ry += dr;
+            if (ry >= g.tin_h) { ry -= g.tin_h; ++p; }
         }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
     }
     __syncthreads();
 
@@ -206,7 +214,15 @@ int launch_tile(float *out, const float *x, const float *taps, int64_t major, in
     TileGeom g;
     g.in_h = in_h; g.in_w = in_w; g.out_h = out_h; g.out_w = out_w; g.major = major;
     g.pqx = floor_div_i(pad_x0, UP); g.pqy = floor_div_i(pad_y0, UP);
-    int tx = ilog2_ceil((out_w + VX - 1) / VX); if (tx > 4) tx = 4;         // <= 16 strips = 64 outputs wide
+    int tx = ilog2_ceil((out_w + VX - 1) / VX);                             // <= 16 strips = 64 outputs wide
+    if (tx > 4) {            // wide planes: 64, 32 or 16 columns per tile, whichever wastes the fewest columns
+        int best = 4, best_w = (out_w + 63) / 64 * 64;
+        for (int c = 3; c >= 2; --c) {
+            const int tw = VX << c, padded = (out_w + tw - 1) / tw * tw;
+            if (padded * 100 < best_w * 96) { best = c; best_w = padded; }
+        }
+        tx = best;
+    }
     int ty = ilog2_ceil((out_h + VY - 1) / VY); if (ty > 8 - tx) ty = 8 - tx;
     g.txs_log2 = tx; g.tys_log2 = ty;
     const int txs = 1 << tx, tys = 1 << ty, ppt = kThreads >> (tx + ty);

@@ -1,0 +1,136 @@
+"""Functional front-end of the tcgen05 implicit-GEMM convolution (csrc/modconv.cu) on NHWC float32 tensors.
+
+Internal to the package: layers.ModulatedConv2d / model.StyledConv route here when conv_backend == "tcgen05"
+and the layer shape is supported (cin % 32 == 0, cout % 128 == 0).  All tensors are plain contiguous
+[batch, h, w, channels] views; callers obtain them from channels_last NCHW tensors with .permute(0, 2, 3, 1).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_I32, _I64, _F, _P = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+
+class ConvArgs(ctypes.Structure):           # mirrors `sr_conv_args` in include/stylerenderer_b200.h
+    _fields_ = [("in_", _P), ("batch", _I64), ("in_h", _I64), ("in_w", _I64), ("cin", _I64),
+                ("weight", _P), ("cout", _I64), ("taps_total", _I64),
+                ("num_taps", _I32), ("tap_dy", _I32 * 9), ("tap_dx", _I32 * 9), ("tap_w", _I32 * 9),
+                ("in_stride", _I32),
+                ("grid_h", _I64), ("grid_w", _I64), ("out_h", _I64), ("out_w", _I64),
+                ("out_stride", _I32), ("out_y0", _I32), ("out_x0", _I32),
+                ("out", _P), ("out2", _P), ("epilogue", _I32),
+                ("rowscale", _P), ("scale2", _P), ("bias", _P), ("noise", _P), ("noise_weight", _P), ("stylemap", _P),
+                ("noise_batch_stride", _I64), ("stylemap_batch_stride", _I64),
+                ("alpha", _F), ("gain", _F)]
+
+
+def supported(cin, cout):
+    return cin % 32 == 0 and cin >= 32 and cout % 128 == 0 and cout >= 128
+
+
+def _check_nhwc(t, name):
+    if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.is_contiguous()):
+        raise RuntimeError(f"{name}: expected a contiguous float32 CUDA tensor [batch, h, w, channels]")
+
+
+def weight_prep(w, scale, mode):
+    """Reference-layout weight [cout, cin, kh, kw] -> GEMM B operand [rows, kh*kw, cols], scaled, tf32-rounded.
+    mode 0: rows=cout, cols=cin (forward);  1: rows=cin, cols=cout, taps flipped (dgrad of the plain conv);
+    mode 2: rows=cin, cols=cout, taps as is (dgrad of the stride-2 transposed conv)."""
+    cout, cin, kh, kw = w.shape
+    rows, cols = (cout, cin) if mode in (0, 3) else (cin, cout)
+    dst = torch.empty(rows, kh * kw, cols, dtype=torch.float32, device=w.device)
+    wc = w.contiguous()
+    with torch.cuda.device(w.device):
+        rc = _lib.lib().sr_conv_weight_prep_tf32(_lib.ptr(dst), _lib.ptr(wc), float(scale), cout, cin, kh, kw, mode,
+                                                 _lib.stream_of(w))
+    _lib.check(rc, "sr_conv_weight_prep_tf32")
+    return dst
+
+
+def modulate(x, style=None):
+    """xs = tf32_round(x * style[b, c]) for NHWC x [B,H,W,C]; style [B,C] or None (rounding only)."""
+    _check_nhwc(x, "modulate")
+    b, h, w, c = x.shape
+    xs = torch.empty_like(x)
+    s = style.contiguous() if style is not None else None
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().sr_modulate_tf32(_lib.ptr(xs), _lib.ptr(x), _lib.ptr(s), b, h * w, c, _lib.stream_of(x))
+    _lib.check(rc, "sr_modulate_tf32")
+    return xs
+
+
+def conv_igemm(x, wmat, taps, out, *, in_stride=1, grid=None, out_stride=1, out_origin=(0, 0), epilogue=0,
+               rowscale=None, out2=None, scale2=None, bias=None, noise=None, noise_weight=None, stylemap=None,
+               alpha=0.2, gain=2 ** 0.5):
+    """out[n, y0 + gy*os, x0 + gx*os, :] = epilogue( sum_t x[n, gy*is + dy_t, gx*is + dx_t, :] @ wmat[:, w_t, :]^T ).
+    taps: list of (dy, dx, weight_tap_index)."""
+    _check_nhwc(x, "conv input")
+    _check_nhwc(out, "conv output")
+    a = ConvArgs()
+    a.in_ = _lib.ptr(x)
+    a.batch, a.in_h, a.in_w, a.cin = x.shape
+    a.weight = _lib.ptr(wmat)
+    a.cout, a.taps_total = wmat.shape[0], wmat.shape[1]
+    assert wmat.is_contiguous() and wmat.shape[2] == x.shape[3] and out.shape[3] == wmat.shape[0] and out.shape[0] == x.shape[0]
+    a.num_taps = len(taps)
+    for i, (dy, dx, wi) in enumerate(taps):
+        a.tap_dy[i], a.tap_dx[i], a.tap_w[i] = dy, dx, wi
+    a.in_stride = in_stride
+    gh, gw = grid if grid is not None else (out.shape[1], out.shape[2])
+    a.grid_h, a.grid_w, a.out_h, a.out_w = gh, gw, out.shape[1], out.shape[2]
+    a.out_stride, a.out_y0, a.out_x0 = out_stride, out_origin[0], out_origin[1]
+    a.out = _lib.ptr(out)
+    a.out2 = _lib.ptr(out2)
+    a.epilogue = epilogue
+    a.rowscale, a.scale2, a.bias = _lib.ptr(rowscale), _lib.ptr(scale2), _lib.ptr(bias)
+    a.noise, a.noise_weight, a.stylemap = _lib.ptr(noise), _lib.ptr(noise_weight), _lib.ptr(stylemap)
+    if noise is not None:
+        assert noise.is_contiguous() and noise.shape[-2:] == out.shape[1:3]
+        a.noise_batch_stride = 0 if noise.numel() == out.shape[1] * out.shape[2] else out.shape[1] * out.shape[2]
+    if stylemap is not None:
+        assert stylemap.shape[1] == 2 and stylemap.stride(3) == 1 and stylemap.stride(2) == out.shape[2] \
+            and stylemap.stride(1) == out.shape[1] * out.shape[2]
+        a.stylemap_batch_stride = stylemap.stride(0)
+    a.alpha, a.gain = alpha, gain
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().sr_conv_igemm_tf32(ctypes.byref(a), _lib.stream_of(x))
+    _lib.check(rc, "sr_conv_igemm_tf32")
+    return out
+
+
+TAPS_3X3 = [(ky - 1, kx - 1, ky * 3 + kx) for ky in range(3) for kx in range(3)]
+
+
+def conv3x3(x, wmat, out=None, **kw):
+    """3x3, stride 1, zero padding 1 (cross-correlation like F.conv2d); wmat from weight_prep(mode 0 or 1)."""
+    if out is None:
+        out = torch.empty(x.shape[0], x.shape[1], x.shape[2], wmat.shape[0], dtype=torch.float32, device=x.device)
+    return conv_igemm(x, wmat, TAPS_3X3, out, **kw)
+
+
+def conv_transpose3x3_s2(x, wmat, out=None, rowscale=None):
+    """Stride-2 transposed 3x3 conv, no padding: [B,H,W,Cin] -> [B,2H+1,2W+1,Cout] as four phase GEMMs
+    (reference layers.py:301-309: F.conv_transpose2d(stride=2, padding=0)); wmat from weight_prep(mode 0)."""
+    b, h, w, _ = x.shape
+    if out is None:
+        out = torch.empty(b, 2 * h + 1, 2 * w + 1, wmat.shape[0], dtype=torch.float32, device=x.device)
+    for py in (0, 1):
+        for px in (0, 1):
+            taps = [(-(ky - py) // 2, -(kx - px) // 2, ky * 3 + kx)
+                    for ky in range(py, 3, 2) for kx in range(px, 3, 2)]
+            conv_igemm(x, wmat, taps, out, grid=(h + 1 - py, w + 1 - px), out_stride=2, out_origin=(py, px),
+                       rowscale=rowscale)
+    return out
+
+
+def conv3x3_s2_gather(g, wmat, out_hw, out=None, rowscale=None):
+    """dgrad of the transposed conv: dx[m,n] = sum_{ky,kx} g[2m+ky, 2n+kx] @ W  (stride-2 gather through TMA
+    element strides); g [B,2H+1,2W+1,Cout], wmat from weight_prep(mode 2) -> [B,H,W,Cin]."""
+    h, w = out_hw
+    if out is None:
+        out = torch.empty(g.shape[0], h, w, wmat.shape[0], dtype=torch.float32, device=g.device)
+    taps = [(ky, kx, ky * 3 + kx) for ky in range(3) for kx in range(3)]
+    return conv_igemm(g, wmat, taps, out, in_stride=2, rowscale=rowscale)

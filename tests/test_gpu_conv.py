@@ -1,0 +1,123 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution (csrc/modconv.cu) against float64 torch convolutions of the
+same tf32-rounded operands (so the only difference left is fp32 accumulation order)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from make_golden import seeded
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tc():
+    assert torch.cuda.is_available()
+    from stylerenderer_b200 import tc_conv
+    return tc_conv
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2)
+
+
+def relerr(got, want):
+    return float((got.double() - want).abs().max() / want.abs().max())
+
+
+CASES = [(2, 16, 16, 64, 128), (3, 8, 8, 32, 256), (9, 4, 4, 96, 128), (1, 24, 40, 32, 384), (2, 64, 64, 128, 128),
+         (5, 5, 5, 32, 128), (2, 9, 9, 64, 256), (1, 17, 33, 32, 128)]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_plain_conv_and_dgrad(tc, case):
+    b, h, w, cin, cout = case
+    x = tc.modulate(nhwc(seeded((b, cin, h, w), 1)).cuda())               # tf32-rounded operand
+    wt = seeded((cout, cin, 3, 3), 2).cuda()
+    wm = tc.weight_prep(wt, 0.05, 0)
+    w_rounded = wm.view(cout, 3, 3, cin).permute(0, 3, 1, 2)              # == tf32(wt * 0.05)
+    y = tc.conv3x3(x, wm)
+    want = F.conv2d(nchw(x).double(), w_rounded.double(), padding=1)
+    assert relerr(nchw(y), want) < 2e-5, case
+    if cin % 128 == 0 and cout % 32 == 0:
+        g = tc.modulate(nhwc(seeded((b, cout, h, w), 3)).cuda())
+        wd = tc.weight_prep(wt, 0.05, 1)
+        dx = tc.conv3x3(g, wd)
+        want = torch.autograd.grad(F.conv2d(nchw(x).double().requires_grad_(True), w_rounded.double(), padding=1).sum() * 0
+                                   + 0, [], allow_unused=True) if False else None
+        xin = nchw(x).double().requires_grad_(True)
+        ref, = torch.autograd.grad(F.conv2d(xin, w_rounded.double(), padding=1), xin, nchw(g).double())
+        assert relerr(nchw(dx), ref) < 2e-5, case
+
+
+def test_styled_epilogue(tc):
+    b, h, w, cin, cout = 3, 16, 16, 64, 128
+    x = tc.modulate(nhwc(seeded((b, cin, h, w), 4)).cuda())
+    wt = seeded((cout, cin, 3, 3), 5).cuda()
+    wm = tc.weight_prep(wt, 0.04, 0)
+    w_rounded = wm.view(cout, 3, 3, cin).permute(0, 3, 1, 2).double()
+    d = (seeded((b, cout), 6).abs() + 0.5).cuda()
+    s2 = (seeded((b, cout), 7) + 1).cuda()
+    bias = seeded((cout,), 8).cuda()
+    noise = seeded((b, 1, h, w), 9).cuda()
+    nw = torch.tensor([0.3], device="cuda")
+    smap = seeded((b, 4, h, w), 10).cuda()[:, 2:]                          # non-contiguous batch stride
+    out = torch.empty(b, h, w, cout, device="cuda")
+    out2 = torch.empty_like(out)
+    tc.conv3x3(x, wm, out=out, epilogue=1, rowscale=d, out2=out2, scale2=s2, bias=bias, noise=noise.view(b, h, w),
+               noise_weight=nw, stylemap=smap)
+    conv = F.conv2d(nchw(x).double(), w_rounded, padding=1) * d.double().view(b, cout, 1, 1)
+    t = conv * smap[:, :1].double() + smap[:, 1:2].double() + 0.3 * noise.double() + bias.double().view(1, -1, 1, 1)
+    want = F.leaky_relu(t, 0.2) * 2 ** 0.5
+    assert relerr(nchw(out), want) < 3e-5
+    assert relerr(nchw(out2), want * s2.double().view(b, cout, 1, 1)) < 6e-4   # tf32 rounding of the second output
+    # broadcast noise plane, no stylemap, no second output
+    out3 = torch.empty_like(out)
+    tc.conv3x3(x, wm, out=out3, epilogue=1, rowscale=d, bias=bias, noise=noise[0, 0].contiguous(), noise_weight=nw)
+    want = F.leaky_relu(conv + 0.3 * noise[0, 0].double() + bias.double().view(1, -1, 1, 1), 0.2) * 2 ** 0.5
+    assert relerr(nchw(out3), want) < 3e-5
+
+
+@pytest.mark.parametrize("case", [(2, 4, 4, 64, 128), (2, 8, 8, 32, 128), (1, 16, 16, 32, 256), (3, 32, 32, 64, 128),
+                                  (1, 7, 12, 32, 128)])
+def test_transposed_conv_and_its_dgrad(tc, case):
+    b, h, w, cin, cout = case
+    x = tc.modulate(nhwc(seeded((b, cin, h, w), 11)).cuda())
+    wt = seeded((cout, cin, 3, 3), 12).cuda()
+    wm = tc.weight_prep(wt, 0.05, 0)
+    w_rounded = wm.view(cout, 3, 3, cin).permute(0, 3, 1, 2).double()      # [cout, cin, 3, 3]
+    d = (seeded((b, cout), 13).abs() + 0.5).cuda()
+    y = tc.conv_transpose3x3_s2(x, wm, rowscale=d)
+    assert y.shape == (b, 2 * h + 1, 2 * w + 1, cout)
+    xin = nchw(x).double().requires_grad_(True)
+    ref = F.conv_transpose2d(xin, w_rounded.transpose(0, 1), stride=2)
+    assert relerr(nchw(y), ref.detach() * d.double().view(b, cout, 1, 1)) < 2e-5, case
+    if cout % 32 == 0 and cin % 128 == 0:
+        g = tc.modulate(nhwc(seeded((b, cout, 2 * h + 1, 2 * w + 1), 14)).cuda())
+        wg = tc.weight_prep(wt, 0.05, 2)
+        dx = tc.conv3x3_s2_gather(g, wg, (h, w))
+        want, = torch.autograd.grad(ref, xin, nchw(g).double())
+        assert relerr(nchw(dx), want) < 2e-5, case
+
+
+def test_transposed_conv_dgrad_wide(tc):
+    b, h, w, cin, cout = 2, 16, 16, 128, 128
+    wt = seeded((cout, cin, 3, 3), 15).cuda()
+    g = tc.modulate(nhwc(seeded((b, cout, 2 * h + 1, 2 * w + 1), 16)).cuda())
+    wg = tc.weight_prep(wt, 0.05, 2)
+    w_rounded = wg.view(cin, 3, 3, cout).permute(3, 0, 1, 2).double()      # back to [cout, cin, 3, 3]
+    dx = tc.conv3x3_s2_gather(g, wg, (h, w))
+    xin = torch.zeros(b, cin, h, w, dtype=torch.float64, device="cuda", requires_grad=True)
+    want, = torch.autograd.grad(F.conv_transpose2d(xin, w_rounded.transpose(0, 1), stride=2), xin, nchw(g).double())
+    assert relerr(nchw(dx), want) < 2e-5
+    # plain dgrad at cin = cout = 128
+    x = tc.modulate(nhwc(seeded((b, cin, h, w), 17)).cuda())
+    gg = tc.modulate(nhwc(seeded((b, cout, h, w), 18)).cuda())
+    wd = tc.weight_prep(wt, 0.05, 1)
+    w_r = wd.view(cin, 3, 3, cout).flip(1, 2).permute(3, 0, 1, 2).double()
+    xin = nchw(x).double().requires_grad_(True)
+    want, = torch.autograd.grad(F.conv2d(xin, w_r, padding=1), xin, nchw(gg).double())
+    assert relerr(nchw(tc.conv3x3(gg, wd)), want) < 2e-5

@@ -156,10 +156,11 @@ def test_upfirdn2d_gradients(op, up, down, pad):
     def run(f, xx, kk):
         xx = xx.clone().requires_grad_(True)
         y = f(xx, kk)
-        gy = (torch.arange(y.numel(), dtype=torch.float32, device=y.device).view_as(y) % 7 - 3) / 3
+        gy = ((torch.arange(y.numel(), dtype=torch.float32, device=y.device).view_as(y) % 7 - 3) / 3).requires_grad_(True)
         gx, = torch.autograd.grad(y, xx, gy, create_graph=True)
-        ggx, = torch.autograd.grad((gx * gx).sum(), xx)
-        return y.detach(), gx.detach(), ggx
+        # the op is linear in x, so the second-order path runs through the cotangent (as in R1 / path regularisers)
+        ggy, = torch.autograd.grad((gx * gx).sum(), gy)
+        return y.detach(), gx.detach(), ggy
     ref = run(lambda a, b: T.upfirdn2d(a, b, up, down, pad), x, k)
     got = run(lambda a, b: op.upfirdn2d(a, b, up=up, down=down, pad=pad), cuda(x), cuda(k))
     for r, g in zip(ref, got):
@@ -173,6 +174,7 @@ def test_upfirdn2d_full_size_properties(op):
     k = (T.fir_taps([1, 3, 3, 1]) * 4).cuda()
     y = op.upfirdn2d(x, k, pad=(1, 1))
     assert y.shape == (8, 128, 256, 256)
+    torch.backends.cudnn.allow_tf32 = False              # the comparison conv must be true fp32
     want = torch.nn.functional.conv2d(x.view(-1, 1, 257, 257), torch.flip(k, [0, 1]).view(1, 1, 4, 4), padding=1)
     want = want.view(8, 128, 256, 256)
     torch.testing.assert_close(y, want, rtol=1e-4, atol=1e-4)
