@@ -150,6 +150,28 @@ typedef struct sr_conv_args {
 } sr_conv_args;
 int sr_conv_igemm_tf32(const sr_conv_args *args, void *stream);
 
+/* Weight gradient of the same contraction on the tensor cores (replaces cuDNN's grouped wgrad under
+ * ModulatedConv2d's backward): for every tap t < num_taps
+ *   dw[co, tap_out[t], ci] (+)= sum_{n, gy, gx} g[n, gy*g_stride + g_dy[t], gx*g_stride + g_dx[t], co]
+ *                                            * x[n, gy*x_stride + x_dy[t], gx*x_stride + x_dx[t], ci]
+ * over a grid_h x grid_w lattice (zero outside either tensor).  g [batch, g_h, g_w, cout] and
+ * x [batch, x_h, x_w, cin] are NHWC fp32 (pre-rounded to tf32), dw is [cout][taps_total][cin] fp32.
+ * cin % 128 == 0, cout % 128 == 0.  Split-K with fp32 atomics: zero_init != 0 clears dw first. */
+typedef struct sr_wgrad_args {
+    const float *g;
+    int64_t batch, g_h, g_w, cout;
+    const float *x;
+    int64_t x_h, x_w, cin;
+    int64_t grid_h, grid_w;
+    int32_t num_taps;
+    int32_t g_dy[9], g_dx[9], x_dy[9], x_dx[9], tap_out[9];
+    int32_t g_stride, x_stride;
+    float *dw;
+    int64_t taps_total;
+    int32_t zero_init;
+} sr_wgrad_args;
+int sr_conv_wgrad_tf32(const sr_wgrad_args *args, void *stream);
+
 /* xs[n,p,c] = tf32_round(x[n,p,c] * style[n,c]) for an NHWC tensor (style == NULL: rounding only). */
 int sr_modulate_tf32(float *xs, const float *x, const float *style, int64_t batch, int64_t pixels, int64_t channels,
                      void *stream);

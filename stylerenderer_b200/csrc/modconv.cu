@@ -268,6 +268,135 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
 }
 
+// ------------------------------------------------------------------------------------ wgrad
+// dW[co, t, ci] += sum over (image, pixel) of  G[n, gy*ga + gdy_t, gx*ga + gdx_t, co] * X[n, gy*xa + xdy_t, gx*xa + xdx_t, ci]
+// i.e. D = A^T B with the reduction (K) running over pixels.  Both operands are read straight from the NHWC
+// tensors, so they are MN-major for the tensor core: a TMA box {32 channels, TW, TH, TN} lands as 64 K-rows of
+// 128 bytes (one 128B-swizzle atom per 8 pixels); M = 128 output channels = 4 such column blocks, LBO apart.
+// Split-K over pixel tiles (gridDim.z) with fp32 atomic accumulation into the zero-initialised result.
+constexpr int WG_BK = 64;                              // pixels per pipeline stage
+constexpr int WG_COLBLK_BYTES = WG_BK * 128;           // one 32-channel column block of a stage
+constexpr int WG_N = 128;
+constexpr int WG_STAGE_BYTES = 2 * 4 * WG_COLBLK_BYTES;
+constexpr int WG_STAGES = 3;
+
+struct WgradKParams {
+    int tw_log2, th_log2, tn_log2;                     // K tile = 64 pixels
+    int tiles_x, tiles_y, tiles_n;
+    int ktiles_per_split;
+    int n_tiles;                                       // cin / 128
+    int g_stride, x_stride;
+    int g_dy[9], g_dx[9], x_dy[9], x_dx[9], tap_out[9];
+    int taps_total, cin;
+    float *dw;                                         // [cout][taps_total][cin]
+};
+
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;             // next 32-element group along M/N
+    d |= (uint64_t)(1024 >> 4) << 32;                  // next 8 rows along K
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
+                  const WgradKParams p)
+{
+    constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                ((uint32_t)(WG_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);   // MN-major A and B
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + WG_STAGES * WG_STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + WG_STAGES;
+    uint64_t *tmem_full_bar = empty_bar + WG_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x / p.n_tiles, n_tile = blockIdx.x % p.n_tiles;
+    const int tap = blockIdx.y;
+    const int total_kt = p.tiles_x * p.tiles_y * p.tiles_n;
+    const int kt0 = blockIdx.z * p.ktiles_per_split;
+    const int kt1 = min(total_kt, kt0 + p.ktiles_per_split);
+    const int num_kt = kt1 - kt0;                      // >= 1 by construction of the grid
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_g) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_x) : "memory");
+        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)WG_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < num_kt; ++it) {
+                const int s = it % WG_STAGES;
+                const uint32_t ph = (it / WG_STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                const int kt = kt0 + it;
+                const int tile_x = kt % p.tiles_x, tile_y = (kt / p.tiles_x) % p.tiles_y, tile_n = kt / (p.tiles_x * p.tiles_y);
+                const int gx0 = tile_x << p.tw_log2, gy0 = tile_y << p.th_log2, n0 = tile_n << p.tn_log2;
+                uint8_t *sa = smem + s * WG_STAGE_BYTES, *sb = sa + 4 * WG_COLBLK_BYTES;
+                mbar_expect_tx(&full_bar[s], WG_STAGE_BYTES);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    tma_load_4d(sa + j * WG_COLBLK_BYTES, &tmap_g, &full_bar[s], m_tile * BLOCK_M + j * 32,
+                                gx0 * p.g_stride + p.g_dx[tap], gy0 * p.g_stride + p.g_dy[tap], n0);
+                    tma_load_4d(sb + j * WG_COLBLK_BYTES, &tmap_x, &full_bar[s], n_tile * WG_N + j * 32,
+                                gx0 * p.x_stride + p.x_dx[tap], gy0 * p.x_stride + p.x_dy[tap], n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int it = 0; it < num_kt; ++it) {
+                const int s = it % WG_STAGES;
+                const uint32_t ph = (it / WG_STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tcgen05_fence_after();
+                const uint32_t a0 = smem_u32(smem + s * WG_STAGE_BYTES), b0 = a0 + 4 * WG_COLBLK_BYTES;
+#pragma unroll
+                for (int k = 0; k < WG_BK / 8; ++k)    // 8 pixels (one swizzle atom of K rows) per instruction
+                    umma_tf32(tmem_base, make_mnmajor_sw128_desc(a0 + k * 1024, WG_COLBLK_BYTES),
+                              make_mnmajor_sw128_desc(b0 + k * 1024, WG_COLBLK_BYTES), kIdesc, (it | k) != 0);
+                tcgen05_commit(&empty_bar[s]);
+            }
+            tcgen05_commit(tmem_full_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        const int co = m_tile * BLOCK_M + q * 32 + lane;
+        float *dst = p.dw + ((long long)co * p.taps_total + p.tap_out[tap]) * p.cin + n_tile * WG_N;
+        mbar_wait(tmem_full_bar, 0);
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < WG_N / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + c * 32 + j, __uint_as_float(r[j]));
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)WG_N) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------ small helper kernels
 // xs[b,p,c] = tf32(x[b,p,c] * s[b,c])  -- the modulated, tensor-core-ready copy of an NHWC activation
 __global__ void __launch_bounds__(256)
@@ -443,6 +572,75 @@ extern "C" int sr_conv_igemm_tf32(const sr_conv_args *a, void *stream)
     if (rc != SR_OK) return rc;
     count_launch();
     return check_launch("sr_conv_igemm_tf32");
+}
+
+extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
+{
+    SR_REQUIRE(a && a->g && a->x && a->dw, "wgrad: null argument");
+    SR_REQUIRE(a->cout >= 128 && a->cout % 128 == 0 && a->cin >= 128 && a->cin % 128 == 0,
+               "wgrad: cin and cout must be multiples of 128 (got %lld, %lld)", (long long)a->cin, (long long)a->cout);
+    SR_REQUIRE(a->num_taps >= 1 && a->num_taps <= 9 && a->g_stride >= 1 && a->x_stride >= 1, "wgrad: bad taps/strides");
+    SR_REQUIRE(a->batch >= 1 && a->grid_h >= 1 && a->grid_w >= 1, "wgrad: empty problem");
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) { set_error("wgrad: cuTensorMapEncodeTiled not available from the driver"); return SR_ERR_DRIVER; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int tw, th, tn;
+    if (a->grid_w > 8) { tw = 16; th = 4; tn = 1; }
+    else if (a->grid_w > 4) { tw = 8; th = 8; tn = 1; }
+    else { tw = 4; th = 4; tn = 4; }
+    CUtensorMap tg, tx;
+    auto make_map = [&](CUtensorMap *m, const float *base, int64_t hh, int64_t ww, int64_t cc, int stride) -> int {
+        cuuint64_t dims[4] = {(cuuint64_t)cc, (cuuint64_t)ww, (cuuint64_t)hh, (cuuint64_t)a->batch};
+        cuuint64_t strides[3] = {(cuuint64_t)cc * 4, (cuuint64_t)ww * cc * 4, (cuuint64_t)hh * ww * cc * 4};
+        const cuuint32_t s = (cuuint32_t)stride;
+        cuuint32_t box[4] = {32, (cuuint32_t)tw * s, (cuuint32_t)th * s, (cuuint32_t)tn};
+        cuuint32_t estr[4] = {1, s, s, 1};
+        CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("wgrad: cuTensorMapEncodeTiled failed with %d", (int)r); return SR_ERR_DRIVER; }
+        return SR_OK;
+    };
+    int rc = make_map(&tg, a->g, a->g_h, a->g_w, a->cout, a->g_stride);
+    if (rc != SR_OK) return rc;
+    rc = make_map(&tx, a->x, a->x_h, a->x_w, a->cin, a->x_stride);
+    if (rc != SR_OK) return rc;
+
+    WgradKParams p;
+    p.tw_log2 = ilog2_exact(tw); p.th_log2 = ilog2_exact(th); p.tn_log2 = ilog2_exact(tn);
+    p.tiles_x = (int)((a->grid_w + tw - 1) / tw);
+    p.tiles_y = (int)((a->grid_h + th - 1) / th);
+    p.tiles_n = (int)((a->batch + tn - 1) / tn);
+    p.n_tiles = (int)(a->cin / WG_N);
+    const int mn_tiles = (int)(a->cout / BLOCK_M) * p.n_tiles;
+    const long long total_kt = (long long)p.tiles_x * p.tiles_y * p.tiles_n;
+    // split K so that about two waves of CTAs cover the 148 SMs
+    long long splits = (2 * kNumSMs + (long long)mn_tiles * a->num_taps - 1) / ((long long)mn_tiles * a->num_taps);
+    if (splits < 1) splits = 1;
+    if (splits > total_kt) splits = total_kt;
+    p.ktiles_per_split = (int)((total_kt + splits - 1) / splits);
+    splits = (total_kt + p.ktiles_per_split - 1) / p.ktiles_per_split;
+    p.g_stride = a->g_stride; p.x_stride = a->x_stride;
+    for (int t = 0; t < 9; ++t) {
+        p.g_dy[t] = a->g_dy[t]; p.g_dx[t] = a->g_dx[t]; p.x_dy[t] = a->x_dy[t]; p.x_dx[t] = a->x_dx[t];
+        p.tap_out[t] = a->tap_out[t];
+    }
+    p.taps_total = (int)a->taps_total; p.cin = (int)a->cin;
+    p.dw = a->dw;
+    const size_t smem = 1024 + (size_t)WG_STAGES * WG_STAGE_BYTES + 256;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    if (a->zero_init) {
+        cudaError_t e = cudaMemsetAsync(a->dw, 0, sizeof(float) * (size_t)a->cout * a->taps_total * a->cin, st);
+        if (e != cudaSuccess) { set_error("wgrad: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    wgrad_tf32_kernel<<<dim3((unsigned)mn_tiles, (unsigned)a->num_taps, (unsigned)splits), kConvThreads, smem, st>>>(tg, tx, p);
+    count_launch();
+    return check_launch("sr_conv_wgrad_tf32");
 }
 
 extern "C" int sr_modulate_tf32(float *xs, const float *x, const float *style, int64_t batch, int64_t pixels,

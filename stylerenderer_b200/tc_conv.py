@@ -26,6 +26,18 @@ class ConvArgs(ctypes.Structure):           # mirrors `sr_conv_args` in include/
                 ("alpha", _F), ("gain", _F)]
 
 
+class WgradArgs(ctypes.Structure):         # mirrors `sr_wgrad_args`
+    _fields_ = [("g", _P), ("batch", _I64), ("g_h", _I64), ("g_w", _I64), ("cout", _I64),
+                ("x", _P), ("x_h", _I64), ("x_w", _I64), ("cin", _I64),
+                ("grid_h", _I64), ("grid_w", _I64), ("num_taps", _I32),
+                ("g_dy", _I32 * 9), ("g_dx", _I32 * 9), ("x_dy", _I32 * 9), ("x_dx", _I32 * 9), ("tap_out", _I32 * 9),
+                ("g_stride", _I32), ("x_stride", _I32), ("dw", _P), ("taps_total", _I64), ("zero_init", _I32)]
+
+
+def wgrad_supported(cin, cout):
+    return cin % 128 == 0 and cout % 128 == 0 and cin >= 128 and cout >= 128
+
+
 def supported(cin, cout):
     return cin % 32 == 0 and cin >= 32 and cout % 128 == 0 and cout >= 128
 
@@ -134,3 +146,38 @@ def conv3x3_s2_gather(g, wmat, out_hw, out=None, rowscale=None):
         out = torch.empty(g.shape[0], h, w, wmat.shape[0], dtype=torch.float32, device=g.device)
     taps = [(ky, kx, ky * 3 + kx) for ky in range(3) for kx in range(3)]
     return conv_igemm(g, wmat, taps, out, in_stride=2, rowscale=rowscale)
+
+
+def wgrad(g, x, taps, grid, *, g_stride=1, x_stride=1, taps_total=9, dw=None):
+    """dw[co, t_out, ci] = sum_{n,gy,gx} g[n, gy*gs + gdy, gx*gs + gdx, co] * x[n, gy*xs + xdy, gx*xs + xdx, ci];
+    taps: list of (g_dy, g_dx, x_dy, x_dx, t_out) -> [cout, taps_total, cin]."""
+    _check_nhwc(g, "wgrad g")
+    _check_nhwc(x, "wgrad x")
+    a = WgradArgs()
+    a.g, a.x = _lib.ptr(g), _lib.ptr(x)
+    a.batch, a.g_h, a.g_w, a.cout = g.shape
+    _, a.x_h, a.x_w, a.cin = x.shape
+    a.grid_h, a.grid_w = grid
+    a.num_taps = len(taps)
+    for i, (gdy, gdx, xdy, xdx, to) in enumerate(taps):
+        a.g_dy[i], a.g_dx[i], a.x_dy[i], a.x_dx[i], a.tap_out[i] = gdy, gdx, xdy, xdx, to
+    a.g_stride, a.x_stride = g_stride, x_stride
+    if dw is None:
+        dw = torch.empty(g.shape[3], taps_total, x.shape[3], dtype=torch.float32, device=g.device)
+    a.dw, a.taps_total, a.zero_init = _lib.ptr(dw), taps_total, 1
+    with torch.cuda.device(g.device):
+        rc = _lib.lib().sr_conv_wgrad_tf32(ctypes.byref(a), _lib.stream_of(g))
+    _lib.check(rc, "sr_conv_wgrad_tf32")
+    return dw
+
+
+def wgrad3x3(g, x):
+    """Weight gradient of conv3x3 (stride 1, pad 1): dw[co, ky*3+kx, ci] = sum g[n,y,x,co] * x[n,y+ky-1,x+kx-1,ci]."""
+    taps = [(0, 0, ky - 1, kx - 1, ky * 3 + kx) for ky in range(3) for kx in range(3)]
+    return wgrad(g, x, taps, (g.shape[1], g.shape[2]))
+
+
+def wgrad_transpose3x3_s2(g, x):
+    """Weight gradient of the stride-2 transposed conv: dw[co, ky*3+kx, ci] = sum g[n,2m+ky,2n+kx,co] * x[n,m,n,ci]."""
+    taps = [(ky, kx, 0, 0, ky * 3 + kx) for ky in range(3) for kx in range(3)]
+    return wgrad(g, x, taps, (x.shape[1], x.shape[2]), g_stride=2)

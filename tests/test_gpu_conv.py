@@ -121,3 +121,23 @@ def test_transposed_conv_dgrad_wide(tc):
     xin = nchw(x).double().requires_grad_(True)
     want, = torch.autograd.grad(F.conv2d(xin, w_r, padding=1), xin, nchw(gg).double())
     assert relerr(nchw(tc.conv3x3(gg, wd)), want) < 2e-5
+
+
+@pytest.mark.parametrize("case", [(2, 16, 16, 128, 128), (3, 8, 8, 128, 256), (9, 4, 4, 256, 128), (1, 20, 36, 128, 128),
+                                  (2, 64, 64, 128, 128), (5, 5, 5, 128, 128)])
+def test_wgrad(tc, case):
+    b, h, w, cin, cout = case
+    x = tc.modulate(nhwc(seeded((b, cin, h, w), 21)).cuda())
+    g = tc.modulate(nhwc(seeded((b, cout, h, w), 22)).cuda())
+    dw = tc.wgrad3x3(g, x)                                                   # [cout, 9, cin]
+    wt = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, device="cuda", requires_grad=True)
+    want, = torch.autograd.grad(F.conv2d(nchw(x).double(), wt, padding=1), wt, nchw(g).double())
+    got = dw.view(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    assert relerr(got, want) < 5e-5, case
+    # transposed stride-2 conv
+    g2 = tc.modulate(nhwc(seeded((b, cout, 2 * h + 1, 2 * w + 1), 23)).cuda())
+    dw2 = tc.wgrad_transpose3x3_s2(g2, x)
+    wt2 = torch.zeros(cin, cout, 3, 3, dtype=torch.float64, device="cuda", requires_grad=True)
+    want2, = torch.autograd.grad(F.conv_transpose2d(nchw(x).double(), wt2, stride=2), wt2, nchw(g2).double())
+    got2 = dw2.view(cout, 3, 3, cin).permute(3, 0, 1, 2)                   # -> [cin, cout, 3, 3]
+    assert relerr(got2, want2) < 5e-5, case
