@@ -272,7 +272,7 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 // dW[co, t, ci] += sum over (image, pixel) of  G[n, gy*ga + gdy_t, gx*ga + gdx_t, co] * X[n, gy*xa + xdy_t, gx*xa + xdx_t, ci]
 // i.e. D = A^T B with the reduction (K) running over pixels.  Both operands are read straight from the NHWC
 // tensors, so they are MN-major for the tensor core: a TMA box {32 channels, TW, TH, TN} lands as 64 K-rows of
-// 128 bytes (one 128B-swizzle atom per 8 pixels); M = 128 output channels = 4 such column blocks, LBO apart.
+// 128 bytes (two 4-row swizzle atoms per K=8 instruction); M = 128 output channels = 4 such column blocks, LBO apart.
 // Split-K over pixel tiles (gridDim.z) with fp32 atomic accumulation into the zero-initialised result.
 constexpr int WG_BK = 64;                              // pixels per pipeline stage
 constexpr int WG_COLBLK_BYTES = WG_BK * 128;           // one 32-channel column block of a stage
@@ -291,13 +291,16 @@ struct WgradKParams {
     float *dw;                                         // [cout][taps_total][cin]
 };
 
+// MN-major tf32 operands exist in one shared-memory layout only: 128-byte swizzle with 32-byte atomicity
+// (cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B = 1, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of
+// 4 K-rows x 128 B; LBO = distance to the next 32-element group along M/N, SBO = distance to the next 4 K-rows.
 __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
-    d |= (uint64_t)(lbo_bytes >> 4) << 16;             // next 32-element group along M/N
-    d |= (uint64_t)(1024 >> 4) << 32;                  // next 8 rows along K
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)1 << 61;
     return d;
 }
 
@@ -596,8 +599,8 @@ extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
         cuuint32_t box[4] = {32, (cuuint32_t)tw * s, (cuuint32_t)th * s, (cuuint32_t)tn};
         cuuint32_t estr[4] = {1, s, s, 1};
         CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("wgrad: cuTensorMapEncodeTiled failed with %d", (int)r); return SR_ERR_DRIVER; }
         return SR_OK;
     };

@@ -165,6 +165,79 @@ upfirdn2d_tile_kernel(float *__restrict__ out, const float *__restrict__ x, cons
     }
 }
 
+// ---- channels-last (NHWC, minor = C) FIR, up = down = 1: the layout of the tcgen05 conv pipeline ---------
+// One thread = 4 channels (float4) x 2 adjacent output columns x a strip of RY output rows.  Consecutive lanes
+// take consecutive channel quads, so every load/store instruction of a warp is one contiguous 512-byte run;
+// a KH-row x (KW+1)-column register window slides down the strip, so each input element is fetched from
+// L1/L2 ~2.5 times per output instead of KH*KW times.
+struct NhwcGeom {
+    int64_t major, total_threads;
+    int in_h, in_w, out_h, out_w, c4, pad_x0, pad_y0, strips_y, pairs_x, rows_per_strip;
+    FastDiv div_c4, div_pairs, div_strips;
+};
+
+template <int KH, int KW>
+__global__ void __launch_bounds__(kThreads)
+upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, const float *__restrict__ taps,
+                      const NhwcGeom g)
+{
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (tid >= g.total_threads) return;
+    uint32_t t = (uint32_t)tid, c, xp, ys, n;
+    g.div_c4.divmod(t, t, c);
+    g.div_pairs.divmod(t, t, xp);
+    g.div_strips.divmod(t, n, ys);
+
+    float tk[KH][KW];
+#pragma unroll
+    for (int a = 0; a < KH; ++a)
+#pragma unroll
+        for (int b = 0; b < KW; ++b) tk[a][b] = __ldg(taps + (KH - 1 - a) * KW + (KW - 1 - b));
+
+    const int ox0 = xp * 2;
+    const int ix0 = ox0 - g.pad_x0;
+    const int oy0 = ys * g.rows_per_strip;
+    const int oy1 = min(g.out_h, oy0 + g.rows_per_strip);
+    const float4 *xin = reinterpret_cast<const float4 *>(x) + (int64_t)n * g.in_h * g.in_w * g.c4 + c;
+    float4 *yout = reinterpret_cast<float4 *>(out) + (int64_t)n * g.out_h * g.out_w * g.c4 + c;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    float4 win[KH][KW + 1];
+    auto load_row = [&](float4 (&row)[KW + 1], int iy) {
+        const bool row_ok = iy >= 0 && iy < g.in_h;
+        const float4 *src = xin + (int64_t)iy * g.in_w * g.c4;
+#pragma unroll
+        for (int b = 0; b < KW + 1; ++b) {
+            const int ix = ix0 + b;
+            row[b] = (row_ok && ix >= 0 && ix < g.in_w) ? __ldg(src + (int64_t)ix * g.c4) : zero;
+        }
+    };
+#pragma unroll
+    for (int a = 0; a < KH - 1; ++a) load_row(win[a], oy0 - g.pad_y0 + a);
+    for (int oy = oy0; oy < oy1; ++oy) {
+        load_row(win[KH - 1], oy - g.pad_y0 + KH - 1);
+        float4 acc[2] = {zero, zero};
+#pragma unroll
+        for (int a = 0; a < KH; ++a)
+#pragma unroll
+            for (int b = 0; b < KW; ++b)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float4 v = win[a][j + b];
+                    const float k = tk[a][b];
+                    acc[j].x = fmaf(v.x, k, acc[j].x); acc[j].y = fmaf(v.y, k, acc[j].y);
+                    acc[j].z = fmaf(v.z, k, acc[j].z); acc[j].w = fmaf(v.w, k, acc[j].w);
+                }
+        float4 *dst = yout + ((int64_t)oy * g.out_w + ox0) * g.c4;
+        dst[0] = acc[0];
+        if (ox0 + 1 < g.out_w) dst[g.c4] = acc[1];
+#pragma unroll
+        for (int a = 0; a < KH - 1; ++a)
+#pragma unroll
+            for (int b = 0; b < KW + 1; ++b) win[a][b] = win[a + 1][b];
+    }
+}
+
 // ---- generic: one thread per output element, any geometry ---------------------------------------
 struct GenericGeom {
     int64_t major, minor, total;
@@ -285,6 +358,22 @@ extern "C" int sr_upfirdn2d_f32(float *out, const float *x, const float *taps,
             else SR_TILE(2, 1, 1, 0, 2);
         }
 #undef SR_TILE
+    }
+    if (rc == SR_ERR_UNSUPPORTED && minor >= 4 && minor % 4 == 0 && up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1 &&
+        kernel_h == 4 && kernel_w == 4 && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(x)) & 15u) == 0) {
+        NhwcGeom g;
+        g.major = major; g.in_h = (int)in_h; g.in_w = (int)in_w; g.out_h = (int)oh; g.out_w = (int)ow;
+        g.c4 = (int)(minor / 4); g.pad_x0 = pad_x0; g.pad_y0 = pad_y0;
+        g.rows_per_strip = oh >= 64 ? 16 : (oh >= 16 ? 8 : 4);
+        g.strips_y = (int)((oh + g.rows_per_strip - 1) / g.rows_per_strip);
+        g.pairs_x = (int)((ow + 1) / 2);
+        g.total_threads = major * g.strips_y * g.pairs_x * g.c4;
+        g.div_c4 = FastDiv((uint32_t)g.c4); g.div_pairs = FastDiv((uint32_t)g.pairs_x); g.div_strips = FastDiv((uint32_t)g.strips_y);
+        if (g.total_threads < 0x7fffffffll) {
+            const int64_t blocks = (g.total_threads + kThreads - 1) / kThreads;
+            upfirdn2d_nhwc_kernel<4, 4><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
+            rc = SR_OK;
+        }
     }
     if (rc == SR_ERR_UNSUPPORTED) {
         GenericGeom g;

@@ -22,7 +22,8 @@ from torch.nn import functional as F
 
 from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
 
-_CONFIG = {"conv_backend": "cudnn"}
+_CONFIG = {"conv_backend": "cudnn", "double_backward": False}
+HAVE_TCGEN05 = True
 
 
 def set_conv_backend(name):
@@ -32,6 +33,22 @@ def set_conv_backend(name):
 
 def get_conv_backend():
     return _CONFIG["conv_backend"]
+
+
+class double_backward:
+    """Context manager for regulariser iterations (R1 / path length, reference train.py:110-134): inside it the
+    StyledConv blocks use the composed-op path whose backward is itself differentiable."""
+
+    def __enter__(self):
+        self._old = _CONFIG["double_backward"]
+        _CONFIG["double_backward"] = True
+
+    def __exit__(self, *a):
+        _CONFIG["double_backward"] = self._old
+
+
+def double_backward_requested():
+    return _CONFIG["double_backward"]
 
 
 def make_kernel(k):                                   # reference layers.py:7-12
@@ -197,6 +214,16 @@ class ModulatedConv2d(nn.Module):                     # reference layers.py:259-
     def forward(self, input, style):
         batch, in_channel = input.shape[:2]
         s, d = self.style_scales(style)
+        if self.kernel_size == 1 and not self.upsample and not self.downsample:
+            # ToRGB: fold the style into B x [Cout, Cin] weights (a few KB) and read the activation once
+            wb = (self.weight[0, :, :, 0, 0] * self.scale).unsqueeze(0) * s.unsqueeze(1)
+            if d is not None:
+                wb = wb * d.unsqueeze(2)
+            h, w = input.shape[2:]
+            if input.is_contiguous(memory_format=torch.channels_last) and not input.is_contiguous():
+                out = torch.matmul(input.permute(0, 2, 3, 1).reshape(batch, h * w, in_channel), wb.transpose(1, 2))
+                return out.view(batch, h, w, self.out_channel).permute(0, 3, 1, 2)
+            return torch.bmm(wb, input.reshape(batch, in_channel, h * w)).view(batch, self.out_channel, h, w)
         out = self.contract(input * s.view(batch, in_channel, 1, 1))
         if d is not None:
             out = out * d.view(batch, self.out_channel, 1, 1)

@@ -11,6 +11,7 @@ import numpy as np
 import torch
 from torch import nn
 
+from . import fused, layers
 from .layers import (ConstantInput, ConvLayer, EqualLinear, ModulatedConv2d, NoiseInjection, PixelNorm, ResBlock,
                      Upsample)
 from .op import FusedLeakyReLU, rasterize
@@ -27,6 +28,9 @@ class StyledConv(nn.Module):                          # reference model.py:11-32
         self.activate = FusedLeakyReLU(out_channel)
 
     def forward(self, input, style, noise=None):
+        if (layers.get_conv_backend() == "tcgen05" and fused.supported(self.conv, input)
+                and not (torch.is_grad_enabled() and layers.double_backward_requested())):
+            return fused.styled_conv(self.conv, self.noise, self.activate, input, style, noise)
         out = self.conv(input, style)
         out = self.noise(out, noise=noise)
         return self.activate(out)

@@ -35,16 +35,35 @@ def upfirdn2d_raw(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad
     return out
 
 
+def _is_channels_last(t):
+    return t.dim() == 4 and t.shape[1] > 1 and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous()
+
+
+def _planes_or_nhwc(t, h, w):
+    """[N,C,h,w] -> ([major,h,w,minor] view for the kernel, channels_last?).  A channels_last tensor IS an
+    [N,h,w,C] array in memory, which the kernel takes with major = N, minor = C (no layout copy)."""
+    if _is_channels_last(t) and t.shape[1] % 4 == 0:
+        return t.permute(0, 2, 3, 1), True
+    return t.reshape(-1, h, w, 1), False
+
+
+def _restore(out4, n, c, cl):
+    """kernel output [major,oh,ow,minor] -> logical [N,C,oh,ow] (channels_last strides if the input had them)."""
+    if cl:
+        return out4.permute(0, 3, 1, 2)
+    return out4.view(n, c, out4.shape[1], out4.shape[2])
+
+
 class UpFirDn2dBackward(Function):                  # reference op/upfirdn2d.py:19-85
     @staticmethod
     def forward(ctx, grad_output, kernel, grad_kernel, up, down, pad, g_pad, in_size, out_size):
         up_x, up_y = up
         down_x, down_y = down
         g_pad_x0, g_pad_x1, g_pad_y0, g_pad_y1 = g_pad
-        grad_output = grad_output.reshape(-1, out_size[0], out_size[1], 1)
+        grad_output, cl = _planes_or_nhwc(grad_output, out_size[0], out_size[1])
         grad_input = upfirdn2d_raw(grad_output, grad_kernel, down_x, down_y, up_x, up_y,
                                    g_pad_x0, g_pad_x1, g_pad_y0, g_pad_y1)
-        grad_input = grad_input.view(in_size[0], in_size[1], in_size[2], in_size[3])
+        grad_input = _restore(grad_input, in_size[0], in_size[1], cl)
         ctx.save_for_backward(kernel)
         ctx.up, ctx.down, ctx.pad = up, down, pad
         ctx.in_size, ctx.out_size = in_size, out_size
@@ -53,9 +72,9 @@ class UpFirDn2dBackward(Function):                  # reference op/upfirdn2d.py:
     @staticmethod
     def backward(ctx, gradgrad_input):
         kernel, = ctx.saved_tensors
-        gradgrad_input = gradgrad_input.reshape(-1, ctx.in_size[2], ctx.in_size[3], 1)
+        gradgrad_input, cl = _planes_or_nhwc(gradgrad_input, ctx.in_size[2], ctx.in_size[3])
         gradgrad_out = upfirdn2d_raw(gradgrad_input, kernel, ctx.up[0], ctx.up[1], ctx.down[0], ctx.down[1], *ctx.pad)
-        gradgrad_out = gradgrad_out.view(ctx.in_size[0], ctx.in_size[1], ctx.out_size[0], ctx.out_size[1])
+        gradgrad_out = _restore(gradgrad_out, ctx.in_size[0], ctx.in_size[1], cl)
         return gradgrad_out, None, None, None, None, None, None, None, None
 
 
@@ -68,7 +87,7 @@ class UpFirDn2d(Function):                          # reference op/upfirdn2d.py:
         kernel_h, kernel_w = kernel.shape
         batch, channel, in_h, in_w = input.shape
         ctx.in_size = input.shape
-        input = input.reshape(-1, in_h, in_w, 1)
+        input, cl = _planes_or_nhwc(input, in_h, in_w)
         ctx.save_for_backward(kernel, torch.flip(kernel, [0, 1]))
         out_h = (in_h * up_y + pad_y0 + pad_y1 - kernel_h) // down_y + 1
         out_w = (in_w * up_x + pad_x0 + pad_x1 - kernel_w) // down_x + 1
@@ -77,7 +96,7 @@ class UpFirDn2d(Function):                          # reference op/upfirdn2d.py:
         ctx.g_pad = (kernel_w - pad_x0 - 1, in_w * up_x - out_w * down_x + pad_x0 - up_x + 1,
                      kernel_h - pad_y0 - 1, in_h * up_y - out_h * down_y + pad_y0 - up_y + 1)
         out = upfirdn2d_raw(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)
-        return out.view(-1, channel, out_h, out_w)
+        return _restore(out, batch, channel, cl)
 
     @staticmethod
     def backward(ctx, grad_output):

@@ -139,6 +139,24 @@ def test_upfirdn2d_vs_oracle(op, case):
     torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("shape,pad", [((2, 8, 9, 9), (1, 1)), ((1, 128, 33, 33), (1, 1)), ((3, 12, 16, 16), (2, 2)),
+                                       ((2, 64, 5, 7), (2, 1)), ((1, 4, 64, 64), (2, 2))])
+def test_upfirdn2d_channels_last(op, shape, pad):
+    """channels_last tensors take the NHWC kernel (no layout copy) and keep their memory format, fwd and bwd."""
+    x = seeded(shape, 30)
+    k = seeded((4, 4), 31)
+    want = O.upfirdn2d(x, k, 1, 1, pad)
+    xc = cuda(x).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    got = op.upfirdn2d(xc, cuda(k), pad=pad)
+    assert got.is_contiguous(memory_format=torch.channels_last)
+    torch.testing.assert_close(got.detach().cpu(), want, rtol=1e-5, atol=1e-5)
+    gy = seeded(want.shape, 32)
+    gx, = torch.autograd.grad(got, xc, cuda(gy).contiguous(memory_format=torch.channels_last))
+    xr = x.clone().requires_grad_(True)
+    gx_want, = torch.autograd.grad(T.upfirdn2d(xr, k, 1, 1, pad), xr, gy)
+    torch.testing.assert_close(gx.cpu(), gx_want, rtol=1e-5, atol=1e-5)
+
+
 def test_upfirdn2d_minor_and_mixed_factors(op):
     """The pybind-level entry with minor > 1 and different x / y factors (reference op/upfirdn2d.cpp:24-26)."""
     x = seeded((3, 6, 7, 4), 22)
