@@ -182,6 +182,31 @@ int sr_modulate_tf32(float *xs, const float *x, const float *style, int64_t batc
 int sr_conv_weight_prep_tf32(float *dst, const float *w, float scale, int64_t cout, int64_t cin, int kh, int kw,
                              int transpose, void *stream);
 
+/* ------------------------------------------------------------------ fused passes of a StyledConv block (NHWC) ---
+ * 4x4 FIR (up = down = 1, same pad on both axes) over an NHWC tensor with the StyledConv tail fused in
+ * (reference layers.py:310 Blur -> model.py:28-31 NoiseInjection + FusedLeakyReLU):
+ *   out[n,y,x,c] = lrelu( fir(x)[n,y,x,c] + noise_weight[0]*noise[n,y,x] + bias[c] ) * gain
+ * noise planar [*, out_h, out_w] with batch stride noise_batch_stride (0 = broadcast), may be NULL. */
+int sr_blur_nhwc_styled_f32(float *out, const float *x, const float *taps, int64_t batch, int64_t in_h, int64_t in_w,
+                            int64_t channels, int pad0, int pad1, const float *noise, int64_t noise_batch_stride,
+                            const float *noise_weight, const float *bias, float alpha, float gain, void *stream);
+
+/* Backward prologue of a StyledConv block, one pass over (gy, y) [batch, pixels, channels]:
+ *   g_pre = gain * (y > 0 ? gy : alpha*gy)                       (reference op/fused_act.py:27-31)
+ *   ga    = d ? tf32_round(g_pre * d[n,c]) : g_pre               (operand of the dgrad / wgrad GEMMs)
+ *   g_bias[c]   = sum g_pre            g_noise_w[0] = sum g_pre * noise[n,p]
+ *   e[n,c]      = sum_p g_pre * (t - noise_w*noise - bias[c]),  t = pre-activation recovered from y  (NULL: skip)
+ * g_bias / g_noise_w / e are zeroed by the call. channels = 4k with k | 256. */
+int sr_styled_bwd_prologue_f32(float *ga, float *g_bias, float *g_noise_w, float *e, const float *gy, const float *y,
+                               const float *noise, int64_t noise_batch_stride, const float *noise_weight,
+                               const float *bias, const float *d, int64_t batch, int64_t pixels, int64_t channels,
+                               float alpha, float gain, void *stream);
+
+/* out[n,p,c] = a[n,p,c] * scale[n,c] (optionally rounded to tf32), dot[n,c] = sum_p a[n,p,c] * other[n,p,c];
+ * out or dot may be NULL; dot is zeroed by the call. */
+int sr_scale_dot_nhwc_f32(float *out, float *dot, const float *a, const float *other, const float *scale,
+                          int64_t batch, int64_t pixels, int64_t channels, int round_out_tf32, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,214 @@
+// Fused elementwise + reduction passes around the tensor-core GEMMs of a StyledConv block (NHWC, float32).
+//
+// They replace the chains of separate full-tensor passes the reference runs in PyTorch around its grouped
+// conv (reference model.py:26-32, layers.py:296-332, op/fused_act.py:27-38): every kernel here reads each
+// activation-sized tensor exactly once and produces, in the same pass, both the tensor the next GEMM
+// consumes (already scaled and rounded to tf32) and the per-channel / per-(sample,channel) reductions the
+// parameter gradients need.  HBM-bound: 128-bit accesses, consecutive lanes = consecutive channel quads
+// (a warp covers one contiguous 512-byte run), reductions in registers -> shared memory -> one global
+// atomic per (CTA, channel).
+#include "common.cuh"
+
+namespace sr {
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float round_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ void f4_fma(float4 &acc, float4 a, float4 b) {
+    acc.x = fmaf(a.x, b.x, acc.x); acc.y = fmaf(a.y, b.y, acc.y); acc.z = fmaf(a.z, b.z, acc.z); acc.w = fmaf(a.w, b.w, acc.w);
+}
+__device__ __forceinline__ void f4_add(float4 &acc, float4 a) { acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w; }
+
+// Block-level reduction over the `lanes_p` pixel lanes of a CTA (threads with equal channel quad), then one
+// atomicAdd per channel.  smem: kThreads float4.
+__device__ __forceinline__ void block_reduce_quads(float4 v, float4 *smem, int c4, int pl, int C4, int lanes_p, float *dst)
+{
+    __syncthreads();
+    smem[pl * C4 + c4] = v;
+    __syncthreads();
+    if (pl == 0) {
+        float4 s = smem[c4];
+        for (int i = 1; i < lanes_p; ++i) f4_add(s, smem[i * C4 + c4]);
+        atomicAdd(dst + 4 * c4 + 0, s.x); atomicAdd(dst + 4 * c4 + 1, s.y);
+        atomicAdd(dst + 4 * c4 + 2, s.z); atomicAdd(dst + 4 * c4 + 3, s.w);
+    }
+}
+
+struct PrologueParams {
+    float *ga;                    // out: tf32(g_pre * d[b,c]) (or g_pre when d == nullptr)
+    float *g_bias;                // [C]      += sum g_pre
+    float *g_noise_w;             // [1]      += sum g_pre * noise
+    float *e;                     // [B,C]    += sum g_pre * (pre_activation - noise_w*noise - bias)   (nullptr: skip)
+    const float *gy, *y, *noise, *noise_w, *bias, *d;
+    long long noise_bstride;
+    int pixels, C4, chunks_per_image, pix_per_chunk;
+    float alpha, gain;
+};
+
+// grid.x = B * chunks_per_image
+__global__ void __launch_bounds__(kThreads)
+styled_bwd_prologue_kernel(const PrologueParams p)
+{
+    __shared__ float4 s_red[kThreads];
+    __shared__ float s_nw[kThreads / 32];
+    const int C4 = p.C4, lanes_p = kThreads / C4;
+    const int c4 = threadIdx.x % C4, pl = threadIdx.x / C4;
+    const int b = blockIdx.x / p.chunks_per_image, chunk = blockIdx.x % p.chunks_per_image;
+    const int p0 = chunk * p.pix_per_chunk, p1 = min(p.pixels, p0 + p.pix_per_chunk);
+    const float4 *gy = reinterpret_cast<const float4 *>(p.gy) + (long long)b * p.pixels * C4 + c4;
+    const float4 *y = reinterpret_cast<const float4 *>(p.y) + (long long)b * p.pixels * C4 + c4;
+    float4 *ga = reinterpret_cast<float4 *>(p.ga) + (long long)b * p.pixels * C4 + c4;
+    const float *nz = p.noise ? p.noise + (long long)b * p.noise_bstride : nullptr;
+    const float nw = p.noise ? __ldg(p.noise_w) : 0.0f;
+    const float4 bias = p.bias ? __ldg(reinterpret_cast<const float4 *>(p.bias) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 dd = p.d ? __ldg(reinterpret_cast<const float4 *>(p.d) + (long long)b * C4 + c4) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float pos = p.gain, neg = p.gain * p.alpha;
+    const float ipos = 1.0f / p.gain, ineg = 1.0f / (p.gain * p.alpha);
+    float4 a_bias = make_float4(0.f, 0.f, 0.f, 0.f), a_e = a_bias;
+    float a_nw = 0.0f;
+    for (int px = p0 + pl; px < p1; px += lanes_p) {
+        const float4 g = ld_stream4(reinterpret_cast<const float *>(gy + (long long)px * C4));
+        const float4 yy = __ldg(y + (long long)px * C4);
+        const float n = nz ? __ldg(nz + px) : 0.0f;
+        float4 gp, u;
+        // reference op/fused_bias_act_kernel.cu:31: (ref > 0 ? g : g*alpha) * scale
+        gp.x = ((yy.x > 0.f) ? g.x : g.x * p.alpha) * p.gain; gp.y = ((yy.y > 0.f) ? g.y : g.y * p.alpha) * p.gain;
+        gp.z = ((yy.z > 0.f) ? g.z : g.z * p.alpha) * p.gain; gp.w = ((yy.w > 0.f) ? g.w : g.w * p.alpha) * p.gain;
+        f4_add(a_bias, gp);
+        a_nw += ((gp.x + gp.y) + (gp.z + gp.w)) * n;
+        if (p.e) {
+            // the pre-activation is recoverable from y (gain, alpha > 0): t = y / gain or y / (gain * alpha)
+            u.x = yy.x * ((yy.x > 0.f) ? ipos : ineg); u.y = yy.y * ((yy.y > 0.f) ? ipos : ineg);
+            u.z = yy.z * ((yy.z > 0.f) ? ipos : ineg); u.w = yy.w * ((yy.w > 0.f) ? ipos : ineg);
+            const float sh = nw * n;
+            u.x -= sh + bias.x; u.y -= sh + bias.y; u.z -= sh + bias.z; u.w -= sh + bias.w;
+            f4_fma(a_e, gp, u);
+        }
+        float4 o = f4_mul(gp, dd);
+        if (p.d) o = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
+        ga[(long long)px * C4] = o;
+    }
+    (void)pos; (void)neg;
+    block_reduce_quads(a_bias, s_red, c4, pl, C4, lanes_p, p.g_bias);
+    if (p.e) block_reduce_quads(a_e, s_red, c4, pl, C4, lanes_p, p.e + (long long)b * C4 * 4);
+    if (p.noise) {
+        a_nw = warp_sum(a_nw);
+        if ((threadIdx.x & 31) == 0) s_nw[threadIdx.x >> 5] = a_nw;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.f;
+            for (int i = 0; i < kThreads / 32; ++i) s += s_nw[i];
+            atomicAdd(p.g_noise_w, s);
+        }
+    }
+}
+
+struct ScaleDotParams {
+    float *out;                   // a * scale[b,c]  (rounded to tf32 when round_out)
+    float *dot;                   // [B,C] += sum_p a * other
+    const float *a, *other, *scale;
+    int pixels, C4, chunks_per_image, pix_per_chunk, round_out;
+};
+
+__global__ void __launch_bounds__(kThreads)
+scale_dot_kernel(const ScaleDotParams p)
+{
+    __shared__ float4 s_red[kThreads];
+    const int C4 = p.C4, lanes_p = kThreads / C4;
+    const int c4 = threadIdx.x % C4, pl = threadIdx.x / C4;
+    const int b = blockIdx.x / p.chunks_per_image, chunk = blockIdx.x % p.chunks_per_image;
+    const int p0 = chunk * p.pix_per_chunk, p1 = min(p.pixels, p0 + p.pix_per_chunk);
+    const long long base = (long long)b * p.pixels * C4 + c4;
+    const float4 *a = reinterpret_cast<const float4 *>(p.a) + base;
+    const float4 *o = p.other ? reinterpret_cast<const float4 *>(p.other) + base : nullptr;
+    float4 *out = p.out ? reinterpret_cast<float4 *>(p.out) + base : nullptr;
+    const float4 sc = p.scale ? __ldg(reinterpret_cast<const float4 *>(p.scale) + (long long)b * C4 + c4)
+                              : make_float4(1.f, 1.f, 1.f, 1.f);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int px = p0 + pl; px < p1; px += lanes_p) {
+        const float4 av = ld_stream4(reinterpret_cast<const float *>(a + (long long)px * C4));
+        if (o) f4_fma(acc, av, ld_stream4(reinterpret_cast<const float *>(o + (long long)px * C4)));
+        if (out) {
+            float4 r = f4_mul(av, sc);
+            if (p.round_out) r = make_float4(round_tf32(r.x), round_tf32(r.y), round_tf32(r.z), round_tf32(r.w));
+            out[(long long)px * C4] = r;
+        }
+    }
+    if (p.dot) block_reduce_quads(acc, s_red, c4, pl, C4, lanes_p, p.dot + (long long)b * C4 * 4);
+}
+
+int pick_chunks(int64_t batch, int64_t pixels, int C4, int *pix_per_chunk) {
+    // about 4 CTAs per SM in flight, at least 64 pixels per pixel lane to amortise the final reduction
+    const int lanes_p = kThreads / C4;
+    int64_t want_ctas = (int64_t)kNumSMs * 8;
+    int64_t chunks = (want_ctas + batch - 1) / batch;
+    int64_t min_pix = (int64_t)lanes_p * 32;
+    int64_t max_chunks = (pixels + min_pix - 1) / min_pix;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    *pix_per_chunk = (int)((pixels + chunks - 1) / chunks);
+    return (int)((pixels + *pix_per_chunk - 1) / *pix_per_chunk);
+}
+
+bool ok_channels(int64_t c) { return c % 4 == 0 && c / 4 <= kThreads && kThreads % (c / 4) == 0; }
+bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+}  // namespace sr
+
+using namespace sr;
+
+extern "C" int sr_styled_bwd_prologue_f32(float *ga, float *g_bias, float *g_noise_w, float *e, const float *gy,
+                                          const float *y, const float *noise, int64_t noise_batch_stride,
+                                          const float *noise_weight, const float *bias, const float *d, int64_t batch,
+                                          int64_t pixels, int64_t channels, float alpha, float gain, void *stream)
+{
+    SR_REQUIRE(ga && g_bias && gy && y, "styled_bwd_prologue: null pointer");
+    SR_REQUIRE(ok_channels(channels), "styled_bwd_prologue: channels must be 4*k with k dividing 256 (got %lld)", (long long)channels);
+    SR_REQUIRE(al16(ga) && al16(gy) && al16(y) && (!bias || al16(bias)) && (!d || al16(d)), "styled_bwd_prologue: 16-byte alignment");
+    SR_REQUIRE(!noise || (noise_weight && g_noise_w), "styled_bwd_prologue: noise needs its weight and gradient slot");
+    SR_REQUIRE(alpha > 0 && gain > 0, "styled_bwd_prologue: alpha, gain must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t er = cudaMemsetAsync(g_bias, 0, sizeof(float) * (size_t)channels, st);
+    if (er == cudaSuccess && g_noise_w) er = cudaMemsetAsync(g_noise_w, 0, sizeof(float), st);
+    if (er == cudaSuccess && e) er = cudaMemsetAsync(e, 0, sizeof(float) * (size_t)(batch * channels), st);
+    if (er != cudaSuccess) { set_error("styled_bwd_prologue: memset: %s", cudaGetErrorString(er)); return (int)er; }
+    if (batch == 0 || pixels == 0) return SR_OK;
+    PrologueParams p;
+    p.ga = ga; p.g_bias = g_bias; p.g_noise_w = g_noise_w; p.e = e; p.gy = gy; p.y = y;
+    p.noise = noise; p.noise_w = noise_weight; p.bias = bias; p.d = d; p.noise_bstride = noise_batch_stride;
+    p.pixels = (int)pixels; p.C4 = (int)(channels / 4);
+    p.chunks_per_image = pick_chunks(batch, pixels, p.C4, &p.pix_per_chunk);
+    p.alpha = alpha; p.gain = gain;
+    styled_bwd_prologue_kernel<<<(unsigned)(batch * p.chunks_per_image), kThreads, 0, st>>>(p);
+    count_launch();
+    return check_launch("sr_styled_bwd_prologue_f32");
+}
+
+extern "C" int sr_scale_dot_nhwc_f32(float *out, float *dot, const float *a, const float *other, const float *scale,
+                                     int64_t batch, int64_t pixels, int64_t channels, int round_out_tf32, void *stream)
+{
+    SR_REQUIRE(a && (out || dot), "scale_dot: nothing to do");
+    SR_REQUIRE(!dot || other, "scale_dot: dot needs the second tensor");
+    SR_REQUIRE(ok_channels(channels), "scale_dot: channels must be 4*k with k dividing 256 (got %lld)", (long long)channels);
+    SR_REQUIRE(al16(a) && (!out || al16(out)) && (!other || al16(other)) && (!scale || al16(scale)), "scale_dot: 16-byte alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dot) {
+        cudaError_t er = cudaMemsetAsync(dot, 0, sizeof(float) * (size_t)(batch * channels), st);
+        if (er != cudaSuccess) { set_error("scale_dot: memset: %s", cudaGetErrorString(er)); return (int)er; }
+    }
+    if (batch == 0 || pixels == 0) return SR_OK;
+    ScaleDotParams p;
+    p.out = out; p.dot = dot; p.a = a; p.other = dot ? other : nullptr; p.scale = scale;
+    p.pixels = (int)pixels; p.C4 = (int)(channels / 4); p.round_out = round_out_tf32;
+    p.chunks_per_image = pick_chunks(batch, pixels, p.C4, &p.pix_per_chunk);
+    scale_dot_kernel<<<(unsigned)(batch * p.chunks_per_image), kThreads, 0, st>>>(p);
+    count_launch();
+    return check_launch("sr_scale_dot_nhwc_f32");
+}

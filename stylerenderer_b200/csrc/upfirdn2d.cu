@@ -174,9 +174,13 @@ struct NhwcGeom {
     int64_t major, total_threads;
     int in_h, in_w, out_h, out_w, c4, pad_x0, pad_y0, strips_y, pairs_x, rows_per_strip;
     FastDiv div_c4, div_pairs, div_strips;
+    // STYLED epilogue: y = lrelu(acc + noise_weight * noise[n, oy, ox] + bias[c]) * gain
+    const float *noise, *noise_weight, *bias;
+    long long noise_bstride;
+    float alpha, gain;
 };
 
-template <int KH, int KW>
+template <int KH, int KW, bool STYLED>
 __global__ void __launch_bounds__(kThreads)
 upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, const float *__restrict__ taps,
                       const NhwcGeom g)
@@ -201,6 +205,14 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
     const float4 *xin = reinterpret_cast<const float4 *>(x) + (int64_t)n * g.in_h * g.in_w * g.c4 + c;
     float4 *yout = reinterpret_cast<float4 *>(out) + (int64_t)n * g.out_h * g.out_w * g.c4 + c;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    float nw = 0.0f;
+    float4 bias4 = zero;
+    const float *nz = nullptr;
+    if (STYLED) {
+        if (g.noise) { nw = __ldg(g.noise_weight); nz = g.noise + (int64_t)n * g.noise_bstride; }
+        if (g.bias) bias4 = __ldg(reinterpret_cast<const float4 *>(g.bias) + c);
+    }
 
     float4 win[KH][KW + 1];
     auto load_row = [&](float4 (&row)[KW + 1], int iy) {
@@ -228,6 +240,17 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
                     acc[j].x = fmaf(v.x, k, acc[j].x); acc[j].y = fmaf(v.y, k, acc[j].y);
                     acc[j].z = fmaf(v.z, k, acc[j].z); acc[j].w = fmaf(v.w, k, acc[j].w);
                 }
+        if (STYLED) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float add = (nz && ox0 + j < g.out_w) ? nw * __ldg(nz + (int64_t)oy * g.out_w + ox0 + j) : 0.0f;
+                float t;
+                t = acc[j].x + add + bias4.x; acc[j].x = ((t > 0.f) ? t : t * g.alpha) * g.gain;
+                t = acc[j].y + add + bias4.y; acc[j].y = ((t > 0.f) ? t : t * g.alpha) * g.gain;
+                t = acc[j].z + add + bias4.z; acc[j].z = ((t > 0.f) ? t : t * g.alpha) * g.gain;
+                t = acc[j].w + add + bias4.w; acc[j].w = ((t > 0.f) ? t : t * g.alpha) * g.gain;
+            }
+        }
         float4 *dst = yout + ((int64_t)oy * g.out_w + ox0) * g.c4;
         dst[0] = acc[0];
         if (ox0 + 1 < g.out_w) dst[g.c4] = acc[1];
@@ -321,10 +344,51 @@ int launch_tile(float *out, const float *x, const float *taps, int64_t major, in
     return SR_OK;
 }
 
+int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, int in_h, int in_w, int oh, int ow,
+                int64_t minor, int pad_x0, int pad_y0, bool styled, const float *noise, long long noise_bstride,
+                const float *noise_weight, const float *bias, float alpha, float gain, cudaStream_t st)
+{
+    NhwcGeom g;
+    g.major = major; g.in_h = in_h; g.in_w = in_w; g.out_h = oh; g.out_w = ow;
+    g.c4 = (int)(minor / 4); g.pad_x0 = pad_x0; g.pad_y0 = pad_y0;
+    g.rows_per_strip = oh >= 64 ? 16 : (oh >= 16 ? 8 : 4);
+    g.strips_y = (oh + g.rows_per_strip - 1) / g.rows_per_strip;
+    g.pairs_x = (ow + 1) / 2;
+    g.total_threads = major * g.strips_y * g.pairs_x * g.c4;
+    g.div_c4 = FastDiv((uint32_t)g.c4); g.div_pairs = FastDiv((uint32_t)g.pairs_x); g.div_strips = FastDiv((uint32_t)g.strips_y);
+    g.noise = noise; g.noise_weight = noise_weight; g.bias = bias; g.noise_bstride = noise_bstride;
+    g.alpha = alpha; g.gain = gain;
+    if (g.total_threads >= 0x7fffffffll) return SR_ERR_UNSUPPORTED;
+    const int64_t blocks = (g.total_threads + kThreads - 1) / kThreads;
+    if (styled) upfirdn2d_nhwc_kernel<4, 4, true><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
+    else upfirdn2d_nhwc_kernel<4, 4, false><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
+    return SR_OK;
+}
+
 }  // namespace
 }  // namespace sr
 
 using namespace sr;
+
+extern "C" int sr_blur_nhwc_styled_f32(float *out, const float *x, const float *taps, int64_t batch, int64_t in_h,
+                                       int64_t in_w, int64_t channels, int pad0, int pad1, const float *noise,
+                                       int64_t noise_batch_stride, const float *noise_weight, const float *bias,
+                                       float alpha, float gain, void *stream)
+{
+    SR_REQUIRE(out && x && taps, "blur_nhwc_styled: null pointer");
+    SR_REQUIRE(channels >= 4 && channels % 4 == 0, "blur_nhwc_styled: channels must be a multiple of 4");
+    SR_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(x)) & 15u) == 0 &&
+               (!bias || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0), "blur_nhwc_styled: 16-byte alignment");
+    SR_REQUIRE(!noise || noise_weight, "blur_nhwc_styled: noise needs noise_weight");
+    const int64_t oh = in_h + pad0 + pad1 - 4 + 1, ow = in_w + pad0 + pad1 - 4 + 1;
+    SR_REQUIRE(oh >= 1 && ow >= 1, "blur_nhwc_styled: FIR larger than the padded input");
+    if (batch == 0) return SR_OK;
+    int rc = launch_nhwc(out, x, taps, batch, (int)in_h, (int)in_w, (int)oh, (int)ow, channels, pad0, pad0, true, noise,
+                         noise_batch_stride, noise_weight, bias, alpha, gain, (cudaStream_t)stream);
+    if (rc != SR_OK) { set_error("blur_nhwc_styled: problem too large"); return rc; }
+    count_launch();
+    return check_launch("sr_blur_nhwc_styled_f32");
+}
 
 extern "C" int sr_upfirdn2d_f32(float *out, const float *x, const float *taps,
                                 int64_t major, int64_t in_h, int64_t in_w, int64_t minor,
@@ -361,19 +425,8 @@ extern "C" int sr_upfirdn2d_f32(float *out, const float *x, const float *taps,
     }
     if (rc == SR_ERR_UNSUPPORTED && minor >= 4 && minor % 4 == 0 && up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1 &&
         kernel_h == 4 && kernel_w == 4 && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(x)) & 15u) == 0) {
-        NhwcGeom g;
-        g.major = major; g.in_h = (int)in_h; g.in_w = (int)in_w; g.out_h = (int)oh; g.out_w = (int)ow;
-        g.c4 = (int)(minor / 4); g.pad_x0 = pad_x0; g.pad_y0 = pad_y0;
-        g.rows_per_strip = oh >= 64 ? 16 : (oh >= 16 ? 8 : 4);
-        g.strips_y = (int)((oh + g.rows_per_strip - 1) / g.rows_per_strip);
-        g.pairs_x = (int)((ow + 1) / 2);
-        g.total_threads = major * g.strips_y * g.pairs_x * g.c4;
-        g.div_c4 = FastDiv((uint32_t)g.c4); g.div_pairs = FastDiv((uint32_t)g.pairs_x); g.div_strips = FastDiv((uint32_t)g.strips_y);
-        if (g.total_threads < 0x7fffffffll) {
-            const int64_t blocks = (g.total_threads + kThreads - 1) / kThreads;
-            upfirdn2d_nhwc_kernel<4, 4><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
-            rc = SR_OK;
-        }
+        rc = launch_nhwc(out, x, taps, major, (int)in_h, (int)in_w, (int)oh, (int)ow, minor, pad_x0, pad_y0, false,
+                         nullptr, 0, nullptr, nullptr, 0.f, 1.f, st);
     }
     if (rc == SR_ERR_UNSUPPORTED) {
         GenericGeom g;

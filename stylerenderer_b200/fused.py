@@ -12,7 +12,6 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from . import tc_conv as tc
-from .op.fused_act import _lrelu_backward, fused_bias_act
 from .op.upfirdn2d import upfirdn2d_raw
 
 
@@ -47,9 +46,8 @@ class StyledConvTC(Function):
                        noise=noise.reshape(-1, h, w).contiguous(), noise_weight=noise_weight)
         else:
             t = tc.conv_transpose3x3_s2(xs, wk, rowscale=d)            # [b, 2h+1, 2w+1, cout] = d * conv_T(xs)
-            tb = upfirdn2d_raw(t, blur_taps, 1, 1, 1, 1, 1, 1, 1, 1)   # NHWC FIR, pad (1,1) -> [b, 2h, 2w, cout]
-            pre = from_nhwc(tb) + noise_weight * noise                 # channels_last logical NCHW
-            y = to_nhwc(fused_bias_act(pre, act_bias, None, 3, 0, alpha, gain))
+            # NHWC FIR (pad 1,1) with the noise + bias + leaky-ReLU tail fused -> [b, 2h, 2w, cout]
+            y = tc.blur_styled(t, blur_taps, (1, 1), noise, noise_weight, act_bias, alpha, gain)
         ctx.save_for_backward(x_nhwc, xs, y, t, weight, s, d, noise, noise_weight, act_bias, blur_taps)
         ctx.cfg = (scale, upsample, alpha, gain)
         return from_nhwc(y)
@@ -63,27 +61,20 @@ class StyledConvTC(Function):
         cout = y.shape[3]
         oh, ow = y.shape[1], y.shape[2]
         gy = to_nhwc(gy)
-        # activation backward with the bias gradient fused (channel-fastest layout: step_b = 1)
-        g_pre, g_bias = _lrelu_backward(from_nhwc(gy), from_nhwc(y), alpha, gain, True)
-        g_pre = to_nhwc(g_pre)                                         # [b, oh, ow, cout]
-        nz = noise.reshape(-1, oh, ow, 1)
-        g_noise_w = (g_pre * nz).sum().reshape(1)
         if not upsample:
-            # d * acc = pre-activation - noise - bias, and the pre-activation is recoverable from y
-            u = torch.where(y > 0, y / gain, y / (gain * alpha))
-            tconv = u - noise_weight * nz - act_bias
-            g_d = (g_pre * tconv).sum((1, 2)) / d
-            ga = tc.modulate(g_pre, d)                                 # tf32(g * d[b,co]): A operand of dgrad / wgrad
+            # one pass: activation backward, bias / noise-weight gradients, e = sum g_pre * (d * acc), ga = tf32(g_pre * d)
+            ga, g_bias, g_noise_w, e = tc.bwd_prologue(gy, y, noise, noise_weight, act_bias, d, alpha, gain, True)
             dxs = tc.conv3x3(ga, tc.weight_prep(weight[0], scale, 1))
             dwk = tc.wgrad3x3(ga, xs)
         else:
+            g_pre, g_bias, g_noise_w, _ = tc.bwd_prologue(gy, y, noise, noise_weight, act_bias, None, alpha, gain, False)
             gt = upfirdn2d_raw(g_pre, torch.flip(blur_taps, [0, 1]), 1, 1, 1, 1, 2, 2, 2, 2)   # transpose of the FIR
-            g_d = (gt * t).sum((1, 2)) / d                             # t = d * acc, dL/dd = sum gt * acc
-            ga = tc.modulate(gt, d)
+            ga, e = tc.scale_dot(gt, t, d, True)                       # ga = tf32(gt * d), e = sum gt * t  (t = d * acc)
             dxs = tc.conv3x3_s2_gather(ga, tc.weight_prep(weight[0], scale, 2), (h, w))
             dwk = tc.wgrad_transpose3x3_s2(ga, xs)
-        g_x = from_nhwc(dxs * s.view(b, 1, 1, cin))
-        g_s = (dxs * x_nhwc).sum((1, 2))
+        g_d = e / d                                                     # dL/dd = sum g * acc = e / d
+        g_x, g_s = tc.scale_dot(dxs, x_nhwc, s, False)                 # dx = dxs * s, ds = sum_p dxs * x
+        g_x = from_nhwc(g_x)
         g_w = (dwk.view(cout, 3, 3, cin).permute(0, 3, 1, 2) * scale).unsqueeze(0)
         return g_x, g_w, g_s, g_d, None, g_noise_w, g_bias, None, None, None, None, None
 

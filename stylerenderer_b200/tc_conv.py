@@ -181,3 +181,58 @@ def wgrad_transpose3x3_s2(g, x):
     """Weight gradient of the stride-2 transposed conv: dw[co, ky*3+kx, ci] = sum g[n,2m+ky,2n+kx,co] * x[n,m,n,ci]."""
     taps = [(ky, kx, 0, 0, ky * 3 + kx) for ky in range(3) for kx in range(3)]
     return wgrad(g, x, taps, (x.shape[1], x.shape[2]), g_stride=2)
+
+
+def _noise_args(noise, oh, ow):
+    if noise is None:
+        return None, 0
+    nz = noise.reshape(-1, oh, ow).contiguous()
+    return nz, (0 if nz.shape[0] == 1 else oh * ow)
+
+
+def blur_styled(t, taps, pad, noise, noise_weight, bias, alpha, gain):
+    """NHWC 4x4 FIR + noise + bias + leaky-ReLU*gain in one pass: [B,IH,IW,C] -> [B,OH,OW,C]."""
+    _check_nhwc(t, "blur_styled")
+    b, ih, iw, c = t.shape
+    oh, ow = ih + pad[0] + pad[1] - 3, iw + pad[0] + pad[1] - 3
+    out = torch.empty(b, oh, ow, c, dtype=torch.float32, device=t.device)
+    nz, nbs = _noise_args(noise, oh, ow)
+    with torch.cuda.device(t.device):
+        rc = _lib.lib().sr_blur_nhwc_styled_f32(_lib.ptr(out), _lib.ptr(t), _lib.ptr(taps.contiguous()), b, ih, iw, c,
+                                                pad[0], pad[1], _lib.ptr(nz), nbs, _lib.ptr(noise_weight), _lib.ptr(bias),
+                                                float(alpha), float(gain), _lib.stream_of(t))
+    _lib.check(rc, "sr_blur_nhwc_styled_f32")
+    return out
+
+
+def bwd_prologue(gy, y, noise, noise_weight, bias, d, alpha, gain, want_e):
+    """-> (ga, g_bias [C], g_noise_w [1], e [B,C] or None); see sr_styled_bwd_prologue_f32."""
+    _check_nhwc(gy, "bwd_prologue gy")
+    _check_nhwc(y, "bwd_prologue y")
+    b, h, w, c = y.shape
+    dev = y.device
+    ga = torch.empty_like(y)
+    g_bias = torch.empty(c, dtype=torch.float32, device=dev)
+    g_nw = torch.empty(1, dtype=torch.float32, device=dev)
+    e = torch.empty(b, c, dtype=torch.float32, device=dev) if want_e else None
+    nz, nbs = _noise_args(noise, h, w)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().sr_styled_bwd_prologue_f32(_lib.ptr(ga), _lib.ptr(g_bias), _lib.ptr(g_nw), _lib.ptr(e), _lib.ptr(gy),
+                                                   _lib.ptr(y), _lib.ptr(nz), nbs, _lib.ptr(noise_weight), _lib.ptr(bias),
+                                                   _lib.ptr(d), b, h * w, c, float(alpha), float(gain), _lib.stream_of(y))
+    _lib.check(rc, "sr_styled_bwd_prologue_f32")
+    return ga, g_bias, g_nw, e
+
+
+def scale_dot(a, other, scale, round_out, want_out=True):
+    """-> (a * scale[b,c] (tf32-rounded if round_out) or None, dot[b,c] = sum_p a*other or None)."""
+    _check_nhwc(a, "scale_dot a")
+    b, h, w, c = a.shape
+    out = torch.empty_like(a) if want_out else None
+    dot = torch.empty(b, c, dtype=torch.float32, device=a.device) if other is not None else None
+    with torch.cuda.device(a.device):
+        rc = _lib.lib().sr_scale_dot_nhwc_f32(_lib.ptr(out), _lib.ptr(dot), _lib.ptr(a), _lib.ptr(other),
+                                              _lib.ptr(scale.contiguous() if scale is not None else None), b, h * w, c,
+                                              int(bool(round_out)), _lib.stream_of(a))
+    _lib.check(rc, "sr_scale_dot_nhwc_f32")
+    return out, dot
