@@ -117,7 +117,7 @@ class KernelTimer:
 
 
 def algorithmic_bytes(name, a):
-    """bytes one launch must move."""
+    """bytes one launch must move (HBM-bound kernels)."""
     if name == "sr_fused_bias_act_f32":
         return 8 * a[8] + 4 * a[10]
     if name == "sr_fused_lrelu_backward_f32":
@@ -127,6 +127,24 @@ def algorithmic_bytes(name, a):
         oh = (ih * uy + py0 + py1 - kh) // dy + 1
         ow = (iw * ux + px0 + px1 - kw) // dx + 1
         return 4 * major * minor * (ih * iw + oh * ow) + 4 * kh * kw
+    if name == "sr_blur_nhwc_styled_f32":
+        b, ih, iw, c, p0, p1 = a[3], a[4], a[5], a[6], a[7], a[8]
+        return 4 * b * c * (ih * iw + (ih + p0 + p1 - 3) * (iw + p0 + p1 - 3))
+    if name == "sr_modulate_tf32":
+        return 8 * a[3] * a[4] * a[5]
+    if name == "sr_styled_bwd_prologue_f32":
+        return 12 * a[11] * a[12] * a[13]
+    if name == "sr_scale_dot_nhwc_f32":
+        n = a[5] * a[6] * a[7]
+        return 4 * n * (1 + (1 if a[0] else 0) + (1 if a[3] else 0))
+    return 0
+
+
+def algorithmic_flops(name, a):
+    """2 * M * N * K of the implicit GEMM (tensor-bound kernels)."""
+    if name in ("sr_conv_igemm_tf32", "sr_conv_wgrad_tf32"):
+        s = a[0]._obj
+        return 2 * s.batch * s.grid_h * s.grid_w * s.num_taps * s.cin * s.cout
     return 0
 
 
@@ -136,16 +154,26 @@ def dominant_kernel_roofline(stats, peaks, total_ms, steps):
     tot = {n: sum(ms for _, ms in calls) for n, calls in stats.items()}
     name = max(tot, key=tot.get)
     calls = stats[name]
-    by = sum(algorithmic_bytes(name, a) for a, _ in calls)
     ms = tot[name]
+    common = {"kernel": name, "launches_per_step": len(calls) / steps, "avg_launch_ms": round(ms / len(calls), 5),
+              "share_of_step": round(ms / total_ms, 4) if total_ms else None, "traffic": None,
+              "all_kernels_ms_per_step": {n: round(v / steps, 4) for n, v in tot.items()}}
+    fl = sum(algorithmic_flops(name, a) for a, _ in calls)
+    if fl:
+        # MEASURED_PEAKS.json holds the dense bf16 rate only; kind::tf32 runs at half of it on sm_100.  The kernel is
+        # timed inside a long step, so the sustained figure applies.
+        peak = peaks["bf16_tflops_sustained"] / 2
+        ach = fl / (ms * 1e-3) / 1e12
+        common.update({"bound": "tensor", "achieved": round(ach, 1), "peak": round(peak, 1), "unit": "TFLOP/s",
+                       "frac": round(ach / peak, 4), "peak_source": peaks["_source"] + " bf16_tflops_sustained / 2 (tf32)",
+                       "algorithmic_flops_per_step": fl // steps})
+        return common
+    by = sum(algorithmic_bytes(name, a) for a, _ in calls)
     ach = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-    peak = peaks["hbm_gbs"]
-    return {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(ach / peak, 4), "traffic": None, "peak_source": peaks["_source"],
-            "launches_per_step": len(calls) / steps, "avg_launch_ms": round(ms / len(calls), 5),
-            "share_of_step": round(ms / total_ms, 4) if total_ms else None,
-            "algorithmic_bytes_per_step": by // steps,
-            "all_kernels_ms_per_step": {n: round(v / steps, 4) for n, v in tot.items()}}
+    common.update({"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                   "frac": round(ach / peaks["hbm_gbs"], 4), "peak_source": peaks["_source"],
+                   "algorithmic_bytes_per_step": by // steps})
+    return common
 
 
 # ----------------------------------------------------------------------------------------------- workloads
@@ -321,6 +349,7 @@ def main():
     if rank == 0:
         names = ["sr_fused_bias_act_f32", "sr_fused_lrelu_backward_f32", "sr_upfirdn2d_f32"]
         names += [n for n in getattr(_lib, "CONV_EXPORTS", ())]
+        # per-launch HBM efficiency of the bandwidth-bound passes, reported beside the dominant kernel
         with KernelTimer(_lib, names) as kt:
             torch.cuda.synchronize()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
