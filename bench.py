@@ -142,6 +142,8 @@ def algorithmic_bytes(name, a):
 
 def algorithmic_flops(name, a):
     """2 * M * N * K of the implicit GEMM (tensor-bound kernels)."""
+    if name == "sr_conv_igemm_multi_tf32":
+        return sum(2 * s.batch * s.grid_h * s.grid_w * s.num_taps * s.cin * s.cout for s in list(a[0])[:a[1]])
     if name in ("sr_conv_igemm_tf32", "sr_conv_wgrad_tf32"):
         s = a[0]._obj
         return 2 * s.batch * s.grid_h * s.grid_w * s.num_taps * s.cin * s.cout

@@ -149,6 +149,10 @@ typedef struct sr_conv_args {
     float alpha, gain;
 } sr_conv_args;
 int sr_conv_igemm_tf32(const sr_conv_args *args, void *stream);
+/* `count` (<= 4) such contractions that share every tensor, stride and epilogue and differ only in tap list,
+ * lattice size and lattice origin -- the four output-parity classes of the stride-2 transposed convolution
+ * (reference layers.py:301-309) -- executed as ONE persistent launch. */
+int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, void *stream);
 
 /* Weight gradient of the same contraction on the tensor cores (replaces cuDNN's grouped wgrad under
  * ModulatedConv2d's backward): for every tap t < num_taps

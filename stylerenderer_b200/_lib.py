@@ -33,6 +33,7 @@ _SIGNATURES = {
     "sr_rasterize_backward_f32": (_I, [_L, _L, _L, _L, _L, _I, _P, _P, _P, _P, _P, _P, _P, _F, _P]),
     "sr_rasterize_backward_f64": (_I, [_L, _L, _L, _L, _L, _I, _P, _P, _P, _P, _P, _P, _P, _D, _P]),
     "sr_conv_igemm_tf32": (_I, [_P, _P]),
+    "sr_conv_igemm_multi_tf32": (_I, [_P, _I, _P]),
     "sr_conv_wgrad_tf32": (_I, [_P, _P]),
     "sr_modulate_tf32": (_I, [_P, _P, _P, _L, _L, _L, _P]),
     "sr_conv_weight_prep_tf32": (_I, [_P, _P, _F, _L, _L, _I, _I, _I, _P]),
@@ -43,7 +44,7 @@ _SIGNATURES = {
 
 EXPORTS = tuple(_SIGNATURES)
 CONV_EXPORTS = ("sr_blur_nhwc_styled_f32", "sr_styled_bwd_prologue_f32", "sr_scale_dot_nhwc_f32",
-                "sr_conv_igemm_tf32", "sr_conv_wgrad_tf32", "sr_modulate_tf32", "sr_conv_weight_prep_tf32")
+                "sr_conv_igemm_tf32", "sr_conv_igemm_multi_tf32", "sr_conv_wgrad_tf32", "sr_modulate_tf32", "sr_conv_weight_prep_tf32")
 
 
 class NativeLibraryError(RuntimeError):

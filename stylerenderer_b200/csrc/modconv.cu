@@ -110,26 +110,57 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // ------------------------------------------------------------------------------------ kernel
-struct ConvKParams {
-    int tw_log2, th_log2, tn_log2;          // tile = 2^tn images x 2^th rows x 2^tw columns = 128 pixels
-    int tiles_x, tiles_y;
-    int batch, grid_h, grid_w;
-    int kblocks_per_tap;                    // cin / 32
+constexpr int kMaxPhases = 4;
+
+struct ConvPhase {                          // one tap list + output lattice (the 4 parity classes of a transposed conv)
     int num_taps;
     int tap_dy[9], tap_dx[9], tap_k0[9];    // input offset of a tap and its first K column in the weight matrix
+    int grid_h, grid_w, tiles_x, tiles_y;
+    int tile_begin;                         // first M tile of this phase
+    long long out_offset;                   // lattice origin (y0 * row + x0 * pix), in floats
+    long long noise_offset;
+};
+
+struct ConvKParams {
+    int tw_log2, th_log2, tn_log2;          // tile = 2^tn images x 2^th rows x 2^tw columns = 128 pixels
+    int batch;
+    int kblocks_per_tap;                    // cin / 32
+    int num_phases, n_tiles, total_tiles;   // total_tiles = (sum of M tiles) * n_tiles
+    ConvPhase ph[kMaxPhases];
     int in_stride;
     int cout;
     long long out_img_stride, out_row_stride, out_pix_stride;   // in floats
-    long long out_offset;                   // lattice origin (y0 * row + x0 * pix), in floats
     float *out, *out2;
     int epilogue;                           // 0: acc * rowscale   1: styled
     const float *rowscale, *scale2, *bias, *noise, *noise_weight, *stylemap;
-    long long noise_img_stride, noise_row_stride, noise_pix_stride, noise_offset;
-    long long map_img_stride;               // stylemap [batch, 2, out_h, out_w] planar: plane stride = out_h*out_w
-    long long map_plane_stride;
+    long long noise_img_stride, noise_row_stride, noise_pix_stride;
+    long long map_img_stride, map_plane_stride;
     float alpha, gain;
 };
 
+struct TileCoord { int phase, gx0, gy0, n0, n_tile; };
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvKParams &p, int T) {
+    TileCoord c;
+    c.n_tile = T % p.n_tiles;
+    int mt = T / p.n_tiles;
+    c.phase = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxPhases; ++i)
+        if (i < p.num_phases && mt >= p.ph[i].tile_begin) c.phase = i;
+    const ConvPhase &ph = p.ph[c.phase];
+    mt -= ph.tile_begin;
+    const int tx = mt % ph.tiles_x, ty = (mt / ph.tiles_x) % ph.tiles_y, tn = mt / (ph.tiles_x * ph.tiles_y);
+    c.gx0 = tx << p.tw_log2; c.gy0 = ty << p.th_log2; c.n0 = tn << p.tn_log2;
+    return c;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent: gridDim.x CTAs (one per SM) walk the tile list round-robin.  The TMEM holds TWO accumulators, so the
+// epilogue of tile i (TMEM -> registers -> fused tail -> global) overlaps the TMA/MMA main loop of tile i+1.
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -144,25 +175,22 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     uint8_t *sB = smem + STAGES * A_BYTES;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * (A_BYTES + B_BYTES));
     uint64_t *empty_bar = full_bar + STAGES;
-    uint64_t *tmem_full_bar = empty_bar + STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+    uint64_t *tmem_full_bar = empty_bar + STAGES;      // [2]
+    uint64_t *tmem_empty_bar = tmem_full_bar + 2;      // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x, n_tile = blockIdx.y;
-    const int tile_x = tile % p.tiles_x, tile_y = (tile / p.tiles_x) % p.tiles_y, tile_n = tile / (p.tiles_x * p.tiles_y);
-    const int gx0 = tile_x << p.tw_log2, gy0 = tile_y << p.th_log2, n0 = tile_n << p.tn_log2;
-    const int num_kb = p.num_taps * p.kblocks_per_tap;
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_b) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {                                   // TMEM: BLOCK_N fp32 columns x 128 lanes
+    if (warp == 1) {                                   // TMEM: 2 accumulators of BLOCK_N fp32 columns x 128 lanes
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)BLOCK_N) : "memory");
+                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BLOCK_N)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tcgen05_fence_before();
@@ -172,32 +200,45 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 
     if (warp == 0) {
         if (lane == 0) {                               // ===== TMA producer
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                const int t = kb / p.kblocks_per_tap, kc = kb - t * p.kblocks_per_tap;
-                mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
-                tma_load_4d(sA + s * A_BYTES, &tmap_a, &full_bar[s], kc * BLOCK_K,
-                            gx0 * p.in_stride + p.tap_dx[t], gy0 * p.in_stride + p.tap_dy[t], n0);
-                tma_load_2d(sB + s * B_BYTES, &tmap_b, &full_bar[s], p.tap_k0[t] + kc * BLOCK_K, n_tile * BLOCK_N);
+            uint32_t it = 0;
+            for (int T = blockIdx.x; T < p.total_tiles; T += gridDim.x) {
+                const TileCoord tc = decode_tile(p, T);
+                const ConvPhase &ph = p.ph[tc.phase];
+                for (int t = 0; t < ph.num_taps; ++t) {
+                    const int cx = tc.gx0 * p.in_stride + ph.tap_dx[t], cy = tc.gy0 * p.in_stride + ph.tap_dy[t];
+                    for (int kc = 0; kc < p.kblocks_per_tap; ++kc, ++it) {
+                        const uint32_t s = it % STAGES, par = (it / STAGES) & 1;
+                        mbar_wait(&empty_bar[s], par ^ 1);
+                        mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+                        tma_load_4d(sA + s * A_BYTES, &tmap_a, &full_bar[s], kc * BLOCK_K, cx, cy, tc.n0);
+                        tma_load_2d(sB + s * B_BYTES, &tmap_b, &full_bar[s], ph.tap_k0[t] + kc * BLOCK_K, tc.n_tile * BLOCK_N);
+                    }
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {                               // ===== MMA issuer
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+            uint32_t it = 0, lt = 0;
+            for (int T = blockIdx.x; T < p.total_tiles; T += gridDim.x, ++lt) {
+                const TileCoord tc = decode_tile(p, T);
+                const int num_kb = p.ph[tc.phase].num_taps * p.kblocks_per_tap;
+                const uint32_t acc = lt & 1, acc_par = (lt >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[acc], acc_par ^ 1);      // epilogue has drained this accumulator
                 tcgen05_fence_after();
-                const uint64_t da = make_kmajor_sw128_desc(smem_u32(sA + s * A_BYTES));
-                const uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + s * B_BYTES));
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, par = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], par);
+                    tcgen05_fence_after();
+                    const uint64_t da = make_kmajor_sw128_desc(smem_u32(sA + s * A_BYTES));
+                    const uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + s * B_BYTES));
 #pragma unroll
-                for (int k = 0; k < BLOCK_K / 8; ++k)  // K = 8 per instruction = 32 bytes along the swizzled row
-                    umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
-                tcgen05_commit(&empty_bar[s]);         // frees the ring slot once these MMAs have read it
+                    for (int k = 0; k < BLOCK_K / 8; ++k)  // K = 8 per instruction = 32 bytes along the swizzled row
+                        umma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
+                    tcgen05_commit(&empty_bar[s]);         // frees the ring slot once these MMAs have read it
+                }
+                tcgen05_commit(&tmem_full_bar[acc]);       // accumulator complete
             }
-            tcgen05_commit(tmem_full_bar);             // accumulator complete
         }
     } else {                                           // ===== epilogue: warp w reads TMEM lanes 32*(w%4)..+31
         const int q = warp & 3;
@@ -205,66 +246,71 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const int tx = row & ((1 << p.tw_log2) - 1);
         const int ty = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
         const int tn = row >> (p.tw_log2 + p.th_log2);
-        const int gx = gx0 + tx, gy = gy0 + ty, n = n0 + tn;
-        const bool valid = gx < p.grid_w && gy < p.grid_h && n < p.batch;
-        const long long opix = (long long)n * p.out_img_stride + (long long)gy * p.out_row_stride +
-                               (long long)gx * p.out_pix_stride + p.out_offset;
-        float pre_add = 0.0f, map_mul = 1.0f;
-        if (p.epilogue == 1 && valid) {
-            if (p.noise)
-                pre_add = __ldg(p.noise_weight) * __ldg(p.noise + (long long)n * p.noise_img_stride +
-                                                        (long long)gy * p.noise_row_stride +
-                                                        (long long)gx * p.noise_pix_stride + p.noise_offset);
-            if (p.stylemap) {
-                const float *m = p.stylemap + (long long)n * p.map_img_stride + (long long)gy * p.noise_row_stride +
-                                 (long long)gx * p.noise_pix_stride + p.noise_offset;
-                map_mul = __ldg(m);
-                pre_add += __ldg(m + p.map_plane_stride);
+        uint32_t lt = 0;
+        for (int T = blockIdx.x; T < p.total_tiles; T += gridDim.x, ++lt) {
+            const TileCoord tc = decode_tile(p, T);
+            const ConvPhase &ph = p.ph[tc.phase];
+            const uint32_t acc = lt & 1, acc_par = (lt >> 1) & 1;
+            const int gx = tc.gx0 + tx, gy = tc.gy0 + ty, n = tc.n0 + tn;
+            const bool valid = gx < ph.grid_w && gy < ph.grid_h && n < p.batch;
+            const long long opix = (long long)n * p.out_img_stride + (long long)gy * p.out_row_stride +
+                                   (long long)gx * p.out_pix_stride + ph.out_offset;
+            float pre_add = 0.0f, map_mul = 1.0f;
+            if (p.epilogue == 1 && valid) {
+                const long long npix = (long long)gy * p.noise_row_stride + (long long)gx * p.noise_pix_stride + ph.noise_offset;
+                if (p.noise) pre_add = __ldg(p.noise_weight) * __ldg(p.noise + (long long)n * p.noise_img_stride + npix);
+                if (p.stylemap) {
+                    const float *m = p.stylemap + (long long)n * p.map_img_stride + npix;
+                    map_mul = __ldg(m);
+                    pre_add += __ldg(m + p.map_plane_stride);
+                }
             }
-        }
-        mbar_wait(tmem_full_bar, 0);
-        tcgen05_fence_after();
+            mbar_wait(&tmem_full_bar[acc], acc_par);
+            tcgen05_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-            if (valid) {
-                const int ch0 = n_tile * BLOCK_N + c * 32;
-                const float4 *rs = p.rowscale ? reinterpret_cast<const float4 *>(p.rowscale + (long long)n * p.cout + ch0) : nullptr;
-                const float4 *s2 = p.out2 ? reinterpret_cast<const float4 *>(p.scale2 + (long long)n * p.cout + ch0) : nullptr;
-                const float4 *bs = (p.epilogue == 1 && p.bias) ? reinterpret_cast<const float4 *>(p.bias + ch0) : nullptr;
-                float4 *o1 = reinterpret_cast<float4 *>(p.out + opix * 1 + ch0);
-                float4 *o2 = p.out2 ? reinterpret_cast<float4 *>(p.out2 + opix + ch0) : nullptr;
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * 32), r);
+                if (valid) {
+                    const int ch0 = tc.n_tile * BLOCK_N + c * 32;
+                    const float4 *rs = p.rowscale ? reinterpret_cast<const float4 *>(p.rowscale + (long long)n * p.cout + ch0) : nullptr;
+                    const float4 *s2 = p.out2 ? reinterpret_cast<const float4 *>(p.scale2 + (long long)n * p.cout + ch0) : nullptr;
+                    const float4 *bs = (p.epilogue == 1 && p.bias) ? reinterpret_cast<const float4 *>(p.bias + ch0) : nullptr;
+                    float4 *o1 = reinterpret_cast<float4 *>(p.out + opix + ch0);
+                    float4 *o2 = p.out2 ? reinterpret_cast<float4 *>(p.out2 + opix + ch0) : nullptr;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float v[4] = {__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                  __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])};
-                    if (rs) { const float4 s = __ldg(rs + j); v[0] *= s.x; v[1] *= s.y; v[2] *= s.z; v[3] *= s.w; }
-                    if (p.epilogue == 1) {
-                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (bs) b = __ldg(bs + j);
-                        const float bb[4] = {b.x, b.y, b.z, b.w};
+                    for (int j = 0; j < 8; ++j) {
+                        float v[4] = {__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                      __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])};
+                        if (rs) { const float4 s = __ldg(rs + j); v[0] *= s.x; v[1] *= s.y; v[2] *= s.z; v[3] *= s.w; }
+                        if (p.epilogue == 1) {
+                            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (bs) b = __ldg(bs + j);
+                            const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float t = v[e] * map_mul + pre_add + bb[e];
-                            v[e] = ((t > 0.0f) ? t : t * p.alpha) * p.gain;
+                            for (int e = 0; e < 4; ++e) {
+                                float t = v[e] * map_mul + pre_add + bb[e];
+                                v[e] = ((t > 0.0f) ? t : t * p.alpha) * p.gain;
+                            }
                         }
-                    }
-                    o1[j] = make_float4(v[0], v[1], v[2], v[3]);
-                    if (o2) {
-                        const float4 s = __ldg(s2 + j);
-                        o2[j] = make_float4(round_tf32(v[0] * s.x), round_tf32(v[1] * s.y), round_tf32(v[2] * s.z),
-                                            round_tf32(v[3] * s.w));
+                        o1[j] = make_float4(v[0], v[1], v[2], v[3]);
+                        if (o2) {
+                            const float4 s = __ldg(s2 + j);
+                            o2[j] = make_float4(round_tf32(v[0] * s.x), round_tf32(v[1] * s.y), round_tf32(v[2] * s.z),
+                                                round_tf32(v[3] * s.w));
+                        }
                     }
                 }
             }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);   // this warp no longer reads accumulator `acc`
         }
-        tcgen05_fence_before();
     }
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)BLOCK_N) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)(2 * BLOCK_N)) : "memory");
     }
 }
 
@@ -466,7 +512,7 @@ EncodeTiledFn encode_tiled() {
 int ilog2_exact(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 template <int BLOCK_N, int STAGES>
-int launch_conv(const CUtensorMap &ta, const CUtensorMap &tb, const ConvKParams &p, int m_tiles, int n_tiles, cudaStream_t st)
+int launch_conv(const CUtensorMap &ta, const CUtensorMap &tb, const ConvKParams &p, cudaStream_t st)
 {
     constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
     const size_t smem = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 256;
@@ -477,7 +523,8 @@ int launch_conv(const CUtensorMap &ta, const CUtensorMap &tb, const ConvKParams 
         if (e != cudaSuccess) { set_error("conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
-    kern<<<dim3((unsigned)m_tiles, (unsigned)n_tiles), kConvThreads, smem, st>>>(ta, tb, p);
+    const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;     // persistent: one CTA per SM
+    kern<<<grid, kConvThreads, smem, st>>>(ta, tb, p);
     return SR_OK;
 }
 
@@ -486,29 +533,71 @@ int launch_conv(const CUtensorMap &ta, const CUtensorMap &tb, const ConvKParams 
 
 using namespace sr;
 
-extern "C" int sr_conv_igemm_tf32(const sr_conv_args *a, void *stream)
+// `count` launches that share tensors / strides / epilogue and differ only in tap list, lattice size and lattice
+// origin (the four parity classes of the stride-2 transposed conv) run as ONE persistent grid.
+extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, void *stream)
 {
-    SR_REQUIRE(a, "conv: null args");
+    SR_REQUIRE(args && count >= 1 && count <= kMaxPhases, "conv: 1..4 phases");
+    const sr_conv_args *a = args;
     SR_REQUIRE(a->in && a->weight && a->out, "conv: null tensor");
     SR_REQUIRE(a->cin >= 32 && a->cin % 32 == 0, "conv: cin must be a multiple of 32 (got %lld)", (long long)a->cin);
     SR_REQUIRE(a->cout >= 128 && a->cout % 128 == 0, "conv: cout must be a multiple of 128 (got %lld)", (long long)a->cout);
-    SR_REQUIRE(a->num_taps >= 1 && a->num_taps <= 9, "conv: 1..9 taps");
     SR_REQUIRE(a->in_stride >= 1 && a->in_stride <= 8 && a->out_stride >= 1, "conv: bad strides");
-    SR_REQUIRE(a->batch >= 1 && a->grid_h >= 1 && a->grid_w >= 1, "conv: empty problem");
+    SR_REQUIRE(a->batch >= 1, "conv: empty problem");
     SR_REQUIRE((reinterpret_cast<uintptr_t>(a->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->weight) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "conv: tensors must be 16-byte aligned");
     SR_REQUIRE(a->epilogue == 0 || a->epilogue == 1, "conv: unknown epilogue");
     SR_REQUIRE(!a->out2 || a->scale2, "conv: out2 needs scale2");
+    SR_REQUIRE(!a->noise || a->noise_weight, "conv: noise needs noise_weight");
+    int64_t max_gw = 0, max_gh = 0;
+    for (int i = 0; i < count; ++i) {
+        const sr_conv_args *b = args + i;
+        SR_REQUIRE(b->num_taps >= 1 && b->num_taps <= 9, "conv: 1..9 taps");
+        SR_REQUIRE(b->grid_h >= 1 && b->grid_w >= 1, "conv: empty lattice");
+        SR_REQUIRE(b->in == a->in && b->weight == a->weight && b->out == a->out && b->out2 == a->out2 && b->cin == a->cin &&
+                   b->cout == a->cout && b->batch == a->batch && b->in_h == a->in_h && b->in_w == a->in_w &&
+                   b->out_h == a->out_h && b->out_w == a->out_w && b->in_stride == a->in_stride &&
+                   b->out_stride == a->out_stride && b->epilogue == a->epilogue && b->taps_total == a->taps_total,
+                   "conv: phases must share tensors, strides and epilogue");
+        if (b->grid_w > max_gw) max_gw = b->grid_w;
+        if (b->grid_h > max_gh) max_gh = b->grid_h;
+    }
     EncodeTiledFn enc = encode_tiled();
     if (!enc) { set_error("conv: cuTensorMapEncodeTiled not available from the driver"); return SR_ERR_DRIVER; }
     cudaStream_t st = (cudaStream_t)stream;
 
     // tile shape: 16x8 pixels of one image, or several whole small images
     int tw, th, tn;
-    if (a->grid_w > 8) { tw = 16; th = 8; tn = 1; }
-    else if (a->grid_w > 4) { tw = 8; th = (a->grid_h > 4) ? 8 : 4; tn = 128 / (tw * th); }
+    if (max_gw > 8) { tw = 16; th = 8; tn = 1; }
+    else if (max_gw > 4) { tw = 8; th = (max_gh > 4) ? 8 : 4; tn = 128 / (tw * th); }
     else { tw = 4; th = 4; tn = 8; }
-    const int block_n = (a->cout % 256 == 0) ? 256 : 128;
+
+    ConvKParams p;
+    p.tw_log2 = ilog2_exact(tw); p.th_log2 = ilog2_exact(th); p.tn_log2 = ilog2_exact(tn);
+    p.batch = (int)a->batch;
+    p.kblocks_per_tap = (int)(a->cin / BLOCK_K);
+    p.num_phases = count;
+    const int tiles_n = (int)((a->batch + tn - 1) / tn);
+    long long m_tiles = 0;
+    for (int i = 0; i < kMaxPhases; ++i) {
+        ConvPhase &ph = p.ph[i];
+        const sr_conv_args *b = args + (i < count ? i : 0);
+        ph.num_taps = b->num_taps;
+        for (int t = 0; t < 9; ++t) { ph.tap_dy[t] = b->tap_dy[t]; ph.tap_dx[t] = b->tap_dx[t]; ph.tap_k0[t] = (int)(b->tap_w[t] * a->cin); }
+        ph.grid_h = (int)b->grid_h; ph.grid_w = (int)b->grid_w;
+        ph.tiles_x = (int)((b->grid_w + tw - 1) / tw);
+        ph.tiles_y = (int)((b->grid_h + th - 1) / th);
+        ph.tile_begin = (int)m_tiles;
+        ph.out_offset = ((long long)b->out_y0 * a->out_w + b->out_x0) * a->cout;
+        ph.noise_offset = (long long)b->out_y0 * a->out_w + b->out_x0;
+        if (i < count) m_tiles += (long long)ph.tiles_x * ph.tiles_y * tiles_n;
+    }
+    // few tiles (low resolutions): prefer 128-wide N tiles so more SMs take part
+    int block_n = (a->cout % 256 == 0) ? 256 : 128;
+    if (block_n == 256 && m_tiles * (a->cout / 256) < kNumSMs / 2) block_n = 128;
+    p.n_tiles = (int)(a->cout / block_n);
+    SR_REQUIRE(m_tiles * p.n_tiles < 0x7fffffffll, "conv: too many tiles");
+    p.total_tiles = (int)(m_tiles * p.n_tiles);
 
     CUtensorMap ta, tb;
     {
@@ -535,47 +624,32 @@ extern "C" int sr_conv_igemm_tf32(const sr_conv_args *a, void *stream)
         if (r != CUDA_SUCCESS) { set_error("conv: cuTensorMapEncodeTiled(B) failed with %d", (int)r); return SR_ERR_DRIVER; }
     }
 
-    ConvKParams p;
-    p.tw_log2 = ilog2_exact(tw); p.th_log2 = ilog2_exact(th); p.tn_log2 = ilog2_exact(tn);
-    p.tiles_x = (int)((a->grid_w + tw - 1) / tw);
-    p.tiles_y = (int)((a->grid_h + th - 1) / th);
-    const int tiles_n = (int)((a->batch + tn - 1) / tn);
-    p.batch = (int)a->batch; p.grid_h = (int)a->grid_h; p.grid_w = (int)a->grid_w;
-    p.kblocks_per_tap = (int)(a->cin / BLOCK_K);
-    p.num_taps = a->num_taps;
-    for (int t = 0; t < 9; ++t) {
-        p.tap_dy[t] = a->tap_dy[t]; p.tap_dx[t] = a->tap_dx[t];
-        p.tap_k0[t] = (int)(a->tap_w[t] * a->cin);
-    }
     p.in_stride = a->in_stride;
     p.cout = (int)a->cout;
     p.out_pix_stride = (long long)a->out_stride * a->cout;
     p.out_row_stride = (long long)a->out_stride * a->out_w * a->cout;
     p.out_img_stride = (long long)a->out_h * a->out_w * a->cout;
-    p.out_offset = ((long long)a->out_y0 * a->out_w + a->out_x0) * a->cout;
     p.out = a->out; p.out2 = a->out2;
     p.epilogue = a->epilogue;
     p.rowscale = a->rowscale; p.scale2 = a->scale2; p.bias = a->bias;
     p.noise = a->noise; p.noise_weight = a->noise_weight; p.stylemap = a->stylemap;
-    SR_REQUIRE(!p.noise || p.noise_weight, "conv: noise needs noise_weight");
     // noise / stylemap are planar [*, out_h, out_w] and are addressed on the same output lattice
     p.noise_pix_stride = a->out_stride;
     p.noise_row_stride = (long long)a->out_stride * a->out_w;
     p.noise_img_stride = a->noise_batch_stride;
-    p.noise_offset = (long long)a->out_y0 * a->out_w + a->out_x0;
     p.map_plane_stride = (long long)a->out_h * a->out_w;
     p.map_img_stride = a->stylemap_batch_stride;
     p.alpha = a->alpha; p.gain = a->gain;
 
-    const long long m_tiles = (long long)p.tiles_x * p.tiles_y * tiles_n;
-    SR_REQUIRE(m_tiles < 0x7fffffffll, "conv: too many tiles");
     int rc;
-    if (block_n == 256) rc = launch_conv<256, 4>(ta, tb, p, (int)m_tiles, (int)(a->cout / 256), st);
-    else rc = launch_conv<128, 6>(ta, tb, p, (int)m_tiles, (int)(a->cout / 128), st);
+    if (block_n == 256) rc = launch_conv<256, 4>(ta, tb, p, st);
+    else rc = launch_conv<128, 6>(ta, tb, p, st);
     if (rc != SR_OK) return rc;
     count_launch();
     return check_launch("sr_conv_igemm_tf32");
 }
+
+extern "C" int sr_conv_igemm_tf32(const sr_conv_args *a, void *stream) { return sr_conv_igemm_multi_tf32(a, 1, stream); }
 
 extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
 {

@@ -74,19 +74,12 @@ def modulate(x, style=None):
     return xs
 
 
-def conv_igemm(x, wmat, taps, out, *, in_stride=1, grid=None, out_stride=1, out_origin=(0, 0), epilogue=0,
-               rowscale=None, out2=None, scale2=None, bias=None, noise=None, noise_weight=None, stylemap=None,
-               alpha=0.2, gain=2 ** 0.5):
-    """out[n, y0 + gy*os, x0 + gx*os, :] = epilogue( sum_t x[n, gy*is + dy_t, gx*is + dx_t, :] @ wmat[:, w_t, :]^T ).
-    taps: list of (dy, dx, weight_tap_index)."""
-    _check_nhwc(x, "conv input")
-    _check_nhwc(out, "conv output")
-    a = ConvArgs()
+def _fill_args(a, x, wmat, taps, out, in_stride, grid, out_stride, out_origin, epilogue, rowscale, out2, scale2, bias,
+               noise, noise_weight, stylemap, alpha, gain):
     a.in_ = _lib.ptr(x)
     a.batch, a.in_h, a.in_w, a.cin = x.shape
     a.weight = _lib.ptr(wmat)
     a.cout, a.taps_total = wmat.shape[0], wmat.shape[1]
-    assert wmat.is_contiguous() and wmat.shape[2] == x.shape[3] and out.shape[3] == wmat.shape[0] and out.shape[0] == x.shape[0]
     a.num_taps = len(taps)
     for i, (dy, dx, wi) in enumerate(taps):
         a.tap_dy[i], a.tap_dx[i], a.tap_w[i] = dy, dx, wi
@@ -107,10 +100,28 @@ def conv_igemm(x, wmat, taps, out, *, in_stride=1, grid=None, out_stride=1, out_
             and stylemap.stride(1) == out.shape[1] * out.shape[2]
         a.stylemap_batch_stride = stylemap.stride(0)
     a.alpha, a.gain = alpha, gain
+
+
+def conv_igemm_multi(x, wmat, phases, out, *, in_stride=1, out_stride=1, epilogue=0, rowscale=None, out2=None,
+                     scale2=None, bias=None, noise=None, noise_weight=None, stylemap=None, alpha=0.2, gain=2 ** 0.5):
+    """One persistent launch over up to 4 phases [(taps, grid, out_origin)] sharing all tensors (see conv_igemm)."""
+    _check_nhwc(x, "conv input")
+    _check_nhwc(out, "conv output")
+    assert wmat.is_contiguous() and wmat.shape[2] == x.shape[3] and out.shape[3] == wmat.shape[0] and out.shape[0] == x.shape[0]
+    arr = (ConvArgs * len(phases))()
+    for a, (taps, grid, origin) in zip(arr, phases):
+        _fill_args(a, x, wmat, taps, out, in_stride, grid, out_stride, origin, epilogue, rowscale, out2, scale2, bias, noise,
+                   noise_weight, stylemap, alpha, gain)
     with torch.cuda.device(x.device):
-        rc = _lib.lib().sr_conv_igemm_tf32(ctypes.byref(a), _lib.stream_of(x))
-    _lib.check(rc, "sr_conv_igemm_tf32")
+        rc = _lib.lib().sr_conv_igemm_multi_tf32(arr, len(phases), _lib.stream_of(x))
+    _lib.check(rc, "sr_conv_igemm_multi_tf32")
     return out
+
+
+def conv_igemm(x, wmat, taps, out, *, grid=None, out_origin=(0, 0), **kw):
+    """out[n, y0 + gy*os, x0 + gx*os, :] = epilogue( sum_t x[n, gy*is + dy_t, gx*is + dx_t, :] @ wmat[:, w_t, :]^T ).
+    taps: list of (dy, dx, weight_tap_index)."""
+    return conv_igemm_multi(x, wmat, [(taps, grid, out_origin)], out, **kw)
 
 
 TAPS_3X3 = [(ky - 1, kx - 1, ky * 3 + kx) for ky in range(3) for kx in range(3)]
@@ -129,13 +140,13 @@ def conv_transpose3x3_s2(x, wmat, out=None, rowscale=None):
     b, h, w, _ = x.shape
     if out is None:
         out = torch.empty(b, 2 * h + 1, 2 * w + 1, wmat.shape[0], dtype=torch.float32, device=x.device)
+    phases = []
     for py in (0, 1):
         for px in (0, 1):
             taps = [(-(ky - py) // 2, -(kx - px) // 2, ky * 3 + kx)
                     for ky in range(py, 3, 2) for kx in range(px, 3, 2)]
-            conv_igemm(x, wmat, taps, out, grid=(h + 1 - py, w + 1 - px), out_stride=2, out_origin=(py, px),
-                       rowscale=rowscale)
-    return out
+            phases.append((taps, (h + 1 - py, w + 1 - px), (py, px)))
+    return conv_igemm_multi(x, wmat, phases, out, out_stride=2, rowscale=rowscale)
 
 
 def conv3x3_s2_gather(g, wmat, out_hw, out=None, rowscale=None):
