@@ -266,6 +266,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step (BASELINE config: 32)")
     ap.add_argument("--conv-backend", default=None, choices=[None, "cudnn", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches only (default: also replay the step as a CUDA graph)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -338,13 +339,52 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()                            # host time to ENQUEUE one eager step (launch-boundness check)
+    step_resident()
+    cpu_enqueue_ms = (time.perf_counter() - t0) * 1e3
     n0 = _lib.launch_count()
     with ClockSampler(local) as clocks:
-        ms = timed(step_resident, args.steps)
-    launches = _lib.launch_count() - n0
+        ms_eager = timed(step_resident, args.steps)
+    launches = (_lib.launch_count() - n0) // args.steps
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e_eager = timed(step_e2e, args.steps)
+
+    # ---- the same step captured once as a CUDA graph and replayed (removes ~1300 host launches per step)
+    ms, ms_e2e, graphed = ms_eager, ms_e2e_eager, False
+    if not args.no_graph:
+        try:
+            z_static = torch.randn(B, 512, device=dev)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    generator_step(G, z_static, cot)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss_static, gz_static = generator_step(G, z_static, cot)
+
+            def step_graph():
+                graph.replay()
+
+            def step_graph_e2e():
+                z_static.copy_(z_host, non_blocking=True)
+                graph.replay()
+                loss_host.copy_(loss_static, non_blocking=True)
+                gz_host.copy_(gz_static, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+            for _ in range(3):
+                step_graph()
+            with ClockSampler(local) as clocks:
+                ms = timed(step_graph, args.steps)
+            ms_e2e = timed(step_graph_e2e, args.steps)
+            graphed = True
+        except Exception as ex:                         # report, never hide: fall back to the eager numbers
+            print(f"[bench] CUDA graph capture failed, reporting eager timings: {ex!r}", file=sys.stderr)
+            ms, ms_e2e = ms_eager, ms_e2e_eager
 
     # ---- live per-kernel timing of the stylerenderer_b200 launches inside a timed region (rank 0)
     roof = None
@@ -373,6 +413,9 @@ def main():
                 "config": {"workload": "StyleGAN2 generator 256x256, batch 32/GPU, random z, fwd+bwd (BASELINE.json configs[1])",
                            "global_batch": world * B, "parallelism": f"dp{world} (image-sharded, no collective)",
                            "conv_backend": layers.get_conv_backend(),
+                           "execution": "cuda_graph_replay" if graphed else "eager",
+                           "eager_images_per_s": round(world * B * args.steps / (ms_eager * 1e-3), 2),
+                           "eager_host_enqueue_ms_per_step": round(cpu_enqueue_ms, 2),
                            "l2": "activations per step (several GB) exceed the 126 MB L2; no explicit flush",
                            "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32)},
                 "clocks": clocks.summary(),

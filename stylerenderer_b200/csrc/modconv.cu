@@ -320,17 +320,14 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 // tensors, so they are MN-major for the tensor core: a TMA box {32 channels, TW, TH, TN} lands as 64 K-rows of
 // 128 bytes (two 4-row swizzle atoms per K=8 instruction); M = 128 output channels = 4 such column blocks, LBO apart.
 // Split-K over pixel tiles (gridDim.z) with fp32 atomic accumulation into the zero-initialised result.
-constexpr int WG_BK = 64;                              // pixels per pipeline stage
-constexpr int WG_COLBLK_BYTES = WG_BK * 128;           // one 32-channel column block of a stage
-constexpr int WG_N = 128;
-constexpr int WG_STAGE_BYTES = 2 * 4 * WG_COLBLK_BYTES;
-constexpr int WG_STAGES = 3;
+// Two shapes: N = 256 input channels x 32 pixels per stage (4 stages; 96 B/clk of shared-memory operand traffic) when
+// cin % 256 == 0, else N = 128 x 64 pixels per stage (3 stages).
 
 struct WgradKParams {
     int tw_log2, th_log2, tn_log2;                     // K tile = 64 pixels
     int tiles_x, tiles_y, tiles_n;
     int ktiles_per_split;
-    int n_tiles;                                       // cin / 128
+    int n_tiles;                                       // cin / WG_N
     int g_stride, x_stride;
     int g_dy[9], g_dx[9], x_dy[9], x_dx[9], tap_out[9];
     int taps_total, cin;
@@ -350,10 +347,14 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, 
     return d;
 }
 
+template <int WG_N, int WG_BK, int WG_STAGES>
 __global__ void __launch_bounds__(kConvThreads, 1)
 wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
                   const WgradKParams p)
 {
+    constexpr int WG_COLBLK_BYTES = WG_BK * 128;           // one 32-channel column block of a stage
+    constexpr int NB = WG_N / 32;                          // column blocks of the B (activation) operand
+    constexpr int WG_STAGE_BYTES = (4 + NB) * WG_COLBLK_BYTES;
     constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                 ((uint32_t)(WG_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);   // MN-major A and B
     extern __shared__ uint8_t smem_raw[];
@@ -400,12 +401,13 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
                 uint8_t *sa = smem + s * WG_STAGE_BYTES, *sb = sa + 4 * WG_COLBLK_BYTES;
                 mbar_expect_tx(&full_bar[s], WG_STAGE_BYTES);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 4; ++j)
                     tma_load_4d(sa + j * WG_COLBLK_BYTES, &tmap_g, &full_bar[s], m_tile * BLOCK_M + j * 32,
                                 gx0 * p.g_stride + p.g_dx[tap], gy0 * p.g_stride + p.g_dy[tap], n0);
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
                     tma_load_4d(sb + j * WG_COLBLK_BYTES, &tmap_x, &full_bar[s], n_tile * WG_N + j * 32,
                                 gx0 * p.x_stride + p.x_dx[tap], gy0 * p.x_stride + p.x_dy[tap], n0);
-                }
             }
         }
     } else if (warp == 1) {
@@ -661,10 +663,18 @@ extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
     EncodeTiledFn enc = encode_tiled();
     if (!enc) { set_error("wgrad: cuTensorMapEncodeTiled not available from the driver"); return SR_ERR_DRIVER; }
     cudaStream_t st = (cudaStream_t)stream;
+    const bool wide = (a->cin % 256 == 0);                 // N = 256, 32 pixels per stage
     int tw, th, tn;
-    if (a->grid_w > 8) { tw = 16; th = 4; tn = 1; }
-    else if (a->grid_w > 4) { tw = 8; th = 8; tn = 1; }
-    else { tw = 4; th = 4; tn = 4; }
+    if (wide) {
+        if (a->grid_w > 8) { tw = 16; th = 2; tn = 1; }
+        else if (a->grid_w > 4) { tw = 8; th = 4; tn = 1; }
+        else { tw = 4; th = 4; tn = 2; }
+    } else {
+        if (a->grid_w > 8) { tw = 16; th = 4; tn = 1; }
+        else if (a->grid_w > 4) { tw = 8; th = 8; tn = 1; }
+        else { tw = 4; th = 4; tn = 4; }
+    }
+    const int wg_n = wide ? 256 : 128;
     CUtensorMap tg, tx;
     auto make_map = [&](CUtensorMap *m, const float *base, int64_t hh, int64_t ww, int64_t cc, int stride) -> int {
         cuuint64_t dims[4] = {(cuuint64_t)cc, (cuuint64_t)ww, (cuuint64_t)hh, (cuuint64_t)a->batch};
@@ -688,7 +698,7 @@ extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
     p.tiles_x = (int)((a->grid_w + tw - 1) / tw);
     p.tiles_y = (int)((a->grid_h + th - 1) / th);
     p.tiles_n = (int)((a->batch + tn - 1) / tn);
-    p.n_tiles = (int)(a->cin / WG_N);
+    p.n_tiles = (int)(a->cin / wg_n);
     const int mn_tiles = (int)(a->cout / BLOCK_M) * p.n_tiles;
     const long long total_kt = (long long)p.tiles_x * p.tiles_y * p.tiles_n;
     // split K so that about two waves of CTAs cover the 148 SMs
@@ -704,18 +714,31 @@ extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
     }
     p.taps_total = (int)a->taps_total; p.cin = (int)a->cin;
     p.dw = a->dw;
-    const size_t smem = 1024 + (size_t)WG_STAGES * WG_STAGE_BYTES + 256;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        configured = true;
-    }
     if (a->zero_init) {
         cudaError_t e = cudaMemsetAsync(a->dw, 0, sizeof(float) * (size_t)a->cout * a->taps_total * a->cin, st);
         if (e != cudaSuccess) { set_error("wgrad: memset: %s", cudaGetErrorString(e)); return (int)e; }
     }
-    wgrad_tf32_kernel<<<dim3((unsigned)mn_tiles, (unsigned)a->num_taps, (unsigned)splits), kConvThreads, smem, st>>>(tg, tx, p);
+    const dim3 grid((unsigned)mn_tiles, (unsigned)a->num_taps, (unsigned)splits);
+    static bool configured[2] = {false, false};
+    if (wide) {
+        auto kern = wgrad_tf32_kernel<256, 32, 4>;
+        const size_t smem = 1024 + (size_t)4 * (4 + 8) * 32 * 128 + 256;
+        if (!configured[0]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { set_error("wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+            configured[0] = true;
+        }
+        kern<<<grid, kConvThreads, smem, st>>>(tg, tx, p);
+    } else {
+        auto kern = wgrad_tf32_kernel<128, 64, 3>;
+        const size_t smem = 1024 + (size_t)3 * (4 + 4) * 64 * 128 + 256;
+        if (!configured[1]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { set_error("wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+            configured[1] = true;
+        }
+        kern<<<grid, kConvThreads, smem, st>>>(tg, tx, p);
+    }
     count_launch();
     return check_launch("sr_conv_wgrad_tf32");
 }
