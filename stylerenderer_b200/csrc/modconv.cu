@@ -25,6 +25,7 @@
 // torch's default cudnn.allow_tf32 = True.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace sr {
 namespace {
@@ -437,7 +438,9 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
             uint32_t r[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(dst + c * 32 + j, __uint_as_float(r[j]));
+            for (int j = 0; j < 32; j += 4)            // 128-bit vector reduction: a quarter of the L2 transactions
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dst + c * 32 + j), "f"(__uint_as_float(r[j])),
+                             "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3])) : "memory");
         }
         tcgen05_fence_before();
     }
@@ -663,7 +666,8 @@ extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
     EncodeTiledFn enc = encode_tiled();
     if (!enc) { set_error("wgrad: cuTensorMapEncodeTiled not available from the driver"); return SR_ERR_DRIVER; }
     cudaStream_t st = (cudaStream_t)stream;
-    const bool wide = (a->cin % 256 == 0);                 // N = 256, 32 pixels per stage
+    static const bool allow_wide = getenv("SR_WGRAD_WIDE") != nullptr;      // experimental N = 256 shape (measured slower in round 1)
+    const bool wide = allow_wide && (a->cin % 256 == 0);   // N = 256, 32 pixels per stage
     int tw, th, tn;
     if (wide) {
         if (a->grid_w > 8) { tw = 16; th = 2; tn = 1; }
