@@ -27,7 +27,7 @@ extern "C" {
 #define SR_ERR_DRIVER (-3)
 
 /* ABI version (bumped on any signature change) and last error text. */
-int sr_abi_version(void);
+int sr_abi_version(void);   /* currently 2 */
 const char *sr_last_error(void);
 /* Number of kernel launches issued by this library in this process (bench.py's gpu_launches). */
 int64_t sr_launch_count(void);
@@ -147,6 +147,11 @@ typedef struct sr_conv_args {
     const float *rowscale, *scale2, *bias, *noise, *noise_weight, *stylemap;
     int64_t noise_batch_stride, stylemap_batch_stride;
     float alpha, gain;
+    /* fused ToRGB (reference model.py:56-69): rgb_out[n,y,x,k] = sum_co out[n,y,x,co] * rgb_weight[n,k,co], k < 3;
+     * rgb_weight [batch,3,cout] are the per-sample modulated 1x1 weights, rgb_out [batch,out_h,out_w,3] is zeroed by
+     * the call.  Both NULL = off. */
+    const float *rgb_weight;
+    float *rgb_out;
 } sr_conv_args;
 int sr_conv_igemm_tf32(const sr_conv_args *args, void *stream);
 /* `count` (<= 4) such contractions that share every tensor, stride and epilogue and differ only in tap list,
@@ -194,6 +199,11 @@ int sr_conv_weight_prep_tf32(float *dst, const float *w, float scale, int64_t co
 int sr_blur_nhwc_styled_f32(float *out, const float *x, const float *taps, int64_t batch, int64_t in_h, int64_t in_w,
                             int64_t channels, int pad0, int pad1, const float *noise, int64_t noise_batch_stride,
                             const float *noise_weight, const float *bias, float alpha, float gain, void *stream);
+/* same, plus a second output out2 = tf32_round(out * scale2[n,c]) (the next layer's modulated GEMM operand). */
+int sr_blur_nhwc_styled2_f32(float *out, float *out2, const float *scale2, const float *x, const float *taps, int64_t batch,
+                             int64_t in_h, int64_t in_w, int64_t channels, int pad0, int pad1, const float *noise,
+                             int64_t noise_batch_stride, const float *noise_weight, const float *bias, float alpha,
+                             float gain, void *stream);
 
 /* Backward prologue of a StyledConv block, one pass over (gy, y) [batch, pixels, channels]:
  *   g_pre = gain * (y > 0 ? gy : alpha*gy)                       (reference op/fused_act.py:27-31)
@@ -205,6 +215,17 @@ int sr_styled_bwd_prologue_f32(float *ga, float *g_bias, float *g_noise_w, float
                                const float *noise, int64_t noise_batch_stride, const float *noise_weight,
                                const float *bias, const float *d, int64_t batch, int64_t pixels, int64_t channels,
                                float alpha, float gain, void *stream);
+/* Chained form: the incoming gradient is assembled on the fly from up to three sources,
+ *   g_total = gy (or 0) + gxs * s_next[n,c] + sum_k g_rgb[n,p,k] * rgb_weight[n,k,c]
+ * (gxs = gradient w.r.t. the NEXT layer's modulated input, g_rgb = gradient of the fused ToRGB output), and the
+ * reductions those sources need are produced in the same pass:
+ *   ds_next[n,c] = sum_p gxs * y,   d_rgb_weight[n,k,c] = sum_p g_rgb[n,p,k] * y[n,p,c].
+ * Everything else as sr_styled_bwd_prologue_f32.  Absent sources are NULL. */
+int sr_styled_bwd_prologue2_f32(float *ga, float *g_bias, float *g_noise_w, float *e, float *ds_next, float *d_rgb_weight,
+                                const float *gy, const float *gxs, const float *s_next, const float *g_rgb,
+                                const float *rgb_weight, const float *y, const float *noise, int64_t noise_batch_stride,
+                                const float *noise_weight, const float *bias, const float *d, int64_t batch,
+                                int64_t pixels, int64_t channels, float alpha, float gain, void *stream);
 
 /* out[n,p,c] = a[n,p,c] * scale[n,c] (optionally rounded to tf32), dot[n,c] = sum_p a[n,p,c] * other[n,p,c];
  * out or dot may be NULL; dot is zeroed by the call. */

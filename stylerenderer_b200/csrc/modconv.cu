@@ -137,6 +137,8 @@ struct ConvKParams {
     long long noise_img_stride, noise_row_stride, noise_pix_stride;
     long long map_img_stride, map_plane_stride;
     float alpha, gain;
+    const float *rgb_w;                     // fused ToRGB: [batch, 3, cout] per-sample 1x1 weights (or nullptr)
+    float *rgb_out;                         // [batch, out_h, out_w, 3], += sum_c out[..., c] * rgb_w[n, k, c]
 };
 
 struct TileCoord { int phase, gx0, gy0, n0, n_tile; };
@@ -266,6 +268,7 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     pre_add += __ldg(m + p.map_plane_stride);
                 }
             }
+            float rgb[3] = {0.0f, 0.0f, 0.0f};
             mbar_wait(&tmem_full_bar[acc], acc_par);
             tcgen05_fence_after();
 #pragma unroll 1
@@ -295,6 +298,14 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                             }
                         }
                         o1[j] = make_float4(v[0], v[1], v[2], v[3]);
+                        if (p.rgb_w) {                      // ToRGB rides the epilogue: 3 dot products over the channel chunk
+                            const float *w0 = p.rgb_w + (long long)n * 3 * p.cout + ch0 + 4 * j;
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                const float4 ww = __ldg(reinterpret_cast<const float4 *>(w0 + (long long)k * p.cout));
+                                rgb[k] = fmaf(v[0], ww.x, fmaf(v[1], ww.y, fmaf(v[2], ww.z, fmaf(v[3], ww.w, rgb[k]))));
+                            }
+                        }
                         if (o2) {
                             const float4 s = __ldg(s2 + j);
                             o2[j] = make_float4(round_tf32(v[0] * s.x), round_tf32(v[1] * s.y), round_tf32(v[2] * s.z),
@@ -306,6 +317,11 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);   // this warp no longer reads accumulator `acc`
+            if (p.rgb_w && valid) {
+                float *dst = p.rgb_out + ((long long)n * p.map_plane_stride + (long long)gy * p.noise_row_stride +
+                                          (long long)gx * p.noise_pix_stride + ph.noise_offset) * 3;
+                atomicAdd(dst, rgb[0]); atomicAdd(dst + 1, rgb[1]); atomicAdd(dst + 2, rgb[2]);
+            }
         }
     }
     __syncthreads();
@@ -645,6 +661,12 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
     p.map_plane_stride = (long long)a->out_h * a->out_w;
     p.map_img_stride = a->stylemap_batch_stride;
     p.alpha = a->alpha; p.gain = a->gain;
+    p.rgb_w = a->rgb_weight; p.rgb_out = a->rgb_out;
+    SR_REQUIRE(!p.rgb_w || p.rgb_out, "conv: rgb_weight needs rgb_out");
+    if (p.rgb_w) {
+        cudaError_t e = cudaMemsetAsync(p.rgb_out, 0, sizeof(float) * 3 * (size_t)(a->batch * a->out_h * a->out_w), st);
+        if (e != cudaSuccess) { set_error("conv: memset(rgb_out): %s", cudaGetErrorString(e)); return (int)e; }
+    }
 
     int rc;
     if (block_n == 256) rc = launch_conv<256, 4>(ta, tb, p, st);

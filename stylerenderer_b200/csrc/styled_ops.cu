@@ -46,6 +46,10 @@ struct PrologueParams {
     float *g_noise_w;             // [1]      += sum g_pre * noise
     float *e;                     // [B,C]    += sum g_pre * (pre_activation - noise_w*noise - bias)   (nullptr: skip)
     const float *gy, *y, *noise, *noise_w, *bias, *d;
+    // chained gradient sources (all optional): g_total = gy + gxs * s_next[b,c] + sum_k g_rgb[b,p,k] * rgb_w[b,k,c]
+    const float *gxs, *s_next, *g_rgb, *rgb_w;
+    float *ds_next;               // [B,C]   += sum_p gxs * y
+    float *d_rgb_w;               // [B,3,C] += sum_p g_rgb[b,p,k] * y
     long long noise_bstride;
     int pixels, C4, chunks_per_image, pix_per_chunk;
     float alpha, gain;
@@ -61,7 +65,17 @@ styled_bwd_prologue_kernel(const PrologueParams p)
     const int c4 = threadIdx.x % C4, pl = threadIdx.x / C4;
     const int b = blockIdx.x / p.chunks_per_image, chunk = blockIdx.x % p.chunks_per_image;
     const int p0 = chunk * p.pix_per_chunk, p1 = min(p.pixels, p0 + p.pix_per_chunk);
-    const float4 *gy = reinterpret_cast<const float4 *>(p.gy) + (long long)b * p.pixels * C4 + c4;
+    const float4 *gy = p.gy ? reinterpret_cast<const float4 *>(p.gy) + (long long)b * p.pixels * C4 + c4 : nullptr;
+    const float4 *gxs = p.gxs ? reinterpret_cast<const float4 *>(p.gxs) + (long long)b * p.pixels * C4 + c4 : nullptr;
+    const float *grgb = p.g_rgb ? p.g_rgb + (long long)b * p.pixels * 3 : nullptr;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 sn = gxs ? __ldg(reinterpret_cast<const float4 *>(p.s_next) + (long long)b * C4 + c4) : zero4;
+    float4 wrgb[3] = {zero4, zero4, zero4};
+    if (grgb) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) wrgb[k] = __ldg(reinterpret_cast<const float4 *>(p.rgb_w) + ((long long)b * 3 + k) * C4 + c4);
+    }
+    float4 a_ds = zero4, a_wb[3] = {zero4, zero4, zero4};
     const float4 *y = reinterpret_cast<const float4 *>(p.y) + (long long)b * p.pixels * C4 + c4;
     float4 *ga = reinterpret_cast<float4 *>(p.ga) + (long long)b * p.pixels * C4 + c4;
     const float *nz = p.noise ? p.noise + (long long)b * p.noise_bstride : nullptr;
@@ -73,8 +87,22 @@ styled_bwd_prologue_kernel(const PrologueParams p)
     float4 a_bias = make_float4(0.f, 0.f, 0.f, 0.f), a_e = a_bias;
     float a_nw = 0.0f;
     for (int px = p0 + pl; px < p1; px += lanes_p) {
-        const float4 g = ld_stream4(reinterpret_cast<const float *>(gy + (long long)px * C4));
         const float4 yy = __ldg(y + (long long)px * C4);
+        float4 g = gy ? ld_stream4(reinterpret_cast<const float *>(gy + (long long)px * C4)) : zero4;
+        if (gxs) {
+            const float4 gx = ld_stream4(reinterpret_cast<const float *>(gxs + (long long)px * C4));
+            f4_fma(g, gx, sn);
+            f4_fma(a_ds, gx, yy);
+        }
+        if (grgb) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float gk = __ldg(grgb + (long long)px * 3 + k);
+                const float4 g4 = make_float4(gk, gk, gk, gk);
+                f4_fma(g, g4, wrgb[k]);
+                f4_fma(a_wb[k], g4, yy);
+            }
+        }
         const float n = nz ? __ldg(nz + px) : 0.0f;
         float4 gp, u;
         // reference op/fused_bias_act_kernel.cu:31: (ref > 0 ? g : g*alpha) * scale
@@ -97,6 +125,12 @@ styled_bwd_prologue_kernel(const PrologueParams p)
     (void)pos; (void)neg;
     block_reduce_quads(a_bias, s_red, c4, pl, C4, lanes_p, p.g_bias);
     if (p.e) block_reduce_quads(a_e, s_red, c4, pl, C4, lanes_p, p.e + (long long)b * C4 * 4);
+    if (gxs) block_reduce_quads(a_ds, s_red, c4, pl, C4, lanes_p, p.ds_next + (long long)b * C4 * 4);
+    if (grgb) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            block_reduce_quads(a_wb[k], s_red, c4, pl, C4, lanes_p, p.d_rgb_w + ((long long)b * 3 + k) * C4 * 4);
+    }
     if (p.noise) {
         a_nw = warp_sum(a_nw);
         if ((threadIdx.x & 31) == 0) s_nw[threadIdx.x >> 5] = a_nw;
@@ -164,31 +198,49 @@ bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 using namespace sr;
 
-extern "C" int sr_styled_bwd_prologue_f32(float *ga, float *g_bias, float *g_noise_w, float *e, const float *gy,
-                                          const float *y, const float *noise, int64_t noise_batch_stride,
-                                          const float *noise_weight, const float *bias, const float *d, int64_t batch,
-                                          int64_t pixels, int64_t channels, float alpha, float gain, void *stream)
+extern "C" int sr_styled_bwd_prologue2_f32(float *ga, float *g_bias, float *g_noise_w, float *e, float *ds_next,
+                                           float *d_rgb_weight, const float *gy, const float *gxs, const float *s_next,
+                                           const float *g_rgb, const float *rgb_weight, const float *y, const float *noise,
+                                           int64_t noise_batch_stride, const float *noise_weight, const float *bias,
+                                           const float *d, int64_t batch, int64_t pixels, int64_t channels, float alpha,
+                                           float gain, void *stream)
 {
-    SR_REQUIRE(ga && g_bias && gy && y, "styled_bwd_prologue: null pointer");
+    SR_REQUIRE(ga && g_bias && y && (gy || gxs || g_rgb), "styled_bwd_prologue: null pointer / no gradient source");
     SR_REQUIRE(ok_channels(channels), "styled_bwd_prologue: channels must be 4*k with k dividing 256 (got %lld)", (long long)channels);
-    SR_REQUIRE(al16(ga) && al16(gy) && al16(y) && (!bias || al16(bias)) && (!d || al16(d)), "styled_bwd_prologue: 16-byte alignment");
+    SR_REQUIRE(al16(ga) && (!gy || al16(gy)) && al16(y) && (!bias || al16(bias)) && (!d || al16(d)) && (!gxs || al16(gxs)) &&
+               (!s_next || al16(s_next)) && (!rgb_weight || al16(rgb_weight)), "styled_bwd_prologue: 16-byte alignment");
     SR_REQUIRE(!noise || (noise_weight && g_noise_w), "styled_bwd_prologue: noise needs its weight and gradient slot");
+    SR_REQUIRE(!gxs || (s_next && ds_next), "styled_bwd_prologue: gxs needs s_next and ds_next");
+    SR_REQUIRE(!g_rgb || (rgb_weight && d_rgb_weight), "styled_bwd_prologue: g_rgb needs rgb_weight and d_rgb_weight");
     SR_REQUIRE(alpha > 0 && gain > 0, "styled_bwd_prologue: alpha, gain must be positive");
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t er = cudaMemsetAsync(g_bias, 0, sizeof(float) * (size_t)channels, st);
     if (er == cudaSuccess && g_noise_w) er = cudaMemsetAsync(g_noise_w, 0, sizeof(float), st);
     if (er == cudaSuccess && e) er = cudaMemsetAsync(e, 0, sizeof(float) * (size_t)(batch * channels), st);
+    if (er == cudaSuccess && gxs) er = cudaMemsetAsync(ds_next, 0, sizeof(float) * (size_t)(batch * channels), st);
+    if (er == cudaSuccess && g_rgb) er = cudaMemsetAsync(d_rgb_weight, 0, sizeof(float) * (size_t)(batch * 3 * channels), st);
     if (er != cudaSuccess) { set_error("styled_bwd_prologue: memset: %s", cudaGetErrorString(er)); return (int)er; }
     if (batch == 0 || pixels == 0) return SR_OK;
     PrologueParams p;
     p.ga = ga; p.g_bias = g_bias; p.g_noise_w = g_noise_w; p.e = e; p.gy = gy; p.y = y;
     p.noise = noise; p.noise_w = noise_weight; p.bias = bias; p.d = d; p.noise_bstride = noise_batch_stride;
+    p.gxs = gxs; p.s_next = s_next; p.g_rgb = g_rgb; p.rgb_w = rgb_weight; p.ds_next = ds_next; p.d_rgb_w = d_rgb_weight;
     p.pixels = (int)pixels; p.C4 = (int)(channels / 4);
     p.chunks_per_image = pick_chunks(batch, pixels, p.C4, &p.pix_per_chunk);
     p.alpha = alpha; p.gain = gain;
     styled_bwd_prologue_kernel<<<(unsigned)(batch * p.chunks_per_image), kThreads, 0, st>>>(p);
     count_launch();
     return check_launch("sr_styled_bwd_prologue_f32");
+}
+
+extern "C" int sr_styled_bwd_prologue_f32(float *ga, float *g_bias, float *g_noise_w, float *e, const float *gy,
+                                          const float *y, const float *noise, int64_t noise_batch_stride,
+                                          const float *noise_weight, const float *bias, const float *d, int64_t batch,
+                                          int64_t pixels, int64_t channels, float alpha, float gain, void *stream)
+{
+    return sr_styled_bwd_prologue2_f32(ga, g_bias, g_noise_w, e, nullptr, nullptr, gy, nullptr, nullptr, nullptr, nullptr, y,
+                                       noise, noise_batch_stride, noise_weight, bias, d, batch, pixels, channels, alpha, gain,
+                                       stream);
 }
 
 extern "C" int sr_scale_dot_nhwc_f32(float *out, float *dot, const float *a, const float *other, const float *scale,

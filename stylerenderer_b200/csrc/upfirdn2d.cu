@@ -170,6 +170,12 @@ upfirdn2d_tile_kernel(float *__restrict__ out, const float *__restrict__ x, cons
 // take consecutive channel quads, so every load/store instruction of a warp is one contiguous 512-byte run;
 // a KH-row x (KW+1)-column register window slides down the strip, so each input element is fetched from
 // L1/L2 ~2.5 times per output instead of KH*KW times.
+__device__ __forceinline__ float round_tf32_(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
 struct NhwcGeom {
     int64_t major, total_threads;
     int in_h, in_w, out_h, out_w, c4, pad_x0, pad_y0, strips_y, pairs_x, rows_per_strip;
@@ -178,6 +184,8 @@ struct NhwcGeom {
     const float *noise, *noise_weight, *bias;
     long long noise_bstride;
     float alpha, gain;
+    float *out2;                  // optional: tf32(y * scale2[n,c])
+    const float *scale2;
 };
 
 template <int KH, int KW, bool STYLED>
@@ -213,6 +221,8 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
         if (g.noise) { nw = __ldg(g.noise_weight); nz = g.noise + (int64_t)n * g.noise_bstride; }
         if (g.bias) bias4 = __ldg(reinterpret_cast<const float4 *>(g.bias) + c);
     }
+    float4 sc2 = zero;
+    if (STYLED && g.out2) sc2 = __ldg(reinterpret_cast<const float4 *>(g.scale2) + (int64_t)n * g.c4 + c);
 
     float4 win[KH][KW + 1];
     auto load_row = [&](float4 (&row)[KW + 1], int iy) {
@@ -254,6 +264,20 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
         float4 *dst = yout + ((int64_t)oy * g.out_w + ox0) * g.c4;
         dst[0] = acc[0];
         if (ox0 + 1 < g.out_w) dst[g.c4] = acc[1];
+        if (STYLED && g.out2) {
+            float4 *dst2 = reinterpret_cast<float4 *>(g.out2) + (int64_t)n * g.out_h * g.out_w * g.c4 + c +
+                           ((int64_t)oy * g.out_w + ox0) * g.c4;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (ox0 + j >= g.out_w) break;
+                float4 o;
+                o.x = round_tf32_(acc[j].x * sc2.x);
+                o.y = round_tf32_(acc[j].y * sc2.y);
+                o.z = round_tf32_(acc[j].z * sc2.z);
+                o.w = round_tf32_(acc[j].w * sc2.w);
+                dst2[(int64_t)j * g.c4] = o;
+            }
+        }
 #pragma unroll
         for (int a = 0; a < KH - 1; ++a)
 #pragma unroll
@@ -346,9 +370,11 @@ int launch_tile(float *out, const float *x, const float *taps, int64_t major, in
 
 int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, int in_h, int in_w, int oh, int ow,
                 int64_t minor, int pad_x0, int pad_y0, bool styled, const float *noise, long long noise_bstride,
-                const float *noise_weight, const float *bias, float alpha, float gain, cudaStream_t st)
+                const float *noise_weight, const float *bias, float alpha, float gain, cudaStream_t st,
+                float *out2 = nullptr, const float *scale2 = nullptr)
 {
     NhwcGeom g;
+    g.out2 = out2; g.scale2 = scale2;
     g.major = major; g.in_h = in_h; g.in_w = in_w; g.out_h = oh; g.out_w = ow;
     g.c4 = (int)(minor / 4); g.pad_x0 = pad_x0; g.pad_y0 = pad_y0;
     g.rows_per_strip = oh >= 64 ? 16 : (oh >= 16 ? 8 : 4);
@@ -370,24 +396,35 @@ int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, in
 
 using namespace sr;
 
+extern "C" int sr_blur_nhwc_styled2_f32(float *out, float *out2, const float *scale2, const float *x, const float *taps,
+                                        int64_t batch, int64_t in_h, int64_t in_w, int64_t channels, int pad0, int pad1,
+                                        const float *noise, int64_t noise_batch_stride, const float *noise_weight,
+                                        const float *bias, float alpha, float gain, void *stream)
+{
+    SR_REQUIRE(out && x && taps, "blur_nhwc_styled: null pointer");
+    SR_REQUIRE(channels >= 4 && channels % 4 == 0, "blur_nhwc_styled: channels must be a multiple of 4");
+    SR_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out2) |
+                 reinterpret_cast<uintptr_t>(scale2)) & 15u) == 0 &&
+               (!bias || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0), "blur_nhwc_styled: 16-byte alignment");
+    SR_REQUIRE(!noise || noise_weight, "blur_nhwc_styled: noise needs noise_weight");
+    SR_REQUIRE(!out2 || scale2, "blur_nhwc_styled: out2 needs scale2");
+    const int64_t oh = in_h + pad0 + pad1 - 4 + 1, ow = in_w + pad0 + pad1 - 4 + 1;
+    SR_REQUIRE(oh >= 1 && ow >= 1, "blur_nhwc_styled: FIR larger than the padded input");
+    if (batch == 0) return SR_OK;
+    int rc = launch_nhwc(out, x, taps, batch, (int)in_h, (int)in_w, (int)oh, (int)ow, channels, pad0, pad0, true, noise,
+                         noise_batch_stride, noise_weight, bias, alpha, gain, (cudaStream_t)stream, out2, scale2);
+    if (rc != SR_OK) { set_error("blur_nhwc_styled: problem too large"); return rc; }
+    count_launch();
+    return check_launch("sr_blur_nhwc_styled_f32");
+}
+
 extern "C" int sr_blur_nhwc_styled_f32(float *out, const float *x, const float *taps, int64_t batch, int64_t in_h,
                                        int64_t in_w, int64_t channels, int pad0, int pad1, const float *noise,
                                        int64_t noise_batch_stride, const float *noise_weight, const float *bias,
                                        float alpha, float gain, void *stream)
 {
-    SR_REQUIRE(out && x && taps, "blur_nhwc_styled: null pointer");
-    SR_REQUIRE(channels >= 4 && channels % 4 == 0, "blur_nhwc_styled: channels must be a multiple of 4");
-    SR_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(x)) & 15u) == 0 &&
-               (!bias || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0), "blur_nhwc_styled: 16-byte alignment");
-    SR_REQUIRE(!noise || noise_weight, "blur_nhwc_styled: noise needs noise_weight");
-    const int64_t oh = in_h + pad0 + pad1 - 4 + 1, ow = in_w + pad0 + pad1 - 4 + 1;
-    SR_REQUIRE(oh >= 1 && ow >= 1, "blur_nhwc_styled: FIR larger than the padded input");
-    if (batch == 0) return SR_OK;
-    int rc = launch_nhwc(out, x, taps, batch, (int)in_h, (int)in_w, (int)oh, (int)ow, channels, pad0, pad0, true, noise,
-                         noise_batch_stride, noise_weight, bias, alpha, gain, (cudaStream_t)stream);
-    if (rc != SR_OK) { set_error("blur_nhwc_styled: problem too large"); return rc; }
-    count_launch();
-    return check_launch("sr_blur_nhwc_styled_f32");
+    return sr_blur_nhwc_styled2_f32(out, nullptr, nullptr, x, taps, batch, in_h, in_w, channels, pad0, pad1, noise,
+                                    noise_batch_stride, noise_weight, bias, alpha, gain, stream);
 }
 
 extern "C" int sr_upfirdn2d_f32(float *out, const float *x, const float *taps,

@@ -89,3 +89,142 @@ def styled_conv(mod_conv, noise_mod, act_mod, x, style, noise):
     taps = mod_conv.blur.kernel if mod_conv.upsample else noise_mod.weight
     return StyledConvTC.apply(x, mod_conv.weight, s, d, noise, noise_mod.weight, act_mod.bias, mod_conv.scale,
                               mod_conv.upsample, taps, act_mod.negative_slope, act_mod.scale)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Chained generator: consecutive StyledConv blocks hand each other the ALREADY MODULATED tf32 operand (written by the
+# producer's epilogue), ToRGB rides the conv epilogue, and in the backward the gradient of a block is assembled inside
+# its prologue pass from the next block's dgrad output and the ToRGB gradient -- no stand-alone modulate / scale / 1x1
+# conv / gradient-accumulation passes remain.
+class ModulateTC(Function):
+    """xs = tf32(x * s[b,c]) as an autograd node (used once, for the constant 4x4 input)."""
+
+    @staticmethod
+    def forward(ctx, x, s):
+        x_nhwc = to_nhwc(x)
+        s = s.contiguous()
+        ctx.save_for_backward(x_nhwc, s)
+        return from_nhwc(tc.modulate(x_nhwc, s))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gxs):
+        x_nhwc, s = ctx.saved_tensors
+        gx, gs = tc.scale_dot(to_nhwc(gxs), x_nhwc, s, False)
+        return from_nhwc(gx), gs
+
+
+class StyledLayerTC(Function):
+    """One StyledConv block of the chain.  Input: xs (already x * s, tf32).  Outputs: (main, rgb) with
+    main = tf32(y * s_next) if s_next is given else y, rgb = sum_c y * rgb_weight (or None)."""
+
+    @staticmethod
+    def forward(ctx, xs, weight, d, noise, noise_weight, act_bias, s_next, rgb_weight, scale, upsample, blur_taps, alpha,
+                gain):
+        ctx.set_materialize_grads(False)                     # unused outputs arrive as None, not as zero tensors
+        xs_nhwc = to_nhwc(xs)
+        b, h, w, cin = xs_nhwc.shape
+        cout = weight.shape[1]
+        d = d.contiguous()
+        wk = tc.weight_prep(weight[0], scale, 0)
+        s_next = s_next.contiguous() if s_next is not None else None
+        rgb_weight = rgb_weight.contiguous() if rgb_weight is not None else None
+        t = rgb = y2 = None
+        if not upsample:
+            y = torch.empty(b, h, w, cout, dtype=torch.float32, device=xs.device)
+            y2 = torch.empty_like(y) if s_next is not None else None
+            rgb = torch.empty(b, h, w, 3, dtype=torch.float32, device=xs.device) if rgb_weight is not None else None
+            tc.conv3x3(xs_nhwc, wk, out=y, epilogue=1, rowscale=d, bias=act_bias, alpha=alpha, gain=gain,
+                       noise=noise.reshape(-1, h, w).contiguous(), noise_weight=noise_weight, out2=y2, scale2=s_next,
+                       rgb_weight=rgb_weight, rgb_out=rgb)
+        else:
+            assert rgb_weight is None
+            t = tc.conv_transpose3x3_s2(xs_nhwc, wk, rowscale=d)
+            if s_next is not None:
+                y, y2 = tc.blur_styled(t, blur_taps, (1, 1), noise, noise_weight, act_bias, alpha, gain, scale2=s_next)
+            else:
+                y = tc.blur_styled(t, blur_taps, (1, 1), noise, noise_weight, act_bias, alpha, gain)
+        ctx.save_for_backward(xs_nhwc, y, t, weight, d, noise, noise_weight, act_bias, blur_taps, s_next, rgb_weight)
+        ctx.cfg = (scale, upsample, alpha, gain)
+        main = from_nhwc(y2 if s_next is not None else y)
+        if rgb is None:
+            rgb = xs.new_zeros(1)
+            ctx.mark_non_differentiable(rgb)
+        return main, rgb
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_main, g_rgb):
+        xs, y, t, weight, d, noise, noise_weight, act_bias, blur_taps, s_next, rgb_weight = ctx.saved_tensors
+        scale, upsample, alpha, gain = ctx.cfg
+        b, h, w, cin = xs.shape
+        cout = y.shape[3]
+        g_main = to_nhwc(g_main) if g_main is not None else None
+        src = dict(gy=None, gxs=None, s_next=None, g_rgb=None, rgb_weight=None)
+        if g_main is not None:
+            if s_next is not None:
+                src.update(gxs=g_main, s_next=s_next)
+            else:
+                src.update(gy=g_main)
+        if rgb_weight is not None and g_rgb is not None:
+            src.update(g_rgb=g_rgb.contiguous(), rgb_weight=rgb_weight)
+        if not upsample:
+            ga, g_bias, g_noise_w, e, ds_next, dwb = tc.bwd_prologue2(y, noise, noise_weight, act_bias, d, alpha, gain, True, **src)
+            dxs = tc.conv3x3(ga, tc.weight_prep(weight[0], scale, 1))
+            dwk = tc.wgrad3x3(ga, xs)
+        else:
+            g_pre, g_bias, g_noise_w, _, ds_next, dwb = tc.bwd_prologue2(y, noise, noise_weight, act_bias, None, alpha, gain,
+                                                                         False, **src)
+            gt = upfirdn2d_raw(g_pre, torch.flip(blur_taps, [0, 1]), 1, 1, 1, 1, 2, 2, 2, 2)
+            ga, e = tc.scale_dot(gt, t, d, True)
+            dxs = tc.conv3x3_s2_gather(ga, tc.weight_prep(weight[0], scale, 2), (h, w))
+            dwk = tc.wgrad_transpose3x3_s2(ga, xs)
+        g_d = e / d
+        g_w = (dwk.view(cout, 3, 3, cin).permute(0, 3, 1, 2) * scale).unsqueeze(0)
+        return (from_nhwc(dxs), g_w, g_d, None, g_noise_w, g_bias, ds_next, dwb, None, None, None, None, None)
+
+
+def chain_supported(gen, x):
+    from . import layers as L
+    if L.get_conv_backend() != "tcgen05" or (torch.is_grad_enabled() and L.double_backward_requested()):
+        return False
+    blocks = [gen.conv1] + list(gen.convs)
+    return all(type(m).__name__ == "StyledConv" and supported(m.conv, x) for m in blocks)
+
+
+def _rgb_weights(to_rgb, style):
+    """Per-sample modulated 1x1 weights of a ToRGB [B,3,C] (reference layers.py:296 with demodulate=False)."""
+    conv = to_rgb.conv
+    s = conv.modulation(style)
+    return (conv.weight[0, :, :, 0, 0] * conv.scale).unsqueeze(0) * s.unsqueeze(1)
+
+
+def generator_chain_forward(gen, latent, noise):
+    """Generator.forward body on the chained tensor-core blocks (same math as reference model.py:169-182)."""
+    blocks = [gen.conv1] + list(gen.convs)
+    lat_idx = list(range(len(blocks)))                       # conv1 -> latent[:,0], convs[j] -> latent[:, j+1]
+    scales = [blk.conv.style_scales(latent[:, li]) for blk, li in zip(blocks, lat_idx)]
+    x0 = gen.input(latent)
+    xs = ModulateTC.apply(x0, scales[0][0])
+    skip = None
+    for k, blk in enumerate(blocks):
+        s_next = scales[k + 1][0] if k + 1 < len(blocks) else None
+        to_rgb, rgb_lat = None, None
+        if k == 0:
+            to_rgb, rgb_lat = gen.to_rgb1, 1
+        elif k % 2 == 0:                                     # after the second conv of every resolution
+            to_rgb, rgb_lat = gen.to_rgbs[k // 2 - 1], k + 1
+        wb = _rgb_weights(to_rgb, latent[:, rgb_lat]) if to_rgb is not None else None
+        b, _, h, w = xs.shape
+        oh, ow = (2 * h, 2 * w) if blk.conv.upsample else (h, w)
+        nz = noise[k]
+        if nz is None:
+            nz = xs.new_empty(b, 1, oh, ow).normal_()
+        taps = blk.conv.blur.kernel if blk.conv.upsample else blk.noise.weight
+        xs, rgb = StyledLayerTC.apply(xs, blk.conv.weight, scales[k][1], nz, blk.noise.weight, blk.activate.bias, s_next, wb,
+                                      blk.conv.scale, blk.conv.upsample, taps, blk.activate.negative_slope,
+                                      blk.activate.scale)
+        if to_rgb is not None:
+            out = rgb.permute(0, 3, 1, 2) + to_rgb.bias
+            skip = out if skip is None else out + to_rgb.upsample(skip)
+    return skip

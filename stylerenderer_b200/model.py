@@ -145,6 +145,10 @@ class Generator(nn.Module):                           # reference model.py:71-18
                 input_is_latent=False, noise=None, randomize_noise=True):
         latent, noise = self._prepare(styles, inject_index, truncation, truncation_latent, input_is_latent, noise,
                                       randomize_noise)
+        if type(self) is Generator and latent.is_cuda and fused.chain_supported(self, self.input.input):
+            # chained tensor-core blocks: modulated operands handed from epilogue to GEMM, ToRGB fused (fused.py)
+            skip = fused.generator_chain_forward(self, latent, noise)
+            return (skip, latent) if return_latents else (skip, None)
         out = self.input(latent)
         out = self.conv1(out, latent[:, 0], noise=noise[0])
         skip = self.to_rgb1(out, latent[:, 1])

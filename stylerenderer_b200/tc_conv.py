@@ -23,7 +23,7 @@ class ConvArgs(ctypes.Structure):           # mirrors `sr_conv_args` in include/
                 ("out", _P), ("out2", _P), ("epilogue", _I32),
                 ("rowscale", _P), ("scale2", _P), ("bias", _P), ("noise", _P), ("noise_weight", _P), ("stylemap", _P),
                 ("noise_batch_stride", _I64), ("stylemap_batch_stride", _I64),
-                ("alpha", _F), ("gain", _F)]
+                ("alpha", _F), ("gain", _F), ("rgb_weight", _P), ("rgb_out", _P)]
 
 
 class WgradArgs(ctypes.Structure):         # mirrors `sr_wgrad_args`
@@ -75,7 +75,8 @@ def modulate(x, style=None):
 
 
 def _fill_args(a, x, wmat, taps, out, in_stride, grid, out_stride, out_origin, epilogue, rowscale, out2, scale2, bias,
-               noise, noise_weight, stylemap, alpha, gain):
+               noise, noise_weight, stylemap, alpha, gain, rgb_weight=None, rgb_out=None):
+    a.rgb_weight, a.rgb_out = _lib.ptr(rgb_weight), _lib.ptr(rgb_out)
     a.in_ = _lib.ptr(x)
     a.batch, a.in_h, a.in_w, a.cin = x.shape
     a.weight = _lib.ptr(wmat)
@@ -103,7 +104,8 @@ def _fill_args(a, x, wmat, taps, out, in_stride, grid, out_stride, out_origin, e
 
 
 def conv_igemm_multi(x, wmat, phases, out, *, in_stride=1, out_stride=1, epilogue=0, rowscale=None, out2=None,
-                     scale2=None, bias=None, noise=None, noise_weight=None, stylemap=None, alpha=0.2, gain=2 ** 0.5):
+                     scale2=None, bias=None, noise=None, noise_weight=None, stylemap=None, alpha=0.2, gain=2 ** 0.5,
+                     rgb_weight=None, rgb_out=None):
     """One persistent launch over up to 4 phases [(taps, grid, out_origin)] sharing all tensors (see conv_igemm)."""
     _check_nhwc(x, "conv input")
     _check_nhwc(out, "conv output")
@@ -111,7 +113,7 @@ def conv_igemm_multi(x, wmat, phases, out, *, in_stride=1, out_stride=1, epilogu
     arr = (ConvArgs * len(phases))()
     for a, (taps, grid, origin) in zip(arr, phases):
         _fill_args(a, x, wmat, taps, out, in_stride, grid, out_stride, origin, epilogue, rowscale, out2, scale2, bias, noise,
-                   noise_weight, stylemap, alpha, gain)
+                   noise_weight, stylemap, alpha, gain, rgb_weight, rgb_out)
     with torch.cuda.device(x.device):
         rc = _lib.lib().sr_conv_igemm_multi_tf32(arr, len(phases), _lib.stream_of(x))
     _lib.check(rc, "sr_conv_igemm_multi_tf32")
@@ -201,19 +203,22 @@ def _noise_args(noise, oh, ow):
     return nz, (0 if nz.shape[0] == 1 else oh * ow)
 
 
-def blur_styled(t, taps, pad, noise, noise_weight, bias, alpha, gain):
-    """NHWC 4x4 FIR + noise + bias + leaky-ReLU*gain in one pass: [B,IH,IW,C] -> [B,OH,OW,C]."""
+def blur_styled(t, taps, pad, noise, noise_weight, bias, alpha, gain, scale2=None):
+    """NHWC 4x4 FIR + noise + bias + leaky-ReLU*gain in one pass: [B,IH,IW,C] -> [B,OH,OW,C];
+    with scale2 [B,C] also returns out2 = tf32(out * scale2) (the next layer's GEMM operand)."""
     _check_nhwc(t, "blur_styled")
     b, ih, iw, c = t.shape
     oh, ow = ih + pad[0] + pad[1] - 3, iw + pad[0] + pad[1] - 3
     out = torch.empty(b, oh, ow, c, dtype=torch.float32, device=t.device)
+    out2 = torch.empty_like(out) if scale2 is not None else None
     nz, nbs = _noise_args(noise, oh, ow)
     with torch.cuda.device(t.device):
-        rc = _lib.lib().sr_blur_nhwc_styled_f32(_lib.ptr(out), _lib.ptr(t), _lib.ptr(taps.contiguous()), b, ih, iw, c,
-                                                pad[0], pad[1], _lib.ptr(nz), nbs, _lib.ptr(noise_weight), _lib.ptr(bias),
-                                                float(alpha), float(gain), _lib.stream_of(t))
-    _lib.check(rc, "sr_blur_nhwc_styled_f32")
-    return out
+        rc = _lib.lib().sr_blur_nhwc_styled2_f32(_lib.ptr(out), _lib.ptr(out2), _lib.ptr(scale2), _lib.ptr(t),
+                                                 _lib.ptr(taps.contiguous()), b, ih, iw, c, pad[0], pad[1], _lib.ptr(nz), nbs,
+                                                 _lib.ptr(noise_weight), _lib.ptr(bias), float(alpha), float(gain),
+                                                 _lib.stream_of(t))
+    _lib.check(rc, "sr_blur_nhwc_styled2_f32")
+    return out if scale2 is None else (out, out2)
 
 
 def bwd_prologue(gy, y, noise, noise_weight, bias, d, alpha, gain, want_e):
@@ -247,3 +252,30 @@ def scale_dot(a, other, scale, round_out, want_out=True):
                                               int(bool(round_out)), _lib.stream_of(a))
     _lib.check(rc, "sr_scale_dot_nhwc_f32")
     return out, dot
+
+
+def bwd_prologue2(y, noise, noise_weight, bias, d, alpha, gain, want_e, gy=None, gxs=None, s_next=None, g_rgb=None,
+                  rgb_weight=None):
+    """Chained backward prologue (sr_styled_bwd_prologue2_f32) -> (ga, g_bias, g_noise_w, e, ds_next, d_rgb_weight)."""
+    _check_nhwc(y, "bwd_prologue2 y")
+    b, h, w, c = y.shape
+    dev = y.device
+    ga = torch.empty_like(y)
+    g_bias = torch.empty(c, dtype=torch.float32, device=dev)
+    g_nw = torch.empty(1, dtype=torch.float32, device=dev)
+    e = torch.empty(b, c, dtype=torch.float32, device=dev) if want_e else None
+    ds_next = torch.empty(b, c, dtype=torch.float32, device=dev) if gxs is not None else None
+    dwb = torch.empty(b, 3, c, dtype=torch.float32, device=dev) if g_rgb is not None else None
+    nz, nbs = _noise_args(noise, h, w)
+    for t_ in (gy, gxs):
+        if t_ is not None:
+            _check_nhwc(t_, "bwd_prologue2 gradient")
+    if g_rgb is not None:
+        assert g_rgb.is_contiguous() and g_rgb.shape == (b, h, w, 3) and rgb_weight.is_contiguous()
+    with torch.cuda.device(dev):
+        rc = _lib.lib().sr_styled_bwd_prologue2_f32(
+            _lib.ptr(ga), _lib.ptr(g_bias), _lib.ptr(g_nw), _lib.ptr(e), _lib.ptr(ds_next), _lib.ptr(dwb), _lib.ptr(gy),
+            _lib.ptr(gxs), _lib.ptr(s_next), _lib.ptr(g_rgb), _lib.ptr(rgb_weight), _lib.ptr(y), _lib.ptr(nz), nbs,
+            _lib.ptr(noise_weight), _lib.ptr(bias), _lib.ptr(d), b, h * w, c, float(alpha), float(gain), _lib.stream_of(y))
+    _lib.check(rc, "sr_styled_bwd_prologue2_f32")
+    return ga, g_bias, g_nw, e, ds_next, dwb

@@ -207,6 +207,53 @@ def test_styled_conv_function_exact_forward(up, shape):
         close(g_, w_.float(), name)
 
 
+@pytest.mark.parametrize("up", [False, True])
+@pytest.mark.parametrize("shape", [(2, 128, 128, 8), (1, 128, 256, 16)])
+def test_styled_layer_chain_exact_forward(up, shape):
+    """The chained block (pre-modulated input, second output for the next layer, fused ToRGB) against fp64 autograd."""
+    import torch.nn.functional as F
+    from stylerenderer_b200 import fused
+    b, cin, cout, r = shape
+    scale, alpha, gain = 2.0 ** -5, 0.2, 2 ** 0.5
+    x, w, s, d, noise, nw, bias, gy = _exact_inputs(b, cin, cout, r, up)
+    g = torch.Generator().manual_seed(77)
+    xs = x * s.view(b, cin, 1, 1)                                          # exact (s is a power of two)
+    s_next = torch.rand(b, cout, generator=g) + 0.5
+    wb = torch.randn(b, 3, cout, generator=g) * 0.1 if not up else None
+    ro = 2 * r if up else r
+    g_rgb = torch.randn(b, ro, ro, 3, generator=g)
+    taps = torch.tensor([1., 3., 3., 1.])
+    taps = (taps[None] * taps[:, None]) / 16
+    leaves = [t.double().requires_grad_(True) for t in ([xs, w, d, nw, bias, s_next] + ([wb] if wb is not None else []))]
+    xd, wd, dd, nwd, bd, snd = leaves[:6]
+    if up:
+        t = F.conv_transpose2d(xd, (wd[0] * scale).transpose(0, 1), stride=2) * dd.view(b, cout, 1, 1)
+        t = F.conv2d(F.pad(t, [1, 1, 1, 1]).reshape(1, b * cout, 2 * r + 3, 2 * r + 3),
+                     taps.double().flip(0, 1).view(1, 1, 4, 4).repeat(b * cout, 1, 1, 1), groups=b * cout).view(b, cout, ro, ro)
+    else:
+        t = F.conv2d(xd, wd[0] * scale, padding=1) * dd.view(b, cout, 1, 1)
+    y = F.leaky_relu(t + nwd * noise.double() + bd.view(1, -1, 1, 1), alpha) * gain
+    main = y * snd.view(b, cout, 1, 1)
+    loss = (main * gy.double()).sum()
+    if wb is not None:
+        rgb_ref = torch.einsum("bchw,bkc->bhwk", y, leaves[6])
+        loss = loss + (rgb_ref * g_rgb.double()).sum()
+    want = torch.autograd.grad(loss, leaves)
+    cu = [t.cuda().requires_grad_(True) for t in ([xs, w, d, nw, bias, s_next] + ([wb] if wb is not None else []))]
+    xc = cu[0].detach().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    got_main, got_rgb = fused.StyledLayerTC.apply(xc, cu[1], cu[2], noise.cuda(), cu[3], cu[4], cu[5],
+                                                  cu[6] if wb is not None else None, scale, up, taps.cuda(), alpha, gain)
+    close(got_main, main.detach().float(), "main (tf32-rounded)")
+    lo = (got_main * gy.cuda()).sum()
+    if wb is not None:
+        close(got_rgb, rgb_ref.detach().float(), "rgb")
+        lo = lo + (got_rgb * g_rgb.cuda()).sum()
+    got = torch.autograd.grad(lo, [xc] + cu[1:])
+    names = ["dxs", "dweight", "dd", "dnoise_w", "dbias", "ds_next", "drgb_weight"]
+    for name, g_, w_ in zip(names, got, want):
+        close(g_, w_.float(), name)
+
+
 def test_fused_pass_kernels():
     """sr_styled_bwd_prologue_f32 / sr_scale_dot_nhwc_f32 / sr_blur_nhwc_styled_f32 against their torch definitions."""
     from stylerenderer_b200 import tc_conv as tc
