@@ -205,6 +205,13 @@ int sr_blur_nhwc_styled2_f32(float *out, float *out2, const float *scale2, const
                              int64_t noise_batch_stride, const float *noise_weight, const float *bias, float alpha,
                              float gain, void *stream);
 
+/* The transpose-side FIR of the up-sampling block's backward with its tail fused:
+ *   f = fir(x) (4x4, up = down = 1, pad (pad0,pad1));  out = tf32_round(f * scale[n,c]);  dot[n,c] = sum_p f * other[n,p,c]
+ * (other has the output's shape; dot is zeroed by the call). */
+int sr_blur_nhwc_scaledot_f32(float *out, float *dot, const float *x, const float *taps, const float *scale,
+                              const float *other, int64_t batch, int64_t in_h, int64_t in_w, int64_t channels, int pad0,
+                              int pad1, void *stream);
+
 /* Backward prologue of a StyledConv block, one pass over (gy, y) [batch, pixels, channels]:
  *   g_pre = gain * (y > 0 ? gy : alpha*gy)                       (reference op/fused_act.py:27-31)
  *   ga    = d ? tf32_round(g_pre * d[n,c]) : g_pre               (operand of the dgrad / wgrad GEMMs)

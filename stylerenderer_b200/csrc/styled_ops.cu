@@ -86,41 +86,58 @@ styled_bwd_prologue_kernel(const PrologueParams p)
     const float ipos = 1.0f / p.gain, ineg = 1.0f / (p.gain * p.alpha);
     float4 a_bias = make_float4(0.f, 0.f, 0.f, 0.f), a_e = a_bias;
     float a_nw = 0.0f;
-    for (int px = p0 + pl; px < p1; px += lanes_p) {
-        const float4 yy = __ldg(y + (long long)px * C4);
-        float4 g = gy ? ld_stream4(reinterpret_cast<const float *>(gy + (long long)px * C4)) : zero4;
-        if (gxs) {
-            const float4 gx = ld_stream4(reinterpret_cast<const float *>(gxs + (long long)px * C4));
-            f4_fma(g, gx, sn);
-            f4_fma(a_ds, gx, yy);
-        }
-        if (grgb) {
+    // two pixels per iteration: twice the loads in flight per thread (the pass is pure streaming)
+    for (int px0 = p0 + pl; px0 < p1; px0 += 2 * lanes_p) {
+        const int pxs[2] = {px0, px0 + lanes_p};
+        float4 yy2[2], g2[2], gx2[2];
+        float gk2[2][3], n2[2];
+        bool ok[2];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float gk = __ldg(grgb + (long long)px * 3 + k);
-                const float4 g4 = make_float4(gk, gk, gk, gk);
-                f4_fma(g, g4, wrgb[k]);
-                f4_fma(a_wb[k], g4, yy);
+        for (int u = 0; u < 2; ++u) {
+            ok[u] = pxs[u] < p1;
+            const long long off = (long long)(ok[u] ? pxs[u] : px0) * C4;
+            yy2[u] = __ldg(y + off);
+            g2[u] = gy ? ld_stream4(reinterpret_cast<const float *>(gy + off)) : zero4;
+            gx2[u] = gxs ? ld_stream4(reinterpret_cast<const float *>(gxs + off)) : zero4;
+            const long long pp = ok[u] ? pxs[u] : px0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) gk2[u][k] = grgb ? __ldg(grgb + pp * 3 + k) : 0.0f;
+            n2[u] = nz ? __ldg(nz + pp) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!ok[u]) continue;
+            const int px = pxs[u];
+            const float4 yy = yy2[u];
+            float4 g = g2[u];
+            if (gxs) { f4_fma(g, gx2[u], sn); f4_fma(a_ds, gx2[u], yy); }
+            if (grgb) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float4 g4 = make_float4(gk2[u][k], gk2[u][k], gk2[u][k], gk2[u][k]);
+                    f4_fma(g, g4, wrgb[k]);
+                    f4_fma(a_wb[k], g4, yy);
+                }
             }
+            const float n = n2[u];
+            float4 gp, uu;
+            // reference op/fused_bias_act_kernel.cu:31: (ref > 0 ? g : g*alpha) * scale
+            gp.x = ((yy.x > 0.f) ? g.x : g.x * p.alpha) * p.gain; gp.y = ((yy.y > 0.f) ? g.y : g.y * p.alpha) * p.gain;
+            gp.z = ((yy.z > 0.f) ? g.z : g.z * p.alpha) * p.gain; gp.w = ((yy.w > 0.f) ? g.w : g.w * p.alpha) * p.gain;
+            f4_add(a_bias, gp);
+            a_nw += ((gp.x + gp.y) + (gp.z + gp.w)) * n;
+            if (p.e) {
+                // the pre-activation is recoverable from y (gain, alpha > 0): t = y / gain or y / (gain * alpha)
+                uu.x = yy.x * ((yy.x > 0.f) ? ipos : ineg); uu.y = yy.y * ((yy.y > 0.f) ? ipos : ineg);
+                uu.z = yy.z * ((yy.z > 0.f) ? ipos : ineg); uu.w = yy.w * ((yy.w > 0.f) ? ipos : ineg);
+                const float sh = nw * n;
+                uu.x -= sh + bias.x; uu.y -= sh + bias.y; uu.z -= sh + bias.z; uu.w -= sh + bias.w;
+                f4_fma(a_e, gp, uu);
+            }
+            float4 o = f4_mul(gp, dd);
+            if (p.d) o = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
+            ga[(long long)px * C4] = o;
         }
-        const float n = nz ? __ldg(nz + px) : 0.0f;
-        float4 gp, u;
-        // reference op/fused_bias_act_kernel.cu:31: (ref > 0 ? g : g*alpha) * scale
-        gp.x = ((yy.x > 0.f) ? g.x : g.x * p.alpha) * p.gain; gp.y = ((yy.y > 0.f) ? g.y : g.y * p.alpha) * p.gain;
-        gp.z = ((yy.z > 0.f) ? g.z : g.z * p.alpha) * p.gain; gp.w = ((yy.w > 0.f) ? g.w : g.w * p.alpha) * p.gain;
-        f4_add(a_bias, gp);
-        a_nw += ((gp.x + gp.y) + (gp.z + gp.w)) * n;
-        if (p.e) {
-            // the pre-activation is recoverable from y (gain, alpha > 0): t = y / gain or y / (gain * alpha)
-            u.x = yy.x * ((yy.x > 0.f) ? ipos : ineg); u.y = yy.y * ((yy.y > 0.f) ? ipos : ineg);
-            u.z = yy.z * ((yy.z > 0.f) ? ipos : ineg); u.w = yy.w * ((yy.w > 0.f) ? ipos : ineg);
-            const float sh = nw * n;
-            u.x -= sh + bias.x; u.y -= sh + bias.y; u.z -= sh + bias.z; u.w -= sh + bias.w;
-            f4_fma(a_e, gp, u);
-        }
-        float4 o = f4_mul(gp, dd);
-        if (p.d) o = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
-        ga[(long long)px * C4] = o;
     }
     (void)pos; (void)neg;
     block_reduce_quads(a_bias, s_red, c4, pl, C4, lanes_p, p.g_bias);

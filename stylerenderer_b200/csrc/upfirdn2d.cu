@@ -186,14 +186,18 @@ struct NhwcGeom {
     float alpha, gain;
     float *out2;                  // optional: tf32(y * scale2[n,c])
     const float *scale2;
+    // SCALEDOT epilogue (backward of the up-sampling block): out = tf32(acc * scale2[n,c]), dot[n,c] += sum acc * other
+    const float *other;
+    float *dot;
 };
 
-template <int KH, int KW, bool STYLED>
+template <int KH, int KW, int MODE>     // MODE 0: plain, 1: STYLED forward tail, 2: SCALEDOT backward tail
 __global__ void __launch_bounds__(kThreads)
 upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, const float *__restrict__ taps,
                       const NhwcGeom g)
 {
     const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    constexpr bool STYLED = (MODE == 1);
     if (tid >= g.total_threads) return;
     uint32_t t = (uint32_t)tid, c, xp, ys, n;
     g.div_c4.divmod(t, t, c);
@@ -222,7 +226,9 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
         if (g.bias) bias4 = __ldg(reinterpret_cast<const float4 *>(g.bias) + c);
     }
     float4 sc2 = zero;
-    if (STYLED && g.out2) sc2 = __ldg(reinterpret_cast<const float4 *>(g.scale2) + (int64_t)n * g.c4 + c);
+    if ((STYLED && g.out2) || MODE == 2) sc2 = __ldg(reinterpret_cast<const float4 *>(g.scale2) + (int64_t)n * g.c4 + c);
+    float4 dot = zero;
+    const float4 *oth = (MODE == 2) ? reinterpret_cast<const float4 *>(g.other) + (int64_t)n * g.out_h * g.out_w * g.c4 + c : nullptr;
 
     float4 win[KH][KW + 1];
     auto load_row = [&](float4 (&row)[KW + 1], int iy) {
@@ -261,6 +267,17 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
                 t = acc[j].w + add + bias4.w; acc[j].w = ((t > 0.f) ? t : t * g.alpha) * g.gain;
             }
         }
+        if (MODE == 2) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (ox0 + j >= g.out_w) break;
+                const float4 tt = __ldg(oth + ((int64_t)oy * g.out_w + ox0 + j) * g.c4);
+                dot.x = fmaf(acc[j].x, tt.x, dot.x); dot.y = fmaf(acc[j].y, tt.y, dot.y);
+                dot.z = fmaf(acc[j].z, tt.z, dot.z); dot.w = fmaf(acc[j].w, tt.w, dot.w);
+                acc[j].x = round_tf32_(acc[j].x * sc2.x); acc[j].y = round_tf32_(acc[j].y * sc2.y);
+                acc[j].z = round_tf32_(acc[j].z * sc2.z); acc[j].w = round_tf32_(acc[j].w * sc2.w);
+            }
+        }
         float4 *dst = yout + ((int64_t)oy * g.out_w + ox0) * g.c4;
         dst[0] = acc[0];
         if (ox0 + 1 < g.out_w) dst[g.c4] = acc[1];
@@ -282,6 +299,10 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
         for (int a = 0; a < KH - 1; ++a)
 #pragma unroll
             for (int b = 0; b < KW + 1; ++b) win[a][b] = win[a + 1][b];
+    }
+    if (MODE == 2) {        // one 128-bit reduction per thread into dot[n, 4c .. 4c+3]
+        float *dp = g.dot + ((int64_t)n * g.c4 + c) * 4;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dp), "f"(dot.x), "f"(dot.y), "f"(dot.z), "f"(dot.w) : "memory");
     }
 }
 
@@ -371,10 +392,10 @@ int launch_tile(float *out, const float *x, const float *taps, int64_t major, in
 int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, int in_h, int in_w, int oh, int ow,
                 int64_t minor, int pad_x0, int pad_y0, bool styled, const float *noise, long long noise_bstride,
                 const float *noise_weight, const float *bias, float alpha, float gain, cudaStream_t st,
-                float *out2 = nullptr, const float *scale2 = nullptr)
+                float *out2 = nullptr, const float *scale2 = nullptr, const float *other = nullptr, float *dot = nullptr)
 {
     NhwcGeom g;
-    g.out2 = out2; g.scale2 = scale2;
+    g.out2 = out2; g.scale2 = scale2; g.other = other; g.dot = dot;
     g.major = major; g.in_h = in_h; g.in_w = in_w; g.out_h = oh; g.out_w = ow;
     g.c4 = (int)(minor / 4); g.pad_x0 = pad_x0; g.pad_y0 = pad_y0;
     g.rows_per_strip = oh >= 64 ? 16 : (oh >= 16 ? 8 : 4);
@@ -386,8 +407,9 @@ int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, in
     g.alpha = alpha; g.gain = gain;
     if (g.total_threads >= 0x7fffffffll) return SR_ERR_UNSUPPORTED;
     const int64_t blocks = (g.total_threads + kThreads - 1) / kThreads;
-    if (styled) upfirdn2d_nhwc_kernel<4, 4, true><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
-    else upfirdn2d_nhwc_kernel<4, 4, false><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
+    if (dot) upfirdn2d_nhwc_kernel<4, 4, 2><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
+    else if (styled) upfirdn2d_nhwc_kernel<4, 4, 1><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
+    else upfirdn2d_nhwc_kernel<4, 4, 0><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
     return SR_OK;
 }
 
@@ -416,6 +438,27 @@ extern "C" int sr_blur_nhwc_styled2_f32(float *out, float *out2, const float *sc
     if (rc != SR_OK) { set_error("blur_nhwc_styled: problem too large"); return rc; }
     count_launch();
     return check_launch("sr_blur_nhwc_styled_f32");
+}
+
+extern "C" int sr_blur_nhwc_scaledot_f32(float *out, float *dot, const float *x, const float *taps, const float *scale,
+                                         const float *other, int64_t batch, int64_t in_h, int64_t in_w, int64_t channels,
+                                         int pad0, int pad1, void *stream)
+{
+    SR_REQUIRE(out && dot && x && taps && scale && other, "blur_nhwc_scaledot: null pointer");
+    SR_REQUIRE(channels >= 4 && channels % 4 == 0, "blur_nhwc_scaledot: channels must be a multiple of 4");
+    SR_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dot) |
+                 reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(other)) & 15u) == 0,
+               "blur_nhwc_scaledot: 16-byte alignment");
+    const int64_t oh = in_h + pad0 + pad1 - 4 + 1, ow = in_w + pad0 + pad1 - 4 + 1;
+    SR_REQUIRE(oh >= 1 && ow >= 1, "blur_nhwc_scaledot: FIR larger than the padded input");
+    cudaError_t er = cudaMemsetAsync(dot, 0, sizeof(float) * (size_t)(batch * channels), (cudaStream_t)stream);
+    if (er != cudaSuccess) { set_error("blur_nhwc_scaledot: memset: %s", cudaGetErrorString(er)); return (int)er; }
+    if (batch == 0) return SR_OK;
+    int rc = launch_nhwc(out, x, taps, batch, (int)in_h, (int)in_w, (int)oh, (int)ow, channels, pad0, pad0, false, nullptr, 0,
+                         nullptr, nullptr, 0.f, 1.f, (cudaStream_t)stream, nullptr, scale, other, dot);
+    if (rc != SR_OK) { set_error("blur_nhwc_scaledot: problem too large"); return rc; }
+    count_launch();
+    return check_launch("sr_blur_nhwc_scaledot_f32");
 }
 
 extern "C" int sr_blur_nhwc_styled_f32(float *out, const float *x, const float *taps, int64_t batch, int64_t in_h,

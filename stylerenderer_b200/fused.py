@@ -68,8 +68,7 @@ class StyledConvTC(Function):
             dwk = tc.wgrad3x3(ga, xs)
         else:
             g_pre, g_bias, g_noise_w, _ = tc.bwd_prologue(gy, y, noise, noise_weight, act_bias, None, alpha, gain, False)
-            gt = upfirdn2d_raw(g_pre, torch.flip(blur_taps, [0, 1]), 1, 1, 1, 1, 2, 2, 2, 2)   # transpose of the FIR
-            ga, e = tc.scale_dot(gt, t, d, True)                       # ga = tf32(gt * d), e = sum gt * t  (t = d * acc)
+            ga, e = tc.blur_scaledot(g_pre, torch.flip(blur_taps, [0, 1]), (2, 2), d, t)   # FIR^T, * d, tf32, sum gt * t
             dxs = tc.conv3x3_s2_gather(ga, tc.weight_prep(weight[0], scale, 2), (h, w))
             dwk = tc.wgrad_transpose3x3_s2(ga, xs)
         g_d = e / d                                                     # dL/dd = sum g * acc = e / d
@@ -175,8 +174,7 @@ class StyledLayerTC(Function):
         else:
             g_pre, g_bias, g_noise_w, _, ds_next, dwb = tc.bwd_prologue2(y, noise, noise_weight, act_bias, None, alpha, gain,
                                                                          False, **src)
-            gt = upfirdn2d_raw(g_pre, torch.flip(blur_taps, [0, 1]), 1, 1, 1, 1, 2, 2, 2, 2)
-            ga, e = tc.scale_dot(gt, t, d, True)
+            ga, e = tc.blur_scaledot(g_pre, torch.flip(blur_taps, [0, 1]), (2, 2), d, t)   # FIR^T, * d, tf32, sum gt * t
             dxs = tc.conv3x3_s2_gather(ga, tc.weight_prep(weight[0], scale, 2), (h, w))
             dwk = tc.wgrad_transpose3x3_s2(ga, xs)
         g_d = e / d

@@ -284,6 +284,14 @@ def test_fused_pass_kernels():
         ref = upfirdn2d_raw(t, k, 1, 1, 1, 1, 1, 1, 1, 1) + nw * noise.view(b, h, w, 1) + bias
         ref = torch.where(ref > 0, ref, ref * 0.2) * 2 ** 0.5
         torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
+        got1, got2 = tc.blur_styled(t, k, (1, 1), noise, nw, bias, 0.2, 2 ** 0.5, scale2=d)
+        assert torch.equal(got1, got)
+        torch.testing.assert_close(got2, ref * d.view(b, 1, 1, c), rtol=6e-4, atol=1e-6)
+        other = seeded((b, h + 2, w + 2, c), 8).cuda()
+        o, dt = tc.blur_scaledot(t, k, (2, 2), d, other)                      # [b,h+1,w+1,c] -> [b,h+2,w+2,c]
+        f = upfirdn2d_raw(t, k, 1, 1, 1, 1, 2, 2, 2, 2)
+        torch.testing.assert_close(o, f * d.view(b, 1, 1, c), rtol=6e-4, atol=1e-6)
+        torch.testing.assert_close(dt, (f * other).sum((1, 2)), rtol=1e-4, atol=1e-2)
 
 
 def test_generator_tcgen05_backend_matches_cudnn_backend():
