@@ -58,9 +58,15 @@ struct Tri {
     int x_lo, x_hi, y_lo, y_hi;
 };
 
+// ceil / floor + clamp to the raster.  The float overloads stay in fp32 (ceilf of a float is exact and equals
+// ceil of its double value), which keeps the slow fp64 pipe out of the per-triangle path.
 __device__ __forceinline__ int clamp_lo(double v) { return v <= 0.0 ? 0 : (v > 1.0e9 ? 1000000000 : (int)ceil(v)); }
 __device__ __forceinline__ int clamp_hi(double v, int span) {
     return v >= (double)(span - 1) ? span - 1 : (v < -1.0 ? -1 : (int)floor(v));
+}
+__device__ __forceinline__ int clamp_lo(float v) { return v <= 0.0f ? 0 : (v > 1.0e9f ? 1000000000 : (int)ceilf(v)); }
+__device__ __forceinline__ int clamp_hi(float v, int span) {
+    return v >= (float)(span - 1) ? span - 1 : (v < -1.0f ? -1 : (int)floorf(v));
 }
 
 // reference op/rasterize.h:9-75 (`barycentric` with det_ != NULL); mirrors oracle sr_tri_setup.
@@ -87,8 +93,8 @@ __device__ __forceinline__ bool tri_setup(Tri<T> &t, int span_x, int span_y, boo
             if (ymin > q[1]) ymin = q[1]; else if (ymax < q[1]) ymax = q[1];
         }
     }
-    t.x_lo = clamp_lo((double)xmin); t.x_hi = clamp_hi((double)xmax, span_x);
-    t.y_lo = clamp_lo((double)ymin); t.y_hi = clamp_hi((double)ymax, span_y);
+    t.x_lo = clamp_lo(xmin); t.x_hi = clamp_hi(xmax, span_x);
+    t.y_lo = clamp_lo(ymin); t.y_hi = clamp_hi(ymax, span_y);
     if (t.x_hi < t.x_lo || t.y_hi < t.y_lo) return false;
     const T *p = t.p;
     T *E = t.E;
@@ -212,21 +218,19 @@ __global__ void __launch_bounds__(kThreads)
 raster_tri_kernel(const RasterGeom g, const T *__restrict__ verts, const int64_t *__restrict__ tris,
                   uint64_t *__restrict__ zkeys, uint32_t *__restrict__ idkeys, T eps)
 {
-    const int64_t total = g.b * g.nf;
+    const int64_t img = blockIdx.y;                      // one grid row per image
+    const int64_t total = g.nf;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     const uint32_t lane = threadIdx.x & 31u;
+    const T *V = verts + (g.shared_v ? 0 : img * g.nv * 3);
+    const int64_t *F = tris + (g.shared_f ? 0 : img * g.nf * 3);
     // warp-uniform trip count: every lane of a warp runs the same number of iterations
     for (int64_t base = (int64_t)blockIdx.x * kThreads + (threadIdx.x & ~31u); base < total; base += stride) {
         const int64_t item = base + lane;
         Tri<T> t;
         bool live = item < total;
-        int64_t img = 0;
-        uint32_t f = 0;
+        const uint32_t f = (uint32_t)item;
         if (live) {
-            img = item / g.nf;
-            f = (uint32_t)(item - img * g.nf);
-            const T *V = verts + (g.shared_v ? 0 : img * g.nv * 3);
-            const int64_t *F = tris + (g.shared_f ? 0 : img * g.nf * 3);
             int64_t ids[3];
             live = load_tri<T>(t, V, F, f, g.nv, ids);
             // reference passes (h, w) for (w, h): x spans h, y spans w (op/rasterize.cpp:38)
@@ -251,54 +255,88 @@ raster_tri_kernel(const RasterGeom g, const T *__restrict__ verts, const int64_t
             s.x_lo = __shfl_sync(0xffffffffu, t.x_lo, src); s.y_lo = __shfl_sync(0xffffffffu, t.y_lo, src);
             const int sbw = __shfl_sync(0xffffffffu, bw, src), sarea = __shfl_sync(0xffffffffu, area, src);
             const uint32_t sf = __shfl_sync(0xffffffffu, f, src);
-            const int64_t simg = __shfl_sync(0xffffffffu, img, src);
             for (int k = lane; k < sarea; k += 32) {
                 const int yy = k / sbw, xx = k - yy * sbw;
-                emit<T, PASS>(s, s.x_lo + xx, s.y_lo + yy, sf, g, eps, zkeys, idkeys, simg);
+                emit<T, PASS>(s, s.x_lo + xx, s.y_lo + yy, sf, g, eps, zkeys, idkeys, img);
             }
         }
     }
 }
 
 // One thread per pixel: decode the winner, recompute its coefficients, write ids / bary (/ interpolated tex).
+// The three outputs are 24 + 12 (+ 4c) bytes per pixel: written per thread they would be strided 8/4-byte stores, so a
+// CTA stages its 256 pixels in shared memory and streams them out as contiguous 16-byte stores.
+constexpr int kMaxStageC = 4;
+
+template <typename V4>
+__device__ __forceinline__ void stream_out(void *gdst, const void *ssrc, int bytes, bool vec_ok)
+{
+    if (vec_ok) {
+        const int n16 = bytes >> 4;
+        for (int i = threadIdx.x; i < n16; i += kThreads)
+            reinterpret_cast<int4 *>(gdst)[i] = reinterpret_cast<const int4 *>(ssrc)[i];
+        const int rem = bytes - (n16 << 4);                  // 0 or a multiple of 4
+        if ((int)threadIdx.x < (rem >> 2))
+            reinterpret_cast<int *>(gdst)[(n16 << 2) + threadIdx.x] = reinterpret_cast<const int *>(ssrc)[(n16 << 2) + threadIdx.x];
+    } else {
+        for (int i = threadIdx.x; i < (bytes >> 2); i += kThreads)
+            reinterpret_cast<int *>(gdst)[i] = reinterpret_cast<const int *>(ssrc)[i];
+    }
+}
+
 template <typename T, bool PACKED>
 __global__ void __launch_bounds__(kThreads)
 raster_resolve_kernel(const RasterGeom g, const T *__restrict__ verts, const int64_t *__restrict__ tris,
                       const uint64_t *__restrict__ zkeys, const uint32_t *__restrict__ idkeys, T eps,
                       int64_t *__restrict__ ids_out, T *__restrict__ bary_out,
-                      const T *__restrict__ tex, int c, T *__restrict__ out)
+                      const T *__restrict__ tex, int c, T *__restrict__ out, int vec_ok)
 {
+    __shared__ __align__(16) int64_t s_ids[kThreads * 3];
+    __shared__ __align__(16) T s_w[kThreads * 3];
+    __shared__ __align__(16) T s_out[kThreads * kMaxStageC];
     const int64_t npix = g.b * g.h * (int64_t)g.w;
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
-    for (int64_t pix = (int64_t)blockIdx.x * kThreads + threadIdx.x; pix < npix; pix += stride) {
-        const uint64_t key = zkeys[pix];
+    const int64_t nblk = (npix + kThreads - 1) / kThreads;
+    const bool stage_out = tex != nullptr && c <= kMaxStageC;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const int64_t pix0 = blk * kThreads, pix = pix0 + threadIdx.x;
+        const int count = (int)((npix - pix0 < kThreads) ? (npix - pix0) : kThreads);
         int64_t ids[3] = {0, 0, 0};
         T w[3] = {0, 0, 0};
-        bool hit = key != 0;
-        if (hit) {
-            const uint32_t f = PACKED ? (0xffffffffu - (uint32_t)key) : idkeys[pix];
-            const int64_t img = pix / (g.h * (int64_t)g.w);
-            const int rem = (int)(pix - img * g.h * (int64_t)g.w);
-            const int y = rem / g.w, x = rem - y * g.w;
-            const T *V = verts + (g.shared_v ? 0 : img * g.nv * 3);
-            const int64_t *F = tris + (g.shared_f ? 0 : img * g.nf * 3);
-            Tri<T> t;
-            T z;
-            hit = load_tri<T>(t, V, F, f, g.nv, ids) && tri_setup<T>(t, g.h, g.w, g.perspective != 0, eps) &&
-                  tri_sample<T>(t, (T)x, (T)y, g.perspective != 0, eps, w, z);
-            if (hit && !g.shared_v) { ids[0] += g.nv * img; ids[1] += g.nv * img; ids[2] += g.nv * img; }
-            if (!hit) { ids[0] = ids[1] = ids[2] = 0; w[0] = w[1] = w[2] = 0; }
+        bool hit = false;
+        if (pix < npix) {
+            const uint64_t key = zkeys[pix];
+            hit = key != 0;
+            if (hit) {
+                const uint32_t f = PACKED ? (0xffffffffu - (uint32_t)key) : idkeys[pix];
+                const int64_t img = pix / (g.h * (int64_t)g.w);
+                const int rem = (int)(pix - img * g.h * (int64_t)g.w);
+                const int y = rem / g.w, x = rem - y * g.w;
+                const T *V = verts + (g.shared_v ? 0 : img * g.nv * 3);
+                const int64_t *F = tris + (g.shared_f ? 0 : img * g.nf * 3);
+                Tri<T> t;
+                T z;
+                hit = load_tri<T>(t, V, F, f, g.nv, ids) && tri_setup<T>(t, g.h, g.w, g.perspective != 0, eps) &&
+                      tri_sample<T>(t, (T)x, (T)y, g.perspective != 0, eps, w, z);
+                if (hit && !g.shared_v) { ids[0] += g.nv * img; ids[1] += g.nv * img; ids[2] += g.nv * img; }
+                if (!hit) { ids[0] = ids[1] = ids[2] = 0; w[0] = w[1] = w[2] = 0; }
+            }
         }
-        ids_out[3 * pix] = ids[0]; ids_out[3 * pix + 1] = ids[1]; ids_out[3 * pix + 2] = ids[2];
-        bary_out[3 * pix] = w[0]; bary_out[3 * pix + 1] = w[1]; bary_out[3 * pix + 2] = w[2];
-        if (tex) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { s_ids[3 * threadIdx.x + k] = ids[k]; s_w[3 * threadIdx.x + k] = w[k]; }
+        if (tex && pix < npix) {
             // op/rasterize.py:29-37: sum_k tex[ids_k] * bary_k  (background: row 0 times 0 = 0)
             for (int ch = 0; ch < c; ++ch) {
                 T v = 0;
                 if (hit) v = tex[ids[0] * c + ch] * w[0] + tex[ids[1] * c + ch] * w[1] + tex[ids[2] * c + ch] * w[2];
-                out[pix * c + ch] = v;
+                if (stage_out) s_out[threadIdx.x * c + ch] = v;
+                else out[pix * c + ch] = v;
             }
         }
+        __syncthreads();
+        stream_out<int4>(ids_out + pix0 * 3, s_ids, count * 3 * (int)sizeof(int64_t), vec_ok);
+        stream_out<int4>(bary_out + pix0 * 3, s_w, count * 3 * (int)sizeof(T), vec_ok);
+        if (stage_out) stream_out<int4>(out + pix0 * c, s_out, count * c * (int)sizeof(T), vec_ok && ((pix0 * c * (int64_t)sizeof(T)) % 16 == 0));
+        __syncthreads();
     }
 }
 
@@ -463,7 +501,11 @@ int rasterize_forward(int64_t b, int64_t nv, int64_t nf, int64_t h, int64_t w, i
     if (e == cudaSuccess && !kF32) e = cudaMemsetAsync(idkeys, 0xff, sizeof(uint32_t) * (size_t)npix, st);
     if (e != cudaSuccess) { set_error("rasterize: memset: %s", cudaGetErrorString(e)); return (int)e; }
     if (nf > 0 && verts && tris) {
-        const int grid = grid_for(b * nf, 16);
+        SR_REQUIRE(b <= 65535, "rasterize: batch too large for one launch");
+        int gx = grid_for(nf, 16);
+        const int per_img = (int)((int64_t)kNumSMs * 16 / b);              // about 16 CTAs per SM over the whole batch
+        if (gx > per_img) gx = per_img < 1 ? 1 : per_img;
+        const dim3 grid((unsigned)gx, (unsigned)b);
         if constexpr (kF32) {
             raster_tri_kernel<T, 0><<<grid, kThreads, 0, st>>>(g, verts, tris, keys, idkeys, eps);
             count_launch();
@@ -473,8 +515,10 @@ int rasterize_forward(int64_t b, int64_t nv, int64_t nf, int64_t h, int64_t w, i
             count_launch(2);
         }
     }
-    raster_resolve_kernel<T, kF32><<<grid_for(npix, 16), kThreads, 0, st>>>(g, verts, tris, keys, idkeys, eps, ids, bary,
-                                                                           tex, (int)c, out);
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(ids) | reinterpret_cast<uintptr_t>(bary) |
+                         reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+    raster_resolve_kernel<T, kF32><<<grid_for(npix, 8), kThreads, 0, st>>>(g, verts, tris, keys, idkeys, eps, ids, bary,
+                                                                          tex, (int)c, out, vec_ok);
     count_launch();
     return check_launch("sr_rasterize_forward");
 }

@@ -192,7 +192,7 @@ struct NhwcGeom {
 };
 
 template <int KH, int KW, int MODE>     // MODE 0: plain, 1: STYLED forward tail, 2: SCALEDOT backward tail
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)      // <= 128 registers: two CTAs per SM keep enough loads in flight
 upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, const float *__restrict__ taps,
                       const NhwcGeom g)
 {
@@ -244,6 +244,12 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
     for (int a = 0; a < KH - 1; ++a) load_row(win[a], oy0 - g.pad_y0 + a);
     for (int oy = oy0; oy < oy1; ++oy) {
         load_row(win[KH - 1], oy - g.pad_y0 + KH - 1);
+        float4 tt[2] = {zero, zero};
+        if (MODE == 2) {                               // issue the loads of the dot operand before the FMA block
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                if (ox0 + j < g.out_w) tt[j] = __ldg(oth + ((int64_t)oy * g.out_w + ox0 + j) * g.c4);
+        }
         float4 acc[2] = {zero, zero};
 #pragma unroll
         for (int a = 0; a < KH; ++a)
@@ -271,9 +277,8 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 if (ox0 + j >= g.out_w) break;
-                const float4 tt = __ldg(oth + ((int64_t)oy * g.out_w + ox0 + j) * g.c4);
-                dot.x = fmaf(acc[j].x, tt.x, dot.x); dot.y = fmaf(acc[j].y, tt.y, dot.y);
-                dot.z = fmaf(acc[j].z, tt.z, dot.z); dot.w = fmaf(acc[j].w, tt.w, dot.w);
+                dot.x = fmaf(acc[j].x, tt[j].x, dot.x); dot.y = fmaf(acc[j].y, tt[j].y, dot.y);
+                dot.z = fmaf(acc[j].z, tt[j].z, dot.z); dot.w = fmaf(acc[j].w, tt[j].w, dot.w);
                 acc[j].x = round_tf32_(acc[j].x * sc2.x); acc[j].y = round_tf32_(acc[j].y * sc2.y);
                 acc[j].z = round_tf32_(acc[j].z * sc2.z); acc[j].w = round_tf32_(acc[j].w * sc2.w);
             }
