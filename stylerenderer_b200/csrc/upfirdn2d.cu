@@ -84,28 +84,40 @@ upfirdn2d_tile_kernel(float *__restrict__ out, const float *__restrict__ x, cons
     //      (2H+1)-wide plane are not 16-byte aligned, which rules out TMA / 16-byte copies in this layout).
     //      Rows are distributed over sub-warps of `lpr` lanes.
     {
+        // only the part of the tile that produces in-range outputs is staged (edge tiles of odd-sized planes are
+        // mostly empty), and tiles that lie fully inside the plane skip the per-element bounds tests
+        const int vw = min(tow, g.out_w - ox0), vh = min(toh, g.out_h - oy0);
+        const int need_cols = min(g.tin_stride, ((vw + VX - 1) / VX - 1) * SX + NWXP);
+        const int need_rows = min(g.tin_h, ((vh + VY - 1) / VY - 1) * SY + NWY);
         int lpr = 32;
-        while (lpr > 1 && (lpr >> 1) >= g.tin_stride) lpr >>= 1;
+        while (lpr > 1 && (lpr >> 1) >= need_cols) lpr >>= 1;
         const int rows_per_pass = kThreads / lpr;
         const int sub = threadIdx.x / lpr, l = threadIdx.x % lpr;
-        const int total_rows = planes_per_tile * g.tin_h;
-        int p = sub / g.tin_h, ry = sub - p * g.tin_h;               // one division, then incremental
-        const int dp = rows_per_pass / g.tin_h, dr = rows_per_pass - dp * g.tin_h;
+        const int total_rows = planes_per_tile * need_rows;
+        int p = sub / need_rows, ry = sub - p * need_rows;           // one division, then incremental
+        const int dp = rows_per_pass / need_rows, dr = rows_per_pass - dp * need_rows;
+        const bool interior = ix0 >= 0 && ix0 + need_cols <= g.in_w && iy0 >= 0 && iy0 + need_rows <= g.in_h &&
+                              plane0 + planes_per_tile <= g.major;
         for (int r = sub; r < total_rows; r += rows_per_pass) {
             const int iy = iy0 + ry;
             const int64_t plane = plane0 + p;
-            const bool row_ok = (iy >= 0) && (iy < g.in_h) && (plane < g.major);
-            const float *src = x + (plane * g.in_h + iy) * (int64_t)g.in_w;
-            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_in + (size_t)r * g.tin_stride);
-            for (int cx = l; cx < g.tin_stride; cx += lpr) {
-                const int ix = ix0 + cx;
-                const bool ok = row_ok && ix >= 0 && ix < g.in_w;
-                const float *gp = ok ? src + ix : x;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n"
-                             :: "r"(dst + 4u * cx), "l"(gp), "r"(ok ? 4 : 0) : "memory");
+            const float *src = x + (plane * g.in_h + iy) * (int64_t)g.in_w + ix0;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_in + ((size_t)p * g.tin_h + ry) * g.tin_stride);
+            if (interior) {
+                for (int cx = l; cx < need_cols; cx += lpr)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(dst + 4u * cx), "l"(src + cx) : "memory");
+            } else {
+                const bool row_ok = (iy >= 0) && (iy < g.in_h) && (plane < g.major);
+                for (int cx = l; cx < need_cols; cx += lpr) {
+                    const int ix = ix0 + cx;
+                    const bool ok = row_ok && ix >= 0 && ix < g.in_w;
+                    const float *gp = ok ? src + cx : x;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n"
+                                 :: "r"(dst + 4u * cx), "l"(gp), "r"(ok ? 4 : 0) : "memory");
+                }
             }
             p += dp; ry += dr;
-            if (ry >= g.tin_h) { ry -= g.tin_h; ++p; }
+            if (ry >= need_rows) { ry -= need_rows; ++p; }
         }
         asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
     }
@@ -117,6 +129,7 @@ upfirdn2d_tile_kernel(float *__restrict__ out, const float *__restrict__ x, cons
     const int p = threadIdx.x >> (g.txs_log2 + g.tys_log2);
     const int64_t plane = plane0 + p;
     const float *wbase = s_in + ((size_t)p * g.tin_h + sy * SY) * g.tin_stride + sx * SX;
+    if (plane >= g.major || ox0 + sx * VX >= g.out_w || oy0 + sy * VY >= g.out_h) return;
 
     float win[NWY][NWXP];
 #pragma unroll
