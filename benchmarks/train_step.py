@@ -130,8 +130,8 @@ def main():
     face = SyntheticMorphableModel(args.mesh_n).to(dev)
     g_reg, d_reg = 4, 16
     g_ratio, d_ratio = g_reg / (g_reg + 1), d_reg / (d_reg + 1)        # train.py:529-536
-    g_optim = torch.optim.Adam(G.parameters(), lr=0.002 * g_ratio, betas=(0, 0.99 ** g_ratio))
-    d_optim = torch.optim.Adam(D.parameters(), lr=0.002 * d_ratio, betas=(0, 0.99 ** d_ratio))
+    g_optim = torch.optim.Adam(G.parameters(), lr=0.002 * g_ratio, betas=(0.0, 0.99 ** g_ratio))
+    d_optim = torch.optim.Adam(D.parameters(), lr=0.002 * d_ratio, betas=(0.0, 0.99 ** d_ratio))
     g_mod, d_mod = G, D
     if world > 1:
         from torch.nn.parallel import DistributedDataParallel as DDP
