@@ -135,7 +135,9 @@ def main():
     g_mod, d_mod = G, D
     if world > 1:
         from torch.nn.parallel import DistributedDataParallel as DDP
-        G = DDP(G, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True)
+        # find_unused_parameters: the reference builds the ToRGB list twice and never uses the second copy (SURVEY.md
+        # section 4 quirk 4), so six modules' parameters never receive gradients
+        G = DDP(G, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True, find_unused_parameters=True)
         D = DDP(D, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True)
     B, tri = args.batch, face.tri
     mean_path = torch.zeros((), device=dev)
