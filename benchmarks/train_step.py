@@ -178,11 +178,22 @@ def main():
             v = vert[:pb].clone().requires_grad_(True)
             n = norm[:pb].clone().requires_grad_(True)
             with layers.double_backward():
-                fake, latents, normals = G([torch.randn(pb, 512, device=dev)], (v, n, tri), return_latents=True,
-                                           return_normals=True)
+                # the unwrapped module: DDP(find_unused_parameters=True) hands back copies of the outputs, which
+                # cannot be differentiated against; the gradient all-reduce of this step is issued explicitly below
+                fake, latents, normals = g_mod([torch.randn(pb, 512, device=dev)], (v, n, tri), return_latents=True,
+                                               return_normals=True)
                 path_loss, mean_path = g_path_regularize(fake, [latents] + normals, mean_path)
                 g_mod.zero_grad(set_to_none=True)
                 (2 * g_reg * path_loss + 0 * fake[0, 0, 0, 0]).backward()
+            if world > 1:
+                grads = [p.grad for p in g_mod.parameters() if p.grad is not None]
+                flat = torch.cat([g.reshape(-1) for g in grads])
+                dist.all_reduce(flat)
+                flat.div_(world)
+                off = 0
+                for g in grads:
+                    g.copy_(flat[off:off + g.numel()].view_as(g))
+                    off += g.numel()
             g_optim.step()
         with torch.no_grad():                                           # EMA (train.py:100-104,358)
             for pe, p in zip(g_ema.parameters(), g_mod.parameters()):
