@@ -78,6 +78,54 @@ class StyledConvTC(Function):
         return g_x, g_w, g_s, g_d, None, g_noise_w, g_bias, None, None, None, None, None
 
 
+class ModConvTC(Function):
+    """The bare ModulatedConv2d contraction y = d[b,o] * conv(x * s[b,i], scale * W) (plain 3x3 or the stride-2
+    transposed 3x3 + FIR of reference layers.py:301-310) on the tensor-core kernels, for callers that apply their own
+    tail (StyledMapConv, user code)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, s, d, scale, upsample, blur_taps):
+        x_nhwc = to_nhwc(x)
+        s, d = s.contiguous(), d.contiguous()
+        xs = tc.modulate(x_nhwc, s)
+        wk = tc.weight_prep(weight[0], scale, 0)
+        if not upsample:
+            saved = y = tc.conv3x3(xs, wk, rowscale=d)
+        else:
+            saved = tc.conv_transpose3x3_s2(xs, wk, rowscale=d)
+            y = upfirdn2d_raw(saved, blur_taps, 1, 1, 1, 1, 1, 1, 1, 1)
+        ctx.save_for_backward(x_nhwc, xs, saved, weight, s, d, blur_taps)
+        ctx.cfg = (scale, upsample)
+        return from_nhwc(y)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x_nhwc, xs, saved, weight, s, d, blur_taps = ctx.saved_tensors
+        scale, upsample = ctx.cfg
+        b, h, w, cin = x_nhwc.shape
+        cout = saved.shape[3]
+        gy = to_nhwc(gy)
+        if not upsample:
+            ga, e = tc.scale_dot(gy, saved, d, True)                   # tf32(gy * d), e = sum gy * (d * acc)
+            dxs = tc.conv3x3(ga, tc.weight_prep(weight[0], scale, 1))
+            dwk = tc.wgrad3x3(ga, xs)
+        else:
+            ga, e = tc.blur_scaledot(gy, torch.flip(blur_taps, [0, 1]), (2, 2), d, saved)
+            dxs = tc.conv3x3_s2_gather(ga, tc.weight_prep(weight[0], scale, 2), (h, w))
+            dwk = tc.wgrad_transpose3x3_s2(ga, xs)
+        g_x, g_s = tc.scale_dot(dxs, x_nhwc, s, False)
+        g_w = (dwk.view(cout, 3, 3, cin).permute(0, 3, 1, 2) * scale).unsqueeze(0)
+        return from_nhwc(g_x), g_w, g_s, e / d, None, None, None
+
+
+def mod_conv(mod, x, style):
+    """ModulatedConv2d.forward on the tensor cores (see ModConvTC)."""
+    s, d = mod.style_scales(style)
+    taps = mod.blur.kernel if mod.upsample else s
+    return ModConvTC.apply(x, mod.weight, s, d, mod.scale, mod.upsample, taps)
+
+
 def styled_conv(mod_conv, noise_mod, act_mod, x, style, noise):
     """The tcgen05 fast path of StyledConv.forward (mod_conv: ModulatedConv2d, act_mod: FusedLeakyReLU)."""
     s, d = mod_conv.style_scales(style)

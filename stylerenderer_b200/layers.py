@@ -213,6 +213,10 @@ class ModulatedConv2d(nn.Module):                     # reference layers.py:259-
 
     def forward(self, input, style):
         batch, in_channel = input.shape[:2]
+        if _CONFIG["conv_backend"] == "tcgen05" and not (torch.is_grad_enabled() and _CONFIG["double_backward"]):
+            from . import fused                          # hand-written tensor-core contraction where the shape allows
+            if fused.supported(self, input):
+                return fused.mod_conv(self, input, style)
         s, d = self.style_scales(style)
         if self.kernel_size == 1 and not self.upsample and not self.downsample:
             # ToRGB: fold the style into B x [Cout, Cin] weights (a few KB) and read the activation once

@@ -294,6 +294,54 @@ def test_fused_pass_kernels():
         torch.testing.assert_close(dt, (f * other).sum((1, 2)), rtol=1e-4, atol=1e-2)
 
 
+@pytest.mark.parametrize("up", [False, True])
+def test_modulated_conv_tcgen05_exact_forward(up):
+    """ModulatedConv2d alone on the tensor cores (the path StyledMapConv and user code take), exact-product operands."""
+    import torch.nn.functional as F
+    from stylerenderer_b200 import fused
+    b, cin, cout, r = 2, 128, 128, 8
+    scale = 2.0 ** -5
+    x, w, s, d, _, _, _, _ = _exact_inputs(b, cin, cout, r, up)
+    ro = 2 * r if up else r
+    gy = torch.randn(b, cout, ro, ro, generator=torch.Generator().manual_seed(5))
+    taps = torch.tensor([1., 3., 3., 1.])
+    taps = (taps[None] * taps[:, None]) / 16
+    leaves = [t.double().requires_grad_(True) for t in (x, w, s, d)]
+    xd, wd, sd, dd = leaves
+    xm = xd * sd.view(b, cin, 1, 1)
+    if up:
+        t = F.conv_transpose2d(xm, (wd[0] * scale).transpose(0, 1), stride=2) * dd.view(b, cout, 1, 1)
+        y = F.conv2d(F.pad(t, [1, 1, 1, 1]).reshape(1, b * cout, 2 * r + 3, 2 * r + 3),
+                     taps.double().flip(0, 1).view(1, 1, 4, 4).repeat(b * cout, 1, 1, 1), groups=b * cout).view(b, cout, ro, ro)
+    else:
+        y = F.conv2d(xm, wd[0] * scale, padding=1) * dd.view(b, cout, 1, 1)
+    want = torch.autograd.grad(y, leaves, gy.double())
+    cu = [t.cuda().requires_grad_(True) for t in (x, w, s, d)]
+    got_y = fused.ModConvTC.apply(cu[0], cu[1], cu[2], cu[3], scale, up, taps.cuda())
+    got = torch.autograd.grad(got_y, cu, gy.cuda())
+    close(got_y, y.detach().float(), "y")
+    for name, g_, w_ in zip(["dx", "dweight", "ds", "dd"], got, want):
+        close(g_, w_.float(), name)
+
+
+def test_generator_with_map_tcgen05_runs_and_matches():
+    """GeneratorWithMap with conv_backend=tcgen05 (StyledMapConv -> tensor-core ModulatedConv2d) vs the composed path."""
+    from stylerenderer_b200 import layers as L, model as M
+    from make_golden import seeded, grid_mesh
+    G = det_fill(M.GeneratorWithMap(32, 64, 2), 720).cuda().eval()
+    v, tri = grid_mesh(24, 2, 721)
+    tex = torch.nn.functional.normalize(seeded((2, 576, 3), 722), dim=-1)
+    z = seeded((2, 64), 723).cuda()
+    mesh = (v.cuda(), tex.cuda(), tri.cuda())
+    img_a, _, _ = G([z], mesh, randomize_noise=False)
+    L.set_conv_backend("tcgen05")
+    try:
+        img_b, _, _ = G([z], mesh, randomize_noise=False)
+    finally:
+        L.set_conv_backend("cudnn")
+    close(img_b, img_a.detach().cpu(), "GAR image")
+
+
 def test_generator_tcgen05_backend_matches_cudnn_backend():
     """Generator(64) end to end: tcgen05 backend (channels_last pipeline) vs the composed-op backend in true fp32."""
     from stylerenderer_b200 import layers as L, model as M
