@@ -111,6 +111,8 @@ def main():
     ap.add_argument("--iters", type=int, default=16, help="timed iterations (a multiple of 16 covers whole regulariser cycles)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--mesh-n", type=int, default=189)
+    ap.add_argument("--conv-backend", default="tcgen05", choices=["cudnn", "tcgen05"],
+                    help="who runs the ModulatedConv2d contractions of G (the Discriminator's plain convs stay on cuDNN)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -124,6 +126,7 @@ def main():
     from stylerenderer_b200 import _lib, layers
     from stylerenderer_b200.model import Discriminator, GeneratorWithMap
 
+    layers.set_conv_backend(args.conv_backend)
     G = GeneratorWithMap(args.size, 512, 8, channel_multiplier=2).to(dev)
     D = Discriminator(args.size, channel_multiplier=2).to(dev)
     g_ema = copy.deepcopy(G).eval()
@@ -222,7 +225,8 @@ def main():
         print(json.dumps({
             "metric": "GAR train step (G+D+rasterize+R1/16+path/4) images/sec", "value": round(world * B * args.iters / (ms * 1e-3), 2),
             "unit": "images/s", "n_gpus": world, "iters": args.iters, "ms_per_iter": round(ms / args.iters, 2),
-            "scaling": "weak", "dtype": "f32 storage, cuDNN convs (tf32) + stylerenderer_b200 ops/rasteriser",
+            "scaling": "weak", "dtype": "f32 storage, tf32 tensor-core convs",
+            "conv_backend": {"generator": args.conv_backend, "discriminator": "cudnn"},
             "config": {"workload": "GeneratorWithMap + Discriminator 256x256 (BASELINE.json configs[3])", "per_gpu_batch": B,
                        "parallelism": f"ddp{world} (NCCL gradient all-reduce, broadcast_buffers=False)",
                        "mesh": f"{args.mesh_n ** 2} verts / {tri.shape[0]} tris"},
