@@ -118,6 +118,7 @@ struct ConvPhase {                          // one tap list + output lattice (th
     int tap_dy[9], tap_dx[9], tap_k0[9];    // input offset of a tap and its first K column in the weight matrix
     int grid_h, grid_w, tiles_x, tiles_y;
     int tile_begin;                         // first M tile of this phase
+    int tile_begin2;                        // same with every phase padded to an even tile count (CTA-pair kernel)
     long long out_offset;                   // lattice origin (y0 * row + x0 * pix), in floats
     long long noise_offset;
 };
@@ -127,6 +128,7 @@ struct ConvKParams {
     int batch;
     int kblocks_per_tap;                    // cin / 32
     int num_phases, n_tiles, total_tiles;   // total_tiles = (sum of M tiles) * n_tiles
+    int total_pairs;                        // CTA-pair kernel: (sum of padded M tiles / 2) * n_tiles
     ConvPhase ph[kMaxPhases];
     int in_stride;
     int cout;
@@ -160,6 +162,78 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams &p, int T) {
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+// Epilogue of one 128-row accumulator: wait for the MMA, tcgen05.ld 32 columns at a time, fused tail, stores.
+// Returns the three ToRGB partial sums of this thread's pixel in rgb[] and whether the pixel is inside the lattice.
+template <int BLOCK_N>
+__device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvPhase &ph, const TileCoord &tc, int q, int tx,
+                                              int ty, int tn, uint32_t tmem_acc, uint64_t *tmem_full, uint32_t acc_par,
+                                              float (&rgb)[3], long long &rgb_index)
+{
+    const int gx = tc.gx0 + tx, gy = tc.gy0 + ty, n = tc.n0 + tn;
+    const bool valid = gx < ph.grid_w && gy < ph.grid_h && n < p.batch;
+    const long long opix = (long long)n * p.out_img_stride + (long long)gy * p.out_row_stride +
+                           (long long)gx * p.out_pix_stride + ph.out_offset;
+    float pre_add = 0.0f, map_mul = 1.0f;
+    if (p.epilogue == 1 && valid) {
+        const long long npix = (long long)gy * p.noise_row_stride + (long long)gx * p.noise_pix_stride + ph.noise_offset;
+        if (p.noise) pre_add = __ldg(p.noise_weight) * __ldg(p.noise + (long long)n * p.noise_img_stride + npix);
+        if (p.stylemap) {
+            const float *m = p.stylemap + (long long)n * p.map_img_stride + npix;
+            map_mul = __ldg(m);
+            pre_add += __ldg(m + p.map_plane_stride);
+        }
+    }
+    rgb[0] = rgb[1] = rgb[2] = 0.0f;
+    mbar_wait(tmem_full, acc_par);
+    tcgen05_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+        if (valid) {
+            const int ch0 = tc.n_tile * BLOCK_N + c * 32;
+            const float4 *rs = p.rowscale ? reinterpret_cast<const float4 *>(p.rowscale + (long long)n * p.cout + ch0) : nullptr;
+            const float4 *s2 = p.out2 ? reinterpret_cast<const float4 *>(p.scale2 + (long long)n * p.cout + ch0) : nullptr;
+            const float4 *bs = (p.epilogue == 1 && p.bias) ? reinterpret_cast<const float4 *>(p.bias + ch0) : nullptr;
+            float4 *o1 = reinterpret_cast<float4 *>(p.out + opix + ch0);
+            float4 *o2 = p.out2 ? reinterpret_cast<float4 *>(p.out2 + opix + ch0) : nullptr;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float v[4] = {__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                              __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])};
+                if (rs) { const float4 s = __ldg(rs + j); v[0] *= s.x; v[1] *= s.y; v[2] *= s.z; v[3] *= s.w; }
+                if (p.epilogue == 1) {
+                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bs) b = __ldg(bs + j);
+                    const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float t = v[e] * map_mul + pre_add + bb[e];
+                        v[e] = ((t > 0.0f) ? t : t * p.alpha) * p.gain;
+                    }
+                }
+                o1[j] = make_float4(v[0], v[1], v[2], v[3]);
+                if (p.rgb_w) {                      // ToRGB rides the epilogue: 3 dot products over the channel chunk
+                    const float *w0 = p.rgb_w + (long long)n * 3 * p.cout + ch0 + 4 * j;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float4 ww = __ldg(reinterpret_cast<const float4 *>(w0 + (long long)k * p.cout));
+                        rgb[k] = fmaf(v[0], ww.x, fmaf(v[1], ww.y, fmaf(v[2], ww.z, fmaf(v[3], ww.w, rgb[k]))));
+                    }
+                }
+                if (o2) {
+                    const float4 s = __ldg(s2 + j);
+                    o2[j] = make_float4(round_tf32(v[0] * s.x), round_tf32(v[1] * s.y), round_tf32(v[2] * s.z),
+                                        round_tf32(v[3] * s.w));
+                }
+            }
+        }
+    }
+    rgb_index = ((long long)n * p.map_plane_stride + (long long)gy * p.noise_row_stride + (long long)gx * p.noise_pix_stride +
+                 ph.noise_offset) * 3;
+    return valid;
 }
 
 // Persistent: gridDim.x CTAs (one per SM) walk the tile list round-robin.  The TMEM holds TWO accumulators, so the
@@ -254,72 +328,15 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             const TileCoord tc = decode_tile(p, T);
             const ConvPhase &ph = p.ph[tc.phase];
             const uint32_t acc = lt & 1, acc_par = (lt >> 1) & 1;
-            const int gx = tc.gx0 + tx, gy = tc.gy0 + ty, n = tc.n0 + tn;
-            const bool valid = gx < ph.grid_w && gy < ph.grid_h && n < p.batch;
-            const long long opix = (long long)n * p.out_img_stride + (long long)gy * p.out_row_stride +
-                                   (long long)gx * p.out_pix_stride + ph.out_offset;
-            float pre_add = 0.0f, map_mul = 1.0f;
-            if (p.epilogue == 1 && valid) {
-                const long long npix = (long long)gy * p.noise_row_stride + (long long)gx * p.noise_pix_stride + ph.noise_offset;
-                if (p.noise) pre_add = __ldg(p.noise_weight) * __ldg(p.noise + (long long)n * p.noise_img_stride + npix);
-                if (p.stylemap) {
-                    const float *m = p.stylemap + (long long)n * p.map_img_stride + npix;
-                    map_mul = __ldg(m);
-                    pre_add += __ldg(m + p.map_plane_stride);
-                }
-            }
-            float rgb[3] = {0.0f, 0.0f, 0.0f};
-            mbar_wait(&tmem_full_bar[acc], acc_par);
-            tcgen05_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * 32), r);
-                if (valid) {
-                    const int ch0 = tc.n_tile * BLOCK_N + c * 32;
-                    const float4 *rs = p.rowscale ? reinterpret_cast<const float4 *>(p.rowscale + (long long)n * p.cout + ch0) : nullptr;
-                    const float4 *s2 = p.out2 ? reinterpret_cast<const float4 *>(p.scale2 + (long long)n * p.cout + ch0) : nullptr;
-                    const float4 *bs = (p.epilogue == 1 && p.bias) ? reinterpret_cast<const float4 *>(p.bias + ch0) : nullptr;
-                    float4 *o1 = reinterpret_cast<float4 *>(p.out + opix + ch0);
-                    float4 *o2 = p.out2 ? reinterpret_cast<float4 *>(p.out2 + opix + ch0) : nullptr;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float v[4] = {__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                      __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])};
-                        if (rs) { const float4 s = __ldg(rs + j); v[0] *= s.x; v[1] *= s.y; v[2] *= s.z; v[3] *= s.w; }
-                        if (p.epilogue == 1) {
-                            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (bs) b = __ldg(bs + j);
-                            const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                float t = v[e] * map_mul + pre_add + bb[e];
-                                v[e] = ((t > 0.0f) ? t : t * p.alpha) * p.gain;
-                            }
-                        }
-                        o1[j] = make_float4(v[0], v[1], v[2], v[3]);
-                        if (p.rgb_w) {                      // ToRGB rides the epilogue: 3 dot products over the channel chunk
-                            const float *w0 = p.rgb_w + (long long)n * 3 * p.cout + ch0 + 4 * j;
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) {
-                                const float4 ww = __ldg(reinterpret_cast<const float4 *>(w0 + (long long)k * p.cout));
-                                rgb[k] = fmaf(v[0], ww.x, fmaf(v[1], ww.y, fmaf(v[2], ww.z, fmaf(v[3], ww.w, rgb[k]))));
-                            }
-                        }
-                        if (o2) {
-                            const float4 s = __ldg(s2 + j);
-                            o2[j] = make_float4(round_tf32(v[0] * s.x), round_tf32(v[1] * s.y), round_tf32(v[2] * s.z),
-                                                round_tf32(v[3] * s.w));
-                        }
-                    }
-                }
-            }
+            float rgb[3];
+            long long rgb_index;
+            const bool valid = epilogue_tile<BLOCK_N>(p, ph, tc, q, tx, ty, tn, tmem_base + acc * BLOCK_N, &tmem_full_bar[acc],
+                                                      acc_par, rgb, rgb_index);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);   // this warp no longer reads accumulator `acc`
             if (p.rgb_w && valid) {
-                float *dst = p.rgb_out + ((long long)n * p.map_plane_stride + (long long)gy * p.noise_row_stride +
-                                          (long long)gx * p.noise_pix_stride + ph.noise_offset) * 3;
+                float *dst = p.rgb_out + rgb_index;
                 atomicAdd(dst, rgb[0]); atomicAdd(dst + 1, rgb[1]); atomicAdd(dst + 2, rgb[2]);
             }
         }
@@ -328,6 +345,177 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)(2 * BLOCK_N)) : "memory");
+    }
+}
+
+
+// ------------------------------------------------------------------------------------ CTA-pair variant (cta_group::2)
+// Two CTAs of a cluster (one TPC) compute a 256-pixel x BLOCK_N tile with ONE tcgen05.mma.cta_group::2 stream issued
+// by the leader: each CTA stages its own 128 pixel rows of A and HALF of the weight tile (BLOCK_N/2 rows), so the
+// shared-memory operand traffic per SM drops from 128 to 96 B/clk at N = 128 (64 instead of 96 at N = 256) -- the limit
+// the single-CTA kernel hits on the 128-channel layers.  Protocol: both producers' TMA loads (cta_group::2 form)
+// complete on the LEADER's full barrier; the leader's tcgen05.commit multicasts to both CTAs' empty / tmem_full
+// barriers; all eight epilogue warps arrive on the leader's tmem_empty barrier.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {      // arrive on the LEADER CTA's copy of `bar`
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_2sm(uint64_t *bar) {      // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ TileCoord decode_tile_pair(const ConvKParams &p, int P, int rank) {
+    TileCoord c;
+    c.n_tile = P % p.n_tiles;
+    int mt = 2 * (P / p.n_tiles) + rank;
+    c.phase = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxPhases; ++i)
+        if (i < p.num_phases && mt >= p.ph[i].tile_begin2) c.phase = i;
+    const ConvPhase &ph = p.ph[c.phase];
+    mt -= ph.tile_begin2;                    // may run one past the real tiles of the phase: decodes to n0 >= batch (all masked)
+    const int tx = mt % ph.tiles_x, ty = (mt / ph.tiles_x) % ph.tiles_y, tn = mt / (ph.tiles_x * ph.tiles_y);
+    c.gx0 = tx << p.tw_log2; c.gy0 = ty << p.th_log2; c.n0 = tn << p.tn_log2;
+    return c;
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                            const ConvKParams p)
+{
+    constexpr int BH_BYTES = (BLOCK_N / 2) * BLOCK_K * 4;                  // this CTA's half of the weight tile
+    constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                                ((uint32_t)((2 * BLOCK_M) >> 4) << 24);     // M = 256 across the pair
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + STAGES * A_BYTES;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * (A_BYTES + BH_BYTES));
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tmem_full_bar = empty_bar + STAGES;      // [2]
+    uint64_t *tmem_empty_bar = tmem_full_bar + 2;      // [2], used in the leader only
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int cluster = (int)cluster_id_x(), num_clusters = (int)cluster_count_x();
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_b) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster_sync_all();                                // barriers of both CTAs exist before any remote arrive
+    if (warp == 1) {                                   // both CTAs, same warp id: 2 accumulators of BLOCK_N columns each
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BLOCK_N)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                               // ===== TMA producer (both CTAs)
+            uint32_t it = 0;
+            for (int P = cluster; P < p.total_pairs; P += num_clusters) {
+                const TileCoord tc = decode_tile_pair(p, P, rank);
+                const ConvPhase &ph = p.ph[tc.phase];
+                for (int t = 0; t < ph.num_taps; ++t) {
+                    const int cx = tc.gx0 * p.in_stride + ph.tap_dx[t], cy = tc.gy0 * p.in_stride + ph.tap_dy[t];
+                    for (int kc = 0; kc < p.kblocks_per_tap; ++kc, ++it) {
+                        const uint32_t s = it % STAGES, par = (it / STAGES) & 1;
+                        mbar_wait(&empty_bar[s], par ^ 1);
+                        if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * (A_BYTES + BH_BYTES));   // bytes of BOTH CTAs
+                        else mbar_arrive_leader(&full_bar[s]);
+                        tma_load_4d_2sm(sA + s * A_BYTES, &tmap_a, &full_bar[s], kc * BLOCK_K, cx, cy, tc.n0);
+                        tma_load_2d_2sm(sB + s * BH_BYTES, &tmap_b, &full_bar[s], ph.tap_k0[t] + kc * BLOCK_K,
+                                        tc.n_tile * BLOCK_N + rank * (BLOCK_N / 2));
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {                  // ===== MMA issuer (leader CTA only)
+            uint32_t it = 0, lt = 0;
+            for (int P = cluster; P < p.total_pairs; P += num_clusters, ++lt) {
+                const TileCoord tc = decode_tile_pair(p, P, 0);
+                const int num_kb = p.ph[tc.phase].num_taps * p.kblocks_per_tap;
+                const uint32_t acc = lt & 1, acc_par = (lt >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[acc], acc_par ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, par = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], par);
+                    tcgen05_fence_after();
+                    const uint64_t da = make_kmajor_sw128_desc(smem_u32(sA + s * A_BYTES));
+                    const uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + s * BH_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 8; ++k)
+                        umma_tf32_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
+                    tcgen05_commit_2sm(&empty_bar[s]);
+                }
+                tcgen05_commit_2sm(&tmem_full_bar[acc]);
+            }
+        }
+    } else {                                           // ===== epilogue (both CTAs, each on its own 128 TMEM lanes)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int tx = row & ((1 << p.tw_log2) - 1);
+        const int ty = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
+        const int tn = row >> (p.tw_log2 + p.th_log2);
+        uint32_t lt = 0;
+        for (int P = cluster; P < p.total_pairs; P += num_clusters, ++lt) {
+            const TileCoord tc = decode_tile_pair(p, P, rank);
+            const ConvPhase &ph = p.ph[tc.phase];
+            const uint32_t acc = lt & 1, acc_par = (lt >> 1) & 1;
+            float rgb[3];
+            long long rgb_index;
+            const bool valid = epilogue_tile<BLOCK_N>(p, ph, tc, q, tx, ty, tn, tmem_base + acc * BLOCK_N, &tmem_full_bar[acc],
+                                                      acc_par, rgb, rgb_index);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
+            if (p.rgb_w && valid) {
+                float *dst = p.rgb_out + rgb_index;
+                atomicAdd(dst, rgb[0]); atomicAdd(dst + 1, rgb[1]); atomicAdd(dst + 2, rgb[2]);
+            }
+        }
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();                                // nobody in the pair touches TMEM / remote barriers any more
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)(2 * BLOCK_N)) : "memory");
     }
 }
 
@@ -549,6 +737,23 @@ int launch_conv(const CUtensorMap &ta, const CUtensorMap &tb, const ConvKParams 
     return SR_OK;
 }
 
+template <int BLOCK_N, int STAGES>
+int launch_conv_2cta(const CUtensorMap &ta, const CUtensorMap &tb, const ConvKParams &p, cudaStream_t st)
+{
+    constexpr int BH_BYTES = (BLOCK_N / 2) * BLOCK_K * 4;
+    const size_t smem = 1024 + (size_t)STAGES * (A_BYTES + BH_BYTES) + 256;
+    auto kern = conv_igemm_tf32_2cta_kernel<BLOCK_N, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("conv: cudaFuncSetAttribute(2cta): %s", cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    int clusters = p.total_pairs < kNumSMs / 2 ? p.total_pairs : kNumSMs / 2;
+    kern<<<2 * clusters, kConvThreads, smem, st>>>(ta, tb, p);        // __cluster_dims__(2,1,1): CTA pairs
+    return SR_OK;
+}
+
 }  // namespace
 }  // namespace sr
 
@@ -599,7 +804,7 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
     p.kblocks_per_tap = (int)(a->cin / BLOCK_K);
     p.num_phases = count;
     const int tiles_n = (int)((a->batch + tn - 1) / tn);
-    long long m_tiles = 0;
+    long long m_tiles = 0, m_tiles2 = 0;
     for (int i = 0; i < kMaxPhases; ++i) {
         ConvPhase &ph = p.ph[i];
         const sr_conv_args *b = args + (i < count ? i : 0);
@@ -609,9 +814,14 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
         ph.tiles_x = (int)((b->grid_w + tw - 1) / tw);
         ph.tiles_y = (int)((b->grid_h + th - 1) / th);
         ph.tile_begin = (int)m_tiles;
+        ph.tile_begin2 = (int)m_tiles2;
         ph.out_offset = ((long long)b->out_y0 * a->out_w + b->out_x0) * a->cout;
         ph.noise_offset = (long long)b->out_y0 * a->out_w + b->out_x0;
-        if (i < count) m_tiles += (long long)ph.tiles_x * ph.tiles_y * tiles_n;
+        if (i < count) {
+            const long long t_ph = (long long)ph.tiles_x * ph.tiles_y * tiles_n;
+            m_tiles += t_ph;
+            m_tiles2 += (t_ph + 1) / 2 * 2;
+        }
     }
     // few tiles (low resolutions): prefer 128-wide N tiles so more SMs take part
     int block_n = (a->cout % 256 == 0) ? 256 : 128;
@@ -619,6 +829,12 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
     p.n_tiles = (int)(a->cout / block_n);
     SR_REQUIRE(m_tiles * p.n_tiles < 0x7fffffffll, "conv: too many tiles");
     p.total_tiles = (int)(m_tiles * p.n_tiles);
+    p.total_pairs = (int)(m_tiles2 / 2 * p.n_tiles);
+    // CTA pairs (cta_group::2) pay off where the single-CTA kernel is limited by shared-memory operand bandwidth
+    // (N = 128 tiles) and need enough tiles to fill 74 pairs; SR_CONV_2CTA=0/1 forces the choice.
+    static const char *force_2cta = getenv("SR_CONV_2CTA");
+    bool use_2cta = (block_n == 128) && p.total_pairs >= kNumSMs / 2;
+    if (force_2cta) use_2cta = force_2cta[0] == '1';
 
     CUtensorMap ta, tb;
     {
@@ -637,7 +853,7 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
         const cuuint64_t ktot = (cuuint64_t)a->taps_total * a->cin;
         cuuint64_t dims[2] = {ktot, (cuuint64_t)a->cout};
         cuuint64_t strides[1] = {ktot * 4};
-        cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)block_n};
+        cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)(use_2cta ? block_n / 2 : block_n)};   // a CTA of a pair stages half the rows
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(a->weight), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -669,7 +885,10 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
     }
 
     int rc;
-    if (block_n == 256) rc = launch_conv<256, 4>(ta, tb, p, st);
+    if (use_2cta) {
+        if (block_n == 256) rc = launch_conv_2cta<256, 6>(ta, tb, p, st);
+        else rc = launch_conv_2cta<128, 8>(ta, tb, p, st);
+    } else if (block_n == 256) rc = launch_conv<256, 4>(ta, tb, p, st);
     else rc = launch_conv<128, 6>(ta, tb, p, st);
     if (rc != SR_OK) return rc;
     count_launch();
