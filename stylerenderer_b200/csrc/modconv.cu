@@ -63,6 +63,14 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 :: "l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void tcgen05_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
@@ -143,6 +151,16 @@ struct ConvKParams {
     float *rgb_out;                         // [batch, out_h, out_w, 3], += sum_c out[..., c] * rgb_w[n, k, c]
 };
 
+// TMA-store descriptors of the output lattice(s): one per phase (the parity classes of a transposed conv write
+// interleaved sub-lattices = strided views of the output), for `out` and for the optional second output.
+// Box = the 32 rows of one epilogue warp x 32 channels, 128-byte swizzled.
+struct alignas(64) ConvOutMaps {
+    CUtensorMap out[kMaxPhases];
+    CUtensorMap out2[kMaxPhases];
+};
+constexpr int kStageBufBytes = 32 * 128;               // one warp, one 32-channel chunk
+constexpr int kEpiSmemBytes = 4 * 2 * kStageBufBytes;  // 4 epilogue warps x 2 buffers
+
 struct TileCoord { int phase, gx0, gy0, n0, n_tile; };
 
 __device__ __forceinline__ TileCoord decode_tile(const ConvKParams &p, int T) {
@@ -164,17 +182,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
-// Epilogue of one 128-row accumulator: wait for the MMA, tcgen05.ld 32 columns at a time, fused tail, stores.
+// Epilogue of one 128-row accumulator: wait for the MMA, tcgen05.ld 32 columns at a time, fused tail, then each warp
+// stages its 32 rows x 32 channels (4 KB, 128-byte swizzled, conflict free) in shared memory and one lane hands the block
+// to the TMA store unit: full 128-byte lines leave the SM (per-thread 16-byte global stores made the epilogue as long
+// as the main loop on the K = 1152 layers), and the unit clips partial tiles and walks strided lattices by itself.
 // Returns the three ToRGB partial sums of this thread's pixel in rgb[] and whether the pixel is inside the lattice.
 template <int BLOCK_N>
-__device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvPhase &ph, const TileCoord &tc, int q, int tx,
-                                              int ty, int tn, uint32_t tmem_acc, uint64_t *tmem_full, uint32_t acc_par,
+__device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvOutMaps &om, const ConvPhase &ph,
+                                              const TileCoord &tc, int q, int lane, int tx, int ty, int tn, uint32_t tmem_acc,
+                                              uint64_t *tmem_full, uint32_t acc_par, uint8_t *stage, uint32_t &stage_sel,
                                               float (&rgb)[3], long long &rgb_index)
 {
     const int gx = tc.gx0 + tx, gy = tc.gy0 + ty, n = tc.n0 + tn;
     const bool valid = gx < ph.grid_w && gy < ph.grid_h && n < p.batch;
-    const long long opix = (long long)n * p.out_img_stride + (long long)gy * p.out_row_stride +
-                           (long long)gx * p.out_pix_stride + ph.out_offset;
+    const int nb = valid ? n : 0;                                     // per-sample vectors of a masked row: any valid row
     float pre_add = 0.0f, map_mul = 1.0f;
     if (p.epilogue == 1 && valid) {
         const long long npix = (long long)gy * p.noise_row_stride + (long long)gx * p.noise_pix_stride + ph.noise_offset;
@@ -185,6 +206,11 @@ __device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvPh
             pre_add += __ldg(m + p.map_plane_stride);
         }
     }
+    // first pixel of this warp's 32 rows (box origin of its TMA stores)
+    const int row0 = q * 32;
+    const int wx = tc.gx0 + (row0 & ((1 << p.tw_log2) - 1));
+    const int wy = tc.gy0 + ((row0 >> p.tw_log2) & ((1 << p.th_log2) - 1));
+    const int wn = tc.n0 + (row0 >> (p.tw_log2 + p.th_log2));
     rgb[0] = rgb[1] = rgb[2] = 0.0f;
     mbar_wait(tmem_full, acc_par);
     tcgen05_fence_after();
@@ -192,43 +218,61 @@ __device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvPh
     for (int c = 0; c < BLOCK_N / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-        if (valid) {
-            const int ch0 = tc.n_tile * BLOCK_N + c * 32;
-            const float4 *rs = p.rowscale ? reinterpret_cast<const float4 *>(p.rowscale + (long long)n * p.cout + ch0) : nullptr;
-            const float4 *s2 = p.out2 ? reinterpret_cast<const float4 *>(p.scale2 + (long long)n * p.cout + ch0) : nullptr;
-            const float4 *bs = (p.epilogue == 1 && p.bias) ? reinterpret_cast<const float4 *>(p.bias + ch0) : nullptr;
-            float4 *o1 = reinterpret_cast<float4 *>(p.out + opix + ch0);
-            float4 *o2 = p.out2 ? reinterpret_cast<float4 *>(p.out2 + opix + ch0) : nullptr;
+        const int ch0 = tc.n_tile * BLOCK_N + c * 32;
+        const float4 *rs = p.rowscale ? reinterpret_cast<const float4 *>(p.rowscale + (long long)nb * p.cout + ch0) : nullptr;
+        const float4 *s2 = p.out2 ? reinterpret_cast<const float4 *>(p.scale2 + (long long)nb * p.cout + ch0) : nullptr;
+        const float4 *bs = (p.epilogue == 1 && p.bias) ? reinterpret_cast<const float4 *>(p.bias + ch0) : nullptr;
+        uint8_t *buf1 = stage + (stage_sel & 1) * kStageBufBytes;
+        uint8_t *buf2 = stage + ((stage_sel + 1) & 1) * kStageBufBytes;
+        // the store that last read buf1 (two stores ago) must have finished reading shared memory
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        float y[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float v[4] = {__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                              __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])};
-                if (rs) { const float4 s = __ldg(rs + j); v[0] *= s.x; v[1] *= s.y; v[2] *= s.z; v[3] *= s.w; }
-                if (p.epilogue == 1) {
-                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (bs) b = __ldg(bs + j);
-                    const float bb[4] = {b.x, b.y, b.z, b.w};
+        for (int j = 0; j < 8; ++j) {
+            float v[4] = {__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                          __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])};
+            if (rs) { const float4 s = __ldg(rs + j); v[0] *= s.x; v[1] *= s.y; v[2] *= s.z; v[3] *= s.w; }
+            if (p.epilogue == 1) {
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bs) b = __ldg(bs + j);
+                const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float t = v[e] * map_mul + pre_add + bb[e];
-                        v[e] = ((t > 0.0f) ? t : t * p.alpha) * p.gain;
-                    }
-                }
-                o1[j] = make_float4(v[0], v[1], v[2], v[3]);
-                if (p.rgb_w) {                      // ToRGB rides the epilogue: 3 dot products over the channel chunk
-                    const float *w0 = p.rgb_w + (long long)n * 3 * p.cout + ch0 + 4 * j;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const float4 ww = __ldg(reinterpret_cast<const float4 *>(w0 + (long long)k * p.cout));
-                        rgb[k] = fmaf(v[0], ww.x, fmaf(v[1], ww.y, fmaf(v[2], ww.z, fmaf(v[3], ww.w, rgb[k]))));
-                    }
-                }
-                if (o2) {
-                    const float4 s = __ldg(s2 + j);
-                    o2[j] = make_float4(round_tf32(v[0] * s.x), round_tf32(v[1] * s.y), round_tf32(v[2] * s.z),
-                                        round_tf32(v[3] * s.w));
+                for (int e = 0; e < 4; ++e) {
+                    float t = v[e] * map_mul + pre_add + bb[e];
+                    v[e] = ((t > 0.0f) ? t : t * p.alpha) * p.gain;
                 }
             }
+            y[4 * j] = v[0]; y[4 * j + 1] = v[1]; y[4 * j + 2] = v[2]; y[4 * j + 3] = v[3];
+            // 128-byte swizzle: 16-byte chunk j of row `lane` lives at chunk j ^ (lane % 8)
+            *reinterpret_cast<float4 *>(buf1 + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+            if (p.rgb_w && valid) {                 // ToRGB rides the epilogue: 3 dot products over the channel chunk
+                const float *w0 = p.rgb_w + (long long)n * 3 * p.cout + ch0 + 4 * j;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float4 ww = __ldg(reinterpret_cast<const float4 *>(w0 + (long long)k * p.cout));
+                    rgb[k] = fmaf(v[0], ww.x, fmaf(v[1], ww.y, fmaf(v[2], ww.z, fmaf(v[3], ww.w, rgb[k]))));
+                }
+            }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) { tma_store_4d(&om.out[tc.phase], buf1, ch0, wx, wy, wn); tma_store_commit(); }
+        ++stage_sel;
+        if (s2) {
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 s = __ldg(s2 + j);
+                *reinterpret_cast<float4 *>(buf2 + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                    make_float4(round_tf32(y[4 * j] * s.x), round_tf32(y[4 * j + 1] * s.y), round_tf32(y[4 * j + 2] * s.z),
+                                round_tf32(y[4 * j + 3] * s.w));
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) { tma_store_4d(&om.out2[tc.phase], buf2, ch0, wx, wy, wn); tma_store_commit(); }
+            ++stage_sel;
         }
     }
     rgb_index = ((long long)n * p.map_plane_stride + (long long)gy * p.noise_row_stride + (long long)gx * p.noise_pix_stride +
@@ -241,6 +285,7 @@ __device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvPh
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                       const __grid_constant__ ConvOutMaps out_maps,
                        const ConvKParams p)
 {
     constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
@@ -255,6 +300,7 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     uint64_t *tmem_full_bar = empty_bar + STAGES;      // [2]
     uint64_t *tmem_empty_bar = tmem_full_bar + 2;      // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+    uint8_t *epi_stage = smem + STAGES * (A_BYTES + B_BYTES) + 1024;   // 1024-byte aligned (swizzle), 8 KB per epilogue warp
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -323,15 +369,16 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const int tx = row & ((1 << p.tw_log2) - 1);
         const int ty = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
         const int tn = row >> (p.tw_log2 + p.th_log2);
-        uint32_t lt = 0;
+        uint32_t lt = 0, stage_sel = 0;
+        uint8_t *my_stage = epi_stage + q * 2 * kStageBufBytes;
         for (int T = blockIdx.x; T < p.total_tiles; T += gridDim.x, ++lt) {
             const TileCoord tc = decode_tile(p, T);
             const ConvPhase &ph = p.ph[tc.phase];
             const uint32_t acc = lt & 1, acc_par = (lt >> 1) & 1;
             float rgb[3];
             long long rgb_index;
-            const bool valid = epilogue_tile<BLOCK_N>(p, ph, tc, q, tx, ty, tn, tmem_base + acc * BLOCK_N, &tmem_full_bar[acc],
-                                                      acc_par, rgb, rgb_index);
+            const bool valid = epilogue_tile<BLOCK_N>(p, out_maps, ph, tc, q, lane, tx, ty, tn, tmem_base + acc * BLOCK_N,
+                                                      &tmem_full_bar[acc], acc_par, my_stage, stage_sel, rgb, rgb_index);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);   // this warp no longer reads accumulator `acc`
@@ -340,6 +387,7 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 atomicAdd(dst, rgb[0]); atomicAdd(dst + 1, rgb[1]); atomicAdd(dst + 2, rgb[2]);
             }
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all TMA stores of this warp landed
     }
     __syncthreads();
     if (warp == 1) {
@@ -406,6 +454,7 @@ __device__ __forceinline__ TileCoord decode_tile_pair(const ConvKParams &p, int 
 template <int BLOCK_N, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                       const __grid_constant__ ConvOutMaps out_maps,
                             const ConvKParams p)
 {
     constexpr int BH_BYTES = (BLOCK_N / 2) * BLOCK_K * 4;                  // this CTA's half of the weight tile
@@ -420,6 +469,7 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     uint64_t *tmem_full_bar = empty_bar + STAGES;      // [2]
     uint64_t *tmem_empty_bar = tmem_full_bar + 2;      // [2], used in the leader only
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+    uint8_t *epi_stage = smem + STAGES * (A_BYTES + BH_BYTES) + 1024;  // 1024-byte aligned (swizzle), 8 KB per epilogue warp
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();
@@ -493,15 +543,16 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
         const int tx = row & ((1 << p.tw_log2) - 1);
         const int ty = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
         const int tn = row >> (p.tw_log2 + p.th_log2);
-        uint32_t lt = 0;
+        uint32_t lt = 0, stage_sel = 0;
+        uint8_t *my_stage = epi_stage + q * 2 * kStageBufBytes;
         for (int P = cluster; P < p.total_pairs; P += num_clusters, ++lt) {
             const TileCoord tc = decode_tile_pair(p, P, rank);
             const ConvPhase &ph = p.ph[tc.phase];
             const uint32_t acc = lt & 1, acc_par = (lt >> 1) & 1;
             float rgb[3];
             long long rgb_index;
-            const bool valid = epilogue_tile<BLOCK_N>(p, ph, tc, q, tx, ty, tn, tmem_base + acc * BLOCK_N, &tmem_full_bar[acc],
-                                                      acc_par, rgb, rgb_index);
+            const bool valid = epilogue_tile<BLOCK_N>(p, out_maps, ph, tc, q, lane, tx, ty, tn, tmem_base + acc * BLOCK_N,
+                                                      &tmem_full_bar[acc], acc_par, my_stage, stage_sel, rgb, rgb_index);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
@@ -510,6 +561,7 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                 atomicAdd(dst, rgb[0]); atomicAdd(dst + 1, rgb[1]); atomicAdd(dst + 2, rgb[2]);
             }
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tcgen05_fence_before();
     cluster_sync_all();                                // nobody in the pair touches TMEM / remote barriers any more
@@ -721,10 +773,10 @@ EncodeTiledFn encode_tiled() {
 int ilog2_exact(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 template <int BLOCK_N, int STAGES>
-int launch_conv(const CUtensorMap &ta, const CUtensorMap &tb, const ConvKParams &p, cudaStream_t st)
+int launch_conv(const CUtensorMap &ta, const CUtensorMap &tb, const ConvOutMaps &om, const ConvKParams &p, cudaStream_t st)
 {
     constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
-    const size_t smem = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 256;
+    const size_t smem = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 1024 + kEpiSmemBytes;
     auto kern = conv_igemm_tf32_kernel<BLOCK_N, STAGES>;
     static bool configured = false;
     if (!configured) {
@@ -733,15 +785,15 @@ int launch_conv(const CUtensorMap &ta, const CUtensorMap &tb, const ConvKParams 
         configured = true;
     }
     const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;     // persistent: one CTA per SM
-    kern<<<grid, kConvThreads, smem, st>>>(ta, tb, p);
+    kern<<<grid, kConvThreads, smem, st>>>(ta, tb, om, p);
     return SR_OK;
 }
 
 template <int BLOCK_N, int STAGES>
-int launch_conv_2cta(const CUtensorMap &ta, const CUtensorMap &tb, const ConvKParams &p, cudaStream_t st)
+int launch_conv_2cta(const CUtensorMap &ta, const CUtensorMap &tb, const ConvOutMaps &om, const ConvKParams &p, cudaStream_t st)
 {
     constexpr int BH_BYTES = (BLOCK_N / 2) * BLOCK_K * 4;
-    const size_t smem = 1024 + (size_t)STAGES * (A_BYTES + BH_BYTES) + 256;
+    const size_t smem = 1024 + (size_t)STAGES * (A_BYTES + BH_BYTES) + 1024 + kEpiSmemBytes;
     auto kern = conv_igemm_tf32_2cta_kernel<BLOCK_N, STAGES>;
     static bool configured = false;
     if (!configured) {
@@ -750,7 +802,7 @@ int launch_conv_2cta(const CUtensorMap &ta, const CUtensorMap &tb, const ConvKPa
         configured = true;
     }
     int clusters = p.total_pairs < kNumSMs / 2 ? p.total_pairs : kNumSMs / 2;
-    kern<<<2 * clusters, kConvThreads, smem, st>>>(ta, tb, p);        // __cluster_dims__(2,1,1): CTA pairs
+    kern<<<2 * clusters, kConvThreads, smem, st>>>(ta, tb, om, p);    // __cluster_dims__(2,1,1): CTA pairs
     return SR_OK;
 }
 
@@ -861,6 +913,31 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
         if (r != CUDA_SUCCESS) { set_error("conv: cuTensorMapEncodeTiled(B) failed with %d", (int)r); return SR_ERR_DRIVER; }
     }
 
+    // output lattices as strided 4-D views {channels, grid_w, grid_h, batch}; box = one epilogue warp's 32 rows x 32 channels
+    ConvOutMaps om;
+    {
+        int bw = tw, bh = 32 / tw, bn = 1;
+        if (bh > th) { bn = bh / th; bh = th; }
+        for (int i = 0; i < kMaxPhases; ++i) {
+            const sr_conv_args *b = args + (i < count ? i : 0);
+            for (int which = 0; which < 2; ++which) {
+                float *base = which == 0 ? a->out : a->out2;
+                CUtensorMap *m = which == 0 ? &om.out[i] : &om.out2[i];
+                if (!base) { om.out2[i] = om.out[i]; continue; }
+                base += ((long long)b->out_y0 * a->out_w + b->out_x0) * a->cout;
+                cuuint64_t dims[4] = {(cuuint64_t)a->cout, (cuuint64_t)b->grid_w, (cuuint64_t)b->grid_h, (cuuint64_t)a->batch};
+                cuuint64_t strides[3] = {(cuuint64_t)a->out_stride * a->cout * 4, (cuuint64_t)a->out_stride * a->out_w * a->cout * 4,
+                                         (cuuint64_t)a->out_h * a->out_w * a->cout * 4};
+                cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+                cuuint32_t estr[4] = {1, 1, 1, 1};
+                CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) { set_error("conv: cuTensorMapEncodeTiled(out) failed with %d", (int)r); return SR_ERR_DRIVER; }
+            }
+        }
+    }
+    SR_REQUIRE(!a->out2 || (reinterpret_cast<uintptr_t>(a->out2) & 15) == 0, "conv: out2 must be 16-byte aligned");
+
     p.in_stride = a->in_stride;
     p.cout = (int)a->cout;
     p.out_pix_stride = (long long)a->out_stride * a->cout;
@@ -886,10 +963,10 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
 
     int rc;
     if (use_2cta) {
-        if (block_n == 256) rc = launch_conv_2cta<256, 6>(ta, tb, p, st);
-        else rc = launch_conv_2cta<128, 8>(ta, tb, p, st);
-    } else if (block_n == 256) rc = launch_conv<256, 4>(ta, tb, p, st);
-    else rc = launch_conv<128, 6>(ta, tb, p, st);
+        if (block_n == 256) rc = launch_conv_2cta<256, 6>(ta, tb, om, p, st);
+        else rc = launch_conv_2cta<128, 8>(ta, tb, om, p, st);
+    } else if (block_n == 256) rc = launch_conv<256, 4>(ta, tb, om, p, st);
+    else rc = launch_conv<128, 6>(ta, tb, om, p, st);
     if (rc != SR_OK) return rc;
     count_launch();
     return check_launch("sr_conv_igemm_tf32");
