@@ -882,10 +882,10 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
     SR_REQUIRE(m_tiles * p.n_tiles < 0x7fffffffll, "conv: too many tiles");
     p.total_tiles = (int)(m_tiles * p.n_tiles);
     p.total_pairs = (int)(m_tiles2 / 2 * p.n_tiles);
-    // CTA pairs (cta_group::2) pay off where the single-CTA kernel is limited by shared-memory operand bandwidth
-    // (N = 128 tiles) and need enough tiles to fill 74 pairs; SR_CONV_2CTA=0/1 forces the choice.
+    // CTA pairs (cta_group::2) halve the weight-tile traffic per SM; they need enough tiles to fill the 74 pairs.
+    // SR_CONV_2CTA=0/1 forces the choice.
     static const char *force_2cta = getenv("SR_CONV_2CTA");
-    bool use_2cta = (block_n == 128) && p.total_pairs >= kNumSMs / 2;
+    bool use_2cta = p.total_pairs >= kNumSMs / 2;      // measured: 921 vs 839 TF/s (512 ch @64^2), 880 vs 783 (256 ch @128^2)
     if (force_2cta) use_2cta = force_2cta[0] == '1';
 
     CUtensorMap ta, tb;
