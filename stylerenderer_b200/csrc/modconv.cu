@@ -707,6 +707,114 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     }
 }
 
+
+// CTA-pair wgrad: the pair accumulates a 256 (cout) x 256 (cin) block of one tap; each CTA stages its own 128 output
+// channels of G and 128 of the 256 input channels of X (64 KB per 64-pixel stage instead of the 96 KB a single CTA would
+// need for the same flops), one tcgen05.mma.cta_group::2 stream, barrier protocol as in conv_igemm_tf32_2cta_kernel.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+wgrad_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
+                       const WgradKParams p)
+{
+    constexpr int WG_BK = 64, WG_STAGES = 3, WG_N = 256;
+    constexpr int WG_COLBLK_BYTES = WG_BK * 128;
+    constexpr int WG_STAGE_BYTES = 8 * WG_COLBLK_BYTES;                  // 4 blocks of G + 4 blocks of X per CTA
+    constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                ((uint32_t)(WG_N >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + WG_STAGES * WG_STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + WG_STAGES;
+    uint64_t *tmem_full_bar = empty_bar + WG_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    const int m_tile = pair / p.n_tiles, n_tile = pair % p.n_tiles;      // in units of 256 channels
+    const int tap = blockIdx.y;
+    const int total_kt = p.tiles_x * p.tiles_y * p.tiles_n;
+    const int kt0 = blockIdx.z * p.ktiles_per_split;
+    const int num_kt = min(total_kt, kt0 + p.ktiles_per_split) - kt0;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_g) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_x) : "memory");
+        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)WG_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < num_kt; ++it) {
+                const int s = it % WG_STAGES;
+                const uint32_t ph = (it / WG_STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                const int kt = kt0 + it;
+                const int tile_x = kt % p.tiles_x, tile_y = (kt / p.tiles_x) % p.tiles_y, tile_n = kt / (p.tiles_x * p.tiles_y);
+                const int gx0 = tile_x << p.tw_log2, gy0 = tile_y << p.th_log2, n0 = tile_n << p.tn_log2;
+                uint8_t *sa = smem + s * WG_STAGE_BYTES, *sb = sa + 4 * WG_COLBLK_BYTES;
+                if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * WG_STAGE_BYTES);
+                else mbar_arrive_leader(&full_bar[s]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    tma_load_4d_2sm(sa + j * WG_COLBLK_BYTES, &tmap_g, &full_bar[s], m_tile * 256 + rank * 128 + j * 32,
+                                    gx0 * p.g_stride + p.g_dx[tap], gy0 * p.g_stride + p.g_dy[tap], n0);
+                    tma_load_4d_2sm(sb + j * WG_COLBLK_BYTES, &tmap_x, &full_bar[s], n_tile * 256 + rank * 128 + j * 32,
+                                    gx0 * p.x_stride + p.x_dx[tap], gy0 * p.x_stride + p.x_dy[tap], n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            for (int it = 0; it < num_kt; ++it) {
+                const int s = it % WG_STAGES;
+                const uint32_t ph = (it / WG_STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tcgen05_fence_after();
+                const uint32_t a0 = smem_u32(smem + s * WG_STAGE_BYTES), b0 = a0 + 4 * WG_COLBLK_BYTES;
+#pragma unroll
+                for (int k = 0; k < WG_BK / 8; ++k)
+                    umma_tf32_2sm(tmem_base, make_mnmajor_sw128_desc(a0 + k * 1024, WG_COLBLK_BYTES),
+                                  make_mnmajor_sw128_desc(b0 + k * 1024, WG_COLBLK_BYTES), kIdesc, (it | k) != 0);
+                tcgen05_commit_2sm(&empty_bar[s]);
+            }
+            tcgen05_commit_2sm(tmem_full_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        const int co = m_tile * 256 + rank * 128 + q * 32 + lane;
+        float *dst = p.dw + ((long long)co * p.taps_total + p.tap_out[tap]) * p.cin + n_tile * WG_N;
+        mbar_wait(tmem_full_bar, 0);
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < WG_N / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dst + c * 32 + j), "f"(__uint_as_float(r[j])),
+                             "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3])) : "memory");
+        }
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)WG_N) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------ small helper kernels
 // xs[b,p,c] = tf32(x[b,p,c] * s[b,c])  -- the modulated, tensor-core-ready copy of an NHWC activation
 __global__ void __launch_bounds__(256)
@@ -985,7 +1093,10 @@ extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
     if (!enc) { set_error("wgrad: cuTensorMapEncodeTiled not available from the driver"); return SR_ERR_DRIVER; }
     cudaStream_t st = (cudaStream_t)stream;
     static const bool allow_wide = getenv("SR_WGRAD_WIDE") != nullptr;      // experimental N = 256 shape (measured slower in round 1)
-    const bool wide = allow_wide && (a->cin % 256 == 0);   // N = 256, 32 pixels per stage
+    static const char *force_pair = getenv("SR_WGRAD_2CTA");
+    bool pair = (a->cout % 256 == 0) && (a->cin % 256 == 0);               // CTA-pair kernel: 256 x 256 block per tap
+    if (force_pair) pair = pair && force_pair[0] == '1';
+    const bool wide = !pair && allow_wide && (a->cin % 256 == 0);           // N = 256, 32 pixels per stage
     int tw, th, tn;
     if (wide) {
         if (a->grid_w > 8) { tw = 16; th = 2; tn = 1; }
@@ -996,7 +1107,7 @@ extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
         else if (a->grid_w > 4) { tw = 8; th = 8; tn = 1; }
         else { tw = 4; th = 4; tn = 4; }
     }
-    const int wg_n = wide ? 256 : 128;
+    const int wg_n = (wide || pair) ? 256 : 128;
     CUtensorMap tg, tx;
     auto make_map = [&](CUtensorMap *m, const float *base, int64_t hh, int64_t ww, int64_t cc, int stride) -> int {
         cuuint64_t dims[4] = {(cuuint64_t)cc, (cuuint64_t)ww, (cuuint64_t)hh, (cuuint64_t)a->batch};
@@ -1021,10 +1132,11 @@ extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
     p.tiles_y = (int)((a->grid_h + th - 1) / th);
     p.tiles_n = (int)((a->batch + tn - 1) / tn);
     p.n_tiles = (int)(a->cin / wg_n);
-    const int mn_tiles = (int)(a->cout / BLOCK_M) * p.n_tiles;
+    const int mn_tiles = (int)(a->cout / (pair ? 256 : BLOCK_M)) * p.n_tiles;      // pair kernel: 256 x 256 blocks
     const long long total_kt = (long long)p.tiles_x * p.tiles_y * p.tiles_n;
-    // split K so that about two waves of CTAs cover the 148 SMs
-    long long splits = (2 * kNumSMs + (long long)mn_tiles * a->num_taps - 1) / ((long long)mn_tiles * a->num_taps);
+    // split K so that about two waves of CTAs cover the 148 SMs (a pair occupies two)
+    const long long want = pair ? kNumSMs : 2 * kNumSMs;
+    long long splits = (want + (long long)mn_tiles * a->num_taps - 1) / ((long long)mn_tiles * a->num_taps);
     if (splits < 1) splits = 1;
     if (splits > total_kt) splits = total_kt;
     p.ktiles_per_split = (int)((total_kt + splits - 1) / splits);
@@ -1040,9 +1152,18 @@ extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
         cudaError_t e = cudaMemsetAsync(a->dw, 0, sizeof(float) * (size_t)a->cout * a->taps_total * a->cin, st);
         if (e != cudaSuccess) { set_error("wgrad: memset: %s", cudaGetErrorString(e)); return (int)e; }
     }
-    const dim3 grid((unsigned)mn_tiles, (unsigned)a->num_taps, (unsigned)splits);
+    const dim3 grid((unsigned)(pair ? 2 * mn_tiles : mn_tiles), (unsigned)a->num_taps, (unsigned)splits);
     static bool configured[2] = {false, false};
-    if (wide) {
+    static bool configured_pair = false;
+    if (pair) {
+        const size_t smem = 1024 + (size_t)3 * 8 * 64 * 128 + 256;
+        if (!configured_pair) {
+            cudaError_t e = cudaFuncSetAttribute(wgrad_tf32_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { set_error("wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+            configured_pair = true;
+        }
+        wgrad_tf32_2cta_kernel<<<grid, kConvThreads, smem, st>>>(tg, tx, p);
+    } else if (wide) {
         auto kern = wgrad_tf32_kernel<256, 32, 4>;
         const size_t smem = 1024 + (size_t)4 * (4 + 8) * 32 * 128 + 256;
         if (!configured[0]) {

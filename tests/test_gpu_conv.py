@@ -124,7 +124,8 @@ def test_transposed_conv_dgrad_wide(tc):
 
 
 @pytest.mark.parametrize("case", [(2, 16, 16, 128, 128), (3, 8, 8, 128, 256), (9, 4, 4, 256, 128), (1, 20, 36, 128, 128),
-                                  (2, 64, 64, 128, 128), (5, 5, 5, 128, 128)])
+                                  (2, 64, 64, 128, 128), (5, 5, 5, 128, 128),
+                                  (2, 16, 16, 256, 256), (3, 8, 8, 512, 256), (5, 4, 4, 256, 512), (1, 32, 32, 256, 256)])   # CTA-pair kernel
 def test_wgrad(tc, case):
     b, h, w, cin, cout = case
     x = tc.modulate(nhwc(seeded((b, cin, h, w), 21)).cuda())
