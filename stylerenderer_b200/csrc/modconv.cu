@@ -1134,11 +1134,23 @@ extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
     p.n_tiles = (int)(a->cin / wg_n);
     const int mn_tiles = (int)(a->cout / (pair ? 256 : BLOCK_M)) * p.n_tiles;      // pair kernel: 256 x 256 blocks
     const long long total_kt = (long long)p.tiles_x * p.tiles_y * p.tiles_n;
-    // split K so that about two waves of CTAs cover the 148 SMs (a pair occupies two)
-    const long long want = pair ? kNumSMs : 2 * kNumSMs;
-    long long splits = (want + (long long)mn_tiles * a->num_taps - 1) / ((long long)mn_tiles * a->num_taps);
-    if (splits < 1) splits = 1;
-    if (splits > total_kt) splits = total_kt;
+    // Split K.  All CTAs of a launch run the same number of K tiles and one CTA (pair) owns an SM (pair), so the
+    // launch executes in whole waves: time ~ ceil(CTAs / slots) * (K tiles per CTA + fixed cost), where the fixed cost
+    // (TMEM alloc, pipeline fill, red.add epilogue) is worth about 16 K tiles.  Pick the split count that minimises it
+    // (e.g. 9 taps x 33 splits = 297 CTAs is THREE waves of 148; 32 splits is two).
+    const long long slots = pair ? kNumSMs / 2 : kNumSMs;
+    const long long base_ctas = (long long)mn_tiles * a->num_taps;
+    long long splits = 1, best_cost = -1;
+    const long long max_splits = total_kt < 4 * slots ? total_kt : 4 * slots;
+    for (long long s = 1; s <= max_splits; ++s) {
+        const long long per = (total_kt + s - 1) / s;
+        const long long real = (total_kt + per - 1) / per;
+        if (real != s) continue;                                  // same work distribution as a smaller s
+        const long long waves = (base_ctas * s + slots - 1) / slots;
+        const long long cost = waves * (per + 16);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; splits = s; }
+        if (base_ctas * s > 6 * slots) break;
+    }
     p.ktiles_per_split = (int)((total_kt + splits - 1) / splits);
     splits = (total_kt + p.ktiles_per_split - 1) / p.ktiles_per_split;
     p.g_stride = a->g_stride; p.x_stride = a->x_stride;
