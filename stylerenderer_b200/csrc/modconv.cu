@@ -55,6 +55,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "DONE_%=:\n"
         "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// One lane polls, the warp re-converges: 32 lanes spinning on a barrier word compete with the tensor core's operand
+// reads for the shared-memory port (measured on the wgrad kernel: +20 % time with all lanes polling).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity, int one_lane = 0) {
+    if (one_lane) {
+        if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+        __syncwarp();
+    } else {
+        mbar_wait(bar, parity);
+    }
+}
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
@@ -106,6 +116,16 @@ __device__ __forceinline__ float round_tf32(float v) {
     return __uint_as_float(r);
 }
 
+// Warp-uniform election of one issuing lane (the same lane every time).  The producer and MMA warps run their loops with
+// all 32 lanes converged and elect only around the asynchronous instructions: inside an `if (lane == 0)` region the
+// compiler cannot use the uniform datapath and wraps every UTMALDG / UTCHMMA operand in an ELECT / R2UR / BRA.U.ANY
+// waterfall loop (~25 instructions per MMA; ncu: the single issuing thread, not the data, bounded the N = 128 layers).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -149,6 +169,8 @@ struct ConvKParams {
     float alpha, gain;
     const float *rgb_w;                     // fused ToRGB: [batch, 3, cout] per-sample 1x1 weights (or nullptr)
     float *rgb_out;                         // [batch, out_h, out_w, 3], += sum_c out[..., c] * rgb_w[n, k, c]
+    int debug;                              // SR_CONV_DEBUG (profiling only): 1 = epilogue handshake only, 2 = no MMAs,
+                                            // 4 = one lane polls the barriers, 8 = halo epilogue stores without TMA
 };
 
 // TMA-store descriptors of the output lattice(s): one per phase (the parity classes of a transposed conv write
@@ -187,11 +209,36 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // to the TMA store unit: full 128-byte lines leave the SM (per-thread 16-byte global stores made the epilogue as long
 // as the main loop on the K = 1152 layers), and the unit clips partial tiles and walks strided lattices by itself.
 // Returns the three ToRGB partial sums of this thread's pixel in rgb[] and whether the pixel is inside the lattice.
-template <int BLOCK_N>
+// STAGED: the per-sample / per-channel vectors of the tile (demodulation, next-layer style, bias, ToRGB weights) were
+// copied to shared memory by stage_tile_vectors() BEFORE the wait for the accumulator, so the chunk loop reads them with
+// broadcast LDS.128 instead of stalling on dependent global loads (ncu: `long_sb` on those loads made the epilogue of a
+// 128-channel tile longer than its main loop).  Requires all 128 rows of the tile to belong to one image (tn = 1).
+constexpr int kVecKinds = 6;                            // rowscale, scale2, bias, rgb_w[0..2]
+template <int BLOCK_N, int THREADS>
+__device__ __forceinline__ void stage_tile_vectors(const ConvKParams &p, const TileCoord &tc, float *vb, int epi_tid)
+{
+    const int n = tc.n0 < p.batch ? tc.n0 : p.batch - 1;        // padded tile of an odd phase: any valid image
+    const int ch0 = tc.n_tile * BLOCK_N;
+    constexpr int Q = BLOCK_N / 4;
+    for (int i = epi_tid; i < kVecKinds * Q; i += THREADS) {
+        const int v = i / Q, c4 = i - v * Q;
+        const float *src = nullptr;
+        if (v == 0) src = p.rowscale ? p.rowscale + (long long)n * p.cout + ch0 : nullptr;
+        else if (v == 1) src = p.out2 ? p.scale2 + (long long)n * p.cout + ch0 : nullptr;
+        else if (v == 2) src = (p.epilogue == 1 && p.bias) ? p.bias + ch0 : nullptr;
+        else src = p.rgb_w ? p.rgb_w + ((long long)n * 3 + (v - 3)) * p.cout + ch0 : nullptr;
+        const float fill = (v == 0) ? 1.0f : 0.0f;
+        const float4 val = src ? __ldg(reinterpret_cast<const float4 *>(src) + c4) : make_float4(fill, fill, fill, fill);
+        *reinterpret_cast<float4 *>(vb + v * BLOCK_N + 4 * c4) = val;
+    }
+}
+
+template <int BLOCK_N, bool STAGED = false>
 __device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvOutMaps &om, const ConvPhase &ph,
                                               const TileCoord &tc, int q, int lane, int tx, int ty, int tn, uint32_t tmem_acc,
                                               uint64_t *tmem_full, uint32_t acc_par, uint8_t *stage, uint32_t &stage_sel,
-                                              float (&rgb)[3], long long &rgb_index)
+                                              float (&rgb)[3], long long &rgb_index, const float *vb = nullptr,
+                                              int c_begin = 0, int c_end = BLOCK_N / 32)
 {
     const int gx = tc.gx0 + tx, gy = tc.gy0 + ty, n = tc.n0 + tn;
     const bool valid = gx < ph.grid_w && gy < ph.grid_h && n < p.batch;
@@ -212,10 +259,28 @@ __device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvOu
     const int wy = tc.gy0 + ((row0 >> p.tw_log2) & ((1 << p.th_log2) - 1));
     const int wn = tc.n0 + (row0 >> (p.tw_log2 + p.th_log2));
     rgb[0] = rgb[1] = rgb[2] = 0.0f;
-    mbar_wait(tmem_full, acc_par);
+    // STAGED: rows leave through shared memory and coalesced 16-byte global stores (lanes 8k..8k+7 write the 128 bytes of
+    // one pixel) instead of TMA stores: nothing in the chunk loop waits for the TMA unit, which is busy with the loads.
+    // rowoff[i] = element offset of row (lane / 8 + 4 i) of this warp's 32 rows, or -1 outside the lattice.
+    long long rowoff[8];
+    const bool direct = STAGED && (p.debug & 8);
+    if (direct) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int R = q * 32 + (lane >> 3) + 4 * i;
+            const int rx = tc.gx0 + (R & ((1 << p.tw_log2) - 1));
+            const int ry = tc.gy0 + ((R >> p.tw_log2) & ((1 << p.th_log2) - 1));
+            const int rn = tc.n0 + (R >> (p.tw_log2 + p.th_log2));
+            const bool ok = rx < ph.grid_w && ry < ph.grid_h && rn < p.batch;
+            rowoff[i] = ok ? (long long)rn * p.out_img_stride + (long long)ry * p.out_row_stride +
+                             (long long)rx * p.out_pix_stride + ph.out_offset + 4 * (lane & 7) : -1;
+        }
+    }
+    mbar_wait_warp(tmem_full, acc_par, p.debug & 4);
     tcgen05_fence_after();
+    if (p.debug & 1) { rgb_index = 0; return false; }
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
         const int ch0 = tc.n_tile * BLOCK_N + c * 32;
@@ -225,17 +290,21 @@ __device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvOu
         uint8_t *buf1 = stage + (stage_sel & 1) * kStageBufBytes;
         uint8_t *buf2 = stage + ((stage_sel + 1) & 1) * kStageBufBytes;
         // the store that last read buf1 (two stores ago) must have finished reading shared memory
-        if (lane == 0) tma_store_wait_read<1>();
-        __syncwarp();
+        if (!direct) {
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+        }
         float y[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float v[4] = {__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                           __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])};
-            if (rs) { const float4 s = __ldg(rs + j); v[0] *= s.x; v[1] *= s.y; v[2] *= s.z; v[3] *= s.w; }
+            if (STAGED) { const float4 s = *reinterpret_cast<const float4 *>(vb + c * 32 + 4 * j); v[0] *= s.x; v[1] *= s.y; v[2] *= s.z; v[3] *= s.w; }
+            else if (rs) { const float4 s = __ldg(rs + j); v[0] *= s.x; v[1] *= s.y; v[2] *= s.z; v[3] *= s.w; }
             if (p.epilogue == 1) {
                 float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (bs) b = __ldg(bs + j);
+                if (STAGED) b = *reinterpret_cast<const float4 *>(vb + 2 * BLOCK_N + c * 32 + 4 * j);
+                else if (bs) b = __ldg(bs + j);
                 const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -250,28 +319,51 @@ __device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvOu
                 const float *w0 = p.rgb_w + (long long)n * 3 * p.cout + ch0 + 4 * j;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const float4 ww = __ldg(reinterpret_cast<const float4 *>(w0 + (long long)k * p.cout));
+                    const float4 ww = STAGED ? *reinterpret_cast<const float4 *>(vb + (3 + k) * BLOCK_N + c * 32 + 4 * j)
+                                             : __ldg(reinterpret_cast<const float4 *>(w0 + (long long)k * p.cout));
                     rgb[k] = fmaf(v[0], ww.x, fmaf(v[1], ww.y, fmaf(v[2], ww.z, fmaf(v[3], ww.w, rgb[k]))));
                 }
             }
         }
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) { tma_store_4d(&om.out[tc.phase], buf1, ch0, wx, wy, wn); tma_store_commit(); }
-        ++stage_sel;
-        if (s2) {
-            if (lane == 0) tma_store_wait_read<1>();
+        if (direct) {
             __syncwarp();
 #pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = (lane >> 3) + 4 * i;
+                const float4 o = *reinterpret_cast<const float4 *>(buf1 + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+                if (rowoff[i] >= 0) st_stream4(p.out + rowoff[i] + ch0, o);
+            }
+        } else {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) { tma_store_4d(&om.out[tc.phase], buf1, ch0, wx, wy, wn); tma_store_commit(); }
+        }
+        ++stage_sel;
+        if (STAGED ? (p.out2 != nullptr) : (s2 != nullptr)) {
+            if (!direct) {
+                if (lane == 0) tma_store_wait_read<1>();
+                __syncwarp();
+            }
+#pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float4 s = __ldg(s2 + j);
+                const float4 s = STAGED ? *reinterpret_cast<const float4 *>(vb + BLOCK_N + c * 32 + 4 * j) : __ldg(s2 + j);
                 *reinterpret_cast<float4 *>(buf2 + lane * 128 + ((j ^ (lane & 7)) << 4)) =
                     make_float4(round_tf32(y[4 * j] * s.x), round_tf32(y[4 * j + 1] * s.y), round_tf32(y[4 * j + 2] * s.z),
                                 round_tf32(y[4 * j + 3] * s.w));
             }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) { tma_store_4d(&om.out2[tc.phase], buf2, ch0, wx, wy, wn); tma_store_commit(); }
+            if (direct) {
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = (lane >> 3) + 4 * i;
+                    const float4 o = *reinterpret_cast<const float4 *>(buf2 + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+                    if (rowoff[i] >= 0) st_stream4(p.out2 + rowoff[i] + ch0, o);
+                }
+            } else {
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) { tma_store_4d(&om.out2[tc.phase], buf2, ch0, wx, wy, wn); tma_store_commit(); }
+            }
             ++stage_sel;
         }
     }
@@ -357,7 +449,7 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     const uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + s * B_BYTES));
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 8; ++k)  // K = 8 per instruction = 32 bytes along the swizzled row
-                        umma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
+                        if (!(p.debug & 2)) umma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
                     tcgen05_commit(&empty_bar[s]);         // frees the ring slot once these MMAs have read it
                 }
                 tcgen05_commit(&tmem_full_bar[acc]);       // accumulator complete
@@ -403,7 +495,9 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 // shared-memory operand traffic per SM drops from 128 to 96 B/clk at N = 128 (64 instead of 96 at N = 256) -- the limit
 // the single-CTA kernel hits on the 128-channel layers.  Protocol: both producers' TMA loads (cta_group::2 form)
 // complete on the LEADER's full barrier; the leader's tcgen05.commit multicasts to both CTAs' empty / tmem_full
-// barriers; all eight epilogue warps arrive on the leader's tmem_empty barrier.
+// barriers; all eight epilogue warps arrive on the leader's tmem_empty barrier.  Only the leader arms a full barrier
+// (one arrival + the bytes of BOTH CTAs): the peer's TMA bytes may land first, the transaction count then simply goes
+// negative until the leader's expect_tx -- a per-stage remote mbarrier.arrive from the peer costs ~190 ns each.
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -478,7 +572,7 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_b) : "memory");
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -505,7 +599,6 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                         const uint32_t s = it % STAGES, par = (it / STAGES) & 1;
                         mbar_wait(&empty_bar[s], par ^ 1);
                         if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * (A_BYTES + BH_BYTES));   // bytes of BOTH CTAs
-                        else mbar_arrive_leader(&full_bar[s]);
                         tma_load_4d_2sm(sA + s * A_BYTES, &tmap_a, &full_bar[s], kc * BLOCK_K, cx, cy, tc.n0);
                         tma_load_2d_2sm(sB + s * BH_BYTES, &tmap_b, &full_bar[s], ph.tap_k0[t] + kc * BLOCK_K,
                                         tc.n_tile * BLOCK_N + rank * (BLOCK_N / 2));
@@ -531,7 +624,7 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                     const uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + s * BH_BYTES));
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 8; ++k)
-                        umma_tf32_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
+                        if (!(p.debug & 2)) umma_tf32_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
                     tcgen05_commit_2sm(&empty_bar[s]);
                 }
                 tcgen05_commit_2sm(&tmem_full_bar[acc]);
@@ -571,8 +664,224 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     }
 }
 
+// ------------------------------------------------------------------------------------ halo variant of the CTA-pair kernel
+// The im2col kernels above fetch one activation box per (tap, K block): every input pixel crosses the L2 -> SM path
+// nine times for a 3x3 conv.  Measured (profiles/r1_ncu_full_summary.md): an SM sustains ~55 B/clk from L2, a
+// 128-pixel x N=128 tile wants 94-128 B/clk, hence 52-56 % tensor-pipe utilisation on the 128-channel layers.
+// Here a tile is 8 x 16 pixels of one image and the producer loads, per K block of 32 channels, ONE halo box
+// {32 ch, 8 + rx, 16 + ry} (rows of 128 B, TMA 128-byte swizzle, zero fill outside the image).  Every tap is then a
+// UMMA descriptor into that box: start address advanced by (dy * halo_w + dx) rows and stride-byte-offset = halo_w rows,
+// so 8-row group g of the operand is tile row g shifted by the tap.  The swizzle XOR is a function of the absolute
+// shared-memory address (profiles/r1_halo_descriptor_experiment.txt: any row shift and SBO = 1280 give exact results
+// with base_offset = 0), so the shifted views read exactly what the TMA unit wrote.  Taps of a strided gather (dgrad of
+// the stride-2 transposed conv) fall into up to four parity classes; each class has its own base-shifted tensor map and
+// halo box ("group").  Operand bytes per SM and K block for a 3x3 conv drop from 9 x (16 + 8) KB to 22.5 + 9 x 8 KB.
+constexpr int kHaloStageBytes = 23 * 1024;          // >= 10 x 18 rows x 128 B, multiple of the 1024-byte swizzle period
+constexpr int kMaxGroups = 6;
+
+struct HaloPhase {
+    int num_groups;
+    int g_map[kMaxGroups];                          // index into HaloMaps::a
+    int g_sbo[kMaxGroups];                          // halo width in bytes (rows of 128 B) = UMMA stride byte offset
+    int g_bytes[kMaxGroups];                        // box bytes (expect_tx)
+    int g_xoff[kMaxGroups], g_yoff[kMaxGroups];     // box origin relative to the tile origin, in lattice units of the map
+    int g_tap_begin[kMaxGroups], g_tap_end[kMaxGroups];
+    int tap_k0[9];                                  // first K column of the tap in the weight matrix (regrouped order)
+    int tap_aoff[9];                                // byte offset of the tap's first operand row inside the halo box
+};
+struct HaloParams { HaloPhase ph[kMaxPhases]; };
+struct alignas(64) HaloMaps { CUtensorMap a[kMaxGroups]; };
+
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// EPI_WARPS = 4 or 8 epilogue warps: with 8, two warps share each 32-lane TMEM quadrant and split the columns, which
+// doubles the number of independent tcgen05.ld -> math -> TMA-store chains that drain an accumulator.
+template <int BLOCK_N, int SA, int SB, int TPS, int EPI_WARPS>   // TPS = taps per weight stage (one barrier round trip per TPS taps)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS, 1)
+conv_halo_tf32_2cta_kernel(const __grid_constant__ HaloMaps amaps, const __grid_constant__ CUtensorMap tmap_b,
+                           const __grid_constant__ ConvOutMaps out_maps, const ConvKParams p, const HaloParams hp)
+{
+    constexpr int BH_BYTES = (BLOCK_N / 2) * BLOCK_K * 4;
+    constexpr int B_STAGE = TPS * BH_BYTES;
+    constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                                ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + SA * kHaloStageBytes;
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(smem + SA * kHaloStageBytes + SB * B_STAGE);
+    uint64_t *a_empty = a_full + SA;
+    uint64_t *b_full = a_empty + SA;
+    uint64_t *b_empty = b_full + SB;
+    uint64_t *tmem_full_bar = b_empty + SB;            // [2]
+    uint64_t *tmem_empty_bar = tmem_full_bar + 2;      // [2], used in the leader only
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+    uint8_t *epi_stage = smem + SA * kHaloStageBytes + SB * B_STAGE + 1024;
+    float *vec_stage = reinterpret_cast<float *>(epi_stage + EPI_WARPS * 2 * kStageBufBytes);   // [2][kVecKinds][BLOCK_N]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)(blockIdx.x & 1);            // __cluster_dims__(2,1,1): CTA rank in the pair
+    const int cluster = (int)(blockIdx.x >> 1), num_clusters = (int)(gridDim.x >> 1);
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < kMaxGroups; ++i) asm volatile("prefetch.tensormap [%0];" :: "l"(&amaps.a[i]) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_b) : "memory");
+        for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 2 * EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BLOCK_N)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {                                   // ===== TMA producer warp (both CTAs: own halo, own half of the weights)
+        uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+        for (int P = cluster; P < p.total_pairs; P += num_clusters) {
+            const TileCoord tc = decode_tile_pair(p, P, rank);
+            const HaloPhase &h = hp.ph[tc.phase];
+            const int brow = tc.n_tile * BLOCK_N + rank * (BLOCK_N / 2);
+            for (int kc = 0; kc < p.kblocks_per_tap; ++kc) {
+                for (int g = 0; g < h.num_groups; ++g) {
+                    mbar_wait_warp(&a_empty[sa], pa ^ 1, p.debug & 4);
+                    if (elect_one()) {
+                        if (rank == 0) mbar_expect_tx(&a_full[sa], 2 * (uint32_t)h.g_bytes[g]);
+                        tma_load_4d_2sm(sA + sa * kHaloStageBytes, &amaps.a[h.g_map[g]], &a_full[sa], kc * BLOCK_K,
+                                        tc.gx0 + h.g_xoff[g], tc.gy0 + h.g_yoff[g], tc.n0);
+                    }
+                    __syncwarp();
+                    if (++sa == SA) { sa = 0; pa ^= 1; }
+                    const int te = h.g_tap_end[g];
+                    for (int t = h.g_tap_begin[g]; t < te; t += TPS) {
+                        const int n = min(TPS, te - t);
+                        mbar_wait_warp(&b_empty[sb], pb ^ 1, p.debug & 4);
+                        if (elect_one()) {
+                            if (rank == 0) mbar_expect_tx(&b_full[sb], 2 * (uint32_t)n * BH_BYTES);
+#pragma unroll
+                            for (int j = 0; j < TPS; ++j)
+                                if (j < n)
+                                    tma_load_2d_2sm(sB + sb * B_STAGE + j * BH_BYTES, &tmap_b, &b_full[sb],
+                                                    h.tap_k0[t + j] + kc * BLOCK_K, brow);
+                        }
+                        __syncwarp();
+                        if (++sb == SB) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {                               // ===== MMA warp (leader CTA only), one elected lane issues
+            uint32_t sa = 0, pa = 0, sb = 0, pb = 0, lt = 0;
+            const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
+            for (int P = cluster; P < p.total_pairs; P += num_clusters, ++lt) {
+                const TileCoord tc = decode_tile_pair(p, P, 0);
+                const HaloPhase &h = hp.ph[tc.phase];
+                const uint32_t acc = lt & 1, acc_par = (lt >> 1) & 1;
+                mbar_wait_warp(&tmem_empty_bar[acc], acc_par ^ 1, p.debug & 4);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                uint32_t accumulate = 0;
+                for (int kc = 0; kc < p.kblocks_per_tap; ++kc) {
+                    for (int g = 0; g < h.num_groups; ++g) {
+                        mbar_wait_warp(&a_full[sa], pa, p.debug & 4);
+                        tcgen05_fence_after();
+                        const uint32_t a_base = sA_u32 + sa * kHaloStageBytes;
+                        const uint32_t sbo = (uint32_t)h.g_sbo[g];
+                        const int te = h.g_tap_end[g];
+                        for (int t = h.g_tap_begin[g]; t < te; t += TPS) {
+                            const int n = min(TPS, te - t);
+                            mbar_wait_warp(&b_full[sb], pb, p.debug & 4);
+                            tcgen05_fence_after();
+                            const uint32_t b_base = sB_u32 + sb * B_STAGE;
+                            if (elect_one()) {
+#pragma unroll
+                                for (int j = 0; j < TPS; ++j) {
+                                    if (j < n) {
+                                        const uint64_t da = make_kmajor_sw128_desc_sbo(a_base + (uint32_t)h.tap_aoff[t + j], sbo);
+                                        const uint64_t db = make_kmajor_sw128_desc(b_base + j * BH_BYTES);
+#pragma unroll
+                                        for (int k = 0; k < BLOCK_K / 8; ++k) {
+                                            if (!(p.debug & 2))
+                                                umma_tf32_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, accumulate);
+                                            accumulate = 1;
+                                        }
+                                    }
+                                }
+                                tcgen05_commit_2sm(&b_empty[sb]);
+                            }
+                            __syncwarp();
+                            accumulate = 1;
+                            if (++sb == SB) { sb = 0; pb ^= 1; }
+                        }
+                        if (elect_one()) tcgen05_commit_2sm(&a_empty[sa]);   // halo box free once all of its taps have been read
+                        __syncwarp();
+                        if (++sa == SA) { sa = 0; pa ^= 1; }
+                    }
+                }
+                if (elect_one()) tcgen05_commit_2sm(&tmem_full_bar[acc]);
+                __syncwarp();
+            }
+        }
+    } else {                                           // ===== epilogue (both CTAs, each on its own 128 TMEM lanes)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int tx = row & ((1 << p.tw_log2) - 1);
+        const int ty = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
+        const int tn = row >> (p.tw_log2 + p.th_log2);
+        uint32_t lt = 0, stage_sel = 0;
+        const int half = (warp - 2) >> 2;                                   // which half of the columns (EPI_WARPS = 8)
+        constexpr int CHUNKS = BLOCK_N / 32 / (EPI_WARPS / 4);
+        uint8_t *my_stage = epi_stage + (warp - 2) * 2 * kStageBufBytes;
+        for (int P = cluster; P < p.total_pairs; P += num_clusters, ++lt) {
+            const TileCoord tc = decode_tile_pair(p, P, rank);
+            const ConvPhase &ph = p.ph[tc.phase];
+            const uint32_t acc = lt & 1, acc_par = (lt >> 1) & 1;
+            float rgb[3];
+            long long rgb_index;
+            // per-tile vectors -> shared memory (double buffered), published to the 4 epilogue warps by a named barrier;
+            // the global loads overlap the wait for the accumulator
+            float *vb = vec_stage + (lt & 1) * (kVecKinds * BLOCK_N);
+            stage_tile_vectors<BLOCK_N, 32 * EPI_WARPS>(p, tc, vb, (int)threadIdx.x - 64);
+            asm volatile("bar.sync 1, %0;" :: "n"(32 * EPI_WARPS) : "memory");
+            const bool valid = epilogue_tile<BLOCK_N, true>(p, out_maps, ph, tc, q, lane, tx, ty, tn, tmem_base + acc * BLOCK_N,
+                                                            &tmem_full_bar[acc], acc_par, my_stage, stage_sel, rgb, rgb_index, vb,
+                                                            half * CHUNKS, (half + 1) * CHUNKS);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
+            if (p.rgb_w && valid) {
+                float *dst = p.rgb_out + rgb_index;
+                atomicAdd(dst, rgb[0]); atomicAdd(dst + 1, rgb[1]); atomicAdd(dst + 2, rgb[2]);
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)(2 * BLOCK_N)) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------ wgrad
-// dW[co, t, ci] += sum over (image, pixel) of  G[n, gy*ga + gdy_t, gx*ga + gdx_t, co] * X[n, gy*xa + xdy_t, gx*xa + xdx_t, ci]
+// dW[co, t, ci] += sum over (image, pixel) of G[n, gy*ga + gdy_t, gx*ga + gdx_t, co] * X[n, gy*xa + xdy_t, gx*xa + xdx_t, ci]
 // i.e. D = A^T B with the reduction (K) running over pixels.  Both operands are read straight from the NHWC
 // tensors, so they are MN-major for the tensor core: a TMA box {32 channels, TW, TH, TN} lands as 64 K-rows of
 // 128 bytes (two 4-row swizzle atoms per K=8 instruction); M = 128 output channels = 4 such column blocks, LBO apart.
@@ -728,7 +1037,7 @@ wgrad_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rank = (int)cluster_ctarank();
+    const int rank = (int)(blockIdx.x & 1);            // __cluster_dims__(2,1,1)
     const int pair = blockIdx.x >> 1;
     const int m_tile = pair / p.n_tiles, n_tile = pair % p.n_tiles;      // in units of 256 channels
     const int tap = blockIdx.y;
@@ -739,7 +1048,7 @@ wgrad_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_g) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_x) : "memory");
-        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -765,7 +1074,6 @@ wgrad_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 const int gx0 = tile_x << p.tw_log2, gy0 = tile_y << p.th_log2, n0 = tile_n << p.tn_log2;
                 uint8_t *sa = smem + s * WG_STAGE_BYTES, *sb = sa + 4 * WG_COLBLK_BYTES;
                 if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * WG_STAGE_BYTES);
-                else mbar_arrive_leader(&full_bar[s]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     tma_load_4d_2sm(sa + j * WG_COLBLK_BYTES, &tmap_g, &full_bar[s], m_tile * 256 + rank * 128 + j * 32,
@@ -914,6 +1222,106 @@ int launch_conv_2cta(const CUtensorMap &ta, const CUtensorMap &tb, const ConvOut
     return SR_OK;
 }
 
+template <int BLOCK_N, int SA, int SB, int TPS, int EPI_WARPS>
+int launch_conv_halo(const HaloMaps &am, const CUtensorMap &tb, const ConvOutMaps &om, const ConvKParams &p, const HaloParams &hp,
+                     cudaStream_t st)
+{
+    constexpr int BH_BYTES = (BLOCK_N / 2) * BLOCK_K * 4;
+    const size_t smem = 1024 + (size_t)SA * kHaloStageBytes + (size_t)SB * TPS * BH_BYTES + 1024 +
+                        (size_t)EPI_WARPS * 2 * kStageBufBytes + 2 * kVecKinds * BLOCK_N * sizeof(float);
+    static_assert(1024 + SA * kHaloStageBytes + SB * TPS * BH_BYTES + 1024 + EPI_WARPS * 2 * kStageBufBytes +
+                  2 * kVecKinds * BLOCK_N * 4 <= 232448, "halo kernel: shared memory budget");
+    auto kern = conv_halo_tf32_2cta_kernel<BLOCK_N, SA, SB, TPS, EPI_WARPS>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("conv: cudaFuncSetAttribute(halo): %s", cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    int clusters = p.total_pairs < kNumSMs / 2 ? p.total_pairs : kNumSMs / 2;
+    kern<<<2 * clusters, 64 + 32 * EPI_WARPS, smem, st>>>(am, tb, om, p, hp);
+    return SR_OK;
+}
+
+// Group the taps of every phase by parity class modulo the input stride and describe each class as a halo box
+// (see conv_halo_tf32_2cta_kernel).  Returns false when the problem does not fit the halo kernel.
+bool build_halo(const sr_conv_args *args, int count, EncodeTiledFn enc, HaloParams &hp, HaloMaps &am)
+{
+    const sr_conv_args *a = args;
+    const int s = a->in_stride;
+    // Default: one (8 + rx)-wide box per parity class; operand groups then start on arbitrary 128-byte rows, which costs
+    // nothing (scratch/umma_align_bench.cu: 64.0 clk per M128 x N128 x K8 for every start row / SBO).  SR_HALO_SPLITX=1
+    // loads one 8-wide box per (class, dx) instead, so every group starts on a 1024-byte atom (experiment; slower).
+    static const char *splitx_env = getenv("SR_HALO_SPLITX");
+    const bool splitx = splitx_env && splitx_env[0] == '1';
+    struct MapKey { int cy, cx, hw, hh; } keys[kMaxGroups];
+    int num_maps = 0;
+    for (int i = 0; i < kMaxPhases; ++i) {
+        HaloPhase &h = hp.ph[i];
+        const sr_conv_args *b = args + (i < count ? i : 0);
+        h.num_groups = 0;
+        int cls_y[kMaxGroups], cls_x[kMaxGroups], cls_q[kMaxGroups], minx[kMaxGroups], maxx[kMaxGroups], miny[kMaxGroups],
+            maxy[kMaxGroups];
+        int tap_group[9];
+        for (int t = 0; t < b->num_taps; ++t) {
+            const int cy = pos_mod_i(b->tap_dy[t], s), cx = pos_mod_i(b->tap_dx[t], s);
+            const int qy = floor_div_i(b->tap_dy[t], s), qx = floor_div_i(b->tap_dx[t], s);
+            int g = 0;
+            for (; g < h.num_groups; ++g) if (cls_y[g] == cy && cls_x[g] == cx && (!splitx || cls_q[g] == qx)) break;
+            if (g == h.num_groups) {
+                if (g == kMaxGroups) return false;
+                cls_y[g] = cy; cls_x[g] = cx; cls_q[g] = qx; minx[g] = maxx[g] = qx; miny[g] = maxy[g] = qy;
+                ++h.num_groups;
+            }
+            if (qx < minx[g]) minx[g] = qx;
+            if (qx > maxx[g]) maxx[g] = qx;
+            if (qy < miny[g]) miny[g] = qy;
+            if (qy > maxy[g]) maxy[g] = qy;
+            tap_group[t] = g;
+        }
+        int pos = 0;
+        for (int g = 0; g < h.num_groups; ++g) {
+            const int hw = 8 + maxx[g] - minx[g], hh = 16 + maxy[g] - miny[g];
+            if (hw * hh * 128 > kHaloStageBytes || hw > 256 || hh > 256) return false;
+            int m = 0;
+            for (; m < num_maps; ++m)
+                if (keys[m].cy == cls_y[g] && keys[m].cx == cls_x[g] && keys[m].hw == hw && keys[m].hh == hh) break;
+            if (m == num_maps) {
+                if (m == kMaxGroups) return false;
+                const int64_t lw = (a->in_w - cls_x[g] + s - 1) / s, lh = (a->in_h - cls_y[g] + s - 1) / s;
+                if (lw < 1 || lh < 1) return false;
+                const float *base = a->in + ((int64_t)cls_y[g] * a->in_w + cls_x[g]) * a->cin;
+                cuuint64_t dims[4] = {(cuuint64_t)a->cin, (cuuint64_t)lw, (cuuint64_t)lh, (cuuint64_t)a->batch};
+                cuuint64_t strides[3] = {(cuuint64_t)a->cin * 4 * s, (cuuint64_t)a->in_w * a->cin * 4 * s,
+                                         (cuuint64_t)a->in_h * a->in_w * a->cin * 4};
+                cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)hw, (cuuint32_t)hh, 1};
+                cuuint32_t estr[4] = {1, 1, 1, 1};
+                if (enc(&am.a[m], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+                keys[m] = {cls_y[g], cls_x[g], hw, hh};
+                ++num_maps;
+            }
+            h.g_map[g] = m; h.g_sbo[g] = hw * 128; h.g_bytes[g] = hw * hh * 128;
+            h.g_xoff[g] = minx[g]; h.g_yoff[g] = miny[g];
+            h.g_tap_begin[g] = pos;
+            for (int t = 0; t < b->num_taps; ++t) {
+                if (tap_group[t] != g) continue;
+                h.tap_k0[pos] = (int)(b->tap_w[t] * a->cin);
+                h.tap_aoff[pos] = ((floor_div_i(b->tap_dy[t], s) - miny[g]) * hw + (floor_div_i(b->tap_dx[t], s) - minx[g])) * 128;
+                ++pos;
+            }
+            h.g_tap_end[g] = pos;
+        }
+        for (int g = h.num_groups; g < kMaxGroups; ++g) {
+            h.g_map[g] = 0; h.g_sbo[g] = 1024; h.g_bytes[g] = 0; h.g_xoff[g] = h.g_yoff[g] = 0; h.g_tap_begin[g] = h.g_tap_end[g] = 0;
+        }
+        for (int t = pos; t < 9; ++t) { h.tap_k0[t] = 0; h.tap_aoff[t] = 0; }
+    }
+    for (int m = num_maps; m < kMaxGroups; ++m) am.a[m] = am.a[0];
+    return num_maps >= 1;
+}
+
 }  // namespace
 }  // namespace sr
 
@@ -952,9 +1360,25 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
     if (!enc) { set_error("conv: cuTensorMapEncodeTiled not available from the driver"); return SR_ERR_DRIVER; }
     cudaStream_t st = (cudaStream_t)stream;
 
+    // Halo kernel (8 x 16 pixel tiles of one image, one activation box per K block instead of one per tap) whenever
+    // the lattice is large enough for CTA pairs; SR_CONV_HALO=0 keeps the im2col kernels (A/B comparison).
+    static const char *force_halo = getenv("SR_CONV_HALO");
+    HaloParams hp;
+    HaloMaps am;
+    bool use_halo = max_gw >= 8 && max_gh >= 16 && !(force_halo && force_halo[0] == '0');
+    if (use_halo) {
+        long long mt2 = 0;
+        for (int i = 0; i < count; ++i) {
+            const long long t_ph = ((args[i].grid_w + 7) / 8) * ((args[i].grid_h + 15) / 16) * a->batch;
+            mt2 += (t_ph + 1) / 2 * 2;
+        }
+        use_halo = mt2 / 2 * (a->cout / 128) >= 32 && build_halo(args, count, enc, hp, am);
+    }
+
     // tile shape: 16x8 pixels of one image, or several whole small images
     int tw, th, tn;
-    if (max_gw > 8) { tw = 16; th = 8; tn = 1; }
+    if (use_halo) { tw = 8; th = 16; tn = 1; }
+    else if (max_gw > 8) { tw = 16; th = 8; tn = 1; }
     else if (max_gw > 4) { tw = 8; th = (max_gh > 4) ? 8 : 4; tn = 128 / (tw * th); }
     else { tw = 4; th = 4; tn = 8; }
 
@@ -985,7 +1409,7 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
     }
     // few tiles (low resolutions): prefer 128-wide N tiles so more SMs take part
     int block_n = (a->cout % 256 == 0) ? 256 : 128;
-    if (block_n == 256 && m_tiles * (a->cout / 256) < kNumSMs / 2) block_n = 128;
+    if (block_n == 256 && (use_halo ? m_tiles2 / 2 : m_tiles) * (a->cout / 256) < kNumSMs / 2) block_n = 128;
     p.n_tiles = (int)(a->cout / block_n);
     SR_REQUIRE(m_tiles * p.n_tiles < 0x7fffffffll, "conv: too many tiles");
     p.total_tiles = (int)(m_tiles * p.n_tiles);
@@ -995,6 +1419,7 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
     static const char *force_2cta = getenv("SR_CONV_2CTA");
     bool use_2cta = p.total_pairs >= kNumSMs / 2;      // measured: 921 vs 839 TF/s (512 ch @64^2), 880 vs 783 (256 ch @128^2)
     if (force_2cta) use_2cta = force_2cta[0] == '1';
+    if (use_halo) use_2cta = true;
 
     CUtensorMap ta, tb;
     {
@@ -1064,13 +1489,25 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
     p.alpha = a->alpha; p.gain = a->gain;
     p.rgb_w = a->rgb_weight; p.rgb_out = a->rgb_out;
     SR_REQUIRE(!p.rgb_w || p.rgb_out, "conv: rgb_weight needs rgb_out");
+    static const char *debug_env = getenv("SR_CONV_DEBUG");
+    p.debug = debug_env ? atoi(debug_env) : 0;
     if (p.rgb_w) {
         cudaError_t e = cudaMemsetAsync(p.rgb_out, 0, sizeof(float) * 3 * (size_t)(a->batch * a->out_h * a->out_w), st);
         if (e != cudaSuccess) { set_error("conv: memset(rgb_out): %s", cudaGetErrorString(e)); return (int)e; }
     }
 
     int rc;
-    if (use_2cta) {
+    if (use_halo) {
+        // 8 epilogue warps pay when a 128-channel tile also writes the pre-modulated second output (measured 0.93 ->
+        // 0.84 ms at 128 ch / 256^2); elsewhere 4 warps and one more pipeline stage are as fast or faster.
+        static const char *epi_env = getenv("SR_CONV_EPI_WARPS");          // A/B: force 4 or 8 epilogue warps
+        bool epi8 = a->out2 != nullptr && block_n == 128;
+        if (epi_env) epi8 = epi_env[0] == '8';
+        if (block_n == 256) rc = epi8 ? launch_conv_halo<256, 2, 6, 1, 8>(am, tb, om, p, hp, st)
+                                      : launch_conv_halo<256, 2, 7, 1, 4>(am, tb, om, p, hp, st);
+        else rc = epi8 ? launch_conv_halo<128, 2, 4, 3, 8>(am, tb, om, p, hp, st)
+                       : launch_conv_halo<128, 3, 4, 3, 4>(am, tb, om, p, hp, st);
+    } else if (use_2cta) {
         if (block_n == 256) rc = launch_conv_2cta<256, 6>(ta, tb, om, p, st);
         else rc = launch_conv_2cta<128, 8>(ta, tb, om, p, st);
     } else if (block_n == 256) rc = launch_conv<256, 4>(ta, tb, om, p, st);

@@ -29,7 +29,9 @@ def relerr(got, want):
 
 
 CASES = [(2, 16, 16, 64, 128), (3, 8, 8, 32, 256), (9, 4, 4, 96, 128), (1, 24, 40, 32, 384), (2, 64, 64, 128, 128),
-         (5, 5, 5, 32, 128), (2, 9, 9, 64, 256), (1, 17, 33, 32, 128)]
+         (5, 5, 5, 32, 128), (2, 9, 9, 64, 256), (1, 17, 33, 32, 128),
+         # large enough for the halo CTA-pair kernel (8 x 16 tiles, one activation box per K block)
+         (8, 32, 32, 64, 128), (4, 40, 56, 32, 256), (16, 33, 17, 32, 128), (8, 64, 64, 32, 256), (6, 32, 48, 128, 384)]
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -53,8 +55,9 @@ def test_plain_conv_and_dgrad(tc, case):
         assert relerr(nchw(dx), ref) < 2e-5, case
 
 
-def test_styled_epilogue(tc):
-    b, h, w, cin, cout = 3, 16, 16, 64, 128
+@pytest.mark.parametrize("shape", [(3, 16, 16, 64, 128), (8, 32, 32, 64, 128), (5, 48, 40, 32, 256)])
+def test_styled_epilogue(tc, shape):
+    b, h, w, cin, cout = shape
     x = tc.modulate(nhwc(seeded((b, cin, h, w), 4)).cuda())
     wt = seeded((cout, cin, 3, 3), 5).cuda()
     wm = tc.weight_prep(wt, 0.04, 0)
@@ -82,7 +85,7 @@ def test_styled_epilogue(tc):
 
 
 @pytest.mark.parametrize("case", [(2, 4, 4, 64, 128), (2, 8, 8, 32, 128), (1, 16, 16, 32, 256), (3, 32, 32, 64, 128),
-                                  (1, 7, 12, 32, 128)])
+                                  (1, 7, 12, 32, 128), (8, 32, 32, 128, 128), (6, 24, 40, 128, 256), (16, 16, 16, 128, 128)])
 def test_transposed_conv_and_its_dgrad(tc, case):
     b, h, w, cin, cout = case
     x = tc.modulate(nhwc(seeded((b, cin, h, w), 11)).cuda())
