@@ -27,7 +27,7 @@ extern "C" {
 #define SR_ERR_DRIVER (-3)
 
 /* ABI version (bumped on any signature change) and last error text. */
-int sr_abi_version(void);   /* currently 2 */
+int sr_abi_version(void);   /* currently 3 */
 const char *sr_last_error(void);
 /* Number of kernel launches issued by this library in this process (bench.py's gpu_launches). */
 int64_t sr_launch_count(void);
@@ -238,6 +238,46 @@ int sr_styled_bwd_prologue2_f32(float *ga, float *g_bias, float *g_noise_w, floa
  * out or dot may be NULL; dot is zeroed by the call. */
 int sr_scale_dot_nhwc_f32(float *out, float *dot, const float *a, const float *other, const float *scale,
                           int64_t batch, int64_t pixels, int64_t channels, int round_out_tf32, void *stream);
+
+/* ------------------------------------------------------------------ style path (all layers per launch) ----
+ * Replaces, for every modulated convolution of a network at once, the reference's per-layer
+ *   style = self.modulation(style)                              (EqualLinear, reference layers.py:232-239, 295)
+ *   demod = rsqrt(weight.pow(2).sum([2,3,4]) + 1e-8)            (reference layers.py:297-299)
+ * in the activation-scaling form of this package (the style scales the activations, the demodulation the outputs):
+ *   s[b,i] = mod_scale * sum_k latent[b, latent_index, k] * mod_weight[i,k] + lr_mul * mod_bias[i]
+ *   d[b,o] = rsqrt( sum_i s[b,i]^2 * wsq[o,i] + eps ),   wsq[o,i] = scale^2 * sum_taps W[o,i,:]^2  (sr_weight_sq_f32)
+ * `layers` is a HOST array of n_layers <= 32 descriptors with DEVICE pointers; every layer is one slice of the same
+ * launches (2 forward, 4 backward).  latent: [batch, n_latent, style_dim].
+ * Backward: given g_s / g_d (either may be NULL) it writes g_mod_weight, g_mod_bias, g_wsq (zeros when the layer has
+ * no demodulation gradient) and accumulates g_latent [batch, n_latent, style_dim] (zeroed by the call);
+ * gs_total [batch, cin] and du [batch, cout] are caller-provided workspaces. */
+typedef struct sr_style_layer {
+    const float *mod_weight;   /* [cin, style_dim] */
+    const float *mod_bias;     /* [cin] */
+    const float *wsq;          /* [cout, cin] or NULL (no demodulation) */
+    float *s;                  /* [batch, cin]  (forward: out, backward: in) */
+    float *d;                  /* [batch, cout] (forward: out, backward: in), NULL without demodulation */
+    int32_t cin, cout, latent_index, reserved;
+    const float *g_s;          /* backward inputs */
+    const float *g_d;
+    float *g_mod_weight;       /* backward outputs */
+    float *g_mod_bias;
+    float *g_wsq;
+    float *gs_total;           /* backward workspaces */
+    float *du;
+} sr_style_layer;
+int sr_style_scales_forward_f32(const sr_style_layer *layers, int n_layers, const float *latent, int64_t batch,
+                                int64_t n_latent, int64_t style_dim, float mod_scale, float lr_mul, float eps, void *stream);
+int sr_style_scales_backward_f32(const sr_style_layer *layers, int n_layers, const float *latent, float *g_latent,
+                                 int64_t batch, int64_t n_latent, int64_t style_dim, float mod_scale, float lr_mul,
+                                 void *stream);
+/* wsq[o,i] = scale^2 * sum_t w[o,i,t]^2 (w: [cout, cin, taps], the reference weight layout) and its gradient
+ * gw[o,i,t] = 2 scale^2 w[o,i,t] g_wsq[o,i]. */
+int sr_weight_sq_f32(float *wsq, const float *w, float scale, int64_t cout, int64_t cin, int taps, void *stream);
+int sr_weight_sq_backward_f32(float *gw, const float *w, const float *g_wsq, float scale, int64_t cout, int64_t cin,
+                              int taps, void *stream);
+/* gw[o,i,t] = scale * dwk[o,t,i]: result of sr_conv_wgrad_tf32 ([cout][taps][cin]) -> reference weight layout. */
+int sr_weight_grad_layout_f32(float *gw, const float *dwk, float scale, int64_t cout, int64_t cin, int taps, void *stream);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@
 // produce them), fp32 accumulation: the same arithmetic class as the reference's cuDNN path under
 // torch's default cudnn.allow_tf32 = True.
 #include "common.cuh"
-#include <cuda.h>
+#include "tma_host.cuh"
 #include <stdlib.h>
 
 namespace sr {
@@ -1168,24 +1168,6 @@ weight_prep_kernel(float *__restrict__ dst, const float *__restrict__ w, float s
 }
 
 // ------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_tiled() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
 int ilog2_exact(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 template <int BLOCK_N, int STAGES>

@@ -17,6 +17,8 @@
 // Everything that is not one of the specialised (up, down, taps, phase) combinations, or has
 // minor > 1, takes the generic one-thread-per-output kernel.
 #include "common.cuh"
+#include "tma_host.cuh"
+#include <stdlib.h>
 
 namespace sr {
 namespace {
@@ -324,6 +326,186 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
     }
 }
 
+// ---- channels-last FIR through TMA-staged tiles (up = down = 1, 4x4 taps, C % 32 == 0, planes >= 32 x 32) --------------
+// Persistent CTAs walk the tile list; a tile is 16 x 32 output pixels x 32 channels.  A producer warp fetches the
+// {32 ch, 19, 35} input box of the next tile with ONE TMA instruction into a 2-stage shared-memory ring (zero fill
+// outside the plane = the FIR padding, so there is not a single bounds test on the load side) while 8 consumer warps
+// run the FIR out of shared memory: thread = 4 channels x 2 columns x 8 rows, sliding 4 x 5 register window fed by
+// LDS.128 (lanes 0-7 read the 128 contiguous bytes of one pixel -> conflict free), results leave as 16-byte stores
+// whose 8-lane groups cover whole 128-byte lines.  HBM sees each input byte once (tile halos overlap in L2).
+constexpr int FT_W = 16, FT_C = 32, FT_STAGES = 2;
+constexpr int FT_IW = FT_W + 3;
+constexpr int FT_CONSUMERS = 256;
+
+struct FirTmaGeom {
+    int out_h, out_w, c, cblocks, tiles_x, tiles_y, total_tiles, pad0;
+    FastDiv div_cb, div_tx, div_ty;
+    const float *noise, *noise_weight, *bias;
+    long long noise_bstride;
+    float alpha, gain;
+    float *out2;
+    const float *scale2, *other;
+    float *dot;
+};
+
+__device__ __forceinline__ void ft_mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nFTW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra FTD_%=;\nbra FTW_%=;\nFTD_%=:\n}\n"
+        :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+template <int MODE, int FT_H, int TR>     // MODE 0 plain, 1 styled forward tail (+ optional out2), 2 scale-dot backward tail
+__global__ void __launch_bounds__(FT_CONSUMERS + 32, FT_H == 32 ? 1 : 2)   // FT_H = 32: one CTA per SM, 16: two; TR < 4: timing experiment only
+fir_nhwc_tma_kernel(float *__restrict__ out, const __grid_constant__ CUtensorMap tmap_x, const float *__restrict__ taps,
+                    const FirTmaGeom g)
+{
+    constexpr int FT_IH = FT_H + 3, FT_STAGE_BYTES = FT_IW * FT_IH * FT_C * 4, RPS = FT_H / 4;   // rows per strip
+    extern __shared__ uint8_t ft_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(ft_raw) + 127) & ~(uintptr_t)127);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + FT_STAGES * FT_STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + FT_STAGES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_x) : "memory");
+        for (int s = 0; s < FT_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&full_bar[s])), "r"(1u) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&empty_bar[s])), "r"(8u) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == FT_CONSUMERS / 32) {                   // ===== producer warp
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            for (uint32_t T = blockIdx.x; T < (uint32_t)g.total_tiles; T += gridDim.x) {
+                uint32_t t = T, cb, tx, ty, n;
+                g.div_cb.divmod(t, t, cb);
+                g.div_tx.divmod(t, t, tx);
+                g.div_ty.divmod(t, n, ty);
+                ft_mbar_wait(&empty_bar[s], ph ^ 1);
+                const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&full_bar[s]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t)FT_STAGE_BYTES) : "memory");
+                asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                             :: "r"((uint32_t)__cvta_generic_to_shared(smem + s * FT_STAGE_BYTES)), "l"(&tmap_x), "r"(bar),
+                                "r"((int)(cb * FT_C)), "r"((int)(tx * FT_W) - g.pad0), "r"((int)(ty * FT_H) - g.pad0), "r"((int)n) : "memory");
+                if (++s == FT_STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers
+    float tk[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) tk[a][b] = __ldg(taps + (3 - a) * 4 + (3 - b));
+    const int q4 = threadIdx.x & 7, cp = (threadIdx.x >> 3) & 7, strip = threadIdx.x >> 6;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    float nw = 0.0f;
+    if (MODE == 1 && g.noise) nw = __ldg(g.noise_weight);
+
+    uint32_t s = 0, ph = 0;
+    for (uint32_t T = blockIdx.x; T < (uint32_t)g.total_tiles; T += gridDim.x) {
+        uint32_t t = T, cb, tx, ty, n;
+        g.div_cb.divmod(t, t, cb);
+        g.div_tx.divmod(t, t, tx);
+        g.div_ty.divmod(t, n, ty);
+        const int ox0 = tx * FT_W + 2 * cp, oy0 = ty * FT_H + RPS * strip;
+        const int ch = cb * FT_C + 4 * q4;
+        float4 bias4 = zero, sc2 = zero;
+        if (MODE == 1 && g.bias) bias4 = __ldg(reinterpret_cast<const float4 *>(g.bias + ch));
+        if ((MODE == 1 && g.out2) || MODE == 2) sc2 = __ldg(reinterpret_cast<const float4 *>(g.scale2 + (long long)n * g.c + ch));
+        const long long pix0 = ((long long)n * g.out_h) * g.out_w;       // first output pixel of the image
+        float4 dot = zero;
+
+        ft_mbar_wait(&full_bar[s], ph);
+        const float4 *tile = reinterpret_cast<const float4 *>(smem + s * FT_STAGE_BYTES) + q4;
+        // window rows: input row (8*strip + r) of the box, columns 2cp .. 2cp+4
+        float4 win[4][5];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 5; ++b) win[a][b] = tile[((RPS * strip + a) * FT_IW + 2 * cp + b) * (FT_C / 4)];
+#pragma unroll
+        for (int r = 0; r < RPS; ++r) {
+#pragma unroll
+            for (int b = 0; b < 5; ++b) win[3][b] = tile[((RPS * strip + r + 3) * FT_IW + 2 * cp + b) * (FT_C / 4)];
+            const int oy = oy0 + r;
+            const bool row_ok = oy < g.out_h;
+            float4 tt[2] = {zero, zero};
+            if (MODE == 2 && row_ok) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    if (ox0 + j < g.out_w)
+                        tt[j] = __ldg(reinterpret_cast<const float4 *>(g.other + (pix0 + (long long)oy * g.out_w + ox0 + j) * g.c + ch));
+            }
+            float4 acc[2] = {zero, zero};
+#pragma unroll
+            for (int a = 0; a < TR; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const float4 v = win[a][j + b];
+                        const float k = tk[a][b];
+                        acc[j].x = fmaf(v.x, k, acc[j].x); acc[j].y = fmaf(v.y, k, acc[j].y);
+                        acc[j].z = fmaf(v.z, k, acc[j].z); acc[j].w = fmaf(v.w, k, acc[j].w);
+                    }
+            if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (ox0 + j >= g.out_w) break;
+                    const long long pix = pix0 + (long long)oy * g.out_w + ox0 + j;
+                    float4 y = acc[j];
+                    if (MODE == 1) {
+                        const float add = g.noise ? nw * __ldg(g.noise + (long long)n * g.noise_bstride + (long long)oy * g.out_w + ox0 + j) : 0.0f;
+                        float u;
+                        u = y.x + add + bias4.x; y.x = ((u > 0.f) ? u : u * g.alpha) * g.gain;
+                        u = y.y + add + bias4.y; y.y = ((u > 0.f) ? u : u * g.alpha) * g.gain;
+                        u = y.z + add + bias4.z; y.z = ((u > 0.f) ? u : u * g.alpha) * g.gain;
+                        u = y.w + add + bias4.w; y.w = ((u > 0.f) ? u : u * g.alpha) * g.gain;
+                    }
+                    if (MODE == 2) {
+                        dot.x = fmaf(y.x, tt[j].x, dot.x); dot.y = fmaf(y.y, tt[j].y, dot.y);
+                        dot.z = fmaf(y.z, tt[j].z, dot.z); dot.w = fmaf(y.w, tt[j].w, dot.w);
+                        y.x = round_tf32_(y.x * sc2.x); y.y = round_tf32_(y.y * sc2.y);
+                        y.z = round_tf32_(y.z * sc2.z); y.w = round_tf32_(y.w * sc2.w);
+                    }
+                    *reinterpret_cast<float4 *>(out + pix * g.c + ch) = y;
+                    if (MODE == 1 && g.out2) {
+                        float4 o;
+                        o.x = round_tf32_(y.x * sc2.x); o.y = round_tf32_(y.y * sc2.y);
+                        o.z = round_tf32_(y.z * sc2.z); o.w = round_tf32_(y.w * sc2.w);
+                        *reinterpret_cast<float4 *>(g.out2 + pix * g.c + ch) = o;
+                    }
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 5; ++b) win[a][b] = win[a + 1][b];
+        }
+        // this warp no longer reads the stage
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"((uint32_t)__cvta_generic_to_shared(&empty_bar[s])) : "memory");
+        if (MODE == 2) {        // lanes with equal channel quad (l, l^8, l^16, l^24) -> one 128-bit reduction per quad and warp
+#pragma unroll
+            for (int o = 8; o < 32; o <<= 1) {
+                dot.x += __shfl_xor_sync(0xffffffffu, dot.x, o); dot.y += __shfl_xor_sync(0xffffffffu, dot.y, o);
+                dot.z += __shfl_xor_sync(0xffffffffu, dot.z, o); dot.w += __shfl_xor_sync(0xffffffffu, dot.w, o);
+            }
+            if (lane < 8) {
+                float *dp = g.dot + (long long)n * g.c + ch;
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dp), "f"(dot.x), "f"(dot.y), "f"(dot.z), "f"(dot.w) : "memory");
+            }
+        }
+        if (++s == FT_STAGES) { s = 0; ph ^= 1; }
+    }
+}
+
 // ---- generic: one thread per output element, any geometry ---------------------------------------
 struct GenericGeom {
     int64_t major, minor, total;
@@ -407,11 +589,84 @@ int launch_tile(float *out, const float *x, const float *taps, int64_t major, in
     return SR_OK;
 }
 
+// TMA path of launch_nhwc: returns SR_ERR_UNSUPPORTED when the shape does not qualify.
+int launch_nhwc_tma(float *out, const float *x, const float *taps, int64_t major, int in_h, int in_w, int oh, int ow,
+                    int64_t minor, int pad0, int mode, const float *noise, long long noise_bstride, const float *noise_weight,
+                    const float *bias, float alpha, float gain, cudaStream_t st, float *out2, const float *scale2,
+                    const float *other, float *dot)
+{
+    // Opt-in (SR_FIR_TMA=1).  Measured on the B=32 generator step (profiles/r1_fir_tma_experiment.md): 1.48 / 1.93 ms for
+    // the forward / backward tails against 1.44 / 1.53 ms of the register-window kernel above; halving the FMAs moves it
+    // by 5 %, so neither variant is arithmetic bound -- the L1-cached direct loads with 16 resident warps hide latency
+    // better than 8 consumer warps behind a 2-stage TMA ring.
+    static const char *on = getenv("SR_FIR_TMA");
+    if (!(on && on[0] == '1')) return SR_ERR_UNSUPPORTED;
+    if (minor % FT_C != 0 || oh < 32 || ow < 32 || (reinterpret_cast<uintptr_t>(x) & 15u)) return SR_ERR_UNSUPPORTED;
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return SR_ERR_UNSUPPORTED;
+    CUtensorMap tm;
+    cuuint64_t dims[4] = {(cuuint64_t)minor, (cuuint64_t)in_w, (cuuint64_t)in_h, (cuuint64_t)major};
+    cuuint64_t strides[3] = {(cuuint64_t)minor * 4, (cuuint64_t)in_w * minor * 4, (cuuint64_t)in_h * in_w * minor * 4};
+    static const char *dbg = getenv("SR_FIR_DEBUG");            // 1: half the taps (timing experiment), 2: 16-row tiles, 2 CTAs/SM
+    const int variant = dbg ? atoi(dbg) : 0;
+    const int FT_H = (variant & 2) ? 16 : 32, FT_IH = FT_H + 3, FT_STAGE_BYTES = FT_IW * FT_IH * FT_C * 4;
+    cuuint32_t box[4] = {FT_C, FT_IW, (cuuint32_t)FT_IH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return SR_ERR_UNSUPPORTED;
+    FirTmaGeom g;
+    g.out_h = oh; g.out_w = ow; g.c = (int)minor; g.cblocks = (int)(minor / FT_C);
+    g.tiles_x = (ow + FT_W - 1) / FT_W; g.tiles_y = (oh + FT_H - 1) / FT_H;
+    const int64_t total = (int64_t)major * g.tiles_x * g.tiles_y * g.cblocks;
+    if (total >= 0x7fffffffll) return SR_ERR_UNSUPPORTED;
+    g.total_tiles = (int)total; g.pad0 = pad0;
+    g.div_cb = FastDiv((uint32_t)g.cblocks); g.div_tx = FastDiv((uint32_t)g.tiles_x); g.div_ty = FastDiv((uint32_t)g.tiles_y);
+    g.noise = noise; g.noise_weight = noise_weight; g.bias = bias; g.noise_bstride = noise_bstride;
+    g.alpha = alpha; g.gain = gain; g.out2 = out2; g.scale2 = scale2; g.other = other; g.dot = dot;
+    const size_t smem = 128 + (size_t)FT_STAGES * FT_STAGE_BYTES + 64;
+    const int slots = (variant & 2) ? 2 * kNumSMs : kNumSMs;
+    const int grid = total < slots ? (int)total : slots;
+    static bool configured[12] = {};
+    auto launch = [&](auto kern, int idx) -> int {
+        if (!configured[idx]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return SR_ERR_UNSUPPORTED;
+            configured[idx] = true;
+        }
+        kern<<<grid, FT_CONSUMERS + 32, smem, st>>>(out, tm, taps, g);
+        return SR_OK;
+    };
+    if (variant == 1) {
+        if (mode == 2) return launch(fir_nhwc_tma_kernel<2, 32, 2>, 3);
+        if (mode == 1) return launch(fir_nhwc_tma_kernel<1, 32, 2>, 4);
+        return launch(fir_nhwc_tma_kernel<0, 32, 2>, 5);
+    }
+    if (variant == 2) {
+        if (mode == 2) return launch(fir_nhwc_tma_kernel<2, 16, 4>, 6);
+        if (mode == 1) return launch(fir_nhwc_tma_kernel<1, 16, 4>, 7);
+        return launch(fir_nhwc_tma_kernel<0, 16, 4>, 8);
+    }
+    if (variant == 3) {
+        if (mode == 2) return launch(fir_nhwc_tma_kernel<2, 16, 2>, 9);
+        if (mode == 1) return launch(fir_nhwc_tma_kernel<1, 16, 2>, 10);
+        return launch(fir_nhwc_tma_kernel<0, 16, 2>, 11);
+    }
+    if (mode == 2) return launch(fir_nhwc_tma_kernel<2, 32, 4>, 2);
+    if (mode == 1) return launch(fir_nhwc_tma_kernel<1, 32, 4>, 1);
+    return launch(fir_nhwc_tma_kernel<0, 32, 4>, 0);
+}
+
 int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, int in_h, int in_w, int oh, int ow,
                 int64_t minor, int pad_x0, int pad_y0, bool styled, const float *noise, long long noise_bstride,
                 const float *noise_weight, const float *bias, float alpha, float gain, cudaStream_t st,
                 float *out2 = nullptr, const float *scale2 = nullptr, const float *other = nullptr, float *dot = nullptr)
 {
+    if (pad_x0 == pad_y0) {
+        const int rc = launch_nhwc_tma(out, x, taps, major, in_h, in_w, oh, ow, minor, pad_x0, dot ? 2 : (styled ? 1 : 0), noise,
+                                       noise_bstride, noise_weight, bias, alpha, gain, st, out2, scale2, other, dot);
+        if (rc == SR_OK) return rc;
+    }
     NhwcGeom g;
     g.out2 = out2; g.scale2 = scale2; g.other = other; g.dot = dot;
     g.major = major; g.in_h = in_h; g.in_w = in_w; g.out_h = oh; g.out_w = ow;

@@ -11,6 +11,7 @@ import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
+from . import style
 from . import tc_conv as tc
 from .op.upfirdn2d import upfirdn2d_raw
 
@@ -226,7 +227,7 @@ class StyledLayerTC(Function):
             dxs = tc.conv3x3_s2_gather(ga, tc.weight_prep(weight[0], scale, 2), (h, w))
             dwk = tc.wgrad_transpose3x3_s2(ga, xs)
         g_d = e / d
-        g_w = (dwk.view(cout, 3, 3, cin).permute(0, 3, 1, 2) * scale).unsqueeze(0)
+        g_w = style.weight_grad_layout(dwk, scale, cout, cin, 3)
         return (from_nhwc(dxs), g_w, g_d, None, g_noise_w, g_bias, ds_next, dwb, None, None, None, None, None)
 
 
@@ -238,29 +239,31 @@ def chain_supported(gen, x):
     return all(type(m).__name__ == "StyledConv" and supported(m.conv, x) for m in blocks)
 
 
-def _rgb_weights(to_rgb, style):
-    """Per-sample modulated 1x1 weights of a ToRGB [B,3,C] (reference layers.py:296 with demodulate=False)."""
+def _rgb_weights(to_rgb, s):
+    """Per-sample modulated 1x1 weights of a ToRGB [B,3,C] (reference layers.py:296 with demodulate=False); s = its style."""
     conv = to_rgb.conv
-    s = conv.modulation(style)
     return (conv.weight[0, :, :, 0, 0] * conv.scale).unsqueeze(0) * s.unsqueeze(1)
 
 
 def generator_chain_forward(gen, latent, noise):
     """Generator.forward body on the chained tensor-core blocks (same math as reference model.py:169-182)."""
     blocks = [gen.conv1] + list(gen.convs)
-    lat_idx = list(range(len(blocks)))                       # conv1 -> latent[:,0], convs[j] -> latent[:, j+1]
-    scales = [blk.conv.style_scales(latent[:, li]) for blk, li in zip(blocks, lat_idx)]
+    # ToRGB after conv1 (latent 1) and after the second conv of every resolution (block k even, latent k + 1)
+    rgbs = {0: (gen.to_rgb1, 1)}
+    rgbs.update({k: (gen.to_rgbs[k // 2 - 1], k + 1) for k in range(2, len(blocks), 2)})
+    # all modulation / demodulation vectors of the network in one batched call (style.py): conv k uses latent[:, k]
+    mods = [blk.conv for blk in blocks] + [rgbs[k][0].conv for k in sorted(rgbs)]
+    lat_idx = list(range(len(blocks))) + [rgbs[k][1] for k in sorted(rgbs)]
+    sd = style.style_scales_all(latent, mods, lat_idx)
+    scales = sd[:len(blocks)]
+    rgb_style = {k: sd[len(blocks) + j][0] for j, k in enumerate(sorted(rgbs))}
     x0 = gen.input(latent)
     xs = ModulateTC.apply(x0, scales[0][0])
     skip = None
     for k, blk in enumerate(blocks):
         s_next = scales[k + 1][0] if k + 1 < len(blocks) else None
-        to_rgb, rgb_lat = None, None
-        if k == 0:
-            to_rgb, rgb_lat = gen.to_rgb1, 1
-        elif k % 2 == 0:                                     # after the second conv of every resolution
-            to_rgb, rgb_lat = gen.to_rgbs[k // 2 - 1], k + 1
-        wb = _rgb_weights(to_rgb, latent[:, rgb_lat]) if to_rgb is not None else None
+        to_rgb = rgbs[k][0] if k in rgbs else None
+        wb = _rgb_weights(to_rgb, rgb_style[k]) if to_rgb is not None else None
         b, _, h, w = xs.shape
         oh, ow = (2 * h, 2 * w) if blk.conv.upsample else (h, w)
         nz = noise[k]

@@ -373,3 +373,43 @@ def test_generator_tcgen05_backend_matches_cudnn_backend():
         worst = min(worst, c)
         assert c > 0.99, f"{n}: cosine {c:.5f}"
     print("worst gradient cosine tcgen05 vs fp32 composed path:", worst)
+
+
+def test_style_scales_all_vs_torch():
+    """Batched style path (csrc/style_ops.cu: s, d for every layer in one call) against the per-layer torch formulation
+    ModulatedConv2d.style_scales (reference layers.py:232-239, 295-299) in float64, values and all gradients."""
+    from stylerenderer_b200 import layers as L, style
+    from make_golden import seeded
+    torch.manual_seed(5)
+    b, n_latent, k = 5, 6, 96
+    specs = [(64, 128, 3, True), (128, 40, 3, True), (40, 3, 1, False), (72, 64, 3, True)]       # cin, cout, ksize, demod
+    mods = [L.ModulatedConv2d(ci, co, ks, k, demodulate=dm).cuda() for ci, co, ks, dm in specs]
+    for j, m in enumerate(mods):
+        with torch.no_grad():
+            m.modulation.bias.copy_(seeded(m.modulation.bias.shape, 40 + j).cuda() * 0.3 + 1)
+    lat_idx = [0, 3, 3, 5]
+    latent = seeded((b, n_latent, k), 50).cuda().requires_grad_(True)
+    got = style.style_scales_all(latent, mods, lat_idx)
+    flat = [t for sd in got for t in sd if t is not None]
+    cots = [seeded(t.shape, 60 + i).cuda() for i, t in enumerate(flat)]
+    params = [p for m in mods for p in (m.modulation.weight, m.modulation.bias, m.weight)]
+    grads = torch.autograd.grad(flat, [latent] + params, cots, allow_unused=True)
+    # torch formulation in float64
+    lat64 = latent.detach().double().requires_grad_(True)
+    p64, want = [], []
+    for m, li in zip(mods, lat_idx):
+        wm, bm, w = (t.detach().double().requires_grad_(True) for t in (m.modulation.weight, m.modulation.bias, m.weight))
+        p64 += [wm, bm, w]
+        s = torch.nn.functional.linear(lat64[:, li], wm * m.modulation.scale, bm * m.modulation.lr_mul)
+        want.append(s)
+        if m.demodulate:
+            wsq = (w[0] * m.scale).pow(2).sum([2, 3])
+            want.append(torch.rsqrt(torch.nn.functional.linear(s * s, wsq) + m.eps))
+    for g, w_ in zip(flat, want):
+        torch.testing.assert_close(g.double(), w_.detach(), rtol=2e-5, atol=1e-6)
+    want_g = torch.autograd.grad(want, [lat64] + p64, [c.double() for c in cots], allow_unused=True)
+    for i, (g, w_) in enumerate(zip(grads, want_g)):
+        if w_ is None:
+            assert g is None or float(g.abs().max()) == 0, i
+            continue
+        torch.testing.assert_close(g.double(), w_, rtol=1e-4, atol=1e-5 * float(w_.abs().max()) + 1e-9, msg=lambda m_: f"grad {i}: {m_}")

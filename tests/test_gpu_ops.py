@@ -140,7 +140,10 @@ def test_upfirdn2d_vs_oracle(op, case):
 
 
 @pytest.mark.parametrize("shape,pad", [((2, 8, 9, 9), (1, 1)), ((1, 128, 33, 33), (1, 1)), ((3, 12, 16, 16), (2, 2)),
-                                       ((2, 64, 5, 7), (2, 1)), ((1, 4, 64, 64), (2, 2))])
+                                       ((2, 64, 5, 7), (2, 1)), ((1, 4, 64, 64), (2, 2)),
+                                       # TMA-staged tile kernel (C % 32 == 0, output >= 32 x 32), ragged edges and pads
+                                       ((2, 64, 70, 45), (1, 1)), ((1, 32, 40, 100), (2, 2)), ((3, 96, 33, 47), (2, 1)),
+                                       ((1, 256, 65, 65), (1, 1))])
 def test_upfirdn2d_channels_last(op, shape, pad):
     """channels_last tensors take the NHWC kernel (no layout copy) and keep their memory format, fwd and bwd."""
     x = seeded(shape, 30)
