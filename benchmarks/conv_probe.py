@@ -29,3 +29,10 @@ elif kind == "up":
     out = torch.empty(B, 2 * r + 1, 2 * r + 1, cout, device=dev)
     ms = time_ms(lambda: tc.conv_transpose3x3_s2(x, wm, out=out, rowscale=d))
     print(f"up {cin}->{cout} @{r}: {ms:.4f} ms ({flop/ms/1e9:.0f} TF) env HALO={os.environ.get('SR_CONV_HALO')} DEBUG={os.environ.get('SR_CONV_DEBUG')} SPLITX={os.environ.get('SR_HALO_SPLITX')}")
+elif kind == "gather":
+    g = tc.modulate(torch.randn(B, 2 * r + 1, 2 * r + 1, cout, device=dev))
+    wg = tc.weight_prep(w, 0.02, 2)
+    out = torch.empty(B, r, r, cin, device=dev)
+    sc = torch.rand(B, cin, device=dev) + 0.5
+    ms = time_ms(lambda: tc.conv3x3_s2_gather(g, wg, (r, r), out=out, rowscale=sc))
+    print(f"gather(dgrad of up) {cin}<-{cout} @{r}: {ms:.4f} ms ({flop/ms/1e9:.0f} TF) env HALO={os.environ.get('SR_CONV_HALO')} DEBUG={os.environ.get('SR_CONV_DEBUG')}")

@@ -413,47 +413,51 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        if (lane == 0) {                               // ===== TMA producer
-            uint32_t it = 0;
-            for (int T = blockIdx.x; T < p.total_tiles; T += gridDim.x) {
-                const TileCoord tc = decode_tile(p, T);
-                const ConvPhase &ph = p.ph[tc.phase];
-                for (int t = 0; t < ph.num_taps; ++t) {
-                    const int cx = tc.gx0 * p.in_stride + ph.tap_dx[t], cy = tc.gy0 * p.in_stride + ph.tap_dy[t];
-                    for (int kc = 0; kc < p.kblocks_per_tap; ++kc, ++it) {
-                        const uint32_t s = it % STAGES, par = (it / STAGES) & 1;
-                        mbar_wait(&empty_bar[s], par ^ 1);
+    if (warp == 0) {                                   // ===== TMA producer warp (converged loop, elect_one issues)
+        uint32_t s = 0, par = 0;
+        for (int T = blockIdx.x; T < p.total_tiles; T += gridDim.x) {
+            const TileCoord tc = decode_tile(p, T);
+            const ConvPhase &ph = p.ph[tc.phase];
+            for (int t = 0; t < ph.num_taps; ++t) {
+                const int cx = tc.gx0 * p.in_stride + ph.tap_dx[t], cy = tc.gy0 * p.in_stride + ph.tap_dy[t];
+                for (int kc = 0; kc < p.kblocks_per_tap; ++kc) {
+                    mbar_wait(&empty_bar[s], par ^ 1);
+                    if (elect_one()) {
                         mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
                         tma_load_4d(sA + s * A_BYTES, &tmap_a, &full_bar[s], kc * BLOCK_K, cx, cy, tc.n0);
                         tma_load_2d(sB + s * B_BYTES, &tmap_b, &full_bar[s], ph.tap_k0[t] + kc * BLOCK_K, tc.n_tile * BLOCK_N);
                     }
+                    __syncwarp();
+                    if (++s == STAGES) { s = 0; par ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {                               // ===== MMA issuer
-            uint32_t it = 0, lt = 0;
-            for (int T = blockIdx.x; T < p.total_tiles; T += gridDim.x, ++lt) {
-                const TileCoord tc = decode_tile(p, T);
-                const int num_kb = p.ph[tc.phase].num_taps * p.kblocks_per_tap;
-                const uint32_t acc = lt & 1, acc_par = (lt >> 1) & 1;
-                mbar_wait(&tmem_empty_bar[acc], acc_par ^ 1);      // epilogue has drained this accumulator
+    } else if (warp == 1) {                            // ===== MMA warp
+        uint32_t s = 0, par = 0, lt = 0;
+        const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
+        for (int T = blockIdx.x; T < p.total_tiles; T += gridDim.x, ++lt) {
+            const TileCoord tc = decode_tile(p, T);
+            const int num_kb = p.ph[tc.phase].num_taps * p.kblocks_per_tap;
+            const uint32_t acc = lt & 1, acc_par = (lt >> 1) & 1;
+            mbar_wait(&tmem_empty_bar[acc], acc_par ^ 1);          // epilogue has drained this accumulator
+            tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full_bar[s], par);
                 tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const uint32_t s = it % STAGES, par = (it / STAGES) & 1;
-                    mbar_wait(&full_bar[s], par);
-                    tcgen05_fence_after();
-                    const uint64_t da = make_kmajor_sw128_desc(smem_u32(sA + s * A_BYTES));
-                    const uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + s * B_BYTES));
+                const uint64_t da = make_kmajor_sw128_desc(sA_u32 + s * A_BYTES);
+                const uint64_t db = make_kmajor_sw128_desc(sB_u32 + s * B_BYTES);
+                if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 8; ++k)  // K = 8 per instruction = 32 bytes along the swizzled row
+                    for (int k = 0; k < BLOCK_K / 8; ++k)      // K = 8 per instruction = 32 bytes along the swizzled row
                         if (!(p.debug & 2)) umma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
-                    tcgen05_commit(&empty_bar[s]);         // frees the ring slot once these MMAs have read it
+                    tcgen05_commit(&empty_bar[s]);             // frees the ring slot once these MMAs have read it
                 }
-                tcgen05_commit(&tmem_full_bar[acc]);       // accumulator complete
+                __syncwarp();
+                if (++s == STAGES) { s = 0; par ^= 1; }
             }
+            if (elect_one()) tcgen05_commit(&tmem_full_bar[acc]);  // accumulator complete
+            __syncwarp();
         }
     } else {                                           // ===== epilogue: warp w reads TMEM lanes 32*(w%4)..+31
         const int q = warp & 3;
@@ -566,8 +570,8 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     uint8_t *epi_stage = smem + STAGES * (A_BYTES + BH_BYTES) + 1024;  // 1024-byte aligned (swizzle), 8 KB per epilogue warp
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rank = (int)cluster_ctarank();
-    const int cluster = (int)cluster_id_x(), num_clusters = (int)cluster_count_x();
+    const int rank = (int)(blockIdx.x & 1);            // __cluster_dims__(2,1,1)
+    const int cluster = (int)(blockIdx.x >> 1), num_clusters = (int)(gridDim.x >> 1);
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_a) : "memory");
@@ -587,28 +591,30 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        if (lane == 0) {                               // ===== TMA producer (both CTAs)
-            uint32_t it = 0;
-            for (int P = cluster; P < p.total_pairs; P += num_clusters) {
-                const TileCoord tc = decode_tile_pair(p, P, rank);
-                const ConvPhase &ph = p.ph[tc.phase];
-                for (int t = 0; t < ph.num_taps; ++t) {
-                    const int cx = tc.gx0 * p.in_stride + ph.tap_dx[t], cy = tc.gy0 * p.in_stride + ph.tap_dy[t];
-                    for (int kc = 0; kc < p.kblocks_per_tap; ++kc, ++it) {
-                        const uint32_t s = it % STAGES, par = (it / STAGES) & 1;
-                        mbar_wait(&empty_bar[s], par ^ 1);
+    if (warp == 0) {                                   // ===== TMA producer warp (both CTAs)
+        uint32_t s = 0, par = 0;
+        for (int P = cluster; P < p.total_pairs; P += num_clusters) {
+            const TileCoord tc = decode_tile_pair(p, P, rank);
+            const ConvPhase &ph = p.ph[tc.phase];
+            for (int t = 0; t < ph.num_taps; ++t) {
+                const int cx = tc.gx0 * p.in_stride + ph.tap_dx[t], cy = tc.gy0 * p.in_stride + ph.tap_dy[t];
+                for (int kc = 0; kc < p.kblocks_per_tap; ++kc) {
+                    mbar_wait(&empty_bar[s], par ^ 1);
+                    if (elect_one()) {
                         if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * (A_BYTES + BH_BYTES));   // bytes of BOTH CTAs
                         tma_load_4d_2sm(sA + s * A_BYTES, &tmap_a, &full_bar[s], kc * BLOCK_K, cx, cy, tc.n0);
                         tma_load_2d_2sm(sB + s * BH_BYTES, &tmap_b, &full_bar[s], ph.tap_k0[t] + kc * BLOCK_K,
                                         tc.n_tile * BLOCK_N + rank * (BLOCK_N / 2));
                     }
+                    __syncwarp();
+                    if (++s == STAGES) { s = 0; par ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {                  // ===== MMA issuer (leader CTA only)
-            uint32_t it = 0, lt = 0;
+        if (rank == 0) {                               // ===== MMA warp (leader CTA only)
+            uint32_t s = 0, par = 0, lt = 0;
+            const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
             for (int P = cluster; P < p.total_pairs; P += num_clusters, ++lt) {
                 const TileCoord tc = decode_tile_pair(p, P, 0);
                 const int num_kb = p.ph[tc.phase].num_taps * p.kblocks_per_tap;
@@ -616,18 +622,22 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                 mbar_wait(&tmem_empty_bar[acc], acc_par ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const uint32_t s = it % STAGES, par = (it / STAGES) & 1;
+                for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[s], par);
                     tcgen05_fence_after();
-                    const uint64_t da = make_kmajor_sw128_desc(smem_u32(sA + s * A_BYTES));
-                    const uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + s * BH_BYTES));
+                    const uint64_t da = make_kmajor_sw128_desc(sA_u32 + s * A_BYTES);
+                    const uint64_t db = make_kmajor_sw128_desc(sB_u32 + s * BH_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 8; ++k)
-                        if (!(p.debug & 2)) umma_tf32_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
-                    tcgen05_commit_2sm(&empty_bar[s]);
+                        for (int k = 0; k < BLOCK_K / 8; ++k)
+                            if (!(p.debug & 2)) umma_tf32_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
+                        tcgen05_commit_2sm(&empty_bar[s]);
+                    }
+                    __syncwarp();
+                    if (++s == STAGES) { s = 0; par ^= 1; }
                 }
-                tcgen05_commit_2sm(&tmem_full_bar[acc]);
+                if (elect_one()) tcgen05_commit_2sm(&tmem_full_bar[acc]);
+                __syncwarp();
             }
         }
     } else {                                           // ===== epilogue (both CTAs, each on its own 128 TMEM lanes)
@@ -1347,7 +1357,11 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
     static const char *force_halo = getenv("SR_CONV_HALO");
     HaloParams hp;
     HaloMaps am;
-    bool use_halo = max_gw >= 8 && max_gh >= 16 && !(force_halo && force_halo[0] == '0');
+    // Only where one box serves many taps (the plain 3x3 conv and its dgrad): for the 4/2/2/1-tap phases of the transposed
+    // conv and for the strided gather the per-tap boxes of the im2col kernel were measured as fast or faster.
+    bool use_halo = max_gw >= 8 && max_gh >= 16 && a->in_stride == 1 && count == 1 && a->num_taps >= 6 &&
+                    !(force_halo && force_halo[0] == '0');
+    if (force_halo && force_halo[0] == '2') use_halo = max_gw >= 8 && max_gh >= 16;      // experiment: halo everywhere
     if (use_halo) {
         long long mt2 = 0;
         for (int i = 0; i < count; ++i) {
