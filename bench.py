@@ -532,7 +532,11 @@ def main():
             e.record()
             torch.cuda.synchronize()
             region_ms = s.elapsed_time(e)
-        roof = dominant_kernel_roofline(kt.stats(), peaks, region_ms, min(args.steps, 5))
+        # share of the step: kernel time per step over the eager device time per step (both CUDA-event timed)
+        n_prof = min(args.steps, 5)
+        roof = dominant_kernel_roofline(kt.stats(), peaks, n_prof * ms_eager / args.steps, n_prof)
+        if roof is not None:
+            roof["profiled_region_ms_per_step"] = round(region_ms / n_prof, 3)
 
     value = world * B * args.steps / (ms * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)

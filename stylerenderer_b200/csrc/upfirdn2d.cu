@@ -133,6 +133,108 @@ upfirdn2d_tile_kernel(float *__restrict__ out, const float *__restrict__ x, cons
     const float *wbase = s_in + ((size_t)p * g.tin_h + sy * SY) * g.tin_stride + sx * SX;
     if (plane >= g.major || ox0 + sx * VX >= g.out_w || oy0 + sy * VY >= g.out_h) return;
 
+    const int ox = ox0 + sx * VX, oyb = oy0 + sy * VY;
+    if (plane >= g.major || ox >= g.out_w) return;
+
+    if (UP == 1 && DOWN == 1 && VY > 2) {
+        // Streaming strip (the blur layers): input rows flow through a 4-deep ring of open output rows, so a thread
+        // produces VX x VY outputs from (VY + KH - 1) x 2 vector loads.  Rank-1 taps (every FIR the model builds is
+        // an outer product, reference layers.py:7-12) take the separable form: KW FMAs for the row filter plus KH to
+        // scatter it over the open rows = 8 instead of 16 FMAs per output; the kernel was issue bound, not HBM bound.
+        int pa = 0, pb = 0;
+        float best = 0.0f;
+#pragma unroll
+        for (int a = 0; a < KH; ++a)
+#pragma unroll
+            for (int b = 0; b < KW; ++b)
+                if (fabsf(tk[a][b]) > best) { best = fabsf(tk[a][b]); pa = a; pb = b; }
+        float kv[KH], kh[KW];
+        bool sep = best > 0.0f;
+        float pivot = 1.0f;
+#pragma unroll
+        for (int a = 0; a < KH; ++a)
+#pragma unroll
+            for (int b = 0; b < KW; ++b)
+                if (a == pa && b == pb) pivot = tk[a][b];
+#pragma unroll
+        for (int a = 0; a < KH; ++a) {
+            kv[a] = 0.0f;
+#pragma unroll
+            for (int b = 0; b < KW; ++b) if (b == pb) kv[a] = tk[a][b];
+        }
+#pragma unroll
+        for (int b = 0; b < KW; ++b) {
+            kh[b] = 0.0f;
+#pragma unroll
+            for (int a = 0; a < KH; ++a) if (a == pa) kh[b] = tk[a][b] / pivot;
+        }
+#pragma unroll
+        for (int a = 0; a < KH; ++a)
+#pragma unroll
+            for (int b = 0; b < KW; ++b)
+                sep = sep && fabsf(kv[a] * kh[b] - tk[a][b]) <= 1e-6f * best;
+
+        float acc[KH][VX];
+#pragma unroll
+        for (int a = 0; a < KH; ++a)
+#pragma unroll
+            for (int vx = 0; vx < VX; ++vx) acc[a][vx] = 0.0f;
+#pragma unroll
+        for (int ir = 0; ir < VY + KH - 1; ++ir) {
+            const float *row = wbase + ir * g.tin_stride;
+            float v[NWXP];
+#pragma unroll
+            for (int b = 0; b < NWXP; b += 4) {
+                const float4 q = *reinterpret_cast<const float4 *>(row + b);
+                v[b] = q.x; v[b + 1] = q.y; v[b + 2] = q.z; v[b + 3] = q.w;
+            }
+            if (sep) {
+                float hrow[VX];
+#pragma unroll
+                for (int vx = 0; vx < VX; ++vx) {
+                    float t = 0.0f;
+#pragma unroll
+                    for (int b = 0; b < KW; ++b) t = fmaf(v[vx + b], kh[b], t);
+                    hrow[vx] = t;
+                }
+#pragma unroll
+                for (int a = 0; a < KH; ++a) {
+                    const int orow = ir - a;                      // output row this input row feeds through tap row a
+                    if (orow < 0 || orow >= VY) continue;
+#pragma unroll
+                    for (int vx = 0; vx < VX; ++vx) acc[orow % KH][vx] = fmaf(hrow[vx], kv[a], acc[orow % KH][vx]);
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < KH; ++a) {
+                    const int orow = ir - a;
+                    if (orow < 0 || orow >= VY) continue;
+#pragma unroll
+                    for (int vx = 0; vx < VX; ++vx)
+#pragma unroll
+                        for (int b = 0; b < KW; ++b) acc[orow % KH][vx] = fmaf(v[vx + b], tk[a][b], acc[orow % KH][vx]);
+                }
+            }
+            const int done = ir - (KH - 1);                       // output row completed by this input row
+            if (done >= 0) {
+                const int oy = oyb + done;
+                if (oy < g.out_h) {
+                    float *dst = out + (plane * g.out_h + oy) * (int64_t)g.out_w + ox;
+                    if (g.vec_store && ox + VX <= g.out_w) {
+                        *reinterpret_cast<float4 *>(dst) = make_float4(acc[done % KH][0], acc[done % KH][1], acc[done % KH][2], acc[done % KH][3]);
+                    } else {
+#pragma unroll
+                        for (int vx = 0; vx < VX; ++vx)
+                            if (ox + vx < g.out_w) dst[vx] = acc[done % KH][vx];
+                    }
+                }
+#pragma unroll
+                for (int vx = 0; vx < VX; ++vx) acc[done % KH][vx] = 0.0f;
+            }
+        }
+        return;
+    }
+
     float win[NWY][NWXP];
 #pragma unroll
     for (int a = 0; a < NWY; ++a) {
@@ -151,8 +253,6 @@ upfirdn2d_tile_kernel(float *__restrict__ out, const float *__restrict__ x, cons
         }
     }
 
-    const int ox = ox0 + sx * VX, oyb = oy0 + sy * VY;
-    if (plane >= g.major || ox >= g.out_w) return;
 #pragma unroll
     for (int vy = 0; vy < VY; ++vy) {
         const int oy = oyb + vy;
@@ -765,7 +865,11 @@ extern "C" int sr_upfirdn2d_f32(float *out, const float *x, const float *taps,
 #define SR_TILE(UP, DOWN, PHX, PHY, VY) \
     rc = launch_tile<UP, DOWN, 4, 4, PHX, PHY, VY>(out, x, taps, major, (int)in_h, (int)in_w, (int)oh, (int)ow, \
                                                    pad_x0, pad_y0, st)
-        if (up_x == 1 && down_x == 1) SR_TILE(1, 1, 0, 0, 2);
+        if (up_x == 1 && down_x == 1) {
+            static const char *strip_env = getenv("SR_UPFIRDN_STRIP");      // A/B: 0 = 4x2 register patch (round-1 kernel)
+            if (strip_env && strip_env[0] == '0') SR_TILE(1, 1, 0, 0, 2);
+            else SR_TILE(1, 1, 0, 0, 8);
+        }
         else if (up_x == 1 && down_x == 2) SR_TILE(1, 2, 0, 0, 2);
         else if (up_x == 2 && down_x == 1) {
             const int phx = pos_mod_i(pad_x0, 2), phy = pos_mod_i(pad_y0, 2);

@@ -139,6 +139,20 @@ def test_upfirdn2d_vs_oracle(op, case):
     torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("shape,pad", [((2, 3, 9, 9), (1, 1)), ((3, 5, 65, 65), (1, 1)), ((1, 2, 257, 257), (1, 1)),
+                                       ((2, 2, 64, 100), (2, 2)), ((1, 3, 31, 200), (2, 1)), ((40, 7, 5, 5), (1, 1))])
+def test_upfirdn2d_separable_taps(op, shape, pad):
+    """Rank-1 FIRs (the only kind the model builds: make_kernel, reference layers.py:7-12) take the separable strip path
+    of the NCHW tile kernel; asymmetric factors so that a wrong flip or a row/column mix-up cannot cancel."""
+    x = seeded(shape, 33)
+    for kv, kh in ((torch.tensor([1., 3., 3., 1.]), torch.tensor([1., 3., 3., 1.])), (seeded((4,), 34), seeded((4,), 35))):
+        k = (kv[:, None] * kh[None, :])
+        k = k / k.abs().sum()
+        want = O.upfirdn2d(x, k, 1, 1, pad)
+        got = op.upfirdn2d(cuda(x), cuda(k), pad=pad).cpu()
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+
+
 @pytest.mark.parametrize("shape,pad", [((2, 8, 9, 9), (1, 1)), ((1, 128, 33, 33), (1, 1)), ((3, 12, 16, 16), (2, 2)),
                                        ((2, 64, 5, 7), (2, 1)), ((1, 4, 64, 64), (2, 2)),
                                        # TMA-staged tile kernel (C % 32 == 0, output >= 32 x 32), ragged edges and pads
