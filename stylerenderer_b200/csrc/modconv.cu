@@ -157,6 +157,10 @@ struct ConvKParams {
     int kblocks_per_tap;                    // cin / 32
     int num_phases, n_tiles, total_tiles;   // total_tiles = (sum of M tiles) * n_tiles
     int total_pairs;                        // CTA-pair kernel: (sum of padded M tiles / 2) * n_tiles
+    // optional tile-major order for multi-phase launches: the phases of one spatial tile back to back, so the four parity
+    // classes of a transposed conv read their shared input tile from L2 instead of streaming the input from DRAM
+    // once per phase (ncu, 256->128 @128^2: 2.15 GB read for a 0.54 GB input with phase-major order); see the host side
+    int interleave, tiles_x_max, tiles_y_max, tiles_n;
     ConvPhase ph[kMaxPhases];
     int in_stride;
     int cout;
@@ -183,12 +187,22 @@ struct alignas(64) ConvOutMaps {
 constexpr int kStageBufBytes = 32 * 128;               // one warp, one 32-channel chunk
 constexpr int kEpiSmemBytes = 4 * 2 * kStageBufBytes;  // 4 epilogue warps x 2 buffers
 
-struct TileCoord { int phase, gx0, gy0, n0, n_tile; };
+struct TileCoord { int phase, gx0, gy0, n0, n_tile; bool skip; };
 
 __device__ __forceinline__ TileCoord decode_tile(const ConvKParams &p, int T) {
     TileCoord c;
     c.n_tile = T % p.n_tiles;
     int mt = T / p.n_tiles;
+    c.skip = false;
+    if (p.interleave) {
+        c.phase = mt % p.num_phases;
+        const int j = mt / p.num_phases;
+        const ConvPhase &ph = p.ph[c.phase];
+        const int tx = j % p.tiles_x_max, ty = (j / p.tiles_x_max) % p.tiles_y_max, tn = j / (p.tiles_x_max * p.tiles_y_max);
+        c.skip = tx >= ph.tiles_x || ty >= ph.tiles_y;            // this phase has no tile here (its lattice is smaller)
+        c.gx0 = tx << p.tw_log2; c.gy0 = ty << p.th_log2; c.n0 = tn << p.tn_log2;
+        return c;
+    }
     c.phase = 0;
 #pragma unroll
     for (int i = 1; i < kMaxPhases; ++i)
@@ -417,6 +431,7 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         uint32_t s = 0, par = 0;
         for (int T = blockIdx.x; T < p.total_tiles; T += gridDim.x) {
             const TileCoord tc = decode_tile(p, T);
+            if (tc.skip) continue;
             const ConvPhase &ph = p.ph[tc.phase];
             for (int t = 0; t < ph.num_taps; ++t) {
                 const int cx = tc.gx0 * p.in_stride + ph.tap_dx[t], cy = tc.gy0 * p.in_stride + ph.tap_dy[t];
@@ -435,8 +450,9 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     } else if (warp == 1) {                            // ===== MMA warp
         uint32_t s = 0, par = 0, lt = 0;
         const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
-        for (int T = blockIdx.x; T < p.total_tiles; T += gridDim.x, ++lt) {
+        for (int T = blockIdx.x; T < p.total_tiles; T += gridDim.x) {
             const TileCoord tc = decode_tile(p, T);
+            if (tc.skip) continue;
             const int num_kb = p.ph[tc.phase].num_taps * p.kblocks_per_tap;
             const uint32_t acc = lt & 1, acc_par = (lt >> 1) & 1;
             mbar_wait(&tmem_empty_bar[acc], acc_par ^ 1);          // epilogue has drained this accumulator
@@ -458,6 +474,7 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             }
             if (elect_one()) tcgen05_commit(&tmem_full_bar[acc]);  // accumulator complete
             __syncwarp();
+            ++lt;
         }
     } else {                                           // ===== epilogue: warp w reads TMEM lanes 32*(w%4)..+31
         const int q = warp & 3;
@@ -467,10 +484,12 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const int tn = row >> (p.tw_log2 + p.th_log2);
         uint32_t lt = 0, stage_sel = 0;
         uint8_t *my_stage = epi_stage + q * 2 * kStageBufBytes;
-        for (int T = blockIdx.x; T < p.total_tiles; T += gridDim.x, ++lt) {
+        for (int T = blockIdx.x; T < p.total_tiles; T += gridDim.x) {
             const TileCoord tc = decode_tile(p, T);
+            if (tc.skip) continue;
             const ConvPhase &ph = p.ph[tc.phase];
             const uint32_t acc = lt & 1, acc_par = (lt >> 1) & 1;
+            ++lt;
             float rgb[3];
             long long rgb_index;
             const bool valid = epilogue_tile<BLOCK_N>(p, out_maps, ph, tc, q, lane, tx, ty, tn, tmem_base + acc * BLOCK_N,
@@ -537,6 +556,26 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, 
 __device__ __forceinline__ TileCoord decode_tile_pair(const ConvKParams &p, int P, int rank) {
     TileCoord c;
     c.n_tile = P % p.n_tiles;
+    c.skip = false;
+    if (p.interleave) {
+        const int pp = P / p.n_tiles;
+        c.phase = pp % p.num_phases;
+        const ConvPhase &ph = p.ph[c.phase];
+        const int per_img = p.tiles_x_max * p.tiles_y_max, total = per_img * p.tiles_n;
+        bool masked[2];
+        int txr = 0, tyr = 0, tnr = 0;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int j = 2 * (pp / p.num_phases) + r;
+            const int tx = j % p.tiles_x_max, ty = (j / p.tiles_x_max) % p.tiles_y_max, tn = j / per_img;
+            masked[r] = j >= total || tx >= ph.tiles_x || ty >= ph.tiles_y;
+            if (r == rank) { txr = tx; tyr = ty; tnr = tn; }
+        }
+        c.skip = masked[0] && masked[1];
+        c.gx0 = txr << p.tw_log2; c.gy0 = tyr << p.th_log2;
+        c.n0 = masked[rank] ? p.batch : (tnr << p.tn_log2);      // n0 >= batch: every row masked, TMA boxes out of range
+        return c;
+    }
     int mt = 2 * (P / p.n_tiles) + rank;
     c.phase = 0;
 #pragma unroll
@@ -595,6 +634,7 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
         uint32_t s = 0, par = 0;
         for (int P = cluster; P < p.total_pairs; P += num_clusters) {
             const TileCoord tc = decode_tile_pair(p, P, rank);
+            if (tc.skip) continue;
             const ConvPhase &ph = p.ph[tc.phase];
             for (int t = 0; t < ph.num_taps; ++t) {
                 const int cx = tc.gx0 * p.in_stride + ph.tap_dx[t], cy = tc.gy0 * p.in_stride + ph.tap_dy[t];
@@ -615,8 +655,9 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
         if (rank == 0) {                               // ===== MMA warp (leader CTA only)
             uint32_t s = 0, par = 0, lt = 0;
             const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
-            for (int P = cluster; P < p.total_pairs; P += num_clusters, ++lt) {
+            for (int P = cluster; P < p.total_pairs; P += num_clusters) {
                 const TileCoord tc = decode_tile_pair(p, P, 0);
+                if (tc.skip) continue;
                 const int num_kb = p.ph[tc.phase].num_taps * p.kblocks_per_tap;
                 const uint32_t acc = lt & 1, acc_par = (lt >> 1) & 1;
                 mbar_wait(&tmem_empty_bar[acc], acc_par ^ 1);
@@ -638,6 +679,7 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                 }
                 if (elect_one()) tcgen05_commit_2sm(&tmem_full_bar[acc]);
                 __syncwarp();
+                ++lt;
             }
         }
     } else {                                           // ===== epilogue (both CTAs, each on its own 128 TMEM lanes)
@@ -648,10 +690,12 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
         const int tn = row >> (p.tw_log2 + p.th_log2);
         uint32_t lt = 0, stage_sel = 0;
         uint8_t *my_stage = epi_stage + q * 2 * kStageBufBytes;
-        for (int P = cluster; P < p.total_pairs; P += num_clusters, ++lt) {
+        for (int P = cluster; P < p.total_pairs; P += num_clusters) {
             const TileCoord tc = decode_tile_pair(p, P, rank);
+            if (tc.skip) continue;
             const ConvPhase &ph = p.ph[tc.phase];
             const uint32_t acc = lt & 1, acc_par = (lt >> 1) & 1;
+            ++lt;
             float rgb[3];
             long long rgb_index;
             const bool valid = epilogue_tile<BLOCK_N>(p, out_maps, ph, tc, q, lane, tx, ty, tn, tmem_base + acc * BLOCK_N,
@@ -1410,6 +1454,23 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
     SR_REQUIRE(m_tiles * p.n_tiles < 0x7fffffffll, "conv: too many tiles");
     p.total_tiles = (int)(m_tiles * p.n_tiles);
     p.total_pairs = (int)(m_tiles2 / 2 * p.n_tiles);
+    // Opt-in (SR_CONV_INTERLEAVE=1): measured SLOWER than phase-major order (0.73 vs 0.70 ms at 256->128 @128^2,
+    // 0.63 vs 0.54 ms at 512->256 @64^2) although it removes the DRAM re-reads -- masked edge tiles and the
+    // alternating K-loop lengths cost more than the extra 1.6 GB of DRAM traffic.
+    static const char *il_env = getenv("SR_CONV_INTERLEAVE");
+    p.interleave = (count > 1 && !use_halo && il_env && il_env[0] == '1') ? 1 : 0;
+    p.tiles_x_max = p.tiles_y_max = 1;
+    p.tiles_n = tiles_n;
+    for (int i = 0; i < count; ++i) {
+        if (p.ph[i].tiles_x > p.tiles_x_max) p.tiles_x_max = p.ph[i].tiles_x;
+        if (p.ph[i].tiles_y > p.tiles_y_max) p.tiles_y_max = p.ph[i].tiles_y;
+    }
+    if (p.interleave) {
+        const long long per = (long long)p.tiles_x_max * p.tiles_y_max * tiles_n;
+        SR_REQUIRE(per * count * p.n_tiles < 0x7fffffffll, "conv: too many tiles");
+        p.total_tiles = (int)(per * count * p.n_tiles);
+        p.total_pairs = (int)((per + 1) / 2 * count * p.n_tiles);
+    }
     // CTA pairs (cta_group::2) halve the weight-tile traffic per SM; they need enough tiles to fill the 74 pairs.
     // SR_CONV_2CTA=0/1 forces the choice.
     static const char *force_2cta = getenv("SR_CONV_2CTA");
