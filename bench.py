@@ -150,34 +150,68 @@ def algorithmic_flops(name, a):
     return 0
 
 
+def launch_signature(name, a):
+    """Shape key of one C-ABI call (launches of the same kernel on different layer shapes are different work)."""
+    try:
+        if name == "sr_conv_igemm_multi_tf32":
+            s = list(a[0])[0]
+            kind = "up" if s.out_stride == 2 else ("gather" if s.in_stride == 2 else "plain")
+            return f"conv:{kind}:{s.cin}:{s.cout}:{s.in_h}"
+        if name == "sr_conv_wgrad_tf32":
+            s = a[0]._obj
+            return f"wgrad:{s.cin}:{s.cout}:{s.grid_h}:{s.g_stride}"
+    except Exception:                                   # noqa: BLE001
+        pass
+    return name
+
+
+def ncu_traffic(sig):
+    """DRAM bytes (read + write) of one launch from the committed `ncu --set full` captures (profiles/r1_ncu_traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    return json.load(open(path)).get(sig)
+
+
 def dominant_kernel_roofline(stats, peaks, total_ms, steps):
+    """Roofline of the dominant launch: the (kernel, layer shape) group with the largest share of the step."""
     if not stats:
         return None
     tot = {n: sum(ms for _, ms in calls) for n, calls in stats.items()}
-    name = max(tot, key=tot.get)
-    calls = stats[name]
-    ms = tot[name]
-    common = {"kernel": name, "launches_per_step": len(calls) / steps, "avg_launch_ms": round(ms / len(calls), 5),
-              "share_of_step": round(ms / total_ms, 4) if total_ms else None, "traffic": None,
+    name = max(tot, key=tot.get)                        # dominant kernel by device time, then its heaviest layer shape
+    groups = {}
+    for a, ms in stats[name]:
+        groups.setdefault(launch_signature(name, a), []).append((a, ms))
+    sig, calls = max(groups.items(), key=lambda kv: sum(ms for _, ms in kv[1]))
+    ms = sum(m for _, m in calls)
+    common = {"kernel": name, "launch": sig, "launches_per_step": len(calls) / steps, "avg_launch_ms": round(ms / len(calls), 5),
+              "share_of_step": round(ms / total_ms, 4) if total_ms else None, "traffic": ncu_traffic(sig),
+              "traffic_source": "profiles/r1_ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
               "all_kernels_ms_per_step": {n: round(v / steps, 4) for n, v in tot.items()}}
     fl = sum(algorithmic_flops(name, a) for a, _ in calls)
     if fl:
-        # MEASURED_PEAKS.json holds the dense bf16 rate only.  Half of it (tf32 issues at half the bf16 rate) would be
-        # 841 TF/s burst / 716 sustained, which the 512-channel layers exceed in isolation (921 TF/s, profiles/), so the
-        # denominator is the nominal dense TF32 peak of B200_PROFILING.md.
+        # MEASURED_PEAKS.json holds the dense bf16 rate only.  Half of it (tf32 issues at half the bf16 rate) is exceeded
+        # by the 512-channel layers in isolation (950 TF/s, profiles/), so the denominator is the nominal dense TF32
+        # peak of B200_PROFILING.md.
         peak = 1100.0
         ach = fl / (ms * 1e-3) / 1e12
+        all_calls = stats[name]
+        fl_all, ms_all = sum(algorithmic_flops(name, a) for a, _ in all_calls), sum(m for _, m in all_calls)
         common.update({"bound": "tensor", "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s",
                        "frac": round(ach / peak, 4),
                        "peak_source": "nominal dense TF32 (no measured TF32 entry; measured bf16 burst / 2 = "
                                       f"{peaks['bf16_tflops'] / 2:.0f} TF/s is exceeded by this kernel in isolation)",
-                       "algorithmic_flops_per_step": fl // steps})
+                       "algorithmic_flops_per_launch": fl // len(calls),
+                       "all_launches_of_kernel": {"launches_per_step": len(all_calls) / steps,
+                                                  "achieved": round(fl_all / (ms_all * 1e-3) / 1e12, 1),
+                                                  "frac": round(fl_all / (ms_all * 1e-3) / 1e12 / peak, 4),
+                                                  "ms_per_step": round(ms_all / steps, 4)}})
         return common
     by = sum(algorithmic_bytes(name, a) for a, _ in calls)
     ach = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
     common.update({"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                    "frac": round(ach / peaks["hbm_gbs"], 4), "peak_source": peaks["_source"],
-                   "algorithmic_bytes_per_step": by // steps})
+                   "algorithmic_bytes_per_launch": by // len(calls)})
     return common
 
 
