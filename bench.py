@@ -42,6 +42,26 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
 
 
+def rank_seed(base, rank):
+    """Per-rank RNG offset: every rank draws its own shard of latents / meshes (reference distributed.py:93-95)."""
+    return int(base) + int(rank)
+
+
+def max_over_ranks_ms(ms, device=None):
+    """Whole-job time of a weakly-scaled step = the slowest rank's device time (all-reduce MAX; identity at world 1)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(ms)
+    t = torch.tensor([float(ms)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def whole_job_rate(units_per_rank, steps, ms, world):
+    """`value` of the bench line: units all ranks processed / the max-over-ranks time."""
+    return world * units_per_rank * steps / (ms * 1e-3)
+
+
 class ClockSampler:
     """nvidia-smi sampling DURING the timed region (B200_PROFILING.md "clocks" line)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -463,7 +483,7 @@ def main():
                     "sample": "oracle/torch_ref.Generator(256) fwd+bwd, batch 2, 2 timed iterations after 1 warm-up "
                               f"({time.perf_counter() - t0:.0f} s of CPU work)"}
 
-    torch.manual_seed(1234 + rank)                      # per-rank RNG offset (reference distributed.py:93-95)
+    torch.manual_seed(rank_seed(1234, rank))            # per-rank RNG offset (reference distributed.py:93-95)
     G = build_generator(dev)
     B = args.batch
     z_dev = torch.randn(B, 512, device=dev)
@@ -485,12 +505,7 @@ def main():
             fn()
         e.record()
         barrier()
-        ms = s.elapsed_time(e)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return max_over_ranks_ms(s.elapsed_time(e), dev)
 
     def step_resident():
         generator_step(G, z_dev, cot)
@@ -572,8 +587,8 @@ def main():
         if roof is not None:
             roof["profiled_region_ms_per_step"] = round(region_ms / n_prof, 3)
 
-    value = world * B * args.steps / (ms * 1e-3)
-    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    value = whole_job_rate(B, args.steps, ms, world)
+    e2e = whole_job_rate(B, args.steps, ms_e2e, world)
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,

@@ -276,6 +276,11 @@ int sr_style_scales_backward_f32(const sr_style_layer *layers, int n_layers, con
 int sr_weight_sq_f32(float *wsq, const float *w, float scale, int64_t cout, int64_t cin, int taps, void *stream);
 int sr_weight_sq_backward_f32(float *gw, const float *w, const float *g_wsq, float scale, int64_t cout, int64_t cin,
                               int taps, void *stream);
+/* One pass over a [cout, cin, taps] weight: fwd[co][t][ci] and tr[ci][t'][co] (t' = taps-1-t when flip_transposed, the
+ * dgrad operand of the plain conv; t' = t for the transposed conv), both tf32(scale*w), and wsq[co][ci] = scale^2 sum_t w^2.
+ * Any output may be NULL.  Same results as sr_conv_weight_prep_tf32 (modes 0 / 1 / 2) + sr_weight_sq_f32. */
+int sr_conv_weight_prep_dual_tf32(float *fwd, float *tr, float *wsq, const float *w, float scale, int64_t cout,
+                                  int64_t cin, int taps, int flip_transposed, void *stream);
 /* gw[o,i,t] = scale * dwk[o,t,i]: result of sr_conv_wgrad_tf32 ([cout][taps][cin]) -> reference weight layout. */
 int sr_weight_grad_layout_f32(float *gw, const float *dwk, float scale, int64_t cout, int64_t cin, int taps, void *stream);
 

@@ -1221,6 +1221,52 @@ weight_prep_kernel(float *__restrict__ dst, const float *__restrict__ w, float s
     }
 }
 
+// One pass over a 3x3 weight: forward GEMM layout, transposed (dgrad) layout and the demodulation statistic together.
+//   fwd[co][t][ci]  = tf32(scale * w[co][ci][t])
+//   tr [ci][t'][co] = tf32(scale * w[co][ci][t]),  t' = taps-1-t (flip = 1, dgrad of the plain conv) or t (flip = 0)
+//   wsq[co][ci]     = scale^2 * sum_t w[co][ci][t]^2                                   (any of the three may be NULL)
+// A CTA owns a 32 x 32 (co, ci) block: the read is one contiguous 32*taps-float run per co, both writes are 128-byte
+// rows (through a shared-memory transpose); the per-mode kernel above scatters 4-byte stores for the transposed layout.
+constexpr int kWP = 32;
+__global__ void __launch_bounds__(256)
+weight_prep_dual_kernel(float *__restrict__ fwd, float *__restrict__ tr, float *__restrict__ wsq, const float *__restrict__ w,
+                        float scale, int cout, int cin, int taps, int flip)
+{
+    extern __shared__ float wt[];                         // [32 co][32 ci * taps + 1]
+    const int row = kWP * taps + 1;
+    const int co0 = blockIdx.y * kWP, ci0 = blockIdx.x * kWP;
+    for (int idx = threadIdx.x; idx < kWP * kWP * taps; idx += 256) {
+        const int r = idx / (kWP * taps), c = idx - r * (kWP * taps);          // c = ci_local * taps + t
+        const int co = co0 + r, ci = ci0 + c / taps;
+        wt[r * row + c] = (co < cout && ci < cin) ? __ldg(w + ((int64_t)co * cin + ci0) * taps + c) * scale : 0.0f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (fwd) {                                            // rows (co, t), 32 consecutive ci
+        for (int q = wid; q < kWP * taps; q += 8) {
+            const int r = q / taps, t = q - r * taps;
+            if (co0 + r < cout && ci0 + lane < cin)
+                fwd[((int64_t)(co0 + r) * taps + t) * cin + ci0 + lane] = round_tf32(wt[r * row + lane * taps + t]);
+        }
+    }
+    if (tr) {                                             // rows (ci, t'), 32 consecutive co
+        for (int q = wid; q < kWP * taps; q += 8) {
+            const int c = q / taps, t = q - c * taps;
+            const int tt = flip ? taps - 1 - t : t;
+            if (ci0 + c < cin && co0 + lane < cout)
+                tr[((int64_t)(ci0 + c) * taps + tt) * cout + co0 + lane] = round_tf32(wt[lane * row + c * taps + t]);
+        }
+    }
+    if (wsq) {
+        for (int q = threadIdx.x; q < kWP * kWP; q += 256) {
+            const int r = q >> 5, c = q & 31;
+            float acc = 0.0f;
+            for (int t = 0; t < taps; ++t) { const float v = wt[r * row + c * taps + t]; acc = fmaf(v, v, acc); }
+            if (co0 + r < cout && ci0 + c < cin) wsq[(int64_t)(co0 + r) * cin + ci0 + c] = acc;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ host side
 int ilog2_exact(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
@@ -1722,4 +1768,17 @@ extern "C" int sr_conv_weight_prep_tf32(float *dst, const float *w, float scale,
     weight_prep_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, w, scale, (int)cout, (int)cin, kh, kw, transpose);
     count_launch();
     return check_launch("sr_conv_weight_prep_tf32");
+}
+
+extern "C" int sr_conv_weight_prep_dual_tf32(float *fwd, float *tr, float *wsq, const float *w, float scale, int64_t cout,
+                                             int64_t cin, int taps, int flip_transposed, void *stream)
+{
+    SR_REQUIRE(w && cout > 0 && cin > 0 && taps > 0 && taps <= 25, "weight_prep_dual: bad arguments");
+    SR_REQUIRE(fwd || tr || wsq, "weight_prep_dual: nothing to produce");
+    const dim3 grid((unsigned)((cin + kWP - 1) / kWP), (unsigned)((cout + kWP - 1) / kWP));
+    const size_t smem = sizeof(float) * kWP * (kWP * taps + 1);
+    weight_prep_dual_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(fwd, tr, wsq, w, scale, (int)cout, (int)cin, taps,
+                                                                    flip_transposed);
+    count_launch();
+    return check_launch("sr_conv_weight_prep_dual_tf32");
 }

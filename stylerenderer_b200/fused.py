@@ -168,13 +168,15 @@ class StyledLayerTC(Function):
 
     @staticmethod
     def forward(ctx, xs, weight, d, noise, noise_weight, act_bias, s_next, rgb_weight, scale, upsample, blur_taps, alpha,
-                gain):
+                gain, wk=None, wkt=None):
         ctx.set_materialize_grads(False)                     # unused outputs arrive as None, not as zero tensors
         xs_nhwc = to_nhwc(xs)
         b, h, w, cin = xs_nhwc.shape
         cout = weight.shape[1]
         d = d.contiguous()
-        wk = tc.weight_prep(weight[0], scale, 0)
+        if wk is None:                                       # operands prepared by the caller (style.WeightPrepAll) or here
+            wk = tc.weight_prep(weight[0], scale, 0)
+        ctx.wkt = wkt
         s_next = s_next.contiguous() if s_next is not None else None
         rgb_weight = rgb_weight.contiguous() if rgb_weight is not None else None
         t = rgb = y2 = None
@@ -218,17 +220,17 @@ class StyledLayerTC(Function):
             src.update(g_rgb=g_rgb.contiguous(), rgb_weight=rgb_weight)
         if not upsample:
             ga, g_bias, g_noise_w, e, ds_next, dwb = tc.bwd_prologue2(y, noise, noise_weight, act_bias, d, alpha, gain, True, **src)
-            dxs = tc.conv3x3(ga, tc.weight_prep(weight[0], scale, 1))
+            dxs = tc.conv3x3(ga, ctx.wkt if ctx.wkt is not None else tc.weight_prep(weight[0], scale, 1))
             dwk = tc.wgrad3x3(ga, xs)
         else:
             g_pre, g_bias, g_noise_w, _, ds_next, dwb = tc.bwd_prologue2(y, noise, noise_weight, act_bias, None, alpha, gain,
                                                                          False, **src)
             ga, e = tc.blur_scaledot(g_pre, torch.flip(blur_taps, [0, 1]), (2, 2), d, t)   # FIR^T, * d, tf32, sum gt * t
-            dxs = tc.conv3x3_s2_gather(ga, tc.weight_prep(weight[0], scale, 2), (h, w))
+            dxs = tc.conv3x3_s2_gather(ga, ctx.wkt if ctx.wkt is not None else tc.weight_prep(weight[0], scale, 2), (h, w))
             dwk = tc.wgrad_transpose3x3_s2(ga, xs)
         g_d = e / d
         g_w = style.weight_grad_layout(dwk, scale, cout, cin, 3)
-        return (from_nhwc(dxs), g_w, g_d, None, g_noise_w, g_bias, ds_next, dwb, None, None, None, None, None)
+        return (from_nhwc(dxs), g_w, g_d, None, g_noise_w, g_bias, ds_next, dwb, None, None, None, None, None, None, None)
 
 
 def chain_supported(gen, x):
@@ -254,7 +256,9 @@ def generator_chain_forward(gen, latent, noise):
     # all modulation / demodulation vectors of the network in one batched call (style.py): conv k uses latent[:, k]
     mods = [blk.conv for blk in blocks] + [rgbs[k][0].conv for k in sorted(rgbs)]
     lat_idx = list(range(len(blocks))) + [rgbs[k][1] for k in sorted(rgbs)]
-    sd = style.style_scales_all(latent, mods, lat_idx)
+    # one pass per conv weight: demodulation statistic + forward / dgrad GEMM operands (style.WeightPrepAll)
+    prep = [style.WeightPrepAll.apply(blk.conv.weight, blk.conv.scale, not blk.conv.upsample) for blk in blocks]
+    sd = style.style_scales_all(latent, mods, lat_idx, [pr[0] for pr in prep] + [None] * len(rgbs))
     scales = sd[:len(blocks)]
     rgb_style = {k: sd[len(blocks) + j][0] for j, k in enumerate(sorted(rgbs))}
     x0 = gen.input(latent)
@@ -272,7 +276,7 @@ def generator_chain_forward(gen, latent, noise):
         taps = blk.conv.blur.kernel if blk.conv.upsample else blk.noise.weight
         xs, rgb = StyledLayerTC.apply(xs, blk.conv.weight, scales[k][1], nz, blk.noise.weight, blk.activate.bias, s_next, wb,
                                       blk.conv.scale, blk.conv.upsample, taps, blk.activate.negative_slope,
-                                      blk.activate.scale)
+                                      blk.activate.scale, prep[k][1], prep[k][2])
         if to_rgb is not None:
             out = rgb.permute(0, 3, 1, 2) + to_rgb.bias
             skip = out if skip is None else out + to_rgb.upsample(skip)

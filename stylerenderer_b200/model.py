@@ -241,3 +241,4 @@ class Discriminator(nn.Module):                       # reference model.py:296-3
         out = torch.cat([out, stddev], 1)
         out = self.final_conv(out)
         return self.final_linear(out.view(batch, -1))
+

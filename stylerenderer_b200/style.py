@@ -52,6 +52,37 @@ class WeightSq(Function):
         return gw, None
 
 
+class WeightPrepAll(Function):
+    """(wsq, wk_fwd, wk_tr) of a 3x3 modulated-conv weight in ONE pass over it (sr_conv_weight_prep_dual_tf32): the
+    demodulation statistic (differentiable, see WeightSq) and the two tf32 GEMM operand layouts the tensor-core block
+    uses in its forward and backward (constants of the step, not differentiable)."""
+
+    @staticmethod
+    def forward(ctx, weight, scale, flip_transposed):
+        from . import tc_conv as tc
+        w = weight.contiguous()
+        wk_f, wk_t, wsq = tc.weight_prep_dual(w[0], scale, flip_transposed)
+        ctx.save_for_backward(w)
+        ctx.scale = float(scale)
+        ctx.mark_non_differentiable(wk_f, wk_t)
+        return wsq, wk_f, wk_t
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_wsq, _gf, _gt):
+        if g_wsq is None:
+            return None, None, None
+        w, = ctx.saved_tensors
+        _, cout, cin, kh, kw = w.shape
+        gw = torch.empty_like(w)
+        g = g_wsq.contiguous()
+        with torch.cuda.device(w.device):
+            rc = _lib.lib().sr_weight_sq_backward_f32(_lib.ptr(gw), _lib.ptr(w), _lib.ptr(g), ctx.scale, cout, cin, kh * kw,
+                                                      _lib.stream_of(w))
+        _lib.check(rc, "sr_weight_sq_backward_f32")
+        return gw, None, None
+
+
 def weight_grad_layout(dwk, scale, cout, cin, k):
     """[cout, k*k, cin] (wgrad kernels) * scale -> [1, cout, cin, k, k] (reference weight layout)."""
     gw = torch.empty(1, cout, cin, k, k, dtype=torch.float32, device=dwk.device)
@@ -148,14 +179,17 @@ class StyleScalesAll(Function):
         return (g_latent, None, *result)
 
 
-def style_scales_all(latent, mods, lat_idx):
-    """mods: list of ModulatedConv2d; lat_idx: latent index per module.  -> list of (s, d or None)."""
+def style_scales_all(latent, mods, lat_idx, wsqs=None):
+    """mods: list of ModulatedConv2d; lat_idx: latent index per module; wsqs: optional precomputed weight statistics
+    (WeightPrepAll) per module, None entries are computed here.  -> list of (s, d or None)."""
     m0 = mods[0].modulation
     assert all(m.modulation.scale == m0.scale and m.modulation.lr_mul == m0.lr_mul and m.modulation.activation is None
                for m in mods)
     tensors = []
-    for m in mods:
-        wsq = WeightSq.apply(m.weight, m.scale) if m.demodulate else None
+    for j, m in enumerate(mods):
+        wsq = None
+        if m.demodulate:
+            wsq = wsqs[j] if (wsqs is not None and wsqs[j] is not None) else WeightSq.apply(m.weight, m.scale)
         tensors += [m.modulation.weight, m.modulation.bias, wsq]
     cfg = (tuple(int(i) for i in lat_idx), m0.scale, m0.lr_mul, mods[0].eps)
     outs = list(StyleScalesAll.apply(latent, cfg, *tensors))

@@ -62,6 +62,21 @@ def weight_prep(w, scale, mode):
     return dst
 
 
+def weight_prep_dual(w, scale, flip_transposed, want_wsq=True):
+    """One pass over a [cout, cin, k, k] weight -> (fwd [cout, k*k, cin], tr [cin, k*k, cout], wsq [cout, cin] or None):
+    weight_prep(mode 0), weight_prep(mode 1 if flip_transposed else 2) and scale^2 * sum_taps w^2 together."""
+    cout, cin, kh, kw = w.shape
+    wc = w.contiguous()
+    fwd = torch.empty(cout, kh * kw, cin, dtype=torch.float32, device=w.device)
+    tr = torch.empty(cin, kh * kw, cout, dtype=torch.float32, device=w.device)
+    wsq = torch.empty(cout, cin, dtype=torch.float32, device=w.device) if want_wsq else None
+    with torch.cuda.device(w.device):
+        rc = _lib.lib().sr_conv_weight_prep_dual_tf32(_lib.ptr(fwd), _lib.ptr(tr), _lib.ptr(wsq), _lib.ptr(wc), float(scale), cout,
+                                                      cin, kh * kw, 1 if flip_transposed else 0, _lib.stream_of(w))
+    _lib.check(rc, "sr_conv_weight_prep_dual_tf32")
+    return fwd, tr, wsq
+
+
 def modulate(x, style=None):
     """xs = tf32_round(x * style[b, c]) for NHWC x [B,H,W,C]; style [B,C] or None (rounding only)."""
     _check_nhwc(x, "modulate")

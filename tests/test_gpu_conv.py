@@ -145,3 +145,17 @@ def test_wgrad(tc, case):
     want2, = torch.autograd.grad(F.conv_transpose2d(nchw(x).double(), wt2, stride=2), wt2, nchw(g2).double())
     got2 = dw2.view(cout, 3, 3, cin).permute(3, 0, 1, 2)                   # -> [cin, cout, 3, 3]
     assert relerr(got2, want2) < 5e-5, case
+
+
+@pytest.mark.parametrize("shape", [(128, 128), (512, 256), (96, 160), (40, 3)])
+def test_weight_prep_dual_matches_single_mode_kernels(tc, shape):
+    """The one-pass weight preparation (forward layout, transposed layout, demodulation statistic) equals the per-mode
+    kernels bit for bit and the torch definition of Wsq (reference layers.py:297)."""
+    cout, cin = shape
+    w = seeded((cout, cin, 3, 3), 41).cuda()
+    for flip, mode in ((True, 1), (False, 2)):
+        fwd, tr, wsq = tc.weight_prep_dual(w, 0.037, flip)
+        assert torch.equal(fwd, tc.weight_prep(w, 0.037, 0))
+        assert torch.equal(tr, tc.weight_prep(w, 0.037, mode))
+        want = (w.double() * 0.037).pow(2).sum([2, 3])
+        torch.testing.assert_close(wsq.double(), want, rtol=1e-5, atol=1e-9)
