@@ -145,7 +145,7 @@ struct ConvPhase {                          // one tap list + output lattice (th
     int num_taps;
     int tap_dy[9], tap_dx[9], tap_k0[9];    // input offset of a tap and its first K column in the weight matrix
     int grid_h, grid_w, tiles_x, tiles_y;
-    int tile_begin;                         // first M tile of this phase
+    int tile_begin;                         // first M tile of this phase inside an image group
     int tile_begin2;                        // same with every phase padded to an even tile count (CTA-pair kernel)
     long long out_offset;                   // lattice origin (y0 * row + x0 * pix), in floats
     long long noise_offset;
@@ -157,10 +157,11 @@ struct ConvKParams {
     int kblocks_per_tap;                    // cin / 32
     int num_phases, n_tiles, total_tiles;   // total_tiles = (sum of M tiles) * n_tiles
     int total_pairs;                        // CTA-pair kernel: (sum of padded M tiles / 2) * n_tiles
-    // optional tile-major order for multi-phase launches: the phases of one spatial tile back to back, so the four parity
-    // classes of a transposed conv read their shared input tile from L2 instead of streaming the input from DRAM
-    // once per phase (ncu, 256->128 @128^2: 2.15 GB read for a 0.54 GB input with phase-major order); see the host side
-    int interleave, tiles_x_max, tiles_y_max, tiles_n;
+    // Tile order: image groups outermost, then phases, then the tiles of the phase.  With one image (or tn-image tile) per
+    // group the four parity classes of a transposed conv visit the same input image back to back, so they read it from L2
+    // instead of streaming the whole batch from DRAM once per phase (ncu, 256->128 @128^2, phase-major order: 2.15 GB
+    // read for a 0.54 GB input, DRAM 57 % busy).  group_n = tiles_n reproduces the phase-major order.
+    int group_n, tiles_n, tiles_per_group, tiles_per_group2;
     ConvPhase ph[kMaxPhases];
     int in_stride;
     int cout;
@@ -193,23 +194,16 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams &p, int T) {
     TileCoord c;
     c.n_tile = T % p.n_tiles;
     int mt = T / p.n_tiles;
-    c.skip = false;
-    if (p.interleave) {
-        c.phase = mt % p.num_phases;
-        const int j = mt / p.num_phases;
-        const ConvPhase &ph = p.ph[c.phase];
-        const int tx = j % p.tiles_x_max, ty = (j / p.tiles_x_max) % p.tiles_y_max, tn = j / (p.tiles_x_max * p.tiles_y_max);
-        c.skip = tx >= ph.tiles_x || ty >= ph.tiles_y;            // this phase has no tile here (its lattice is smaller)
-        c.gx0 = tx << p.tw_log2; c.gy0 = ty << p.th_log2; c.n0 = tn << p.tn_log2;
-        return c;
-    }
+    const int g = mt / p.tiles_per_group;
+    mt -= g * p.tiles_per_group;
     c.phase = 0;
 #pragma unroll
     for (int i = 1; i < kMaxPhases; ++i)
         if (i < p.num_phases && mt >= p.ph[i].tile_begin) c.phase = i;
     const ConvPhase &ph = p.ph[c.phase];
     mt -= ph.tile_begin;
-    const int tx = mt % ph.tiles_x, ty = (mt / ph.tiles_x) % ph.tiles_y, tn = mt / (ph.tiles_x * ph.tiles_y);
+    const int tx = mt % ph.tiles_x, ty = (mt / ph.tiles_x) % ph.tiles_y, tn = g * p.group_n + mt / (ph.tiles_x * ph.tiles_y);
+    c.skip = tn >= p.tiles_n;                                   // last, partial image group
     c.gx0 = tx << p.tw_log2; c.gy0 = ty << p.th_log2; c.n0 = tn << p.tn_log2;
     return c;
 }
@@ -556,35 +550,23 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, 
 __device__ __forceinline__ TileCoord decode_tile_pair(const ConvKParams &p, int P, int rank) {
     TileCoord c;
     c.n_tile = P % p.n_tiles;
-    c.skip = false;
-    if (p.interleave) {
-        const int pp = P / p.n_tiles;
-        c.phase = pp % p.num_phases;
-        const ConvPhase &ph = p.ph[c.phase];
-        const int per_img = p.tiles_x_max * p.tiles_y_max, total = per_img * p.tiles_n;
-        bool masked[2];
-        int txr = 0, tyr = 0, tnr = 0;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int j = 2 * (pp / p.num_phases) + r;
-            const int tx = j % p.tiles_x_max, ty = (j / p.tiles_x_max) % p.tiles_y_max, tn = j / per_img;
-            masked[r] = j >= total || tx >= ph.tiles_x || ty >= ph.tiles_y;
-            if (r == rank) { txr = tx; tyr = ty; tnr = tn; }
-        }
-        c.skip = masked[0] && masked[1];
-        c.gx0 = txr << p.tw_log2; c.gy0 = tyr << p.th_log2;
-        c.n0 = masked[rank] ? p.batch : (tnr << p.tn_log2);      // n0 >= batch: every row masked, TMA boxes out of range
-        return c;
-    }
-    int mt = 2 * (P / p.n_tiles) + rank;
+    int mt = 2 * (P / p.n_tiles);                               // first tile of the pair (pairs never straddle a phase)
+    const int g = mt / p.tiles_per_group2;
+    mt -= g * p.tiles_per_group2;
     c.phase = 0;
 #pragma unroll
     for (int i = 1; i < kMaxPhases; ++i)
         if (i < p.num_phases && mt >= p.ph[i].tile_begin2) c.phase = i;
     const ConvPhase &ph = p.ph[c.phase];
-    mt -= ph.tile_begin2;                    // may run one past the real tiles of the phase: decodes to n0 >= batch (all masked)
-    const int tx = mt % ph.tiles_x, ty = (mt / ph.tiles_x) % ph.tiles_y, tn = mt / (ph.tiles_x * ph.tiles_y);
-    c.gx0 = tx << p.tw_log2; c.gy0 = ty << p.th_log2; c.n0 = tn << p.tn_log2;
+    mt -= ph.tile_begin2;
+    const int per_img = ph.tiles_x * ph.tiles_y;
+    const int tn_first = g * p.group_n + mt / per_img;
+    c.skip = tn_first >= p.tiles_n;                             // whole pair beyond the last image group
+    mt += rank;                                                 // may run one past the real tiles of the phase ...
+    const int tl = mt / per_img;                                // ... then tl == group_n: mask it (n0 >= batch)
+    const int tx = mt % ph.tiles_x, ty = (mt / ph.tiles_x) % ph.tiles_y, tn = g * p.group_n + tl;
+    c.gx0 = tx << p.tw_log2; c.gy0 = ty << p.th_log2;
+    c.n0 = (tl >= p.group_n || tn >= p.tiles_n) ? p.batch : (tn << p.tn_log2);
     return c;
 }
 
@@ -1474,6 +1456,13 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
     p.kblocks_per_tap = (int)(a->cin / BLOCK_K);
     p.num_phases = count;
     const int tiles_n = (int)((a->batch + tn - 1) / tn);
+    // multi-phase launches whose input does not fit in L2: one image per group (measured 0.66 vs 0.70 ms at 256->128
+    // @128^2, 537 MB input; no gain or a small loss below that); SR_CONV_PHASE_MAJOR=1/0 forces phase- / group-major order
+    static const char *pm_env = getenv("SR_CONV_PHASE_MAJOR");
+    const double in_bytes = 4.0 * (double)a->batch * a->in_h * a->in_w * a->cin;
+    bool group_major = count > 1 && in_bytes > 384e6;
+    if (pm_env) group_major = count > 1 && pm_env[0] == '0';
+    const int group_n = group_major ? 1 : tiles_n;
     long long m_tiles = 0, m_tiles2 = 0;
     for (int i = 0; i < kMaxPhases; ++i) {
         ConvPhase &ph = p.ph[i];
@@ -1488,11 +1477,15 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
         ph.out_offset = ((long long)b->out_y0 * a->out_w + b->out_x0) * a->cout;
         ph.noise_offset = (long long)b->out_y0 * a->out_w + b->out_x0;
         if (i < count) {
-            const long long t_ph = (long long)ph.tiles_x * ph.tiles_y * tiles_n;
+            const long long t_ph = (long long)ph.tiles_x * ph.tiles_y * group_n;
             m_tiles += t_ph;
             m_tiles2 += (t_ph + 1) / 2 * 2;
         }
     }
+    p.group_n = group_n; p.tiles_n = tiles_n;
+    p.tiles_per_group = (int)m_tiles; p.tiles_per_group2 = (int)m_tiles2;
+    const long long num_groups = (tiles_n + group_n - 1) / group_n;
+    m_tiles *= num_groups; m_tiles2 *= num_groups;          // totals over the batch
     // few tiles (low resolutions): prefer 128-wide N tiles so more SMs take part
     int block_n = (a->cout % 256 == 0) ? 256 : 128;
     if (block_n == 256 && (use_halo ? m_tiles2 / 2 : m_tiles) * (a->cout / 256) < kNumSMs / 2) block_n = 128;
@@ -1500,23 +1493,6 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
     SR_REQUIRE(m_tiles * p.n_tiles < 0x7fffffffll, "conv: too many tiles");
     p.total_tiles = (int)(m_tiles * p.n_tiles);
     p.total_pairs = (int)(m_tiles2 / 2 * p.n_tiles);
-    // Opt-in (SR_CONV_INTERLEAVE=1): measured SLOWER than phase-major order (0.73 vs 0.70 ms at 256->128 @128^2,
-    // 0.63 vs 0.54 ms at 512->256 @64^2) although it removes the DRAM re-reads -- masked edge tiles and the
-    // alternating K-loop lengths cost more than the extra 1.6 GB of DRAM traffic.
-    static const char *il_env = getenv("SR_CONV_INTERLEAVE");
-    p.interleave = (count > 1 && !use_halo && il_env && il_env[0] == '1') ? 1 : 0;
-    p.tiles_x_max = p.tiles_y_max = 1;
-    p.tiles_n = tiles_n;
-    for (int i = 0; i < count; ++i) {
-        if (p.ph[i].tiles_x > p.tiles_x_max) p.tiles_x_max = p.ph[i].tiles_x;
-        if (p.ph[i].tiles_y > p.tiles_y_max) p.tiles_y_max = p.ph[i].tiles_y;
-    }
-    if (p.interleave) {
-        const long long per = (long long)p.tiles_x_max * p.tiles_y_max * tiles_n;
-        SR_REQUIRE(per * count * p.n_tiles < 0x7fffffffll, "conv: too many tiles");
-        p.total_tiles = (int)(per * count * p.n_tiles);
-        p.total_pairs = (int)((per + 1) / 2 * count * p.n_tiles);
-    }
     // CTA pairs (cta_group::2) halve the weight-tile traffic per SM; they need enough tiles to fill the 74 pairs.
     // SR_CONV_2CTA=0/1 forces the choice.
     static const char *force_2cta = getenv("SR_CONV_2CTA");
