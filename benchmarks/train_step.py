@@ -113,6 +113,9 @@ def main():
     ap.add_argument("--mesh-n", type=int, default=189)
     ap.add_argument("--conv-backend", default="tcgen05", choices=["cudnn", "tcgen05"],
                     help="who runs the ModulatedConv2d contractions of G (the Discriminator's plain convs stay on cuDNN)")
+    ap.add_argument("--no-cudnn-benchmark", action="store_true", help="keep cuDNN's heuristic algorithm choice for the Discriminator")
+    ap.add_argument("--d-nchw", action="store_true", help="keep the Discriminator in NCHW (default: channels_last, no layout conversions)")
+    ap.add_argument("--profile", action="store_true", help="print the top CUDA kernels of the timed iterations (torch.profiler)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -127,8 +130,14 @@ def main():
     from stylerenderer_b200.model import Discriminator, GeneratorWithMap
 
     layers.set_conv_backend(args.conv_backend)
+    # the Discriminator's plain convolutions are cuDNN's: let it pick its algorithms by measurement (the heuristic picks
+    # 20 TFLOP/s "sm80 indexed" kernels for the 64-channel layers at 256^2) and keep D in channels_last so that no
+    # NCHW<->NHWC conversion kernels run around them (our upfirdn2d / fused_leaky_relu take channels_last as is)
+    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
     G = GeneratorWithMap(args.size, 512, 8, channel_multiplier=2).to(dev)
     D = Discriminator(args.size, channel_multiplier=2).to(dev)
+    if not args.d_nchw:
+        D = D.to(memory_format=torch.channels_last)
     g_ema = copy.deepcopy(G).eval()
     face = SyntheticMorphableModel(args.mesh_n).to(dev)
     g_reg, d_reg = 4, 16
@@ -153,6 +162,8 @@ def main():
     def iteration(i):
         nonlocal mean_path
         real = torch.randn(B, 3, args.size, args.size, device=dev)
+        if not args.d_nchw:
+            real = real.contiguous(memory_format=torch.channels_last)
         # ---- D step (train.py:245-268)
         requires_grad(g_mod, False); requires_grad(d_mod, True)
         vert, norm = sample_mesh(B)
@@ -163,10 +174,11 @@ def main():
         d_optim.step()
         if i % d_reg == 0:                                              # R1 (train.py:281-289): double backward through D
             real.requires_grad = True
-            real_pred = D(real)
-            r1 = d_r1_loss(real_pred, real)
-            d_mod.zero_grad(set_to_none=True)
-            (10 / 2 * r1 * d_reg + 0 * real_pred[0]).backward()
+            with layers.double_backward():                              # the tensor-core blocks are first-order only
+                real_pred = D(real)
+                r1 = d_r1_loss(real_pred, real)
+                d_mod.zero_grad(set_to_none=True)
+                (10 / 2 * r1 * d_reg + 0 * real_pred[0]).backward()
             d_optim.step()
         # ---- G step (train.py:292-333)
         requires_grad(g_mod, True); requires_grad(d_mod, False)
@@ -210,8 +222,16 @@ def main():
     n0 = _lib.launch_count()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for i in range(args.iters):
-        iteration(i)
+    if args.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(args.iters):
+                iteration(i)
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90), file=sys.stderr)
+    else:
+        for i in range(args.iters):
+            iteration(i)
     e.record()
     if world > 1:
         dist.barrier()
@@ -226,7 +246,7 @@ def main():
             "metric": "GAR train step (G+D+rasterize+R1/16+path/4) images/sec", "value": round(world * B * args.iters / (ms * 1e-3), 2),
             "unit": "images/s", "n_gpus": world, "iters": args.iters, "ms_per_iter": round(ms / args.iters, 2),
             "scaling": "weak", "dtype": "f32 storage, tf32 tensor-core convs",
-            "conv_backend": {"generator": args.conv_backend, "discriminator": "cudnn"},
+            "conv_backend": {"generator": args.conv_backend, "discriminator": args.conv_backend + " (ResBlock convs; 3-channel stem, final conv and regulariser iterations on cuDNN)"},
             "config": {"workload": "GeneratorWithMap + Discriminator 256x256 (BASELINE.json configs[3])", "per_gpu_batch": B,
                        "parallelism": f"ddp{world} (NCCL gradient all-reduce, broadcast_buffers=False)",
                        "mesh": f"{args.mesh_n ** 2} verts / {tri.shape[0]} tris"},

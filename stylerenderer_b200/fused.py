@@ -120,6 +120,93 @@ class ModConvTC(Function):
         return from_nhwc(g_x), g_w, g_s, e / d, None, None, None
 
 
+_ONES = {}
+
+
+def _ones(b, c, device):
+    key = (b, c, str(device))
+    if key not in _ONES:
+        _ONES[key] = torch.ones(b, c, dtype=torch.float32, device=device)
+    return _ONES[key]
+
+
+TAPS_S2 = [(ky, kx, ky * 3 + kx) for ky in range(3) for kx in range(3)]
+
+
+class PlainConvTC(Function):
+    """EqualConv2d (+ FusedLeakyReLU) of the Discriminator / ConvLayer stack (reference layers.py:204-221, 341-378) on the
+    tensor-core kernels: kind 's1' = 3x3 stride 1 pad 1, 's2' = 3x3 stride 2 pad 0 (after the Blur), 'p2' = 1x1 stride 2.
+    Same implicit-GEMM kernels as the modulated convolution (no style: the operand is only rounded to tf32), bias +
+    leaky-ReLU in the conv epilogue, activation backward + bias gradient + tf32 operand in one prologue pass."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, scale, kind, alpha, gain):
+        x_nhwc = to_nhwc(x)
+        b, h, w, cin = x_nhwc.shape
+        cout, _, k, _ = weight.shape
+        xr = tc.modulate(x_nhwc)
+        wk_f, wk_t, _ = tc.weight_prep_dual(weight, scale, kind == "s1", want_wsq=False)
+        act = bias is not None
+        kw = dict(epilogue=1, bias=bias, alpha=alpha, gain=gain) if act else dict(epilogue=0)
+        if kind == "s1":
+            y = tc.conv3x3(xr, wk_f, **kw)
+        else:
+            oh, ow = (h - k) // 2 + 1, (w - k) // 2 + 1
+            y = torch.empty(b, oh, ow, cout, dtype=torch.float32, device=x.device)
+            taps = TAPS_S2 if k == 3 else [(0, 0, 0)]
+            tc.conv_igemm(xr, wk_f, taps, y, in_stride=2, **kw)
+        ctx.save_for_backward(xr, y if act else None, wk_t, bias)
+        ctx.cfg = (scale, kind, alpha, gain, k, cin, cout, (h, w))
+        return from_nhwc(y)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        xr, y, wk_t, bias = ctx.saved_tensors
+        scale, kind, alpha, gain, k, cin, cout, (h, w) = ctx.cfg
+        gy = to_nhwc(gy)
+        b, oh, ow, _ = gy.shape
+        g_bias = None
+        if y is not None:       # activation backward + bias gradient + tf32 operand in one pass (d = 1)
+            ga, g_bias, _, _ = tc.bwd_prologue(gy, y, None, None, bias, _ones(b, cout, gy.device), alpha, gain, False)
+        else:
+            ga = tc.modulate(gy)
+        if kind == "s1":
+            dx = tc.conv3x3(ga, wk_t)
+            dwk = tc.wgrad3x3(ga, xr)
+        elif kind == "s2":
+            dx = tc.conv_transpose3x3_s2(ga, wk_t)
+            dwk = tc.wgrad(ga, xr, [(0, 0, ky, kx, ky * 3 + kx) for ky in range(3) for kx in range(3)], (oh, ow), x_stride=2)
+        else:
+            dx = torch.zeros(b, h, w, cin, dtype=torch.float32, device=gy.device)
+            tc.conv_igemm_multi(ga, wk_t, [([(0, 0, 0)], (oh, ow), (0, 0))], dx, out_stride=2)
+            dwk = tc.wgrad(ga, xr, [(0, 0, 0, 0, 0)], (oh, ow), x_stride=2, taps_total=1)
+        g_w = style.weight_grad_layout(dwk, scale, cout, cin, k)[0]
+        return from_nhwc(dx), g_w, g_bias, None, None, None, None
+
+
+def plain_conv_supported(conv, x):
+    """EqualConv2d shapes the tensor-core path takes: 3x3 s1 p1, 3x3 s2 p0, 1x1 s2 p0 with channels in multiples of 128."""
+    k = conv.weight.shape[2]
+    cout, cin = conv.weight.shape[:2]
+    kind = {(3, 1, 1): "s1", (3, 2, 0): "s2", (1, 2, 0): "p2"}.get((k, conv.stride, conv.padding))
+    if kind is None or not (x.is_cuda and x.dtype == torch.float32 and tc.supported(cin, cout) and tc.wgrad_supported(cin, cout)):
+        return None
+    if kind == "s2" and (x.shape[2] % 2 == 0 or x.shape[3] % 2 == 0):      # dgrad = transposed conv: needs odd (2m+1) inputs
+        return None
+    if kind == "p2" and (x.shape[2] < 1 or x.shape[3] < 1):
+        return None
+    return kind
+
+
+def plain_conv(conv, act, x, kind):
+    """ConvLayer body (EqualConv2d [+ FusedLeakyReLU]) on the tensor cores; `act` is the FusedLeakyReLU module or None."""
+    if act is not None:      # this fork keeps a bias in the conv AND in the activation (reference layers.py:365-375): they add up
+        bias = act.bias if conv.bias is None else act.bias + conv.bias
+        return PlainConvTC.apply(x, conv.weight, bias, conv.scale, kind, act.negative_slope, act.scale)
+    return PlainConvTC.apply(x, conv.weight, None, conv.scale, kind, 0.2, 1.0)
+
+
 def mod_conv(mod, x, style):
     """ModulatedConv2d.forward on the tensor cores (see ModConvTC)."""
     s, d = mod.style_scales(style)

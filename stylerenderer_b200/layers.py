@@ -277,6 +277,28 @@ class ConvLayer(nn.Sequential):                       # reference layers.py:341-
             layers.append(FusedLeakyReLU(out_channel) if bias else ScaledLeakyReLU(0.2))
         super().__init__(*layers)
 
+    def forward(self, input):
+        # tensor-core path (conv_backend "tcgen05", first-order gradients): [Blur ->] EqualConv2d [+ FusedLeakyReLU] with the
+        # bias / activation in the conv epilogue; anything else (3-channel stems, SpectralNorm-free odd shapes, R1 / path
+        # regulariser iterations under double_backward()) takes the composed cuDNN path below, like the reference
+        if _CONFIG["conv_backend"] == "tcgen05" and not (torch.is_grad_enabled() and _CONFIG["double_backward"]):
+            mods = list(self)
+            blur = mods[0] if isinstance(mods[0], Blur) else None
+            rest = mods[1:] if blur is not None else mods
+            conv = rest[0]
+            act = rest[1] if len(rest) > 1 else None
+            if isinstance(conv, EqualConv2d) and (isinstance(act, FusedLeakyReLU) or (act is None and conv.bias is None)):
+                from . import fused
+                x = blur(input) if blur is not None else input
+                kind = fused.plain_conv_supported(conv, x)
+                if kind is not None:
+                    return fused.plain_conv(conv, act, x, kind)
+                input, start = x, (1 if blur is not None else 0)
+                for m in mods[start:]:
+                    input = m(input)
+                return input
+        return super().forward(input)
+
 
 class ResBlock(nn.Module):                            # reference layers.py:379-391
     def __init__(self, in_channel, out_channel, blur_kernel=[1, 3, 3, 1], downsample=True):

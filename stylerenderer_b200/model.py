@@ -234,11 +234,11 @@ class Discriminator(nn.Module):                       # reference model.py:296-3
         out = self.convs(input)
         batch, channel, height, width = out.shape
         group = min(batch, self.stddev_group)
-        stddev = out.view(group, -1, self.stddev_feat, channel // self.stddev_feat, height, width)
+        stddev = out.reshape(group, -1, self.stddev_feat, channel // self.stddev_feat, height, width)
         stddev = torch.sqrt(stddev.var(0, unbiased=False) + 1e-8)
         stddev = stddev.mean([2, 3, 4], keepdim=True).squeeze(2)
         stddev = stddev.repeat(group, 1, height, width)
         out = torch.cat([out, stddev], 1)
         out = self.final_conv(out)
-        return self.final_linear(out.view(batch, -1))
+        return self.final_linear(out.reshape(batch, -1))
 

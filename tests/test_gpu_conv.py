@@ -159,3 +159,33 @@ def test_weight_prep_dual_matches_single_mode_kernels(tc, shape):
         assert torch.equal(tr, tc.weight_prep(w, 0.037, mode))
         want = (w.double() * 0.037).pow(2).sum([2, 3])
         torch.testing.assert_close(wsq.double(), want, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("kind,shape", [("s1", (2, 128, 128, 24, 40)), ("s1", (3, 256, 128, 16, 16)),
+                                        ("s2", (2, 128, 256, 33, 33)), ("s2", (1, 128, 128, 65, 37)),
+                                        ("p2", (2, 128, 128, 31, 31)), ("p2", (3, 256, 128, 15, 33))])
+def test_plain_conv_layer_tc(kind, shape):
+    """EqualConv2d [+ bias + FusedLeakyReLU] of the Discriminator (reference layers.py:204-221, 341-378) on the tensor-core
+    kernels: values and every gradient against float64 torch on the same tf32-rounded operands."""
+    from stylerenderer_b200 import fused, tc_conv as tcm
+    b, cin, cout, h, w = shape
+    k, stride, pad = {"s1": (3, 1, 1), "s2": (3, 2, 0), "p2": (1, 2, 0)}[kind]
+    x = tcm.modulate(nhwc(seeded((b, cin, h, w), 51)).cuda()).permute(0, 3, 1, 2).requires_grad_(True)   # tf32-exact input
+    wt = seeded((cout, cin, k, k), 52).cuda().requires_grad_(True)
+    bias = (seeded((cout,), 53).cuda() * 0.2).requires_grad_(True) if kind != "p2" else None
+    scale = 1.0 / (cin * k * k) ** 0.5
+    y = fused.PlainConvTC.apply(x, wt, bias, scale, kind, 0.2, 2 ** 0.5)
+    gy = seeded(tuple(y.shape), 54).cuda()
+    grads = torch.autograd.grad(y, [x, wt] + ([bias] if bias is not None else []), gy)
+    w_r = tcm.weight_prep(wt.detach(), scale, 0).view(cout, k, k, cin).permute(0, 3, 1, 2).double().requires_grad_(True)
+    x64 = x.detach().double().requires_grad_(True)
+    b64 = bias.detach().double().requires_grad_(True) if bias is not None else None
+    t = F.conv2d(x64, w_r, stride=stride, padding=pad)
+    want = F.leaky_relu(t + b64.view(1, -1, 1, 1), 0.2) * 2 ** 0.5 if bias is not None else t
+    assert relerr(y.detach(), want.detach()) < 3e-5, (kind, shape)
+    # gradients: the backward operand (activation backward of gy) is rounded to tf32 inside the block -> 1e-3 level
+    wg = torch.autograd.grad(want, [x64, w_r] + ([b64] if bias is not None else []), gy.double())
+    assert relerr(grads[0], wg[0]) < 2e-3, (kind, "dx")
+    assert relerr(grads[1], wg[1] * scale) < 2e-3, (kind, "dw")       # d/dw = scale * d/d(scale*w)
+    if bias is not None:
+        assert relerr(grads[2], wg[2]) < 1e-4, (kind, "dbias")

@@ -413,3 +413,33 @@ def test_style_scales_all_vs_torch():
             assert g is None or float(g.abs().max()) == 0, i
             continue
         torch.testing.assert_close(g.double(), w_, rtol=1e-4, atol=1e-5 * float(w_.abs().max()) + 1e-9, msg=lambda m_: f"grad {i}: {m_}")
+
+
+def test_discriminator_tcgen05_backend_matches_cudnn_backend():
+    """Discriminator(64) (channels 512, all ResBlock convs on the tensor-core path) vs the composed cuDNN path in true fp32:
+    logits and every gradient (input, weights, both biases of a ConvLayer)."""
+    from stylerenderer_b200 import layers as L, model as M
+    from make_golden import seeded
+    D = det_fill(M.Discriminator(64), 730).cuda().to(memory_format=torch.channels_last)
+    x = seeded((4, 3, 64, 64), 731).cuda().contiguous(memory_format=torch.channels_last)
+
+    def run():
+        xx = x.clone().requires_grad_(True)
+        y = D(xx)
+        ps = [p for _, p in sorted(D.named_parameters())]
+        return y.detach(), torch.autograd.grad(y.sum(), [xx] + ps)
+    y_a, g_a = run()
+    L.set_conv_backend("tcgen05")
+    try:
+        y_b, g_b = run()
+    finally:
+        L.set_conv_backend("cudnn")
+    close(y_b, y_a.cpu(), "discriminator logits")
+    names = ["x"] + [n for n, _ in sorted(D.named_parameters())]
+    for n, a, bb in zip(names, g_a, g_b):
+        if float(a.abs().max()) == 0:
+            continue
+        a, bb = a.double().flatten(), bb.double().flatten()
+        c = float((a @ bb) / (a.norm() * bb.norm()))
+        assert c > 0.999, f"{n}: cosine {c:.5f}"
+        assert abs(float(bb.norm() / a.norm()) - 1) < 2e-2, f"{n}: norm ratio {float(bb.norm() / a.norm()):.4f}"
