@@ -120,6 +120,100 @@ class ModConvTC(Function):
         return from_nhwc(g_x), g_w, g_s, e / d, None, None, None
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Twice (arbitrarily often) differentiable convolutions on the tensor-core kernels, for the regulariser iterations
+# (R1 / path length, reference train.py:110-134) that differentiate through a backward pass.  The three bilinear maps
+#   conv(x, w),  dgrad(g, w),  wgrad(g, x)
+# are autograd Functions whose backward passes are built from each other, exactly like torch's own convolution
+# double-backward; every one of them is one launch of the implicit-GEMM / wgrad kernels on tf32-rounded operands.
+# kind 'plain': 3x3, stride 1, pad 1;  kind 'up': stride-2 transposed 3x3 (reference layers.py:301-309), output (2H+1)^2.
+def _conv_fwd(x, w, kind):
+    xr, wk = tc.modulate(x), tc.weight_prep(w, 1.0, 0)
+    return tc.conv3x3(xr, wk) if kind == "plain" else tc.conv_transpose3x3_s2(xr, wk)
+
+
+def _conv_dgrad(g, w, kind, hw):
+    gr = tc.modulate(g)
+    if kind == "plain":
+        return tc.conv3x3(gr, tc.weight_prep(w, 1.0, 1))
+    return tc.conv3x3_s2_gather(gr, tc.weight_prep(w, 1.0, 2), hw)
+
+
+def _conv_wgrad(g, x, kind):
+    gr, xr = tc.modulate(g), tc.modulate(x)
+    dwk = tc.wgrad3x3(gr, xr) if kind == "plain" else tc.wgrad_transpose3x3_s2(gr, xr)
+    return style.weight_grad_layout(dwk, 1.0, g.shape[3], x.shape[3], 3)[0]
+
+
+class ConvTC(Function):
+    """y = conv(x, w): x [B,H,W,Cin] NHWC, w [Cout,Cin,3,3] -> [B,H',W',Cout]."""
+
+    @staticmethod
+    def forward(ctx, x, w, kind):
+        x, w = x.contiguous(), w.contiguous()
+        ctx.save_for_backward(x, w)
+        ctx.kind = kind
+        return _conv_fwd(x, w, kind)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = ConvDgradTC.apply(gy, w, ctx.kind, (x.shape[1], x.shape[2])) if ctx.needs_input_grad[0] else None
+        gw = ConvWgradTC.apply(gy, x, ctx.kind) if ctx.needs_input_grad[1] else None
+        return gx, gw, None
+
+
+class ConvDgradTC(Function):
+    """gx = dgrad(g, w): the gradient of conv(x, w) w.r.t. x for the output gradient g."""
+
+    @staticmethod
+    def forward(ctx, g, w, kind, hw):
+        g, w = g.contiguous(), w.contiguous()
+        ctx.save_for_backward(g, w)
+        ctx.kind = kind
+        return _conv_dgrad(g, w, kind, hw)
+
+    @staticmethod
+    def backward(ctx, ggx):
+        g, w = ctx.saved_tensors
+        ggx = ggx.contiguous()
+        d_g = ConvTC.apply(ggx, w, ctx.kind) if ctx.needs_input_grad[0] else None
+        d_w = ConvWgradTC.apply(g, ggx, ctx.kind) if ctx.needs_input_grad[1] else None
+        return d_g, d_w, None, None
+
+
+class ConvWgradTC(Function):
+    """gw = wgrad(g, x) [Cout,Cin,3,3]: the gradient of conv(x, w) w.r.t. w for the output gradient g."""
+
+    @staticmethod
+    def forward(ctx, g, x, kind):
+        g, x = g.contiguous(), x.contiguous()
+        ctx.save_for_backward(g, x)
+        ctx.kind = kind
+        return _conv_wgrad(g, x, kind)
+
+    @staticmethod
+    def backward(ctx, ggw):
+        g, x = ctx.saved_tensors
+        ggw = ggw.contiguous()
+        d_g = ConvTC.apply(x, ggw, ctx.kind) if ctx.needs_input_grad[0] else None
+        d_x = ConvDgradTC.apply(g, ggw, ctx.kind, (x.shape[1], x.shape[2])) if ctx.needs_input_grad[1] else None
+        return d_g, d_x, None
+
+
+def mod_conv_dd(mod, x, style):
+    """ModulatedConv2d.forward for iterations that need double backward: the modulation / demodulation are plain torch
+    ops (differentiable to any order), the contraction is ConvTC on the tensor cores."""
+    s, d = mod.style_scales(style)
+    b, cin = x.shape[:2]
+    xs = (x * s.view(b, cin, 1, 1)).permute(0, 2, 3, 1).contiguous()
+    y = ConvTC.apply(xs, mod.weight[0] * mod.scale, "up" if mod.upsample else "plain").permute(0, 3, 1, 2)
+    if mod.upsample:
+        y = mod.blur(y)
+    return y * d.view(b, -1, 1, 1)
+
+
 _ONES = {}
 
 

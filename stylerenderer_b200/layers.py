@@ -213,9 +213,11 @@ class ModulatedConv2d(nn.Module):                     # reference layers.py:259-
 
     def forward(self, input, style):
         batch, in_channel = input.shape[:2]
-        if _CONFIG["conv_backend"] == "tcgen05" and not (torch.is_grad_enabled() and _CONFIG["double_backward"]):
+        if _CONFIG["conv_backend"] == "tcgen05":
             from . import fused                          # hand-written tensor-core contraction where the shape allows
             if fused.supported(self, input):
+                if torch.is_grad_enabled() and _CONFIG["double_backward"]:
+                    return fused.mod_conv_dd(self, input, style)     # twice differentiable (R1 / path-length iterations)
                 return fused.mod_conv(self, input, style)
         s, d = self.style_scales(style)
         if self.kernel_size == 1 and not self.upsample and not self.downsample:

@@ -189,3 +189,31 @@ def test_plain_conv_layer_tc(kind, shape):
     assert relerr(grads[1], wg[1] * scale) < 2e-3, (kind, "dw")       # d/dw = scale * d/d(scale*w)
     if bias is not None:
         assert relerr(grads[2], wg[2]) < 1e-4, (kind, "dbias")
+
+
+@pytest.mark.parametrize("kind,shape", [("plain", (2, 128, 128, 12, 20)), ("up", (2, 128, 256, 9, 7))])
+def test_conv_tc_double_backward(kind, shape):
+    """ConvTC / ConvDgradTC / ConvWgradTC (the twice-differentiable tensor-core convolution used on R1 / path-length
+    iterations): first and second order gradients against torch's float64 convolution double backward."""
+    from stylerenderer_b200 import fused
+    b, cin, cout, h, w = shape
+    x = (seeded((b, h, w, cin), 61).cuda()).requires_grad_(True)
+    wt = (seeded((cout, cin, 3, 3), 62).cuda() * 0.05).requires_grad_(True)
+    y = fused.ConvTC.apply(x, wt, kind)
+    gy = seeded(tuple(y.shape), 63).cuda().requires_grad_(True)
+    gx, gw = torch.autograd.grad(y, (x, wt), gy, create_graph=True)
+    # a scalar that depends on the first-order gradients (like the path-length penalty) and its gradients
+    c1, c2 = seeded(tuple(gx.shape), 64).cuda(), seeded(tuple(gw.shape), 65).cuda()
+    pen = (gx * c1).sum() + (gw * c2).sum() + (gx ** 2).sum() * 0.01
+    got = torch.autograd.grad(pen, (x, wt, gy))
+
+    x64, w64, g64 = (t.detach().double().requires_grad_(True) for t in (x, wt, gy))
+    xn = x64.permute(0, 3, 1, 2)
+    yr = F.conv2d(xn, w64, padding=1) if kind == "plain" else F.conv_transpose2d(xn, w64.transpose(0, 1), stride=2)
+    assert relerr(y.detach().permute(0, 3, 1, 2), yr.detach()) < 2e-3
+    gxr, gwr = torch.autograd.grad(yr, (x64, w64), g64.permute(0, 3, 1, 2), create_graph=True)
+    assert relerr(gx.detach(), gxr.detach()) < 2e-3 and relerr(gw.detach(), gwr.detach()) < 2e-3
+    penr = (gxr * c1.double()).sum() + (gwr * c2.double()).sum() + (gxr ** 2).sum() * 0.01
+    want = torch.autograd.grad(penr, (x64, w64, g64))
+    for name, a, bb in zip(("d/dx", "d/dw", "d/dgy"), got, want):
+        assert relerr(a, bb) < 3e-3, (kind, name, relerr(a, bb))
