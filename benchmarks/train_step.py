@@ -154,10 +154,12 @@ def main():
     B, tri = args.batch, face.tri
     mean_path = torch.zeros((), device=dev)
 
+    from stylerenderer_b200 import mesh as mesh_frontend
+
     def sample_mesh(n):
         with torch.no_grad():
-            vert = random_pose(face(face.random_input(n)))
-            return vert, vertex_normals(vert, tri)
+            vert = random_pose(face(face.random_input(n))).contiguous()
+            return vert, mesh_frontend.mesh_point_normal(vert, tri)          # sr_mesh_vertex_normals_f32
 
     def iteration(i):
         nonlocal mean_path

@@ -284,6 +284,15 @@ int sr_conv_weight_prep_dual_tf32(float *fwd, float *tr, float *wsq, const float
 /* gw[o,i,t] = scale * dwk[o,t,i]: result of sr_conv_wgrad_tf32 ([cout][taps][cin]) -> reference weight layout. */
 int sr_weight_grad_layout_f32(float *gw, const float *dwk, float scale, int64_t cout, int64_t cin, int taps, void *stream);
 
+/* ------------------------------------------------------------------ mesh front-end -------------
+ * Area-weighted vertex normals, replaces `mesh_point_normal` (reference utils_3d.py:379-404: three host-built sparse
+ * matrix products + Normalize, reference layers.py:13-30):
+ *   normals[b,v,:] = normalize( sum over faces f containing v of (v_b - v_a) x (v_c - v_a) ),  |.| clamped at eps.
+ * verts [batch,nv,3], tris int64 [nf,3] (shared_f) or [batch,nf,3]; faces with an index outside [0,nv) are skipped.
+ * Accumulation uses float atomics (summation order not deterministic). */
+int sr_mesh_vertex_normals_f32(float *normals, const float *verts, const int64_t *tris, int64_t batch, int64_t nv,
+                               int64_t nf, int shared_f, float eps, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

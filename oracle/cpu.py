@@ -172,3 +172,15 @@ def rasterize_grads(v, tex, ind, coeff, grad_out, perspective=False, eps=1e-6):
     _raster_fn("sr_oracle_raster_scatter", v.dtype)(_I64(ind.numel() // 3), _I64(c), _p(ind), _p(coeff.contiguous()),
                                                     _p(dc), _p(tex_c), _p(g), _p(gv), _p(gt))
     return gv.view(v.shape).to(v.dtype), gt.view(tex.shape).to(tex.dtype)
+
+
+def mesh_point_normal(v, tri):
+    """<-> utils_3d.py:379-404 (`mesh_point_normal`): v [b, n, 3] float32, tri int64 [f, 3] -> unit normals [b, n, 3]."""
+    v = v[..., :3].contiguous().float()
+    tri = tri.contiguous().long()
+    b, n, _ = v.shape
+    out = torch.empty(b, n, 3, dtype=torch.float32)
+    scratch = torch.empty(n * 3, dtype=torch.float32)
+    lib().sr_oracle_vertex_normals_f32(_p(out), _p(v), _p(tri), _I64(b), _I64(n), _I64(tri.shape[0]), _p(scratch),
+                                       ctypes.c_float(1e-8))
+    return out

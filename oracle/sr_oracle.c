@@ -99,3 +99,40 @@ void sr_oracle_bias_grad_f32(double *gb, const float *dx, int64_t size_x, int64_
 #include "raster_body.inc"
 #undef REAL
 #undef FN
+
+/* ------------------------------------------------------------------ mesh vertex normals ---- */
+/* `mesh_point_normal` (utils_3d.py:379-404) + `Normalize` L2 (layers.py:13-30):
+ *   fn[f] = (v_b - v_a) x (v_c - v_a)   (elementwise products and differences, :384-388);
+ *   for corner j = 0..2: vn += sparse.mm(I_j, fn)  -- a per-corner partial sum over the faces in list order, added to
+ *   the running total (:390-403);  vn / max(sqrt(sum vn^2), eps).
+ * The sparse product's internal summation order is not specified; the partial sums are taken here in face order. */
+void sr_oracle_vertex_normals_f32(float *out, const float *v, const int64_t *tri, int64_t batch, int64_t nv, int64_t nf,
+                                  float *scratch /* [nv*3] */, float eps)
+{
+    int64_t b, f, i, j;
+    for (b = 0; b < batch; ++b) {
+        const float *vb = v + b * nv * 3;
+        float *o = out + b * nv * 3;
+        for (i = 0; i < nv * 3; ++i) o[i] = 0.0f;
+        for (j = 0; j < 3; ++j) {
+            for (i = 0; i < nv * 3; ++i) scratch[i] = 0.0f;
+            for (f = 0; f < nf; ++f) {
+                const int64_t ia = tri[f * 3], ib = tri[f * 3 + 1], ic = tri[f * 3 + 2], id = tri[f * 3 + j];
+                float ab[3], ac[3], n[3];
+                int c;
+                for (c = 0; c < 3; ++c) { ab[c] = vb[ib * 3 + c] - vb[ia * 3 + c]; ac[c] = vb[ic * 3 + c] - vb[ia * 3 + c]; }
+                n[0] = ab[1] * ac[2] - ab[2] * ac[1];
+                n[1] = ab[2] * ac[0] - ab[0] * ac[2];
+                n[2] = ab[0] * ac[1] - ab[1] * ac[0];
+                for (c = 0; c < 3; ++c) scratch[id * 3 + c] += n[c];
+            }
+            for (i = 0; i < nv * 3; ++i) o[i] += scratch[i];
+        }
+        for (i = 0; i < nv; ++i) {
+            float x = o[i * 3], y = o[i * 3 + 1], z = o[i * 3 + 2];
+            float nrm = sqrtf(x * x + y * y + z * z);
+            if (nrm < eps) nrm = eps;
+            o[i * 3] = x / nrm; o[i * 3 + 1] = y / nrm; o[i * 3 + 2] = z / nrm;
+        }
+    }
+}

@@ -49,6 +49,7 @@ _SIGNATURES = {
     "sr_weight_sq_backward_f32": (_I, [_P, _P, _P, _F, _L, _L, _I, _P]),
     "sr_weight_grad_layout_f32": (_I, [_P, _P, _F, _L, _L, _I, _P]),
     "sr_conv_weight_prep_dual_tf32": (_I, [_P, _P, _P, _P, _F, _L, _L, _I, _I, _P]),
+    "sr_mesh_vertex_normals_f32": (_I, [_P, _P, _P, _L, _L, _L, _I, _F, _P]),
 }
 
 EXPORTS = tuple(_SIGNATURES)
