@@ -260,8 +260,13 @@ def generator_step(G, z, cot):
 def cpu_reference_generator_rate(batch, iters, threads=None):
     """Native-PyTorch CPU restatement of the reference (oracle/torch_ref.py) -- the checker, timed as a baseline."""
     from oracle import torch_ref as T
-    if threads:
-        torch.set_num_threads(threads)
+    if threads is None:
+        try:
+            threads = max(1, len(os.sched_getaffinity(0)))
+        except (AttributeError, OSError):
+            threads = max(1, os.cpu_count() or 1)
+    prev_threads = torch.get_num_threads()
+    torch.set_num_threads(threads)
     torch.manual_seed(0)
     G = T.Generator(256, 512, 8, channel_multiplier=2)
     z = torch.randn(batch, 512)
@@ -276,7 +281,9 @@ def cpu_reference_generator_rate(batch, iters, threads=None):
         (img * cot).sum().backward()
         if it:                                          # first pass = warm-up
             times.append(time.perf_counter() - t0)
-    return batch * len(times) / sum(times), torch.get_num_threads()
+    used = torch.get_num_threads()
+    torch.set_num_threads(prev_threads)
+    return batch * len(times) / sum(times), used
 
 
 def run_reference_arm(args):
@@ -286,6 +293,11 @@ def run_reference_arm(args):
     batch = 2
     per_step = []
     from oracle import torch_ref as T
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would make the baseline 10x slower)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, OSError):
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     torch.manual_seed(0)
     G = T.Generator(256, 512, 8, channel_multiplier=2)
     z = torch.randn(batch, 512)
