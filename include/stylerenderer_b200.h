@@ -234,6 +234,23 @@ int sr_styled_bwd_prologue2_f32(float *ga, float *g_bias, float *g_noise_w, floa
                                 const float *noise_weight, const float *bias, const float *d, int64_t batch,
                                 int64_t pixels, int64_t channels, float alpha, float gain, void *stream);
 
+/* StyledMapConv variants (reference model.py:33-55: `out = out * stylemap[:, :1] + stylemap[:, 1:2]` between the conv and
+ * the noise): stylemap = [batch, 2, h, w] planes with batch stride `stylemap_batch_stride` floats (plane stride h*w), may
+ * be NULL.  The FIR tail computes y = lrelu(fir * map0 + map1 + noise_w*noise + bias) * gain; the backward prologue hands
+ * gp * map0 (* d) to the GEMMs and accumulates g_stylemap [batch, 2, pixels] (zeroed by the call):
+ *   g_map1 = sum_c gp,  g_map0 = sum_c gp * conv_d  (conv_d recovered as (t - map1 - noise - bias) / map0). */
+int sr_blur_nhwc_styled3_f32(float *out, float *out2, const float *scale2, const float *x, const float *taps,
+                             int64_t batch, int64_t in_h, int64_t in_w, int64_t channels, int pad0, int pad1,
+                             const float *noise, int64_t noise_batch_stride, const float *noise_weight,
+                             const float *bias, float alpha, float gain, const float *stylemap,
+                             int64_t stylemap_batch_stride, void *stream);
+int sr_styled_bwd_prologue3_f32(float *ga, float *g_bias, float *g_noise_w, float *e, float *ds_next, float *d_rgb_weight,
+                                const float *gy, const float *gxs, const float *s_next, const float *g_rgb,
+                                const float *rgb_weight, const float *y, const float *noise, int64_t noise_batch_stride,
+                                const float *noise_weight, const float *bias, const float *d, int64_t batch,
+                                int64_t pixels, int64_t channels, float alpha, float gain, const float *stylemap,
+                                int64_t stylemap_batch_stride, float *g_stylemap, void *stream);
+
 /* out[n,p,c] = a[n,p,c] * scale[n,c] (optionally rounded to tf32), dot[n,c] = sum_p a[n,p,c] * other[n,p,c];
  * out or dot may be NULL; dot is zeroed by the call. */
 int sr_scale_dot_nhwc_f32(float *out, float *dot, const float *a, const float *other, const float *scale,

@@ -50,13 +50,16 @@ _SIGNATURES = {
     "sr_weight_grad_layout_f32": (_I, [_P, _P, _F, _L, _L, _I, _P]),
     "sr_conv_weight_prep_dual_tf32": (_I, [_P, _P, _P, _P, _F, _L, _L, _I, _I, _P]),
     "sr_mesh_vertex_normals_f32": (_I, [_P, _P, _P, _L, _L, _L, _I, _F, _P]),
+    "sr_blur_nhwc_styled3_f32": (_I, [_P, _P, _P, _P, _P, _L, _L, _L, _L, _I, _I, _P, _L, _P, _P, _F, _F, _P, _L, _P]),
+    "sr_styled_bwd_prologue3_f32": (_I, [_P] * 13 + [_L, _P, _P, _P, _L, _L, _L, _F, _F, _P, _L, _P, _P]),
 }
 
 EXPORTS = tuple(_SIGNATURES)
 CONV_EXPORTS = ("sr_blur_nhwc_scaledot_f32", "sr_blur_nhwc_styled_f32", "sr_blur_nhwc_styled2_f32", "sr_styled_bwd_prologue_f32", "sr_styled_bwd_prologue2_f32", "sr_scale_dot_nhwc_f32",
                 "sr_conv_igemm_tf32", "sr_conv_igemm_multi_tf32", "sr_conv_wgrad_tf32", "sr_modulate_tf32", "sr_conv_weight_prep_tf32",
                 "sr_style_scales_forward_f32", "sr_style_scales_backward_f32", "sr_weight_sq_f32", "sr_weight_sq_backward_f32",
-                "sr_weight_grad_layout_f32", "sr_conv_weight_prep_dual_tf32")
+                "sr_weight_grad_layout_f32", "sr_conv_weight_prep_dual_tf32", "sr_blur_nhwc_styled3_f32",
+                "sr_styled_bwd_prologue3_f32")
 
 
 class NativeLibraryError(RuntimeError):

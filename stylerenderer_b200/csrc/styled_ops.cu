@@ -53,6 +53,12 @@ struct PrologueParams {
     long long noise_bstride;
     int pixels, C4, chunks_per_image, pix_per_chunk;
     float alpha, gain;
+    // StyledMapConv (reference model.py:48-52): t = conv_d * map0[b,p] + map1[b,p] + noise_w * noise + bias.  Then the
+    // gradient handed to the GEMMs is gp * map0 (* d), e = sum gp * (conv_d * map0), and per pixel
+    //   g_map1 = sum_c gp,   g_map0 = sum_c gp * conv_d = (sum_c gp * (t - map1 - noise_w * noise - bias)) / map0.
+    const float *stylemap;        // [B, 2, pixels] planes (batch stride map_bstride, plane stride = pixels) or nullptr
+    long long map_bstride;
+    float *g_map;                 // [B, 2, pixels] contiguous, += (zeroed by the caller)
 };
 
 // grid.x = B * chunks_per_image
@@ -90,7 +96,7 @@ styled_bwd_prologue_kernel(const PrologueParams p)
     for (int px0 = p0 + pl; px0 < p1; px0 += 2 * lanes_p) {
         const int pxs[2] = {px0, px0 + lanes_p};
         float4 yy2[2], g2[2], gx2[2];
-        float gk2[2][3], n2[2];
+        float gk2[2][3], n2[2], m02[2], m12[2];
         bool ok[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -103,6 +109,8 @@ styled_bwd_prologue_kernel(const PrologueParams p)
 #pragma unroll
             for (int k = 0; k < 3; ++k) gk2[u][k] = grgb ? __ldg(grgb + pp * 3 + k) : 0.0f;
             n2[u] = nz ? __ldg(nz + pp) : 0.0f;
+            m02[u] = p.stylemap ? __ldg(p.stylemap + (long long)b * p.map_bstride + pp) : 1.0f;
+            m12[u] = p.stylemap ? __ldg(p.stylemap + (long long)b * p.map_bstride + p.pixels + pp) : 0.0f;
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -126,13 +134,31 @@ styled_bwd_prologue_kernel(const PrologueParams p)
             gp.z = ((yy.z > 0.f) ? g.z : g.z * p.alpha) * p.gain; gp.w = ((yy.w > 0.f) ? g.w : g.w * p.alpha) * p.gain;
             f4_add(a_bias, gp);
             a_nw += ((gp.x + gp.y) + (gp.z + gp.w)) * n;
-            if (p.e) {
+            if (p.e || p.stylemap) {
                 // the pre-activation is recoverable from y (gain, alpha > 0): t = y / gain or y / (gain * alpha)
                 uu.x = yy.x * ((yy.x > 0.f) ? ipos : ineg); uu.y = yy.y * ((yy.y > 0.f) ? ipos : ineg);
                 uu.z = yy.z * ((yy.z > 0.f) ? ipos : ineg); uu.w = yy.w * ((yy.w > 0.f) ? ipos : ineg);
-                const float sh = nw * n;
+                const float sh = nw * n + m12[u];
                 uu.x -= sh + bias.x; uu.y -= sh + bias.y; uu.z -= sh + bias.z; uu.w -= sh + bias.w;
-                f4_fma(a_e, gp, uu);
+                if (p.e) f4_fma(a_e, gp, uu);
+            }
+            if (p.stylemap) {
+                // per-pixel reductions over the channels: the C4 threads of a pixel are consecutive (whole warps when
+                // C4 >= 32, aligned sub-warp groups when C4 is a smaller power of two)
+                float s1 = (gp.x + gp.y) + (gp.z + gp.w);
+                float s0 = fmaf(gp.x, uu.x, fmaf(gp.y, uu.y, fmaf(gp.z, uu.z, gp.w * uu.w)));
+                const int width = C4 < 32 ? C4 : 32;
+                const unsigned amask = __activemask();          // sub-warp pixel groups may be masked off independently
+                for (int o_ = width >> 1; o_ > 0; o_ >>= 1) {
+                    s1 += __shfl_xor_sync(amask, s1, o_);
+                    s0 += __shfl_xor_sync(amask, s0, o_);
+                }
+                if ((threadIdx.x & (width - 1)) == 0) {
+                    float *gm = p.g_map + (long long)b * 2 * p.pixels + px;
+                    atomicAdd(gm, s0 / m02[u]);
+                    atomicAdd(gm + p.pixels, s1);
+                }
+                gp.x *= m02[u]; gp.y *= m02[u]; gp.z *= m02[u]; gp.w *= m02[u];
             }
             float4 o = f4_mul(gp, dd);
             if (p.d) o = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
@@ -215,13 +241,17 @@ bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 using namespace sr;
 
-extern "C" int sr_styled_bwd_prologue2_f32(float *ga, float *g_bias, float *g_noise_w, float *e, float *ds_next,
+extern "C" int sr_styled_bwd_prologue3_f32(float *ga, float *g_bias, float *g_noise_w, float *e, float *ds_next,
                                            float *d_rgb_weight, const float *gy, const float *gxs, const float *s_next,
                                            const float *g_rgb, const float *rgb_weight, const float *y, const float *noise,
                                            int64_t noise_batch_stride, const float *noise_weight, const float *bias,
                                            const float *d, int64_t batch, int64_t pixels, int64_t channels, float alpha,
-                                           float gain, void *stream)
+                                           float gain, const float *stylemap, int64_t stylemap_batch_stride, float *g_stylemap,
+                                           void *stream)
 {
+    SR_REQUIRE(!stylemap || g_stylemap, "styled_bwd_prologue: stylemap needs g_stylemap");
+    SR_REQUIRE(!stylemap || (channels / 4 >= 32 || ((channels / 4) & (channels / 4 - 1)) == 0),
+               "styled_bwd_prologue: with a stylemap channels/4 must be >= 32 or a power of two");
     SR_REQUIRE(ga && g_bias && y && (gy || gxs || g_rgb), "styled_bwd_prologue: null pointer / no gradient source");
     SR_REQUIRE(ok_channels(channels), "styled_bwd_prologue: channels must be 4*k with k dividing 256 (got %lld)", (long long)channels);
     SR_REQUIRE(al16(ga) && (!gy || al16(gy)) && al16(y) && (!bias || al16(bias)) && (!d || al16(d)) && (!gxs || al16(gxs)) &&
@@ -236,6 +266,7 @@ extern "C" int sr_styled_bwd_prologue2_f32(float *ga, float *g_bias, float *g_no
     if (er == cudaSuccess && e) er = cudaMemsetAsync(e, 0, sizeof(float) * (size_t)(batch * channels), st);
     if (er == cudaSuccess && gxs) er = cudaMemsetAsync(ds_next, 0, sizeof(float) * (size_t)(batch * channels), st);
     if (er == cudaSuccess && g_rgb) er = cudaMemsetAsync(d_rgb_weight, 0, sizeof(float) * (size_t)(batch * 3 * channels), st);
+    if (er == cudaSuccess && stylemap) er = cudaMemsetAsync(g_stylemap, 0, sizeof(float) * (size_t)(batch * 2 * pixels), st);
     if (er != cudaSuccess) { set_error("styled_bwd_prologue: memset: %s", cudaGetErrorString(er)); return (int)er; }
     if (batch == 0 || pixels == 0) return SR_OK;
     PrologueParams p;
@@ -245,9 +276,22 @@ extern "C" int sr_styled_bwd_prologue2_f32(float *ga, float *g_bias, float *g_no
     p.pixels = (int)pixels; p.C4 = (int)(channels / 4);
     p.chunks_per_image = pick_chunks(batch, pixels, p.C4, &p.pix_per_chunk);
     p.alpha = alpha; p.gain = gain;
+    p.stylemap = stylemap; p.map_bstride = stylemap_batch_stride; p.g_map = g_stylemap;
     styled_bwd_prologue_kernel<<<(unsigned)(batch * p.chunks_per_image), kThreads, 0, st>>>(p);
     count_launch();
     return check_launch("sr_styled_bwd_prologue_f32");
+}
+
+extern "C" int sr_styled_bwd_prologue2_f32(float *ga, float *g_bias, float *g_noise_w, float *e, float *ds_next,
+                                           float *d_rgb_weight, const float *gy, const float *gxs, const float *s_next,
+                                           const float *g_rgb, const float *rgb_weight, const float *y, const float *noise,
+                                           int64_t noise_batch_stride, const float *noise_weight, const float *bias,
+                                           const float *d, int64_t batch, int64_t pixels, int64_t channels, float alpha,
+                                           float gain, void *stream)
+{
+    return sr_styled_bwd_prologue3_f32(ga, g_bias, g_noise_w, e, ds_next, d_rgb_weight, gy, gxs, s_next, g_rgb, rgb_weight, y,
+                                       noise, noise_batch_stride, noise_weight, bias, d, batch, pixels, channels, alpha, gain,
+                                       nullptr, 0, nullptr, stream);
 }
 
 extern "C" int sr_styled_bwd_prologue_f32(float *ga, float *g_bias, float *g_noise_w, float *e, const float *gy,

@@ -304,6 +304,9 @@ struct NhwcGeom {
     // SCALEDOT epilogue (backward of the up-sampling block): out = tf32(acc * scale2[n,c]), dot[n,c] += sum acc * other
     const float *other;
     float *dot;
+    // STYLED with a style map (StyledMapConv, reference model.py:50): y = lrelu(acc * map0 + map1 + noise + bias) * gain
+    const float *stylemap;        // [B, 2, out_h, out_w] planes (batch stride map_bstride) or nullptr
+    long long map_bstride;
 };
 
 template <int KH, int KW, int MODE>     // MODE 0: plain, 1: STYLED forward tail, 2: SCALEDOT backward tail
@@ -380,12 +383,18 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
         if (STYLED) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const float add = (nz && ox0 + j < g.out_w) ? nw * __ldg(nz + (int64_t)oy * g.out_w + ox0 + j) : 0.0f;
+                float add = (nz && ox0 + j < g.out_w) ? nw * __ldg(nz + (int64_t)oy * g.out_w + ox0 + j) : 0.0f;
+                float m0 = 1.0f;
+                if (g.stylemap && ox0 + j < g.out_w) {
+                    const float *mp = g.stylemap + (int64_t)n * g.map_bstride + (int64_t)oy * g.out_w + ox0 + j;
+                    m0 = __ldg(mp);
+                    add += __ldg(mp + (int64_t)g.out_h * g.out_w);
+                }
                 float t;
-                t = acc[j].x + add + bias4.x; acc[j].x = ((t > 0.f) ? t : t * g.alpha) * g.gain;
-                t = acc[j].y + add + bias4.y; acc[j].y = ((t > 0.f) ? t : t * g.alpha) * g.gain;
-                t = acc[j].z + add + bias4.z; acc[j].z = ((t > 0.f) ? t : t * g.alpha) * g.gain;
-                t = acc[j].w + add + bias4.w; acc[j].w = ((t > 0.f) ? t : t * g.alpha) * g.gain;
+                t = fmaf(acc[j].x, m0, add + bias4.x); acc[j].x = ((t > 0.f) ? t : t * g.alpha) * g.gain;
+                t = fmaf(acc[j].y, m0, add + bias4.y); acc[j].y = ((t > 0.f) ? t : t * g.alpha) * g.gain;
+                t = fmaf(acc[j].z, m0, add + bias4.z); acc[j].z = ((t > 0.f) ? t : t * g.alpha) * g.gain;
+                t = fmaf(acc[j].w, m0, add + bias4.w); acc[j].w = ((t > 0.f) ? t : t * g.alpha) * g.gain;
             }
         }
         if (MODE == 2) {
@@ -760,15 +769,17 @@ int launch_nhwc_tma(float *out, const float *x, const float *taps, int64_t major
 int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, int in_h, int in_w, int oh, int ow,
                 int64_t minor, int pad_x0, int pad_y0, bool styled, const float *noise, long long noise_bstride,
                 const float *noise_weight, const float *bias, float alpha, float gain, cudaStream_t st,
-                float *out2 = nullptr, const float *scale2 = nullptr, const float *other = nullptr, float *dot = nullptr)
+                float *out2 = nullptr, const float *scale2 = nullptr, const float *other = nullptr, float *dot = nullptr,
+                const float *stylemap = nullptr, long long map_bstride = 0)
 {
-    if (pad_x0 == pad_y0) {
+    if (pad_x0 == pad_y0 && !stylemap) {
         const int rc = launch_nhwc_tma(out, x, taps, major, in_h, in_w, oh, ow, minor, pad_x0, dot ? 2 : (styled ? 1 : 0), noise,
                                        noise_bstride, noise_weight, bias, alpha, gain, st, out2, scale2, other, dot);
         if (rc == SR_OK) return rc;
     }
     NhwcGeom g;
     g.out2 = out2; g.scale2 = scale2; g.other = other; g.dot = dot;
+    g.stylemap = stylemap; g.map_bstride = map_bstride;
     g.major = major; g.in_h = in_h; g.in_w = in_w; g.out_h = oh; g.out_w = ow;
     g.c4 = (int)(minor / 4); g.pad_x0 = pad_x0; g.pad_y0 = pad_y0;
     g.rows_per_strip = oh >= 64 ? 16 : (oh >= 16 ? 8 : 4);
@@ -791,10 +802,11 @@ int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, in
 
 using namespace sr;
 
-extern "C" int sr_blur_nhwc_styled2_f32(float *out, float *out2, const float *scale2, const float *x, const float *taps,
+extern "C" int sr_blur_nhwc_styled3_f32(float *out, float *out2, const float *scale2, const float *x, const float *taps,
                                         int64_t batch, int64_t in_h, int64_t in_w, int64_t channels, int pad0, int pad1,
                                         const float *noise, int64_t noise_batch_stride, const float *noise_weight,
-                                        const float *bias, float alpha, float gain, void *stream)
+                                        const float *bias, float alpha, float gain, const float *stylemap,
+                                        int64_t stylemap_batch_stride, void *stream)
 {
     SR_REQUIRE(out && x && taps, "blur_nhwc_styled: null pointer");
     SR_REQUIRE(channels >= 4 && channels % 4 == 0, "blur_nhwc_styled: channels must be a multiple of 4");
@@ -807,10 +819,20 @@ extern "C" int sr_blur_nhwc_styled2_f32(float *out, float *out2, const float *sc
     SR_REQUIRE(oh >= 1 && ow >= 1, "blur_nhwc_styled: FIR larger than the padded input");
     if (batch == 0) return SR_OK;
     int rc = launch_nhwc(out, x, taps, batch, (int)in_h, (int)in_w, (int)oh, (int)ow, channels, pad0, pad0, true, noise,
-                         noise_batch_stride, noise_weight, bias, alpha, gain, (cudaStream_t)stream, out2, scale2);
+                         noise_batch_stride, noise_weight, bias, alpha, gain, (cudaStream_t)stream, out2, scale2, nullptr, nullptr,
+                         stylemap, stylemap_batch_stride);
     if (rc != SR_OK) { set_error("blur_nhwc_styled: problem too large"); return rc; }
     count_launch();
     return check_launch("sr_blur_nhwc_styled_f32");
+}
+
+extern "C" int sr_blur_nhwc_styled2_f32(float *out, float *out2, const float *scale2, const float *x, const float *taps,
+                                        int64_t batch, int64_t in_h, int64_t in_w, int64_t channels, int pad0, int pad1,
+                                        const float *noise, int64_t noise_batch_stride, const float *noise_weight,
+                                        const float *bias, float alpha, float gain, void *stream)
+{
+    return sr_blur_nhwc_styled3_f32(out, out2, scale2, x, taps, batch, in_h, in_w, channels, pad0, pad1, noise,
+                                    noise_batch_stride, noise_weight, bias, alpha, gain, nullptr, 0, stream);
 }
 
 extern "C" int sr_blur_nhwc_scaledot_f32(float *out, float *dot, const float *x, const float *taps, const float *scale,

@@ -344,12 +344,13 @@ class ModulateTC(Function):
 
 
 class StyledLayerTC(Function):
-    """One StyledConv block of the chain.  Input: xs (already x * s, tf32).  Outputs: (main, rgb) with
-    main = tf32(y * s_next) if s_next is given else y, rgb = sum_c y * rgb_weight (or None)."""
+    """One StyledConv / StyledMapConv block of the chain.  Input: xs (already x * s, tf32).  Outputs: (main, rgb) with
+    main = tf32(y * s_next) if s_next is given else y, rgb = sum_c y * rgb_weight (or None).  With `stylemap` [B,2,H,W]
+    the block is a StyledMapConv (reference model.py:33-55): t = conv_d * map0 + map1 + noise + bias."""
 
     @staticmethod
     def forward(ctx, xs, weight, d, noise, noise_weight, act_bias, s_next, rgb_weight, scale, upsample, blur_taps, alpha,
-                gain, wk=None, wkt=None):
+                gain, wk=None, wkt=None, stylemap=None):
         ctx.set_materialize_grads(False)                     # unused outputs arrive as None, not as zero tensors
         xs_nhwc = to_nhwc(xs)
         b, h, w, cin = xs_nhwc.shape
@@ -367,15 +368,16 @@ class StyledLayerTC(Function):
             rgb = torch.empty(b, h, w, 3, dtype=torch.float32, device=xs.device) if rgb_weight is not None else None
             tc.conv3x3(xs_nhwc, wk, out=y, epilogue=1, rowscale=d, bias=act_bias, alpha=alpha, gain=gain,
                        noise=noise.reshape(-1, h, w).contiguous(), noise_weight=noise_weight, out2=y2, scale2=s_next,
-                       rgb_weight=rgb_weight, rgb_out=rgb)
+                       rgb_weight=rgb_weight, rgb_out=rgb, stylemap=stylemap)
         else:
             assert rgb_weight is None
             t = tc.conv_transpose3x3_s2(xs_nhwc, wk, rowscale=d)
             if s_next is not None:
-                y, y2 = tc.blur_styled(t, blur_taps, (1, 1), noise, noise_weight, act_bias, alpha, gain, scale2=s_next)
+                y, y2 = tc.blur_styled(t, blur_taps, (1, 1), noise, noise_weight, act_bias, alpha, gain, scale2=s_next,
+                                       stylemap=stylemap)
             else:
-                y = tc.blur_styled(t, blur_taps, (1, 1), noise, noise_weight, act_bias, alpha, gain)
-        ctx.save_for_backward(xs_nhwc, y, t, weight, d, noise, noise_weight, act_bias, blur_taps, s_next, rgb_weight)
+                y = tc.blur_styled(t, blur_taps, (1, 1), noise, noise_weight, act_bias, alpha, gain, stylemap=stylemap)
+        ctx.save_for_backward(xs_nhwc, y, t, weight, d, noise, noise_weight, act_bias, blur_taps, s_next, rgb_weight, stylemap)
         ctx.cfg = (scale, upsample, alpha, gain)
         main = from_nhwc(y2 if s_next is not None else y)
         if rgb is None:
@@ -386,7 +388,7 @@ class StyledLayerTC(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, g_main, g_rgb):
-        xs, y, t, weight, d, noise, noise_weight, act_bias, blur_taps, s_next, rgb_weight = ctx.saved_tensors
+        xs, y, t, weight, d, noise, noise_weight, act_bias, blur_taps, s_next, rgb_weight, stylemap = ctx.saved_tensors
         scale, upsample, alpha, gain = ctx.cfg
         b, h, w, cin = xs.shape
         cout = y.shape[3]
@@ -399,19 +401,24 @@ class StyledLayerTC(Function):
                 src.update(gy=g_main)
         if rgb_weight is not None and g_rgb is not None:
             src.update(g_rgb=g_rgb.contiguous(), rgb_weight=rgb_weight)
+        g_map = None
         if not upsample:
-            ga, g_bias, g_noise_w, e, ds_next, dwb = tc.bwd_prologue2(y, noise, noise_weight, act_bias, d, alpha, gain, True, **src)
+            res = tc.bwd_prologue2(y, noise, noise_weight, act_bias, d, alpha, gain, True, stylemap=stylemap, **src)
+            ga, g_bias, g_noise_w, e, ds_next, dwb = res[:6]
+            g_map = res[6] if stylemap is not None else None
             dxs = tc.conv3x3(ga, ctx.wkt if ctx.wkt is not None else tc.weight_prep(weight[0], scale, 1))
             dwk = tc.wgrad3x3(ga, xs)
         else:
-            g_pre, g_bias, g_noise_w, _, ds_next, dwb = tc.bwd_prologue2(y, noise, noise_weight, act_bias, None, alpha, gain,
-                                                                         False, **src)
+            res = tc.bwd_prologue2(y, noise, noise_weight, act_bias, None, alpha, gain, False, stylemap=stylemap, **src)
+            g_pre, g_bias, g_noise_w, _, ds_next, dwb = res[:6]
+            g_map = res[6] if stylemap is not None else None
             ga, e = tc.blur_scaledot(g_pre, torch.flip(blur_taps, [0, 1]), (2, 2), d, t)   # FIR^T, * d, tf32, sum gt * t
             dxs = tc.conv3x3_s2_gather(ga, ctx.wkt if ctx.wkt is not None else tc.weight_prep(weight[0], scale, 2), (h, w))
             dwk = tc.wgrad_transpose3x3_s2(ga, xs)
         g_d = e / d
         g_w = style.weight_grad_layout(dwk, scale, cout, cin, 3)
-        return (from_nhwc(dxs), g_w, g_d, None, g_noise_w, g_bias, ds_next, dwb, None, None, None, None, None, None, None)
+        return (from_nhwc(dxs), g_w, g_d, None, g_noise_w, g_bias, ds_next, dwb, None, None, None, None, None, None, None,
+                g_map)
 
 
 def chain_supported(gen, x):
@@ -419,7 +426,7 @@ def chain_supported(gen, x):
     if L.get_conv_backend() != "tcgen05" or (torch.is_grad_enabled() and L.double_backward_requested()):
         return False
     blocks = [gen.conv1] + list(gen.convs)
-    return all(type(m).__name__ == "StyledConv" and supported(m.conv, x) for m in blocks)
+    return all(type(m).__name__ in ("StyledConv", "StyledMapConv") and supported(m.conv, x) for m in blocks)
 
 
 def _rgb_weights(to_rgb, s):
@@ -428,8 +435,10 @@ def _rgb_weights(to_rgb, s):
     return (conv.weight[0, :, :, 0, 0] * conv.scale).unsqueeze(0) * s.unsqueeze(1)
 
 
-def generator_chain_forward(gen, latent, noise):
-    """Generator.forward body on the chained tensor-core blocks (same math as reference model.py:169-182)."""
+def generator_chain_forward(gen, latent, noise, maps_fn=None):
+    """Generator.forward body on the chained tensor-core blocks (same math as reference model.py:169-182).  With
+    `maps_fn(k, h, w)` -> style map [B,2,h,w] (or None) for block k the blocks are StyledMapConv (GeneratorWithMap,
+    reference model.py:259-285)."""
     blocks = [gen.conv1] + list(gen.convs)
     # ToRGB after conv1 (latent 1) and after the second conv of every resolution (block k even, latent k + 1)
     rgbs = {0: (gen.to_rgb1, 1)}
@@ -451,13 +460,14 @@ def generator_chain_forward(gen, latent, noise):
         wb = _rgb_weights(to_rgb, rgb_style[k]) if to_rgb is not None else None
         b, _, h, w = xs.shape
         oh, ow = (2 * h, 2 * w) if blk.conv.upsample else (h, w)
+        smap = maps_fn(k, oh, ow) if maps_fn is not None else None
         nz = noise[k]
         if nz is None:
             nz = xs.new_empty(b, 1, oh, ow).normal_()
         taps = blk.conv.blur.kernel if blk.conv.upsample else blk.noise.weight
         xs, rgb = StyledLayerTC.apply(xs, blk.conv.weight, scales[k][1], nz, blk.noise.weight, blk.activate.bias, s_next, wb,
                                       blk.conv.scale, blk.conv.upsample, taps, blk.activate.negative_slope,
-                                      blk.activate.scale, prep[k][1], prep[k][2])
+                                      blk.activate.scale, prep[k][1], prep[k][2], smap)
         if to_rgb is not None:
             out = rgb.permute(0, 3, 1, 2) + to_rgb.bias
             skip = out if skip is None else out + to_rgb.upsample(skip)

@@ -189,6 +189,29 @@ class GeneratorWithMap(Generator):                    # reference model.py:188-2
                 truncation_latent=None, input_is_latent=False, noise=None, randomize_noise=True):
         latent, noise = self._prepare(styles, inject_index, truncation, truncation_latent, input_is_latent, noise,
                                       randomize_noise)
+        if latent.is_cuda and fused.chain_supported(self, self.input.input):
+            # chained tensor-core StyledMapConv blocks (fused.py); the rasterised normal maps and the style-map nets are
+            # evaluated per resolution exactly as below and handed to the blocks' epilogues
+            norm_maps, cache = [], {}
+
+            def maps_fn(k, h, w):
+                j = (k + 1) // 2                                         # resolution index: block 0 -> 0, blocks 1,2 -> 1, ...
+                if j not in cache:
+                    nm = rasterize(mesh[0], mesh[1], mesh[2], h, w).permute(0, 3, 1, 2)
+                    norm_maps.append(nm)
+                    if j == 0:
+                        cache[j] = self.norm1(nm)
+                    elif len(self.convs) == len(self.norm_to_style):
+                        i = 2 * j - 1
+                        cache[j] = self.norm_to_style[i](self.norm_to_style[i - 1](nm))
+                    else:
+                        cache[j] = self.norm_to_style[j - 1](nm)
+                m = cache[j] = cache[j].contiguous()                    # NCHW planes (the nets run on channels_last views)
+                if j == 0:
+                    return m
+                return m[:, :2] if k % 2 == 1 else m[:, 2:]
+            skip = fused.generator_chain_forward(self, latent, noise, maps_fn)
+            return skip, (latent if return_latents else None), (norm_maps if return_normals else None)
         out = self.input(latent)
         norm_maps = [rasterize(mesh[0], mesh[1], mesh[2], int(out.shape[2]), int(out.shape[3])).permute(0, 3, 1, 2)]
         maps = self.norm1(norm_maps[-1])

@@ -218,8 +218,17 @@ def _noise_args(noise, oh, ow):
     return nz, (0 if nz.shape[0] == 1 else oh * ow)
 
 
-def blur_styled(t, taps, pad, noise, noise_weight, bias, alpha, gain, scale2=None):
-    """NHWC 4x4 FIR + noise + bias + leaky-ReLU*gain in one pass: [B,IH,IW,C] -> [B,OH,OW,C];
+def _map_args(stylemap, oh, ow):
+    """[B,2,oh,ow] style map (possibly a channel slice of a wider tensor) -> (tensor, batch stride in floats)."""
+    if stylemap is None:
+        return None, 0
+    assert stylemap.shape[1] == 2 and stylemap.shape[2:] == (oh, ow) and stylemap.stride(3) == 1 and \
+        stylemap.stride(2) == ow and stylemap.stride(1) == oh * ow, "stylemap must be [B,2,H,W] with contiguous planes"
+    return stylemap, stylemap.stride(0)
+
+
+def blur_styled(t, taps, pad, noise, noise_weight, bias, alpha, gain, scale2=None, stylemap=None):
+    """NHWC 4x4 FIR (* map0 + map1) + noise + bias + leaky-ReLU*gain in one pass: [B,IH,IW,C] -> [B,OH,OW,C];
     with scale2 [B,C] also returns out2 = tf32(out * scale2) (the next layer's GEMM operand)."""
     _check_nhwc(t, "blur_styled")
     b, ih, iw, c = t.shape
@@ -227,12 +236,13 @@ def blur_styled(t, taps, pad, noise, noise_weight, bias, alpha, gain, scale2=Non
     out = torch.empty(b, oh, ow, c, dtype=torch.float32, device=t.device)
     out2 = torch.empty_like(out) if scale2 is not None else None
     nz, nbs = _noise_args(noise, oh, ow)
+    sm, sms = _map_args(stylemap, oh, ow)
     with torch.cuda.device(t.device):
-        rc = _lib.lib().sr_blur_nhwc_styled2_f32(_lib.ptr(out), _lib.ptr(out2), _lib.ptr(scale2), _lib.ptr(t),
+        rc = _lib.lib().sr_blur_nhwc_styled3_f32(_lib.ptr(out), _lib.ptr(out2), _lib.ptr(scale2), _lib.ptr(t),
                                                  _lib.ptr(taps.contiguous()), b, ih, iw, c, pad[0], pad[1], _lib.ptr(nz), nbs,
                                                  _lib.ptr(noise_weight), _lib.ptr(bias), float(alpha), float(gain),
-                                                 _lib.stream_of(t))
-    _lib.check(rc, "sr_blur_nhwc_styled2_f32")
+                                                 _lib.ptr(sm), sms, _lib.stream_of(t))
+    _lib.check(rc, "sr_blur_nhwc_styled3_f32")
     return out if scale2 is None else (out, out2)
 
 
@@ -270,8 +280,9 @@ def scale_dot(a, other, scale, round_out, want_out=True):
 
 
 def bwd_prologue2(y, noise, noise_weight, bias, d, alpha, gain, want_e, gy=None, gxs=None, s_next=None, g_rgb=None,
-                  rgb_weight=None):
-    """Chained backward prologue (sr_styled_bwd_prologue2_f32) -> (ga, g_bias, g_noise_w, e, ds_next, d_rgb_weight)."""
+                  rgb_weight=None, stylemap=None):
+    """Chained backward prologue (sr_styled_bwd_prologue3_f32) -> (ga, g_bias, g_noise_w, e, ds_next, d_rgb_weight[, g_map]);
+    g_map [B,2,H,W] is appended when a stylemap is given."""
     _check_nhwc(y, "bwd_prologue2 y")
     b, h, w, c = y.shape
     dev = y.device
@@ -287,12 +298,17 @@ def bwd_prologue2(y, noise, noise_weight, bias, d, alpha, gain, want_e, gy=None,
             _check_nhwc(t_, "bwd_prologue2 gradient")
     if g_rgb is not None:
         assert g_rgb.is_contiguous() and g_rgb.shape == (b, h, w, 3) and rgb_weight.is_contiguous()
+    sm, sms = _map_args(stylemap, h, w)
+    g_map = torch.empty(b, 2, h, w, dtype=torch.float32, device=dev) if sm is not None else None
     with torch.cuda.device(dev):
-        rc = _lib.lib().sr_styled_bwd_prologue2_f32(
+        rc = _lib.lib().sr_styled_bwd_prologue3_f32(
             _lib.ptr(ga), _lib.ptr(g_bias), _lib.ptr(g_nw), _lib.ptr(e), _lib.ptr(ds_next), _lib.ptr(dwb), _lib.ptr(gy),
             _lib.ptr(gxs), _lib.ptr(s_next), _lib.ptr(g_rgb), _lib.ptr(rgb_weight), _lib.ptr(y), _lib.ptr(nz), nbs,
-            _lib.ptr(noise_weight), _lib.ptr(bias), _lib.ptr(d), b, h * w, c, float(alpha), float(gain), _lib.stream_of(y))
-    _lib.check(rc, "sr_styled_bwd_prologue2_f32")
+            _lib.ptr(noise_weight), _lib.ptr(bias), _lib.ptr(d), b, h * w, c, float(alpha), float(gain), _lib.ptr(sm), sms,
+            _lib.ptr(g_map), _lib.stream_of(y))
+    _lib.check(rc, "sr_styled_bwd_prologue3_f32")
+    if sm is not None:
+        return ga, g_bias, g_nw, e, ds_next, dwb, g_map
     return ga, g_bias, g_nw, e, ds_next, dwb
 
 

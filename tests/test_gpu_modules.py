@@ -207,10 +207,12 @@ def test_styled_conv_function_exact_forward(up, shape):
         close(g_, w_.float(), name)
 
 
+@pytest.mark.parametrize("with_map", [False, True])
 @pytest.mark.parametrize("up", [False, True])
 @pytest.mark.parametrize("shape", [(2, 128, 128, 8), (1, 128, 256, 16)])
-def test_styled_layer_chain_exact_forward(up, shape):
-    """The chained block (pre-modulated input, second output for the next layer, fused ToRGB) against fp64 autograd."""
+def test_styled_layer_chain_exact_forward(up, shape, with_map):
+    """The chained block (pre-modulated input, second output for the next layer, fused ToRGB; with_map: the StyledMapConv
+    affine `t * map0 + map1` of reference model.py:50 and the gradients of both maps) against fp64 autograd."""
     import torch.nn.functional as F
     from stylerenderer_b200 import fused
     b, cin, cout, r = shape
@@ -224,7 +226,13 @@ def test_styled_layer_chain_exact_forward(up, shape):
     g_rgb = torch.randn(b, ro, ro, 3, generator=g)
     taps = torch.tensor([1., 3., 3., 1.])
     taps = (taps[None] * taps[:, None]) / 16
+    smap = None
+    if with_map:                                         # a channel slice of a wider map tensor, map0 away from zero
+        wide = torch.randn(b, 4, ro, ro, generator=g)
+        wide[:, 2] = wide[:, 2].abs() + 0.5
+        smap = wide[:, 2:]
     leaves = [t.double().requires_grad_(True) for t in ([xs, w, d, nw, bias, s_next] + ([wb] if wb is not None else []))]
+    smd = smap.double().requires_grad_(True) if with_map else None
     xd, wd, dd, nwd, bd, snd = leaves[:6]
     if up:
         t = F.conv_transpose2d(xd, (wd[0] * scale).transpose(0, 1), stride=2) * dd.view(b, cout, 1, 1)
@@ -232,24 +240,30 @@ def test_styled_layer_chain_exact_forward(up, shape):
                      taps.double().flip(0, 1).view(1, 1, 4, 4).repeat(b * cout, 1, 1, 1), groups=b * cout).view(b, cout, ro, ro)
     else:
         t = F.conv2d(xd, wd[0] * scale, padding=1) * dd.view(b, cout, 1, 1)
+    if with_map:
+        t = t * smd[:, :1] + smd[:, 1:2]
     y = F.leaky_relu(t + nwd * noise.double() + bd.view(1, -1, 1, 1), alpha) * gain
     main = y * snd.view(b, cout, 1, 1)
     loss = (main * gy.double()).sum()
     if wb is not None:
         rgb_ref = torch.einsum("bchw,bkc->bhwk", y, leaves[6])
         loss = loss + (rgb_ref * g_rgb.double()).sum()
-    want = torch.autograd.grad(loss, leaves)
+    want = torch.autograd.grad(loss, leaves + ([smd] if with_map else []))
     cu = [t.cuda().requires_grad_(True) for t in ([xs, w, d, nw, bias, s_next] + ([wb] if wb is not None else []))]
     xc = cu[0].detach().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    smc = None
+    if with_map:
+        smc = wide.cuda()[:, 2:].requires_grad_(True)   # non-contiguous batch stride (4 planes per image)
     got_main, got_rgb = fused.StyledLayerTC.apply(xc, cu[1], cu[2], noise.cuda(), cu[3], cu[4], cu[5],
-                                                  cu[6] if wb is not None else None, scale, up, taps.cuda(), alpha, gain)
+                                                  cu[6] if wb is not None else None, scale, up, taps.cuda(), alpha, gain,
+                                                  None, None, smc)
     close(got_main, main.detach().float(), "main (tf32-rounded)")
     lo = (got_main * gy.cuda()).sum()
     if wb is not None:
         close(got_rgb, rgb_ref.detach().float(), "rgb")
         lo = lo + (got_rgb * g_rgb.cuda()).sum()
-    got = torch.autograd.grad(lo, [xc] + cu[1:])
-    names = ["dxs", "dweight", "dd", "dnoise_w", "dbias", "ds_next", "drgb_weight"]
+    got = torch.autograd.grad(lo, [xc] + cu[1:] + ([smc] if with_map else []))
+    names = ["dxs", "dweight", "dd", "dnoise_w", "dbias", "ds_next"] + (["drgb_weight"] if wb is not None else []) + ["dstylemap"]
     for name, g_, w_ in zip(names, got, want):
         close(g_, w_.float(), name)
 
@@ -325,21 +339,42 @@ def test_modulated_conv_tcgen05_exact_forward(up):
 
 
 def test_generator_with_map_tcgen05_runs_and_matches():
-    """GeneratorWithMap with conv_backend=tcgen05 (StyledMapConv -> tensor-core ModulatedConv2d) vs the composed path."""
+    """GeneratorWithMap with conv_backend=tcgen05 (chained StyledMapConv blocks: style map in the conv epilogue / FIR tail,
+    map gradients from the backward prologue) vs the composed path in true fp32: image and every gradient, including
+    the ones that flow through the style maps into the rasterised normals (mesh vertices and normals)."""
     from stylerenderer_b200 import layers as L, model as M
     from make_golden import seeded, grid_mesh
     G = det_fill(M.GeneratorWithMap(32, 64, 2), 720).cuda().eval()
     v, tri = grid_mesh(24, 2, 721)
     tex = torch.nn.functional.normalize(seeded((2, 576, 3), 722), dim=-1)
     z = seeded((2, 64), 723).cuda()
-    mesh = (v.cuda(), tex.cuda(), tri.cuda())
-    img_a, _, _ = G([z], mesh, randomize_noise=False)
+    cot = seeded((2, 3, 32, 32), 724).cuda()
+
+    def run():
+        zz = z.clone().requires_grad_(True)
+        vv, tt = v.cuda().requires_grad_(True), tex.cuda().requires_grad_(True)
+        img, _, _ = G([zz], (vv, tt, tri.cuda()), randomize_noise=False)
+        ps = [p for _, p in sorted(G.named_parameters()) if p.requires_grad]
+        return img.detach(), torch.autograd.grad(img, [zz, vv, tt] + ps, cot, allow_unused=True)
+    img_a, gr_a = run()
     L.set_conv_backend("tcgen05")
     try:
-        img_b, _, _ = G([z], mesh, randomize_noise=False)
+        img_b, gr_b = run()
     finally:
         L.set_conv_backend("cudnn")
     close(img_b, img_a.detach().cpu(), "GAR image")
+    names = ["z", "verts", "tex"] + [n for n, p in sorted(G.named_parameters()) if p.requires_grad]
+    worst = 1.0
+    for n, a, bb in zip(names, gr_a, gr_b):
+        if a is None or float(a.abs().max()) == 0:
+            continue
+        assert bb is not None, n
+        a, bb = a.double().flatten(), bb.double().flatten()
+        c = float((a @ bb) / (a.norm() * bb.norm()))
+        worst = min(worst, c)
+        assert c > 0.99, f"{n}: cosine {c:.5f}"
+        assert abs(float(bb.norm() / a.norm()) - 1) < 5e-2, f"{n}: norm ratio {float(bb.norm() / a.norm()):.4f}"
+    print("worst gradient cosine (GeneratorWithMap, tcgen05 chain vs fp32 composed path):", worst)
 
 
 def test_generator_tcgen05_backend_matches_cudnn_backend():
