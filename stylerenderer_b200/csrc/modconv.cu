@@ -589,6 +589,7 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     uint64_t *tmem_empty_bar = tmem_full_bar + 2;      // [2], used in the leader only
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
     uint8_t *epi_stage = smem + STAGES * (A_BYTES + BH_BYTES) + 1024;  // 1024-byte aligned (swizzle), 8 KB per epilogue warp
+    float *vec_stage = reinterpret_cast<float *>(epi_stage + kEpiSmemBytes);   // [2][kVecKinds][BLOCK_N] (one-image tiles)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)(blockIdx.x & 1);            // __cluster_dims__(2,1,1)
@@ -680,8 +681,17 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
             ++lt;
             float rgb[3];
             long long rgb_index;
-            const bool valid = epilogue_tile<BLOCK_N>(p, out_maps, ph, tc, q, lane, tx, ty, tn, tmem_base + acc * BLOCK_N,
-                                                      &tmem_full_bar[acc], acc_par, my_stage, stage_sel, rgb, rgb_index);
+            bool valid;
+            if (p.tn_log2 == 0) {        // all rows of the tile belong to one image: per-tile vectors through shared memory
+                float *vb = vec_stage + (acc & 1) * (kVecKinds * BLOCK_N);     // (ncu: the rowscale loads were the epilogue's stall)
+                stage_tile_vectors<BLOCK_N, 128>(p, tc, vb, (int)threadIdx.x - 64);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                valid = epilogue_tile<BLOCK_N, true>(p, out_maps, ph, tc, q, lane, tx, ty, tn, tmem_base + acc * BLOCK_N,
+                                                     &tmem_full_bar[acc], acc_par, my_stage, stage_sel, rgb, rgb_index, vb);
+            } else {
+                valid = epilogue_tile<BLOCK_N>(p, out_maps, ph, tc, q, lane, tx, ty, tn, tmem_base + acc * BLOCK_N,
+                                               &tmem_full_bar[acc], acc_par, my_stage, stage_sel, rgb, rgb_index);
+            }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
@@ -1273,7 +1283,9 @@ template <int BLOCK_N, int STAGES>
 int launch_conv_2cta(const CUtensorMap &ta, const CUtensorMap &tb, const ConvOutMaps &om, const ConvKParams &p, cudaStream_t st)
 {
     constexpr int BH_BYTES = (BLOCK_N / 2) * BLOCK_K * 4;
-    const size_t smem = 1024 + (size_t)STAGES * (A_BYTES + BH_BYTES) + 1024 + kEpiSmemBytes;
+    const size_t smem = 1024 + (size_t)STAGES * (A_BYTES + BH_BYTES) + 1024 + kEpiSmemBytes + 2 * kVecKinds * BLOCK_N * sizeof(float);
+    static_assert(1024 + STAGES * (A_BYTES + BH_BYTES) + 1024 + kEpiSmemBytes + 2 * kVecKinds * BLOCK_N * 4 <= 232448,
+                  "CTA-pair conv kernel: shared memory budget");
     auto kern = conv_igemm_tf32_2cta_kernel<BLOCK_N, STAGES>;
     static bool configured = false;
     if (!configured) {
@@ -1587,8 +1599,8 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
         else rc = epi8 ? launch_conv_halo<128, 2, 4, 3, 8>(am, tb, om, p, hp, st)
                        : launch_conv_halo<128, 3, 4, 3, 4>(am, tb, om, p, hp, st);
     } else if (use_2cta) {
-        if (block_n == 256) rc = launch_conv_2cta<256, 6>(ta, tb, om, p, st);
-        else rc = launch_conv_2cta<128, 8>(ta, tb, om, p, st);
+        if (block_n == 256) rc = launch_conv_2cta<256, 5>(ta, tb, om, p, st);
+        else rc = launch_conv_2cta<128, 7>(ta, tb, om, p, st);
     } else if (block_n == 256) rc = launch_conv<256, 4>(ta, tb, om, p, st);
     else rc = launch_conv<128, 6>(ta, tb, om, p, st);
     if (rc != SR_OK) return rc;
