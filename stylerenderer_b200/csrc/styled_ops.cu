@@ -61,7 +61,8 @@ struct PrologueParams {
     float *g_map;                 // [B, 2, pixels] contiguous, += (zeroed by the caller)
 };
 
-// grid.x = B * chunks_per_image
+// grid.x = B * chunks_per_image.  MAP = StyledMapConv variant (compile-time: the plain path keeps its register budget)
+template <bool MAP>
 __global__ void __launch_bounds__(kThreads)
 styled_bwd_prologue_kernel(const PrologueParams p)
 {
@@ -109,8 +110,8 @@ styled_bwd_prologue_kernel(const PrologueParams p)
 #pragma unroll
             for (int k = 0; k < 3; ++k) gk2[u][k] = grgb ? __ldg(grgb + pp * 3 + k) : 0.0f;
             n2[u] = nz ? __ldg(nz + pp) : 0.0f;
-            m02[u] = p.stylemap ? __ldg(p.stylemap + (long long)b * p.map_bstride + pp) : 1.0f;
-            m12[u] = p.stylemap ? __ldg(p.stylemap + (long long)b * p.map_bstride + p.pixels + pp) : 0.0f;
+            m02[u] = MAP ? __ldg(p.stylemap + (long long)b * p.map_bstride + pp) : 1.0f;
+            m12[u] = MAP ? __ldg(p.stylemap + (long long)b * p.map_bstride + p.pixels + pp) : 0.0f;
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -134,15 +135,15 @@ styled_bwd_prologue_kernel(const PrologueParams p)
             gp.z = ((yy.z > 0.f) ? g.z : g.z * p.alpha) * p.gain; gp.w = ((yy.w > 0.f) ? g.w : g.w * p.alpha) * p.gain;
             f4_add(a_bias, gp);
             a_nw += ((gp.x + gp.y) + (gp.z + gp.w)) * n;
-            if (p.e || p.stylemap) {
+            if (p.e || MAP) {
                 // the pre-activation is recoverable from y (gain, alpha > 0): t = y / gain or y / (gain * alpha)
                 uu.x = yy.x * ((yy.x > 0.f) ? ipos : ineg); uu.y = yy.y * ((yy.y > 0.f) ? ipos : ineg);
                 uu.z = yy.z * ((yy.z > 0.f) ? ipos : ineg); uu.w = yy.w * ((yy.w > 0.f) ? ipos : ineg);
-                const float sh = nw * n + m12[u];
+                const float sh = MAP ? nw * n + m12[u] : nw * n;
                 uu.x -= sh + bias.x; uu.y -= sh + bias.y; uu.z -= sh + bias.z; uu.w -= sh + bias.w;
                 if (p.e) f4_fma(a_e, gp, uu);
             }
-            if (p.stylemap) {
+            if (MAP) {
                 // per-pixel reductions over the channels: the C4 threads of a pixel are consecutive (whole warps when
                 // C4 >= 32, aligned sub-warp groups when C4 is a smaller power of two)
                 float s1 = (gp.x + gp.y) + (gp.z + gp.w);
@@ -277,7 +278,8 @@ extern "C" int sr_styled_bwd_prologue3_f32(float *ga, float *g_bias, float *g_no
     p.chunks_per_image = pick_chunks(batch, pixels, p.C4, &p.pix_per_chunk);
     p.alpha = alpha; p.gain = gain;
     p.stylemap = stylemap; p.map_bstride = stylemap_batch_stride; p.g_map = g_stylemap;
-    styled_bwd_prologue_kernel<<<(unsigned)(batch * p.chunks_per_image), kThreads, 0, st>>>(p);
+    if (stylemap) styled_bwd_prologue_kernel<true><<<(unsigned)(batch * p.chunks_per_image), kThreads, 0, st>>>(p);
+    else styled_bwd_prologue_kernel<false><<<(unsigned)(batch * p.chunks_per_image), kThreads, 0, st>>>(p);
     count_launch();
     return check_launch("sr_styled_bwd_prologue_f32");
 }

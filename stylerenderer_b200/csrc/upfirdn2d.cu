@@ -280,6 +280,186 @@ upfirdn2d_tile_kernel(float *__restrict__ out, const float *__restrict__ x, cons
     }
 }
 
+// ---- NCHW blur (up = down = 1, 4x4 taps) straight from global memory, no shared-memory staging ------------------------
+// The tile kernel above stages its input with 4-byte cp.async because the rows of a (2H+1)-wide plane are not 16-byte
+// aligned -- one copy instruction plus address arithmetic per input element, which is what bounds it (ncu: sm 75 %,
+// DRAM 32 %).  Here a thread owns 4 output columns x RY rows and reads, per input row, the THREE aligned 16-byte quads
+// that cover the 7 floats it needs from the flat [major*H*W] array (consecutive lanes -> consecutive quads: every load
+// instruction of a warp is one contiguous 512-byte run, neighbouring lanes' quads overlap in L1).  The position of the
+// 7 floats inside the 12 loaded ones is the row's alignment phase (address mod 4), the same for every lane of a warp, so
+// the FIR body is instantiated for the four phases and selected by a warp-uniform switch.  Rows stream through a 4-deep
+// ring of open output rows; rank-1 taps use the separable form (8 FMAs per output).
+constexpr int BR_RY = 16;                 // output rows per thread
+
+struct RowsGeom {
+    int in_h, in_w, out_h, out_w, pad_x0, pad_y0, txs, tys, bands;
+    int64_t major, total;                 // total floats of the input
+    FastDiv div_bands;
+};
+
+__device__ __forceinline__ float4 br_load_quad(const float *__restrict__ x, int64_t q, int64_t total) {
+    if (q >= 0 && q + 4 <= total) return __ldg(reinterpret_cast<const float4 *>(x + q));
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = (q + i >= 0 && q + i < total) ? __ldg(x + q + i) : 0.0f;
+    return make_float4(v[0], v[1], v[2], v[3]);
+}
+
+template <int P>
+__device__ __forceinline__ void br_row(const float (&f)[12], int c0, int in_w, bool edge, bool sep, const float (&kh)[4],
+                                       const float (&kv)[4], const float (&tk)[4][4], float (&acc)[4][4], int ir)
+{
+    float u[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) u[i] = f[P + i];
+    if (edge) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+            if (c0 + i < 0 || c0 + i >= in_w) u[i] = 0.0f;
+    }
+    if (sep) {
+        float h[4];
+#pragma unroll
+        for (int vx = 0; vx < 4; ++vx) {
+            float t = 0.0f;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) t = fmaf(u[vx + b], kh[b], t);
+            h[vx] = t;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int slot = (ir - a) & 3;                      // ring slot of output row ir - a (rows outside the strip are
+#pragma unroll                                                  // never stored, their slots are reset before reuse)
+            for (int vx = 0; vx < 4; ++vx) acc[slot][vx] = fmaf(h[vx], kv[a], acc[slot][vx]);
+        }
+    } else {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int slot = (ir - a) & 3;
+#pragma unroll
+            for (int vx = 0; vx < 4; ++vx)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[slot][vx] = fmaf(u[vx + b], tk[a][b], acc[slot][vx]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+upfirdn2d_blur_rows_kernel(float *__restrict__ out, const float *__restrict__ x, const float *__restrict__ taps,
+                           const RowsGeom g)
+{
+    uint32_t band, plane;
+    g.div_bands.divmod(blockIdx.x, plane, band);
+    const int sx = threadIdx.x % g.txs, sy = threadIdx.x / g.txs;
+    const int ox = sx * 4, oy0 = (band * g.tys + sy) * BR_RY;
+    if (ox >= g.out_w || oy0 >= g.out_h) return;
+
+    float tk[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) tk[a][b] = __ldg(taps + (3 - a) * 4 + (3 - b));
+    // rank-1 factorisation tk[a][b] = kv[a] * kh[b] through the largest tap (see upfirdn2d_tile_kernel)
+    int pa = 0, pb = 0;
+    float best = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (fabsf(tk[a][b]) > best) { best = fabsf(tk[a][b]); pa = a; pb = b; }
+    float kv[4], kh[4], pivot = 1.0f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (a == pa && b == pb) pivot = tk[a][b];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        kv[a] = 0.0f; kh[a] = 0.0f;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (b == pb) kv[a] = tk[a][b];
+            if (b == pa) kh[a] = tk[b][a] / pivot;
+        }
+    }
+    bool sep = best > 0.0f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) sep = sep && fabsf(kv[a] * kh[b] - tk[a][b]) <= 1e-6f * best;
+
+    const int c0 = ox - g.pad_x0;                               // first input column of this thread's window
+    const bool edge = c0 < 0 || c0 + 6 >= g.in_w;
+    const int64_t plane_base = (int64_t)plane * g.in_h * g.in_w;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int vx = 0; vx < 4; ++vx) acc[a][vx] = 0.0f;
+    const int rows = min(BR_RY, g.out_h - oy0);
+#pragma unroll 1
+    for (int ir = 0; ir < rows + 3; ++ir) {
+        const int iy = oy0 - g.pad_y0 + ir;
+        if (iy >= 0 && iy < g.in_h) {                           // rows of the vertical padding contribute nothing
+            const int64_t A = plane_base + (int64_t)iy * g.in_w + c0;
+            const int64_t Q = A & ~(int64_t)3;
+            const int phase = (int)(A - Q);
+            float f[12];
+#pragma unroll
+            for (int qd = 0; qd < 3; ++qd) {
+                const float4 v = br_load_quad(x, Q + 4 * qd, g.total);
+                f[4 * qd] = v.x; f[4 * qd + 1] = v.y; f[4 * qd + 2] = v.z; f[4 * qd + 3] = v.w;
+            }
+            switch (phase) {
+                case 0: br_row<0>(f, c0, g.in_w, edge, sep, kh, kv, tk, acc, ir); break;
+                case 1: br_row<1>(f, c0, g.in_w, edge, sep, kh, kv, tk, acc, ir); break;
+                case 2: br_row<2>(f, c0, g.in_w, edge, sep, kh, kv, tk, acc, ir); break;
+                default: br_row<3>(f, c0, g.in_w, edge, sep, kh, kv, tk, acc, ir); break;
+            }
+        }
+        const int done = ir - 3;                                // output row completed by this input row
+        if (done >= 0) {
+            const int slot = done & 3;
+            float *dst = out + ((int64_t)plane * g.out_h + oy0 + done) * (int64_t)g.out_w + ox;
+            if (ox + 4 <= g.out_w && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+                *reinterpret_cast<float4 *>(dst) = make_float4(acc[slot][0], acc[slot][1], acc[slot][2], acc[slot][3]);
+            } else {
+#pragma unroll
+                for (int vx = 0; vx < 4; ++vx)
+                    if (ox + vx < g.out_w) dst[vx] = acc[slot][vx];
+            }
+        }
+        // the slot of output row ir + 1 (first touched by the next input row) must start from zero
+#pragma unroll
+        for (int vx = 0; vx < 4; ++vx) acc[(ir + 1) & 3][vx] = 0.0f;
+    }
+}
+
+int launch_blur_rows(float *out, const float *x, const float *taps, int64_t major, int in_h, int in_w, int oh, int ow,
+                     int pad_x0, int pad_y0, cudaStream_t st)
+{
+    // Opt-in (SR_UPFIRDN_ROWS=1): measured SLOWER than the shared-memory strip kernel (blur 257^2 -> 256^2: 0.90 vs
+    // 0.81 ms; its backward 256^2 -> 257^2: 1.50 vs 1.02 ms, profiles/r1_kernel_bench_strip.jsonl) -- the three
+    // overlapping quads per thread and row cost more L1 bandwidth than the 4-byte staging costs issue slots.
+    static const char *on = getenv("SR_UPFIRDN_ROWS");
+    if (!(on && on[0] == '1')) return SR_ERR_UNSUPPORTED;
+    if (ow < 128 || pad_x0 < 0 || pad_x0 > 3 || pad_y0 < 0 || pad_y0 > 3 || (reinterpret_cast<uintptr_t>(x) & 15u))
+        return SR_ERR_UNSUPPORTED;
+    RowsGeom g;
+    g.in_h = in_h; g.in_w = in_w; g.out_h = oh; g.out_w = ow; g.pad_x0 = pad_x0; g.pad_y0 = pad_y0;
+    g.major = major; g.total = major * in_h * in_w;
+    int txs = 32;
+    while (txs * 4 < ow && txs < kThreads) txs <<= 1;           // threads across a row: 32, 64, 128 or 256
+    if (txs * 4 < ow) return SR_ERR_UNSUPPORTED;                // rows wider than 1024 outputs: tile kernel
+    g.txs = txs; g.tys = kThreads / txs;
+    g.bands = (oh + g.tys * BR_RY - 1) / (g.tys * BR_RY);
+    g.div_bands = FastDiv((uint32_t)g.bands);
+    const int64_t blocks = major * g.bands;
+    if (blocks >= 0x7fffffffll) return SR_ERR_UNSUPPORTED;
+    upfirdn2d_blur_rows_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
+    return SR_OK;
+}
+
 // ---- channels-last (NHWC, minor = C) FIR, up = down = 1: the layout of the tcgen05 conv pipeline ---------
 // One thread = 4 channels (float4) x 2 adjacent output columns x a strip of RY output rows.  Consecutive lanes
 // take consecutive channel quads, so every load/store instruction of a warp is one contiguous 512-byte run;
@@ -887,7 +1067,10 @@ extern "C" int sr_upfirdn2d_f32(float *out, const float *x, const float *taps,
 #define SR_TILE(UP, DOWN, PHX, PHY, VY) \
     rc = launch_tile<UP, DOWN, 4, 4, PHX, PHY, VY>(out, x, taps, major, (int)in_h, (int)in_w, (int)oh, (int)ow, \
                                                    pad_x0, pad_y0, st)
-        if (up_x == 1 && down_x == 1) {
+        if (up_x == 1 && down_x == 1 && pad_x0 == pad_y0 &&
+            launch_blur_rows(out, x, taps, major, (int)in_h, (int)in_w, (int)oh, (int)ow, pad_x0, pad_y0, st) == SR_OK) {
+            rc = SR_OK;
+        } else if (up_x == 1 && down_x == 1) {
             static const char *strip_env = getenv("SR_UPFIRDN_STRIP");      // A/B: 0 = 4x2 register patch (round-1 kernel)
             if (strip_env && strip_env[0] == '0') SR_TILE(1, 1, 0, 0, 2);
             else SR_TILE(1, 1, 0, 0, 8);

@@ -125,6 +125,9 @@ UPFIR_CASES = [
     (1, 2, 128, 128, 4, 4, 1, 2, 1, 1), (1, 2, 16, 16, 4, 4, 1, 2, 0, 3),
     (1, 2, 8, 8, 3, 3, 1, 1, 1, 1), (1, 2, 8, 9, 2, 2, 2, 1, 1, 0), (1, 2, 10, 10, 4, 4, 1, 1, -1, 2),
     (1, 2, 8, 8, 4, 4, 2, 2, 1, 2), (1, 2, 12, 12, 6, 6, 3, 2, 3, 2), (1, 1, 7, 5, 5, 3, 1, 1, 2, 2),
+    # wide rows: the direct-from-global blur kernel (aligned quads + phase select), general (non-separable) taps
+    (1, 2, 40, 300, 4, 4, 1, 1, 1, 1), (2, 1, 19, 131, 4, 4, 1, 1, 2, 2), (1, 1, 6, 1030, 4, 4, 1, 1, 1, 1),
+    (3, 2, 33, 257, 4, 4, 1, 1, 3, 3), (1, 1, 70, 129, 4, 4, 1, 1, 0, 0),
 ]
 
 
