@@ -126,23 +126,47 @@ class ModConvTC(Function):
 #   conv(x, w),  dgrad(g, w),  wgrad(g, x)
 # are autograd Functions whose backward passes are built from each other, exactly like torch's own convolution
 # double-backward; every one of them is one launch of the implicit-GEMM / wgrad kernels on tf32-rounded operands.
-# kind 'plain': 3x3, stride 1, pad 1;  kind 'up': stride-2 transposed 3x3 (reference layers.py:301-309), output (2H+1)^2.
+# kind 'plain': 3x3, stride 1, pad 1;  kind 'up': stride-2 transposed 3x3 (reference layers.py:301-309), output (2H+1)^2;
+# kinds 'down' / 'down1': 3x3 / 1x1, stride 2, pad 0 (the Discriminator's down-sampling ConvLayers after their Blur).
 def _conv_fwd(x, w, kind):
     xr, wk = tc.modulate(x), tc.weight_prep(w, 1.0, 0)
-    return tc.conv3x3(xr, wk) if kind == "plain" else tc.conv_transpose3x3_s2(xr, wk)
+    if kind == "plain":
+        return tc.conv3x3(xr, wk)
+    if kind == "up":
+        return tc.conv_transpose3x3_s2(xr, wk)
+    b, h, wd, _ = x.shape                                       # 'down' (3x3 s2 p0) / 'down1' (1x1 s2 p0)
+    k = w.shape[2]
+    y = torch.empty(b, (h - k) // 2 + 1, (wd - k) // 2 + 1, w.shape[0], dtype=torch.float32, device=x.device)
+    return tc.conv_igemm(xr, wk, TAPS_S2 if k == 3 else [(0, 0, 0)], y, in_stride=2)
 
 
 def _conv_dgrad(g, w, kind, hw):
     gr = tc.modulate(g)
     if kind == "plain":
         return tc.conv3x3(gr, tc.weight_prep(w, 1.0, 1))
-    return tc.conv3x3_s2_gather(gr, tc.weight_prep(w, 1.0, 2), hw)
+    if kind == "up":
+        return tc.conv3x3_s2_gather(gr, tc.weight_prep(w, 1.0, 2), hw)
+    wt = tc.weight_prep(w, 1.0, 2)
+    if kind == "down":
+        assert hw == (2 * g.shape[1] + 1, 2 * g.shape[2] + 1)
+        return tc.conv_transpose3x3_s2(gr, wt)
+    dx = torch.zeros(g.shape[0], hw[0], hw[1], w.shape[1], dtype=torch.float32, device=g.device)
+    return tc.conv_igemm_multi(gr, wt, [([(0, 0, 0)], (g.shape[1], g.shape[2]), (0, 0))], dx, out_stride=2)
 
 
-def _conv_wgrad(g, x, kind):
+def _conv_wgrad(g, x, kind, k=3):
     gr, xr = tc.modulate(g), tc.modulate(x)
-    dwk = tc.wgrad3x3(gr, xr) if kind == "plain" else tc.wgrad_transpose3x3_s2(gr, xr)
-    return style.weight_grad_layout(dwk, 1.0, g.shape[3], x.shape[3], 3)[0]
+    if kind == "plain":
+        dwk = tc.wgrad3x3(gr, xr)
+    elif kind == "up":
+        dwk = tc.wgrad_transpose3x3_s2(gr, xr)
+    elif kind == "down":
+        dwk = tc.wgrad(gr, xr, [(0, 0, ky, kx, ky * 3 + kx) for ky in range(3) for kx in range(3)], (g.shape[1], g.shape[2]),
+                       x_stride=2)
+    else:
+        dwk = tc.wgrad(gr, xr, [(0, 0, 0, 0, 0)], (g.shape[1], g.shape[2]), x_stride=2, taps_total=1)
+        k = 1
+    return style.weight_grad_layout(dwk, 1.0, g.shape[3], x.shape[3], k)[0]
 
 
 class ConvTC(Function):
@@ -200,6 +224,20 @@ class ConvWgradTC(Function):
         d_g = ConvTC.apply(x, ggw, ctx.kind) if ctx.needs_input_grad[0] else None
         d_x = ConvDgradTC.apply(g, ggw, ctx.kind, (x.shape[1], x.shape[2])) if ctx.needs_input_grad[1] else None
         return d_g, d_x, None
+
+
+_DD_KIND = {"s1": "plain", "s2": "down", "p2": "down1"}
+
+
+def plain_conv_dd(conv, act, x, kind):
+    """ConvLayer body for iterations that need double backward (R1, reference train.py:110-114): the contraction is the
+    twice-differentiable ConvTC, bias / activation are the (twice differentiable) fused_leaky_relu op."""
+    from .op import fused_leaky_relu
+    y = ConvTC.apply(x.permute(0, 2, 3, 1).contiguous(), conv.weight * conv.scale, _DD_KIND[kind]).permute(0, 3, 1, 2)
+    if act is None:
+        return y
+    bias = act.bias if conv.bias is None else act.bias + conv.bias
+    return fused_leaky_relu(y, bias, act.negative_slope, act.scale)
 
 
 def mod_conv_dd(mod, x, style):

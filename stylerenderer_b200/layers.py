@@ -280,10 +280,11 @@ class ConvLayer(nn.Sequential):                       # reference layers.py:341-
         super().__init__(*layers)
 
     def forward(self, input):
-        # tensor-core path (conv_backend "tcgen05", first-order gradients): [Blur ->] EqualConv2d [+ FusedLeakyReLU] with the
-        # bias / activation in the conv epilogue; anything else (3-channel stems, SpectralNorm-free odd shapes, R1 / path
-        # regulariser iterations under double_backward()) takes the composed cuDNN path below, like the reference
-        if _CONFIG["conv_backend"] == "tcgen05" and not (torch.is_grad_enabled() and _CONFIG["double_backward"]):
+        # tensor-core path (conv_backend "tcgen05"): [Blur ->] EqualConv2d [+ FusedLeakyReLU] with the bias / activation in
+        # the conv epilogue, or -- on R1 / path regulariser iterations under double_backward() -- the twice-differentiable
+        # ConvTC + fused_leaky_relu; anything else (3-channel stems, odd shapes) takes the composed cuDNN path below
+        if _CONFIG["conv_backend"] == "tcgen05":
+            dd = torch.is_grad_enabled() and _CONFIG["double_backward"]
             mods = list(self)
             blur = mods[0] if isinstance(mods[0], Blur) else None
             rest = mods[1:] if blur is not None else mods
@@ -294,7 +295,7 @@ class ConvLayer(nn.Sequential):                       # reference layers.py:341-
                 x = blur(input) if blur is not None else input
                 kind = fused.plain_conv_supported(conv, x)
                 if kind is not None:
-                    return fused.plain_conv(conv, act, x, kind)
+                    return fused.plain_conv_dd(conv, act, x, kind) if dd else fused.plain_conv(conv, act, x, kind)
                 input, start = x, (1 if blur is not None else 0)
                 for m in mods[start:]:
                     input = m(input)

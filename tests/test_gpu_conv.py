@@ -191,14 +191,16 @@ def test_plain_conv_layer_tc(kind, shape):
         assert relerr(grads[2], wg[2]) < 1e-4, (kind, "dbias")
 
 
-@pytest.mark.parametrize("kind,shape", [("plain", (2, 128, 128, 12, 20)), ("up", (2, 128, 256, 9, 7))])
+@pytest.mark.parametrize("kind,shape", [("plain", (2, 128, 128, 12, 20)), ("up", (2, 128, 256, 9, 7)),
+                                        ("down", (2, 128, 128, 17, 13)), ("down1", (2, 256, 128, 15, 9))])
 def test_conv_tc_double_backward(kind, shape):
     """ConvTC / ConvDgradTC / ConvWgradTC (the twice-differentiable tensor-core convolution used on R1 / path-length
     iterations): first and second order gradients against torch's float64 convolution double backward."""
     from stylerenderer_b200 import fused
     b, cin, cout, h, w = shape
     x = (seeded((b, h, w, cin), 61).cuda()).requires_grad_(True)
-    wt = (seeded((cout, cin, 3, 3), 62).cuda() * 0.05).requires_grad_(True)
+    k = 1 if kind == "down1" else 3
+    wt = (seeded((cout, cin, k, k), 62).cuda() * 0.05).requires_grad_(True)
     y = fused.ConvTC.apply(x, wt, kind)
     gy = seeded(tuple(y.shape), 63).cuda().requires_grad_(True)
     gx, gw = torch.autograd.grad(y, (x, wt), gy, create_graph=True)
@@ -209,7 +211,12 @@ def test_conv_tc_double_backward(kind, shape):
 
     x64, w64, g64 = (t.detach().double().requires_grad_(True) for t in (x, wt, gy))
     xn = x64.permute(0, 3, 1, 2)
-    yr = F.conv2d(xn, w64, padding=1) if kind == "plain" else F.conv_transpose2d(xn, w64.transpose(0, 1), stride=2)
+    if kind == "plain":
+        yr = F.conv2d(xn, w64, padding=1)
+    elif kind == "up":
+        yr = F.conv_transpose2d(xn, w64.transpose(0, 1), stride=2)
+    else:
+        yr = F.conv2d(xn, w64, stride=2)
     assert relerr(y.detach().permute(0, 3, 1, 2), yr.detach()) < 2e-3
     gxr, gwr = torch.autograd.grad(yr, (x64, w64), g64.permute(0, 3, 1, 2), create_graph=True)
     assert relerr(gx.detach(), gxr.detach()) < 2e-3 and relerr(gw.detach(), gwr.detach()) < 2e-3
