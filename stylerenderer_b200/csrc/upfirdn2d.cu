@@ -526,7 +526,7 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
     float4 sc2 = zero;
     if ((STYLED && g.out2) || MODE == 2) sc2 = __ldg(reinterpret_cast<const float4 *>(g.scale2) + (int64_t)n * g.c4 + c);
     float4 dot = zero;
-    const float4 *oth = (MODE == 2) ? reinterpret_cast<const float4 *>(g.other) + (int64_t)n * g.out_h * g.out_w * g.c4 + c : nullptr;
+    const float4 *oth = (MODE == 2 && g.other) ? reinterpret_cast<const float4 *>(g.other) + (int64_t)n * g.out_h * g.out_w * g.c4 + c : nullptr;
 
     float4 win[KH][KW + 1];
     auto load_row = [&](float4 (&row)[KW + 1], int iy) {
@@ -543,7 +543,7 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
     for (int oy = oy0; oy < oy1; ++oy) {
         load_row(win[KH - 1], oy - g.pad_y0 + KH - 1);
         float4 tt[2] = {zero, zero};
-        if (MODE == 2) {                               // issue the loads of the dot operand before the FMA block
+        if (MODE == 2 && oth) {                        // issue the loads of the dot operand before the FMA block
 #pragma unroll
             for (int j = 0; j < 2; ++j)
                 if (ox0 + j < g.out_w) tt[j] = __ldg(oth + ((int64_t)oy * g.out_w + ox0 + j) * g.c4);
@@ -609,7 +609,7 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
 #pragma unroll
             for (int b = 0; b < KW + 1; ++b) win[a][b] = win[a + 1][b];
     }
-    if (MODE == 2) {        // one 128-bit reduction per thread into dot[n, 4c .. 4c+3]
+    if (MODE == 2 && g.dot) {   // one 128-bit reduction per thread into dot[n, 4c .. 4c+3]
         float *dp = g.dot + ((int64_t)n * g.c4 + c) * 4;
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dp), "f"(dot.x), "f"(dot.y), "f"(dot.z), "f"(dot.w) : "memory");
     }
@@ -953,7 +953,8 @@ int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, in
                 const float *stylemap = nullptr, long long map_bstride = 0)
 {
     if (pad_x0 == pad_y0 && !stylemap) {
-        const int rc = launch_nhwc_tma(out, x, taps, major, in_h, in_w, oh, ow, minor, pad_x0, dot ? 2 : (styled ? 1 : 0), noise,
+        const int rc = (!dot && !styled && scale2) ? SR_ERR_UNSUPPORTED :
+                       launch_nhwc_tma(out, x, taps, major, in_h, in_w, oh, ow, minor, pad_x0, dot ? 2 : (styled ? 1 : 0), noise,
                                        noise_bstride, noise_weight, bias, alpha, gain, st, out2, scale2, other, dot);
         if (rc == SR_OK) return rc;
     }
@@ -971,7 +972,7 @@ int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, in
     g.alpha = alpha; g.gain = gain;
     if (g.total_threads >= 0x7fffffffll) return SR_ERR_UNSUPPORTED;
     const int64_t blocks = (g.total_threads + kThreads - 1) / kThreads;
-    if (dot) upfirdn2d_nhwc_kernel<4, 4, 2><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
+    if (dot || (!styled && scale2)) upfirdn2d_nhwc_kernel<4, 4, 2><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
     else if (styled) upfirdn2d_nhwc_kernel<4, 4, 1><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
     else upfirdn2d_nhwc_kernel<4, 4, 0><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
     return SR_OK;
@@ -1019,15 +1020,18 @@ extern "C" int sr_blur_nhwc_scaledot_f32(float *out, float *dot, const float *x,
                                          const float *other, int64_t batch, int64_t in_h, int64_t in_w, int64_t channels,
                                          int pad0, int pad1, void *stream)
 {
-    SR_REQUIRE(out && dot && x && taps && scale && other, "blur_nhwc_scaledot: null pointer");
+    SR_REQUIRE(out && x && taps && scale, "blur_nhwc_scaledot: null pointer");
+    SR_REQUIRE((dot == nullptr) == (other == nullptr), "blur_nhwc_scaledot: dot and other go together (both NULL = scale only)");
     SR_REQUIRE(channels >= 4 && channels % 4 == 0, "blur_nhwc_scaledot: channels must be a multiple of 4");
     SR_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dot) |
                  reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(other)) & 15u) == 0,
                "blur_nhwc_scaledot: 16-byte alignment");
     const int64_t oh = in_h + pad0 + pad1 - 4 + 1, ow = in_w + pad0 + pad1 - 4 + 1;
     SR_REQUIRE(oh >= 1 && ow >= 1, "blur_nhwc_scaledot: FIR larger than the padded input");
-    cudaError_t er = cudaMemsetAsync(dot, 0, sizeof(float) * (size_t)(batch * channels), (cudaStream_t)stream);
-    if (er != cudaSuccess) { set_error("blur_nhwc_scaledot: memset: %s", cudaGetErrorString(er)); return (int)er; }
+    if (dot) {
+        cudaError_t er = cudaMemsetAsync(dot, 0, sizeof(float) * (size_t)(batch * channels), (cudaStream_t)stream);
+        if (er != cudaSuccess) { set_error("blur_nhwc_scaledot: memset: %s", cudaGetErrorString(er)); return (int)er; }
+    }
     if (batch == 0) return SR_OK;
     int rc = launch_nhwc(out, x, taps, batch, (int)in_h, (int)in_w, (int)oh, (int)ow, channels, pad0, pad0, false, nullptr, 0,
                          nullptr, nullptr, 0.f, 1.f, (cudaStream_t)stream, nullptr, scale, other, dot);

@@ -415,7 +415,7 @@ class StyledLayerTC(Function):
                                        stylemap=stylemap)
             else:
                 y = tc.blur_styled(t, blur_taps, (1, 1), noise, noise_weight, act_bias, alpha, gain, stylemap=stylemap)
-        ctx.save_for_backward(xs_nhwc, y, t, weight, d, noise, noise_weight, act_bias, blur_taps, s_next, rgb_weight, stylemap)
+        ctx.save_for_backward(xs_nhwc, y, None, weight, d, noise, noise_weight, act_bias, blur_taps, s_next, rgb_weight, stylemap)
         ctx.cfg = (scale, upsample, alpha, gain)
         main = from_nhwc(y2 if s_next is not None else y)
         if rgb is None:
@@ -447,10 +447,12 @@ class StyledLayerTC(Function):
             dxs = tc.conv3x3(ga, ctx.wkt if ctx.wkt is not None else tc.weight_prep(weight[0], scale, 1))
             dwk = tc.wgrad3x3(ga, xs)
         else:
-            res = tc.bwd_prologue2(y, noise, noise_weight, act_bias, None, alpha, gain, False, stylemap=stylemap, **src)
-            g_pre, g_bias, g_noise_w, _, ds_next, dwb = res[:6]
+            # e = sum_p gp * (fir(t) * map0) comes from the prologue (fir(t) * map0 is recoverable from y, like the plain
+            # block's conv output), so the FIR^T pass does not have to read the saved transposed-conv output t again
+            res = tc.bwd_prologue2(y, noise, noise_weight, act_bias, None, alpha, gain, True, stylemap=stylemap, **src)
+            g_pre, g_bias, g_noise_w, e, ds_next, dwb = res[:6]
             g_map = res[6] if stylemap is not None else None
-            ga, e = tc.blur_scaledot(g_pre, torch.flip(blur_taps, [0, 1]), (2, 2), d, t)   # FIR^T, * d, tf32, sum gt * t
+            ga, _ = tc.blur_scaledot(g_pre, torch.flip(blur_taps, [0, 1]), (2, 2), d)       # FIR^T, * d, tf32
             dxs = tc.conv3x3_s2_gather(ga, ctx.wkt if ctx.wkt is not None else tc.weight_prep(weight[0], scale, 2), (h, w))
             dwk = tc.wgrad_transpose3x3_s2(ga, xs)
         g_d = e / d

@@ -312,14 +312,15 @@ def bwd_prologue2(y, noise, noise_weight, bias, d, alpha, gain, want_e, gy=None,
     return ga, g_bias, g_nw, e, ds_next, dwb
 
 
-def blur_scaledot(x, taps, pad, scale, other):
-    """(tf32(fir(x) * scale[b,c]), dot[b,c] = sum_p fir(x) * other): the up-sampling block's backward FIR with its tail."""
+def blur_scaledot(x, taps, pad, scale, other=None):
+    """(tf32(fir(x) * scale[b,c]), dot[b,c] = sum_p fir(x) * other): the up-sampling block's backward FIR with its tail.
+    other = None: scale only (dot is None) -- the block gets its demodulation gradient from the prologue instead."""
     _check_nhwc(x, "blur_scaledot")
     b, ih, iw, c = x.shape
     oh, ow = ih + pad[0] + pad[1] - 3, iw + pad[0] + pad[1] - 3
-    assert other.shape == (b, oh, ow, c) and other.is_contiguous()
+    assert other is None or (other.shape == (b, oh, ow, c) and other.is_contiguous())
     out = torch.empty(b, oh, ow, c, dtype=torch.float32, device=x.device)
-    dot = torch.empty(b, c, dtype=torch.float32, device=x.device)
+    dot = torch.empty(b, c, dtype=torch.float32, device=x.device) if other is not None else None
     with torch.cuda.device(x.device):
         rc = _lib.lib().sr_blur_nhwc_scaledot_f32(_lib.ptr(out), _lib.ptr(dot), _lib.ptr(x), _lib.ptr(taps.contiguous()),
                                                   _lib.ptr(scale.contiguous()), _lib.ptr(other), b, ih, iw, c, pad[0], pad[1],
