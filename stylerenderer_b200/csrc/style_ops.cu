@@ -75,14 +75,17 @@ style_rows_dot_kernel(const StyleTable tab, const float *__restrict__ latent, in
 }
 
 // ---- backward, per (layer, sample): du = -1/2 g_d d^3;  gs_total = g_s + 2 s (du @ Wsq) ------------------------------
+// A CTA owns 32 input channels (one per lane); its 8 warps split the sum over the output channels and combine through
+// shared memory (a thread-per-channel loop over all 512 outputs was a 0.12 ms latency chain per launch).
 __global__ void __launch_bounds__(256)
 style_bwd_gs_kernel(const StyleTable tab, int batch)
 {
     const sr_style_layer &L = tab.l[blockIdx.y];
-    const int i0 = blockIdx.x * 256;
+    const int i0 = blockIdx.x * 32;
     if (i0 >= L.cin) return;
     const int b0 = blockIdx.z * kSB;
     extern __shared__ float du_s[];                      // [kSB][cout]
+    __shared__ float part[8][kSB][32];
     const bool demod = L.wsq != nullptr && L.g_d != nullptr;
     if (demod) {
         for (int idx = threadIdx.x; idx < kSB * L.cout; idx += 256) {
@@ -96,26 +99,30 @@ style_bwd_gs_kernel(const StyleTable tab, int batch)
             }
             du_s[idx] = v;
         }
-        __syncthreads();
     }
-    const int i = i0 + threadIdx.x;
-    if (i >= L.cin) return;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = i0 + lane;
     float t[kSB];
 #pragma unroll
     for (int sb = 0; sb < kSB; ++sb) t[sb] = 0.0f;
-    if (demod) {
-        for (int o = 0; o < L.cout; ++o) {
+    if (demod && i < L.cin) {
+        for (int o = warp; o < L.cout; o += 8) {
             const float w = __ldg(L.wsq + (int64_t)o * L.cin + i);
 #pragma unroll
             for (int sb = 0; sb < kSB; ++sb) t[sb] = fmaf(du_s[sb * L.cout + o], w, t[sb]);
         }
     }
 #pragma unroll
-    for (int sb = 0; sb < kSB; ++sb) {
-        const int b = b0 + sb;
-        if (b >= batch) break;
+    for (int sb = 0; sb < kSB; ++sb) part[warp][sb][lane] = t[sb];
+    __syncthreads();
+    if (warp < kSB && i < L.cin && b0 + warp < batch) {      // warp sb finishes sample sb
+        float sum = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += part[w][warp][lane];
+        const int b = b0 + warp;
         const float gs = L.g_s ? __ldg(L.g_s + (int64_t)b * L.cin + i) : 0.0f;
-        L.gs_total[(int64_t)b * L.cin + i] = gs + 2.0f * L.s[(int64_t)b * L.cin + i] * t[sb];
+        L.gs_total[(int64_t)b * L.cin + i] = gs + 2.0f * L.s[(int64_t)b * L.cin + i] * sum;
     }
 }
 
@@ -178,32 +185,41 @@ style_bwd_outer_kernel(const StyleTable tab, const float *__restrict__ latent, i
 }
 
 // ---- g_latent[b, li, k] += scale * sum_i gs_total[b,i] * Wm[i,k] -------------------------------------------------------
+// Same shape of work: a CTA owns 32 latent components (one per lane), its 8 warps split the sum over the channels.
 __global__ void __launch_bounds__(256)
 style_bwd_latent_kernel(const StyleTable tab, float *__restrict__ g_latent, int batch, int n_latent, int style_dim,
                         float mod_scale)
 {
     const sr_style_layer &L = tab.l[blockIdx.y];
-    const int k = blockIdx.x * 256 + threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = blockIdx.x * 32 + lane;
     const int b0 = blockIdx.z * kSB;
     extern __shared__ float gs_s[];                      // [kSB][cin]
+    __shared__ float part[8][kSB][32];
     for (int idx = threadIdx.x; idx < kSB * L.cin; idx += 256) {
         const int sb = idx / L.cin, i = idx - sb * L.cin;
         gs_s[idx] = (b0 + sb < batch) ? L.gs_total[(int64_t)(b0 + sb) * L.cin + i] : 0.0f;
     }
     __syncthreads();
-    if (k >= style_dim) return;
     float acc[kSB];
 #pragma unroll
     for (int sb = 0; sb < kSB; ++sb) acc[sb] = 0.0f;
-    for (int i = 0; i < L.cin; ++i) {
-        const float w = __ldg(L.mod_weight + (int64_t)i * style_dim + k);
+    if (k < style_dim) {
+        for (int i = warp; i < L.cin; i += 8) {
+            const float w = __ldg(L.mod_weight + (int64_t)i * style_dim + k);
 #pragma unroll
-        for (int sb = 0; sb < kSB; ++sb) acc[sb] = fmaf(gs_s[sb * L.cin + i], w, acc[sb]);
+            for (int sb = 0; sb < kSB; ++sb) acc[sb] = fmaf(gs_s[sb * L.cin + i], w, acc[sb]);
+        }
     }
 #pragma unroll
-    for (int sb = 0; sb < kSB; ++sb)
-        if (b0 + sb < batch)
-            atomicAdd(g_latent + ((int64_t)(b0 + sb) * n_latent + L.latent_index) * style_dim + k, mod_scale * acc[sb]);
+    for (int sb = 0; sb < kSB; ++sb) part[warp][sb][lane] = acc[sb];
+    __syncthreads();
+    if (warp < kSB && k < style_dim && b0 + warp < batch) {
+        float sum = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += part[w][warp][lane];
+        atomicAdd(g_latent + ((int64_t)(b0 + warp) * n_latent + L.latent_index) * style_dim + k, mod_scale * sum);
+    }
 }
 
 // ---- Wsq[o,i] = scale^2 * sum_t W[o,i,t]^2 and its gradient  gW[o,i,t] = 2 scale^2 W[o,i,t] * gWsq[o,i] -----------------
@@ -220,21 +236,30 @@ weight_sq_kernel(float *__restrict__ wsq, const float *__restrict__ w, float sca
 
 __global__ void __launch_bounds__(256)
 weight_sq_backward_kernel(float *__restrict__ gw, const float *__restrict__ w, const float *__restrict__ g_wsq, float scale2,
-                          int64_t total, int taps)
+                          uint32_t total, FastDiv div_taps)
 {
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256)
-        gw[i] = 2.0f * scale2 * __ldg(w + i) * __ldg(g_wsq + i / taps);
+    // 32-bit indices and a multiply-shift division: the 64-bit `i / taps` of a naive version costs more than the memory traffic
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u)
+        gw[i] = 2.0f * scale2 * __ldg(w + i) * __ldg(g_wsq + div_taps.div(i));
 }
 
 // ---- gW[o,i,t] = scale * dwk[o,t,i]  (GEMM layout of the wgrad kernels -> reference layout) ----------------------------
+// One CTA per (o, block of 256 input channels): the [taps][256] slab is read with coalesced rows, transposed through shared
+// memory and written as one contiguous run of 256 * taps floats.
+constexpr int kGL = 256;
 __global__ void __launch_bounds__(256)
 weight_grad_layout_kernel(float *__restrict__ gw, const float *__restrict__ dwk, float scale, int cout, int cin, int taps)
 {
-    const int64_t pairs = (int64_t)cout * cin;
-    for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < pairs; p += (int64_t)gridDim.x * 256) {
-        const int64_t o = p / cin, i = p - o * cin;
-        float *dst = gw + p * taps;
-        for (int t = 0; t < taps; ++t) dst[t] = scale * __ldg(dwk + (o * taps + t) * cin + i);
+    extern __shared__ float slab[];                       // [taps][kGL + 1]
+    const int o = blockIdx.y, i0 = blockIdx.x * kGL;
+    const int n = min(kGL, cin - i0);
+    for (int t = 0; t < taps; ++t)
+        if ((int)threadIdx.x < n) slab[t * (kGL + 1) + threadIdx.x] = __ldg(dwk + ((int64_t)o * taps + t) * cin + i0 + threadIdx.x);
+    __syncthreads();
+    float *dst = gw + ((int64_t)o * cin + i0) * taps;
+    for (int idx = threadIdx.x; idx < n * taps; idx += 256) {
+        const int i = idx / taps, t = idx - i * taps;
+        dst[idx] = scale * slab[t * (kGL + 1) + i];
     }
 }
 
@@ -304,14 +329,14 @@ extern "C" int sr_style_scales_backward_f32(const sr_style_layer *layers, int n_
     cudaError_t e = cudaMemsetAsync(g_latent, 0, sizeof(float) * (size_t)(batch * n_latent * style_dim), st);
     if (e != cudaSuccess) { set_error("style_scales_backward: memset: %s", cudaGetErrorString(e)); return (int)e; }
     const unsigned gz = (unsigned)((batch + kSB - 1) / kSB);
-    style_bwd_gs_kernel<<<dim3((max_cin + 255) / 256, n_layers, gz), 256, kSB * (max_cout > 0 ? max_cout : 1) * sizeof(float), st>>>(
+    style_bwd_gs_kernel<<<dim3((max_cin + 31) / 32, n_layers, gz), 256, kSB * (max_cout > 0 ? max_cout : 1) * sizeof(float), st>>>(
         tab, (int)batch);
     if (max_cout > 0)
         style_bwd_outer_kernel<0><<<dim3((max_cin + 255) / 256, n_layers, (max_cout + 15) / 16), 256, 0, st>>>(
             tab, latent, (int)batch, (int)n_latent, (int)style_dim, mod_scale, lr_mul);
     style_bwd_outer_kernel<1><<<dim3((unsigned)((style_dim + 255) / 256), n_layers, (max_cin + 15) / 16), 256, 0, st>>>(
         tab, latent, (int)batch, (int)n_latent, (int)style_dim, mod_scale, lr_mul);
-    style_bwd_latent_kernel<<<dim3((unsigned)((style_dim + 255) / 256), n_layers, gz), 256, kSB * max_cin * sizeof(float), st>>>(
+    style_bwd_latent_kernel<<<dim3((unsigned)((style_dim + 31) / 32), n_layers, gz), 256, kSB * max_cin * sizeof(float), st>>>(
         tab, g_latent, (int)batch, (int)n_latent, (int)style_dim, mod_scale);
     count_launch(max_cout > 0 ? 4 : 3);
     return check_launch("sr_style_scales_backward_f32");
@@ -333,9 +358,11 @@ extern "C" int sr_weight_sq_backward_f32(float *gw, const float *w, const float 
 {
     SR_REQUIRE(gw && w && g_wsq && cout >= 1 && cin >= 1 && taps >= 1, "weight_sq_backward: bad arguments");
     const int64_t total = cout * cin * taps;
+    SR_REQUIRE(total < 0x7fffffffll, "weight_sq_backward: weight too large");
     int64_t blocks = (total + 255) / 256;
-    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    weight_sq_backward_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(gw, w, g_wsq, scale * scale, total, taps);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    weight_sq_backward_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(gw, w, g_wsq, scale * scale, (uint32_t)total,
+                                                                             FastDiv((uint32_t)taps));
     count_launch();
     return check_launch("sr_weight_sq_backward_f32");
 }
@@ -344,10 +371,10 @@ extern "C" int sr_weight_grad_layout_f32(float *gw, const float *dwk, float scal
                                          void *stream)
 {
     SR_REQUIRE(gw && dwk && cout >= 1 && cin >= 1 && taps >= 1, "weight_grad_layout: bad arguments");
-    const int64_t pairs = cout * cin;
-    int64_t blocks = (pairs + 255) / 256;
-    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    weight_grad_layout_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(gw, dwk, scale, (int)cout, (int)cin, taps);
+    SR_REQUIRE(cout <= 65535 && taps <= 32, "weight_grad_layout: cout <= 65535, taps <= 32");
+    const dim3 grid((unsigned)((cin + kGL - 1) / kGL), (unsigned)cout);
+    weight_grad_layout_kernel<<<grid, 256, sizeof(float) * taps * (kGL + 1), (cudaStream_t)stream>>>(gw, dwk, scale, (int)cout,
+                                                                                                (int)cin, taps);
     count_launch();
     return check_launch("sr_weight_grad_layout_f32");
 }
