@@ -1169,6 +1169,120 @@ wgrad_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
     }
 }
 
+// CTA-pair wgrad for 128-wide channel blocks: the pair accumulates TWO taps of a 128 (cout) x 128 (cin) block with one
+// M = 256 x N = 128 tcgen05.mma.cta_group::2 stream.  The M halves are the two taps: CTA r stages the 128 output channels
+// of G shifted by ITS tap and 64 of the 128 input channels of the (common, unshifted) X tile.  Per SM that is 96 instead
+// of 128 B/clk of shared-memory operand reads and 48 instead of 64 KB of TMA traffic per 64-pixel stage -- the two limits
+// of the single-CTA N = 128 kernel (ncu: tensor pipe 60 %).  All taps must read X at the same offset; the host moves the
+// tap shift of a plain 3x3 conv from X to G (sum over x-pixels of g[p - tap] * x[p], zero fill outside G).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+wgrad_tf32_2cta_taps_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
+                            const WgradKParams p, int num_taps)
+{
+    constexpr int WG_BK = 64, WG_STAGES = 4, WG_N = 128;
+    constexpr int WG_COLBLK_BYTES = WG_BK * 128;
+    constexpr int WG_STAGE_BYTES = 6 * WG_COLBLK_BYTES;                  // 4 blocks of G (128 co) + 2 blocks of X (64 ci) per CTA
+    constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                ((uint32_t)(WG_N >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + WG_STAGES * WG_STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + WG_STAGES;
+    uint64_t *tmem_full_bar = empty_bar + WG_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)(blockIdx.x & 1);
+    const int blk = blockIdx.x >> 1;
+    const int m_tile = blk / p.n_tiles, n_tile = blk % p.n_tiles;        // in units of 128 channels
+    const int tap_raw = 2 * blockIdx.y + rank;
+    const bool tap_valid = tap_raw < num_taps;
+    const int tap = tap_valid ? tap_raw : num_taps - 1;                   // odd tap count: the last pair's second half idles
+    const int total_kt = p.tiles_x * p.tiles_y * p.tiles_n;
+    const int kt0 = blockIdx.z * p.ktiles_per_split;
+    const int num_kt = min(total_kt, kt0 + p.ktiles_per_split) - kt0;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_g) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_x) : "memory");
+        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)WG_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < num_kt; ++it) {
+                const int s = it % WG_STAGES;
+                const uint32_t ph = (it / WG_STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                const int kt = kt0 + it;
+                const int tile_x = kt % p.tiles_x, tile_y = (kt / p.tiles_x) % p.tiles_y, tile_n = kt / (p.tiles_x * p.tiles_y);
+                const int gx0 = tile_x << p.tw_log2, gy0 = tile_y << p.th_log2, n0 = tile_n << p.tn_log2;
+                uint8_t *sa = smem + s * WG_STAGE_BYTES, *sb = sa + 4 * WG_COLBLK_BYTES;
+                if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * WG_STAGE_BYTES);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    tma_load_4d_2sm(sa + j * WG_COLBLK_BYTES, &tmap_g, &full_bar[s], m_tile * 128 + j * 32,
+                                    gx0 * p.g_stride + p.g_dx[tap], gy0 * p.g_stride + p.g_dy[tap], n0);
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    tma_load_4d_2sm(sb + j * WG_COLBLK_BYTES, &tmap_x, &full_bar[s], n_tile * 128 + rank * 64 + j * 32,
+                                    gx0 * p.x_stride + p.x_dx[0], gy0 * p.x_stride + p.x_dy[0], n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            for (int it = 0; it < num_kt; ++it) {
+                const int s = it % WG_STAGES;
+                const uint32_t ph = (it / WG_STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tcgen05_fence_after();
+                const uint32_t a0 = smem_u32(smem + s * WG_STAGE_BYTES), b0 = a0 + 4 * WG_COLBLK_BYTES;
+#pragma unroll
+                for (int k = 0; k < WG_BK / 8; ++k)
+                    umma_tf32_2sm(tmem_base, make_mnmajor_sw128_desc(a0 + k * 1024, WG_COLBLK_BYTES),
+                                  make_mnmajor_sw128_desc(b0 + k * 1024, WG_COLBLK_BYTES), kIdesc, (it | k) != 0);
+                tcgen05_commit_2sm(&empty_bar[s]);
+            }
+            tcgen05_commit_2sm(tmem_full_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        const int co = m_tile * 128 + q * 32 + lane;
+        float *dst = p.dw + ((long long)co * p.taps_total + p.tap_out[tap]) * p.cin + n_tile * WG_N;
+        mbar_wait(tmem_full_bar, 0);
+        tcgen05_fence_after();
+        if (tap_valid) {
+#pragma unroll 1
+            for (int c = 0; c < WG_N / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dst + c * 32 + j), "f"(__uint_as_float(r[j])),
+                                 "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3])) : "memory");
+            }
+        }
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)WG_N) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------ small helper kernels
 // xs[b,p,c] = tf32(x[b,p,c] * s[b,c])  -- the modulated, tensor-core-ready copy of an NHWC activation
 __global__ void __launch_bounds__(256)
@@ -1625,6 +1739,29 @@ extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
     bool pair = (a->cout % 256 == 0) && (a->cin % 256 == 0);               // CTA-pair kernel: 256 x 256 block per tap
     if (force_pair) pair = pair && force_pair[0] == '1';
     const bool wide = !pair && allow_wide && (a->cin % 256 == 0);           // N = 256, 32 pixels per stage
+    // Two-tap CTA pairs for 128-wide channel blocks (wgrad_tf32_2cta_taps_kernel): every tap must read X at the same
+    // offset.  True as given for the transposed conv (taps shift G); for a stride-1 conv whose taps shift X over an X of
+    // the same size as G, the shift moves to G:  sum_p g[p] x[p + t] = sum_p' g[p' - t] x[p']  (zero fill outside G).
+    static const char *taps2_env = getenv("SR_WGRAD_TAPS2");                // A/B: 0 = single-CTA N = 128 kernel
+    int32_t tg_dy[9], tg_dx[9], tx_dy[9], tx_dx[9];
+    bool taps2 = !pair && !wide && a->num_taps >= 2 && !(taps2_env && taps2_env[0] == '0');
+    if (taps2) {
+        bool x_same = true, g_zero = true;
+        for (int t = 0; t < a->num_taps; ++t) {
+            x_same &= a->x_dy[t] == a->x_dy[0] && a->x_dx[t] == a->x_dx[0];
+            g_zero &= a->g_dy[t] == 0 && a->g_dx[t] == 0;
+        }
+        for (int t = 0; t < 9; ++t) { tg_dy[t] = a->g_dy[t]; tg_dx[t] = a->g_dx[t]; tx_dy[t] = a->x_dy[t]; tx_dx[t] = a->x_dx[t]; }
+        if (!x_same) {
+            const bool movable = g_zero && a->g_stride == 1 && a->x_stride == 1 && a->g_h == a->x_h && a->g_w == a->x_w &&
+                                 a->grid_h == a->x_h && a->grid_w == a->x_w;
+            if (movable) {
+                for (int t = 0; t < a->num_taps; ++t) { tg_dy[t] = -a->x_dy[t]; tg_dx[t] = -a->x_dx[t]; tx_dy[t] = 0; tx_dx[t] = 0; }
+            } else {
+                taps2 = false;
+            }
+        }
+    }
     int tw, th, tn;
     if (wide) {
         if (a->grid_w > 8) { tw = 16; th = 2; tn = 1; }
@@ -1666,8 +1803,8 @@ extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
     // launch executes in whole waves: time ~ ceil(CTAs / slots) * (K tiles per CTA + fixed cost), where the fixed cost
     // (TMEM alloc, pipeline fill, red.add epilogue) is worth about 16 K tiles.  Pick the split count that minimises it
     // (e.g. 9 taps x 33 splits = 297 CTAs is THREE waves of 148; 32 splits is two).
-    const long long slots = pair ? kNumSMs / 2 : kNumSMs;
-    const long long base_ctas = (long long)mn_tiles * a->num_taps;
+    const long long slots = (pair || taps2) ? kNumSMs / 2 : kNumSMs;
+    const long long base_ctas = (long long)mn_tiles * (taps2 ? (a->num_taps + 1) / 2 : a->num_taps);
     long long splits = 1, best_cost = -1;
     const long long max_splits = total_kt < 4 * slots ? total_kt : 4 * slots;
     for (long long s = 1; s <= max_splits; ++s) {
@@ -1684,6 +1821,7 @@ extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
     p.g_stride = a->g_stride; p.x_stride = a->x_stride;
     for (int t = 0; t < 9; ++t) {
         p.g_dy[t] = a->g_dy[t]; p.g_dx[t] = a->g_dx[t]; p.x_dy[t] = a->x_dy[t]; p.x_dx[t] = a->x_dx[t];
+        if (taps2) { p.g_dy[t] = tg_dy[t]; p.g_dx[t] = tg_dx[t]; p.x_dy[t] = tx_dy[t]; p.x_dx[t] = tx_dx[t]; }
         p.tap_out[t] = a->tap_out[t];
     }
     p.taps_total = (int)a->taps_total; p.cin = (int)a->cin;
@@ -1694,8 +1832,17 @@ extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
     }
     const dim3 grid((unsigned)(pair ? 2 * mn_tiles : mn_tiles), (unsigned)a->num_taps, (unsigned)splits);
     static bool configured[2] = {false, false};
-    static bool configured_pair = false;
-    if (pair) {
+    static bool configured_pair = false, configured_taps2 = false;
+    if (taps2) {
+        const size_t smem = 1024 + (size_t)4 * 6 * 64 * 128 + 256;
+        if (!configured_taps2) {
+            cudaError_t e = cudaFuncSetAttribute(wgrad_tf32_2cta_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { set_error("wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+            configured_taps2 = true;
+        }
+        const dim3 grid2((unsigned)(2 * mn_tiles), (unsigned)((a->num_taps + 1) / 2), (unsigned)splits);
+        wgrad_tf32_2cta_taps_kernel<<<grid2, kConvThreads, smem, st>>>(tg, tx, p, (int)a->num_taps);
+    } else if (pair) {
         const size_t smem = 1024 + (size_t)3 * 8 * 64 * 128 + 256;
         if (!configured_pair) {
             cudaError_t e = cudaFuncSetAttribute(wgrad_tf32_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
