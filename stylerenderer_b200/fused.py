@@ -66,16 +66,16 @@ class StyledConvTC(Function):
             # one pass: activation backward, bias / noise-weight gradients, e = sum g_pre * (d * acc), ga = tf32(g_pre * d)
             ga, g_bias, g_noise_w, e = tc.bwd_prologue(gy, y, noise, noise_weight, act_bias, d, alpha, gain, True)
             dxs = tc.conv3x3(ga, tc.weight_prep(weight[0], scale, 1))
-            dwk = tc.wgrad3x3(ga, xs)
+            dwk = tc.wgrad3x3(ga, xs) if ctx.needs_input_grad[1] else None
         else:
             g_pre, g_bias, g_noise_w, _ = tc.bwd_prologue(gy, y, noise, noise_weight, act_bias, None, alpha, gain, False)
             ga, e = tc.blur_scaledot(g_pre, torch.flip(blur_taps, [0, 1]), (2, 2), d, t)   # FIR^T, * d, tf32, sum gt * t
             dxs = tc.conv3x3_s2_gather(ga, tc.weight_prep(weight[0], scale, 2), (h, w))
-            dwk = tc.wgrad_transpose3x3_s2(ga, xs)
+            dwk = tc.wgrad_transpose3x3_s2(ga, xs) if ctx.needs_input_grad[1] else None
         g_d = e / d                                                     # dL/dd = sum g * acc = e / d
         g_x, g_s = tc.scale_dot(dxs, x_nhwc, s, False)                 # dx = dxs * s, ds = sum_p dxs * x
         g_x = from_nhwc(g_x)
-        g_w = (dwk.view(cout, 3, 3, cin).permute(0, 3, 1, 2) * scale).unsqueeze(0)
+        g_w = (dwk.view(cout, 3, 3, cin).permute(0, 3, 1, 2) * scale).unsqueeze(0) if dwk is not None else None
         return g_x, g_w, g_s, g_d, None, g_noise_w, g_bias, None, None, None, None, None
 
 
@@ -110,13 +110,13 @@ class ModConvTC(Function):
         if not upsample:
             ga, e = tc.scale_dot(gy, saved, d, True)                   # tf32(gy * d), e = sum gy * (d * acc)
             dxs = tc.conv3x3(ga, tc.weight_prep(weight[0], scale, 1))
-            dwk = tc.wgrad3x3(ga, xs)
+            dwk = tc.wgrad3x3(ga, xs) if ctx.needs_input_grad[1] else None
         else:
             ga, e = tc.blur_scaledot(gy, torch.flip(blur_taps, [0, 1]), (2, 2), d, saved)
             dxs = tc.conv3x3_s2_gather(ga, tc.weight_prep(weight[0], scale, 2), (h, w))
-            dwk = tc.wgrad_transpose3x3_s2(ga, xs)
+            dwk = tc.wgrad_transpose3x3_s2(ga, xs) if ctx.needs_input_grad[1] else None
         g_x, g_s = tc.scale_dot(dxs, x_nhwc, s, False)
-        g_w = (dwk.view(cout, 3, 3, cin).permute(0, 3, 1, 2) * scale).unsqueeze(0)
+        g_w = (dwk.view(cout, 3, 3, cin).permute(0, 3, 1, 2) * scale).unsqueeze(0) if dwk is not None else None
         return from_nhwc(g_x), g_w, g_s, e / d, None, None, None
 
 
@@ -303,17 +303,23 @@ class PlainConvTC(Function):
             ga, g_bias, _, _ = tc.bwd_prologue(gy, y, None, None, bias, _ones(b, cout, gy.device), alpha, gain, False)
         else:
             ga = tc.modulate(gy)
+        need_w = ctx.needs_input_grad[1]          # False in the generator's step of the GAN loop (reference train.py:292-293)
+        dwk = None
         if kind == "s1":
             dx = tc.conv3x3(ga, wk_t)
-            dwk = tc.wgrad3x3(ga, xr)
+            if need_w:
+                dwk = tc.wgrad3x3(ga, xr)
         elif kind == "s2":
             dx = tc.conv_transpose3x3_s2(ga, wk_t)
-            dwk = tc.wgrad(ga, xr, [(0, 0, ky, kx, ky * 3 + kx) for ky in range(3) for kx in range(3)], (oh, ow), x_stride=2)
+            if need_w:
+                dwk = tc.wgrad(ga, xr, [(0, 0, ky, kx, ky * 3 + kx) for ky in range(3) for kx in range(3)], (oh, ow),
+                               x_stride=2)
         else:
             dx = torch.zeros(b, h, w, cin, dtype=torch.float32, device=gy.device)
             tc.conv_igemm_multi(ga, wk_t, [([(0, 0, 0)], (oh, ow), (0, 0))], dx, out_stride=2)
-            dwk = tc.wgrad(ga, xr, [(0, 0, 0, 0, 0)], (oh, ow), x_stride=2, taps_total=1)
-        g_w = style.weight_grad_layout(dwk, scale, cout, cin, k)[0]
+            if need_w:
+                dwk = tc.wgrad(ga, xr, [(0, 0, 0, 0, 0)], (oh, ow), x_stride=2, taps_total=1)
+        g_w = style.weight_grad_layout(dwk, scale, cout, cin, k)[0] if need_w else None
         return from_nhwc(dx), g_w, g_bias, None, None, None, None
 
 
@@ -440,12 +446,15 @@ class StyledLayerTC(Function):
         if rgb_weight is not None and g_rgb is not None:
             src.update(g_rgb=g_rgb.contiguous(), rgb_weight=rgb_weight)
         g_map = None
+        # frozen weights (latent inversion): the weight-gradient GEMM (a third of the backward
+        # flops) and its layout pass are skipped; every other gradient is unchanged
+        need_w = ctx.needs_input_grad[1]
         if not upsample:
             res = tc.bwd_prologue2(y, noise, noise_weight, act_bias, d, alpha, gain, True, stylemap=stylemap, **src)
             ga, g_bias, g_noise_w, e, ds_next, dwb = res[:6]
             g_map = res[6] if stylemap is not None else None
             dxs = tc.conv3x3(ga, ctx.wkt if ctx.wkt is not None else tc.weight_prep(weight[0], scale, 1))
-            dwk = tc.wgrad3x3(ga, xs)
+            dwk = tc.wgrad3x3(ga, xs) if need_w else None
         else:
             # e = sum_p gp * (fir(t) * map0) comes from the prologue (fir(t) * map0 is recoverable from y, like the plain
             # block's conv output), so the FIR^T pass does not have to read the saved transposed-conv output t again
@@ -454,9 +463,9 @@ class StyledLayerTC(Function):
             g_map = res[6] if stylemap is not None else None
             ga, _ = tc.blur_scaledot(g_pre, torch.flip(blur_taps, [0, 1]), (2, 2), d)       # FIR^T, * d, tf32
             dxs = tc.conv3x3_s2_gather(ga, ctx.wkt if ctx.wkt is not None else tc.weight_prep(weight[0], scale, 2), (h, w))
-            dwk = tc.wgrad_transpose3x3_s2(ga, xs)
+            dwk = tc.wgrad_transpose3x3_s2(ga, xs) if need_w else None
         g_d = e / d
-        g_w = style.weight_grad_layout(dwk, scale, cout, cin, 3)
+        g_w = style.weight_grad_layout(dwk, scale, cout, cin, 3) if need_w else None
         return (from_nhwc(dxs), g_w, g_d, None, g_noise_w, g_bias, ds_next, dwb, None, None, None, None, None, None, None,
                 g_map)
 

@@ -410,6 +410,37 @@ def test_generator_tcgen05_backend_matches_cudnn_backend():
     print("worst gradient cosine tcgen05 vs fp32 composed path:", worst)
 
 
+def test_generator_frozen_weights_latent_gradient_is_unchanged():
+    """Latent inversion back-propagates to the latents only: with every parameter frozen the
+    chained blocks skip their weight-gradient GEMMs, and the latent gradient must equal the one of the full backward
+    (the same kernels on the same operands; only the order of float atomics inside the reductions may differ)."""
+    from stylerenderer_b200 import _lib, layers as L, model as M
+    from make_golden import seeded
+    G = det_fill(M.Generator(64, 64, 2), 730).cuda().eval()
+    w = seeded((2, G.n_latent, 64), 731).cuda()
+    cot = seeded((2, 3, 64, 64), 732).cuda()
+
+    def run():
+        ww = w.clone().requires_grad_(True)
+        n0 = _lib.launch_count()
+        img, _ = G([ww], input_is_latent=True, randomize_noise=False)
+        g, = torch.autograd.grad(img, [ww], cot)
+        return img.detach(), g, _lib.launch_count() - n0
+    L.set_conv_backend("tcgen05")
+    try:
+        img_a, g_a, n_a = run()
+        for p in G.parameters():
+            p.requires_grad_(False)
+        img_b, g_b, n_b = run()
+    finally:
+        L.set_conv_backend("cudnn")
+    scale = float(g_a.abs().max())
+    assert float((img_a - img_b).abs().max()) <= 1e-5 * float(img_a.abs().max())
+    assert float((g_a - g_b).abs().max()) <= 1e-5 * scale, float((g_a - g_b).abs().max()) / scale
+    assert n_b < n_a, (n_a, n_b)                       # the wgrad / weight-gradient layout launches are gone
+    print("launches per fwd+bwd: all gradients", n_a, "latents only", n_b)
+
+
 def test_style_scales_all_vs_torch():
     """Batched style path (csrc/style_ops.cu: s, d for every layer in one call) against the per-layer torch formulation
     ModulatedConv2d.style_scales (reference layers.py:232-239, 295-299) in float64, values and all gradients."""
