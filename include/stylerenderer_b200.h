@@ -114,6 +114,31 @@ int sr_rasterize_backward_f64(int64_t b, int64_t n, int64_t h, int64_t w, int64_
                               const double *verts, const double *tex, const int64_t *ids, const double *bary,
                               const double *gout, double *grad_verts, double *grad_tex, double eps, void *stream);
 
+/* Resolution pyramid: the SAME mesh rasterised at several square sizes in one triangle pass + one resolve pass
+ * (forward) and one scatter pass (backward).  Replaces the seven independent `rasterize(..., h)` calls of
+ * GeneratorWithMap.forward (reference model.py:260-270: sizes 4, 8, ..., 256) -- each triangle's indices and vertices are
+ * loaded once, the per-size set-up arithmetic is the reference's, so every level is bit-identical to a single-size
+ * `sr_rasterize_forward_f32` call (and to `rasterize_cpu`).  `levels` is a HOST array; pointers inside are device
+ * pointers.  keys: workspace of `sr_rasterize_pyramid_workspace_bytes` bytes.
+ * Backward: levels with gout == NULL take no part; all others scatter-add into the same zero-filled
+ * grad_verts [b*n,3] / grad_tex [b*n,c] (either may be NULL). */
+#define SR_RASTER_MAX_LEVELS 8
+typedef struct sr_raster_level {
+    int64_t size;          /* h == w of this level */
+    int64_t *ids;          /* [b,size,size,3] */
+    void *bary;            /* float [b,size,size,3] */
+    void *out;             /* float [b,size,size,c] (forward, required when tex != NULL) */
+    const void *gout;      /* float [b,size,size,c] (backward: gradient of out) or NULL */
+} sr_raster_level;
+int64_t sr_rasterize_pyramid_workspace_bytes(int64_t b, int n_levels, const int64_t *sizes);
+int sr_rasterize_pyramid_forward_f32(int64_t b, int64_t nv, int64_t nf, int n_levels, const sr_raster_level *levels,
+                                     int shared_v, int shared_f, int perspective,
+                                     const float *verts, const int64_t *tris, uint64_t *keys, float eps,
+                                     const float *tex, int64_t c, void *stream);
+int sr_rasterize_pyramid_backward_f32(int64_t b, int64_t n, int n_levels, const sr_raster_level *levels, int64_t c,
+                                      int perspective, const float *verts, const float *tex,
+                                      float *grad_verts, float *grad_tex, float eps, void *stream);
+
 /* ------------------------------------------------------------------ modulated convolution ------
  * Replaces the dense contraction inside ModulatedConv2d.forward (reference layers.py:293-323: cuDNN grouped
  * conv2d / conv_transpose2d over B per-sample weight copies) with ONE shared-weight implicit GEMM on the

@@ -32,6 +32,9 @@ _SIGNATURES = {
     "sr_rasterize_dcoeff_f64": (_I, [_L, _L, _L, _L, _I, _P, _P, _P, _D, _P]),
     "sr_rasterize_backward_f32": (_I, [_L, _L, _L, _L, _L, _I, _P, _P, _P, _P, _P, _P, _P, _F, _P]),
     "sr_rasterize_backward_f64": (_I, [_L, _L, _L, _L, _L, _I, _P, _P, _P, _P, _P, _P, _P, _D, _P]),
+    "sr_rasterize_pyramid_workspace_bytes": (_L, [_L, _I, _P]),
+    "sr_rasterize_pyramid_forward_f32": (_I, [_L, _L, _L, _I, _P, _I, _I, _I, _P, _P, _P, _F, _P, _L, _P]),
+    "sr_rasterize_pyramid_backward_f32": (_I, [_L, _L, _I, _P, _L, _I, _P, _P, _P, _P, _F, _P]),
     "sr_conv_igemm_tf32": (_I, [_P, _P]),
     "sr_conv_igemm_multi_tf32": (_I, [_P, _I, _P]),
     "sr_conv_wgrad_tf32": (_I, [_P, _P]),

@@ -213,6 +213,38 @@ __device__ __forceinline__ void emit(const Tri<T> &t, int x, int y, uint32_t f, 
     }
 }
 
+// Coverage of one set-up triangle per lane (t valid where `live`): small boxes are walked by their own lane, boxes of
+// more than 32 pixels are re-distributed over the warp.  Must be called by all 32 lanes (ballot / shuffles).
+template <typename T, int PASS>
+__device__ __forceinline__ void cover_warp(const Tri<T> &t, bool live, uint32_t f, uint32_t lane, const RasterGeom &g, T eps,
+                                           uint64_t *__restrict__ zkeys, uint32_t *__restrict__ idkeys, int64_t img)
+{
+    int bw = 0, area = 0;
+    if (live) { bw = t.x_hi - t.x_lo + 1; area = bw * (t.y_hi - t.y_lo + 1); }
+    const bool big = live && area > 32;
+    if (live && !big) {
+        for (int y = t.y_lo; y <= t.y_hi; ++y)
+            for (int x = t.x_lo; x <= t.x_hi; ++x) emit<T, PASS>(t, x, y, f, g, eps, zkeys, idkeys, img);
+    }
+    // big boxes: the whole warp walks the box of one lane at a time, 32 pixels per step
+    uint32_t pending = __ballot_sync(0xffffffffu, big);
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        Tri<T> s;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) { s.p[c] = __shfl_sync(0xffffffffu, t.p[c], src); s.E[c] = __shfl_sync(0xffffffffu, t.E[c], src); }
+        s.det = __shfl_sync(0xffffffffu, t.det, src);
+        s.x_lo = __shfl_sync(0xffffffffu, t.x_lo, src); s.y_lo = __shfl_sync(0xffffffffu, t.y_lo, src);
+        const int sbw = __shfl_sync(0xffffffffu, bw, src), sarea = __shfl_sync(0xffffffffu, area, src);
+        const uint32_t sf = __shfl_sync(0xffffffffu, f, src);
+        for (int k = lane; k < sarea; k += 32) {
+            const int yy = k / sbw, xx = k - yy * sbw;
+            emit<T, PASS>(s, s.x_lo + xx, s.y_lo + yy, sf, g, eps, zkeys, idkeys, img);
+        }
+    }
+}
+
 template <typename T, int PASS>
 __global__ void __launch_bounds__(kThreads)
 raster_tri_kernel(const RasterGeom g, const T *__restrict__ verts, const int64_t *__restrict__ tris,
@@ -236,29 +268,59 @@ raster_tri_kernel(const RasterGeom g, const T *__restrict__ verts, const int64_t
             // reference passes (h, w) for (w, h): x spans h, y spans w (op/rasterize.cpp:38)
             if (live) live = tri_setup<T>(t, g.h, g.w, g.perspective != 0, eps);
         }
-        int bw = 0, area = 0;
-        if (live) { bw = t.x_hi - t.x_lo + 1; area = bw * (t.y_hi - t.y_lo + 1); }
-        const bool big = live && area > 32;
-        if (live && !big) {
-            for (int y = t.y_lo; y <= t.y_hi; ++y)
-                for (int x = t.x_lo; x <= t.x_hi; ++x) emit<T, PASS>(t, x, y, f, g, eps, zkeys, idkeys, img);
+        cover_warp<T, PASS>(t, live, f, lane, g, eps, zkeys, idkeys, img);
+    }
+}
+
+// ---- resolution pyramid: the same mesh rasterised at several square sizes in one launch per pass -------------------
+// GeneratorWithMap renders the normal map at 4, 8, ..., 256 pixels every forward (reference model.py:260-270: seven
+// independent rasterize calls).  One triangle pass loads each triangle (3 int64 ids + 9 gathered floats) ONCE and sets
+// it up per level -- the pixel transform depends on the size, so the per-level arithmetic stays exactly the reference's
+// and the result is bit-identical to seven single-size calls; at the coarse levels nearly every triangle leaves after
+// the empty-box test.  One resolve launch and one backward launch walk the concatenated 256-pixel blocks of all levels.
+constexpr int kMaxLevels = SR_RASTER_MAX_LEVELS;
+
+template <typename T>
+struct Pyramid {
+    int n;
+    int size[kMaxLevels];
+    int64_t key_off[kMaxLevels];          // first key of the level inside the workspace
+    int64_t blk_off[kMaxLevels + 1];      // prefix sum of 256-pixel blocks
+    int64_t *ids[kMaxLevels];
+    T *bary[kMaxLevels];
+    T *out[kMaxLevels];
+    const T *gout[kMaxLevels];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+raster_tri_pyramid_kernel(const RasterGeom g0, const Pyramid<T> L, const T *__restrict__ verts,
+                          const int64_t *__restrict__ tris, uint64_t *__restrict__ zkeys, T eps)
+{
+    const int64_t img = blockIdx.y;
+    const int64_t total = g0.nf;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    const uint32_t lane = threadIdx.x & 31u;
+    const T *V = verts + (g0.shared_v ? 0 : img * g0.nv * 3);
+    const int64_t *F = tris + (g0.shared_f ? 0 : img * g0.nf * 3);
+    for (int64_t base = (int64_t)blockIdx.x * kThreads + (threadIdx.x & ~31u); base < total; base += stride) {
+        const int64_t item = base + lane;
+        Tri<T> raw;
+        bool loaded = item < total;
+        const uint32_t f = (uint32_t)item;
+        if (loaded) {
+            int64_t ids[3];
+            loaded = load_tri<T>(raw, V, F, f, g0.nv, ids);
         }
-        // big boxes: the whole warp walks the box of one lane at a time, 32 pixels per step
-        uint32_t pending = __ballot_sync(0xffffffffu, big);
-        while (pending) {
-            const int src = __ffs(pending) - 1;
-            pending &= pending - 1;
-            Tri<T> s;
+        if (!__any_sync(0xffffffffu, loaded)) continue;
+        for (int l = 0; l < L.n; ++l) {                      // warp-uniform
+            RasterGeom g = g0;
+            g.h = g.w = L.size[l];
+            Tri<T> t;
 #pragma unroll
-            for (int c = 0; c < 9; ++c) { s.p[c] = __shfl_sync(0xffffffffu, t.p[c], src); s.E[c] = __shfl_sync(0xffffffffu, t.E[c], src); }
-            s.det = __shfl_sync(0xffffffffu, t.det, src);
-            s.x_lo = __shfl_sync(0xffffffffu, t.x_lo, src); s.y_lo = __shfl_sync(0xffffffffu, t.y_lo, src);
-            const int sbw = __shfl_sync(0xffffffffu, bw, src), sarea = __shfl_sync(0xffffffffu, area, src);
-            const uint32_t sf = __shfl_sync(0xffffffffu, f, src);
-            for (int k = lane; k < sarea; k += 32) {
-                const int yy = k / sbw, xx = k - yy * sbw;
-                emit<T, PASS>(s, s.x_lo + xx, s.y_lo + yy, sf, g, eps, zkeys, idkeys, img);
-            }
+            for (int c = 0; c < 9; ++c) t.p[c] = raw.p[c];
+            const bool live = loaded && tri_setup<T>(t, g.h, g.w, g.perspective != 0, eps);
+            cover_warp<T, 0>(t, live, f, lane, g, eps, zkeys + L.key_off[l], nullptr, img);
         }
     }
 }
@@ -284,6 +346,63 @@ __device__ __forceinline__ void stream_out(void *gdst, const void *ssrc, int byt
     }
 }
 
+template <typename T>
+struct ResolveStage {
+    int64_t ids[kThreads * 3];
+    T w[kThreads * 3];
+    T out[kThreads * kMaxStageC];
+};
+
+// 256 consecutive pixels (block `blk`) of one raster geometry; called by the whole CTA.
+template <typename T, bool PACKED>
+__device__ __forceinline__ void resolve_block(const RasterGeom &g, const T *__restrict__ verts, const int64_t *__restrict__ tris,
+                                              const uint64_t *__restrict__ zkeys, const uint32_t *__restrict__ idkeys, T eps,
+                                              int64_t *__restrict__ ids_out, T *__restrict__ bary_out,
+                                              const T *__restrict__ tex, int c, T *__restrict__ out, int vec_ok,
+                                              int64_t blk, int64_t npix, ResolveStage<T> &st)
+{
+    const bool stage_out = tex != nullptr && c <= kMaxStageC;
+    const int64_t pix0 = blk * kThreads, pix = pix0 + threadIdx.x;
+    const int count = (int)((npix - pix0 < kThreads) ? (npix - pix0) : kThreads);
+    int64_t ids[3] = {0, 0, 0};
+    T w[3] = {0, 0, 0};
+    bool hit = false;
+    if (pix < npix) {
+        const uint64_t key = zkeys[pix];
+        hit = key != 0;
+        if (hit) {
+            const uint32_t f = PACKED ? (0xffffffffu - (uint32_t)key) : idkeys[pix];
+            const int64_t img = pix / (g.h * (int64_t)g.w);
+            const int rem = (int)(pix - img * g.h * (int64_t)g.w);
+            const int y = rem / g.w, x = rem - y * g.w;
+            const T *V = verts + (g.shared_v ? 0 : img * g.nv * 3);
+            const int64_t *F = tris + (g.shared_f ? 0 : img * g.nf * 3);
+            Tri<T> t;
+            T z;
+            hit = load_tri<T>(t, V, F, f, g.nv, ids) && tri_setup<T>(t, g.h, g.w, g.perspective != 0, eps) &&
+                  tri_sample<T>(t, (T)x, (T)y, g.perspective != 0, eps, w, z);
+            if (hit && !g.shared_v) { ids[0] += g.nv * img; ids[1] += g.nv * img; ids[2] += g.nv * img; }
+            if (!hit) { ids[0] = ids[1] = ids[2] = 0; w[0] = w[1] = w[2] = 0; }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { st.ids[3 * threadIdx.x + k] = ids[k]; st.w[3 * threadIdx.x + k] = w[k]; }
+    if (tex && pix < npix) {
+        // op/rasterize.py:29-37: sum_k tex[ids_k] * bary_k  (background: row 0 times 0 = 0)
+        for (int ch = 0; ch < c; ++ch) {
+            T v = 0;
+            if (hit) v = tex[ids[0] * c + ch] * w[0] + tex[ids[1] * c + ch] * w[1] + tex[ids[2] * c + ch] * w[2];
+            if (stage_out) st.out[threadIdx.x * c + ch] = v;
+            else out[pix * c + ch] = v;
+        }
+    }
+    __syncthreads();
+    stream_out<int4>(ids_out + pix0 * 3, st.ids, count * 3 * (int)sizeof(int64_t), vec_ok);
+    stream_out<int4>(bary_out + pix0 * 3, st.w, count * 3 * (int)sizeof(T), vec_ok);
+    if (stage_out) stream_out<int4>(out + pix0 * c, st.out, count * c * (int)sizeof(T), vec_ok && ((pix0 * c * (int64_t)sizeof(T)) % 16 == 0));
+    __syncthreads();
+}
+
 template <typename T, bool PACKED>
 __global__ void __launch_bounds__(kThreads)
 raster_resolve_kernel(const RasterGeom g, const T *__restrict__ verts, const int64_t *__restrict__ tris,
@@ -291,52 +410,29 @@ raster_resolve_kernel(const RasterGeom g, const T *__restrict__ verts, const int
                       int64_t *__restrict__ ids_out, T *__restrict__ bary_out,
                       const T *__restrict__ tex, int c, T *__restrict__ out, int vec_ok)
 {
-    __shared__ __align__(16) int64_t s_ids[kThreads * 3];
-    __shared__ __align__(16) T s_w[kThreads * 3];
-    __shared__ __align__(16) T s_out[kThreads * kMaxStageC];
+    __shared__ __align__(16) ResolveStage<T> st;
     const int64_t npix = g.b * g.h * (int64_t)g.w;
     const int64_t nblk = (npix + kThreads - 1) / kThreads;
-    const bool stage_out = tex != nullptr && c <= kMaxStageC;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x)
+        resolve_block<T, PACKED>(g, verts, tris, zkeys, idkeys, eps, ids_out, bary_out, tex, c, out, vec_ok, blk, npix, st);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+raster_resolve_pyramid_kernel(const RasterGeom g0, const Pyramid<T> L, const T *__restrict__ verts,
+                              const int64_t *__restrict__ tris, const uint64_t *__restrict__ zkeys, T eps,
+                              const T *__restrict__ tex, int c, int vec_ok)
+{
+    __shared__ __align__(16) ResolveStage<T> st;
+    const int64_t nblk = L.blk_off[L.n];
     for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-        const int64_t pix0 = blk * kThreads, pix = pix0 + threadIdx.x;
-        const int count = (int)((npix - pix0 < kThreads) ? (npix - pix0) : kThreads);
-        int64_t ids[3] = {0, 0, 0};
-        T w[3] = {0, 0, 0};
-        bool hit = false;
-        if (pix < npix) {
-            const uint64_t key = zkeys[pix];
-            hit = key != 0;
-            if (hit) {
-                const uint32_t f = PACKED ? (0xffffffffu - (uint32_t)key) : idkeys[pix];
-                const int64_t img = pix / (g.h * (int64_t)g.w);
-                const int rem = (int)(pix - img * g.h * (int64_t)g.w);
-                const int y = rem / g.w, x = rem - y * g.w;
-                const T *V = verts + (g.shared_v ? 0 : img * g.nv * 3);
-                const int64_t *F = tris + (g.shared_f ? 0 : img * g.nf * 3);
-                Tri<T> t;
-                T z;
-                hit = load_tri<T>(t, V, F, f, g.nv, ids) && tri_setup<T>(t, g.h, g.w, g.perspective != 0, eps) &&
-                      tri_sample<T>(t, (T)x, (T)y, g.perspective != 0, eps, w, z);
-                if (hit && !g.shared_v) { ids[0] += g.nv * img; ids[1] += g.nv * img; ids[2] += g.nv * img; }
-                if (!hit) { ids[0] = ids[1] = ids[2] = 0; w[0] = w[1] = w[2] = 0; }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { s_ids[3 * threadIdx.x + k] = ids[k]; s_w[3 * threadIdx.x + k] = w[k]; }
-        if (tex && pix < npix) {
-            // op/rasterize.py:29-37: sum_k tex[ids_k] * bary_k  (background: row 0 times 0 = 0)
-            for (int ch = 0; ch < c; ++ch) {
-                T v = 0;
-                if (hit) v = tex[ids[0] * c + ch] * w[0] + tex[ids[1] * c + ch] * w[1] + tex[ids[2] * c + ch] * w[2];
-                if (stage_out) s_out[threadIdx.x * c + ch] = v;
-                else out[pix * c + ch] = v;
-            }
-        }
-        __syncthreads();
-        stream_out<int4>(ids_out + pix0 * 3, s_ids, count * 3 * (int)sizeof(int64_t), vec_ok);
-        stream_out<int4>(bary_out + pix0 * 3, s_w, count * 3 * (int)sizeof(T), vec_ok);
-        if (stage_out) stream_out<int4>(out + pix0 * c, s_out, count * c * (int)sizeof(T), vec_ok && ((pix0 * c * (int64_t)sizeof(T)) % 16 == 0));
-        __syncthreads();
+        int l = 0;
+        while (blk >= L.blk_off[l + 1]) ++l;                 // CTA-uniform
+        RasterGeom g = g0;
+        g.h = g.w = L.size[l];
+        const int64_t npix = g.b * g.h * (int64_t)g.w;
+        resolve_block<T, true>(g, verts, tris, zkeys + L.key_off[l], nullptr, eps, L.ids[l], L.bary[l], tex, c, L.out[l],
+                               vec_ok, blk - L.blk_off[l], npix, st);
     }
 }
 
@@ -432,6 +528,41 @@ raster_dcoeff_kernel(int64_t b, int64_t n, int h, int w, int perspective, const 
 
 // Fused backward: no dcoeff tensor, no sparse matrix -- contract in registers, scatter with atomics.
 template <typename T>
+__device__ __forceinline__ void backward_pixel(int64_t b, int64_t n, int h, int w, int c, int perspective,
+                                               const T *__restrict__ verts, const T *__restrict__ tex,
+                                               const int64_t *__restrict__ ids, const T *__restrict__ bary,
+                                               const T *__restrict__ gout, T *__restrict__ grad_v, T *__restrict__ grad_tex,
+                                               T eps, int64_t pix)
+{
+    const T w0 = bary[3 * pix], w1 = bary[3 * pix + 1], w2 = bary[3 * pix + 2];
+    if (w0 == (T)0 && w1 == (T)0 && w2 == (T)0) return;                 // background
+    const int64_t I[3] = {ids[3 * pix], ids[3 * pix + 1], ids[3 * pix + 2]};
+    const T wk[3] = {w0, w1, w2};
+    T diff[3] = {0, 0, 0};
+    for (int ch = 0; ch < c; ++ch) {
+        const T gc = gout[pix * c + ch];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            diff[k] += gc * __ldg(tex + I[k] * c + ch);
+            if (grad_tex) atomicAdd(grad_tex + I[k] * c + ch, gc * wk[k]);
+        }
+    }
+    if (!grad_v) return;
+    T q[9], d[27];
+    if (!gather_pixel_tri<T>(verts, I, n * b, q)) return;
+    const int rem = (int)(pix % (h * (int64_t)w));
+    if (!bary_grad<T>(q, (T)(rem % w), (T)(rem / w), (T)h, (T)w, perspective != 0, eps, d)) return;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (a == 2 && !perspective) continue;                       // d/dz is exactly 0 in orthographic mode
+            const T s = diff[0] * d[k * 3 + a] + diff[1] * d[9 + k * 3 + a] + diff[2] * d[18 + k * 3 + a];
+            atomicAdd(grad_v + I[k] * 3 + a, s);
+        }
+}
+
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
 raster_backward_kernel(int64_t b, int64_t n, int h, int w, int c, int perspective, const T *__restrict__ verts,
                        const T *__restrict__ tex, const int64_t *__restrict__ ids, const T *__restrict__ bary,
@@ -439,33 +570,26 @@ raster_backward_kernel(int64_t b, int64_t n, int h, int w, int c, int perspectiv
 {
     const int64_t npix = b * h * (int64_t)w;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
-    for (int64_t pix = (int64_t)blockIdx.x * kThreads + threadIdx.x; pix < npix; pix += stride) {
-        const T w0 = bary[3 * pix], w1 = bary[3 * pix + 1], w2 = bary[3 * pix + 2];
-        if (w0 == (T)0 && w1 == (T)0 && w2 == (T)0) continue;           // background
-        const int64_t I[3] = {ids[3 * pix], ids[3 * pix + 1], ids[3 * pix + 2]};
-        const T wk[3] = {w0, w1, w2};
-        T diff[3] = {0, 0, 0};
-        for (int ch = 0; ch < c; ++ch) {
-            const T gc = gout[pix * c + ch];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                diff[k] += gc * __ldg(tex + I[k] * c + ch);
-                if (grad_tex) atomicAdd(grad_tex + I[k] * c + ch, gc * wk[k]);
-            }
-        }
-        if (!grad_v) continue;
-        T q[9], d[27];
-        if (!gather_pixel_tri<T>(verts, I, n * b, q)) continue;
-        const int rem = (int)(pix % (h * (int64_t)w));
-        if (!bary_grad<T>(q, (T)(rem % w), (T)(rem / w), (T)h, (T)w, perspective != 0, eps, d)) continue;
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                if (a == 2 && !perspective) continue;                   // d/dz is exactly 0 in orthographic mode
-                const T s = diff[0] * d[k * 3 + a] + diff[1] * d[9 + k * 3 + a] + diff[2] * d[18 + k * 3 + a];
-                atomicAdd(grad_v + I[k] * 3 + a, s);
-            }
+    for (int64_t pix = (int64_t)blockIdx.x * kThreads + threadIdx.x; pix < npix; pix += stride)
+        backward_pixel<T>(b, n, h, w, c, perspective, verts, tex, ids, bary, gout, grad_v, grad_tex, eps, pix);
+}
+
+// every level of a pyramid scatters into the SAME grad_v / grad_tex (the sum autograd would form from per-level calls)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+raster_backward_pyramid_kernel(int64_t b, int64_t n, const Pyramid<T> L, int c, int perspective,
+                               const T *__restrict__ verts, const T *__restrict__ tex, T *__restrict__ grad_v,
+                               T *__restrict__ grad_tex, T eps)
+{
+    const int64_t nblk = L.blk_off[L.n];
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        int l = 0;
+        while (blk >= L.blk_off[l + 1]) ++l;
+        const int size = L.size[l];
+        const int64_t pix = (blk - L.blk_off[l]) * kThreads + threadIdx.x;
+        if (pix < b * size * (int64_t)size)
+            backward_pixel<T>(b, n, size, size, c, perspective, verts, tex, L.ids[l], L.bary[l], L.gout[l], grad_v, grad_tex,
+                              eps, pix);
     }
 }
 
@@ -552,10 +676,114 @@ int rasterize_backward(int64_t b, int64_t n, int64_t h, int64_t w, int64_t c, in
     return check_launch("sr_rasterize_backward");
 }
 
+// levels -> device table; `backward` keeps only the levels that carry a gradient
+template <typename T>
+int build_pyramid(Pyramid<T> &L, int64_t b, int n_levels, const sr_raster_level *levels, bool backward, bool &vec_ok)
+{
+    SR_REQUIRE(n_levels >= 1 && n_levels <= kMaxLevels && levels, "rasterize_pyramid: 1..SR_RASTER_MAX_LEVELS levels");
+    L.n = 0;
+    L.blk_off[0] = 0;
+    int64_t keys = 0;
+    uintptr_t bits = 0;
+    for (int i = 0; i < n_levels; ++i) {
+        const sr_raster_level &lv = levels[i];
+        SR_REQUIRE(lv.size >= 1 && lv.size <= 32768, "rasterize_pyramid: bad level size");
+        const int64_t npix = b * lv.size * lv.size;
+        if (backward && !lv.gout) continue;
+        SR_REQUIRE(lv.ids && lv.bary, "rasterize_pyramid: null ids / bary");
+        const int l = L.n++;
+        L.size[l] = (int)lv.size;
+        L.key_off[l] = keys;
+        L.blk_off[l + 1] = L.blk_off[l] + (npix + kThreads - 1) / kThreads;
+        L.ids[l] = lv.ids;
+        L.bary[l] = reinterpret_cast<T *>(lv.bary);
+        L.out[l] = reinterpret_cast<T *>(lv.out);
+        L.gout[l] = reinterpret_cast<const T *>(lv.gout);
+        keys += npix;
+        bits |= reinterpret_cast<uintptr_t>(lv.ids) | reinterpret_cast<uintptr_t>(lv.bary) | reinterpret_cast<uintptr_t>(lv.out);
+    }
+    vec_ok = (bits & 15u) == 0;
+    return SR_OK;
+}
+
+int rasterize_pyramid_forward(int64_t b, int64_t nv, int64_t nf, int n_levels, const sr_raster_level *levels, int shared_v,
+                              int shared_f, int perspective, const float *verts, const int64_t *tris, uint64_t *keys,
+                              float eps, const float *tex, int64_t c, void *stream)
+{
+    SR_REQUIRE(b >= 0 && nv >= 0 && nf >= 0, "rasterize_pyramid: bad sizes");
+    SR_REQUIRE(nf < 0xffffffffll, "rasterize_pyramid: too many triangles");
+    if (b == 0) return SR_OK;
+    Pyramid<float> L;
+    bool vec_ok = false;
+    if (int rc = build_pyramid<float>(L, b, n_levels, levels, false, vec_ok)) return rc;
+    SR_REQUIRE(keys, "rasterize_pyramid: null workspace");
+    for (int l = 0; l < L.n; ++l) SR_REQUIRE(!tex || L.out[l], "rasterize_pyramid: tex given without out");
+    SR_REQUIRE(!tex || c >= 1, "rasterize_pyramid: tex given without channels");
+    cudaStream_t st = (cudaStream_t)stream;
+    RasterGeom g;
+    g.b = b; g.nv = nv; g.nf = nf; g.h = g.w = 0;
+    g.shared_v = shared_v; g.shared_f = shared_f; g.perspective = perspective;
+    if (eps < 0) eps = -eps;
+    const int64_t nkeys = L.key_off[L.n - 1] + b * (int64_t)L.size[L.n - 1] * L.size[L.n - 1];
+    cudaError_t e = cudaMemsetAsync(keys, 0, sizeof(uint64_t) * (size_t)nkeys, st);
+    if (e != cudaSuccess) { set_error("rasterize_pyramid: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    if (nf > 0 && verts && tris) {
+        SR_REQUIRE(b <= 65535, "rasterize_pyramid: batch too large for one launch");
+        int gx = grid_for(nf, 16);
+        const int per_img = (int)((int64_t)kNumSMs * 16 / b);
+        if (gx > per_img) gx = per_img < 1 ? 1 : per_img;
+        raster_tri_pyramid_kernel<float><<<dim3((unsigned)gx, (unsigned)b), kThreads, 0, st>>>(g, L, verts, tris, keys, eps);
+        count_launch();
+    }
+    const int64_t nblk = L.blk_off[L.n];
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    raster_resolve_pyramid_kernel<float><<<(unsigned)(nblk < cap ? nblk : cap), kThreads, 0, st>>>(
+        g, L, verts, tris, keys, eps, tex, (int)c, vec_ok ? 1 : 0);
+    count_launch();
+    return check_launch("sr_rasterize_pyramid_forward_f32");
+}
+
+int rasterize_pyramid_backward(int64_t b, int64_t n, int n_levels, const sr_raster_level *levels, int64_t c, int perspective,
+                               const float *verts, const float *tex, float *grad_v, float *grad_tex, float eps, void *stream)
+{
+    SR_REQUIRE(b >= 0 && n >= 0 && c >= 1, "rasterize_pyramid_backward: bad sizes");
+    if (b == 0 || (!grad_v && !grad_tex)) return SR_OK;
+    Pyramid<float> L;
+    bool vec_ok = false;
+    if (int rc = build_pyramid<float>(L, b, n_levels, levels, true, vec_ok)) return rc;
+    if (L.n == 0) return SR_OK;                               // no level carries a gradient
+    SR_REQUIRE(verts && tex, "rasterize_pyramid_backward: null pointer");
+    if (eps < 0) eps = -eps;
+    const int64_t nblk = L.blk_off[L.n];
+    const int64_t cap = (int64_t)kNumSMs * 16;
+    raster_backward_pyramid_kernel<float><<<(unsigned)(nblk < cap ? nblk : cap), kThreads, 0, (cudaStream_t)stream>>>(
+        b, n, L, (int)c, perspective, verts, tex, grad_v, grad_tex, eps);
+    count_launch();
+    return check_launch("sr_rasterize_pyramid_backward_f32");
+}
+
 }  // namespace
 }  // namespace sr
 
 using namespace sr;
+
+extern "C" int64_t sr_rasterize_pyramid_workspace_bytes(int64_t b, int n_levels, const int64_t *sizes) {
+    int64_t npix = 0;
+    for (int i = 0; i < n_levels; ++i) npix += b * sizes[i] * sizes[i];
+    return npix * 8 + 16;
+}
+extern "C" int sr_rasterize_pyramid_forward_f32(int64_t b, int64_t nv, int64_t nf, int n_levels,
+                                                const sr_raster_level *levels, int shared_v, int shared_f, int perspective,
+                                                const float *verts, const int64_t *tris, uint64_t *keys, float eps,
+                                                const float *tex, int64_t c, void *stream) {
+    return rasterize_pyramid_forward(b, nv, nf, n_levels, levels, shared_v, shared_f, perspective, verts, tris, keys, eps, tex,
+                                     c, stream);
+}
+extern "C" int sr_rasterize_pyramid_backward_f32(int64_t b, int64_t n, int n_levels, const sr_raster_level *levels, int64_t c,
+                                                 int perspective, const float *verts, const float *tex, float *grad_verts,
+                                                 float *grad_tex, float eps, void *stream) {
+    return rasterize_pyramid_backward(b, n, n_levels, levels, c, perspective, verts, tex, grad_verts, grad_tex, eps, stream);
+}
 
 extern "C" int64_t sr_rasterize_workspace_bytes(int64_t b, int64_t h, int64_t w, int is_f64) {
     const int64_t npix = b * h * w;

@@ -14,7 +14,8 @@ from torch import nn
 from . import fused, layers
 from .layers import (ConstantInput, ConvLayer, EqualLinear, ModulatedConv2d, NoiseInjection, PixelNorm, ResBlock,
                      Upsample)
-from .op import FusedLeakyReLU, rasterize
+from .op import FusedLeakyReLU, rasterize, rasterize_pyramid
+from .op.rasterize import MAX_LEVELS
 
 
 class StyledConv(nn.Module):                          # reference model.py:11-32
@@ -185,6 +186,16 @@ class GeneratorWithMap(Generator):                    # reference model.py:188-2
             self.to_rgbs.append(ToRGB(out_channel, style_dim))
             in_channel = out_channel
 
+    def _normal_maps(self, mesh):
+        """The rasterised normal map at every resolution 4, 8, ..., size as [B,3,r,r] views (reference model.py:260-270
+        calls rasterize once per resolution; here all of them come from one pyramid launch set, same values)."""
+        sizes = [2 ** i for i in range(2, self.log_size + 1)]
+        if mesh[0].dtype == torch.float32 and len(sizes) <= MAX_LEVELS:
+            maps = rasterize_pyramid(mesh[0], mesh[1], mesh[2], sizes)
+        else:
+            maps = [rasterize(mesh[0], mesh[1], mesh[2], r, r) for r in sizes]
+        return [m.permute(0, 3, 1, 2) for m in maps]
+
     def forward(self, styles, mesh, return_normals=False, return_latents=False, inject_index=None, truncation=1,
                 truncation_latent=None, input_is_latent=False, noise=None, randomize_noise=True):
         latent, noise = self._prepare(styles, inject_index, truncation, truncation_latent, input_is_latent, noise,
@@ -194,10 +205,13 @@ class GeneratorWithMap(Generator):                    # reference model.py:188-2
             # evaluated per resolution exactly as below and handed to the blocks' epilogues
             norm_maps, cache = [], {}
 
+            normals = self._normal_maps(mesh)
+
             def maps_fn(k, h, w):
                 j = (k + 1) // 2                                         # resolution index: block 0 -> 0, blocks 1,2 -> 1, ...
                 if j not in cache:
-                    nm = rasterize(mesh[0], mesh[1], mesh[2], h, w).permute(0, 3, 1, 2)
+                    nm = normals[j]
+                    assert nm.shape[2] == h and nm.shape[3] == w
                     norm_maps.append(nm)
                     if j == 0:
                         cache[j] = self.norm1(nm)
@@ -213,15 +227,15 @@ class GeneratorWithMap(Generator):                    # reference model.py:188-2
             skip = fused.generator_chain_forward(self, latent, noise, maps_fn)
             return skip, (latent if return_latents else None), (norm_maps if return_normals else None)
         out = self.input(latent)
-        norm_maps = [rasterize(mesh[0], mesh[1], mesh[2], int(out.shape[2]), int(out.shape[3])).permute(0, 3, 1, 2)]
+        normals = self._normal_maps(mesh)
+        norm_maps = [normals[0]]
         maps = self.norm1(norm_maps[-1])
         out = self.conv1(out, latent[:, 0], maps, noise=noise[0])
         skip = self.to_rgb1(out, latent[:, 1])
         i = 1
         for conv1, conv2, noise1, noise2, to_rgb in zip(self.convs[::2], self.convs[1::2], noise[1::2], noise[2::2],
                                                         self.to_rgbs):
-            norm_maps.append(rasterize(mesh[0], mesh[1], mesh[2], 2 * int(out.shape[2]),
-                                       2 * int(out.shape[3])).permute(0, 3, 1, 2))
+            norm_maps.append(normals[len(norm_maps)])
             if len(self.convs) == len(self.norm_to_style):              # reference model.py:271-275
                 maps = self.norm_to_style[i](self.norm_to_style[i - 1](norm_maps[-1]))
             else:

@@ -7,6 +7,8 @@ the resolve kernel, and the backward contracts d(coeff)/d(vertex) in registers a
 atomics instead of materialising a [b,h,w,3,9] tensor and a host-built sparse matrix
 (reference op/rasterize.py:39-80).
 """
+import ctypes
+
 import torch
 from torch.autograd import Function
 
@@ -139,3 +141,87 @@ def rasterize(v, tex, tri, h=256, w=0, perspective=False, eps=1e-6, return_buffe
     _lib.require_cuda(v, "rasterize")
     out, ind, coeff = Rasterize.apply(v, tex, tri, h, w, perspective, eps)
     return (out, ind, coeff) if return_buffers else out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Resolution pyramid: the same mesh at several square sizes in one triangle pass / resolve pass / scatter pass
+# (sr_rasterize_pyramid_*; GeneratorWithMap renders 4, 8, ..., 256 every forward, reference model.py:260-270).
+MAX_LEVELS = 8
+
+
+class RasterLevel(ctypes.Structure):                 # mirrors `sr_raster_level` in include/stylerenderer_b200.h
+    _fields_ = [("size", ctypes.c_int64), ("ids", ctypes.c_void_p), ("bary", ctypes.c_void_p), ("out", ctypes.c_void_p),
+                ("gout", ctypes.c_void_p)]
+
+
+def _levels(sizes, inds, coeffs, outs=None, gouts=None):
+    arr = (RasterLevel * len(sizes))()
+    for i, sz in enumerate(sizes):
+        a = arr[i]
+        a.size, a.ids, a.bary = int(sz), _lib.ptr(inds[i]), _lib.ptr(coeffs[i])
+        a.out = _lib.ptr(outs[i]) if outs is not None else None
+        a.gout = _lib.ptr(gouts[i]) if gouts is not None else None
+    return arr
+
+
+class RasterizePyramid(Function):
+    """(v, tex, tri) -> one interpolated map [b,s,s,c] per size s, each bit-identical to `Rasterize` at that size."""
+
+    @staticmethod
+    def forward(ctx, v, tex, tri, sizes, perspective, eps):
+        _lib.require_cuda(v, "rasterize_pyramid")
+        if v.dtype != torch.float32:
+            raise RuntimeError("rasterize_pyramid: float32 vertices only (use rasterize() per size for float64)")
+        if not 1 <= len(sizes) <= MAX_LEVELS:
+            raise RuntimeError(f"rasterize_pyramid: 1..{MAX_LEVELS} sizes")
+        ctx.set_materialize_grads(False)
+        scalar_tex = tex.dim() == v.dim() - 1
+        c = 1 if scalar_tex else int(tex.shape[-1])
+        tex = tex.to(v.dtype).contiguous()
+        vc, tric = v.contiguous(), tri.contiguous()
+        dev = vc.device
+        inds, coeffs, outs = [], [], []
+        b = nv = nf = shared_v = shared_f = None
+        for sz in sizes:
+            b, nv, nf, h, w, shared_v, shared_f, lead = _problem(vc, tric, sz, sz)
+            inds.append(torch.empty(*lead, 3, dtype=torch.int64, device=dev))
+            coeffs.append(torch.empty(*lead, 3, dtype=vc.dtype, device=dev))
+            outs.append(torch.empty(*lead, c, dtype=vc.dtype, device=dev))
+        L = _lib.lib()
+        csz = (ctypes.c_int64 * len(sizes))(*[int(s) for s in sizes])
+        ws = torch.empty(L.sr_rasterize_pyramid_workspace_bytes(b, len(sizes), csz) // 8 + 1, dtype=torch.int64, device=dev)
+        arr = _levels(sizes, inds, coeffs, outs)
+        with torch.cuda.device(dev):
+            rc = L.sr_rasterize_pyramid_forward_f32(b, nv, nf, len(sizes), arr, int(shared_v), int(shared_f),
+                                                    int(bool(perspective)), _lib.ptr(vc), _lib.ptr(tric), _lib.ptr(ws),
+                                                    abs(float(eps)), _lib.ptr(tex), c, _lib.stream_of(vc))
+        _lib.check(rc, "sr_rasterize_pyramid_forward_f32")
+        ctx.save_for_backward(vc, tex, *inds, *coeffs)
+        ctx.cfg = (tuple(int(s) for s in sizes), bool(perspective), float(eps), c, b)
+        return tuple(o[..., 0] if scalar_tex else o for o in outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        sizes, perspective, eps, c, b = ctx.cfg
+        saved = ctx.saved_tensors
+        vc, tex = saved[0], saved[1]
+        n_lv = len(sizes)
+        inds, coeffs = saved[2:2 + n_lv], saved[2 + n_lv:2 + 2 * n_lv]
+        need_v, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_v or need_t) or all(g is None for g in grads):
+            return (None,) * 6
+        gouts = [g.to(vc.dtype).contiguous() if g is not None else None for g in grads]
+        grad_v = torch.zeros_like(vc) if need_v else None
+        grad_t = torch.zeros_like(tex) if need_t else None
+        arr = _levels(sizes, inds, coeffs, None, gouts)
+        with torch.cuda.device(vc.device):
+            rc = _lib.lib().sr_rasterize_pyramid_backward_f32(b, vc.shape[-2], n_lv, arr, c, int(perspective), _lib.ptr(vc),
+                                                              _lib.ptr(tex), _lib.ptr(grad_v), _lib.ptr(grad_t),
+                                                              abs(eps), _lib.stream_of(vc))
+        _lib.check(rc, "sr_rasterize_pyramid_backward_f32")
+        return grad_v, grad_t, None, None, None, None
+
+
+def rasterize_pyramid(v, tex, tri, sizes, perspective=False, eps=1e-6):
+    """[rasterize(v, tex, tri, s) for s in sizes] in three launches instead of 3 * len(sizes) (same values, bit for bit)."""
+    return list(RasterizePyramid.apply(v, tex, tri, tuple(sizes), perspective, eps))

@@ -353,3 +353,111 @@ def test_rasterize_config3_full_size(op):
     # depth check: z = sum coeff * v_z is the max over all candidate triangles -> re-rendering is idempotent
     out2, ind2, coeff2 = op.rasterize(vc, tc, fc, 256, return_buffers=True)
     assert torch.equal(ind, ind2) and torch.equal(coeff, coeff2) and torch.equal(out, out2)
+
+
+# ----------------------------------------------------------------------------------- rasterize pyramid
+PYRAMID_SIZES = [4, 8, 16, 32, 64, 128, 256]
+
+
+@pytest.mark.parametrize("perspective", [False, True])
+def test_rasterize_pyramid_bit_exact_vs_oracle_and_single_size(op, perspective):
+    """sr_rasterize_pyramid_forward_f32: every level of the GeneratorWithMap pyramid (reference model.py:260-270) must be
+    bit-identical to the oracle's rasterize_cpu restatement at that size -- ids, coefficients -- and to the single-size
+    kernel including the interpolated attributes."""
+    from stylerenderer_b200.op.rasterize import RasterizePyramid
+    v, tri = grid_mesh(40, 3, 3100)
+    if perspective:
+        v[..., 2] -= 3
+    tex = seeded((3, 1600, 3), 3101)
+    vc, tc, fc = cuda(v), cuda(tex), cuda(tri)
+    outs = op.rasterize_pyramid(vc, tc, fc, PYRAMID_SIZES, perspective)
+    assert [tuple(o.shape) for o in outs] == [(3, s, s, 3) for s in PYRAMID_SIZES]
+    for s, o in zip(PYRAMID_SIZES, outs):
+        out1, ind1, coeff1 = op.rasterize(vc, tc, fc, s, 0, perspective, return_buffers=True)
+        assert torch.equal(o, out1), s
+        ind_w, coeff_w, _ = O.rasterize_forward(v, tri, s, 0, perspective, 1e-6)
+        assert torch.equal(ind1.cpu(), ind_w) and torch.equal(coeff1.cpu(), coeff_w), s
+    # the buffers the pyramid itself wrote (saved for its backward), not only the interpolated maps
+    vr = vc.clone().requires_grad_(True)
+    outs = RasterizePyramid.apply(vr, tc, fc, tuple(PYRAMID_SIZES), perspective, 1e-6)
+    saved = outs[0].grad_fn.saved_tensors
+    inds, coeffs = saved[2:2 + len(PYRAMID_SIZES)], saved[2 + len(PYRAMID_SIZES):]
+    for s, ind, coeff in zip(PYRAMID_SIZES, inds, coeffs):
+        ind_w, coeff_w, _ = O.rasterize_forward(v, tri, s, 0, perspective, 1e-6)
+        assert torch.equal(ind.cpu(), ind_w) and torch.equal(coeff.cpu(), coeff_w), s
+
+
+def test_rasterize_pyramid_edge_cases(op):
+    g = torch.Generator().manual_seed(6)
+    v = torch.rand(2, 50, 3, generator=g) * 2.6 - 1.3                # soup with big, degenerate and invalid triangles
+    v[:, 10] = v[:, 11]
+    tri = torch.randint(0, 50, (300, 3), generator=g)
+    tri[5] = torch.tensor([10, 11, 20]); tri[6] = torch.tensor([7, 7, 7]); tri[7] = torch.tensor([0, 60, 1])
+    tex = seeded((2, 50), 3)                                          # scalar attribute [b,n]
+    sizes = [1, 7, 33, 128]                                           # any square sizes, not only powers of two
+    outs = op.rasterize_pyramid(cuda(v), cuda(tex), cuda(tri), sizes)
+    for s, o in zip(sizes, outs):
+        assert o.shape == (2, s, s)
+        assert torch.equal(o, op.rasterize(cuda(v), cuda(tex), cuda(tri), s)), s
+    # per-batch triangle lists, the unbatched form, an empty mesh, a single level
+    trib = torch.stack([tri, tri.flip(0)])
+    for vv, ff, tt in [(v, trib, tex), (v[0], tri, tex[0])]:
+        outs = op.rasterize_pyramid(cuda(vv), cuda(tt), cuda(ff), [8, 16])
+        for s, o in zip([8, 16], outs):
+            assert torch.equal(o, op.rasterize(cuda(vv), cuda(tt), cuda(ff), s))
+    empty = op.rasterize_pyramid(cuda(v), cuda(tex), torch.zeros(0, 3, dtype=torch.int64, device="cuda"), [4, 8])
+    assert all(float(o.abs().sum()) == 0 for o in empty)
+    one, = op.rasterize_pyramid(cuda(v), cuda(tex), cuda(tri), [16])
+    assert torch.equal(one, op.rasterize(cuda(v), cuda(tex), cuda(tri), 16))
+    with pytest.raises(RuntimeError):
+        op.rasterize_pyramid(cuda(v), cuda(tex), cuda(tri), list(range(1, 10)))      # more than SR_RASTER_MAX_LEVELS
+    with pytest.raises(RuntimeError):
+        op.rasterize_pyramid(v, tex, tri, [8])                                       # CPU tensors: no fallback
+    with pytest.raises(RuntimeError):
+        op.rasterize_pyramid(cuda(v).double(), cuda(tex).double(), cuda(tri), [8])   # float32 only
+
+
+def test_rasterize_pyramid_backward_is_the_sum_of_the_levels(op):
+    """One scatter launch for all levels = the sum of the per-size backward passes (oracle: O.rasterize_grads per level);
+    levels without a gradient take no part."""
+    v, tri = grid_mesh(30, 2, 87)
+    tex = seeded((2, 900, 3), 88)
+    sizes = [4, 16, 48, 64]
+    gos = [seeded((2, s, s, 3), 90 + i) for i, s in enumerate(sizes)]
+    gv_w, gt_w = torch.zeros_like(v), torch.zeros_like(tex)
+    for s, go in zip(sizes, gos):
+        if s == 16:
+            continue                                                   # this level's output is unused below
+        out_w, ind_w, coeff_w = O.rasterize(v, tex, tri, s)
+        a, b_ = O.rasterize_grads(v, tex, ind_w, coeff_w, go)
+        gv_w += a
+        gt_w += b_
+    vc, tc = cuda(v).requires_grad_(True), cuda(tex).requires_grad_(True)
+    outs = op.rasterize_pyramid(vc, tc, cuda(tri), sizes)
+    used = [(o, go) for s, o, go in zip(sizes, outs, gos) if s != 16]
+    gv, gt = torch.autograd.grad([o for o, _ in used], (vc, tc), [cuda(go) for _, go in used])
+    torch.testing.assert_close(gv.cpu(), gv_w, rtol=1e-3, atol=1e-4 * float(gv_w.abs().max()))
+    torch.testing.assert_close(gt.cpu(), gt_w, rtol=1e-3, atol=1e-4 * float(gt_w.abs().max()))
+    # only the vertex gradient / only the attribute gradient
+    outs = op.rasterize_pyramid(vc, tc.detach(), cuda(tri), sizes)
+    gv2, = torch.autograd.grad(outs, (vc,), [cuda(go) for go in gos])
+    outs = op.rasterize_pyramid(vc.detach(), tc, cuda(tri), sizes)
+    gt2, = torch.autograd.grad(outs, (tc,), [cuda(go) for go in gos])
+    assert gv2.shape == v.shape and gt2.shape == tex.shape and float(gv2.abs().max()) > 0 and float(gt2.abs().max()) > 0
+
+
+def test_rasterize_pyramid_config3_mesh(op):
+    """BFM-size mesh (35 721 verts / 70 688 tris), batch 8, the seven GeneratorWithMap sizes: identical to seven
+    single-size calls, in 3 launches instead of 21."""
+    from stylerenderer_b200 import _lib
+    v, tri = grid_mesh(189, 8, 4242, jitter=0.002)
+    tex = torch.nn.functional.normalize(seeded((8, 189 * 189, 3), 4243), dim=-1)
+    vc, tc, fc = cuda(v), cuda(tex), cuda(tri)
+    n0 = _lib.launch_count()
+    outs = op.rasterize_pyramid(vc, tc, fc, PYRAMID_SIZES)
+    n1 = _lib.launch_count()
+    singles = [op.rasterize(vc, tc, fc, s) for s in PYRAMID_SIZES]
+    n2 = _lib.launch_count()
+    for s, o, o1 in zip(PYRAMID_SIZES, outs, singles):
+        assert torch.equal(o, o1), s
+    assert n1 - n0 == 2 and n2 - n1 == 2 * len(PYRAMID_SIZES), (n1 - n0, n2 - n1)
