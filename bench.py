@@ -81,7 +81,7 @@ class ClockSampler:
                     self.samples.append(f)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._t.start()
@@ -150,6 +150,18 @@ def algorithmic_bytes(name, a):
     if name == "sr_blur_nhwc_styled_f32":
         b, ih, iw, c, p0, p1 = a[3], a[4], a[5], a[6], a[7], a[8]
         return 4 * b * c * (ih * iw + (ih + p0 + p1 - 3) * (iw + p0 + p1 - 3))
+    if name == "sr_blur_nhwc_styled3_f32":              # x -> y (+ the next layer's tf32 operand)
+        b, ih, iw, c, p0, p1 = a[5:11]
+        return 4 * b * c * (ih * iw + (ih + p0 + p1 - 3) * (iw + p0 + p1 - 3) * (2 if a[1] else 1))
+    if name == "sr_blur_nhwc_scaledot_f32":             # g -> tf32 operand (+ one more read when the dot product is asked for)
+        b, ih, iw, c, p0, p1 = a[6:12]
+        return 4 * b * c * (ih * iw + (ih + p0 + p1 - 3) * (iw + p0 + p1 - 3) * (2 if a[5] else 1))
+    if name in ("sr_styled_bwd_prologue2_f32", "sr_styled_bwd_prologue3_f32"):
+        return 12 * a[17] * a[18] * a[19]               # read the gradient source and y, write the GEMM operand
+    if name == "sr_conv_weight_prep_dual_tf32":
+        return 4 * a[5] * a[6] * a[7] * (1 + (1 if a[0] else 0) + (1 if a[1] else 0))
+    if name == "sr_weight_grad_layout_f32":
+        return 8 * a[3] * a[4] * a[5]
     if name == "sr_modulate_tf32":
         return 8 * a[3] * a[4] * a[5]
     if name == "sr_styled_bwd_prologue_f32":
@@ -208,6 +220,15 @@ def dominant_kernel_roofline(stats, peaks, total_ms, steps):
               "share_of_step": round(ms / total_ms, 4) if total_ms else None, "traffic": ncu_traffic(sig),
               "traffic_source": "profiles/r1_ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
               "all_kernels_ms_per_step": {n: round(v / steps, 4) for n, v in tot.items()}}
+    # the bandwidth-bound passes of the step against the measured copy bandwidth (BASELINE metric: "HBM GB/s vs roofline")
+    hbm = {}
+    for n, kcalls in stats.items():
+        by_n = sum(algorithmic_bytes(n, a) for a, _ in kcalls)
+        ms_n = sum(m for _, m in kcalls)
+        if by_n and ms_n > 0:
+            gbs = by_n / (ms_n * 1e-3) / 1e9
+            hbm[n] = {"ms_per_step": round(ms_n / steps, 4), "GBps": round(gbs, 1), "frac": round(gbs / peaks["hbm_gbs"], 4)}
+    common["hbm_kernels"] = hbm
     fl = sum(algorithmic_flops(name, a) for a, _ in calls)
     if fl:
         # MEASURED_PEAKS.json holds the dense bf16 rate only.  Half of it (tf32 issues at half the bf16 rate) is exceeded
@@ -453,7 +474,7 @@ def run_rasterize(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step (BASELINE config: 32)")
@@ -538,10 +559,10 @@ def main():
     n0 = _lib.launch_count()
     with ClockSampler(local) as clocks:
         ms_eager = timed(step_resident, args.steps)
-    launches = (_lib.launch_count() - n0) // args.steps
-    for _ in range(2):
-        step_e2e()
-    ms_e2e_eager = timed(step_e2e, args.steps)
+        launches = (_lib.launch_count() - n0) // args.steps
+        for _ in range(2):
+            step_e2e()
+        ms_e2e_eager = timed(step_e2e, args.steps)
 
     # ---- the same step captured once as a CUDA graph and replayed (removes ~1300 host launches per step)
     ms, ms_e2e, graphed = ms_eager, ms_e2e_eager, False
@@ -570,9 +591,9 @@ def main():
 
             for _ in range(3):
                 step_graph()
-            with ClockSampler(local) as clocks:
+            with ClockSampler(local) as clocks:             # sampled over both timed regions (device-resident and e2e)
                 ms = timed(step_graph, args.steps)
-            ms_e2e = timed(step_graph_e2e, args.steps)
+                ms_e2e = timed(step_graph_e2e, args.steps)
             graphed = True
         except Exception as ex:                         # report, never hide: fall back to the eager numbers
             print(f"[bench] CUDA graph capture failed, reporting eager timings: {ex!r}", file=sys.stderr)
