@@ -225,7 +225,7 @@ def dominant_kernel_roofline(stats, peaks, total_ms, steps):
     for n, kcalls in stats.items():
         by_n = sum(algorithmic_bytes(n, a) for a, _ in kcalls)
         ms_n = sum(m for _, m in kcalls)
-        if by_n and ms_n > 0:
+        if by_n and ms_n / steps >= 0.1:                 # launch-latency-bound calls on [B,512] vectors say nothing about HBM
             gbs = by_n / (ms_n * 1e-3) / 1e9
             hbm[n] = {"ms_per_step": round(ms_n / steps, 4), "GBps": round(gbs, 1), "frac": round(gbs / peaks["hbm_gbs"], 4)}
     common["hbm_kernels"] = hbm
