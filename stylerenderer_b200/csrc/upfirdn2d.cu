@@ -615,6 +615,207 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
     }
 }
 
+// ---- channels-last FIR, row-streaming form (default) ------------------------------------------------------------------
+// Same thread decomposition and tails as upfirdn2d_nhwc_kernel (4 channels x 2 columns x a strip of rows), but the
+// input rows flow through a ring of the KH open output rows instead of a KH x (KW+1) input window: a thread keeps
+// 4 x 2 accumulators + the 5 pixels of the current row (52 instead of 100 vector registers' worth of state), so more
+// CTAs fit and more loads are in flight -- the kernel was latency bound (ncu: sm 54 %, DRAM 50 %, occupancy 24 %).
+// Rank-1 taps (every FIR the model builds is an outer product, reference layers.py:7-12) take the separable form: 4
+// FMAs for the row filter + 4 to scatter it over the open rows = 8 instead of 16 per output (checked on the device,
+// like upfirdn2d_tile_kernel); general taps accumulate in the same (a, b) order as the 2-D kernel (bit-identical).
+// PF: the next input row is loaded before the current one is consumed (two rows in flight per thread); MINB = CTAs per SM
+// the register allocation is bounded for.
+template <int MODE, bool PF, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+fir_nhwc_ring_kernel(float *__restrict__ out, const float *__restrict__ x, const float *__restrict__ taps, const NhwcGeom g)
+{
+    constexpr int K = 4;
+    constexpr bool STYLED = (MODE == 1);
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (tid >= g.total_threads) return;
+    uint32_t t = (uint32_t)tid, c, xp, ys, n;
+    g.div_c4.divmod(t, t, c);
+    g.div_pairs.divmod(t, t, xp);
+    g.div_strips.divmod(t, n, ys);
+
+    // flipped taps tk[a][b] = taps[K-1-a][K-1-b]; rank-1 factorisation tk[a][b] = kv[a] * kh[b] through the largest tap
+    float kv[K], kh[K];
+    bool sep;
+    {
+        float tk[K][K];
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+#pragma unroll
+            for (int b = 0; b < K; ++b) tk[a][b] = __ldg(taps + (K - 1 - a) * K + (K - 1 - b));
+        int pa = 0, pb = 0;
+        float best = 0.0f;
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+#pragma unroll
+            for (int b = 0; b < K; ++b)
+                if (fabsf(tk[a][b]) > best) { best = fabsf(tk[a][b]); pa = a; pb = b; }
+        float pivot = 1.0f;
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+#pragma unroll
+            for (int b = 0; b < K; ++b)
+                if (a == pa && b == pb) pivot = tk[a][b];
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+            kv[a] = 0.0f; kh[a] = 0.0f;
+#pragma unroll
+            for (int b = 0; b < K; ++b) {
+                if (b == pb) kv[a] = tk[a][b];
+                if (b == pa) kh[a] = tk[b][a] / pivot;
+            }
+        }
+        sep = best > 0.0f;
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+#pragma unroll
+            for (int b = 0; b < K; ++b) sep = sep && fabsf(kv[a] * kh[b] - tk[a][b]) <= 1e-6f * best;
+    }
+
+    const int ox0 = xp * 2;
+    const int ix0 = ox0 - g.pad_x0;
+    const int oy0 = ys * g.rows_per_strip;
+    const int oy1 = min(g.out_h, oy0 + g.rows_per_strip);
+    const float4 *xin = reinterpret_cast<const float4 *>(x) + (int64_t)n * g.in_h * g.in_w * g.c4 + c;
+    float4 *yout = reinterpret_cast<float4 *>(out) + (int64_t)n * g.out_h * g.out_w * g.c4 + c;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool col1 = ox0 + 1 < g.out_w;
+
+    float nw = 0.0f;
+    float4 bias4 = zero;
+    const float *nz = nullptr;
+    if (STYLED) {
+        if (g.noise) { nw = __ldg(g.noise_weight); nz = g.noise + (int64_t)n * g.noise_bstride; }
+        if (g.bias) bias4 = __ldg(reinterpret_cast<const float4 *>(g.bias) + c);
+    }
+    float4 sc2 = zero;
+    if ((STYLED && g.out2) || MODE == 2) sc2 = __ldg(reinterpret_cast<const float4 *>(g.scale2) + (int64_t)n * g.c4 + c);
+    float4 dot = zero;
+    const float4 *oth = (MODE == 2 && g.other) ? reinterpret_cast<const float4 *>(g.other) + (int64_t)n * g.out_h * g.out_w * g.c4 + c : nullptr;
+
+    float4 acc[K][2];                                      // acc[s]: output row (current - (K-1) + s), still open
+#pragma unroll
+    for (int s = 0; s < K; ++s) { acc[s][0] = zero; acc[s][1] = zero; }
+    const int nsteps = oy1 - oy0 + K - 1;
+    auto load_row = [&](float4 (&row)[K + 1], int iy) {
+        const bool row_ok = iy >= 0 && iy < g.in_h;
+        const float4 *src = xin + (int64_t)iy * g.in_w * g.c4;
+#pragma unroll
+        for (int b = 0; b < K + 1; ++b) {
+            const int ix = ix0 + b;
+            row[b] = (row_ok && ix >= 0 && ix < g.in_w) ? __ldg(src + (int64_t)ix * g.c4) : zero;
+        }
+    };
+    float4 vn[K + 1];
+    if (PF) load_row(vn, oy0 - g.pad_y0);
+#pragma unroll 2
+    for (int r = 0; r < nsteps; ++r) {
+        const int iy = oy0 - g.pad_y0 + r;                 // input row of this step
+        const int oy = oy0 + r - (K - 1);                  // output row this step completes (a strip's first K-1 steps: none)
+        float4 v[K + 1];
+        if (PF) {
+#pragma unroll
+            for (int b = 0; b < K + 1; ++b) v[b] = vn[b];
+            if (r + 1 < nsteps) load_row(vn, iy + 1);
+        }
+        float4 tt[2] = {zero, zero};
+        if (MODE == 2 && oth && oy >= oy0) {               // issue the loads of the dot operand before the FMA block
+            tt[0] = __ldg(oth + ((int64_t)oy * g.out_w + ox0) * g.c4);
+            if (col1) tt[1] = __ldg(oth + ((int64_t)oy * g.out_w + ox0 + 1) * g.c4);
+        }
+        if (PF || (iy >= 0 && iy < g.in_h)) {              // (PF: rows outside the plane arrive as zeros)
+            if (!PF) load_row(v, iy);
+            if (sep) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    float4 h = zero;
+#pragma unroll
+                    for (int b = 0; b < K; ++b) {
+                        h.x = fmaf(v[j + b].x, kh[b], h.x); h.y = fmaf(v[j + b].y, kh[b], h.y);
+                        h.z = fmaf(v[j + b].z, kh[b], h.z); h.w = fmaf(v[j + b].w, kh[b], h.w);
+                    }
+#pragma unroll
+                    for (int a = 0; a < K; ++a) {          // input row iy is tap row a of output row iy + pad - a
+                        float4 &d = acc[K - 1 - a][j];
+                        d.x = fmaf(h.x, kv[a], d.x); d.y = fmaf(h.y, kv[a], d.y);
+                        d.z = fmaf(h.z, kv[a], d.z); d.w = fmaf(h.w, kv[a], d.w);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < K; ++a)
+#pragma unroll
+                    for (int b = 0; b < K; ++b) {
+                        const float k = __ldg(taps + (K - 1 - a) * K + (K - 1 - b));
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            float4 &d = acc[K - 1 - a][j];
+                            d.x = fmaf(v[j + b].x, k, d.x); d.y = fmaf(v[j + b].y, k, d.y);
+                            d.z = fmaf(v[j + b].z, k, d.z); d.w = fmaf(v[j + b].w, k, d.w);
+                        }
+                    }
+            }
+        }
+        if (oy >= oy0) {
+            float4 o[2] = {acc[0][0], acc[0][1]};
+            if (STYLED) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const bool in = (j == 0) || col1;
+                    float add = (nz && in) ? nw * __ldg(nz + (int64_t)oy * g.out_w + ox0 + j) : 0.0f;
+                    float m0 = 1.0f;
+                    if (g.stylemap && in) {
+                        const float *mp = g.stylemap + (int64_t)n * g.map_bstride + (int64_t)oy * g.out_w + ox0 + j;
+                        m0 = __ldg(mp);
+                        add += __ldg(mp + (int64_t)g.out_h * g.out_w);
+                    }
+                    float u;
+                    u = fmaf(o[j].x, m0, add + bias4.x); o[j].x = ((u > 0.f) ? u : u * g.alpha) * g.gain;
+                    u = fmaf(o[j].y, m0, add + bias4.y); o[j].y = ((u > 0.f) ? u : u * g.alpha) * g.gain;
+                    u = fmaf(o[j].z, m0, add + bias4.z); o[j].z = ((u > 0.f) ? u : u * g.alpha) * g.gain;
+                    u = fmaf(o[j].w, m0, add + bias4.w); o[j].w = ((u > 0.f) ? u : u * g.alpha) * g.gain;
+                }
+            }
+            if (MODE == 2) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (j == 1 && !col1) break;
+                    dot.x = fmaf(o[j].x, tt[j].x, dot.x); dot.y = fmaf(o[j].y, tt[j].y, dot.y);
+                    dot.z = fmaf(o[j].z, tt[j].z, dot.z); dot.w = fmaf(o[j].w, tt[j].w, dot.w);
+                    o[j].x = round_tf32_(o[j].x * sc2.x); o[j].y = round_tf32_(o[j].y * sc2.y);
+                    o[j].z = round_tf32_(o[j].z * sc2.z); o[j].w = round_tf32_(o[j].w * sc2.w);
+                }
+            }
+            float4 *dst = yout + ((int64_t)oy * g.out_w + ox0) * g.c4;
+            dst[0] = o[0];
+            if (col1) dst[g.c4] = o[1];
+            if (STYLED && g.out2) {
+                float4 *dst2 = reinterpret_cast<float4 *>(g.out2) + (int64_t)n * g.out_h * g.out_w * g.c4 + c +
+                               ((int64_t)oy * g.out_w + ox0) * g.c4;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (j == 1 && !col1) break;
+                    float4 q;
+                    q.x = round_tf32_(o[j].x * sc2.x); q.y = round_tf32_(o[j].y * sc2.y);
+                    q.z = round_tf32_(o[j].z * sc2.z); q.w = round_tf32_(o[j].w * sc2.w);
+                    dst2[(int64_t)j * g.c4] = q;
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < K - 1; ++s) { acc[s][0] = acc[s + 1][0]; acc[s][1] = acc[s + 1][1]; }
+        acc[K - 1][0] = zero; acc[K - 1][1] = zero;
+    }
+    if (MODE == 2 && g.dot) {   // one 128-bit reduction per thread into dot[n, 4c .. 4c+3]
+        float *dp = g.dot + ((int64_t)n * g.c4 + c) * 4;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dp), "f"(dot.x), "f"(dot.y), "f"(dot.z), "f"(dot.w) : "memory");
+    }
+}
+
 // ---- channels-last FIR through TMA-staged tiles (up = down = 1, 4x4 taps, C % 32 == 0, planes >= 32 x 32) --------------
 // Persistent CTAs walk the tile list; a tile is 16 x 32 output pixels x 32 channels.  A producer warp fetches the
 // {32 ch, 19, 35} input box of the next tile with ONE TMA instruction into a 2-stage shared-memory ring (zero fill
@@ -972,9 +1173,26 @@ int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, in
     g.alpha = alpha; g.gain = gain;
     if (g.total_threads >= 0x7fffffffll) return SR_ERR_UNSUPPORTED;
     const int64_t blocks = (g.total_threads + kThreads - 1) / kThreads;
-    if (dot || (!styled && scale2)) upfirdn2d_nhwc_kernel<4, 4, 2><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
-    else if (styled) upfirdn2d_nhwc_kernel<4, 4, 1><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
-    else upfirdn2d_nhwc_kernel<4, 4, 0><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
+    // A/B switch, read per call: 0 = the 4x5 input-window kernel, 1 = ring bounded for 3 CTAs per SM, 2 = ring at 2 CTAs
+    // per SM, 3 = ring + explicit next-row prefetch at 2 CTAs per SM
+    const char *ring_env = getenv("SR_FIR_RING");
+    const int ring = (ring_env && ring_env[0] >= '0' && ring_env[0] <= '3') ? ring_env[0] - '0' : 3;
+    const int mode = (dot || (!styled && scale2)) ? 2 : (styled ? 1 : 0);
+#define SR_RING(PF, MINB)                                                                                          \
+    do {                                                                                                           \
+        if (mode == 2) fir_nhwc_ring_kernel<2, PF, MINB><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);       \
+        else if (mode == 1) fir_nhwc_ring_kernel<1, PF, MINB><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);  \
+        else fir_nhwc_ring_kernel<0, PF, MINB><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);                 \
+    } while (0)
+    if (ring == 1) SR_RING(false, 3);
+    else if (ring == 2) SR_RING(false, 2);
+    else if (ring == 3) SR_RING(true, 2);
+    else {
+        if (mode == 2) upfirdn2d_nhwc_kernel<4, 4, 2><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
+        else if (mode == 1) upfirdn2d_nhwc_kernel<4, 4, 1><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
+        else upfirdn2d_nhwc_kernel<4, 4, 0><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
+    }
+#undef SR_RING
     return SR_OK;
 }
 

@@ -308,6 +308,45 @@ def test_fused_pass_kernels():
         torch.testing.assert_close(dt, (f * other).sum((1, 2)), rtol=1e-4, atol=1e-2)
 
 
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("rank1", [True, False])
+def test_fir_nhwc_kernel_variants_vs_oracle(variant, rank1, monkeypatch):
+    """Every channels-last FIR kernel (SR_FIR_RING: 0 = input-window kernel, 1-3 = row-streaming ring kernels, 3 is the
+    default) in its three modes -- plain, styled tail, scale(+dot) tail -- against the oracle's upfirdn2d
+    (oracle/sr_oracle.c, reference op/upfirdn2d.py:159-200), with the model's rank-1 taps (separable form inside the
+    ring kernels, reference layers.py:7-12) and with general, asymmetric taps (2-D form)."""
+    from oracle import cpu as O
+    from stylerenderer_b200 import tc_conv as tc
+    from stylerenderer_b200.op import upfirdn2d_raw
+    from make_golden import seeded
+    monkeypatch.setenv("SR_FIR_RING", variant)
+    k1 = torch.tensor([1., 3., 3., 1.])
+    k = (torch.outer(k1, k1) / 64 * 4) if rank1 else seeded((4, 4), 16)
+    for (b, h, w, c) in [(2, 8, 8, 128), (3, 5, 7, 256), (1, 33, 35, 512), (2, 64, 64, 128), (1, 3, 2, 4)]:
+        t = seeded((b, h + 1, w + 1, c), 17)
+        noise, nw = seeded((b, 1, h, w), 18), torch.tensor([0.4])
+        bias, d = seeded((c,), 19), seeded((b, c), 20).abs() + 0.5
+
+        def fir(pad):
+            return O.upfirdn2d(t.permute(0, 3, 1, 2).contiguous(), k, pad=(pad, pad)).permute(0, 2, 3, 1).contiguous()
+        f1, f2 = fir(1), fir(2)                                            # [b,h,w,c] and [b,h+2,w+2,c]
+        tol = dict(rtol=1e-5, atol=1e-5)
+        got = upfirdn2d_raw(t.cuda(), k.cuda(), 1, 1, 1, 1, 1, 1, 1, 1)    # plain mode
+        torch.testing.assert_close(got.cpu(), f1, **tol)
+        ref = f1 + nw * noise.view(b, h, w, 1) + bias
+        ref = torch.where(ref > 0, ref, ref * 0.2) * 2 ** 0.5
+        got1, got2 = tc.blur_styled(t.cuda(), k.cuda(), (1, 1), noise.cuda(), nw.cuda(), bias.cuda(), 0.2, 2 ** 0.5,
+                                    scale2=d.cuda())
+        torch.testing.assert_close(got1.cpu(), ref, **tol)
+        torch.testing.assert_close(got2.cpu(), ref * d.view(b, 1, 1, c), rtol=6e-4, atol=1e-5)     # tf32 rounding
+        other = seeded((b, h + 2, w + 2, c), 21)
+        o, dt = tc.blur_scaledot(t.cuda(), k.cuda(), (2, 2), d.cuda(), other.cuda())
+        torch.testing.assert_close(o.cpu(), f2 * d.view(b, 1, 1, c), rtol=6e-4, atol=1e-5)
+        torch.testing.assert_close(dt.cpu(), (f2 * other).sum((1, 2)), rtol=1e-4, atol=1e-2)
+        o2, none = tc.blur_scaledot(t.cuda(), k.cuda(), (2, 2), d.cuda())
+        assert none is None and torch.equal(o2, o)
+
+
 @pytest.mark.parametrize("up", [False, True])
 def test_modulated_conv_tcgen05_exact_forward(up):
     """ModulatedConv2d alone on the tensor cores (the path StyledMapConv and user code take), exact-product operands."""
