@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""A/B timing of the channels-last FIR kernels (SR_FIR_RING = 0..3, see csrc/upfirdn2d.cu) on the generator's two largest
+"""A/B timing of the channels-last FIR kernels (SR_FIR_RING = 0..5, see csrc/upfirdn2d.cu) on the generator's two largest
 up-sampling blocks: forward tail (fir + noise + bias + lrelu + tf32 second output) and backward tail (fir^T * d -> tf32).
 CUDA events, inputs larger than L2; prints one JSON line per (variant, shape)."""
 import json
@@ -39,7 +39,7 @@ def main():
         bias, d = torch.randn(c, device=dev), torch.rand(B, c, device=dev) + 0.5
         by_f = 4 * B * c * ((r + 1) ** 2 + 2 * r * r)
         by_b = 4 * B * c * (r * r + (r + 1) ** 2)
-        for variant in ("0", "1", "2", "3"):
+        for variant in ("0", "1", "2", "3", "4", "5"):
             os.environ["SR_FIR_RING"] = variant
             ms_f = timed(lambda: tc.blur_styled(t, taps, (1, 1), noise, nw, bias, 0.2, 2 ** 0.5, scale2=d))
             ms_b = timed(lambda: tc.blur_scaledot(g, taps, (2, 2), d))

@@ -623,15 +623,17 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
 // Rank-1 taps (every FIR the model builds is an outer product, reference layers.py:7-12) take the separable form: 4
 // FMAs for the row filter + 4 to scatter it over the open rows = 8 instead of 16 per output (checked on the device,
 // like upfirdn2d_tile_kernel); general taps accumulate in the same (a, b) order as the 2-D kernel (bit-identical).
-// PF: the next input row is loaded before the current one is consumed (two rows in flight per thread); MINB = CTAs per SM
-// the register allocation is bounded for.
-template <int MODE, bool PF, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB)
+// D = input rows in flight per thread: a row buffer is re-loaded (row r + D) right after step r consumed it, so D row
+// loads overlap every step -- the kernel is bound by the latency of its sequential row loop (time ~ waves x rows x
+// latency, A/B record in profiles/r1_fir_ring_experiment.md), not by arithmetic.  NT = threads per CTA, MINB = CTAs per
+// SM the register allocation is bounded for.
+template <int MODE, int D, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 fir_nhwc_ring_kernel(float *__restrict__ out, const float *__restrict__ x, const float *__restrict__ taps, const NhwcGeom g)
 {
     constexpr int K = 4;
     constexpr bool STYLED = (MODE == 1);
-    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t tid = (int64_t)blockIdx.x * NT + threadIdx.x;
     if (tid >= g.total_threads) return;
     uint32_t t = (uint32_t)tid, c, xp, ys, n;
     g.div_c4.divmod(t, t, c);
@@ -710,25 +712,18 @@ fir_nhwc_ring_kernel(float *__restrict__ out, const float *__restrict__ x, const
             row[b] = (row_ok && ix >= 0 && ix < g.in_w) ? __ldg(src + (int64_t)ix * g.c4) : zero;
         }
     };
-    float4 vn[K + 1];
-    if (PF) load_row(vn, oy0 - g.pad_y0);
-#pragma unroll 2
-    for (int r = 0; r < nsteps; ++r) {
-        const int iy = oy0 - g.pad_y0 + r;                 // input row of this step
-        const int oy = oy0 + r - (K - 1);                  // output row this step completes (a strip's first K-1 steps: none)
-        float4 v[K + 1];
-        if (PF) {
+    float4 buf[D][K + 1];
 #pragma unroll
-            for (int b = 0; b < K + 1; ++b) v[b] = vn[b];
-            if (r + 1 < nsteps) load_row(vn, iy + 1);
-        }
+    for (int u = 0; u < D; ++u)
+        if (u < nsteps) load_row(buf[u], oy0 - g.pad_y0 + u);
+    auto step = [&](const float4 (&v)[K + 1], int r) {
+        const int oy = oy0 + r - (K - 1);                  // output row this step completes (a strip's first K-1 steps: none)
         float4 tt[2] = {zero, zero};
         if (MODE == 2 && oth && oy >= oy0) {               // issue the loads of the dot operand before the FMA block
             tt[0] = __ldg(oth + ((int64_t)oy * g.out_w + ox0) * g.c4);
             if (col1) tt[1] = __ldg(oth + ((int64_t)oy * g.out_w + ox0 + 1) * g.c4);
         }
-        if (PF || (iy >= 0 && iy < g.in_h)) {              // (PF: rows outside the plane arrive as zeros)
-            if (!PF) load_row(v, iy);
+        {                                                  // (rows outside the plane arrive as zeros)
             if (sep) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -809,6 +804,16 @@ fir_nhwc_ring_kernel(float *__restrict__ out, const float *__restrict__ x, const
 #pragma unroll
         for (int s = 0; s < K - 1; ++s) { acc[s][0] = acc[s + 1][0]; acc[s][1] = acc[s + 1][1]; }
         acc[K - 1][0] = zero; acc[K - 1][1] = zero;
+    };
+    for (int r0 = 0; r0 < nsteps; r0 += D) {
+#pragma unroll
+        for (int u = 0; u < D; ++u) {
+            const int r = r0 + u;
+            if (r < nsteps) {
+                step(buf[u], r);
+                if (r + D < nsteps) load_row(buf[u], oy0 - g.pad_y0 + r + D);
+            }
+        }
     }
     if (MODE == 2 && g.dot) {   // one 128-bit reduction per thread into dot[n, 4c .. 4c+3]
         float *dp = g.dot + ((int64_t)n * g.c4 + c) * 4;
@@ -1173,20 +1178,24 @@ int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, in
     g.alpha = alpha; g.gain = gain;
     if (g.total_threads >= 0x7fffffffll) return SR_ERR_UNSUPPORTED;
     const int64_t blocks = (g.total_threads + kThreads - 1) / kThreads;
-    // A/B switch, read per call: 0 = the 4x5 input-window kernel, 1 = ring bounded for 3 CTAs per SM, 2 = ring at 2 CTAs
-    // per SM, 3 = ring + explicit next-row prefetch at 2 CTAs per SM
+    // A/B switch, read per call: 0 = the 4x5 input-window kernel (default: measured best, profiles/r1_fir_ring_experiment.md),
+    // 1-5 = row-streaming ring kernels with (rows in flight, threads per CTA, CTAs per SM) = (2,256,2) (3,128,3) (3,256,1)
+    // (4,128,2) (1,256,2)
     const char *ring_env = getenv("SR_FIR_RING");
-    const int ring = (ring_env && ring_env[0] >= '0' && ring_env[0] <= '3') ? ring_env[0] - '0' : 3;
+    const int ring = (ring_env && ring_env[0] >= '0' && ring_env[0] <= '5') ? ring_env[0] - '0' : 0;
     const int mode = (dot || (!styled && scale2)) ? 2 : (styled ? 1 : 0);
-#define SR_RING(PF, MINB)                                                                                          \
-    do {                                                                                                           \
-        if (mode == 2) fir_nhwc_ring_kernel<2, PF, MINB><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);       \
-        else if (mode == 1) fir_nhwc_ring_kernel<1, PF, MINB><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);  \
-        else fir_nhwc_ring_kernel<0, PF, MINB><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);                 \
+#define SR_RING(D, NT, MINB)                                                                                           \
+    do {                                                                                                               \
+        const unsigned nb = (unsigned)((g.total_threads + NT - 1) / NT);                                               \
+        if (mode == 2) fir_nhwc_ring_kernel<2, D, NT, MINB><<<nb, NT, 0, st>>>(out, x, taps, g);                        \
+        else if (mode == 1) fir_nhwc_ring_kernel<1, D, NT, MINB><<<nb, NT, 0, st>>>(out, x, taps, g);                   \
+        else fir_nhwc_ring_kernel<0, D, NT, MINB><<<nb, NT, 0, st>>>(out, x, taps, g);                                  \
     } while (0)
-    if (ring == 1) SR_RING(false, 3);
-    else if (ring == 2) SR_RING(false, 2);
-    else if (ring == 3) SR_RING(true, 2);
+    if (ring == 1) SR_RING(2, 256, 2);
+    else if (ring == 2) SR_RING(3, 128, 3);
+    else if (ring == 3) SR_RING(3, 256, 1);
+    else if (ring == 4) SR_RING(4, 128, 2);
+    else if (ring == 5) SR_RING(1, 256, 2);
     else {
         if (mode == 2) upfirdn2d_nhwc_kernel<4, 4, 2><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
         else if (mode == 1) upfirdn2d_nhwc_kernel<4, 4, 1><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);

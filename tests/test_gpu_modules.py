@@ -308,11 +308,11 @@ def test_fused_pass_kernels():
         torch.testing.assert_close(dt, (f * other).sum((1, 2)), rtol=1e-4, atol=1e-2)
 
 
-@pytest.mark.parametrize("variant", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4", "5"])
 @pytest.mark.parametrize("rank1", [True, False])
 def test_fir_nhwc_kernel_variants_vs_oracle(variant, rank1, monkeypatch):
-    """Every channels-last FIR kernel (SR_FIR_RING: 0 = input-window kernel, 1-3 = row-streaming ring kernels, 3 is the
-    default) in its three modes -- plain, styled tail, scale(+dot) tail -- against the oracle's upfirdn2d
+    """Every channels-last FIR kernel (SR_FIR_RING: 0 = input-window kernel, the default; 1-5 = row-streaming ring kernels
+    with 1-4 input rows in flight per thread) in its three modes -- plain, styled tail, scale(+dot) tail -- against the oracle's upfirdn2d
     (oracle/sr_oracle.c, reference op/upfirdn2d.py:159-200), with the model's rank-1 taps (separable form inside the
     ring kernels, reference layers.py:7-12) and with general, asymmetric taps (2-D form)."""
     from oracle import cpu as O
