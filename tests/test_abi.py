@@ -51,6 +51,18 @@ def test_no_cpu_fallback_and_argument_errors():
     assert b"up/down" in L.sr_last_error()
     assert L.sr_rasterize_forward_f32(1, 3, 1, 4, 8, 0, 1, 0, None, None, None, None, None, 1e-6, None, 0, None, None) == -1
     assert b"square" in L.sr_last_error()
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        op.rasterize_pyramid(torch.zeros(1, 3, 3), torch.zeros(1, 3, 2), torch.zeros(1, 3, dtype=torch.int64), [4, 8])
+    assert L.sr_rasterize_pyramid_forward_f32(1, 3, 1, 0, None, 0, 1, 0, None, None, None, 1e-6, None, 0, None) == -1
+    assert b"levels" in L.sr_last_error()
+    from stylerenderer_b200.op.rasterize import RasterLevel
+    lv = (RasterLevel * 1)()
+    lv[0].size = 0
+    assert L.sr_rasterize_pyramid_forward_f32(1, 3, 1, 1, lv, 0, 1, 0, None, None, None, 1e-6, None, 0, None) == -1
+    assert b"level size" in L.sr_last_error()
+    import ctypes
+    sizes = (ctypes.c_int64 * 3)(4, 8, 16)
+    assert L.sr_rasterize_pyramid_workspace_bytes(2, 3, sizes) == 2 * (16 + 64 + 256) * 8 + 16
 
 
 def test_product_does_not_import_the_oracle():
