@@ -449,6 +449,47 @@ def test_generator_tcgen05_backend_matches_cudnn_backend():
     print("worst gradient cosine tcgen05 vs fp32 composed path:", worst)
 
 
+def test_generator_config2_full_size_properties():
+    """BASELINE.json configs[1] at its real size -- Generator(256, 512, 8), batch 32 -- where the CPU oracle is too slow to
+    be the checker: (a) the chained tcgen05 path against this package's composed path in true fp32 (itself pinned to the
+    reference by the golden fixtures), (b) linearity of the backward pass in the cotangent, (c) independence of an
+    image from the rest of its batch."""
+    from stylerenderer_b200 import layers as L, model as M
+    from make_golden import seeded
+    torch.manual_seed(0)
+    G = M.Generator(256, 512, 8, channel_multiplier=2)
+    with torch.no_grad():
+        for n, p in G.named_parameters():
+            if n.endswith("noise.weight") or n.endswith("activate.bias"):
+                p.normal_(0, 0.1)
+    G = G.cuda().eval()
+    z = seeded((32, 512), 740).cuda()
+    cots = [seeded((32, 3, 256, 256), 741).cuda(), seeded((32, 3, 256, 256), 742).cuda()]
+
+    def run(zin, cot):
+        zz = zin.clone().requires_grad_(True)
+        img, _ = G([zz], randomize_noise=False)
+        gz = torch.autograd.grad(img, [zz], cot)[0] if cot is not None else None
+        return img.detach(), gz
+    img_ref, gz_ref = run(z, cots[0])                                       # composed ops, fp32 (allow_tf32 off)
+    L.set_conv_backend("tcgen05")
+    try:
+        img, gz1 = run(z, cots[0])
+        _, gz2 = run(z, cots[1])
+        _, gz12 = run(z, 2.0 * cots[0] - 3.0 * cots[1])
+        img8, _ = run(z[:8], None)
+    finally:
+        L.set_conv_backend("cudnn")
+    err = float((img - img_ref).abs().max() / img_ref.abs().max())
+    cos = float((gz1.double().flatten() @ gz_ref.double().flatten()) / (gz1.double().norm() * gz_ref.double().norm()))
+    print(f"Generator(256) B=32: tcgen05 (tf32) vs fp32 composed path: image max-norm rel err {err:.2e}, dz cosine {cos:.6f}")
+    assert err <= 5e-3 and cos > 0.99
+    lin = 2.0 * gz1 - 3.0 * gz2
+    lin_err = float((gz12 - lin).abs().max() / lin.abs().max())
+    assert lin_err <= 5e-3, lin_err                                         # tf32 rounding of the GEMM operands only
+    assert float((img8 - img[:8]).abs().max()) <= 1e-5 * float(img.abs().max())
+
+
 def test_generator_frozen_weights_latent_gradient_is_unchanged():
     """Latent inversion back-propagates to the latents only: with every parameter frozen the
     chained blocks skip their weight-gradient GEMMs, and the latent gradient must equal the one of the full backward
