@@ -483,15 +483,15 @@ def test_generator_config2_full_size_properties():
     err = float((img - img_ref).abs().max() / img_ref.abs().max())
     cos = float((gz1.double().flatten() @ gz_ref.double().flatten()) / (gz1.double().norm() * gz_ref.double().norm()))
     print(f"Generator(256) B=32: tcgen05 (tf32) vs fp32 composed path: image max-norm rel err {err:.2e}, dz cosine {cos:.6f}")
-    assert err <= 5e-3 and cos > 0.99
+    assert err <= 2e-3 and cos > 0.99                                       # measured on B200: 9.5e-4, 0.99984
     lin = 2.0 * gz1 - 3.0 * gz2
     lin_err = float((gz12 - lin).abs().max() / lin.abs().max())
-    assert lin_err <= 5e-3, lin_err                                         # tf32 rounding of the GEMM operands only
+    assert lin_err <= 2e-3, lin_err                                         # tf32 rounding of the GEMM operands only (3.9e-4)
     # a batch of 8 selects other kernel variants than a batch of 32 (halo / im2col / CTA-pair tiles, split counts), whose
-    # fp32 accumulation orders differ and can flip the tf32 rounding of a handed-on operand: same bound as (a)
+    # fp32 accumulation orders differ and can flip the tf32 rounding of a handed-on operand: a tf32-level difference
     dep = float((img8 - img[:8]).abs().max() / img.abs().max())
     print(f"batch 8 vs batch 32, same latents: max-norm rel difference {dep:.2e}; linearity error {lin_err:.2e}")
-    assert dep <= 5e-3, dep
+    assert dep <= 2e-3, dep                                                 # measured 4.8e-4
 
 
 def test_generator_frozen_weights_latent_gradient_is_unchanged():
