@@ -4,8 +4,10 @@ demodulate/noise/bias/leaky-ReLU epilogue; backward: activation backward -> dgra
 Replaces, for one StyledConv (reference model.py:26-32 + layers.py:293-323 + op/fused_act.py), the chain
   weight*style -> demod -> grouped conv [-> blur] -> + noise -> + bias, lrelu, *sqrt2
 and its autograd graph.  Internal layout is NHWC; logical shapes stay NCHW (channels_last strides) so callers and
-the state_dict are untouched.  First-order gradients only (the R1 / path-length regularisers need double backward
-and run on the composed-op path, see layers.get_conv_backend()).
+the state_dict are untouched.  The fused blocks (StyledConvTC, ModConvTC, StyledLayerTC, PlainConvTC) give first-order
+gradients; iterations that differentiate through a backward pass (R1 / path-length regularisers, entered through
+layers.double_backward()) use the mutually recursive ConvTC / ConvDgradTC / ConvWgradTC Functions below, which are
+differentiable to any order on the same tensor-core kernels.
 """
 import torch
 from torch.autograd import Function

@@ -37,7 +37,8 @@ def get_conv_backend():
 
 class double_backward:
     """Context manager for regulariser iterations (R1 / path length, reference train.py:110-134): inside it the
-    StyledConv blocks use the composed-op path whose backward is itself differentiable."""
+    convolutions run as twice-differentiable autograd Functions (fused.mod_conv_dd / fused.plain_conv_dd on the
+    tensor-core kernels, or the composed torch ops with the "cudnn" backend) instead of the fused first-order blocks."""
 
     def __enter__(self):
         self._old = _CONFIG["double_backward"]
