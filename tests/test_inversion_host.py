@@ -45,5 +45,5 @@ def test_perceptual_distance_drives_an_optimisation():
         loss = (P.distance(P.features(x), tf) + 0.1 * ((x - target) ** 2).mean((1, 2, 3))).sum()
         loss.backward()
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert losses[-1] < 0.7 * losses[0], losses
