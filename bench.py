@@ -42,6 +42,41 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
 
 
+def measure_tf32_peak(dev, sustain_s=2.0):
+    """Dense TF32 tensor-core throughput of THIS GPU, measured in this run the way MEASURED_PEAKS.json measures bf16:
+    torch.matmul (cuBLAS, allow_tf32) on 8192^3 fp32 operands, best of 10 single launches (burst) and back to back for
+    `sustain_s` seconds (sustained).  The sustained figure is the roofline denominator of kernels timed inside the step."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        c = torch.empty(n, n, device=dev)
+        fl = 2.0 * n ** 3
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(10):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); torch.matmul(a, b, out=c); e.record()
+            torch.cuda.synchronize()
+            best = min(best, s.elapsed_time(e))
+        reps = max(10, int(sustain_s * 1e3 / best))
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e.record()
+        torch.cuda.synchronize()
+        sus = s.elapsed_time(e) / reps
+        return {"tf32_tflops": round(fl / (best * 1e-3) / 1e12, 1), "tf32_tflops_sustained": round(fl / (sus * 1e-3) / 1e12, 1),
+                "how": f"torch.matmul fp32 8192^3, allow_tf32: best of 10 (burst), {reps} back to back (sustained)"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
 def rank_seed(base, rank):
     """Per-rank RNG offset: every rank draws its own shard of latents / meshes (reference distributed.py:93-95)."""
     return int(base) + int(rank)
@@ -206,19 +241,24 @@ def ncu_traffic(sig):
 
 
 def dominant_kernel_roofline(stats, peaks, total_ms, steps):
-    """Roofline of the dominant launch: the (kernel, layer shape) group with the largest share of the step."""
+    """Roofline of the dominant KERNEL of the step: every launch of the C-ABI entry point with the largest share of the
+    device time (flops or bytes of all its launches / their summed CUDA-event time).  The heaviest single layer shape of
+    that kernel is reported beside it (`heaviest_launch`), as are the bandwidth-bound passes of the step (`hbm_kernels`)."""
     if not stats:
         return None
     tot = {n: sum(ms for _, ms in calls) for n, calls in stats.items()}
-    name = max(tot, key=tot.get)                        # dominant kernel by device time, then its heaviest layer shape
+    name = max(tot, key=tot.get)                        # dominant kernel by device time
+    all_calls = stats[name]
+    ms_all = tot[name]
     groups = {}
-    for a, ms in stats[name]:
+    for a, ms in all_calls:
         groups.setdefault(launch_signature(name, a), []).append((a, ms))
     sig, calls = max(groups.items(), key=lambda kv: sum(ms for _, ms in kv[1]))
     ms = sum(m for _, m in calls)
-    common = {"kernel": name, "launch": sig, "launches_per_step": len(calls) / steps, "avg_launch_ms": round(ms / len(calls), 5),
-              "share_of_step": round(ms / total_ms, 4) if total_ms else None, "traffic": ncu_traffic(sig),
-              "traffic_source": "profiles/r1_ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+    common = {"kernel": name, "launches_per_step": len(all_calls) / steps, "avg_launch_ms": round(ms_all / len(all_calls), 5),
+              "share_of_step": round(ms_all / total_ms, 4) if total_ms else None,
+              "traffic": ncu_traffic(sig),
+              "traffic_source": f"profiles/r1_ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one '{sig}' launch)",
               "all_kernels_ms_per_step": {n: round(v / steps, 4) for n, v in tot.items()}}
     # the bandwidth-bound passes of the step against the measured copy bandwidth (BASELINE metric: "HBM GB/s vs roofline")
     hbm = {}
@@ -229,30 +269,30 @@ def dominant_kernel_roofline(stats, peaks, total_ms, steps):
             gbs = by_n / (ms_n * 1e-3) / 1e9
             hbm[n] = {"ms_per_step": round(ms_n / steps, 4), "GBps": round(gbs, 1), "frac": round(gbs / peaks["hbm_gbs"], 4)}
     common["hbm_kernels"] = hbm
-    fl = sum(algorithmic_flops(name, a) for a, _ in calls)
-    if fl:
-        # MEASURED_PEAKS.json holds the dense bf16 rate only.  Half of it (tf32 issues at half the bf16 rate) is exceeded
-        # by the 512-channel layers in isolation (950 TF/s, profiles/), so the denominator is the nominal dense TF32
-        # peak of B200_PROFILING.md.
-        peak = 1100.0
-        ach = fl / (ms * 1e-3) / 1e12
-        all_calls = stats[name]
-        fl_all, ms_all = sum(algorithmic_flops(name, a) for a, _ in all_calls), sum(m for _, m in all_calls)
-        common.update({"bound": "tensor", "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s",
-                       "frac": round(ach / peak, 4),
-                       "peak_source": "nominal dense TF32 (no measured TF32 entry; measured bf16 burst / 2 = "
-                                      f"{peaks['bf16_tflops'] / 2:.0f} TF/s is exceeded by this kernel in isolation)",
-                       "algorithmic_flops_per_launch": fl // len(calls),
-                       "all_launches_of_kernel": {"launches_per_step": len(all_calls) / steps,
-                                                  "achieved": round(fl_all / (ms_all * 1e-3) / 1e12, 1),
-                                                  "frac": round(fl_all / (ms_all * 1e-3) / 1e12 / peak, 4),
-                                                  "ms_per_step": round(ms_all / steps, 4)}})
+    fl_all = sum(algorithmic_flops(name, a) for a, _ in all_calls)
+    if fl_all:
+        # denominator: the dense TF32 rate cuBLAS sustains on this GPU in this run (measure_tf32_peak), because these
+        # launches are timed inside a long step; the burst figure and the nominal 1100 TF/s are given beside it
+        peak = peaks.get("tf32_tflops_sustained") or 1100.0
+        ach = fl_all / (ms_all * 1e-3) / 1e12
+        fl = sum(algorithmic_flops(name, a) for a, _ in calls)
+        ach1 = fl / (ms * 1e-3) / 1e12
+        common.update({"bound": "tensor", "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
+                       "peak_source": peaks.get("tf32_how", "nominal dense TF32 (B200_PROFILING.md)"),
+                       "peak_burst": peaks.get("tf32_tflops"), "peak_nominal": 1100.0,
+                       "frac_of_burst": round(ach / peaks["tf32_tflops"], 4) if peaks.get("tf32_tflops") else None,
+                       "frac_of_nominal": round(ach / 1100.0, 4),
+                       "algorithmic_flops_per_step": fl_all // steps,
+                       "heaviest_launch": {"launch": sig, "launches_per_step": len(calls) / steps,
+                                           "avg_launch_ms": round(ms / len(calls), 5), "achieved": round(ach1, 1),
+                                           "frac": round(ach1 / peak, 4), "share_of_step": round(ms / total_ms, 4) if total_ms else None,
+                                           "algorithmic_flops_per_launch": fl // len(calls)}})
         return common
-    by = sum(algorithmic_bytes(name, a) for a, _ in calls)
-    ach = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    by = sum(algorithmic_bytes(name, a) for a, _ in all_calls)
+    ach = by / (ms_all * 1e-3) / 1e9 if ms_all > 0 else 0.0
     common.update({"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                    "frac": round(ach / peaks["hbm_gbs"], 4), "peak_source": peaks["_source"],
-                   "algorithmic_bytes_per_launch": by // len(calls)})
+                   "algorithmic_bytes_per_step": by // steps})
     return common
 
 
@@ -275,7 +315,53 @@ def generator_step(G, z, cot):
     img, _ = G([z])
     loss = (img * cot).sum()
     loss.backward()
-    return loss.detach(), z.grad
+    return loss.detach(), z.grad, img.detach()
+
+
+def gpu_reference_generator_rate(dev, batch, iters=5):
+    """SURVEY.md section 2a's bar, timed on THIS GPU in this run: the reference's GPU formulation of the same step --
+    per-sample modulated weights + cuDNN grouped conv (reference layers.py:296-322, restated in oracle/torch_ref.py) with
+    the reference's own upfirdn2d / fused_bias_act CUDA kernels compiled for sm_100a (oracle/_ref via oracle/ref_cuda.py;
+    stock torch ops when oracle/_ref was not built), torch's default cudnn.allow_tf32.  Not a product path: a baseline."""
+    from oracle import ref_cuda, torch_ref as T
+    torch.manual_seed(0)
+    G = T.Generator(256, 512, 8, channel_multiplier=2)
+    with torch.no_grad():
+        for n, p in G.named_parameters():
+            if n.endswith("noise.weight") or n.endswith("activate.bias"):
+                p.normal_(0, 0.1)
+    G = G.to(dev)
+    z = torch.randn(batch, 512, device=dev)
+    cot = torch.randn(batch, 3, 256, 256, device=dev)
+    have_ref = ref_cuda.available()
+    import contextlib
+    ctx = ref_cuda.reference_cuda_ops() if have_ref else contextlib.nullcontext()
+
+    def step():
+        for p in G.parameters():
+            p.grad = None
+        zz = z.detach().requires_grad_(True)
+        img, _ = G([zz])
+        (img * cot).sum().backward()
+
+    with ctx:
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            step()
+        e.record()
+        torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / iters
+    del G
+    torch.cuda.empty_cache()
+    return {"value": round(batch / (ms * 1e-3), 2), "unit": UNIT, "ms_per_step": round(ms, 3), "batch": batch,
+            "what": "oracle/torch_ref.Generator(256) on CUDA, eager: per-sample weights + cuDNN grouped conv (reference "
+                    "layers.py:296-322), " + ("reference upfirdn2d / fused_bias_act CUDA kernels (oracle/_ref, sm_100a)"
+                                              if have_ref else "stock torch upfirdn2d / leaky_relu (oracle/_ref not built)"),
+            "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32), "timed_steps": iters}
 
 
 def cpu_reference_generator_rate(batch, iters, threads=None):
@@ -471,6 +557,74 @@ def run_rasterize(args):
         dist.destroy_process_group()
 
 
+def run_train_step(args):
+    """BASELINE.json configs[3]: the full GAR train step (GeneratorWithMap + Discriminator + rasterise + R1/16 + path/4,
+    reference train.py:239-358) under DistributedDataParallel -- the one workload of the path with a data-plane collective
+    (NCCL gradient all-reduce).  A "step" is one training iteration; --steps should be a multiple of 16 (one regulariser
+    cycle).  Same JSON contract as the headline workload."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sr_train_step", os.path.join(ROOT, "benchmarks", "train_step.py"))
+    ts = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ts)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available()
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
+    steps = args.steps if args.steps_given else 16
+    cfg = ts.default_args(batch=16 if not args.batch_given else args.batch, iters=steps, warmup=max(args.warmup, 3),
+                          conv_backend=args.conv_backend or "tcgen05")
+    peaks = measured_peaks()
+    cpu_base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        try:
+            rate, cores = ts.cpu_train_step_rate(256, iters=1)
+            cpu_base = {"value": round(rate, 4), "unit": "images/s", "cores": cores, "kind": "port",
+                        "sample": "oracle/torch_ref GeneratorWithMap + Discriminator (+ oracle/sr_oracle.c rasteriser), one D step + "
+                                  f"one G step at batch 1, 1 timed iteration after 1 warm-up ({time.perf_counter() - t0:.0f} s of CPU work)"}
+        except Exception as ex:                         # noqa: BLE001
+            cpu_base = {"unavailable": repr(ex)[:200]}
+    torch.cuda.set_device(local)
+    if rank == 0:
+        tf = measure_tf32_peak(torch.device("cuda", local))
+        peaks.update({"tf32_tflops": tf["tf32_tflops"], "tf32_tflops_sustained": tf["tf32_tflops_sustained"],
+                      "tf32_how": "measured in this run: " + tf["how"]})
+    with ClockSampler(local) as clocks:
+        res, st = ts.run(cfg)
+    roof = None
+    if rank == 0:
+        _lib = st["lib"]
+        names = ["sr_fused_bias_act_f32", "sr_fused_lrelu_backward_f32", "sr_upfirdn2d_f32"] + list(getattr(_lib, "CONV_EXPORTS", ()))
+        n_prof = 4                                      # iterations 1..4: one path-length iteration, no R1
+    # every rank runs the profiled iterations (DDP's all-reduce is collective); only rank 0 times its kernels
+    if rank == 0:
+        with KernelTimer(_lib, names) as kt:
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for i in range(1, 1 + n_prof):
+                st["iteration"](i)
+            e.record()
+            torch.cuda.synchronize()
+        roof = dominant_kernel_roofline(kt.stats(), peaks, s.elapsed_time(e), n_prof)
+    else:
+        for i in range(1, 5):
+            st["iteration"](i)
+    if rank == 0:
+        line = {"metric": res["metric"], "value": res["value"], "unit": "images/s", "n_gpus": world, "steps": steps,
+                "warmup": cfg.warmup, "ms_per_step": res["ms_per_iter"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+                "config": dict(res["config"], global_batch=world * cfg.batch, conv_backend=res["conv_backend"],
+                               execution="eager", l2="activations per iteration exceed the 126 MB L2; no explicit flush"),
+                "clocks": clocks.summary(), "e2e": res.get("e2e"), "gpu_launches": int(res["gpu_launches_per_iter"]),
+                "roofline": roof, "cpu_baseline": cpu_base, "collective": res["collective"], "losses": res["losses"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -480,14 +634,20 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step (BASELINE config: 32)")
     ap.add_argument("--conv-backend", default=None, choices=[None, "cudnn", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="generator", choices=["generator", "rasterize"],
-                    help="generator = BASELINE.json configs[1] (headline); rasterize = configs[2]")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's GPU formulation (gpu_reference)")
+    ap.add_argument("--workload", default="generator", choices=["generator", "rasterize", "train_step"],
+                    help="generator = BASELINE.json configs[1] (headline); rasterize = configs[2]; train_step = configs[3] "
+                         "(DDP gradient all-reduce)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches only (default: also replay the step as a CUDA graph)")
     args = ap.parse_args()
+    args.steps_given = any(a == "--steps" or a.startswith("--steps=") for a in sys.argv[1:])
+    args.batch_given = any(a == "--batch" or a.startswith("--batch=") for a in sys.argv[1:])
     if args.impl == "reference":
         return run_reference_arm(args)
     if args.workload == "rasterize":
         return run_rasterize(args)
+    if args.workload == "train_step":
+        return run_train_step(args)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -506,6 +666,10 @@ def main():
     elif getattr(layers, "HAVE_TCGEN05", False):
         layers.set_conv_backend("tcgen05")
     peaks = measured_peaks()
+    if rank == 0:
+        tf = measure_tf32_peak(dev)
+        peaks.update({"tf32_tflops": tf["tf32_tflops"], "tf32_tflops_sustained": tf["tf32_tflops_sustained"],
+                      "tf32_how": "measured in this run: " + tf["how"]})
 
     # ---- CPU baseline (rank 0, bounded sample, before the GPU timing)
     cpu_base = None
@@ -524,6 +688,7 @@ def main():
     z_host = torch.randn(B, 512).pin_memory()
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     gz_host = torch.empty(B, 512).pin_memory()
+    img_host = torch.empty(B, 3, 256, 256).pin_memory()     # the step's result: the generated images come back too
 
     def barrier():
         if world > 1:
@@ -545,9 +710,10 @@ def main():
 
     def step_e2e():
         z = z_host.to(dev, non_blocking=True)
-        loss, gz = generator_step(G, z, cot)
+        loss, gz, img = generator_step(G, z, cot)
         loss_host.copy_(loss, non_blocking=True)
         gz_host.copy_(gz, non_blocking=True)
+        img_host.copy_(img, non_blocking=True)
         torch.cuda.current_stream().synchronize()       # the caller reads the result every step
 
     for _ in range(max(args.warmup, 3)):
@@ -577,7 +743,7 @@ def main():
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                loss_static, gz_static = generator_step(G, z_static, cot)
+                loss_static, gz_static, img_static = generator_step(G, z_static, cot)
 
             def step_graph():
                 graph.replay()
@@ -587,6 +753,7 @@ def main():
                 graph.replay()
                 loss_host.copy_(loss_static, non_blocking=True)
                 gz_host.copy_(gz_static, non_blocking=True)
+                img_host.copy_(img_static, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
 
             for _ in range(3):
@@ -620,6 +787,18 @@ def main():
         if roof is not None:
             roof["profiled_region_ms_per_step"] = round(region_ms / n_prof, 3)
 
+    gpu_ref = None
+    if rank == 0 and not args.no_gpu_reference:
+        try:
+            del graph
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        try:
+            gpu_ref = gpu_reference_generator_rate(dev, B)
+        except Exception as ex:                         # noqa: BLE001 -- a baseline must not take the bench line down
+            gpu_ref = {"unavailable": repr(ex)[:200]}
+
     value = whole_job_rate(B, args.steps, ms, world)
     e2e = whole_job_rate(B, args.steps, ms_e2e, world)
     if rank == 0:
@@ -637,9 +816,13 @@ def main():
                            "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32)},
                 "clocks": clocks.summary(),
                 "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": z_host.numel() * 4,
-                        "d2h_bytes_per_step": 4 + gz_host.numel() * 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
+                        "d2h_bytes_per_step": 4 + gz_host.numel() * 4 + img_host.numel() * 4,
+                        "d2h": "loss + dz + the generated images [B,3,256,256] fp32",
+                        "ms_per_step": round(ms_e2e / args.steps, 3)},
                 "gpu_launches": int(launches),
-                "roofline": roof, "cpu_baseline": cpu_base}
+                "roofline": roof, "cpu_baseline": cpu_base, "gpu_reference": gpu_ref,
+                "measured_peaks": {k: v for k, v in peaks.items() if k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained",
+                                                                          "tf32_tflops", "tf32_tflops_sustained", "_source")}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

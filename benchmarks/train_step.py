@@ -99,9 +99,275 @@ def g_path_regularize(fake_img, latents, mean_path_length, decay=0.01):
     return (path_lengths - path_mean).pow(2).mean(), path_mean.detach()
 
 
-def requires_grad(model, flag):
-    for p in model.parameters():
+def dead_parameters(gen):
+    """The reference builds the ToRGB list twice (model.py:86 + :122) and its forward only
+    walks the first half: the second half's parameters never receive a gradient.  They are frozen for the whole run, so
+    DDP's reducer never waits for them (no find_unused_parameters graph walk per step)."""
+    if len(gen.to_rgbs) != len(gen.convs):               # one ToRGB per resolution = no duplicates
+        return []
+    return [p for m in list(gen.to_rgbs)[len(gen.to_rgbs) // 2:] for p in m.parameters()]
+
+
+def requires_grad(params, flag):
+    for p in params:
         p.requires_grad = flag
+
+
+def cpu_train_step_rate(size, iters=2):
+    """cpu_baseline of the train-step workload: the oracle's CPU restatement of the reference modules
+    (oracle/torch_ref.GeneratorWithMap / Discriminator + oracle/sr_oracle.c rasteriser), one D step + one G step per
+    iteration at batch 1 on the host cores (no regulariser iterations: a bounded sample, and they only add work)."""
+    import time
+    from oracle import cpu as O, torch_ref as T
+    try:
+        threads = max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        threads = max(1, os.cpu_count() or 1)
+    prev = torch.get_num_threads()
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+
+    def rast(v, tex, tri, h, w):
+        return O.rasterize(v.detach(), tex.detach(), tri, h)[0]
+    G = T.GeneratorWithMap(size, 512, 8, channel_multiplier=2, rasterize=rast)
+    D = T.Discriminator(size, channel_multiplier=2)
+    face = SyntheticMorphableModel(189)
+    times = []
+    for it in range(iters + 1):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            vert = random_pose(face(face.random_input(1))).contiguous()
+            norm = vertex_normals(vert, face.tri)
+        real = torch.randn(1, 3, size, size)
+        with torch.no_grad():
+            fake, _, _ = G([torch.randn(1, 512)], (vert, norm, face.tri))
+        for p in D.parameters():
+            p.grad = None
+        d_logistic_loss(D(real), D(fake)).backward()
+        fake, _, _ = G([torch.randn(1, 512)], (vert, norm, face.tri))
+        for p in G.parameters():
+            p.grad = None
+        F.softplus(-D(fake)).mean().backward()
+        if it:
+            times.append(time.perf_counter() - t0)
+    torch.set_num_threads(prev)
+    return len(times) / sum(times), threads
+
+
+def run(args):
+    """One process of the train-step benchmark (rank from the environment).  Returns the result dict on rank 0, None
+    elsewhere.  `args`: batch, size, iters, warmup, mesh_n, conv_backend, no_cudnn_benchmark, d_nchw, profile, e2e."""
+    import time
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1234 + rank)                                     # reference distributed.py:93-95
+    from stylerenderer_b200 import _lib, layers
+    from stylerenderer_b200.model import Discriminator, GeneratorWithMap
+
+    layers.set_conv_backend(args.conv_backend)
+    # the Discriminator's 3-channel stem / 513-channel final conv are cuDNN's: let it pick its algorithms by measurement
+    # and keep D in channels_last so that no NCHW<->NHWC conversion kernels run around them
+    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
+    G = GeneratorWithMap(args.size, 512, 8, channel_multiplier=2).to(dev)
+    D = Discriminator(args.size, channel_multiplier=2).to(dev)
+    if not args.d_nchw:
+        D = D.to(memory_format=torch.channels_last)
+    g_ema = copy.deepcopy(G).eval()
+    face = SyntheticMorphableModel(args.mesh_n).to(dev)
+    g_reg, d_reg = 4, 16
+    g_ratio, d_ratio = g_reg / (g_reg + 1), d_reg / (d_reg + 1)        # train.py:529-536
+    dead = dead_parameters(G)
+    requires_grad(dead, False)
+    dead_ids = {id(p) for p in dead}
+    g_params = [p for p in G.parameters() if id(p) not in dead_ids]
+    d_params = list(D.parameters())
+    g_optim = torch.optim.Adam(g_params, lr=0.002 * g_ratio, betas=(0.0, 0.99 ** g_ratio))
+    d_optim = torch.optim.Adam(d_params, lr=0.002 * d_ratio, betas=(0.0, 0.99 ** d_ratio))
+    g_mod, d_mod = G, D
+    buckets = None
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        G = DDP(G, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True)
+        D = DDP(D, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True)
+    B, tri = args.batch, face.tri
+    mean_path = torch.zeros((), device=dev)
+    real_host = torch.randn(B, 3, args.size, args.size).pin_memory()
+    loss_host = torch.zeros(4).pin_memory()
+    losses = {}
+
+    from stylerenderer_b200 import mesh as mesh_frontend
+
+    def sample_mesh(n):
+        with torch.no_grad():
+            vert = random_pose(face(face.random_input(n))).contiguous()
+            return vert, mesh_frontend.mesh_point_normal(vert, tri)          # sr_mesh_vertex_normals_f32
+
+    def iteration(i, e2e=False):
+        nonlocal mean_path
+        if e2e:                                                         # the "real" batch arrives from pinned host memory
+            real = real_host.to(dev, non_blocking=True)
+        else:
+            real = torch.randn(B, 3, args.size, args.size, device=dev)
+        if not args.d_nchw:
+            real = real.contiguous(memory_format=torch.channels_last)
+        # ---- D step (train.py:245-268)
+        requires_grad(g_params, False); requires_grad(d_params, True)
+        vert, norm = sample_mesh(B)
+        fake, _, _ = g_mod([torch.randn(B, 512, device=dev)], (vert, norm, tri))
+        d_loss = d_logistic_loss(D(real), D(fake))
+        d_mod.zero_grad(set_to_none=True)
+        d_loss.backward()
+        d_optim.step()
+        losses["d"] = d_loss.detach()
+        if i % d_reg == 0:                                              # R1 (train.py:281-289): double backward through D
+            real.requires_grad = True
+            with layers.double_backward():                              # the tensor-core blocks are first-order only
+                real_pred = D(real)
+                r1 = d_r1_loss(real_pred, real)
+                d_mod.zero_grad(set_to_none=True)
+                (10 / 2 * r1 * d_reg + 0 * real_pred[0]).backward()
+            d_optim.step()
+            losses["r1"] = r1.detach()
+        # ---- G step (train.py:292-333)
+        requires_grad(g_params, True); requires_grad(d_params, False)
+        vert, norm = sample_mesh(B)
+        fake, _, _ = G([torch.randn(B, 512, device=dev)], (vert, norm, tri))
+        g_loss = F.softplus(-d_mod(fake)).mean()
+        g_mod.zero_grad(set_to_none=True)
+        g_loss.backward()
+        g_optim.step()
+        losses["g"] = g_loss.detach()
+        if i % g_reg == 0:                                              # path length (train.py:335-354): double backward through G
+            pb = max(1, B // 2)
+            v = vert[:pb].clone().requires_grad_(True)
+            n = norm[:pb].clone().requires_grad_(True)
+            with layers.double_backward():
+                # the unwrapped module (the loss differentiates the output w.r.t. intermediate tensors, which DDP's
+                # output copies would break); the gradient all-reduce of this step is issued explicitly below
+                fake, latents, normals = g_mod([torch.randn(pb, 512, device=dev)], (v, n, tri), return_latents=True,
+                                               return_normals=True)
+                path_loss, mean_path = g_path_regularize(fake, [latents] + normals, mean_path)
+                g_mod.zero_grad(set_to_none=True)
+                (2 * g_reg * path_loss + 0 * fake[0, 0, 0, 0]).backward()
+            if world > 1:
+                grads = [p.grad for p in g_params if p.grad is not None]
+                flat = torch.cat([g.reshape(-1) for g in grads])
+                dist.all_reduce(flat)
+                flat.div_(world)
+                off = 0
+                for g in grads:
+                    g.copy_(flat[off:off + g.numel()].view_as(g))
+                    off += g.numel()
+            g_optim.step()
+            losses["path"] = path_loss.detach()
+        with torch.no_grad():                                           # EMA (train.py:100-104,358)
+            for pe, p in zip(g_ema.parameters(), g_mod.parameters()):
+                pe.mul_(0.999).add_(p.detach(), alpha=0.001)
+        if e2e:                                                         # the loop reads its scalars every iteration (train.py:360-372)
+            loss_host[0].copy_(losses["d"], non_blocking=True)
+            loss_host[1].copy_(losses["g"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    def timed(n_iters, e2e=False):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(n_iters):
+            iteration(i, e2e)
+        e.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for i in range(max(args.warmup, 3)):
+        iteration(i)
+    n0 = _lib.launch_count()
+    if args.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            ms = timed(args.iters)
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90), file=sys.stderr)
+    else:
+        ms = timed(args.iters)
+    launches = (_lib.launch_count() - n0) // args.iters
+    ms_e2e = timed(args.iters, e2e=True) if getattr(args, "e2e", True) else None
+
+    # ---- the collective: DDP's gradient all-reduce (bucket layout from the reducer) and its stand-alone cost
+    comm = None
+    if world > 1:
+        def bucket_info(m):
+            try:
+                sizes = [int(x) for x in m._get_ddp_logging_data().get("bucket_sizes", "").split(",") if x.strip()]
+                return {"buckets": len(sizes), "bytes": sum(sizes)}
+            except Exception:                                           # noqa: BLE001
+                return None
+        n_g = sum(p.numel() for p in g_params)
+        n_d = sum(p.numel() for p in d_params)
+        flat = torch.zeros(n_g + n_d, device=dev)
+        for _ in range(3):
+            dist.all_reduce(flat)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(10):
+            dist.all_reduce(flat)
+        e.record()
+        torch.cuda.synchronize()
+        ar_ms = s.elapsed_time(e) / 10
+        comm = {"collective": "NCCL all-reduce of the G and D gradients (DDP buckets, overlapped with the backward)",
+                "gradient_bytes_per_iteration": 4 * (n_g + n_d), "generator": bucket_info(G), "discriminator": bucket_info(D),
+                "allreduce_ms_standalone": round(ar_ms, 3),
+                "allreduce_busbw_GBps": round(2 * (world - 1) / world * 4 * (n_g + n_d) / (ar_ms * 1e-3) / 1e9, 1)}
+
+    # ---- sanity: a benchmark of a diverged model measures nothing (ADVICE r1)
+    finite = all(bool(torch.isfinite(v).all()) for v in losses.values())
+    finite = finite and all(bool(torch.isfinite(p).all()) for p in list(g_params)[:40] + list(d_params)[:20])
+    if not finite:
+        raise RuntimeError(f"train step diverged: losses {dict((k, float(v)) for k, v in losses.items())}")
+
+    state = dict(iteration=iteration, lib=_lib, dev=dev, world=world, rank=rank, local=local, B=B, tri=tri)
+    if rank != 0:
+        return None, state
+    res = {
+        "metric": "GAR train step (G+D+rasterize+R1/16+path/4) images/sec", "value": round(world * B * args.iters / (ms * 1e-3), 2),
+        "unit": "images/s", "n_gpus": world, "iters": args.iters, "ms_per_iter": round(ms / args.iters, 2),
+        "scaling": "weak", "dtype": "f32 storage, tf32 tensor-core convs",
+        "conv_backend": {"generator": args.conv_backend, "discriminator": args.conv_backend + " (ResBlock convs; 3-channel stem, final conv on cuDNN)"},
+        "config": {"workload": "GeneratorWithMap + Discriminator 256x256 (BASELINE.json configs[3])", "per_gpu_batch": B,
+                   "parallelism": f"ddp{world} (NCCL gradient all-reduce, broadcast_buffers=False, dead ToRGB copies frozen)",
+                   "mesh": f"{args.mesh_n ** 2} verts / {tri.shape[0]} tris"},
+        "gpu_launches_per_iter": launches, "losses": {k: round(float(v), 5) for k, v in losses.items()},
+        "collective": comm}
+    if ms_e2e is not None:
+        res["e2e"] = {"value": round(world * B * args.iters / (ms_e2e * 1e-3), 2), "unit": "images/s",
+                      "h2d_bytes_per_step": real_host.numel() * 4, "d2h_bytes_per_step": 8,
+                      "ms_per_step": round(ms_e2e / args.iters, 2),
+                      "what": "the real-image batch from pinned host memory every iteration, D / G losses read back"}
+    return res, state
+
+
+def default_args(**over):
+    ns = argparse.Namespace(batch=16, size=256, iters=16, warmup=3, mesh_n=189, conv_backend="tcgen05",
+                            no_cudnn_benchmark=False, d_nchw=False, profile=False, e2e=True)
+    for k, v in over.items():
+        setattr(ns, k, v)
+    return ns
 
 
 def main():
@@ -112,148 +378,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--mesh-n", type=int, default=189)
     ap.add_argument("--conv-backend", default="tcgen05", choices=["cudnn", "tcgen05"],
-                    help="who runs the ModulatedConv2d contractions of G (the Discriminator's plain convs stay on cuDNN)")
+                    help="who runs the ModulatedConv2d contractions of G and the ResBlock convs of D")
     ap.add_argument("--no-cudnn-benchmark", action="store_true", help="keep cuDNN's heuristic algorithm choice for the Discriminator")
     ap.add_argument("--d-nchw", action="store_true", help="keep the Discriminator in NCHW (default: channels_last, no layout conversions)")
     ap.add_argument("--profile", action="store_true", help="print the top CUDA kernels of the timed iterations (torch.profiler)")
+    ap.add_argument("--no-e2e", dest="e2e", action="store_false")
     args = ap.parse_args()
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    torch.manual_seed(1234 + rank)                                     # reference distributed.py:93-95
-    from stylerenderer_b200 import _lib, layers
-    from stylerenderer_b200.model import Discriminator, GeneratorWithMap
-
-    layers.set_conv_backend(args.conv_backend)
-    # the Discriminator's plain convolutions are cuDNN's: let it pick its algorithms by measurement (the heuristic picks
-    # 20 TFLOP/s "sm80 indexed" kernels for the 64-channel layers at 256^2) and keep D in channels_last so that no
-    # NCHW<->NHWC conversion kernels run around them (our upfirdn2d / fused_leaky_relu take channels_last as is)
-    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
-    G = GeneratorWithMap(args.size, 512, 8, channel_multiplier=2).to(dev)
-    D = Discriminator(args.size, channel_multiplier=2).to(dev)
-    if not args.d_nchw:
-        D = D.to(memory_format=torch.channels_last)
-    g_ema = copy.deepcopy(G).eval()
-    face = SyntheticMorphableModel(args.mesh_n).to(dev)
-    g_reg, d_reg = 4, 16
-    g_ratio, d_ratio = g_reg / (g_reg + 1), d_reg / (d_reg + 1)        # train.py:529-536
-    g_optim = torch.optim.Adam(G.parameters(), lr=0.002 * g_ratio, betas=(0.0, 0.99 ** g_ratio))
-    d_optim = torch.optim.Adam(D.parameters(), lr=0.002 * d_ratio, betas=(0.0, 0.99 ** d_ratio))
-    g_mod, d_mod = G, D
-    if world > 1:
-        from torch.nn.parallel import DistributedDataParallel as DDP
-        # find_unused_parameters: the reference builds the ToRGB list twice and never uses the second copy (SURVEY.md
-        # section 4 quirk 4), so six modules' parameters never receive gradients
-        G = DDP(G, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True, find_unused_parameters=True)
-        D = DDP(D, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True)
-    B, tri = args.batch, face.tri
-    mean_path = torch.zeros((), device=dev)
-
-    from stylerenderer_b200 import mesh as mesh_frontend
-
-    def sample_mesh(n):
-        with torch.no_grad():
-            vert = random_pose(face(face.random_input(n))).contiguous()
-            return vert, mesh_frontend.mesh_point_normal(vert, tri)          # sr_mesh_vertex_normals_f32
-
-    def iteration(i):
-        nonlocal mean_path
-        real = torch.randn(B, 3, args.size, args.size, device=dev)
-        if not args.d_nchw:
-            real = real.contiguous(memory_format=torch.channels_last)
-        # ---- D step (train.py:245-268)
-        requires_grad(g_mod, False); requires_grad(d_mod, True)
-        vert, norm = sample_mesh(B)
-        fake, _, _ = g_mod([torch.randn(B, 512, device=dev)], (vert, norm, tri))
-        d_loss = d_logistic_loss(D(real), D(fake))
-        d_mod.zero_grad(set_to_none=True)
-        d_loss.backward()
-        d_optim.step()
-        if i % d_reg == 0:                                              # R1 (train.py:281-289): double backward through D
-            real.requires_grad = True
-            with layers.double_backward():                              # the tensor-core blocks are first-order only
-                real_pred = D(real)
-                r1 = d_r1_loss(real_pred, real)
-                d_mod.zero_grad(set_to_none=True)
-                (10 / 2 * r1 * d_reg + 0 * real_pred[0]).backward()
-            d_optim.step()
-        # ---- G step (train.py:292-333)
-        requires_grad(g_mod, True); requires_grad(d_mod, False)
-        vert, norm = sample_mesh(B)
-        fake, _, _ = G([torch.randn(B, 512, device=dev)], (vert, norm, tri))
-        g_loss = F.softplus(-d_mod(fake)).mean()
-        g_mod.zero_grad(set_to_none=True)
-        g_loss.backward()
-        g_optim.step()
-        if i % g_reg == 0:                                              # path length (train.py:335-354): double backward through G
-            pb = max(1, B // 2)
-            v = vert[:pb].clone().requires_grad_(True)
-            n = norm[:pb].clone().requires_grad_(True)
-            with layers.double_backward():
-                # the unwrapped module: DDP(find_unused_parameters=True) hands back copies of the outputs, which
-                # cannot be differentiated against; the gradient all-reduce of this step is issued explicitly below
-                fake, latents, normals = g_mod([torch.randn(pb, 512, device=dev)], (v, n, tri), return_latents=True,
-                                               return_normals=True)
-                path_loss, mean_path = g_path_regularize(fake, [latents] + normals, mean_path)
-                g_mod.zero_grad(set_to_none=True)
-                (2 * g_reg * path_loss + 0 * fake[0, 0, 0, 0]).backward()
-            if world > 1:
-                grads = [p.grad for p in g_mod.parameters() if p.grad is not None]
-                flat = torch.cat([g.reshape(-1) for g in grads])
-                dist.all_reduce(flat)
-                flat.div_(world)
-                off = 0
-                for g in grads:
-                    g.copy_(flat[off:off + g.numel()].view_as(g))
-                    off += g.numel()
-            g_optim.step()
-        with torch.no_grad():                                           # EMA (train.py:100-104,358)
-            for pe, p in zip(g_ema.parameters(), g_mod.parameters()):
-                pe.mul_(0.999).add_(p.detach(), alpha=0.001)
-
-    for i in range(args.warmup):
-        iteration(i)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    n0 = _lib.launch_count()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    if args.profile and rank == 0:
-        from torch.profiler import ProfilerActivity, profile
-        with profile(activities=[ProfilerActivity.CUDA]) as prof:
-            for i in range(args.iters):
-                iteration(i)
-            torch.cuda.synchronize()
-        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90), file=sys.stderr)
-    else:
-        for i in range(args.iters):
-            iteration(i)
-    e.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = s.elapsed_time(e)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    if rank == 0:
-        print(json.dumps({
-            "metric": "GAR train step (G+D+rasterize+R1/16+path/4) images/sec", "value": round(world * B * args.iters / (ms * 1e-3), 2),
-            "unit": "images/s", "n_gpus": world, "iters": args.iters, "ms_per_iter": round(ms / args.iters, 2),
-            "scaling": "weak", "dtype": "f32 storage, tf32 tensor-core convs",
-            "conv_backend": {"generator": args.conv_backend, "discriminator": args.conv_backend + " (ResBlock convs; 3-channel stem, final conv and regulariser iterations on cuDNN)"},
-            "config": {"workload": "GeneratorWithMap + Discriminator 256x256 (BASELINE.json configs[3])", "per_gpu_batch": B,
-                       "parallelism": f"ddp{world} (NCCL gradient all-reduce, broadcast_buffers=False)",
-                       "mesh": f"{args.mesh_n ** 2} verts / {tri.shape[0]} tris"},
-            "gpu_launches_per_iter": (_lib.launch_count() - n0) // args.iters}), flush=True)
-    if world > 1:
+    res, _ = run(args)
+    if res is not None:
+        print(json.dumps(res), flush=True)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
         dist.destroy_process_group()
 
 

@@ -153,7 +153,11 @@ int sr_rasterize_pyramid_backward_f32(int64_t b, int64_t n, int n_levels, const 
  *   0: out = D * rowscale[n, co]                                  (rowscale may be NULL)
  *   1: t = D * rowscale[n,co] (* stylemap[n,0,y,x] + stylemap[n,1,y,x]) + noise_weight[0]*noise[n,y,x] + bias[co]
  *      out = (t > 0 ? t : alpha*t) * gain          -- the StyledConv / StyledMapConv tail (reference model.py:26-32,48-55)
- *   in both cases, if out2 != NULL: out2 = tf32_round(out * scale2[n, co]) (next layer's modulated input).
+ *   2: as 1, but `out` receives D * rowscale[n,co] -- the demodulated conv output BEFORE the map affine / noise / bias /
+ *      activation, which is what the StyledMapConv backward needs (sr_styled_bwd_prologue3_f32 rebuilds the activated
+ *      value from it; a map that is exactly 0 would make it unrecoverable from the activated one); out2 and the fused
+ *      ToRGB still see the activated value y.
+ *   in every case, if out2 != NULL: out2 = tf32_round(y * scale2[n, co]) (next layer's modulated input; y = out for 0/1).
  * noise is planar [*, out_h, out_w] with batch stride noise_batch_stride (0 broadcasts one plane);
  * stylemap is planar with two planes of out_h*out_w per image and batch stride stylemap_batch_stride. */
 typedef struct sr_conv_args {
@@ -261,9 +265,11 @@ int sr_styled_bwd_prologue2_f32(float *ga, float *g_bias, float *g_noise_w, floa
 
 /* StyledMapConv variants (reference model.py:33-55: `out = out * stylemap[:, :1] + stylemap[:, 1:2]` between the conv and
  * the noise): stylemap = [batch, 2, h, w] planes with batch stride `stylemap_batch_stride` floats (plane stride h*w), may
- * be NULL.  The FIR tail computes y = lrelu(fir * map0 + map1 + noise_w*noise + bias) * gain; the backward prologue hands
- * gp * map0 (* d) to the GEMMs and accumulates g_stylemap [batch, 2, pixels] (zeroed by the call):
- *   g_map1 = sum_c gp,  g_map0 = sum_c gp * conv_d  (conv_d recovered as (t - map1 - noise - bias) / map0). */
+ * be NULL.  The FIR tail computes y = lrelu(fir * map0 + map1 + noise_w*noise + bias) * gain.  WITH a stylemap `out`
+ * receives fir (the filtered conv output BEFORE the map affine) and only out2 = tf32_round(y * scale2) sees y; the
+ * backward prologue then takes that tensor in place of `y`, rebuilds y from it, hands gp * map0 (* d) to the GEMMs and
+ * accumulates g_stylemap [batch, 2, pixels] (zeroed by the call):
+ *   g_map1 = sum_c gp,  g_map0 = sum_c gp * conv_d      (no division by map0: the map may be exactly 0). */
 int sr_blur_nhwc_styled3_f32(float *out, float *out2, const float *scale2, const float *x, const float *taps,
                              int64_t batch, int64_t in_h, int64_t in_w, int64_t channels, int pad0, int pad1,
                              const float *noise, int64_t noise_batch_stride, const float *noise_weight,

@@ -167,7 +167,8 @@ struct ConvKParams {
     int cout;
     long long out_img_stride, out_row_stride, out_pix_stride;   // in floats
     float *out, *out2;
-    int epilogue;                           // 0: acc * rowscale   1: styled
+    int epilogue;                           // 0: acc * rowscale   1: styled   2: styled, but `out` receives acc * rowscale (the
+                                            //    value before the map affine / noise / bias / activation; out2 and ToRGB see y)
     const float *rowscale, *scale2, *bias, *noise, *noise_weight, *stylemap;
     long long noise_img_stride, noise_row_stride, noise_pix_stride;
     long long map_img_stride, map_plane_stride;
@@ -233,7 +234,7 @@ __device__ __forceinline__ void stage_tile_vectors(const ConvKParams &p, const T
         const float *src = nullptr;
         if (v == 0) src = p.rowscale ? p.rowscale + (long long)n * p.cout + ch0 : nullptr;
         else if (v == 1) src = p.out2 ? p.scale2 + (long long)n * p.cout + ch0 : nullptr;
-        else if (v == 2) src = (p.epilogue == 1 && p.bias) ? p.bias + ch0 : nullptr;
+        else if (v == 2) src = (p.epilogue >= 1 && p.bias) ? p.bias + ch0 : nullptr;
         else src = p.rgb_w ? p.rgb_w + ((long long)n * 3 + (v - 3)) * p.cout + ch0 : nullptr;
         const float fill = (v == 0) ? 1.0f : 0.0f;
         const float4 val = src ? __ldg(reinterpret_cast<const float4 *>(src) + c4) : make_float4(fill, fill, fill, fill);
@@ -252,7 +253,7 @@ __device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvOu
     const bool valid = gx < ph.grid_w && gy < ph.grid_h && n < p.batch;
     const int nb = valid ? n : 0;                                     // per-sample vectors of a masked row: any valid row
     float pre_add = 0.0f, map_mul = 1.0f;
-    if (p.epilogue == 1 && valid) {
+    if (p.epilogue >= 1 && valid) {
         const long long npix = (long long)gy * p.noise_row_stride + (long long)gx * p.noise_pix_stride + ph.noise_offset;
         if (p.noise) pre_add = __ldg(p.noise_weight) * __ldg(p.noise + (long long)n * p.noise_img_stride + npix);
         if (p.stylemap) {
@@ -294,7 +295,7 @@ __device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvOu
         const int ch0 = tc.n_tile * BLOCK_N + c * 32;
         const float4 *rs = p.rowscale ? reinterpret_cast<const float4 *>(p.rowscale + (long long)nb * p.cout + ch0) : nullptr;
         const float4 *s2 = p.out2 ? reinterpret_cast<const float4 *>(p.scale2 + (long long)nb * p.cout + ch0) : nullptr;
-        const float4 *bs = (p.epilogue == 1 && p.bias) ? reinterpret_cast<const float4 *>(p.bias + ch0) : nullptr;
+        const float4 *bs = (p.epilogue >= 1 && p.bias) ? reinterpret_cast<const float4 *>(p.bias + ch0) : nullptr;
         uint8_t *buf1 = stage + (stage_sel & 1) * kStageBufBytes;
         uint8_t *buf2 = stage + ((stage_sel + 1) & 1) * kStageBufBytes;
         // the store that last read buf1 (two stores ago) must have finished reading shared memory
@@ -309,7 +310,8 @@ __device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvOu
                           __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])};
             if (STAGED) { const float4 s = *reinterpret_cast<const float4 *>(vb + c * 32 + 4 * j); v[0] *= s.x; v[1] *= s.y; v[2] *= s.z; v[3] *= s.w; }
             else if (rs) { const float4 s = __ldg(rs + j); v[0] *= s.x; v[1] *= s.y; v[2] *= s.z; v[3] *= s.w; }
-            if (p.epilogue == 1) {
+            const float4 pre = make_float4(v[0], v[1], v[2], v[3]);      // demodulated conv output (epilogue 2 stores this)
+            if (p.epilogue >= 1) {
                 float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (STAGED) b = *reinterpret_cast<const float4 *>(vb + 2 * BLOCK_N + c * 32 + 4 * j);
                 else if (bs) b = __ldg(bs + j);
@@ -322,7 +324,8 @@ __device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvOu
             }
             y[4 * j] = v[0]; y[4 * j + 1] = v[1]; y[4 * j + 2] = v[2]; y[4 * j + 3] = v[3];
             // 128-byte swizzle: 16-byte chunk j of row `lane` lives at chunk j ^ (lane % 8)
-            *reinterpret_cast<float4 *>(buf1 + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4 *>(buf1 + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                (p.epilogue == 2) ? pre : make_float4(v[0], v[1], v[2], v[3]);
             if (p.rgb_w && valid) {                 // ToRGB rides the epilogue: 3 dot products over the channel chunk
                 const float *w0 = p.rgb_w + (long long)n * 3 * p.cout + ch0 + 4 * j;
 #pragma unroll
@@ -1530,7 +1533,7 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
     SR_REQUIRE(a->batch >= 1, "conv: empty problem");
     SR_REQUIRE((reinterpret_cast<uintptr_t>(a->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->weight) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "conv: tensors must be 16-byte aligned");
-    SR_REQUIRE(a->epilogue == 0 || a->epilogue == 1, "conv: unknown epilogue");
+    SR_REQUIRE(a->epilogue >= 0 && a->epilogue <= 2, "conv: unknown epilogue");
     SR_REQUIRE(!a->out2 || a->scale2, "conv: out2 needs scale2");
     SR_REQUIRE(!a->noise || a->noise_weight, "conv: noise needs noise_weight");
     int64_t max_gw = 0, max_gh = 0;

@@ -8,6 +8,7 @@
 // (a warp covers one contiguous 512-byte run), reductions in registers -> shared memory -> one global
 // atomic per (CTA, channel).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace sr {
 namespace {
@@ -53,45 +54,59 @@ struct PrologueParams {
     long long noise_bstride;
     int pixels, C4, chunks_per_image, pix_per_chunk;
     float alpha, gain;
-    // StyledMapConv (reference model.py:48-52): t = conv_d * map0[b,p] + map1[b,p] + noise_w * noise + bias.  Then the
+    // StyledMapConv (reference model.py:48-52): t = conv_d * map0[b,p] + map1[b,p] + noise_w * noise + bias.  With a
+    // stylemap `y` holds conv_d -- the demodulated (and, in an up-sampling block, filtered) conv output BEFORE the map
+    // affine, which is what the forward kernels store for these blocks -- and the activated output is rebuilt here.  The
     // gradient handed to the GEMMs is gp * map0 (* d), e = sum gp * (conv_d * map0), and per pixel
-    //   g_map1 = sum_c gp,   g_map0 = sum_c gp * conv_d = (sum_c gp * (t - map1 - noise_w * noise - bias)) / map0.
+    //   g_map1 = sum_c gp,   g_map0 = sum_c gp * conv_d          (no division: map0 may be exactly 0).
     const float *stylemap;        // [B, 2, pixels] planes (batch stride map_bstride, plane stride = pixels) or nullptr
     long long map_bstride;
     float *g_map;                 // [B, 2, pixels] contiguous, += (zeroed by the caller)
 };
 
-// grid.x = B * chunks_per_image.  MAP = StyledMapConv variant (compile-time: the plain path keeps its register budget)
-template <bool MAP>
-__global__ void __launch_bounds__(kThreads)
+// grid.x = B * chunks_per_image.  MAP = StyledMapConv variant (compile-time: the plain path keeps its register budget).
+// SPEC < 0: the optional inputs are run-time branches (one kernel for every call, 117 registers = 2 CTAs per SM).
+// SPEC >= 0: bit mask of the inputs that are present (1 gy, 2 gxs, 4 ToRGB, 8 e, 16 noise, 32 d), compiled in for the
+// combinations the chained generator produces -- the up-sampling blocks' combination needs 64 registers (4 CTAs per SM,
+// MINB), the ToRGB ones 80 (profiles/r1_prologue_specialisation_ptxas.md).  SR_PROLOGUE_SPEC=0 forces the run-time kernel.
+constexpr int kSpecGy = 1, kSpecGxs = 2, kSpecRgb = 4, kSpecE = 8, kSpecNoise = 16, kSpecD = 32;
+
+template <bool MAP, int SPEC, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 styled_bwd_prologue_kernel(const PrologueParams p)
 {
+    constexpr bool S = SPEC >= 0;
+    const bool has_gy = S ? ((SPEC & kSpecGy) != 0) : (p.gy != nullptr);
+    const bool has_gxs = S ? ((SPEC & kSpecGxs) != 0) : (p.gxs != nullptr);
+    const bool has_rgb = S ? ((SPEC & kSpecRgb) != 0) : (p.g_rgb != nullptr);
+    const bool has_e = S ? ((SPEC & kSpecE) != 0) : (p.e != nullptr);
+    const bool has_noise = S ? ((SPEC & kSpecNoise) != 0) : (p.noise != nullptr);
+    const bool has_d = S ? ((SPEC & kSpecD) != 0) : (p.d != nullptr);
     __shared__ float4 s_red[kThreads];
     __shared__ float s_nw[kThreads / 32];
     const int C4 = p.C4, lanes_p = kThreads / C4;
     const int c4 = threadIdx.x % C4, pl = threadIdx.x / C4;
     const int b = blockIdx.x / p.chunks_per_image, chunk = blockIdx.x % p.chunks_per_image;
     const int p0 = chunk * p.pix_per_chunk, p1 = min(p.pixels, p0 + p.pix_per_chunk);
-    const float4 *gy = p.gy ? reinterpret_cast<const float4 *>(p.gy) + (long long)b * p.pixels * C4 + c4 : nullptr;
-    const float4 *gxs = p.gxs ? reinterpret_cast<const float4 *>(p.gxs) + (long long)b * p.pixels * C4 + c4 : nullptr;
-    const float *grgb = p.g_rgb ? p.g_rgb + (long long)b * p.pixels * 3 : nullptr;
+    const float4 *gy = has_gy ? reinterpret_cast<const float4 *>(p.gy) + (long long)b * p.pixels * C4 + c4 : nullptr;
+    const float4 *gxs = has_gxs ? reinterpret_cast<const float4 *>(p.gxs) + (long long)b * p.pixels * C4 + c4 : nullptr;
+    const float *grgb = has_rgb ? p.g_rgb + (long long)b * p.pixels * 3 : nullptr;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 sn = gxs ? __ldg(reinterpret_cast<const float4 *>(p.s_next) + (long long)b * C4 + c4) : zero4;
+    const float4 sn = has_gxs ? __ldg(reinterpret_cast<const float4 *>(p.s_next) + (long long)b * C4 + c4) : zero4;
     float4 wrgb[3] = {zero4, zero4, zero4};
-    if (grgb) {
+    if (has_rgb) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) wrgb[k] = __ldg(reinterpret_cast<const float4 *>(p.rgb_w) + ((long long)b * 3 + k) * C4 + c4);
     }
     float4 a_ds = zero4, a_wb[3] = {zero4, zero4, zero4};
     const float4 *y = reinterpret_cast<const float4 *>(p.y) + (long long)b * p.pixels * C4 + c4;
     float4 *ga = reinterpret_cast<float4 *>(p.ga) + (long long)b * p.pixels * C4 + c4;
-    const float *nz = p.noise ? p.noise + (long long)b * p.noise_bstride : nullptr;
-    const float nw = p.noise ? __ldg(p.noise_w) : 0.0f;
-    const float4 bias = p.bias ? __ldg(reinterpret_cast<const float4 *>(p.bias) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 dd = p.d ? __ldg(reinterpret_cast<const float4 *>(p.d) + (long long)b * C4 + c4) : make_float4(1.f, 1.f, 1.f, 1.f);
-    const float pos = p.gain, neg = p.gain * p.alpha;
+    const float *nz = has_noise ? p.noise + (long long)b * p.noise_bstride : nullptr;
+    const float nw = has_noise ? __ldg(p.noise_w) : 0.0f;
+    const float4 bias = p.bias ? __ldg(reinterpret_cast<const float4 *>(p.bias) + c4) : zero4;
+    const float4 dd = has_d ? __ldg(reinterpret_cast<const float4 *>(p.d) + (long long)b * C4 + c4) : make_float4(1.f, 1.f, 1.f, 1.f);
     const float ipos = 1.0f / p.gain, ineg = 1.0f / (p.gain * p.alpha);
-    float4 a_bias = make_float4(0.f, 0.f, 0.f, 0.f), a_e = a_bias;
+    float4 a_bias = zero4, a_e = zero4;
     float a_nw = 0.0f;
     // two pixels per iteration: twice the loads in flight per thread (the pass is pure streaming)
     for (int px0 = p0 + pl; px0 < p1; px0 += 2 * lanes_p) {
@@ -104,12 +119,12 @@ styled_bwd_prologue_kernel(const PrologueParams p)
             ok[u] = pxs[u] < p1;
             const long long off = (long long)(ok[u] ? pxs[u] : px0) * C4;
             yy2[u] = __ldg(y + off);
-            g2[u] = gy ? ld_stream4(reinterpret_cast<const float *>(gy + off)) : zero4;
-            gx2[u] = gxs ? ld_stream4(reinterpret_cast<const float *>(gxs + off)) : zero4;
+            g2[u] = has_gy ? ld_stream4(reinterpret_cast<const float *>(gy + off)) : zero4;
+            gx2[u] = has_gxs ? ld_stream4(reinterpret_cast<const float *>(gxs + off)) : zero4;
             const long long pp = ok[u] ? pxs[u] : px0;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) gk2[u][k] = grgb ? __ldg(grgb + pp * 3 + k) : 0.0f;
-            n2[u] = nz ? __ldg(nz + pp) : 0.0f;
+            for (int k = 0; k < 3; ++k) gk2[u][k] = has_rgb ? __ldg(grgb + pp * 3 + k) : 0.0f;
+            n2[u] = has_noise ? __ldg(nz + pp) : 0.0f;
             m02[u] = MAP ? __ldg(p.stylemap + (long long)b * p.map_bstride + pp) : 1.0f;
             m12[u] = MAP ? __ldg(p.stylemap + (long long)b * p.map_bstride + p.pixels + pp) : 0.0f;
         }
@@ -117,10 +132,21 @@ styled_bwd_prologue_kernel(const PrologueParams p)
         for (int u = 0; u < 2; ++u) {
             if (!ok[u]) continue;
             const int px = pxs[u];
-            const float4 yy = yy2[u];
+            const float n = n2[u];
+            // MAP: the saved tensor is cd = the demodulated conv output BEFORE the map affine (see PrologueParams); the
+            // activated output is rebuilt from it with the forward's own expression.  Otherwise the saved tensor is y.
+            float4 yy = yy2[u], cd = yy2[u];
+            if (MAP) {
+                const float sh = nw * n + m12[u];
+                float t;
+                t = fmaf(cd.x, m02[u], sh + bias.x); yy.x = ((t > 0.f) ? t : t * p.alpha) * p.gain;
+                t = fmaf(cd.y, m02[u], sh + bias.y); yy.y = ((t > 0.f) ? t : t * p.alpha) * p.gain;
+                t = fmaf(cd.z, m02[u], sh + bias.z); yy.z = ((t > 0.f) ? t : t * p.alpha) * p.gain;
+                t = fmaf(cd.w, m02[u], sh + bias.w); yy.w = ((t > 0.f) ? t : t * p.alpha) * p.gain;
+            }
             float4 g = g2[u];
-            if (gxs) { f4_fma(g, gx2[u], sn); f4_fma(a_ds, gx2[u], yy); }
-            if (grgb) {
+            if (has_gxs) { f4_fma(g, gx2[u], sn); f4_fma(a_ds, gx2[u], yy); }
+            if (has_rgb) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const float4 g4 = make_float4(gk2[u][k], gk2[u][k], gk2[u][k], gk2[u][k]);
@@ -128,26 +154,23 @@ styled_bwd_prologue_kernel(const PrologueParams p)
                     f4_fma(a_wb[k], g4, yy);
                 }
             }
-            const float n = n2[u];
-            float4 gp, uu;
+            float4 gp;
             // reference op/fused_bias_act_kernel.cu:31: (ref > 0 ? g : g*alpha) * scale
             gp.x = ((yy.x > 0.f) ? g.x : g.x * p.alpha) * p.gain; gp.y = ((yy.y > 0.f) ? g.y : g.y * p.alpha) * p.gain;
             gp.z = ((yy.z > 0.f) ? g.z : g.z * p.alpha) * p.gain; gp.w = ((yy.w > 0.f) ? g.w : g.w * p.alpha) * p.gain;
             f4_add(a_bias, gp);
             a_nw += ((gp.x + gp.y) + (gp.z + gp.w)) * n;
-            if (p.e || MAP) {
-                // the pre-activation is recoverable from y (gain, alpha > 0): t = y / gain or y / (gain * alpha)
-                uu.x = yy.x * ((yy.x > 0.f) ? ipos : ineg); uu.y = yy.y * ((yy.y > 0.f) ? ipos : ineg);
-                uu.z = yy.z * ((yy.z > 0.f) ? ipos : ineg); uu.w = yy.w * ((yy.w > 0.f) ? ipos : ineg);
-                const float sh = MAP ? nw * n + m12[u] : nw * n;
-                uu.x -= sh + bias.x; uu.y -= sh + bias.y; uu.z -= sh + bias.z; uu.w -= sh + bias.w;
-                if (p.e) f4_fma(a_e, gp, uu);
-            }
             if (MAP) {
-                // per-pixel reductions over the channels: the C4 threads of a pixel are consecutive (whole warps when
-                // C4 >= 32, aligned sub-warp groups when C4 is a smaller power of two)
+                // e = sum gp * (cd * map0); per pixel g_map0 = sum_c gp * cd and g_map1 = sum_c gp -- no division by the
+                // map (background pixels of the rasterised normal map have map0 == 0 exactly at default init).
+                // The C4 threads of a pixel are consecutive (whole warps when C4 >= 32, aligned sub-warp groups when C4
+                // is a smaller power of two).
+                if (has_e) {
+                    const float4 cm = make_float4(cd.x * m02[u], cd.y * m02[u], cd.z * m02[u], cd.w * m02[u]);
+                    f4_fma(a_e, gp, cm);
+                }
                 float s1 = (gp.x + gp.y) + (gp.z + gp.w);
-                float s0 = fmaf(gp.x, uu.x, fmaf(gp.y, uu.y, fmaf(gp.z, uu.z, gp.w * uu.w)));
+                float s0 = fmaf(gp.x, cd.x, fmaf(gp.y, cd.y, fmaf(gp.z, cd.z, gp.w * cd.w)));
                 const int width = C4 < 32 ? C4 : 32;
                 const unsigned amask = __activemask();          // sub-warp pixel groups may be masked off independently
                 for (int o_ = width >> 1; o_ > 0; o_ >>= 1) {
@@ -156,26 +179,33 @@ styled_bwd_prologue_kernel(const PrologueParams p)
                 }
                 if ((threadIdx.x & (width - 1)) == 0) {
                     float *gm = p.g_map + (long long)b * 2 * p.pixels + px;
-                    atomicAdd(gm, s0 / m02[u]);
+                    atomicAdd(gm, s0);
                     atomicAdd(gm + p.pixels, s1);
                 }
                 gp.x *= m02[u]; gp.y *= m02[u]; gp.z *= m02[u]; gp.w *= m02[u];
+            } else if (has_e) {
+                // the pre-activation is recoverable from y (gain, alpha > 0): t = y / gain or y / (gain * alpha)
+                float4 uu;
+                uu.x = yy.x * ((yy.x > 0.f) ? ipos : ineg); uu.y = yy.y * ((yy.y > 0.f) ? ipos : ineg);
+                uu.z = yy.z * ((yy.z > 0.f) ? ipos : ineg); uu.w = yy.w * ((yy.w > 0.f) ? ipos : ineg);
+                const float sh = nw * n;
+                uu.x -= sh + bias.x; uu.y -= sh + bias.y; uu.z -= sh + bias.z; uu.w -= sh + bias.w;
+                f4_fma(a_e, gp, uu);
             }
             float4 o = f4_mul(gp, dd);
-            if (p.d) o = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
+            if (has_d) o = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
             ga[(long long)px * C4] = o;
         }
     }
-    (void)pos; (void)neg;
     block_reduce_quads(a_bias, s_red, c4, pl, C4, lanes_p, p.g_bias);
-    if (p.e) block_reduce_quads(a_e, s_red, c4, pl, C4, lanes_p, p.e + (long long)b * C4 * 4);
-    if (gxs) block_reduce_quads(a_ds, s_red, c4, pl, C4, lanes_p, p.ds_next + (long long)b * C4 * 4);
-    if (grgb) {
+    if (has_e) block_reduce_quads(a_e, s_red, c4, pl, C4, lanes_p, p.e + (long long)b * C4 * 4);
+    if (has_gxs) block_reduce_quads(a_ds, s_red, c4, pl, C4, lanes_p, p.ds_next + (long long)b * C4 * 4);
+    if (has_rgb) {
 #pragma unroll
         for (int k = 0; k < 3; ++k)
             block_reduce_quads(a_wb[k], s_red, c4, pl, C4, lanes_p, p.d_rgb_w + ((long long)b * 3 + k) * C4 * 4);
     }
-    if (p.noise) {
+    if (has_noise) {
         a_nw = warp_sum(a_nw);
         if ((threadIdx.x & 31) == 0) s_nw[threadIdx.x >> 5] = a_nw;
         __syncthreads();
@@ -278,8 +308,31 @@ extern "C" int sr_styled_bwd_prologue3_f32(float *ga, float *g_bias, float *g_no
     p.chunks_per_image = pick_chunks(batch, pixels, p.C4, &p.pix_per_chunk);
     p.alpha = alpha; p.gain = gain;
     p.stylemap = stylemap; p.map_bstride = stylemap_batch_stride; p.g_map = g_stylemap;
-    if (stylemap) styled_bwd_prologue_kernel<true><<<(unsigned)(batch * p.chunks_per_image), kThreads, 0, st>>>(p);
-    else styled_bwd_prologue_kernel<false><<<(unsigned)(batch * p.chunks_per_image), kThreads, 0, st>>>(p);
+    const unsigned nb = (unsigned)(batch * p.chunks_per_image);
+    // kernels specialised on the inputs present (see styled_bwd_prologue_kernel); SR_PROLOGUE_SPEC=0: run-time checks only
+    static const char *spec_env = getenv("SR_PROLOGUE_SPEC");
+    const int spec = (gy ? kSpecGy : 0) | (gxs ? kSpecGxs : 0) | (g_rgb ? kSpecRgb : 0) | (e ? kSpecE : 0) |
+                     (noise ? kSpecNoise : 0) | (d ? kSpecD : 0);
+    bool launched = false;
+    const bool spec_rgb = !(spec_env && spec_env[0] == '2');       // A/B: 2 = ToRGB combinations stay on the run-time kernel
+    if (!(spec_env && spec_env[0] == '0') && !stylemap && (spec_rgb || !g_rgb)) {
+        launched = true;
+        switch (spec) {                                   // the combinations the chained generator produces
+        case kSpecGxs | kSpecE | kSpecNoise:                                     // up-sampling block
+            styled_bwd_prologue_kernel<false, kSpecGxs | kSpecE | kSpecNoise, 4><<<nb, kThreads, 0, st>>>(p); break;
+        case kSpecGxs | kSpecE | kSpecNoise | kSpecD:                            // plain block without ToRGB
+            styled_bwd_prologue_kernel<false, kSpecGxs | kSpecE | kSpecNoise | kSpecD, 4><<<nb, kThreads, 0, st>>>(p); break;
+        case kSpecGxs | kSpecRgb | kSpecE | kSpecNoise | kSpecD:                 // plain block with ToRGB
+            styled_bwd_prologue_kernel<false, kSpecGxs | kSpecRgb | kSpecE | kSpecNoise | kSpecD, 3><<<nb, kThreads, 0, st>>>(p); break;
+        case kSpecGy | kSpecRgb | kSpecE | kSpecNoise | kSpecD:                  // last block (image gradient + ToRGB)
+            styled_bwd_prologue_kernel<false, kSpecGy | kSpecRgb | kSpecE | kSpecNoise | kSpecD, 3><<<nb, kThreads, 0, st>>>(p); break;
+        default: launched = false;
+        }
+    }
+    if (!launched) {
+        if (stylemap) styled_bwd_prologue_kernel<true, -1, 1><<<nb, kThreads, 0, st>>>(p);
+        else styled_bwd_prologue_kernel<false, -1, 1><<<nb, kThreads, 0, st>>>(p);
+    }
     count_launch();
     return check_launch("sr_styled_bwd_prologue_f32");
 }

@@ -484,7 +484,8 @@ struct NhwcGeom {
     // SCALEDOT epilogue (backward of the up-sampling block): out = tf32(acc * scale2[n,c]), dot[n,c] += sum acc * other
     const float *other;
     float *dot;
-    // STYLED with a style map (StyledMapConv, reference model.py:50): y = lrelu(acc * map0 + map1 + noise + bias) * gain
+    // STYLED with a style map (StyledMapConv, reference model.py:50): y = lrelu(acc * map0 + map1 + noise + bias) * gain;
+    // `out` then receives acc (what the backward needs; map0 may be exactly 0) and only out2 sees y
     const float *stylemap;        // [B, 2, out_h, out_w] planes (batch stride map_bstride) or nullptr
     long long map_bstride;
 };
@@ -560,6 +561,7 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
                     acc[j].x = fmaf(v.x, k, acc[j].x); acc[j].y = fmaf(v.y, k, acc[j].y);
                     acc[j].z = fmaf(v.z, k, acc[j].z); acc[j].w = fmaf(v.w, k, acc[j].w);
                 }
+        float4 pre[2] = {acc[0], acc[1]};                  // filtered value before the tail (stored instead of y with a stylemap)
         if (STYLED) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -588,8 +590,9 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
             }
         }
         float4 *dst = yout + ((int64_t)oy * g.out_w + ox0) * g.c4;
-        dst[0] = acc[0];
-        if (ox0 + 1 < g.out_w) dst[g.c4] = acc[1];
+        const bool keep_pre = STYLED && g.stylemap;
+        dst[0] = keep_pre ? pre[0] : acc[0];
+        if (ox0 + 1 < g.out_w) dst[g.c4] = keep_pre ? pre[1] : acc[1];
         if (STYLED && g.out2) {
             float4 *dst2 = reinterpret_cast<float4 *>(g.out2) + (int64_t)n * g.out_h * g.out_w * g.c4 + c +
                            ((int64_t)oy * g.out_w + ox0) * g.c4;
@@ -757,6 +760,7 @@ fir_nhwc_ring_kernel(float *__restrict__ out, const float *__restrict__ x, const
         }
         if (oy >= oy0) {
             float4 o[2] = {acc[0][0], acc[0][1]};
+            const float4 pre[2] = {acc[0][0], acc[0][1]};      // stored instead of y with a stylemap
             if (STYLED) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -786,8 +790,9 @@ fir_nhwc_ring_kernel(float *__restrict__ out, const float *__restrict__ x, const
                 }
             }
             float4 *dst = yout + ((int64_t)oy * g.out_w + ox0) * g.c4;
-            dst[0] = o[0];
-            if (col1) dst[g.c4] = o[1];
+            const bool keep_pre = STYLED && g.stylemap;
+            dst[0] = keep_pre ? pre[0] : o[0];
+            if (col1) dst[g.c4] = keep_pre ? pre[1] : o[1];
             if (STYLED && g.out2) {
                 float4 *dst2 = reinterpret_cast<float4 *>(g.out2) + (int64_t)n * g.out_h * g.out_w * g.c4 + c +
                                ((int64_t)oy * g.out_w + ox0) * g.c4;

@@ -28,8 +28,23 @@ def from_nhwc(x):
 
 
 def supported(mod, x):
+    """Shapes the fused tensor-core blocks take.  The up-sampling blocks hard-code the reference's default FIR geometry
+    (4x4 taps, pad (1,1), reference layers.py:270-275 with blur_kernel of length 4): any other blur_kernel takes the
+    composed path."""
+    if mod.upsample and not (tuple(mod.blur.kernel.shape) == (4, 4) and tuple(mod.blur.pad) == (1, 1)):
+        return False
     return (x.is_cuda and x.dtype == torch.float32 and mod.kernel_size == 3 and not mod.downsample and mod.demodulate
             and tc.supported(mod.in_channel, mod.out_channel) and tc.wgrad_supported(mod.in_channel, mod.out_channel))
+
+
+def _noise_needs_grad(noise):
+    """The fused blocks return no gradient for the noise input (per-layer noise optimisation, StyleGAN2 projection):
+    such calls take the composed path, which propagates it."""
+    if noise is None:
+        return False
+    if isinstance(noise, (list, tuple)):
+        return any(_noise_needs_grad(n) for n in noise)
+    return torch.is_grad_enabled() and noise.requires_grad
 
 
 class StyledConvTC(Function):
@@ -412,9 +427,12 @@ class StyledLayerTC(Function):
             y = torch.empty(b, h, w, cout, dtype=torch.float32, device=xs.device)
             y2 = torch.empty_like(y) if s_next is not None else None
             rgb = torch.empty(b, h, w, 3, dtype=torch.float32, device=xs.device) if rgb_weight is not None else None
-            tc.conv3x3(xs_nhwc, wk, out=y, epilogue=1, rowscale=d, bias=act_bias, alpha=alpha, gain=gain,
-                       noise=noise.reshape(-1, h, w).contiguous(), noise_weight=noise_weight, out2=y2, scale2=s_next,
-                       rgb_weight=rgb_weight, rgb_out=rgb, stylemap=stylemap)
+            # StyledMapConv: `y` receives the demodulated conv output before the map affine (epilogue 2); the backward
+            # prologue rebuilds the activated value from it -- a map that is exactly 0 (background of the rasterised
+            # normals at default init) makes it unrecoverable from the activated one
+            tc.conv3x3(xs_nhwc, wk, out=y, epilogue=2 if stylemap is not None else 1, rowscale=d, bias=act_bias, alpha=alpha,
+                       gain=gain, noise=noise.reshape(-1, h, w).contiguous(), noise_weight=noise_weight, out2=y2,
+                       scale2=s_next, rgb_weight=rgb_weight, rgb_out=rgb, stylemap=stylemap)
         else:
             assert rgb_weight is None
             t = tc.conv_transpose3x3_s2(xs_nhwc, wk, rowscale=d)
@@ -425,7 +443,11 @@ class StyledLayerTC(Function):
                 y = tc.blur_styled(t, blur_taps, (1, 1), noise, noise_weight, act_bias, alpha, gain, stylemap=stylemap)
         ctx.save_for_backward(xs_nhwc, y, None, weight, d, noise, noise_weight, act_bias, blur_taps, s_next, rgb_weight, stylemap)
         ctx.cfg = (scale, upsample, alpha, gain)
-        main = from_nhwc(y2 if s_next is not None else y)
+        if s_next is None and stylemap is not None:          # y holds the pre-map value: no activated output to hand on
+            main = xs.new_zeros(1)
+            ctx.mark_non_differentiable(main)
+        else:
+            main = from_nhwc(y2 if s_next is not None else y)
         if rgb is None:
             rgb = xs.new_zeros(1)
             ctx.mark_non_differentiable(rgb)
@@ -472,9 +494,11 @@ class StyledLayerTC(Function):
                 g_map)
 
 
-def chain_supported(gen, x):
+def chain_supported(gen, x, noise=None):
     from . import layers as L
     if L.get_conv_backend() != "tcgen05" or (torch.is_grad_enabled() and L.double_backward_requested()):
+        return False
+    if _noise_needs_grad(noise):
         return False
     blocks = [gen.conv1] + list(gen.convs)
     return all(type(m).__name__ in ("StyledConv", "StyledMapConv") and supported(m.conv, x) for m in blocks)

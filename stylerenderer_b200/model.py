@@ -30,7 +30,8 @@ class StyledConv(nn.Module):                          # reference model.py:11-32
 
     def forward(self, input, style, noise=None):
         if (layers.get_conv_backend() == "tcgen05" and fused.supported(self.conv, input)
-                and not (torch.is_grad_enabled() and layers.double_backward_requested())):
+                and not (torch.is_grad_enabled() and layers.double_backward_requested())
+                and not fused._noise_needs_grad(noise)):
             return fused.styled_conv(self.conv, self.noise, self.activate, input, style, noise)
         out = self.conv(input, style)
         out = self.noise(out, noise=noise)
@@ -146,7 +147,7 @@ class Generator(nn.Module):                           # reference model.py:71-18
                 input_is_latent=False, noise=None, randomize_noise=True):
         latent, noise = self._prepare(styles, inject_index, truncation, truncation_latent, input_is_latent, noise,
                                       randomize_noise)
-        if type(self) is Generator and latent.is_cuda and fused.chain_supported(self, self.input.input):
+        if type(self) is Generator and latent.is_cuda and fused.chain_supported(self, self.input.input, noise):
             # chained tensor-core blocks: modulated operands handed from epilogue to GEMM, ToRGB fused (fused.py)
             skip = fused.generator_chain_forward(self, latent, noise)
             return (skip, latent) if return_latents else (skip, None)
@@ -200,7 +201,7 @@ class GeneratorWithMap(Generator):                    # reference model.py:188-2
                 truncation_latent=None, input_is_latent=False, noise=None, randomize_noise=True):
         latent, noise = self._prepare(styles, inject_index, truncation, truncation_latent, input_is_latent, noise,
                                       randomize_noise)
-        if latent.is_cuda and fused.chain_supported(self, self.input.input):
+        if latent.is_cuda and fused.chain_supported(self, self.input.input, noise):
             # chained tensor-core StyledMapConv blocks (fused.py); the rasterised normal maps and the style-map nets are
             # evaluated per resolution exactly as below and handed to the blocks' epilogues
             norm_maps, cache = [], {}

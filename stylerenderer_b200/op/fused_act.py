@@ -109,7 +109,10 @@ class FusedLeakyReLU(nn.Module):                    # reference op/fused_act.py:
 
 
 def fused_leaky_relu(input, bias, negative_slope=0.2, scale=2 ** 0.5):
-    """reference op/fused_act.py:86-97.  CUDA tensors only; the slope argument is honoured (the reference's
-    CPU branch ignores it, its CUDA branch does not)."""
-    _lib.require_cuda(input, "fused_leaky_relu")
+    """reference op/fused_act.py:86-97: CPU tensors take plain torch ops (like the reference's dispatcher), CUDA tensors
+    the sm_100a kernel (no fallback there).  The reference's CPU branch hard-codes slope 0.2 whatever `negative_slope`
+    says (op/fused_act.py:91); that is reproduced, because it is what every CPU caller of the reference gets."""
+    if input.device.type == "cpu":
+        shape = [1, bias.shape[0]] + [1] * (input.dim() - 2)
+        return torch.nn.functional.leaky_relu(input + bias.reshape(shape), 0.2) * scale
     return FusedLeakyReLUFunction.apply(input, bias, negative_slope, scale)

@@ -106,7 +106,28 @@ class UpFirDn2d(Function):                          # reference op/upfirdn2d.py:
         return grad_input, None, None, None, None
 
 
+def upfirdn2d_cpu(input, kernel, up=1, down=1, pad=(0, 0)):
+    """The operator on CPU tensors in plain torch ops (differentiable to any order through autograd) -- the role of the
+    reference's `upfirdn2d_native` (reference op/upfirdn2d.py:159-200), which its dispatcher takes for CPU tensors
+    (op/upfirdn2d.py:146-150; callers: utils_face.py:515-517, BASELINE.json configs[0]).  Steps per [n, c] plane:
+    zero-stuff by `up`, pad (negative pads crop), true convolution with `kernel`, keep every `down`-th sample."""
+    import torch.nn.functional as F
+    n, c, h, w = input.shape
+    kh, kw = kernel.shape
+    planes = input.reshape(n * c, 1, h, w)
+    if up > 1:                                                   # sample (i, j) -> (i*up, j*up), zeros in between
+        stuffed = planes.new_zeros(n * c, 1, h * up, w * up)
+        stuffed[:, :, ::up, ::up] = planes
+        planes = stuffed
+    planes = F.pad(planes, [pad[0], pad[1], pad[0], pad[1]])     # F.pad crops for negative amounts
+    taps = torch.flip(kernel, [0, 1]).to(planes.dtype).reshape(1, 1, kh, kw)   # conv2d correlates: flip = convolution
+    out = F.conv2d(planes, taps)[:, :, ::down, ::down]
+    return out.reshape(n, c, out.shape[2], out.shape[3])
+
+
 def upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0)):
-    """reference op/upfirdn2d.py:145-157.  CUDA tensors only (no native-PyTorch CPU fallback here)."""
-    _lib.require_cuda(input, "upfirdn2d")
+    """reference op/upfirdn2d.py:145-157: CPU tensors take the plain-torch formulation (like the reference's dispatcher),
+    CUDA tensors the sm_100a kernel -- which fails loudly when the library is missing, it never falls back."""
+    if input.device.type == "cpu":
+        return upfirdn2d_cpu(input, kernel, up, down, pad)
     return UpFirDn2d.apply(input, kernel, (up, up), (down, down), (pad[0], pad[1], pad[0], pad[1]))

@@ -42,6 +42,70 @@ def supported(cin, cout):
     return cin % 32 == 0 and cin >= 32 and cout % 128 == 0 and cout >= 128
 
 
+# ------------------------------------------------------------------------------------------------- operand precision
+# "tf32"   (default): GEMM operands are rounded to tf32 by the kernels that produce them (cvt.rna), one MMA per product:
+#          the arithmetic class of the reference's cuDNN path under torch's default cudnn.allow_tf32 = True.
+# "tf32x3" (parity mode): fp32-faithful split operands.  Every operand x is split into hi = tf32(x) and lo = x - hi and the
+#          SAME tcgen05 pipelines accumulate  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  into one TMEM accumulator: the conv
+#          kernels get the three terms as a three times longer K loop (operand channels [hi | lo | hi] against weight
+#          columns [hi | hi | lo]), the weight-gradient kernel as three accumulating launches.  Products then carry
+#          ~2^-21 relative error instead of 2^-11, so no leaky-ReLU mask flips and every gradient can be checked at the
+#          1e-3 bar with generic inputs.  3x the tensor-core work plus unfused glue passes: a checking mode, not a fast one.
+_PRECISION = {"mode": "tf32"}
+
+
+def set_precision(mode):
+    assert mode in ("tf32", "tf32x3")
+    _PRECISION["mode"] = mode
+
+
+def get_precision():
+    return _PRECISION["mode"]
+
+
+class precision:
+    """with tc_conv.precision("tf32x3"): ... (restores the previous mode)."""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = get_precision()
+        set_precision(self.mode)
+
+    def __exit__(self, *a):
+        set_precision(self.prev)
+
+
+def _exact():
+    return _PRECISION["mode"] == "tf32x3"
+
+
+def split_tf32(x):
+    """x -> (hi, lo): hi = x rounded to tf32 (nearest, ties away: the bit trick equals cvt.rna.tf32.f32), lo = x - hi
+    (exact in fp32; the tensor core then truncates lo to its own 10 mantissa bits, a 2^-21 relative residual)."""
+    xi = x.contiguous().view(torch.int32)
+    hi = ((xi + 0x1000) & -0x2000).view(torch.float32)
+    return hi, x - hi
+
+
+def _lrelu(t, alpha, gain):
+    return torch.where(t > 0, t, t * alpha) * gain
+
+
+def _styled_tail(pre, noise, noise_weight, bias, stylemap, alpha, gain):
+    """y = lrelu(pre (* map0 + map1) + noise_weight * noise + bias) * gain on NHWC tensors (tf32x3 glue only)."""
+    b, h, w, _ = pre.shape
+    t = pre
+    if stylemap is not None:
+        t = t * stylemap[:, 0].reshape(b, h, w, 1) + stylemap[:, 1].reshape(b, h, w, 1)
+    if noise is not None:
+        t = t + noise_weight * noise.reshape(-1, h, w, 1)
+    if bias is not None:
+        t = t + bias
+    return _lrelu(t, alpha, gain)
+
+
 def _check_nhwc(t, name):
     if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.is_contiguous()):
         raise RuntimeError(f"{name}: expected a contiguous float32 CUDA tensor [batch, h, w, channels]")
@@ -52,6 +116,13 @@ def weight_prep(w, scale, mode):
     mode 0: rows=cout, cols=cin (forward);  1: rows=cin, cols=cout, taps flipped (dgrad of the plain conv);
     mode 2: rows=cin, cols=cout, taps as is (dgrad of the stride-2 transposed conv)."""
     cout, cin, kh, kw = w.shape
+    if _exact():                                             # same layouts, unrounded (split by the GEMM wrappers)
+        ws = w.detach() * scale
+        if mode in (0, 3):
+            return ws.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin).contiguous()
+        if mode == 1:
+            ws = ws.flip(2, 3)
+        return ws.permute(1, 2, 3, 0).reshape(cin, kh * kw, cout).contiguous()
     rows, cols = (cout, cin) if mode in (0, 3) else (cin, cout)
     dst = torch.empty(rows, kh * kw, cols, dtype=torch.float32, device=w.device)
     wc = w.contiguous()
@@ -66,6 +137,10 @@ def weight_prep_dual(w, scale, flip_transposed, want_wsq=True):
     """One pass over a [cout, cin, k, k] weight -> (fwd [cout, k*k, cin], tr [cin, k*k, cout], wsq [cout, cin] or None):
     weight_prep(mode 0), weight_prep(mode 1 if flip_transposed else 2) and scale^2 * sum_taps w^2 together."""
     cout, cin, kh, kw = w.shape
+    if _exact():
+        ws = w.detach() * scale
+        return (weight_prep(w, scale, 0), weight_prep(w, scale, 1 if flip_transposed else 2),
+                ws.pow(2).sum((2, 3)) if want_wsq else None)
     wc = w.contiguous()
     fwd = torch.empty(cout, kh * kw, cin, dtype=torch.float32, device=w.device)
     tr = torch.empty(cin, kh * kw, cout, dtype=torch.float32, device=w.device)
@@ -81,6 +156,8 @@ def modulate(x, style=None):
     """xs = tf32_round(x * style[b, c]) for NHWC x [B,H,W,C]; style [B,C] or None (rounding only)."""
     _check_nhwc(x, "modulate")
     b, h, w, c = x.shape
+    if _exact():
+        return x * style.reshape(b, 1, 1, c) if style is not None else x.clone()
     xs = torch.empty_like(x)
     s = style.contiguous() if style is not None else None
     with torch.cuda.device(x.device):
@@ -110,7 +187,10 @@ def _fill_args(a, x, wmat, taps, out, in_stride, grid, out_stride, out_origin, e
     a.noise, a.noise_weight, a.stylemap = _lib.ptr(noise), _lib.ptr(noise_weight), _lib.ptr(stylemap)
     if noise is not None:
         assert noise.is_contiguous() and noise.shape[-2:] == out.shape[1:3]
-        a.noise_batch_stride = 0 if noise.numel() == out.shape[1] * out.shape[2] else out.shape[1] * out.shape[2]
+        plane = out.shape[1] * out.shape[2]
+        if noise.numel() not in (plane, plane * out.shape[0]):
+            raise RuntimeError(f"noise batch must be 1 or {out.shape[0]} (got {noise.numel() // max(plane, 1)} planes)")
+        a.noise_batch_stride = 0 if noise.numel() == plane else plane
     if stylemap is not None:
         assert stylemap.shape[1] == 2 and stylemap.stride(3) == 1 and stylemap.stride(2) == out.shape[2] \
             and stylemap.stride(1) == out.shape[1] * out.shape[2]
@@ -125,6 +205,11 @@ def conv_igemm_multi(x, wmat, phases, out, *, in_stride=1, out_stride=1, epilogu
     _check_nhwc(x, "conv input")
     _check_nhwc(out, "conv output")
     assert wmat.is_contiguous() and wmat.shape[2] == x.shape[3] and out.shape[3] == wmat.shape[0] and out.shape[0] == x.shape[0]
+    if _exact():                     # split operands: K = [hi | lo | hi] x [hi | hi | lo] through the same kernels
+        xh, xl = split_tf32(x)
+        wh, wl = split_tf32(wmat)
+        x = torch.cat([xh, xl, xh], 3)
+        wmat = torch.cat([wh, wh, wl], 2)
     arr = (ConvArgs * len(phases))()
     for a, (taps, grid, origin) in zip(arr, phases):
         _fill_args(a, x, wmat, taps, out, in_stride, grid, out_stride, origin, epilogue, rowscale, out2, scale2, bias, noise,
@@ -132,6 +217,9 @@ def conv_igemm_multi(x, wmat, phases, out, *, in_stride=1, out_stride=1, epilogu
     with torch.cuda.device(x.device):
         rc = _lib.lib().sr_conv_igemm_multi_tf32(arr, len(phases), _lib.stream_of(x))
     _lib.check(rc, "sr_conv_igemm_multi_tf32")
+    if _exact() and out2 is not None:   # the next layer's operand, unrounded (the kernel wrote its tf32 rounding)
+        y = out if epilogue != 2 else _styled_tail(out, noise, noise_weight, bias, stylemap, alpha, gain)
+        out2.copy_(y * scale2.reshape(out.shape[0], 1, 1, -1))
     return out
 
 
@@ -193,9 +281,17 @@ def wgrad(g, x, taps, grid, *, g_stride=1, x_stride=1, taps_total=9, dw=None):
     if dw is None:
         dw = torch.empty(g.shape[3], taps_total, x.shape[3], dtype=torch.float32, device=g.device)
     a.dw, a.taps_total, a.zero_init = _lib.ptr(dw), taps_total, 1
+    if _exact():                     # G_hi X_hi + G_lo X_hi + G_hi X_lo accumulated by three launches of the same kernel
+        gh, gl = split_tf32(g)
+        xh, xl = split_tf32(x)
+        terms = [(gh, xh), (gl, xh), (gh, xl)]
+    else:
+        terms = [(g, x)]
     with torch.cuda.device(g.device):
-        rc = _lib.lib().sr_conv_wgrad_tf32(ctypes.byref(a), _lib.stream_of(g))
-    _lib.check(rc, "sr_conv_wgrad_tf32")
+        for i, (gt, xt) in enumerate(terms):
+            a.g, a.x, a.zero_init = _lib.ptr(gt), _lib.ptr(xt), 1 if i == 0 else 0
+            rc = _lib.lib().sr_conv_wgrad_tf32(ctypes.byref(a), _lib.stream_of(g))
+            _lib.check(rc, "sr_conv_wgrad_tf32")
     return dw
 
 
@@ -211,10 +307,12 @@ def wgrad_transpose3x3_s2(g, x):
     return wgrad(g, x, taps, (x.shape[1], x.shape[2]), g_stride=2)
 
 
-def _noise_args(noise, oh, ow):
+def _noise_args(noise, oh, ow, batch=None):
     if noise is None:
         return None, 0
     nz = noise.reshape(-1, oh, ow).contiguous()
+    if batch is not None and nz.shape[0] not in (1, batch):
+        raise RuntimeError(f"noise batch must be 1 or {batch} (got {nz.shape[0]})")
     return nz, (0 if nz.shape[0] == 1 else oh * ow)
 
 
@@ -235,7 +333,7 @@ def blur_styled(t, taps, pad, noise, noise_weight, bias, alpha, gain, scale2=Non
     oh, ow = ih + pad[0] + pad[1] - 3, iw + pad[0] + pad[1] - 3
     out = torch.empty(b, oh, ow, c, dtype=torch.float32, device=t.device)
     out2 = torch.empty_like(out) if scale2 is not None else None
-    nz, nbs = _noise_args(noise, oh, ow)
+    nz, nbs = _noise_args(noise, oh, ow, b)
     sm, sms = _map_args(stylemap, oh, ow)
     with torch.cuda.device(t.device):
         rc = _lib.lib().sr_blur_nhwc_styled3_f32(_lib.ptr(out), _lib.ptr(out2), _lib.ptr(scale2), _lib.ptr(t),
@@ -243,6 +341,9 @@ def blur_styled(t, taps, pad, noise, noise_weight, bias, alpha, gain, scale2=Non
                                                  _lib.ptr(noise_weight), _lib.ptr(bias), float(alpha), float(gain),
                                                  _lib.ptr(sm), sms, _lib.stream_of(t))
     _lib.check(rc, "sr_blur_nhwc_styled3_f32")
+    if _exact() and scale2 is not None:
+        y = out if stylemap is None else _styled_tail(out, noise, noise_weight, bias, stylemap, alpha, gain)
+        out2.copy_(y * scale2.reshape(b, 1, 1, c))
     return out if scale2 is None else (out, out2)
 
 
@@ -256,12 +357,15 @@ def bwd_prologue(gy, y, noise, noise_weight, bias, d, alpha, gain, want_e):
     g_bias = torch.empty(c, dtype=torch.float32, device=dev)
     g_nw = torch.empty(1, dtype=torch.float32, device=dev)
     e = torch.empty(b, c, dtype=torch.float32, device=dev) if want_e else None
-    nz, nbs = _noise_args(noise, h, w)
+    nz, nbs = _noise_args(noise, h, w, b)
+    d_k = None if _exact() else d                       # tf32x3: the kernel leaves g_pre unrounded, * d below
     with torch.cuda.device(dev):
         rc = _lib.lib().sr_styled_bwd_prologue_f32(_lib.ptr(ga), _lib.ptr(g_bias), _lib.ptr(g_nw), _lib.ptr(e), _lib.ptr(gy),
                                                    _lib.ptr(y), _lib.ptr(nz), nbs, _lib.ptr(noise_weight), _lib.ptr(bias),
-                                                   _lib.ptr(d), b, h * w, c, float(alpha), float(gain), _lib.stream_of(y))
+                                                   _lib.ptr(d_k), b, h * w, c, float(alpha), float(gain), _lib.stream_of(y))
     _lib.check(rc, "sr_styled_bwd_prologue_f32")
+    if d is not None and d_k is None:
+        ga = ga * d.reshape(b, 1, 1, c)
     return ga, g_bias, g_nw, e
 
 
@@ -271,6 +375,8 @@ def scale_dot(a, other, scale, round_out, want_out=True):
     b, h, w, c = a.shape
     out = torch.empty_like(a) if want_out else None
     dot = torch.empty(b, c, dtype=torch.float32, device=a.device) if other is not None else None
+    if _exact():
+        round_out = False
     with torch.cuda.device(a.device):
         rc = _lib.lib().sr_scale_dot_nhwc_f32(_lib.ptr(out), _lib.ptr(dot), _lib.ptr(a), _lib.ptr(other),
                                               _lib.ptr(scale.contiguous() if scale is not None else None), b, h * w, c,
@@ -292,7 +398,7 @@ def bwd_prologue2(y, noise, noise_weight, bias, d, alpha, gain, want_e, gy=None,
     e = torch.empty(b, c, dtype=torch.float32, device=dev) if want_e else None
     ds_next = torch.empty(b, c, dtype=torch.float32, device=dev) if gxs is not None else None
     dwb = torch.empty(b, 3, c, dtype=torch.float32, device=dev) if g_rgb is not None else None
-    nz, nbs = _noise_args(noise, h, w)
+    nz, nbs = _noise_args(noise, h, w, b)
     for t_ in (gy, gxs):
         if t_ is not None:
             _check_nhwc(t_, "bwd_prologue2 gradient")
@@ -300,13 +406,16 @@ def bwd_prologue2(y, noise, noise_weight, bias, d, alpha, gain, want_e, gy=None,
         assert g_rgb.is_contiguous() and g_rgb.shape == (b, h, w, 3) and rgb_weight.is_contiguous()
     sm, sms = _map_args(stylemap, h, w)
     g_map = torch.empty(b, 2, h, w, dtype=torch.float32, device=dev) if sm is not None else None
+    d_k = None if _exact() else d                       # tf32x3: the kernel leaves g_pre unrounded, * d below
     with torch.cuda.device(dev):
         rc = _lib.lib().sr_styled_bwd_prologue3_f32(
             _lib.ptr(ga), _lib.ptr(g_bias), _lib.ptr(g_nw), _lib.ptr(e), _lib.ptr(ds_next), _lib.ptr(dwb), _lib.ptr(gy),
             _lib.ptr(gxs), _lib.ptr(s_next), _lib.ptr(g_rgb), _lib.ptr(rgb_weight), _lib.ptr(y), _lib.ptr(nz), nbs,
-            _lib.ptr(noise_weight), _lib.ptr(bias), _lib.ptr(d), b, h * w, c, float(alpha), float(gain), _lib.ptr(sm), sms,
+            _lib.ptr(noise_weight), _lib.ptr(bias), _lib.ptr(d_k), b, h * w, c, float(alpha), float(gain), _lib.ptr(sm), sms,
             _lib.ptr(g_map), _lib.stream_of(y))
     _lib.check(rc, "sr_styled_bwd_prologue3_f32")
+    if d is not None and d_k is None:
+        ga = ga * d.reshape(b, 1, 1, c)
     if sm is not None:
         return ga, g_bias, g_nw, e, ds_next, dwb, g_map
     return ga, g_bias, g_nw, e, ds_next, dwb
@@ -319,6 +428,10 @@ def blur_scaledot(x, taps, pad, scale, other=None):
     b, ih, iw, c = x.shape
     oh, ow = ih + pad[0] + pad[1] - 3, iw + pad[0] + pad[1] - 3
     assert other is None or (other.shape == (b, oh, ow, c) and other.is_contiguous())
+    if _exact():                                         # plain FIR kernel + unrounded torch tail
+        from .op.upfirdn2d import upfirdn2d_raw
+        f = upfirdn2d_raw(x, taps, 1, 1, 1, 1, pad[0], pad[1], pad[0], pad[1])
+        return f * scale.reshape(b, 1, 1, c), ((f * other).sum((1, 2)) if other is not None else None)
     out = torch.empty(b, oh, ow, c, dtype=torch.float32, device=x.device)
     dot = torch.empty(b, c, dtype=torch.float32, device=x.device) if other is not None else None
     with torch.cuda.device(x.device):

@@ -1,5 +1,6 @@
 """CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol
-include/stylerenderer_b200.h declares; the product refuses CPU tensors (no fallback) and never imports oracle/."""
+include/stylerenderer_b200.h declares; the kernel entry points refuse CPU tensors (no fallback) and the product never
+imports oracle/."""
 import ctypes
 import os
 import re
@@ -37,12 +38,15 @@ def test_sm100a_code_is_in_the_library():
 
 
 def test_no_cpu_fallback_and_argument_errors():
+    """The kernel entry points refuse CPU tensors (the C-ABI path never falls back).  The two dispatchers the reference
+    itself routes by device -- op.upfirdn2d / op.fused_leaky_relu (reference op/upfirdn2d.py:146-150, op/fused_act.py:87-94)
+    -- take plain torch ops for CPU tensors like the reference does (tests/test_cpu_dispatch.py)."""
     from stylerenderer_b200 import op
     x = torch.zeros(1, 3, 8, 8)
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
-        op.upfirdn2d(x, torch.ones(4, 4))
+        op.upfirdn2d_raw(x.view(3, 8, 8, 1), torch.ones(4, 4), 1, 1, 1, 1, 0, 0, 0, 0)
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
-        op.fused_leaky_relu(x, torch.zeros(3))
+        op.fused_bias_act(x, torch.zeros(3), None, 3, 0, 0.2, 1.0)
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
         op.rasterize(torch.zeros(1, 3, 3), torch.zeros(1, 3, 2), torch.zeros(1, 3, dtype=torch.int64), 4)
     # argument validation happens before any CUDA call, so it can be exercised without a GPU
