@@ -135,6 +135,12 @@ int sr_rasterize_pyramid_forward_f32(int64_t b, int64_t nv, int64_t nf, int n_le
                                      int shared_v, int shared_f, int perspective,
                                      const float *verts, const int64_t *tris, uint64_t *keys, float eps,
                                      const float *tex, int64_t c, void *stream);
+/* Forward-only form: only the interpolated maps are produced.  levels[i].ids / .bary may be NULL (then not written);
+ * planar != 0 writes each map as [b, c, size, size] planes (NCHW, what the convolution stack consumes) instead of
+ * [b, size, size, c].  Values are those of sr_rasterize_pyramid_forward_f32. */
+int sr_rasterize_pyramid_maps_f32(int64_t b, int64_t nv, int64_t nf, int n_levels, const sr_raster_level *levels,
+                                  int shared_v, int shared_f, int perspective, const float *verts, const int64_t *tris,
+                                  uint64_t *keys, float eps, const float *tex, int64_t c, int planar, void *stream);
 int sr_rasterize_pyramid_backward_f32(int64_t b, int64_t n, int n_levels, const sr_raster_level *levels, int64_t c,
                                       int perspective, const float *verts, const float *tex,
                                       float *grad_verts, float *grad_tex, float eps, void *stream);
@@ -340,6 +346,19 @@ int sr_weight_grad_layout_f32(float *gw, const float *dwk, float scale, int64_t 
  * Accumulation uses float atomics (summation order not deterministic). */
 int sr_mesh_vertex_normals_f32(float *normals, const float *verts, const int64_t *tris, int64_t batch, int64_t nv,
                                int64_t nf, int shared_f, float eps, void *stream);
+/* Rigid pose + scale, replaces the batched matmul of `random_apply_pose3D` (reference utils_3d.py:374-376):
+ *   out[b,v,:] = verts[b,v,:3] . R[b] + t[b],   pose[b] = the 3x4 matrix [R | t] row-major ([batch,12]).
+ * verts rows are `vert_stride` floats apart (>= 3: extra per-vertex columns are ignored, like v[..., :3]). */
+int sr_mesh_pose_apply_f32(float *out, const float *verts, const float *pose, int64_t batch, int64_t nv,
+                           int64_t vert_stride, void *stream);
+/* The whole mesh front-end of GeneratorWithMap in one call (reference face_model.py:71-72 -> utils_3d.py:360-404 ->
+ * model.py:260-270): (optional) pose -> area-weighted vertex normals -> the normal map at every resolution of the
+ * generator as [batch, 3, size, size] planes (levels[i].out; .ids / .bary may be NULL and are then not written).
+ * verts_out [batch,nv,3] receives the posed vertices (required with a pose), normals [batch,nv,3] the vertex normals;
+ * tris int64 [nf,3] shared by the batch; keys = workspace of sr_rasterize_pyramid_workspace_bytes. Forward only. */
+int sr_mesh_normal_pyramid_f32(int64_t batch, int64_t nv, int64_t nf, const float *verts_in, int64_t vert_stride,
+                               const float *pose, const int64_t *tris, float *verts_out, float *normals, int n_levels,
+                               const sr_raster_level *levels, uint64_t *keys, float eps, void *stream);
 
 #ifdef __cplusplus
 }

@@ -53,6 +53,9 @@ _SIGNATURES = {
     "sr_weight_grad_layout_f32": (_I, [_P, _P, _F, _L, _L, _I, _P]),
     "sr_conv_weight_prep_dual_tf32": (_I, [_P, _P, _P, _P, _F, _L, _L, _I, _I, _P]),
     "sr_mesh_vertex_normals_f32": (_I, [_P, _P, _P, _L, _L, _L, _I, _F, _P]),
+    "sr_mesh_pose_apply_f32": (_I, [_P, _P, _P, _L, _L, _L, _P]),
+    "sr_mesh_normal_pyramid_f32": (_I, [_L, _L, _L, _P, _L, _P, _P, _P, _P, _I, _P, _P, _F, _P]),
+    "sr_rasterize_pyramid_maps_f32": (_I, [_L, _L, _L, _I, _P, _I, _I, _I, _P, _P, _P, _F, _P, _L, _I, _P]),
     "sr_blur_nhwc_styled3_f32": (_I, [_P, _P, _P, _P, _P, _L, _L, _L, _L, _I, _I, _P, _L, _P, _P, _F, _F, _P, _L, _P]),
     "sr_styled_bwd_prologue3_f32": (_I, [_P] * 13 + [_L, _P, _P, _P, _L, _L, _L, _F, _F, _P, _L, _P, _P]),
 }

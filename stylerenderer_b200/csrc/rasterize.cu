@@ -292,6 +292,7 @@ struct Pyramid {
     T *bary[kMaxLevels];
     T *out[kMaxLevels];
     const T *gout[kMaxLevels];
+    int planar;                           // forward: interpolated maps are written as [b, c, size, size] planes (NCHW)
 };
 
 template <typename T>
@@ -361,21 +362,26 @@ __device__ __forceinline__ void resolve_block(const RasterGeom &g, const T *__re
                                               const uint64_t *__restrict__ zkeys, const uint32_t *__restrict__ idkeys, T eps,
                                               int64_t *__restrict__ ids_out, T *__restrict__ bary_out,
                                               const T *__restrict__ tex, int c, T *__restrict__ out, int vec_ok,
-                                              int64_t blk, int64_t npix, ResolveStage<T> &st)
+                                              int64_t blk, int64_t npix, ResolveStage<T> &st, bool planar = false)
 {
-    const bool stage_out = tex != nullptr && c <= kMaxStageC;
+    // planar: the map leaves as [b, c, h, w] planes -- consecutive threads are consecutive pixels of one plane, so the
+    // per-thread 4-byte stores coalesce by themselves; ids_out / bary_out may then be NULL (forward-only callers: the mesh
+    // is sampled under no_grad in the training loop, reference train.py:249-251, so nothing reads those buffers back)
+    const bool stage_out = tex != nullptr && c <= kMaxStageC && !planar;
     const int64_t pix0 = blk * kThreads, pix = pix0 + threadIdx.x;
     const int count = (int)((npix - pix0 < kThreads) ? (npix - pix0) : kThreads);
     int64_t ids[3] = {0, 0, 0};
     T w[3] = {0, 0, 0};
     bool hit = false;
+    int64_t img = 0;
+    int rem = 0;
     if (pix < npix) {
         const uint64_t key = zkeys[pix];
         hit = key != 0;
+        img = pix / (g.h * (int64_t)g.w);
+        rem = (int)(pix - img * g.h * (int64_t)g.w);
         if (hit) {
             const uint32_t f = PACKED ? (0xffffffffu - (uint32_t)key) : idkeys[pix];
-            const int64_t img = pix / (g.h * (int64_t)g.w);
-            const int rem = (int)(pix - img * g.h * (int64_t)g.w);
             const int y = rem / g.w, x = rem - y * g.w;
             const T *V = verts + (g.shared_v ? 0 : img * g.nv * 3);
             const int64_t *F = tris + (g.shared_f ? 0 : img * g.nf * 3);
@@ -395,12 +401,13 @@ __device__ __forceinline__ void resolve_block(const RasterGeom &g, const T *__re
             T v = 0;
             if (hit) v = tex[ids[0] * c + ch] * w[0] + tex[ids[1] * c + ch] * w[1] + tex[ids[2] * c + ch] * w[2];
             if (stage_out) st.out[threadIdx.x * c + ch] = v;
+            else if (planar) out[((img * c + ch) * g.h * (int64_t)g.w) + rem] = v;
             else out[pix * c + ch] = v;
         }
     }
     __syncthreads();
-    stream_out<int4>(ids_out + pix0 * 3, st.ids, count * 3 * (int)sizeof(int64_t), vec_ok);
-    stream_out<int4>(bary_out + pix0 * 3, st.w, count * 3 * (int)sizeof(T), vec_ok);
+    if (ids_out) stream_out<int4>(ids_out + pix0 * 3, st.ids, count * 3 * (int)sizeof(int64_t), vec_ok);
+    if (bary_out) stream_out<int4>(bary_out + pix0 * 3, st.w, count * 3 * (int)sizeof(T), vec_ok);
     if (stage_out) stream_out<int4>(out + pix0 * c, st.out, count * c * (int)sizeof(T), vec_ok && ((pix0 * c * (int64_t)sizeof(T)) % 16 == 0));
     __syncthreads();
 }
@@ -434,7 +441,7 @@ raster_resolve_pyramid_kernel(const RasterGeom g0, const Pyramid<T> L, const T *
         g.h = g.w = L.size[l];
         const int64_t npix = g.b * g.h * (int64_t)g.w;
         resolve_block<T, true>(g, verts, tris, zkeys + L.key_off[l], nullptr, eps, L.ids[l], L.bary[l], tex, c, L.out[l],
-                               vec_ok, blk - L.blk_off[l], npix, st);
+                               vec_ok, blk - L.blk_off[l], npix, st, L.planar != 0);
     }
 }
 
@@ -680,10 +687,12 @@ int rasterize_backward(int64_t b, int64_t n, int64_t h, int64_t w, int64_t c, in
 
 // levels -> device table; `backward` keeps only the levels that carry a gradient
 template <typename T>
-int build_pyramid(Pyramid<T> &L, int64_t b, int n_levels, const sr_raster_level *levels, bool backward, bool &vec_ok)
+int build_pyramid(Pyramid<T> &L, int64_t b, int n_levels, const sr_raster_level *levels, bool backward, bool &vec_ok,
+                  bool maps_only = false)
 {
     SR_REQUIRE(n_levels >= 1 && n_levels <= kMaxLevels && levels, "rasterize_pyramid: 1..SR_RASTER_MAX_LEVELS levels");
     L.n = 0;
+    L.planar = 0;
     L.blk_off[0] = 0;
     int64_t keys = 0;
     uintptr_t bits = 0;
@@ -692,7 +701,7 @@ int build_pyramid(Pyramid<T> &L, int64_t b, int n_levels, const sr_raster_level 
         SR_REQUIRE(lv.size >= 1 && lv.size <= 32768, "rasterize_pyramid: bad level size");
         const int64_t npix = b * lv.size * lv.size;
         if (backward && !lv.gout) continue;
-        SR_REQUIRE(lv.ids && lv.bary, "rasterize_pyramid: null ids / bary");
+        SR_REQUIRE(maps_only || (lv.ids && lv.bary), "rasterize_pyramid: null ids / bary");
         const int l = L.n++;
         L.size[l] = (int)lv.size;
         L.key_off[l] = keys;
@@ -710,14 +719,16 @@ int build_pyramid(Pyramid<T> &L, int64_t b, int n_levels, const sr_raster_level 
 
 int rasterize_pyramid_forward(int64_t b, int64_t nv, int64_t nf, int n_levels, const sr_raster_level *levels, int shared_v,
                               int shared_f, int perspective, const float *verts, const int64_t *tris, uint64_t *keys,
-                              float eps, const float *tex, int64_t c, void *stream)
+                              float eps, const float *tex, int64_t c, void *stream, bool maps_only = false, bool planar = false)
 {
     SR_REQUIRE(b >= 0 && nv >= 0 && nf >= 0, "rasterize_pyramid: bad sizes");
     SR_REQUIRE(nf < 0xffffffffll, "rasterize_pyramid: too many triangles");
+    SR_REQUIRE(!maps_only || tex, "rasterize_pyramid_maps: needs tex");
     if (b == 0) return SR_OK;
     Pyramid<float> L;
     bool vec_ok = false;
-    if (int rc = build_pyramid<float>(L, b, n_levels, levels, false, vec_ok)) return rc;
+    if (int rc = build_pyramid<float>(L, b, n_levels, levels, false, vec_ok, maps_only)) return rc;
+    L.planar = planar ? 1 : 0;
     SR_REQUIRE(keys, "rasterize_pyramid: null workspace");
     for (int l = 0; l < L.n; ++l) SR_REQUIRE(!tex || L.out[l], "rasterize_pyramid: tex given without out");
     SR_REQUIRE(!tex || c >= 1, "rasterize_pyramid: tex given without channels");
@@ -780,6 +791,13 @@ extern "C" int sr_rasterize_pyramid_forward_f32(int64_t b, int64_t nv, int64_t n
                                                 const float *tex, int64_t c, void *stream) {
     return rasterize_pyramid_forward(b, nv, nf, n_levels, levels, shared_v, shared_f, perspective, verts, tris, keys, eps, tex,
                                      c, stream);
+}
+extern "C" int sr_rasterize_pyramid_maps_f32(int64_t b, int64_t nv, int64_t nf, int n_levels, const sr_raster_level *levels,
+                                             int shared_v, int shared_f, int perspective, const float *verts,
+                                             const int64_t *tris, uint64_t *keys, float eps, const float *tex, int64_t c,
+                                             int planar, void *stream) {
+    return rasterize_pyramid_forward(b, nv, nf, n_levels, levels, shared_v, shared_f, perspective, verts, tris, keys, eps, tex,
+                                     c, stream, true, planar != 0);
 }
 extern "C" int sr_rasterize_pyramid_backward_f32(int64_t b, int64_t n, int n_levels, const sr_raster_level *levels, int64_t c,
                                                  int perspective, const float *verts, const float *tex, float *grad_verts,

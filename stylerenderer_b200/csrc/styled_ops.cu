@@ -314,7 +314,10 @@ extern "C" int sr_styled_bwd_prologue3_f32(float *ga, float *g_bias, float *g_no
     const int spec = (gy ? kSpecGy : 0) | (gxs ? kSpecGxs : 0) | (g_rgb ? kSpecRgb : 0) | (e ? kSpecE : 0) |
                      (noise ? kSpecNoise : 0) | (d ? kSpecD : 0);
     bool launched = false;
-    const bool spec_rgb = !(spec_env && spec_env[0] == '2');       // A/B: 2 = ToRGB combinations stay on the run-time kernel
+    // measured (B200, B = 32 generator step, profiles/r2_prologue_spec.md): specialising the combinations WITHOUT the ToRGB
+    // gradient (64 registers, no spill) takes the pass from 2.59 to 2.46 ms; the ToRGB combinations at 80 registers spill
+    // and lose the gain (2.55 ms), so they stay on the run-time kernel unless SR_PROLOGUE_SPEC=1
+    const bool spec_rgb = spec_env && spec_env[0] == '1';
     if (!(spec_env && spec_env[0] == '0') && !stylemap && (spec_rgb || !g_rgb)) {
         launched = true;
         switch (spec) {                                   // the combinations the chained generator produces

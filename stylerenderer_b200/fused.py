@@ -18,6 +18,16 @@ from . import tc_conv as tc
 from .op.upfirdn2d import upfirdn2d_raw
 
 
+def _mode_operand(ctx, t):
+    """A GEMM operand saved by the forward, as the backward's operand mode wants it.  When the forward ran in the
+    fp32-faithful mode (tc_conv "tf32x3": saved operands are unrounded) and the backward runs in the shipped tf32 mode --
+    the parity tests do that to check the tf32 backward kernels on the reference's own activations / leaky-ReLU masks --
+    the operand gets the tf32 rounding its producer would have applied."""
+    if t is not None and getattr(ctx, "exact_fwd", False) and not tc._exact():
+        return tc.split_tf32(t)[0]
+    return t
+
+
 def to_nhwc(x):
     """logical [N,C,H,W] -> contiguous [N,H,W,C] (a free view when x is channels_last)."""
     return x.permute(0, 2, 3, 1).contiguous()
@@ -68,12 +78,14 @@ class StyledConvTC(Function):
             y = tc.blur_styled(t, blur_taps, (1, 1), noise, noise_weight, act_bias, alpha, gain)
         ctx.save_for_backward(x_nhwc, xs, y, t, weight, s, d, noise, noise_weight, act_bias, blur_taps)
         ctx.cfg = (scale, upsample, alpha, gain)
+        ctx.exact_fwd = tc._exact()
         return from_nhwc(y)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
         x_nhwc, xs, y, t, weight, s, d, noise, noise_weight, act_bias, blur_taps = ctx.saved_tensors
+        xs = _mode_operand(ctx, xs)
         scale, upsample, alpha, gain = ctx.cfg
         b, h, w, cin = x_nhwc.shape
         cout = y.shape[3]
@@ -114,12 +126,14 @@ class ModConvTC(Function):
             y = upfirdn2d_raw(saved, blur_taps, 1, 1, 1, 1, 1, 1, 1, 1)
         ctx.save_for_backward(x_nhwc, xs, saved, weight, s, d, blur_taps)
         ctx.cfg = (scale, upsample)
+        ctx.exact_fwd = tc._exact()
         return from_nhwc(y)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
         x_nhwc, xs, saved, weight, s, d, blur_taps = ctx.saved_tensors
+        xs = _mode_operand(ctx, xs)
         scale, upsample = ctx.cfg
         b, h, w, cin = x_nhwc.shape
         cout = saved.shape[3]
@@ -306,12 +320,14 @@ class PlainConvTC(Function):
             tc.conv_igemm(xr, wk_f, taps, y, in_stride=2, **kw)
         ctx.save_for_backward(xr, y if act else None, wk_t, bias)
         ctx.cfg = (scale, kind, alpha, gain, k, cin, cout, (h, w))
+        ctx.exact_fwd = tc._exact()
         return from_nhwc(y)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
         xr, y, wk_t, bias = ctx.saved_tensors
+        xr, wk_t = _mode_operand(ctx, xr), _mode_operand(ctx, wk_t)
         scale, kind, alpha, gain, k, cin, cout, (h, w) = ctx.cfg
         gy = to_nhwc(gy)
         b, oh, ow, _ = gy.shape
@@ -443,6 +459,7 @@ class StyledLayerTC(Function):
                 y = tc.blur_styled(t, blur_taps, (1, 1), noise, noise_weight, act_bias, alpha, gain, stylemap=stylemap)
         ctx.save_for_backward(xs_nhwc, y, None, weight, d, noise, noise_weight, act_bias, blur_taps, s_next, rgb_weight, stylemap)
         ctx.cfg = (scale, upsample, alpha, gain)
+        ctx.exact_fwd = tc._exact()
         if s_next is None and stylemap is not None:          # y holds the pre-map value: no activated output to hand on
             main = xs.new_zeros(1)
             ctx.mark_non_differentiable(main)
@@ -457,6 +474,7 @@ class StyledLayerTC(Function):
     @once_differentiable
     def backward(ctx, g_main, g_rgb):
         xs, y, t, weight, d, noise, noise_weight, act_bias, blur_taps, s_next, rgb_weight, stylemap = ctx.saved_tensors
+        xs, wkt = _mode_operand(ctx, xs), _mode_operand(ctx, ctx.wkt)
         scale, upsample, alpha, gain = ctx.cfg
         b, h, w, cin = xs.shape
         cout = y.shape[3]
@@ -477,7 +495,7 @@ class StyledLayerTC(Function):
             res = tc.bwd_prologue2(y, noise, noise_weight, act_bias, d, alpha, gain, True, stylemap=stylemap, **src)
             ga, g_bias, g_noise_w, e, ds_next, dwb = res[:6]
             g_map = res[6] if stylemap is not None else None
-            dxs = tc.conv3x3(ga, ctx.wkt if ctx.wkt is not None else tc.weight_prep(weight[0], scale, 1))
+            dxs = tc.conv3x3(ga, wkt if wkt is not None else tc.weight_prep(weight[0], scale, 1))
             dwk = tc.wgrad3x3(ga, xs) if need_w else None
         else:
             # e = sum_p gp * (fir(t) * map0) comes from the prologue (fir(t) * map0 is recoverable from y, like the plain
@@ -486,7 +504,7 @@ class StyledLayerTC(Function):
             g_pre, g_bias, g_noise_w, e, ds_next, dwb = res[:6]
             g_map = res[6] if stylemap is not None else None
             ga, _ = tc.blur_scaledot(g_pre, torch.flip(blur_taps, [0, 1]), (2, 2), d)       # FIR^T, * d, tf32
-            dxs = tc.conv3x3_s2_gather(ga, ctx.wkt if ctx.wkt is not None else tc.weight_prep(weight[0], scale, 2), (h, w))
+            dxs = tc.conv3x3_s2_gather(ga, wkt if wkt is not None else tc.weight_prep(weight[0], scale, 2), (h, w))
             dwk = tc.wgrad_transpose3x3_s2(ga, xs) if need_w else None
         g_d = e / d
         g_w = style.weight_grad_layout(dwk, scale, cout, cin, 3) if need_w else None

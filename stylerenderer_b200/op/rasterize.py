@@ -225,3 +225,36 @@ class RasterizePyramid(Function):
 def rasterize_pyramid(v, tex, tri, sizes, perspective=False, eps=1e-6):
     """[rasterize(v, tex, tri, s) for s in sizes] in three launches instead of 3 * len(sizes) (same values, bit for bit)."""
     return list(RasterizePyramid.apply(v, tex, tri, tuple(sizes), perspective, eps))
+
+
+def rasterize_pyramid_maps(v, tex, tri, sizes, perspective=False, eps=1e-6, planar=True):
+    """Forward-only pyramid: only the interpolated maps, no index / coefficient buffers (36 of the 48 bytes per pixel the
+    full forward writes), as [b, c, s, s] planes when `planar` (NCHW, what the style-map nets consume).  Same values as
+    `rasterize_pyramid`.  For meshes that need no gradient -- the training loop samples them under no_grad (reference
+    train.py:249-251)."""
+    _lib.require_cuda(v, "rasterize_pyramid_maps")
+    if v.dtype != torch.float32 or tex.dim() != v.dim():
+        raise RuntimeError("rasterize_pyramid_maps: float32 vertices and [.., n, c] attributes only")
+    if not 1 <= len(sizes) <= MAX_LEVELS:
+        raise RuntimeError(f"rasterize_pyramid_maps: 1..{MAX_LEVELS} sizes")
+    c = int(tex.shape[-1])
+    vc, texc, tric = v.detach().contiguous(), tex.detach().to(v.dtype).contiguous(), tri.contiguous()
+    dev = vc.device
+    outs = []
+    b = nv = nf = shared_v = shared_f = None
+    for sz in sizes:
+        b, nv, nf, h, w, shared_v, shared_f, lead = _problem(vc, tric, sz, sz)
+        shape = (*lead[:-2], c, sz, sz) if planar else (*lead, c)
+        outs.append(torch.empty(shape, dtype=vc.dtype, device=dev))
+    L = _lib.lib()
+    csz = (ctypes.c_int64 * len(sizes))(*[int(s) for s in sizes])
+    ws = torch.empty(L.sr_rasterize_pyramid_workspace_bytes(b, len(sizes), csz) // 8 + 1, dtype=torch.int64, device=dev)
+    arr = (RasterLevel * len(sizes))()
+    for i, sz in enumerate(sizes):
+        arr[i].size, arr[i].out = int(sz), _lib.ptr(outs[i])
+    with torch.cuda.device(dev):
+        rc = L.sr_rasterize_pyramid_maps_f32(b, nv, nf, len(sizes), arr, int(shared_v), int(shared_f), int(bool(perspective)),
+                                             _lib.ptr(vc), _lib.ptr(tric), _lib.ptr(ws), abs(float(eps)), _lib.ptr(texc), c,
+                                             1 if planar else 0, _lib.stream_of(vc))
+    _lib.check(rc, "sr_rasterize_pyramid_maps_f32")
+    return outs

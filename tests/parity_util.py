@@ -1,0 +1,113 @@
+"""Shared helpers of the GPU parity tests: error measures, the network-level gradient envelope (see the docstring of
+tests/test_gpu_parity_tc.py for why gradients through leaky-ReLUs are held as an envelope) and the operand-mode context."""
+import torch
+
+REL = 1e-3
+REPORT = {}
+
+
+class tcgen05:
+    """conv_backend = tcgen05 in the given operand mode; counts the tensor-core GEMM launches made inside."""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        from stylerenderer_b200 import _lib, layers as L, tc_conv as tc
+        self.L, self.tc, self.lib = L, tc, _lib.lib()
+        self.prev_backend, self.prev_mode = L.get_conv_backend(), tc.get_precision()
+        L.set_conv_backend("tcgen05")
+        tc.set_precision("tf32x3" if self.mode == "mixed" else self.mode)
+        self.calls = 0
+        self._orig = {}
+        for n in ("sr_conv_igemm_multi_tf32", "sr_conv_wgrad_tf32"):
+            fn = getattr(self.lib, n)
+            self._orig[n] = fn
+
+            def wrapped(*a, _fn=fn):
+                self.calls += 1
+                return _fn(*a)
+            setattr(self.lib, n, wrapped)
+        return self
+
+    def backward_mode(self):
+        """Call between the forward and the backward: "mixed" switches the operand mode to tf32 for the backward."""
+        if self.mode == "mixed":
+            self.tc.set_precision("tf32")
+
+    def __exit__(self, *a):
+        for n, fn in self._orig.items():
+            setattr(self.lib, n, fn)
+        self.L.set_conv_backend(self.prev_backend)
+        self.tc.set_precision(self.prev_mode)
+
+
+def rel_err(got, want):
+    got, want = got.detach().cpu().double(), want.detach().cpu().double()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    return float((got - want).abs().max() / max(float(want.abs().max()), 1e-30))
+
+
+def hold(key, got, want, tol):
+    e = rel_err(got, want)
+    REPORT[key] = e
+    assert e <= tol, f"{key}: max-norm relative error {e:.3e} > {tol:.1e}"
+    return e
+
+
+def hold_param_grads(key, got, want, tol):
+    """want: {name: tensor | {"slice", "norm"} | None} (make_golden_tc.compress)."""
+    assert set(got) == set(want), key
+    for n, w in want.items():
+        g = got[n]
+        if w is None:
+            assert g is None or float(g.abs().max()) == 0, f"{key}/{n}"
+        elif isinstance(w, dict):
+            idx = tuple(slice(0, s) for s in w["slice"].shape)
+            scale = float(w["norm"]) / (g.numel() ** 0.5)           # rms of the full gradient: the slice's own max can be tiny
+            e = float((g[idx].detach().cpu().double() - w["slice"].double()).abs().max()) / max(float(w["slice"].abs().max()), scale)
+            REPORT[f"{key}/{n}[slice]"] = e
+            assert e <= tol, f"{key}/{n}: slice error {e:.3e} > {tol:.1e}"
+            en = abs(float(g.double().norm()) - float(w["norm"])) / float(w["norm"])
+            REPORT[f"{key}/{n}[norm]"] = en
+            assert en <= tol, f"{key}/{n}: norm error {en:.3e}"
+        else:
+            hold(f"{key}/{n}", g, w, tol)
+
+
+def param_errors(key, got, want):
+    """[(error, name)] of every parameter gradient against make_golden_tc.compress()-style references."""
+    errs = []
+    assert set(got) == set(want), key
+    for n, w in want.items():
+        g = got[n]
+        if w is None:
+            assert g is None or float(g.abs().max()) == 0, f"{key}/{n}"
+        elif isinstance(w, dict):
+            idx = tuple(slice(0, s_) for s_ in w["slice"].shape)
+            scale = float(w["norm"]) / (g.numel() ** 0.5)
+            e = float((g[idx].detach().cpu().double() - w["slice"].double()).abs().max()) / max(float(w["slice"].abs().max()), scale)
+            errs.append((e, n + "[slice]"))
+            errs.append((abs(float(g.double().norm()) - float(w["norm"])) / float(w["norm"]), n + "[norm]"))
+        else:
+            errs.append((rel_err(g, w), n))
+    return errs
+
+
+# network-level gradient envelopes (see the module docstring): (median, fraction within 1e-3, max)
+ENVELOPE = {"tf32x3": (1e-3, 0.75, 5e-2), "mixed": (1e-3, 0.70, 5e-2), "tf32": (1e-2, 0.0, 3e-1)}
+
+
+def hold_envelope(key, errs, mode):
+    """errs: [(error, name)] over every gradient tensor of a network."""
+    import statistics
+    assert errs and all(e == e and e != float("inf") for e, _ in errs), f"{key}: non-finite gradient error"
+    med_tol, frac_tol, max_tol = ENVELOPE[mode]
+    vals = sorted(e for e, _ in errs)
+    med, worst = statistics.median(vals), max(errs)
+    frac = sum(1 for v in vals if v <= REL) / len(vals)
+    REPORT[key + "/gradients"] = {"tensors": len(vals), "median": med, "within_1e-3": frac, "max": worst[0], "argmax": worst[1]}
+    print(f"{key}: {len(vals)} gradient tensors, median {med:.2e}, {100 * frac:.0f}% within 1e-3, max {worst[0]:.2e} ({worst[1]})")
+    assert med <= med_tol, f"{key}: median gradient error {med:.2e} > {med_tol:.0e}"
+    assert frac >= frac_tol, f"{key}: only {100 * frac:.0f}% of the gradient tensors within 1e-3"
+    assert worst[0] <= max_tol, f"{key}: {worst[1]} error {worst[0]:.2e} > {max_tol:.0e}"

@@ -148,15 +148,29 @@ def test_styled_conv_tcgen05_vs_oracle(up, shape):
     finally:
         L.set_conv_backend("cudnn")
     close(got_y, want_y, "y")
-    # Gradients: a tf32 forward moves pre-activations by ~3e-4, which flips the leaky-ReLU mask of the few elements
-    # that sit that close to zero; at these tiny spatial sizes one flip is a percent-level change of a max-norm.
-    # (The exact-forward test below checks the backward kernels themselves to 1e-3.)
-    def cos(a, b_):
+    # Gradients in the shipped tf32 mode: a tf32 forward moves pre-activations by ~3e-4, which flips the leaky-ReLU mask of
+    # the few elements that sit that close to zero; at these tiny spatial sizes one flip is a percent-level change of a
+    # max-norm, so the bound here is on the relative L2 error ...
+    def l2(a, b_):
         a, b_ = a.detach().cpu().double().flatten(), b_.detach().cpu().double().flatten()
-        return float((a @ b_) / (a.norm() * b_.norm()))
-    assert cos(got_g[0], want_g[0]) > 0.999 and cos(got_g[1], want_g[1]) > 0.999
+        return float((a - b_).norm() / b_.norm())
+    assert l2(got_g[0], want_g[0]) < 3e-2 and l2(got_g[1], want_g[1]) < 3e-2
     for k in want_p:
-        assert cos(got_p[k], want_p[k]) > 0.995, k
+        assert l2(got_p[k], want_p[k]) < 6e-2, k
+    # ... and the SAME backward kernels in tf32 on the fp32-faithful forward's activations (no flips) meet 1e-3 on every
+    # gradient with these generic inputs, as does the fp32-faithful mode end to end
+    from parity_util import tcgen05
+    for mode in ("mixed", "tf32x3"):
+        with tcgen05(mode) as t:
+            xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+            sc = style.cuda().requires_grad_(True)
+            y_ = mod(xc, sc, noise.cuda())
+            t.backward_mode()
+            names = [n for n, _ in sorted(mod.named_parameters())]
+            gr = torch.autograd.grad(y_, [xc, sc] + [p for _, p in sorted(mod.named_parameters())], gy.cuda(), allow_unused=True)
+        close(y_, want_y, f"y [{mode}]")
+        close(gr[0], want_g[0], f"gx [{mode}]"); close(gr[1], want_g[1], f"gs [{mode}]")
+        check_param_grads(dict(zip(names, gr[2:])), {k_: v_.detach() if v_ is not None else None for k_, v_ in want_p.items()})
 
 
 def _exact_inputs(b, cin, cout, r, up):
@@ -403,17 +417,14 @@ def test_generator_with_map_tcgen05_runs_and_matches():
         L.set_conv_backend("cudnn")
     close(img_b, img_a.detach().cpu(), "GAR image")
     names = ["z", "verts", "tex"] + [n for n, p in sorted(G.named_parameters()) if p.requires_grad]
-    worst = 1.0
+    from parity_util import hold_envelope, rel_err
+    errs = []
     for n, a, bb in zip(names, gr_a, gr_b):
         if a is None or float(a.abs().max()) == 0:
             continue
         assert bb is not None, n
-        a, bb = a.double().flatten(), bb.double().flatten()
-        c = float((a @ bb) / (a.norm() * bb.norm()))
-        worst = min(worst, c)
-        assert c > 0.99, f"{n}: cosine {c:.5f}"
-        assert abs(float(bb.norm() / a.norm()) - 1) < 5e-2, f"{n}: norm ratio {float(bb.norm() / a.norm()):.4f}"
-    print("worst gradient cosine (GeneratorWithMap, tcgen05 chain vs fp32 composed path):", worst)
+        errs.append((rel_err(bb, a), n))
+    hold_envelope("gwm32_tcgen05_vs_composed[tf32]", errs, "tf32")
 
 
 def test_generator_tcgen05_backend_matches_cudnn_backend():
@@ -438,15 +449,9 @@ def test_generator_tcgen05_backend_matches_cudnn_backend():
         L.set_conv_backend("cudnn")
     close(img_b, img_a.cpu(), "image")
     names = ["z"] + [n for n, p in sorted(G.named_parameters()) if p.requires_grad]
-    worst = 1.0
-    for n, a, bb in zip(names, gr_a, gr_b):
-        if a is None or float(a.abs().max()) == 0:
-            continue
-        a, bb = a.double().flatten(), bb.double().flatten()
-        c = float((a @ bb) / (a.norm() * bb.norm()))
-        worst = min(worst, c)
-        assert c > 0.99, f"{n}: cosine {c:.5f}"
-    print("worst gradient cosine tcgen05 vs fp32 composed path:", worst)
+    from parity_util import hold_envelope, rel_err
+    errs = [(rel_err(bb, a), n) for n, a, bb in zip(names, gr_a, gr_b) if a is not None and float(a.abs().max()) > 0]
+    hold_envelope("generator64_tcgen05_vs_composed[tf32]", errs, "tf32")
 
 
 def test_generator_config2_full_size_properties():
@@ -481,9 +486,12 @@ def test_generator_config2_full_size_properties():
     finally:
         L.set_conv_backend("cudnn")
     err = float((img - img_ref).abs().max() / img_ref.abs().max())
-    cos = float((gz1.double().flatten() @ gz_ref.double().flatten()) / (gz1.double().norm() * gz_ref.double().norm()))
-    print(f"Generator(256) B=32: tcgen05 (tf32) vs fp32 composed path: image max-norm rel err {err:.2e}, dz cosine {cos:.6f}")
-    assert err <= 2e-3 and cos > 0.99                                       # measured on B200: 9.5e-4, 0.99984
+    gz_err = float((gz1 - gz_ref).abs().max() / gz_ref.abs().max())
+    print(f"Generator(256) B=32: tcgen05 (tf32) vs fp32 composed path: image max-norm rel err {err:.2e}, dz max-norm rel err {gz_err:.2e}")
+    # the checker here is this package's composed path on cuDNN fp32 (itself ~1e-3 from the oracle in places); the oracle
+    # comparison of this very configuration at 1e-3 is tests/test_gpu_parity_tc.py::test_headline_generator256_vs_oracle
+    assert err <= 1.5e-3, err                                               # measured on B200: 9.5e-4
+    assert gz_err <= 5e-2, gz_err                                           # leaky-ReLU mask flips (parity_util envelope)
     lin = 2.0 * gz1 - 3.0 * gz2
     lin_err = float((gz12 - lin).abs().max() / lin.abs().max())
     assert lin_err <= 2e-3, lin_err                                         # tf32 rounding of the GEMM operands only (3.9e-4)
@@ -586,10 +594,6 @@ def test_discriminator_tcgen05_backend_matches_cudnn_backend():
         L.set_conv_backend("cudnn")
     close(y_b, y_a.cpu(), "discriminator logits")
     names = ["x"] + [n for n, _ in sorted(D.named_parameters())]
-    for n, a, bb in zip(names, g_a, g_b):
-        if float(a.abs().max()) == 0:
-            continue
-        a, bb = a.double().flatten(), bb.double().flatten()
-        c = float((a @ bb) / (a.norm() * bb.norm()))
-        assert c > 0.999, f"{n}: cosine {c:.5f}"
-        assert abs(float(bb.norm() / a.norm()) - 1) < 2e-2, f"{n}: norm ratio {float(bb.norm() / a.norm()):.4f}"
+    from parity_util import hold_envelope, rel_err
+    errs = [(rel_err(bb, a), n) for n, a, bb in zip(names, g_a, g_b) if float(a.abs().max()) > 0]
+    hold_envelope("discriminator64_tcgen05_vs_composed[tf32]", errs, "tf32")
