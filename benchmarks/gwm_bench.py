@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--conv-backend", default="tcgen05")
+    ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     from stylerenderer_b200 import _lib, layers, mesh, model as M
     layers.set_conv_backend(args.conv_backend)
@@ -37,20 +38,40 @@ def main():
         img, _, _ = G([zz], (v, normals, tri))
         (img * cot).sum().backward()
 
+    def timed(fn):
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(args.steps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / args.steps
+
     for _ in range(3):
         step()
-    torch.cuda.synchronize()
     n0 = _lib.launch_count()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(args.steps):
-        step()
-    e.record()
-    torch.cuda.synchronize()
-    ms = s.elapsed_time(e) / args.steps
+    ms_eager = timed(step)
+    launches = (_lib.launch_count() - n0) // args.steps
+    # the same step captured once as a CUDA graph and replayed (the eager step is bound by ~10 ms of host enqueue)
+    ms, execution = ms_eager, "eager"
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        for _ in range(3):
+            graph.replay()
+        ms, execution = timed(graph.replay), "cuda_graph_replay"
+    assert all(p.grad is None or bool(torch.isfinite(p.grad).all()) for p in G.parameters()), "non-finite gradient"
     print(json.dumps({"metric": "GeneratorWithMap fwd+bwd images/sec @256px", "value": round(B / ms * 1e3, 1), "ms_per_step": round(ms, 2),
-                      "batch": B, "conv_backend": args.conv_backend, "execution": "eager",
-                      "gpu_launches": (_lib.launch_count() - n0) // args.steps}))
+                      "eager_ms_per_step": round(ms_eager, 2), "batch": B, "conv_backend": args.conv_backend,
+                      "execution": execution, "gpu_launches": launches}))
 
 
 if __name__ == "__main__":

@@ -204,11 +204,15 @@ def run(args):
     losses = {}
 
     from stylerenderer_b200 import mesh as mesh_frontend
+    sizes = [2 ** i for i in range(2, int(math.log2(args.size)) + 1)]
+    pose_sigma = torch.tensor(mesh_frontend.DEFAULT_POSE_SIGMA, device=dev)
 
     def sample_mesh(n):
+        """Fused front-end (sr_mesh_normal_pyramid_f32): morphable-model GEMM -> pose -> vertex normals -> the normal map at
+        every generator resolution as NCHW planes, no index / coefficient buffers (train.py:249-251: under no_grad)."""
         with torch.no_grad():
-            vert = random_pose(face(face.random_input(n))).contiguous()
-            return vert, mesh_frontend.mesh_point_normal(vert, tri)          # sr_mesh_vertex_normals_f32
+            T = mesh_frontend.pose_matrices(torch.randn(n, 7, device=dev) * pose_sigma)
+            return mesh_frontend.normal_pyramid(face(face.random_input(n)), tri, sizes, pose=T)
 
     def iteration(i, e2e=False):
         nonlocal mean_path
@@ -220,8 +224,8 @@ def run(args):
             real = real.contiguous(memory_format=torch.channels_last)
         # ---- D step (train.py:245-268)
         requires_grad(g_params, False); requires_grad(d_params, True)
-        vert, norm = sample_mesh(B)
-        fake, _, _ = g_mod([torch.randn(B, 512, device=dev)], (vert, norm, tri))
+        vert, norm, maps = sample_mesh(B)
+        fake, _, _ = g_mod([torch.randn(B, 512, device=dev)], maps)
         d_loss = d_logistic_loss(D(real), D(fake))
         d_mod.zero_grad(set_to_none=True)
         d_loss.backward()
@@ -238,8 +242,8 @@ def run(args):
             losses["r1"] = r1.detach()
         # ---- G step (train.py:292-333)
         requires_grad(g_params, True); requires_grad(d_params, False)
-        vert, norm = sample_mesh(B)
-        fake, _, _ = G([torch.randn(B, 512, device=dev)], (vert, norm, tri))
+        vert, norm, maps = sample_mesh(B)
+        fake, _, _ = G([torch.randn(B, 512, device=dev)], maps)
         g_loss = F.softplus(-d_mod(fake)).mean()
         g_mod.zero_grad(set_to_none=True)
         g_loss.backward()

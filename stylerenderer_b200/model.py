@@ -14,7 +14,8 @@ from torch import nn
 from . import fused, layers
 from .layers import (ConstantInput, ConvLayer, EqualLinear, ModulatedConv2d, NoiseInjection, PixelNorm, ResBlock,
                      Upsample)
-from .op import FusedLeakyReLU, rasterize, rasterize_pyramid
+from .mesh import NormalMaps
+from .op import FusedLeakyReLU, rasterize, rasterize_pyramid, rasterize_pyramid_maps
 from .op.rasterize import MAX_LEVELS
 
 
@@ -191,7 +192,15 @@ class GeneratorWithMap(Generator):                    # reference model.py:188-2
         """The rasterised normal map at every resolution 4, 8, ..., size as [B,3,r,r] views (reference model.py:260-270
         calls rasterize once per resolution; here all of them come from one pyramid launch set, same values)."""
         sizes = [2 ** i for i in range(2, self.log_size + 1)]
-        if mesh[0].dtype == torch.float32 and len(sizes) <= MAX_LEVELS:
+        if isinstance(mesh, NormalMaps):                 # already rendered by the fused front-end (mesh.normal_pyramid)
+            assert [m.shape[-1] for m in mesh] == sizes, "NormalMaps must hold one map per resolution 4 .. size"
+            return list(mesh)
+        pyramid_ok = mesh[0].dtype == torch.float32 and len(sizes) <= MAX_LEVELS
+        no_grad = not (torch.is_grad_enabled() and (mesh[0].requires_grad or mesh[1].requires_grad))
+        if pyramid_ok and no_grad and mesh[0].is_cuda and mesh[1].dim() == mesh[0].dim():
+            # forward-only: [b,3,r,r] planes straight from the resolve pass, no index / coefficient buffers
+            return rasterize_pyramid_maps(mesh[0], mesh[1], mesh[2], sizes, planar=True)
+        if pyramid_ok:
             maps = rasterize_pyramid(mesh[0], mesh[1], mesh[2], sizes)
         else:
             maps = [rasterize(mesh[0], mesh[1], mesh[2], r, r) for r in sizes]
