@@ -750,34 +750,23 @@ def main():
             def step_graph():
                 graph.replay()
 
-            # End-to-end step: z arrives from pinned host memory, loss + dz + the 25 MB of generated images go back to
-            # the host EVERY step.  The read-back runs on a copy stream out of a snapshot of the graph's static outputs,
-            # so it overlaps the next step's compute (the caller sees step i's results while step i+1 runs: ordinary
-            # double buffering of a serving / training loop); the timed region ends after the last copy has landed.
-            copy_stream = torch.cuda.Stream()
-            snap = [torch.empty_like(loss_static), torch.empty_like(gz_static), torch.empty_like(img_static)]
-            ev_snap, ev_copied = torch.cuda.Event(), torch.cuda.Event()
-            ev_copied.record()
-
             def step_graph_e2e():
-                cur = torch.cuda.current_stream()
+                # z arrives from pinned host memory; loss + dz + the 25 MB of generated images go back to the host every
+                # step and the caller waits for them.  (Overlapping the read-back with the next step's compute through a
+                # copy stream + snapshot buffers was measured SLOWER on this path -- 24.9 vs 20.5 ms per step,
+                # profiles/r2_bench_e2e_overlap.json -- so the step stays synchronous.)
                 z_static.copy_(z_host, non_blocking=True)
                 graph.replay()
-                cur.wait_event(ev_copied)                  # the previous read-back has left the snapshot buffers
-                snap[0].copy_(loss_static); snap[1].copy_(gz_static); snap[2].copy_(img_static)   # 25 MB device copy: ~10 us
-                ev_snap.record(cur)
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(ev_snap)
-                    loss_host.copy_(snap[0], non_blocking=True)
-                    gz_host.copy_(snap[1], non_blocking=True)
-                    img_host.copy_(snap[2], non_blocking=True)
-                    ev_copied.record(copy_stream)
+                loss_host.copy_(loss_static, non_blocking=True)
+                gz_host.copy_(gz_static, non_blocking=True)
+                img_host.copy_(img_static, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
 
             for _ in range(3):
                 step_graph()
             with ClockSampler(local) as clocks:             # sampled over both timed regions (device-resident and e2e)
                 ms = timed(step_graph, args.steps)
-                ms_e2e = timed(step_graph_e2e, args.steps, lambda: torch.cuda.current_stream().wait_event(ev_copied))
+                ms_e2e = timed(step_graph_e2e, args.steps)
             graphed = True
         except Exception as ex:                         # report, never hide: fall back to the eager numbers
             print(f"[bench] CUDA graph capture failed, reporting eager timings: {ex!r}", file=sys.stderr)

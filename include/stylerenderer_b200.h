@@ -75,7 +75,9 @@ int sr_upfirdn2d_f32(float *out, const float *x, const float *taps,
  *   verts [b,nv,3] (or [nv,3] when shared_v), tris int64 [nf,3] when shared_f else [b,nf,3]
  *   ids   int64 [b,h,w,3]  = winning triangle's vertex ids (+ nv*batch unless shared_v), 0 = background
  *   bary  [b,h,w,3]        = normalised barycentric coefficients, 0 = background
- *   keys  uint64 [b,h,w]   workspace (depth/triangle keys), contents undefined on return
+ *   keys  workspace of sr_rasterize_workspace_bytes() bytes (16-byte aligned), contents undefined on return:
+ *         uint64 [b,h,w] depth/triangle keys, then (float path) the products of the per-vertex / per-triangle
+ *         pre-pass -- pixel-space vertices [b,nv,3] and the triangle list narrowed to int32 [b,nf,3]
  * Deterministic: among equal depths the first triangle in list order wins, like the reference's
  * CPU loop (the reference CUDA kernel is racy).  Bit-exact with that CPU loop for ids and bary.
  * Optional fused attribute interpolation (reference op/rasterize.py:29-37): when tex != NULL,
@@ -90,8 +92,8 @@ int sr_rasterize_forward_f64(int64_t b, int64_t nv, int64_t nf, int64_t h, int64
                              const double *verts, const int64_t *tris,
                              int64_t *ids, double *bary, uint64_t *keys, double eps,
                              const double *tex, int64_t c, double *out, void *stream);
-/* size in bytes of the `keys` workspace for a given problem */
-int64_t sr_rasterize_workspace_bytes(int64_t b, int64_t h, int64_t w, int is_f64);
+/* size in bytes of the `keys` workspace for a given problem (nv, nf: vertices per image, triangles per list) */
+int64_t sr_rasterize_workspace_bytes(int64_t b, int64_t nv, int64_t nf, int64_t h, int64_t w, int is_f64);
 
 /* Reference-shaped backward (`rasterize.backward`, op/rasterize.cpp:179-241): dcoeff [b,h,w,3,9]
  * = d bary_i / d vertex_k.{x,y,z}; pixels whose three ids are not distinct are left untouched
@@ -130,7 +132,7 @@ typedef struct sr_raster_level {
     void *out;             /* float [b,size,size,c] (forward, required when tex != NULL) */
     const void *gout;      /* float [b,size,size,c] (backward: gradient of out) or NULL */
 } sr_raster_level;
-int64_t sr_rasterize_pyramid_workspace_bytes(int64_t b, int n_levels, const int64_t *sizes);
+int64_t sr_rasterize_pyramid_workspace_bytes(int64_t b, int64_t nv, int64_t nf, int n_levels, const int64_t *sizes);
 int sr_rasterize_pyramid_forward_f32(int64_t b, int64_t nv, int64_t nf, int n_levels, const sr_raster_level *levels,
                                      int shared_v, int shared_f, int perspective,
                                      const float *verts, const int64_t *tris, uint64_t *keys, float eps,
@@ -292,6 +294,40 @@ int sr_styled_bwd_prologue3_f32(float *ga, float *g_bias, float *g_noise_w, floa
  * out or dot may be NULL; dot is zeroed by the call. */
 int sr_scale_dot_nhwc_f32(float *out, float *dot, const float *a, const float *other, const float *scale,
                           int64_t batch, int64_t pixels, int64_t channels, int round_out_tf32, void *stream);
+
+/* ------------------------------------------------------------------ bf16 operand mode ------------------------
+ * BASELINE.json configs[3] (the GAR train step) asks for bf16 convolutions.  In this mode the GEMM OPERANDS -- the
+ * modulated activations, the re-laid-out weights and the gradient operand of the dgrad / wgrad GEMMs -- are bfloat16
+ * tensors (tcgen05 kind::f16, twice the tensor-core rate and half the operand bytes of the tf32 form); accumulation,
+ * the saved activations, all epilogue vectors, reductions and parameter gradients stay fp32.  Each function below is
+ * its *_f32 / *_tf32 namesake with the operand pointers retyped (`void *` = bfloat16 data of the same logical shape):
+ *   sr_conv_igemm_multi_bf16   in, weight, out2 are bf16 (cin % 64 == 0); out fp32
+ *   sr_conv_wgrad_bf16         g, x are bf16; dw fp32
+ *   sr_modulate_bf16           xs bf16
+ *   sr_conv_weight_prep_dual_bf16   fwd, tr bf16; wsq fp32
+ *   sr_blur_nhwc_styled3_bf16  out2 bf16 (out fp32)
+ *   sr_blur_nhwc_scaledot_bf16 out bf16
+ *   sr_styled_bwd_prologue3_bf16    ga bf16 when d != NULL (fp32 g_pre otherwise: it then feeds the backward FIR) */
+int sr_conv_igemm_multi_bf16(const sr_conv_args *args, int count, void *stream);
+int sr_conv_wgrad_bf16(const sr_wgrad_args *args, void *stream);
+int sr_modulate_bf16(void *xs, const float *x, const float *style, int64_t batch, int64_t pixels, int64_t channels,
+                     void *stream);
+int sr_conv_weight_prep_dual_bf16(void *fwd, void *tr, float *wsq, const float *w, float scale, int64_t cout, int64_t cin,
+                                  int taps, int flip_transposed, void *stream);
+int sr_blur_nhwc_styled3_bf16(float *out, void *out2, const float *scale2, const float *x, const float *taps,
+                              int64_t batch, int64_t in_h, int64_t in_w, int64_t channels, int pad0, int pad1,
+                              const float *noise, int64_t noise_batch_stride, const float *noise_weight,
+                              const float *bias, float alpha, float gain, const float *stylemap,
+                              int64_t stylemap_batch_stride, void *stream);
+int sr_blur_nhwc_scaledot_bf16(void *out, float *dot, const float *x, const float *taps, const float *scale,
+                               const float *other, int64_t batch, int64_t in_h, int64_t in_w, int64_t channels, int pad0,
+                               int pad1, void *stream);
+int sr_styled_bwd_prologue3_bf16(void *ga, float *g_bias, float *g_noise_w, float *e, float *ds_next, float *d_rgb_weight,
+                                 const float *gy, const float *gxs, const float *s_next, const float *g_rgb,
+                                 const float *rgb_weight, const float *y, const float *noise, int64_t noise_batch_stride,
+                                 const float *noise_weight, const float *bias, const float *d, int64_t batch,
+                                 int64_t pixels, int64_t channels, float alpha, float gain, const float *stylemap,
+                                 int64_t stylemap_batch_stride, float *g_stylemap, void *stream);
 
 /* ------------------------------------------------------------------ style path (all layers per launch) ----
  * Replaces, for every modulated convolution of a network at once, the reference's per-layer

@@ -25,14 +25,14 @@ _SIGNATURES = {
     "sr_fused_bias_act_f32": (_I, [_P, _P, _P, _P, _I, _I, _F, _F, _L, _L, _L, _P]),
     "sr_fused_lrelu_backward_f32": (_I, [_P, _P, _P, _P, _F, _F, _L, _L, _L, _P]),
     "sr_upfirdn2d_f32": (_I, [_P, _P, _P, _L, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
-    "sr_rasterize_workspace_bytes": (_L, [_L, _L, _L, _I]),
+    "sr_rasterize_workspace_bytes": (_L, [_L, _L, _L, _L, _L, _I]),
     "sr_rasterize_forward_f32": (_I, [_L, _L, _L, _L, _L, _I, _I, _I, _P, _P, _P, _P, _P, _F, _P, _L, _P, _P]),
     "sr_rasterize_forward_f64": (_I, [_L, _L, _L, _L, _L, _I, _I, _I, _P, _P, _P, _P, _P, _D, _P, _L, _P, _P]),
     "sr_rasterize_dcoeff_f32": (_I, [_L, _L, _L, _L, _I, _P, _P, _P, _F, _P]),
     "sr_rasterize_dcoeff_f64": (_I, [_L, _L, _L, _L, _I, _P, _P, _P, _D, _P]),
     "sr_rasterize_backward_f32": (_I, [_L, _L, _L, _L, _L, _I, _P, _P, _P, _P, _P, _P, _P, _F, _P]),
     "sr_rasterize_backward_f64": (_I, [_L, _L, _L, _L, _L, _I, _P, _P, _P, _P, _P, _P, _P, _D, _P]),
-    "sr_rasterize_pyramid_workspace_bytes": (_L, [_L, _I, _P]),
+    "sr_rasterize_pyramid_workspace_bytes": (_L, [_L, _L, _L, _I, _P]),
     "sr_rasterize_pyramid_forward_f32": (_I, [_L, _L, _L, _I, _P, _I, _I, _I, _P, _P, _P, _F, _P, _L, _P]),
     "sr_rasterize_pyramid_backward_f32": (_I, [_L, _L, _I, _P, _L, _I, _P, _P, _P, _P, _F, _P]),
     "sr_conv_igemm_tf32": (_I, [_P, _P]),
@@ -52,6 +52,13 @@ _SIGNATURES = {
     "sr_weight_sq_backward_f32": (_I, [_P, _P, _P, _F, _L, _L, _I, _P]),
     "sr_weight_grad_layout_f32": (_I, [_P, _P, _F, _L, _L, _I, _P]),
     "sr_conv_weight_prep_dual_tf32": (_I, [_P, _P, _P, _P, _F, _L, _L, _I, _I, _P]),
+    "sr_conv_igemm_multi_bf16": (_I, [_P, _I, _P]),
+    "sr_conv_wgrad_bf16": (_I, [_P, _P]),
+    "sr_modulate_bf16": (_I, [_P, _P, _P, _L, _L, _L, _P]),
+    "sr_conv_weight_prep_dual_bf16": (_I, [_P, _P, _P, _P, _F, _L, _L, _I, _I, _P]),
+    "sr_blur_nhwc_styled3_bf16": (_I, [_P, _P, _P, _P, _P, _L, _L, _L, _L, _I, _I, _P, _L, _P, _P, _F, _F, _P, _L, _P]),
+    "sr_blur_nhwc_scaledot_bf16": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _I, _I, _P]),
+    "sr_styled_bwd_prologue3_bf16": (_I, [_P] * 13 + [_L, _P, _P, _P, _L, _L, _L, _F, _F, _P, _L, _P, _P]),
     "sr_mesh_vertex_normals_f32": (_I, [_P, _P, _P, _L, _L, _L, _I, _F, _P]),
     "sr_mesh_pose_apply_f32": (_I, [_P, _P, _P, _L, _L, _L, _P]),
     "sr_mesh_normal_pyramid_f32": (_I, [_L, _L, _L, _P, _L, _P, _P, _P, _P, _I, _P, _P, _F, _P]),
@@ -65,7 +72,9 @@ CONV_EXPORTS = ("sr_blur_nhwc_scaledot_f32", "sr_blur_nhwc_styled_f32", "sr_blur
                 "sr_conv_igemm_tf32", "sr_conv_igemm_multi_tf32", "sr_conv_wgrad_tf32", "sr_modulate_tf32", "sr_conv_weight_prep_tf32",
                 "sr_style_scales_forward_f32", "sr_style_scales_backward_f32", "sr_weight_sq_f32", "sr_weight_sq_backward_f32",
                 "sr_weight_grad_layout_f32", "sr_conv_weight_prep_dual_tf32", "sr_blur_nhwc_styled3_f32",
-                "sr_styled_bwd_prologue3_f32")
+                "sr_styled_bwd_prologue3_f32", "sr_conv_igemm_multi_bf16", "sr_conv_wgrad_bf16", "sr_modulate_bf16",
+                "sr_conv_weight_prep_dual_bf16", "sr_blur_nhwc_styled3_bf16", "sr_blur_nhwc_scaledot_bf16",
+                "sr_styled_bwd_prologue3_bf16")
 
 
 class NativeLibraryError(RuntimeError):

@@ -17,6 +17,6 @@ void set_error(const char *fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace sr
 
-extern "C" int sr_abi_version(void) { return 3; }
+extern "C" int sr_abi_version(void) { return 4; }
 extern "C" const char *sr_last_error(void) { return sr::g_err; }
 extern "C" int64_t sr_launch_count(void) { return sr::g_launches.load(std::memory_order_relaxed); }

@@ -97,6 +97,24 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         "}\n" :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// same with 16-bit operands (kind::f16: bf16 x bf16 -> fp32; K = 16 elements = the same 32 bytes per instruction)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// two floats -> one 32-bit word of two bf16 (round to nearest even), `lo` in the low half = the lower address
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// instruction descriptor: tf32 formats (2) -> bf16 formats (1) for both operands
+__device__ __forceinline__ uint32_t idesc_bf16(uint32_t idesc_tf32) { return idesc_tf32 - (1u << 7) - (1u << 10); }
+
 // K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor:
 // start >> 4 at [0,14), LBO >> 4 at [16,30) (unused for swizzled K-major, 1), SBO >> 4 at [32,46),
 // version 1 at [46,48), layout SWIZZLE_128B = 2 at [61,64)).
@@ -154,7 +172,10 @@ struct ConvPhase {                          // one tap list + output lattice (th
 struct ConvKParams {
     int tw_log2, th_log2, tn_log2;          // tile = 2^tn images x 2^th rows x 2^tw columns = 128 pixels
     int batch;
-    int kblocks_per_tap;                    // cin / 32
+    int op16;                               // 0: fp32 words holding tf32 operands (kind::tf32)   1: bf16 operands (kind::f16);
+                                            // applies to the activation operand, the weights and the second output
+    int kelems;                             // channels per 128-byte K block: 32 (tf32) or 64 (bf16)
+    int kblocks_per_tap;                    // cin / kelems
     int num_phases, n_tiles, total_tiles;   // total_tiles = (sum of M tiles) * n_tiles
     int total_pairs;                        // CTA-pair kernel: (sum of padded M tiles / 2) * n_tiles
     // Tile order: image groups outermost, then phases, then the tiles of the phase.  With one image (or tn-image tile) per
@@ -272,7 +293,7 @@ __device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvOu
     // one pixel) instead of TMA stores: nothing in the chunk loop waits for the TMA unit, which is busy with the loads.
     // rowoff[i] = element offset of row (lane / 8 + 4 i) of this warp's 32 rows, or -1 outside the lattice.
     long long rowoff[8];
-    const bool direct = STAGED && (p.debug & 8);
+    const bool direct = STAGED && (p.debug & 8) && !p.op16;
     if (direct) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -355,12 +376,29 @@ __device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvOu
                 if (lane == 0) tma_store_wait_read<1>();
                 __syncwarp();
             }
+            if (p.op16) {
+                // bf16 operand for the next layer: 32 channels = 64 bytes per row, 64-byte swizzle (16-byte chunk q of row r
+                // lives at chunk q ^ ((r >> 1) & 3): conflict free for the 8 lanes of a store wavefront)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 s = STAGED ? *reinterpret_cast<const float4 *>(vb + BLOCK_N + c * 32 + 4 * j) : __ldg(s2 + j);
-                *reinterpret_cast<float4 *>(buf2 + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                    make_float4(round_tf32(y[4 * j] * s.x), round_tf32(y[4 * j + 1] * s.y), round_tf32(y[4 * j + 2] * s.z),
-                                round_tf32(y[4 * j + 3] * s.w));
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int j = 2 * q4 + h;
+                        const float4 s = STAGED ? *reinterpret_cast<const float4 *>(vb + BLOCK_N + c * 32 + 4 * j) : __ldg(s2 + j);
+                        w[2 * h] = pack_bf16(y[4 * j] * s.x, y[4 * j + 1] * s.y);
+                        w[2 * h + 1] = pack_bf16(y[4 * j + 2] * s.z, y[4 * j + 3] * s.w);
+                    }
+                    *reinterpret_cast<uint4 *>(buf2 + lane * 64 + ((q4 ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 s = STAGED ? *reinterpret_cast<const float4 *>(vb + BLOCK_N + c * 32 + 4 * j) : __ldg(s2 + j);
+                    *reinterpret_cast<float4 *>(buf2 + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                        make_float4(round_tf32(y[4 * j] * s.x), round_tf32(y[4 * j + 1] * s.y), round_tf32(y[4 * j + 2] * s.z),
+                                    round_tf32(y[4 * j + 3] * s.w));
+                }
             }
             if (direct) {
                 __syncwarp();
@@ -436,8 +474,8 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     mbar_wait(&empty_bar[s], par ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
-                        tma_load_4d(sA + s * A_BYTES, &tmap_a, &full_bar[s], kc * BLOCK_K, cx, cy, tc.n0);
-                        tma_load_2d(sB + s * B_BYTES, &tmap_b, &full_bar[s], ph.tap_k0[t] + kc * BLOCK_K, tc.n_tile * BLOCK_N);
+                        tma_load_4d(sA + s * A_BYTES, &tmap_a, &full_bar[s], kc * p.kelems, cx, cy, tc.n0);
+                        tma_load_2d(sB + s * B_BYTES, &tmap_b, &full_bar[s], ph.tap_k0[t] + kc * p.kelems, tc.n_tile * BLOCK_N);
                     }
                     __syncwarp();
                     if (++s == STAGES) { s = 0; par ^= 1; }
@@ -462,8 +500,11 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 const uint64_t db = make_kmajor_sw128_desc(sB_u32 + s * B_BYTES);
                 if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 8; ++k)      // K = 8 per instruction = 32 bytes along the swizzled row
-                        if (!(p.debug & 2)) umma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
+                    for (int k = 0; k < BLOCK_K / 8; ++k) {    // one instruction = 32 bytes along the swizzled row (8 tf32 / 16 bf16)
+                        if (p.debug & 2) continue;
+                        if (p.op16) umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_bf16(kIdesc), (kb | k) != 0);
+                        else umma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
+                    }
                     tcgen05_commit(&empty_bar[s]);             // frees the ring slot once these MMAs have read it
                 }
                 __syncwarp();
@@ -550,6 +591,15 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, 
         "}\n" :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 __device__ __forceinline__ TileCoord decode_tile_pair(const ConvKParams &p, int P, int rank) {
     TileCoord c;
     c.n_tile = P % p.n_tiles;
@@ -628,8 +678,8 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                     mbar_wait(&empty_bar[s], par ^ 1);
                     if (elect_one()) {
                         if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * (A_BYTES + BH_BYTES));   // bytes of BOTH CTAs
-                        tma_load_4d_2sm(sA + s * A_BYTES, &tmap_a, &full_bar[s], kc * BLOCK_K, cx, cy, tc.n0);
-                        tma_load_2d_2sm(sB + s * BH_BYTES, &tmap_b, &full_bar[s], ph.tap_k0[t] + kc * BLOCK_K,
+                        tma_load_4d_2sm(sA + s * A_BYTES, &tmap_a, &full_bar[s], kc * p.kelems, cx, cy, tc.n0);
+                        tma_load_2d_2sm(sB + s * BH_BYTES, &tmap_b, &full_bar[s], ph.tap_k0[t] + kc * p.kelems,
                                         tc.n_tile * BLOCK_N + rank * (BLOCK_N / 2));
                     }
                     __syncwarp();
@@ -656,8 +706,11 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                     const uint64_t db = make_kmajor_sw128_desc(sB_u32 + s * BH_BYTES);
                     if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / 8; ++k)
-                            if (!(p.debug & 2)) umma_tf32_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
+                        for (int k = 0; k < BLOCK_K / 8; ++k) {
+                            if (p.debug & 2) continue;
+                            if (p.op16) umma_f16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_bf16(kIdesc), (kb | k) != 0);
+                            else umma_tf32_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
+                        }
                         tcgen05_commit_2sm(&empty_bar[s]);
                     }
                     __syncwarp();
@@ -811,7 +864,7 @@ conv_halo_tf32_2cta_kernel(const __grid_constant__ HaloMaps amaps, const __grid_
                     mbar_wait_warp(&a_empty[sa], pa ^ 1, p.debug & 4);
                     if (elect_one()) {
                         if (rank == 0) mbar_expect_tx(&a_full[sa], 2 * (uint32_t)h.g_bytes[g]);
-                        tma_load_4d_2sm(sA + sa * kHaloStageBytes, &amaps.a[h.g_map[g]], &a_full[sa], kc * BLOCK_K,
+                        tma_load_4d_2sm(sA + sa * kHaloStageBytes, &amaps.a[h.g_map[g]], &a_full[sa], kc * p.kelems,
                                         tc.gx0 + h.g_xoff[g], tc.gy0 + h.g_yoff[g], tc.n0);
                     }
                     __syncwarp();
@@ -826,7 +879,7 @@ conv_halo_tf32_2cta_kernel(const __grid_constant__ HaloMaps amaps, const __grid_
                             for (int j = 0; j < TPS; ++j)
                                 if (j < n)
                                     tma_load_2d_2sm(sB + sb * B_STAGE + j * BH_BYTES, &tmap_b, &b_full[sb],
-                                                    h.tap_k0[t + j] + kc * BLOCK_K, brow);
+                                                    h.tap_k0[t + j] + kc * p.kelems, brow);
                         }
                         __syncwarp();
                         if (++sb == SB) { sb = 0; pb ^= 1; }
@@ -866,8 +919,10 @@ conv_halo_tf32_2cta_kernel(const __grid_constant__ HaloMaps amaps, const __grid_
                                         const uint64_t db = make_kmajor_sw128_desc(b_base + j * BH_BYTES);
 #pragma unroll
                                         for (int k = 0; k < BLOCK_K / 8; ++k) {
-                                            if (!(p.debug & 2))
-                                                umma_tf32_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, accumulate);
+                                            if (!(p.debug & 2)) {
+                                                if (p.op16) umma_f16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_bf16(kIdesc), accumulate);
+                                                else umma_tf32_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, accumulate);
+                                            }
                                             accumulate = 1;
                                         }
                                     }
@@ -947,6 +1002,8 @@ struct WgradKParams {
     int g_dy[9], g_dx[9], x_dy[9], x_dx[9], tap_out[9];
     int taps_total, cin;
     float *dw;                                         // [cout][taps_total][cin]
+    int op16;                                          // 1: bf16 operands (64 channels per 128-byte column block, K = 16 pixels
+                                                       // per instruction, plain 128-byte swizzle); 0: tf32 in fp32 words
 };
 
 // MN-major tf32 operands exist in one shared-memory layout only: 128-byte swizzle with 32-byte atomicity
@@ -959,6 +1016,19 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, 
     d |= (uint64_t)(512 >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)1 << 61;
+    return d;
+}
+
+// 16-bit MN-major operands use the plain 128-byte swizzle (cute::UMMA::LayoutType::SWIZZLE_128B = 2, TMA
+// CU_TENSOR_MAP_SWIZZLE_128B): atoms of 8 K-rows x 128 B (64 channels); LBO = distance to the next 64-channel group along
+// M/N, SBO = distance to the next 8 K-rows.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc16(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
     return d;
 }
 
@@ -1014,15 +1084,18 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
                 const int tile_x = kt % p.tiles_x, tile_y = (kt / p.tiles_x) % p.tiles_y, tile_n = kt / (p.tiles_x * p.tiles_y);
                 const int gx0 = tile_x << p.tw_log2, gy0 = tile_y << p.th_log2, n0 = tile_n << p.tn_log2;
                 uint8_t *sa = smem + s * WG_STAGE_BYTES, *sb = sa + 4 * WG_COLBLK_BYTES;
-                mbar_expect_tx(&full_bar[s], WG_STAGE_BYTES);
+                const int cb = p.op16 ? 64 : 32, gb = p.op16 ? 2 : 4, xb = p.op16 ? NB / 2 : NB;   // channels per block, blocks
+                mbar_expect_tx(&full_bar[s], (gb + xb) * WG_COLBLK_BYTES);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    tma_load_4d(sa + j * WG_COLBLK_BYTES, &tmap_g, &full_bar[s], m_tile * BLOCK_M + j * 32,
-                                gx0 * p.g_stride + p.g_dx[tap], gy0 * p.g_stride + p.g_dy[tap], n0);
+                    if (j < gb)
+                        tma_load_4d(sa + j * WG_COLBLK_BYTES, &tmap_g, &full_bar[s], m_tile * BLOCK_M + j * cb,
+                                    gx0 * p.g_stride + p.g_dx[tap], gy0 * p.g_stride + p.g_dy[tap], n0);
 #pragma unroll
                 for (int j = 0; j < NB; ++j)
-                    tma_load_4d(sb + j * WG_COLBLK_BYTES, &tmap_x, &full_bar[s], n_tile * WG_N + j * 32,
-                                gx0 * p.x_stride + p.x_dx[tap], gy0 * p.x_stride + p.x_dy[tap], n0);
+                    if (j < xb)
+                        tma_load_4d(sb + j * WG_COLBLK_BYTES, &tmap_x, &full_bar[s], n_tile * WG_N + j * cb,
+                                    gx0 * p.x_stride + p.x_dx[tap], gy0 * p.x_stride + p.x_dy[tap], n0);
             }
         }
     } else if (warp == 1) {
@@ -1033,10 +1106,17 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
                 mbar_wait(&full_bar[s], ph);
                 tcgen05_fence_after();
                 const uint32_t a0 = smem_u32(smem + s * WG_STAGE_BYTES), b0 = a0 + 4 * WG_COLBLK_BYTES;
+                if (p.op16) {
 #pragma unroll
-                for (int k = 0; k < WG_BK / 8; ++k)    // 8 pixels (one swizzle atom of K rows) per instruction
-                    umma_tf32(tmem_base, make_mnmajor_sw128_desc(a0 + k * 1024, WG_COLBLK_BYTES),
-                              make_mnmajor_sw128_desc(b0 + k * 1024, WG_COLBLK_BYTES), kIdesc, (it | k) != 0);
+                    for (int k = 0; k < WG_BK / 16; ++k)   // 16 pixels (two 8-row atoms) per instruction
+                        umma_f16(tmem_base, make_mnmajor_sw128_desc16(a0 + k * 2048, WG_COLBLK_BYTES),
+                                 make_mnmajor_sw128_desc16(b0 + k * 2048, WG_COLBLK_BYTES), idesc_bf16(kIdesc), (it | k) != 0);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < WG_BK / 8; ++k)    // 8 pixels (one swizzle atom of K rows) per instruction
+                        umma_tf32(tmem_base, make_mnmajor_sw128_desc(a0 + k * 1024, WG_COLBLK_BYTES),
+                                  make_mnmajor_sw128_desc(b0 + k * 1024, WG_COLBLK_BYTES), kIdesc, (it | k) != 0);
+                }
                 tcgen05_commit(&empty_bar[s]);
             }
             tcgen05_commit(tmem_full_bar);
@@ -1122,12 +1202,14 @@ wgrad_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 const int tile_x = kt % p.tiles_x, tile_y = (kt / p.tiles_x) % p.tiles_y, tile_n = kt / (p.tiles_x * p.tiles_y);
                 const int gx0 = tile_x << p.tw_log2, gy0 = tile_y << p.th_log2, n0 = tile_n << p.tn_log2;
                 uint8_t *sa = smem + s * WG_STAGE_BYTES, *sb = sa + 4 * WG_COLBLK_BYTES;
-                if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * WG_STAGE_BYTES);
+                const int cb = p.op16 ? 64 : 32, nb = p.op16 ? 2 : 4;                     // channels per block, blocks per operand
+                if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * 2 * nb * WG_COLBLK_BYTES);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    tma_load_4d_2sm(sa + j * WG_COLBLK_BYTES, &tmap_g, &full_bar[s], m_tile * 256 + rank * 128 + j * 32,
+                    if (j >= nb) break;
+                    tma_load_4d_2sm(sa + j * WG_COLBLK_BYTES, &tmap_g, &full_bar[s], m_tile * 256 + rank * 128 + j * cb,
                                     gx0 * p.g_stride + p.g_dx[tap], gy0 * p.g_stride + p.g_dy[tap], n0);
-                    tma_load_4d_2sm(sb + j * WG_COLBLK_BYTES, &tmap_x, &full_bar[s], n_tile * 256 + rank * 128 + j * 32,
+                    tma_load_4d_2sm(sb + j * WG_COLBLK_BYTES, &tmap_x, &full_bar[s], n_tile * 256 + rank * 128 + j * cb,
                                     gx0 * p.x_stride + p.x_dx[tap], gy0 * p.x_stride + p.x_dy[tap], n0);
                 }
             }
@@ -1140,10 +1222,17 @@ wgrad_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 mbar_wait(&full_bar[s], ph);
                 tcgen05_fence_after();
                 const uint32_t a0 = smem_u32(smem + s * WG_STAGE_BYTES), b0 = a0 + 4 * WG_COLBLK_BYTES;
+                if (p.op16) {
 #pragma unroll
-                for (int k = 0; k < WG_BK / 8; ++k)
-                    umma_tf32_2sm(tmem_base, make_mnmajor_sw128_desc(a0 + k * 1024, WG_COLBLK_BYTES),
-                                  make_mnmajor_sw128_desc(b0 + k * 1024, WG_COLBLK_BYTES), kIdesc, (it | k) != 0);
+                    for (int k = 0; k < WG_BK / 16; ++k)
+                        umma_f16_2sm(tmem_base, make_mnmajor_sw128_desc16(a0 + k * 2048, WG_COLBLK_BYTES),
+                                     make_mnmajor_sw128_desc16(b0 + k * 2048, WG_COLBLK_BYTES), idesc_bf16(kIdesc), (it | k) != 0);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < WG_BK / 8; ++k)
+                        umma_tf32_2sm(tmem_base, make_mnmajor_sw128_desc(a0 + k * 1024, WG_COLBLK_BYTES),
+                                      make_mnmajor_sw128_desc(b0 + k * 1024, WG_COLBLK_BYTES), kIdesc, (it | k) != 0);
+                }
                 tcgen05_commit_2sm(&empty_bar[s]);
             }
             tcgen05_commit_2sm(tmem_full_bar);
@@ -1233,15 +1322,18 @@ wgrad_tf32_2cta_taps_kernel(const __grid_constant__ CUtensorMap tmap_g, const __
                 const int tile_x = kt % p.tiles_x, tile_y = (kt / p.tiles_x) % p.tiles_y, tile_n = kt / (p.tiles_x * p.tiles_y);
                 const int gx0 = tile_x << p.tw_log2, gy0 = tile_y << p.th_log2, n0 = tile_n << p.tn_log2;
                 uint8_t *sa = smem + s * WG_STAGE_BYTES, *sb = sa + 4 * WG_COLBLK_BYTES;
-                if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * WG_STAGE_BYTES);
+                const int cb = p.op16 ? 64 : 32, gb = p.op16 ? 2 : 4, xb = p.op16 ? 1 : 2;      // channels per block, blocks of G / X
+                if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * (gb + xb) * WG_COLBLK_BYTES);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    tma_load_4d_2sm(sa + j * WG_COLBLK_BYTES, &tmap_g, &full_bar[s], m_tile * 128 + j * 32,
-                                    gx0 * p.g_stride + p.g_dx[tap], gy0 * p.g_stride + p.g_dy[tap], n0);
+                    if (j < gb)
+                        tma_load_4d_2sm(sa + j * WG_COLBLK_BYTES, &tmap_g, &full_bar[s], m_tile * 128 + j * cb,
+                                        gx0 * p.g_stride + p.g_dx[tap], gy0 * p.g_stride + p.g_dy[tap], n0);
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
-                    tma_load_4d_2sm(sb + j * WG_COLBLK_BYTES, &tmap_x, &full_bar[s], n_tile * 128 + rank * 64 + j * 32,
-                                    gx0 * p.x_stride + p.x_dx[0], gy0 * p.x_stride + p.x_dy[0], n0);
+                    if (j < xb)
+                        tma_load_4d_2sm(sb + j * WG_COLBLK_BYTES, &tmap_x, &full_bar[s], n_tile * 128 + rank * 64 + j * cb,
+                                        gx0 * p.x_stride + p.x_dx[0], gy0 * p.x_stride + p.x_dy[0], n0);
             }
         }
     } else if (warp == 1) {
@@ -1252,10 +1344,17 @@ wgrad_tf32_2cta_taps_kernel(const __grid_constant__ CUtensorMap tmap_g, const __
                 mbar_wait(&full_bar[s], ph);
                 tcgen05_fence_after();
                 const uint32_t a0 = smem_u32(smem + s * WG_STAGE_BYTES), b0 = a0 + 4 * WG_COLBLK_BYTES;
+                if (p.op16) {
 #pragma unroll
-                for (int k = 0; k < WG_BK / 8; ++k)
-                    umma_tf32_2sm(tmem_base, make_mnmajor_sw128_desc(a0 + k * 1024, WG_COLBLK_BYTES),
-                                  make_mnmajor_sw128_desc(b0 + k * 1024, WG_COLBLK_BYTES), kIdesc, (it | k) != 0);
+                    for (int k = 0; k < WG_BK / 16; ++k)
+                        umma_f16_2sm(tmem_base, make_mnmajor_sw128_desc16(a0 + k * 2048, WG_COLBLK_BYTES),
+                                     make_mnmajor_sw128_desc16(b0 + k * 2048, WG_COLBLK_BYTES), idesc_bf16(kIdesc), (it | k) != 0);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < WG_BK / 8; ++k)
+                        umma_tf32_2sm(tmem_base, make_mnmajor_sw128_desc(a0 + k * 1024, WG_COLBLK_BYTES),
+                                      make_mnmajor_sw128_desc(b0 + k * 1024, WG_COLBLK_BYTES), kIdesc, (it | k) != 0);
+                }
                 tcgen05_commit_2sm(&empty_bar[s]);
             }
             tcgen05_commit_2sm(tmem_full_bar);
@@ -1288,6 +1387,7 @@ wgrad_tf32_2cta_taps_kernel(const __grid_constant__ CUtensorMap tmap_g, const __
 
 // ------------------------------------------------------------------------------------ small helper kernels
 // xs[b,p,c] = tf32(x[b,p,c] * s[b,c])  -- the modulated, tensor-core-ready copy of an NHWC activation
+template <bool BF16>
 __global__ void __launch_bounds__(256)
 modulate_tf32_kernel(float *__restrict__ xs, const float *__restrict__ x, const float *__restrict__ s,
                      uint32_t n4, FastDiv c4_div, FastDiv img4_div, int c4)
@@ -1299,8 +1399,12 @@ modulate_tf32_kernel(float *__restrict__ xs, const float *__restrict__ x, const 
         img4_div.divmod(i, b, rem);                   // image index
         const float4 v = ld_stream4(x + 4ull * i);
         const float4 m = s ? __ldg(reinterpret_cast<const float4 *>(s) + (size_t)b * c4 + cq) : make_float4(1.f, 1.f, 1.f, 1.f);
-        float4 o = make_float4(round_tf32(v.x * m.x), round_tf32(v.y * m.y), round_tf32(v.z * m.z), round_tf32(v.w * m.w));
-        *reinterpret_cast<float4 *>(xs + 4ull * i) = o;
+        if (BF16) {                                   // xs is a bfloat16 tensor: 4 channels = 8 bytes
+            reinterpret_cast<uint2 *>(xs)[i] = make_uint2(pack_bf16(v.x * m.x, v.y * m.y), pack_bf16(v.z * m.z, v.w * m.w));
+        } else {
+            float4 o = make_float4(round_tf32(v.x * m.x), round_tf32(v.y * m.y), round_tf32(v.z * m.z), round_tf32(v.w * m.w));
+            *reinterpret_cast<float4 *>(xs + 4ull * i) = o;
+        }
     }
 }
 
@@ -1337,9 +1441,19 @@ weight_prep_kernel(float *__restrict__ dst, const float *__restrict__ w, float s
 // A CTA owns a 32 x 32 (co, ci) block: the read is one contiguous 32*taps-float run per co, both writes are 128-byte
 // rows (through a shared-memory transpose); the per-mode kernel above scatters 4-byte stores for the transposed layout.
 constexpr int kWP = 32;
+__device__ __forceinline__ void store_operand(float *base, int64_t idx, float v, bool bf16) {
+    if (bf16) {
+        uint16_t h;
+        asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(h) : "f"(v));
+        reinterpret_cast<uint16_t *>(base)[idx] = h;
+    } else {
+        base[idx] = round_tf32(v);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 weight_prep_dual_kernel(float *__restrict__ fwd, float *__restrict__ tr, float *__restrict__ wsq, const float *__restrict__ w,
-                        float scale, int cout, int cin, int taps, int flip)
+                        float scale, int cout, int cin, int taps, int flip, int bf16)
 {
     extern __shared__ float wt[];                         // [32 co][32 ci * taps + 1]
     const int row = kWP * taps + 1;
@@ -1355,7 +1469,7 @@ weight_prep_dual_kernel(float *__restrict__ fwd, float *__restrict__ tr, float *
         for (int q = wid; q < kWP * taps; q += 8) {
             const int r = q / taps, t = q - r * taps;
             if (co0 + r < cout && ci0 + lane < cin)
-                fwd[((int64_t)(co0 + r) * taps + t) * cin + ci0 + lane] = round_tf32(wt[r * row + lane * taps + t]);
+                store_operand(fwd, ((int64_t)(co0 + r) * taps + t) * cin + ci0 + lane, wt[r * row + lane * taps + t], bf16 != 0);
         }
     }
     if (tr) {                                             // rows (ci, t'), 32 consecutive co
@@ -1363,7 +1477,7 @@ weight_prep_dual_kernel(float *__restrict__ fwd, float *__restrict__ tr, float *
             const int c = q / taps, t = q - c * taps;
             const int tt = flip ? taps - 1 - t : t;
             if (ci0 + c < cin && co0 + lane < cout)
-                tr[((int64_t)(ci0 + c) * taps + tt) * cout + co0 + lane] = round_tf32(wt[lane * row + c * taps + t]);
+                store_operand(tr, ((int64_t)(ci0 + c) * taps + tt) * cout + co0 + lane, wt[lane * row + c * taps + t], bf16 != 0);
         }
     }
     if (wsq) {
@@ -1438,8 +1552,10 @@ int launch_conv_halo(const HaloMaps &am, const CUtensorMap &tb, const ConvOutMap
 
 // Group the taps of every phase by parity class modulo the input stride and describe each class as a halo box
 // (see conv_halo_tf32_2cta_kernel).  Returns false when the problem does not fit the halo kernel.
-bool build_halo(const sr_conv_args *args, int count, EncodeTiledFn enc, HaloParams &hp, HaloMaps &am)
+bool build_halo(const sr_conv_args *args, int count, EncodeTiledFn enc, HaloParams &hp, HaloMaps &am, int op16)
 {
+    const int esize = op16 ? 2 : 4, kelems = 128 / esize;
+    const CUtensorMapDataType dtype = op16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     const sr_conv_args *a = args;
     const int s = a->in_stride;
     // Default: one (8 + rx)-wide box per parity class; operand groups then start on arbitrary 128-byte rows, which costs
@@ -1483,13 +1599,13 @@ bool build_halo(const sr_conv_args *args, int count, EncodeTiledFn enc, HaloPara
                 if (m == kMaxGroups) return false;
                 const int64_t lw = (a->in_w - cls_x[g] + s - 1) / s, lh = (a->in_h - cls_y[g] + s - 1) / s;
                 if (lw < 1 || lh < 1) return false;
-                const float *base = a->in + ((int64_t)cls_y[g] * a->in_w + cls_x[g]) * a->cin;
+                const char *base = reinterpret_cast<const char *>(a->in) + ((int64_t)cls_y[g] * a->in_w + cls_x[g]) * a->cin * esize;
                 cuuint64_t dims[4] = {(cuuint64_t)a->cin, (cuuint64_t)lw, (cuuint64_t)lh, (cuuint64_t)a->batch};
-                cuuint64_t strides[3] = {(cuuint64_t)a->cin * 4 * s, (cuuint64_t)a->in_w * a->cin * 4 * s,
-                                         (cuuint64_t)a->in_h * a->in_w * a->cin * 4};
-                cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)hw, (cuuint32_t)hh, 1};
+                cuuint64_t strides[3] = {(cuuint64_t)a->cin * esize * s, (cuuint64_t)a->in_w * a->cin * esize * s,
+                                         (cuuint64_t)a->in_h * a->in_w * a->cin * esize};
+                cuuint32_t box[4] = {(cuuint32_t)kelems, (cuuint32_t)hw, (cuuint32_t)hh, 1};
                 cuuint32_t estr[4] = {1, 1, 1, 1};
-                if (enc(&am.a[m], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims, strides, box, estr,
+                if (enc(&am.a[m], dtype, 4, const_cast<char *>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
                 keys[m] = {cls_y[g], cls_x[g], hw, hh};
@@ -1522,12 +1638,14 @@ using namespace sr;
 
 // `count` launches that share tensors / strides / epilogue and differ only in tap list, lattice size and lattice
 // origin (the four parity classes of the stride-2 transposed conv) run as ONE persistent grid.
-extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, void *stream)
+static int conv_igemm_multi(const sr_conv_args *args, int count, void *stream, int op16)
 {
     SR_REQUIRE(args && count >= 1 && count <= kMaxPhases, "conv: 1..4 phases");
     const sr_conv_args *a = args;
+    const int esize = op16 ? 2 : 4, kelems = 128 / esize;          // one K block = one 128-byte swizzle row of channels
+    const CUtensorMapDataType op_dtype = op16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     SR_REQUIRE(a->in && a->weight && a->out, "conv: null tensor");
-    SR_REQUIRE(a->cin >= 32 && a->cin % 32 == 0, "conv: cin must be a multiple of 32 (got %lld)", (long long)a->cin);
+    SR_REQUIRE(a->cin >= kelems && a->cin % kelems == 0, "conv: cin must be a multiple of %d (got %lld)", kelems, (long long)a->cin);
     SR_REQUIRE(a->cout >= 128 && a->cout % 128 == 0, "conv: cout must be a multiple of 128 (got %lld)", (long long)a->cout);
     SR_REQUIRE(a->in_stride >= 1 && a->in_stride <= 8 && a->out_stride >= 1, "conv: bad strides");
     SR_REQUIRE(a->batch >= 1, "conv: empty problem");
@@ -1569,7 +1687,7 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
             const long long t_ph = ((args[i].grid_w + 7) / 8) * ((args[i].grid_h + 15) / 16) * a->batch;
             mt2 += (t_ph + 1) / 2 * 2;
         }
-        use_halo = mt2 / 2 * (a->cout / 128) >= 32 && build_halo(args, count, enc, hp, am);
+        use_halo = mt2 / 2 * (a->cout / 128) >= 32 && build_halo(args, count, enc, hp, am, op16);
     }
 
     // tile shape: 16x8 pixels of one image, or several whole small images
@@ -1582,7 +1700,8 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
     ConvKParams p;
     p.tw_log2 = ilog2_exact(tw); p.th_log2 = ilog2_exact(th); p.tn_log2 = ilog2_exact(tn);
     p.batch = (int)a->batch;
-    p.kblocks_per_tap = (int)(a->cin / BLOCK_K);
+    p.op16 = op16; p.kelems = kelems;
+    p.kblocks_per_tap = (int)(a->cin / kelems);
     p.num_phases = count;
     const int tiles_n = (int)((a->batch + tn - 1) / tn);
     // multi-phase launches whose input does not fit in L2: one image per group (measured 0.66 vs 0.70 ms at 256->128
@@ -1632,12 +1751,12 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
     CUtensorMap ta, tb;
     {
         cuuint64_t dims[4] = {(cuuint64_t)a->cin, (cuuint64_t)a->in_w, (cuuint64_t)a->in_h, (cuuint64_t)a->batch};
-        cuuint64_t strides[3] = {(cuuint64_t)a->cin * 4, (cuuint64_t)a->in_w * a->cin * 4,
-                                 (cuuint64_t)a->in_h * a->in_w * a->cin * 4};
+        cuuint64_t strides[3] = {(cuuint64_t)a->cin * esize, (cuuint64_t)a->in_w * a->cin * esize,
+                                 (cuuint64_t)a->in_h * a->in_w * a->cin * esize};
         const cuuint32_t s = (cuuint32_t)a->in_stride;
-        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)tw * s, (cuuint32_t)th * s, (cuuint32_t)tn};
+        cuuint32_t box[4] = {(cuuint32_t)kelems, (cuuint32_t)tw * s, (cuuint32_t)th * s, (cuuint32_t)tn};
         cuuint32_t estr[4] = {1, s, s, 1};
-        CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(a->in), dims, strides, box, estr,
+        CUresult r = enc(&ta, op_dtype, 4, const_cast<float *>(a->in), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv: cuTensorMapEncodeTiled(A) failed with %d", (int)r); return SR_ERR_DRIVER; }
@@ -1645,10 +1764,10 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
     {
         const cuuint64_t ktot = (cuuint64_t)a->taps_total * a->cin;
         cuuint64_t dims[2] = {ktot, (cuuint64_t)a->cout};
-        cuuint64_t strides[1] = {ktot * 4};
-        cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)(use_2cta ? block_n / 2 : block_n)};   // a CTA of a pair stages half the rows
+        cuuint64_t strides[1] = {ktot * esize};
+        cuuint32_t box[2] = {(cuuint32_t)kelems, (cuuint32_t)(use_2cta ? block_n / 2 : block_n)};   // a CTA of a pair stages half the rows
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(a->weight), dims, strides, box, estr,
+        CUresult r = enc(&tb, op_dtype, 2, const_cast<float *>(a->weight), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv: cuTensorMapEncodeTiled(B) failed with %d", (int)r); return SR_ERR_DRIVER; }
@@ -1662,17 +1781,22 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
         for (int i = 0; i < kMaxPhases; ++i) {
             const sr_conv_args *b = args + (i < count ? i : 0);
             for (int which = 0; which < 2; ++which) {
-                float *base = which == 0 ? a->out : a->out2;
+                char *base = reinterpret_cast<char *>(which == 0 ? a->out : a->out2);
                 CUtensorMap *m = which == 0 ? &om.out[i] : &om.out2[i];
                 if (!base) { om.out2[i] = om.out[i]; continue; }
-                base += ((long long)b->out_y0 * a->out_w + b->out_x0) * a->cout;
+                // `out` is always fp32; the second output (the next layer's operand) has the operand type: a warp's
+                // 32 x 32-channel block is 128-byte rows (fp32, 128-byte swizzle) or 64-byte rows (bf16, 64-byte swizzle)
+                const bool o16 = which == 1 && op16;
+                const long long es = o16 ? 2 : 4;
+                base += ((long long)b->out_y0 * a->out_w + b->out_x0) * a->cout * es;
                 cuuint64_t dims[4] = {(cuuint64_t)a->cout, (cuuint64_t)b->grid_w, (cuuint64_t)b->grid_h, (cuuint64_t)a->batch};
-                cuuint64_t strides[3] = {(cuuint64_t)a->out_stride * a->cout * 4, (cuuint64_t)a->out_stride * a->out_w * a->cout * 4,
-                                         (cuuint64_t)a->out_h * a->out_w * a->cout * 4};
+                cuuint64_t strides[3] = {(cuuint64_t)(a->out_stride * a->cout * es), (cuuint64_t)(a->out_stride * a->out_w * a->cout * es),
+                                         (cuuint64_t)(a->out_h * a->out_w * a->cout * es)};
                 cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
                 cuuint32_t estr[4] = {1, 1, 1, 1};
-                CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                CUresult r = enc(m, o16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides,
+                                 box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, o16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r != CUDA_SUCCESS) { set_error("conv: cuTensorMapEncodeTiled(out) failed with %d", (int)r); return SR_ERR_DRIVER; }
             }
         }
@@ -1725,11 +1849,16 @@ extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, voi
     return check_launch("sr_conv_igemm_tf32");
 }
 
-extern "C" int sr_conv_igemm_tf32(const sr_conv_args *a, void *stream) { return sr_conv_igemm_multi_tf32(a, 1, stream); }
+extern "C" int sr_conv_igemm_multi_tf32(const sr_conv_args *args, int count, void *stream) { return conv_igemm_multi(args, count, stream, 0); }
+extern "C" int sr_conv_igemm_tf32(const sr_conv_args *a, void *stream) { return conv_igemm_multi(a, 1, stream, 0); }
+// bf16 operand form: `in`, `weight` and `out2` point to bfloat16 data of the same logical shapes; `out`, the epilogue
+// vectors and the accumulation stay fp32.  cin % 64 == 0.  (BASELINE.json configs[3]: the bf16 train step.)
+extern "C" int sr_conv_igemm_multi_bf16(const sr_conv_args *args, int count, void *stream) { return conv_igemm_multi(args, count, stream, 1); }
 
-extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
+static int conv_wgrad(const sr_wgrad_args *a, void *stream, int op16)
 {
     SR_REQUIRE(a && a->g && a->x && a->dw, "wgrad: null argument");
+    const int esize = op16 ? 2 : 4;
     SR_REQUIRE(a->cout >= 128 && a->cout % 128 == 0 && a->cin >= 128 && a->cin % 128 == 0,
                "wgrad: cin and cout must be multiples of 128 (got %lld, %lld)", (long long)a->cin, (long long)a->cout);
     SR_REQUIRE(a->num_taps >= 1 && a->num_taps <= 9 && a->g_stride >= 1 && a->x_stride >= 1, "wgrad: bad taps/strides");
@@ -1779,12 +1908,14 @@ extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
     CUtensorMap tg, tx;
     auto make_map = [&](CUtensorMap *m, const float *base, int64_t hh, int64_t ww, int64_t cc, int stride) -> int {
         cuuint64_t dims[4] = {(cuuint64_t)cc, (cuuint64_t)ww, (cuuint64_t)hh, (cuuint64_t)a->batch};
-        cuuint64_t strides[3] = {(cuuint64_t)cc * 4, (cuuint64_t)ww * cc * 4, (cuuint64_t)hh * ww * cc * 4};
+        cuuint64_t strides[3] = {(cuuint64_t)cc * esize, (cuuint64_t)ww * cc * esize, (cuuint64_t)hh * ww * cc * esize};
         const cuuint32_t s = (cuuint32_t)stride;
-        cuuint32_t box[4] = {32, (cuuint32_t)tw * s, (cuuint32_t)th * s, (cuuint32_t)tn};
+        cuuint32_t box[4] = {(cuuint32_t)(128 / esize), (cuuint32_t)tw * s, (cuuint32_t)th * s, (cuuint32_t)tn};
         cuuint32_t estr[4] = {1, s, s, 1};
-        CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+        // MN-major operands: tf32 exists only with 32-byte swizzle atomicity, 16-bit types take the plain 128-byte swizzle
+        CUresult r = enc(m, op16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                         const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         op16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("wgrad: cuTensorMapEncodeTiled failed with %d", (int)r); return SR_ERR_DRIVER; }
         return SR_OK;
@@ -1829,6 +1960,7 @@ extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
     }
     p.taps_total = (int)a->taps_total; p.cin = (int)a->cin;
     p.dw = a->dw;
+    p.op16 = op16;
     if (a->zero_init) {
         cudaError_t e = cudaMemsetAsync(a->dw, 0, sizeof(float) * (size_t)a->cout * a->taps_total * a->cin, st);
         if (e != cudaSuccess) { set_error("wgrad: memset: %s", cudaGetErrorString(e)); return (int)e; }
@@ -1876,8 +2008,12 @@ extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream)
     return check_launch("sr_conv_wgrad_tf32");
 }
 
-extern "C" int sr_modulate_tf32(float *xs, const float *x, const float *style, int64_t batch, int64_t pixels,
-                                int64_t channels, void *stream)
+extern "C" int sr_conv_wgrad_tf32(const sr_wgrad_args *a, void *stream) { return conv_wgrad(a, stream, 0); }
+// bf16 operand form: g and x point to bfloat16 NHWC tensors; dw stays fp32 (split-K reduction with fp32 atomics).
+extern "C" int sr_conv_wgrad_bf16(const sr_wgrad_args *a, void *stream) { return conv_wgrad(a, stream, 1); }
+
+static int modulate_any(float *xs, const float *x, const float *style, int64_t batch, int64_t pixels, int64_t channels,
+                        void *stream, bool bf16)
 {
     SR_REQUIRE(xs && x, "modulate: null pointer");
     SR_REQUIRE(channels % 4 == 0, "modulate: channels must be a multiple of 4");
@@ -1888,11 +2024,28 @@ extern "C" int sr_modulate_tf32(float *xs, const float *x, const float *style, i
     SR_REQUIRE(n4 < 0x7fffffffll, "modulate: tensor too large");
     int64_t blocks = (n4 + 255) / 256;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    modulate_tf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        xs, x, style, (uint32_t)n4, FastDiv((uint32_t)(channels / 4)), FastDiv((uint32_t)(pixels * channels / 4)),
-        (int)(channels / 4));
+    if (bf16)
+        modulate_tf32_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            xs, x, style, (uint32_t)n4, FastDiv((uint32_t)(channels / 4)), FastDiv((uint32_t)(pixels * channels / 4)),
+            (int)(channels / 4));
+    else
+        modulate_tf32_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            xs, x, style, (uint32_t)n4, FastDiv((uint32_t)(channels / 4)), FastDiv((uint32_t)(pixels * channels / 4)),
+            (int)(channels / 4));
     count_launch();
     return check_launch("sr_modulate_tf32");
+}
+
+extern "C" int sr_modulate_tf32(float *xs, const float *x, const float *style, int64_t batch, int64_t pixels,
+                                int64_t channels, void *stream)
+{
+    return modulate_any(xs, x, style, batch, pixels, channels, stream, false);
+}
+// xs is a bfloat16 tensor [batch, pixels, channels] (round to nearest even)
+extern "C" int sr_modulate_bf16(void *xs, const float *x, const float *style, int64_t batch, int64_t pixels,
+                                int64_t channels, void *stream)
+{
+    return modulate_any(reinterpret_cast<float *>(xs), x, style, batch, pixels, channels, stream, true);
 }
 
 extern "C" int sr_conv_weight_prep_tf32(float *dst, const float *w, float scale, int64_t cout, int64_t cin, int kh, int kw,
@@ -1908,15 +2061,28 @@ extern "C" int sr_conv_weight_prep_tf32(float *dst, const float *w, float scale,
     return check_launch("sr_conv_weight_prep_tf32");
 }
 
-extern "C" int sr_conv_weight_prep_dual_tf32(float *fwd, float *tr, float *wsq, const float *w, float scale, int64_t cout,
-                                             int64_t cin, int taps, int flip_transposed, void *stream)
+static int weight_prep_dual_any(float *fwd, float *tr, float *wsq, const float *w, float scale, int64_t cout, int64_t cin,
+                                int taps, int flip_transposed, void *stream, int bf16)
 {
     SR_REQUIRE(w && cout > 0 && cin > 0 && taps > 0 && taps <= 25, "weight_prep_dual: bad arguments");
     SR_REQUIRE(fwd || tr || wsq, "weight_prep_dual: nothing to produce");
     const dim3 grid((unsigned)((cin + kWP - 1) / kWP), (unsigned)((cout + kWP - 1) / kWP));
     const size_t smem = sizeof(float) * kWP * (kWP * taps + 1);
     weight_prep_dual_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(fwd, tr, wsq, w, scale, (int)cout, (int)cin, taps,
-                                                                    flip_transposed);
+                                                                    flip_transposed, bf16);
     count_launch();
     return check_launch("sr_conv_weight_prep_dual_tf32");
+}
+
+extern "C" int sr_conv_weight_prep_dual_tf32(float *fwd, float *tr, float *wsq, const float *w, float scale, int64_t cout,
+                                             int64_t cin, int taps, int flip_transposed, void *stream)
+{
+    return weight_prep_dual_any(fwd, tr, wsq, w, scale, cout, cin, taps, flip_transposed, stream, 0);
+}
+// fwd / tr are bfloat16 tensors of the same shapes; wsq stays fp32 (computed from the unrounded weights)
+extern "C" int sr_conv_weight_prep_dual_bf16(void *fwd, void *tr, float *wsq, const float *w, float scale, int64_t cout,
+                                             int64_t cin, int taps, int flip_transposed, void *stream)
+{
+    return weight_prep_dual_any(reinterpret_cast<float *>(fwd), reinterpret_cast<float *>(tr), wsq, w, scale, cout, cin, taps,
+                                flip_transposed, stream, 1);
 }

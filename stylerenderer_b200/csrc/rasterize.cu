@@ -69,8 +69,28 @@ __device__ __forceinline__ int clamp_hi(float v, int span) {
     return v >= (float)(span - 1) ? span - 1 : (v < -1.0f ? -1 : (int)floorf(v));
 }
 
-// reference op/rasterize.h:9-75 (`barycentric` with det_ != NULL); mirrors oracle sr_tri_setup.
+// NDC -> pixel coordinates of ONE vertex (reference op/rasterize.h:15-22), in place: q = (x, y, z) -> (X, Y, z).
+// The perspective rejection (z >= -eps) is NOT decided here: it needs the untouched z, which stays in q[2].
 template <typename T>
+__device__ __forceinline__ void project_vertex(T *q, int span_x, int span_y, bool perspective, T eps)
+{
+    using R = RN<T>;
+    if (perspective && !(q[2] >= -eps)) {
+        q[0] = R::div(q[0], -q[2]);
+        q[1] = R::div(q[1], -q[2]);
+    }
+    // ((1 + x) * W / 2) - .5 : the reference subtracts a double .5 and rounds back, which for
+    // +,-,*,/ equals the single-precision operation (innocuous double rounding)
+    // `/ 2` as `* 0.5`: bit-identical for every finite or infinite input (a power-of-two scaling, checked on the CPU
+    // over all 2^32 float patterns) and one FMUL instead of an IEEE division (FCHK + slow path)
+    q[0] = R::sub(R::mul(R::mul(R::add((T)1, q[0]), (T)span_x), (T)0.5), (T)0.5);
+    q[1] = R::sub(R::mul(R::mul(R::sub((T)1, q[1]), (T)span_y), (T)0.5), (T)0.5);
+}
+
+// reference op/rasterize.h:9-75 (`barycentric` with det_ != NULL); mirrors oracle sr_tri_setup.
+// PROJECTED: t.p already holds pixel coordinates (project_vertex, e.g. from the per-vertex pre-pass).
+// CLIP: compute the clamped pixel box and reject empty ones (the resolve pass knows its pixel and skips it).
+template <typename T, bool PROJECTED = false, bool CLIP = true>
 __device__ __forceinline__ bool tri_setup(Tri<T> &t, int span_x, int span_y, bool perspective, T eps)
 {
     using R = RN<T>;
@@ -78,26 +98,21 @@ __device__ __forceinline__ bool tri_setup(Tri<T> &t, int span_x, int span_y, boo
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         T *q = t.p + 3 * c;
-        if (perspective) {
-            if (q[2] >= -eps) return false;
-            q[0] = R::div(q[0], -q[2]);
-            q[1] = R::div(q[1], -q[2]);
-        }
-        // ((1 + x) * W / 2) - .5 : the reference subtracts a double .5 and rounds back, which for
-        // +,-,*,/ equals the single-precision operation (innocuous double rounding)
-        // `/ 2` as `* 0.5`: bit-identical for every finite or infinite input (a power-of-two scaling, checked on the CPU
-        // over all 2^32 float patterns) and one FMUL instead of an IEEE division (FCHK + slow path)
-        q[0] = R::sub(R::mul(R::mul(R::add((T)1, q[0]), (T)span_x), (T)0.5), (T)0.5);
-        q[1] = R::sub(R::mul(R::mul(R::sub((T)1, q[1]), (T)span_y), (T)0.5), (T)0.5);
-        if (c == 0) { xmin = xmax = q[0]; ymin = ymax = q[1]; }
-        else {
-            if (xmin > q[0]) xmin = q[0]; else if (xmax < q[0]) xmax = q[0];
-            if (ymin > q[1]) ymin = q[1]; else if (ymax < q[1]) ymax = q[1];
+        if (perspective && q[2] >= -eps) return false;
+        if (!PROJECTED) project_vertex<T>(q, span_x, span_y, perspective, eps);
+        if (CLIP) {
+            if (c == 0) { xmin = xmax = q[0]; ymin = ymax = q[1]; }
+            else {
+                if (xmin > q[0]) xmin = q[0]; else if (xmax < q[0]) xmax = q[0];
+                if (ymin > q[1]) ymin = q[1]; else if (ymax < q[1]) ymax = q[1];
+            }
         }
     }
-    t.x_lo = clamp_lo(xmin); t.x_hi = clamp_hi(xmax, span_x);
-    t.y_lo = clamp_lo(ymin); t.y_hi = clamp_hi(ymax, span_y);
-    if (t.x_hi < t.x_lo || t.y_hi < t.y_lo) return false;
+    if (CLIP) {
+        t.x_lo = clamp_lo(xmin); t.x_hi = clamp_hi(xmax, span_x);
+        t.y_lo = clamp_lo(ymin); t.y_hi = clamp_hi(ymax, span_y);
+        if (t.x_hi < t.x_lo || t.y_hi < t.y_lo) return false;
+    }
     const T *p = t.p;
     T *E = t.E;
     E[0] = R::sub(R::mul(p[3], p[7]), R::mul(p[4], p[6]));
@@ -194,6 +209,53 @@ __device__ __forceinline__ bool load_tri(Tri<T> &t, const T *__restrict__ V, con
     return true;
 }
 
+// ---- per-vertex / per-triangle pre-pass (float path) -------------------------------------------------------------
+// A BFM-size mesh has 6 triangle corners per vertex and the resolve pass sets the winning triangle up once more per
+// pixel: the NDC -> pixel transform of a vertex used to run ~9 times per image.  The pre-pass runs it ONCE per (image,
+// vertex, raster size) with the same single-rounded operations (bit-identical coordinates) and narrows the triangle list
+// to int32 (-1 in the first slot = a corner outside [0, nv): skipped like reference op/rasterize.cpp:30-33), so the
+// triangle and resolve passes gather 12-byte ids and ready-made pixel coordinates.
+//   P [level][image or 1][nv][3] = (X, Y, z)      F32 [image or 1][nf][3]
+struct PreLevels { int n; int size[SR_RASTER_MAX_LEVELS]; };
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+raster_prepass_kernel(const RasterGeom g, const PreLevels L, const T *__restrict__ verts, const int64_t *__restrict__ tris,
+                      T *__restrict__ P, int32_t *__restrict__ F32, T eps)
+{
+    const int64_t nvert = (g.shared_v ? 1 : g.b) * g.nv, ntri = (g.shared_f ? 1 : g.b) * g.nf;
+    const int64_t stride = (int64_t)gridDim.x * kThreads, first = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    for (int64_t i = first; i < nvert; i += stride) {
+        const T x = __ldg(verts + 3 * i), y = __ldg(verts + 3 * i + 1), z = __ldg(verts + 3 * i + 2);
+        for (int l = 0; l < L.n; ++l) {
+            T q[3] = {x, y, z};
+            // reference passes (h, w) for (w, h): x spans h, y spans w (op/rasterize.cpp:38); square targets only
+            project_vertex<T>(q, L.size[l], L.size[l], g.perspective != 0, eps);
+            T *o = P + ((int64_t)l * nvert + i) * 3;
+            o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
+        }
+    }
+    for (int64_t i = first; i < ntri; i += stride) {
+        const int64_t a = __ldg(tris + 3 * i), b = __ldg(tris + 3 * i + 1), c = __ldg(tris + 3 * i + 2);
+        const bool ok = a >= 0 && b >= 0 && c >= 0 && a < g.nv && b < g.nv && c < g.nv;
+        F32[3 * i] = ok ? (int32_t)a : -1; F32[3 * i + 1] = ok ? (int32_t)b : 0; F32[3 * i + 2] = ok ? (int32_t)c : 0;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ bool load_tri_pre(Tri<T> &t, const T *__restrict__ P, const int32_t *__restrict__ F, int64_t f,
+                                             int32_t ids[3])
+{
+    ids[0] = __ldg(F + 3 * f); ids[1] = __ldg(F + 3 * f + 1); ids[2] = __ldg(F + 3 * f + 2);
+    if (ids[0] < 0) return false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const T *s = P + 3 * (int64_t)ids[k];
+        t.p[3 * k] = __ldg(s); t.p[3 * k + 1] = __ldg(s + 1); t.p[3 * k + 2] = __ldg(s + 2);
+    }
+    return true;
+}
+
 // PASS 0: float, packed (z, ~id) key.  PASS 1: double, max ordered z.  PASS 2: double, min id among z == zmax.
 template <typename T, int PASS>
 __device__ __forceinline__ void emit(const Tri<T> &t, int x, int y, uint32_t f, const RasterGeom &g, T eps,
@@ -250,7 +312,8 @@ __device__ __forceinline__ void cover_warp(const Tri<T> &t, bool live, uint32_t 
 template <typename T, int PASS>
 __global__ void __launch_bounds__(kThreads)
 raster_tri_kernel(const RasterGeom g, const T *__restrict__ verts, const int64_t *__restrict__ tris,
-                  uint64_t *__restrict__ zkeys, uint32_t *__restrict__ idkeys, T eps)
+                  uint64_t *__restrict__ zkeys, uint32_t *__restrict__ idkeys, T eps,
+                  const T *__restrict__ P = nullptr, const int32_t *__restrict__ F32 = nullptr)
 {
     const int64_t img = blockIdx.y;                      // one grid row per image
     const int64_t total = g.nf;
@@ -258,6 +321,8 @@ raster_tri_kernel(const RasterGeom g, const T *__restrict__ verts, const int64_t
     const uint32_t lane = threadIdx.x & 31u;
     const T *V = verts + (g.shared_v ? 0 : img * g.nv * 3);
     const int64_t *F = tris + (g.shared_f ? 0 : img * g.nf * 3);
+    const T *Pi = P ? P + (g.shared_v ? 0 : img * g.nv * 3) : nullptr;         // pre-pass products of this image
+    const int32_t *Fi = F32 ? F32 + (g.shared_f ? 0 : img * g.nf * 3) : nullptr;
     // warp-uniform trip count: every lane of a warp runs the same number of iterations
     for (int64_t base = (int64_t)blockIdx.x * kThreads + (threadIdx.x & ~31u); base < total; base += stride) {
         const int64_t item = base + lane;
@@ -265,10 +330,15 @@ raster_tri_kernel(const RasterGeom g, const T *__restrict__ verts, const int64_t
         bool live = item < total;
         const uint32_t f = (uint32_t)item;
         if (live) {
-            int64_t ids[3];
-            live = load_tri<T>(t, V, F, f, g.nv, ids);
-            // reference passes (h, w) for (w, h): x spans h, y spans w (op/rasterize.cpp:38)
-            if (live) live = tri_setup<T>(t, g.h, g.w, g.perspective != 0, eps);
+            if (Pi) {
+                int32_t ids[3];
+                live = load_tri_pre<T>(t, Pi, Fi, f, ids) && tri_setup<T, true>(t, g.h, g.w, g.perspective != 0, eps);
+            } else {
+                int64_t ids[3];
+                live = load_tri<T>(t, V, F, f, g.nv, ids);
+                // reference passes (h, w) for (w, h): x spans h, y spans w (op/rasterize.cpp:38)
+                if (live) live = tri_setup<T>(t, g.h, g.w, g.perspective != 0, eps);
+            }
         }
         cover_warp<T, PASS>(t, live, f, lane, g, eps, zkeys, idkeys, img);
     }
@@ -298,31 +368,40 @@ struct Pyramid {
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 raster_tri_pyramid_kernel(const RasterGeom g0, const Pyramid<T> L, const T *__restrict__ verts,
-                          const int64_t *__restrict__ tris, uint64_t *__restrict__ zkeys, T eps)
+                          const int64_t *__restrict__ tris, uint64_t *__restrict__ zkeys, T eps,
+                          const T *__restrict__ P, const int32_t *__restrict__ F32)
 {
     const int64_t img = blockIdx.y;
     const int64_t total = g0.nf;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     const uint32_t lane = threadIdx.x & 31u;
-    const T *V = verts + (g0.shared_v ? 0 : img * g0.nv * 3);
-    const int64_t *F = tris + (g0.shared_f ? 0 : img * g0.nf * 3);
+    const int64_t level_stride = (g0.shared_v ? 1 : g0.b) * g0.nv * 3;         // P: [level][image or 1][nv][3]
+    const T *Pi = P + (g0.shared_v ? 0 : img * g0.nv * 3);
+    const int32_t *Fi = F32 + (g0.shared_f ? 0 : img * g0.nf * 3);
     for (int64_t base = (int64_t)blockIdx.x * kThreads + (threadIdx.x & ~31u); base < total; base += stride) {
         const int64_t item = base + lane;
-        Tri<T> raw;
         bool loaded = item < total;
         const uint32_t f = (uint32_t)item;
+        int32_t ids[3] = {-1, 0, 0};
         if (loaded) {
-            int64_t ids[3];
-            loaded = load_tri<T>(raw, V, F, f, g0.nv, ids);
+            ids[0] = __ldg(Fi + 3 * item); ids[1] = __ldg(Fi + 3 * item + 1); ids[2] = __ldg(Fi + 3 * item + 2);
+            loaded = ids[0] >= 0;
         }
         if (!__any_sync(0xffffffffu, loaded)) continue;
         for (int l = 0; l < L.n; ++l) {                      // warp-uniform
             RasterGeom g = g0;
             g.h = g.w = L.size[l];
             Tri<T> t;
+            bool live = loaded;
+            if (live) {
+                const T *Pl = Pi + l * level_stride;
 #pragma unroll
-            for (int c = 0; c < 9; ++c) t.p[c] = raw.p[c];
-            const bool live = loaded && tri_setup<T>(t, g.h, g.w, g.perspective != 0, eps);
+                for (int k = 0; k < 3; ++k) {
+                    const T *s = Pl + 3 * (int64_t)ids[k];
+                    t.p[3 * k] = __ldg(s); t.p[3 * k + 1] = __ldg(s + 1); t.p[3 * k + 2] = __ldg(s + 2);
+                }
+                live = tri_setup<T, true>(t, g.h, g.w, g.perspective != 0, eps);
+            }
             cover_warp<T, 0>(t, live, f, lane, g, eps, zkeys + L.key_off[l], nullptr, img);
         }
     }
@@ -362,7 +441,8 @@ __device__ __forceinline__ void resolve_block(const RasterGeom &g, const T *__re
                                               const uint64_t *__restrict__ zkeys, const uint32_t *__restrict__ idkeys, T eps,
                                               int64_t *__restrict__ ids_out, T *__restrict__ bary_out,
                                               const T *__restrict__ tex, int c, T *__restrict__ out, int vec_ok,
-                                              int64_t blk, int64_t npix, ResolveStage<T> &st, bool planar = false)
+                                              int64_t blk, int64_t npix, ResolveStage<T> &st, bool planar = false,
+                                              const T *__restrict__ P = nullptr, const int32_t *__restrict__ F32 = nullptr)
 {
     // planar: the map leaves as [b, c, h, w] planes -- consecutive threads are consecutive pixels of one plane, so the
     // per-thread 4-byte stores coalesce by themselves; ids_out / bary_out may then be NULL (forward-only callers: the mesh
@@ -387,8 +467,16 @@ __device__ __forceinline__ void resolve_block(const RasterGeom &g, const T *__re
             const int64_t *F = tris + (g.shared_f ? 0 : img * g.nf * 3);
             Tri<T> t;
             T z;
-            hit = load_tri<T>(t, V, F, f, g.nv, ids) && tri_setup<T>(t, g.h, g.w, g.perspective != 0, eps) &&
-                  tri_sample<T>(t, (T)x, (T)y, g.perspective != 0, eps, w, z);
+            if (P) {             // pre-projected corners, no pixel box needed: the edge matrix and the sample only
+                int32_t i32[3];
+                hit = load_tri_pre<T>(t, P + (g.shared_v ? 0 : img * g.nv * 3), F32 + (g.shared_f ? 0 : img * g.nf * 3), f, i32) &&
+                      tri_setup<T, true, false>(t, g.h, g.w, g.perspective != 0, eps) &&
+                      tri_sample<T>(t, (T)x, (T)y, g.perspective != 0, eps, w, z);
+                ids[0] = i32[0]; ids[1] = i32[1]; ids[2] = i32[2];
+            } else {
+                hit = load_tri<T>(t, V, F, f, g.nv, ids) && tri_setup<T>(t, g.h, g.w, g.perspective != 0, eps) &&
+                      tri_sample<T>(t, (T)x, (T)y, g.perspective != 0, eps, w, z);
+            }
             if (hit && !g.shared_v) { ids[0] += g.nv * img; ids[1] += g.nv * img; ids[2] += g.nv * img; }
             if (!hit) { ids[0] = ids[1] = ids[2] = 0; w[0] = w[1] = w[2] = 0; }
         }
@@ -417,21 +505,25 @@ __global__ void __launch_bounds__(kThreads)
 raster_resolve_kernel(const RasterGeom g, const T *__restrict__ verts, const int64_t *__restrict__ tris,
                       const uint64_t *__restrict__ zkeys, const uint32_t *__restrict__ idkeys, T eps,
                       int64_t *__restrict__ ids_out, T *__restrict__ bary_out,
-                      const T *__restrict__ tex, int c, T *__restrict__ out, int vec_ok)
+                      const T *__restrict__ tex, int c, T *__restrict__ out, int vec_ok,
+                      const T *__restrict__ P = nullptr, const int32_t *__restrict__ F32 = nullptr)
 {
     __shared__ __align__(16) ResolveStage<T> st;
     const int64_t npix = g.b * g.h * (int64_t)g.w;
     const int64_t nblk = (npix + kThreads - 1) / kThreads;
     for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x)
-        resolve_block<T, PACKED>(g, verts, tris, zkeys, idkeys, eps, ids_out, bary_out, tex, c, out, vec_ok, blk, npix, st);
+        resolve_block<T, PACKED>(g, verts, tris, zkeys, idkeys, eps, ids_out, bary_out, tex, c, out, vec_ok, blk, npix, st,
+                                 false, P, F32);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 raster_resolve_pyramid_kernel(const RasterGeom g0, const Pyramid<T> L, const T *__restrict__ verts,
                               const int64_t *__restrict__ tris, const uint64_t *__restrict__ zkeys, T eps,
-                              const T *__restrict__ tex, int c, int vec_ok)
+                              const T *__restrict__ tex, int c, int vec_ok, const T *__restrict__ P,
+                              const int32_t *__restrict__ F32)
 {
+    const int64_t level_stride = (g0.shared_v ? 1 : g0.b) * g0.nv * 3;
     __shared__ __align__(16) ResolveStage<T> st;
     const int64_t nblk = L.blk_off[L.n];
     for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
@@ -441,7 +533,7 @@ raster_resolve_pyramid_kernel(const RasterGeom g0, const Pyramid<T> L, const T *
         g.h = g.w = L.size[l];
         const int64_t npix = g.b * g.h * (int64_t)g.w;
         resolve_block<T, true>(g, verts, tris, zkeys + L.key_off[l], nullptr, eps, L.ids[l], L.bary[l], tex, c, L.out[l],
-                               vec_ok, blk - L.blk_off[l], npix, st, L.planar != 0);
+                               vec_ok, blk - L.blk_off[l], npix, st, L.planar != 0, P + l * level_stride, F32);
     }
 }
 
@@ -602,6 +694,13 @@ raster_backward_pyramid_kernel(int64_t b, int64_t n, const Pyramid<T> L, int c, 
     }
 }
 
+// Workspace of the float path: [keys: npix u64][P: levels x b x nv x 3 floats, 16-byte aligned][F32: b x nf x 3 int32]
+// (sized for per-image vertex / triangle lists; shared ones use the first image's slice).
+inline int64_t align16(int64_t v) { return (v + 15) & ~(int64_t)15; }
+inline int64_t pre_bytes(int64_t b, int64_t nv, int64_t nf, int n_levels) {
+    return align16(b * nv * 3 * 4 * n_levels) + align16(b * nf * 3 * 4);
+}
+
 int grid_for(int64_t items, int per_sm) {
     int64_t blocks = (items + kThreads - 1) / kThreads;
     const int64_t cap = (int64_t)kNumSMs * per_sm;
@@ -630,6 +729,13 @@ int rasterize_forward(int64_t b, int64_t nv, int64_t nf, int64_t h, int64_t w, i
     g.shared_v = shared_v; g.shared_f = shared_f; g.perspective = perspective;
     if (eps < 0) eps = -eps;
     uint32_t *idkeys = reinterpret_cast<uint32_t *>(keys + npix);
+    // float path: per-vertex / per-triangle pre-pass products behind the keys (see raster_prepass_kernel)
+    T *P = nullptr;
+    int32_t *F32 = nullptr;
+    if (kF32 && nf > 0 && verts && tris) {
+        P = reinterpret_cast<T *>(reinterpret_cast<char *>(keys) + align16(npix * 8));
+        F32 = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(P) + align16(b * nv * 3 * 4));
+    }
     cudaError_t e = cudaMemsetAsync(keys, 0, sizeof(uint64_t) * (size_t)npix, st);
     if (e == cudaSuccess && !kF32) e = cudaMemsetAsync(idkeys, 0xff, sizeof(uint32_t) * (size_t)npix, st);
     if (e != cudaSuccess) { set_error("rasterize: memset: %s", cudaGetErrorString(e)); return (int)e; }
@@ -640,8 +746,12 @@ int rasterize_forward(int64_t b, int64_t nv, int64_t nf, int64_t h, int64_t w, i
         if (gx > per_img) gx = per_img < 1 ? 1 : per_img;
         const dim3 grid((unsigned)gx, (unsigned)b);
         if constexpr (kF32) {
-            raster_tri_kernel<T, 0><<<grid, kThreads, 0, st>>>(g, verts, tris, keys, idkeys, eps);
-            count_launch();
+            PreLevels pl;
+            pl.n = 1; pl.size[0] = (int)h;
+            const int64_t items = ((shared_v ? 1 : b) * nv > (shared_f ? 1 : b) * nf) ? (shared_v ? 1 : b) * nv : (shared_f ? 1 : b) * nf;
+            raster_prepass_kernel<T><<<grid_for(items, 8), kThreads, 0, st>>>(g, pl, verts, tris, P, F32, eps);
+            raster_tri_kernel<T, 0><<<grid, kThreads, 0, st>>>(g, verts, tris, keys, idkeys, eps, P, F32);
+            count_launch(2);
         } else {
             raster_tri_kernel<T, 1><<<grid, kThreads, 0, st>>>(g, verts, tris, keys, idkeys, eps);
             raster_tri_kernel<T, 2><<<grid, kThreads, 0, st>>>(g, verts, tris, keys, idkeys, eps);
@@ -651,7 +761,7 @@ int rasterize_forward(int64_t b, int64_t nv, int64_t nf, int64_t h, int64_t w, i
     const int vec_ok = ((reinterpret_cast<uintptr_t>(ids) | reinterpret_cast<uintptr_t>(bary) |
                          reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
     raster_resolve_kernel<T, kF32><<<grid_for(npix, 8), kThreads, 0, st>>>(g, verts, tris, keys, idkeys, eps, ids, bary,
-                                                                          tex, (int)c, out, vec_ok);
+                                                                          tex, (int)c, out, vec_ok, P, F32);
     count_launch();
     return check_launch("sr_rasterize_forward");
 }
@@ -740,18 +850,25 @@ int rasterize_pyramid_forward(int64_t b, int64_t nv, int64_t nf, int n_levels, c
     const int64_t nkeys = L.key_off[L.n - 1] + b * (int64_t)L.size[L.n - 1] * L.size[L.n - 1];
     cudaError_t e = cudaMemsetAsync(keys, 0, sizeof(uint64_t) * (size_t)nkeys, st);
     if (e != cudaSuccess) { set_error("rasterize_pyramid: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    float *P = reinterpret_cast<float *>(reinterpret_cast<char *>(keys) + align16(nkeys * 8));
+    int32_t *F32 = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(P) + align16(b * nv * 3 * 4 * (int64_t)L.n));
     if (nf > 0 && verts && tris) {
         SR_REQUIRE(b <= 65535, "rasterize_pyramid: batch too large for one launch");
+        PreLevels pl;
+        pl.n = L.n;
+        for (int l = 0; l < L.n; ++l) pl.size[l] = L.size[l];
+        const int64_t nvert = (shared_v ? 1 : b) * nv, ntri = (shared_f ? 1 : b) * nf;
+        raster_prepass_kernel<float><<<grid_for(nvert > ntri ? nvert : ntri, 8), kThreads, 0, st>>>(g, pl, verts, tris, P, F32, eps);
         int gx = grid_for(nf, 16);
         const int per_img = (int)((int64_t)kNumSMs * 16 / b);
         if (gx > per_img) gx = per_img < 1 ? 1 : per_img;
-        raster_tri_pyramid_kernel<float><<<dim3((unsigned)gx, (unsigned)b), kThreads, 0, st>>>(g, L, verts, tris, keys, eps);
-        count_launch();
+        raster_tri_pyramid_kernel<float><<<dim3((unsigned)gx, (unsigned)b), kThreads, 0, st>>>(g, L, verts, tris, keys, eps, P, F32);
+        count_launch(2);
     }
     const int64_t nblk = L.blk_off[L.n];
     const int64_t cap = (int64_t)kNumSMs * 8;
     raster_resolve_pyramid_kernel<float><<<(unsigned)(nblk < cap ? nblk : cap), kThreads, 0, st>>>(
-        g, L, verts, tris, keys, eps, tex, (int)c, vec_ok ? 1 : 0);
+        g, L, verts, tris, keys, eps, tex, (int)c, vec_ok ? 1 : 0, P, F32);
     count_launch();
     return check_launch("sr_rasterize_pyramid_forward_f32");
 }
@@ -780,10 +897,10 @@ int rasterize_pyramid_backward(int64_t b, int64_t n, int n_levels, const sr_rast
 
 using namespace sr;
 
-extern "C" int64_t sr_rasterize_pyramid_workspace_bytes(int64_t b, int n_levels, const int64_t *sizes) {
+extern "C" int64_t sr_rasterize_pyramid_workspace_bytes(int64_t b, int64_t nv, int64_t nf, int n_levels, const int64_t *sizes) {
     int64_t npix = 0;
     for (int i = 0; i < n_levels; ++i) npix += b * sizes[i] * sizes[i];
-    return npix * 8 + 16;
+    return align16(npix * 8) + pre_bytes(b, nv, nf, n_levels) + 16;
 }
 extern "C" int sr_rasterize_pyramid_forward_f32(int64_t b, int64_t nv, int64_t nf, int n_levels,
                                                 const sr_raster_level *levels, int shared_v, int shared_f, int perspective,
@@ -805,9 +922,9 @@ extern "C" int sr_rasterize_pyramid_backward_f32(int64_t b, int64_t n, int n_lev
     return rasterize_pyramid_backward(b, n, n_levels, levels, c, perspective, verts, tex, grad_verts, grad_tex, eps, stream);
 }
 
-extern "C" int64_t sr_rasterize_workspace_bytes(int64_t b, int64_t h, int64_t w, int is_f64) {
+extern "C" int64_t sr_rasterize_workspace_bytes(int64_t b, int64_t nv, int64_t nf, int64_t h, int64_t w, int is_f64) {
     const int64_t npix = b * h * w;
-    return npix * 8 + (is_f64 ? npix * 4 : 0) + 16;
+    return align16(npix * 8) + (is_f64 ? npix * 4 : pre_bytes(b, nv, nf, 1)) + 16;
 }
 
 extern "C" int sr_rasterize_forward_f32(int64_t b, int64_t nv, int64_t nf, int64_t h, int64_t w, int shared_v,

@@ -59,6 +59,7 @@ struct PrologueParams {
     // affine, which is what the forward kernels store for these blocks -- and the activated output is rebuilt here.  The
     // gradient handed to the GEMMs is gp * map0 (* d), e = sum gp * (conv_d * map0), and per pixel
     //   g_map1 = sum_c gp,   g_map0 = sum_c gp * conv_d          (no division: map0 may be exactly 0).
+    int ga_bf16;                  // ga is a bfloat16 tensor (the 16-bit operand of the dgrad / wgrad GEMMs; only with d)
     const float *stylemap;        // [B, 2, pixels] planes (batch stride map_bstride, plane stride = pixels) or nullptr
     long long map_bstride;
     float *g_map;                 // [B, 2, pixels] contiguous, += (zeroed by the caller)
@@ -193,8 +194,15 @@ styled_bwd_prologue_kernel(const PrologueParams p)
                 f4_fma(a_e, gp, uu);
             }
             float4 o = f4_mul(gp, dd);
-            if (has_d) o = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
-            ga[(long long)px * C4] = o;
+            if (has_d && p.ga_bf16) {
+                uint32_t lo, hi;
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(o.y), "f"(o.x));
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(o.w), "f"(o.z));
+                reinterpret_cast<uint2 *>(p.ga)[((long long)b * p.pixels + px) * C4 + c4] = make_uint2(lo, hi);
+            } else {
+                if (has_d) o = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
+                ga[(long long)px * C4] = o;
+            }
         }
     }
     block_reduce_quads(a_bias, s_red, c4, pl, C4, lanes_p, p.g_bias);
@@ -272,13 +280,13 @@ bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 using namespace sr;
 
-extern "C" int sr_styled_bwd_prologue3_f32(float *ga, float *g_bias, float *g_noise_w, float *e, float *ds_next,
-                                           float *d_rgb_weight, const float *gy, const float *gxs, const float *s_next,
-                                           const float *g_rgb, const float *rgb_weight, const float *y, const float *noise,
-                                           int64_t noise_batch_stride, const float *noise_weight, const float *bias,
-                                           const float *d, int64_t batch, int64_t pixels, int64_t channels, float alpha,
-                                           float gain, const float *stylemap, int64_t stylemap_batch_stride, float *g_stylemap,
-                                           void *stream)
+static int styled_bwd_prologue_any(float *ga, float *g_bias, float *g_noise_w, float *e, float *ds_next,
+                                   float *d_rgb_weight, const float *gy, const float *gxs, const float *s_next,
+                                   const float *g_rgb, const float *rgb_weight, const float *y, const float *noise,
+                                   int64_t noise_batch_stride, const float *noise_weight, const float *bias,
+                                   const float *d, int64_t batch, int64_t pixels, int64_t channels, float alpha,
+                                   float gain, const float *stylemap, int64_t stylemap_batch_stride, float *g_stylemap,
+                                   void *stream, int ga_bf16)
 {
     SR_REQUIRE(!stylemap || g_stylemap, "styled_bwd_prologue: stylemap needs g_stylemap");
     SR_REQUIRE(!stylemap || (channels / 4 >= 32 || ((channels / 4) & (channels / 4 - 1)) == 0),
@@ -308,6 +316,7 @@ extern "C" int sr_styled_bwd_prologue3_f32(float *ga, float *g_bias, float *g_no
     p.chunks_per_image = pick_chunks(batch, pixels, p.C4, &p.pix_per_chunk);
     p.alpha = alpha; p.gain = gain;
     p.stylemap = stylemap; p.map_bstride = stylemap_batch_stride; p.g_map = g_stylemap;
+    p.ga_bf16 = (ga_bf16 && d) ? 1 : 0;
     const unsigned nb = (unsigned)(batch * p.chunks_per_image);
     // kernels specialised on the inputs present (see styled_bwd_prologue_kernel); SR_PROLOGUE_SPEC=0: run-time checks only
     static const char *spec_env = getenv("SR_PROLOGUE_SPEC");
@@ -338,6 +347,33 @@ extern "C" int sr_styled_bwd_prologue3_f32(float *ga, float *g_bias, float *g_no
     }
     count_launch();
     return check_launch("sr_styled_bwd_prologue_f32");
+}
+
+extern "C" int sr_styled_bwd_prologue3_f32(float *ga, float *g_bias, float *g_noise_w, float *e, float *ds_next,
+                                           float *d_rgb_weight, const float *gy, const float *gxs, const float *s_next,
+                                           const float *g_rgb, const float *rgb_weight, const float *y, const float *noise,
+                                           int64_t noise_batch_stride, const float *noise_weight, const float *bias,
+                                           const float *d, int64_t batch, int64_t pixels, int64_t channels, float alpha,
+                                           float gain, const float *stylemap, int64_t stylemap_batch_stride, float *g_stylemap,
+                                           void *stream)
+{
+    return styled_bwd_prologue_any(ga, g_bias, g_noise_w, e, ds_next, d_rgb_weight, gy, gxs, s_next, g_rgb, rgb_weight, y, noise,
+                                   noise_batch_stride, noise_weight, bias, d, batch, pixels, channels, alpha, gain, stylemap,
+                                   stylemap_batch_stride, g_stylemap, stream, 0);
+}
+// bf16 operand form: with d != NULL, ga is a bfloat16 tensor (the GEMM operand); with d == NULL it stays fp32 (it then feeds
+// the backward FIR, sr_blur_nhwc_scaledot_bf16).
+extern "C" int sr_styled_bwd_prologue3_bf16(void *ga, float *g_bias, float *g_noise_w, float *e, float *ds_next,
+                                            float *d_rgb_weight, const float *gy, const float *gxs, const float *s_next,
+                                            const float *g_rgb, const float *rgb_weight, const float *y, const float *noise,
+                                            int64_t noise_batch_stride, const float *noise_weight, const float *bias,
+                                            const float *d, int64_t batch, int64_t pixels, int64_t channels, float alpha,
+                                            float gain, const float *stylemap, int64_t stylemap_batch_stride,
+                                            float *g_stylemap, void *stream)
+{
+    return styled_bwd_prologue_any(reinterpret_cast<float *>(ga), g_bias, g_noise_w, e, ds_next, d_rgb_weight, gy, gxs, s_next,
+                                   g_rgb, rgb_weight, y, noise, noise_batch_stride, noise_weight, bias, d, batch, pixels, channels,
+                                   alpha, gain, stylemap, stylemap_batch_stride, g_stylemap, stream, 1);
 }
 
 extern "C" int sr_styled_bwd_prologue2_f32(float *ga, float *g_bias, float *g_noise_w, float *e, float *ds_next,

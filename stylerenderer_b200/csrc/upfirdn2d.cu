@@ -488,7 +488,15 @@ struct NhwcGeom {
     // `out` then receives acc (what the backward needs; map0 may be exactly 0) and only out2 sees y
     const float *stylemap;        // [B, 2, out_h, out_w] planes (batch stride map_bstride) or nullptr
     long long map_bstride;
+    int op16;                     // the GEMM operand this pass produces (STYLED: out2, SCALEDOT: out) is a bfloat16 tensor
 };
+
+__device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
+    uint2 r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.x) : "f"(b), "f"(a));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.y) : "f"(d), "f"(c));
+    return r;
+}
 
 template <int KH, int KW, int MODE>     // MODE 0: plain, 1: STYLED forward tail, 2: SCALEDOT backward tail
 __global__ void __launch_bounds__(kThreads, 2)      // <= 128 registers: two CTAs per SM keep enough loads in flight
@@ -585,26 +593,39 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
                 if (ox0 + j >= g.out_w) break;
                 dot.x = fmaf(acc[j].x, tt[j].x, dot.x); dot.y = fmaf(acc[j].y, tt[j].y, dot.y);
                 dot.z = fmaf(acc[j].z, tt[j].z, dot.z); dot.w = fmaf(acc[j].w, tt[j].w, dot.w);
-                acc[j].x = round_tf32_(acc[j].x * sc2.x); acc[j].y = round_tf32_(acc[j].y * sc2.y);
-                acc[j].z = round_tf32_(acc[j].z * sc2.z); acc[j].w = round_tf32_(acc[j].w * sc2.w);
+                acc[j].x = acc[j].x * sc2.x; acc[j].y = acc[j].y * sc2.y; acc[j].z = acc[j].z * sc2.z; acc[j].w = acc[j].w * sc2.w;
+                if (!g.op16) {
+                    acc[j].x = round_tf32_(acc[j].x); acc[j].y = round_tf32_(acc[j].y);
+                    acc[j].z = round_tf32_(acc[j].z); acc[j].w = round_tf32_(acc[j].w);
+                }
             }
         }
-        float4 *dst = yout + ((int64_t)oy * g.out_w + ox0) * g.c4;
-        const bool keep_pre = STYLED && g.stylemap;
-        dst[0] = keep_pre ? pre[0] : acc[0];
-        if (ox0 + 1 < g.out_w) dst[g.c4] = keep_pre ? pre[1] : acc[1];
+        const int64_t opix = (int64_t)n * g.out_h * g.out_w * g.c4 + c + ((int64_t)oy * g.out_w + ox0) * g.c4;   // in channel quads
+        if (MODE == 2 && g.op16) {                         // the scaled gradient leaves as a bfloat16 operand
+            uint2 *d16 = reinterpret_cast<uint2 *>(out) + opix;
+            d16[0] = pack4_bf16(acc[0].x, acc[0].y, acc[0].z, acc[0].w);
+            if (ox0 + 1 < g.out_w) d16[g.c4] = pack4_bf16(acc[1].x, acc[1].y, acc[1].z, acc[1].w);
+        } else {
+            float4 *dst = yout + ((int64_t)oy * g.out_w + ox0) * g.c4;
+            const bool keep_pre = STYLED && g.stylemap;
+            dst[0] = keep_pre ? pre[0] : acc[0];
+            if (ox0 + 1 < g.out_w) dst[g.c4] = keep_pre ? pre[1] : acc[1];
+        }
         if (STYLED && g.out2) {
-            float4 *dst2 = reinterpret_cast<float4 *>(g.out2) + (int64_t)n * g.out_h * g.out_w * g.c4 + c +
-                           ((int64_t)oy * g.out_w + ox0) * g.c4;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 if (ox0 + j >= g.out_w) break;
-                float4 o;
-                o.x = round_tf32_(acc[j].x * sc2.x);
-                o.y = round_tf32_(acc[j].y * sc2.y);
-                o.z = round_tf32_(acc[j].z * sc2.z);
-                o.w = round_tf32_(acc[j].w * sc2.w);
-                dst2[(int64_t)j * g.c4] = o;
+                if (g.op16) {
+                    reinterpret_cast<uint2 *>(g.out2)[opix + (int64_t)j * g.c4] =
+                        pack4_bf16(acc[j].x * sc2.x, acc[j].y * sc2.y, acc[j].z * sc2.z, acc[j].w * sc2.w);
+                } else {
+                    float4 o;
+                    o.x = round_tf32_(acc[j].x * sc2.x);
+                    o.y = round_tf32_(acc[j].y * sc2.y);
+                    o.z = round_tf32_(acc[j].z * sc2.z);
+                    o.w = round_tf32_(acc[j].w * sc2.w);
+                    reinterpret_cast<float4 *>(g.out2)[opix + (int64_t)j * g.c4] = o;
+                }
             }
         }
 #pragma unroll
@@ -1161,9 +1182,9 @@ int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, in
                 int64_t minor, int pad_x0, int pad_y0, bool styled, const float *noise, long long noise_bstride,
                 const float *noise_weight, const float *bias, float alpha, float gain, cudaStream_t st,
                 float *out2 = nullptr, const float *scale2 = nullptr, const float *other = nullptr, float *dot = nullptr,
-                const float *stylemap = nullptr, long long map_bstride = 0)
+                const float *stylemap = nullptr, long long map_bstride = 0, int op16 = 0)
 {
-    if (pad_x0 == pad_y0 && !stylemap) {
+    if (pad_x0 == pad_y0 && !stylemap && !op16) {
         const int rc = (!dot && !styled && scale2) ? SR_ERR_UNSUPPORTED :
                        launch_nhwc_tma(out, x, taps, major, in_h, in_w, oh, ow, minor, pad_x0, dot ? 2 : (styled ? 1 : 0), noise,
                                        noise_bstride, noise_weight, bias, alpha, gain, st, out2, scale2, other, dot);
@@ -1171,7 +1192,7 @@ int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, in
     }
     NhwcGeom g;
     g.out2 = out2; g.scale2 = scale2; g.other = other; g.dot = dot;
-    g.stylemap = stylemap; g.map_bstride = map_bstride;
+    g.stylemap = stylemap; g.map_bstride = map_bstride; g.op16 = op16;
     g.major = major; g.in_h = in_h; g.in_w = in_w; g.out_h = oh; g.out_w = ow;
     g.c4 = (int)(minor / 4); g.pad_x0 = pad_x0; g.pad_y0 = pad_y0;
     g.rows_per_strip = oh >= 64 ? 16 : (oh >= 16 ? 8 : 4);
@@ -1187,7 +1208,7 @@ int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, in
     // 1-5 = row-streaming ring kernels with (rows in flight, threads per CTA, CTAs per SM) = (2,256,2) (3,128,3) (3,256,1)
     // (4,128,2) (1,256,2)
     const char *ring_env = getenv("SR_FIR_RING");
-    const int ring = (ring_env && ring_env[0] >= '0' && ring_env[0] <= '5') ? ring_env[0] - '0' : 0;
+    const int ring = (ring_env && ring_env[0] >= '0' && ring_env[0] <= '5' && !op16) ? ring_env[0] - '0' : 0;
     const int mode = (dot || (!styled && scale2)) ? 2 : (styled ? 1 : 0);
 #define SR_RING(D, NT, MINB)                                                                                           \
     do {                                                                                                               \
@@ -1215,11 +1236,11 @@ int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, in
 
 using namespace sr;
 
-extern "C" int sr_blur_nhwc_styled3_f32(float *out, float *out2, const float *scale2, const float *x, const float *taps,
-                                        int64_t batch, int64_t in_h, int64_t in_w, int64_t channels, int pad0, int pad1,
-                                        const float *noise, int64_t noise_batch_stride, const float *noise_weight,
-                                        const float *bias, float alpha, float gain, const float *stylemap,
-                                        int64_t stylemap_batch_stride, void *stream)
+static int blur_nhwc_styled_any(float *out, float *out2, const float *scale2, const float *x, const float *taps,
+                                int64_t batch, int64_t in_h, int64_t in_w, int64_t channels, int pad0, int pad1,
+                                const float *noise, int64_t noise_batch_stride, const float *noise_weight,
+                                const float *bias, float alpha, float gain, const float *stylemap,
+                                int64_t stylemap_batch_stride, void *stream, int op16)
 {
     SR_REQUIRE(out && x && taps, "blur_nhwc_styled: null pointer");
     SR_REQUIRE(channels >= 4 && channels % 4 == 0, "blur_nhwc_styled: channels must be a multiple of 4");
@@ -1233,10 +1254,30 @@ extern "C" int sr_blur_nhwc_styled3_f32(float *out, float *out2, const float *sc
     if (batch == 0) return SR_OK;
     int rc = launch_nhwc(out, x, taps, batch, (int)in_h, (int)in_w, (int)oh, (int)ow, channels, pad0, pad0, true, noise,
                          noise_batch_stride, noise_weight, bias, alpha, gain, (cudaStream_t)stream, out2, scale2, nullptr, nullptr,
-                         stylemap, stylemap_batch_stride);
+                         stylemap, stylemap_batch_stride, op16);
     if (rc != SR_OK) { set_error("blur_nhwc_styled: problem too large"); return rc; }
     count_launch();
     return check_launch("sr_blur_nhwc_styled_f32");
+}
+
+extern "C" int sr_blur_nhwc_styled3_f32(float *out, float *out2, const float *scale2, const float *x, const float *taps,
+                                        int64_t batch, int64_t in_h, int64_t in_w, int64_t channels, int pad0, int pad1,
+                                        const float *noise, int64_t noise_batch_stride, const float *noise_weight,
+                                        const float *bias, float alpha, float gain, const float *stylemap,
+                                        int64_t stylemap_batch_stride, void *stream)
+{
+    return blur_nhwc_styled_any(out, out2, scale2, x, taps, batch, in_h, in_w, channels, pad0, pad1, noise, noise_batch_stride,
+                                noise_weight, bias, alpha, gain, stylemap, stylemap_batch_stride, stream, 0);
+}
+// out2 is a bfloat16 tensor (the next layer's 16-bit GEMM operand); everything else as sr_blur_nhwc_styled3_f32
+extern "C" int sr_blur_nhwc_styled3_bf16(float *out, void *out2, const float *scale2, const float *x, const float *taps,
+                                         int64_t batch, int64_t in_h, int64_t in_w, int64_t channels, int pad0, int pad1,
+                                         const float *noise, int64_t noise_batch_stride, const float *noise_weight,
+                                         const float *bias, float alpha, float gain, const float *stylemap,
+                                         int64_t stylemap_batch_stride, void *stream)
+{
+    return blur_nhwc_styled_any(out, reinterpret_cast<float *>(out2), scale2, x, taps, batch, in_h, in_w, channels, pad0, pad1, noise,
+                                noise_batch_stride, noise_weight, bias, alpha, gain, stylemap, stylemap_batch_stride, stream, 1);
 }
 
 extern "C" int sr_blur_nhwc_styled2_f32(float *out, float *out2, const float *scale2, const float *x, const float *taps,
@@ -1248,9 +1289,9 @@ extern "C" int sr_blur_nhwc_styled2_f32(float *out, float *out2, const float *sc
                                     noise_batch_stride, noise_weight, bias, alpha, gain, nullptr, 0, stream);
 }
 
-extern "C" int sr_blur_nhwc_scaledot_f32(float *out, float *dot, const float *x, const float *taps, const float *scale,
-                                         const float *other, int64_t batch, int64_t in_h, int64_t in_w, int64_t channels,
-                                         int pad0, int pad1, void *stream)
+static int blur_nhwc_scaledot_any(float *out, float *dot, const float *x, const float *taps, const float *scale,
+                                  const float *other, int64_t batch, int64_t in_h, int64_t in_w, int64_t channels,
+                                  int pad0, int pad1, void *stream, int op16)
 {
     SR_REQUIRE(out && x && taps && scale, "blur_nhwc_scaledot: null pointer");
     SR_REQUIRE((dot == nullptr) == (other == nullptr), "blur_nhwc_scaledot: dot and other go together (both NULL = scale only)");
@@ -1266,10 +1307,25 @@ extern "C" int sr_blur_nhwc_scaledot_f32(float *out, float *dot, const float *x,
     }
     if (batch == 0) return SR_OK;
     int rc = launch_nhwc(out, x, taps, batch, (int)in_h, (int)in_w, (int)oh, (int)ow, channels, pad0, pad0, false, nullptr, 0,
-                         nullptr, nullptr, 0.f, 1.f, (cudaStream_t)stream, nullptr, scale, other, dot);
+                         nullptr, nullptr, 0.f, 1.f, (cudaStream_t)stream, nullptr, scale, other, dot, nullptr, 0, op16);
     if (rc != SR_OK) { set_error("blur_nhwc_scaledot: problem too large"); return rc; }
     count_launch();
     return check_launch("sr_blur_nhwc_scaledot_f32");
+}
+
+extern "C" int sr_blur_nhwc_scaledot_f32(float *out, float *dot, const float *x, const float *taps, const float *scale,
+                                         const float *other, int64_t batch, int64_t in_h, int64_t in_w, int64_t channels,
+                                         int pad0, int pad1, void *stream)
+{
+    return blur_nhwc_scaledot_any(out, dot, x, taps, scale, other, batch, in_h, in_w, channels, pad0, pad1, stream, 0);
+}
+// out is a bfloat16 tensor (the 16-bit operand of the dgrad / wgrad GEMMs)
+extern "C" int sr_blur_nhwc_scaledot_bf16(void *out, float *dot, const float *x, const float *taps, const float *scale,
+                                          const float *other, int64_t batch, int64_t in_h, int64_t in_w, int64_t channels,
+                                          int pad0, int pad1, void *stream)
+{
+    return blur_nhwc_scaledot_any(reinterpret_cast<float *>(out), dot, x, taps, scale, other, batch, in_h, in_w, channels, pad0,
+                                  pad1, stream, 1);
 }
 
 extern "C" int sr_blur_nhwc_styled_f32(float *out, const float *x, const float *taps, int64_t batch, int64_t in_h,

@@ -28,6 +28,15 @@ def _mode_operand(ctx, t):
     return t
 
 
+def _proxy(op_nhwc):
+    """bf16 operand mode: the GEMM operand a block hands to the next one is a bfloat16 tensor, but the gradient that comes
+    back for it (the next block's dgrad output) is fp32 -- autograd would cast a gradient to the dtype of the tensor it
+    belongs to.  So the autograd edge is carried by this zero-storage fp32 stand-in of the operand's logical [N,C,H,W]
+    shape, and the bfloat16 data travels beside it as a non-differentiable output."""
+    b, h, w, c = op_nhwc.shape
+    return op_nhwc.new_zeros(1, dtype=torch.float32).expand(b, c, h, w)
+
+
 def to_nhwc(x):
     """logical [N,C,H,W] -> contiguous [N,H,W,C] (a free view when x is channels_last)."""
     return x.permute(0, 2, 3, 1).contiguous()
@@ -410,11 +419,15 @@ class ModulateTC(Function):
         x_nhwc = to_nhwc(x)
         s = s.contiguous()
         ctx.save_for_backward(x_nhwc, s)
-        return from_nhwc(tc.modulate(x_nhwc, s))
+        xs = tc.modulate(x_nhwc, s)
+        if xs.dtype != torch.float32:                    # bf16 operand mode: (fp32 stand-in for autograd, operand data)
+            ctx.mark_non_differentiable(xs)
+            return _proxy(xs), xs
+        return from_nhwc(xs), None
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, gxs):
+    def backward(ctx, gxs, _g_op=None):
         x_nhwc, s = ctx.saved_tensors
         gx, gs = tc.scale_dot(to_nhwc(gxs), x_nhwc, s, False)
         return from_nhwc(gx), gs
@@ -427,9 +440,10 @@ class StyledLayerTC(Function):
 
     @staticmethod
     def forward(ctx, xs, weight, d, noise, noise_weight, act_bias, s_next, rgb_weight, scale, upsample, blur_taps, alpha,
-                gain, wk=None, wkt=None, stylemap=None):
+                gain, wk=None, wkt=None, stylemap=None, xs_op=None):
         ctx.set_materialize_grads(False)                     # unused outputs arrive as None, not as zero tensors
-        xs_nhwc = to_nhwc(xs)
+        # xs_op: the bfloat16 operand [B,H,W,C] in bf16 operand mode (xs is then its fp32 stand-in, see _proxy)
+        xs_nhwc = xs_op if xs_op is not None else to_nhwc(xs)
         b, h, w, cin = xs_nhwc.shape
         cout = weight.shape[1]
         d = d.contiguous()
@@ -441,7 +455,7 @@ class StyledLayerTC(Function):
         t = rgb = y2 = None
         if not upsample:
             y = torch.empty(b, h, w, cout, dtype=torch.float32, device=xs.device)
-            y2 = torch.empty_like(y) if s_next is not None else None
+            y2 = tc.operand_like(y) if s_next is not None else None
             rgb = torch.empty(b, h, w, 3, dtype=torch.float32, device=xs.device) if rgb_weight is not None else None
             # StyledMapConv: `y` receives the demodulated conv output before the map affine (epilogue 2); the backward
             # prologue rebuilds the activated value from it -- a map that is exactly 0 (background of the rasterised
@@ -460,19 +474,23 @@ class StyledLayerTC(Function):
         ctx.save_for_backward(xs_nhwc, y, None, weight, d, noise, noise_weight, act_bias, blur_taps, s_next, rgb_weight, stylemap)
         ctx.cfg = (scale, upsample, alpha, gain)
         ctx.exact_fwd = tc._exact()
+        op_out = None
         if s_next is None and stylemap is not None:          # y holds the pre-map value: no activated output to hand on
             main = xs.new_zeros(1)
             ctx.mark_non_differentiable(main)
+        elif s_next is not None and y2.dtype != torch.float32:
+            main, op_out = _proxy(y2), y2                    # bf16 operand mode
+            ctx.mark_non_differentiable(op_out)
         else:
             main = from_nhwc(y2 if s_next is not None else y)
         if rgb is None:
             rgb = xs.new_zeros(1)
             ctx.mark_non_differentiable(rgb)
-        return main, rgb
+        return main, rgb, op_out
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, g_main, g_rgb):
+    def backward(ctx, g_main, g_rgb, _g_op=None):
         xs, y, t, weight, d, noise, noise_weight, act_bias, blur_taps, s_next, rgb_weight, stylemap = ctx.saved_tensors
         xs, wkt = _mode_operand(ctx, xs), _mode_operand(ctx, ctx.wkt)
         scale, upsample, alpha, gain = ctx.cfg
@@ -509,7 +527,7 @@ class StyledLayerTC(Function):
         g_d = e / d
         g_w = style.weight_grad_layout(dwk, scale, cout, cin, 3) if need_w else None
         return (from_nhwc(dxs), g_w, g_d, None, g_noise_w, g_bias, ds_next, dwb, None, None, None, None, None, None, None,
-                g_map)
+                g_map, None)
 
 
 def chain_supported(gen, x, noise=None):
@@ -545,7 +563,7 @@ def generator_chain_forward(gen, latent, noise, maps_fn=None):
     scales = sd[:len(blocks)]
     rgb_style = {k: sd[len(blocks) + j][0] for j, k in enumerate(sorted(rgbs))}
     x0 = gen.input(latent)
-    xs = ModulateTC.apply(x0, scales[0][0])
+    xs, xs_op = ModulateTC.apply(x0, scales[0][0])
     skip = None
     for k, blk in enumerate(blocks):
         s_next = scales[k + 1][0] if k + 1 < len(blocks) else None
@@ -558,9 +576,9 @@ def generator_chain_forward(gen, latent, noise, maps_fn=None):
         if nz is None:
             nz = xs.new_empty(b, 1, oh, ow).normal_()
         taps = blk.conv.blur.kernel if blk.conv.upsample else blk.noise.weight
-        xs, rgb = StyledLayerTC.apply(xs, blk.conv.weight, scales[k][1], nz, blk.noise.weight, blk.activate.bias, s_next, wb,
-                                      blk.conv.scale, blk.conv.upsample, taps, blk.activate.negative_slope,
-                                      blk.activate.scale, prep[k][1], prep[k][2], smap)
+        xs, rgb, xs_op = StyledLayerTC.apply(xs, blk.conv.weight, scales[k][1], nz, blk.noise.weight, blk.activate.bias, s_next,
+                                             wb, blk.conv.scale, blk.conv.upsample, taps, blk.activate.negative_slope,
+                                             blk.activate.scale, prep[k][1], prep[k][2], smap, xs_op)
         if to_rgb is not None:
             out = rgb.permute(0, 3, 1, 2) + to_rgb.bias
             skip = out if skip is None else out + to_rgb.upsample(skip)

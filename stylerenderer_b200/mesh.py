@@ -239,7 +239,7 @@ def normal_pyramid(verts, tri, sizes, pose=None, eps=1e-6):
     maps = [torch.empty(b, 3, int(s), int(s), dtype=torch.float32, device=dev) for s in sizes]
     L = _lib.lib()
     csz = (ctypes.c_int64 * len(sizes))(*[int(s) for s in sizes])
-    ws = torch.empty(L.sr_rasterize_pyramid_workspace_bytes(b, len(sizes), csz) // 8 + 1, dtype=torch.int64, device=dev)
+    ws = torch.empty(L.sr_rasterize_pyramid_workspace_bytes(b, n, t.shape[0], len(sizes), csz) // 8 + 1, dtype=torch.int64, device=dev)
     arr = (RasterLevel * len(sizes))()
     for i, s in enumerate(sizes):
         arr[i].size, arr[i].out = int(s), _lib.ptr(maps[i])

@@ -57,7 +57,7 @@ def _forward(vertices, triangles, height, width, perspective, eps, tex=None, c=0
     ind = torch.empty(*lead, 3, dtype=torch.int64, device=dev)
     coeff = torch.empty(*lead, 3, dtype=v.dtype, device=dev)
     L = _lib.lib()
-    ws = torch.empty(L.sr_rasterize_workspace_bytes(b, h, w, int(sfx == "f64")) // 8 + 1, dtype=torch.int64, device=dev)
+    ws = torch.empty(L.sr_rasterize_workspace_bytes(b, nv, nf, h, w, int(sfx == "f64")) // 8 + 1, dtype=torch.int64, device=dev)
     out = None
     if tex is not None:
         tex = tex.contiguous()
@@ -189,7 +189,7 @@ class RasterizePyramid(Function):
             outs.append(torch.empty(*lead, c, dtype=vc.dtype, device=dev))
         L = _lib.lib()
         csz = (ctypes.c_int64 * len(sizes))(*[int(s) for s in sizes])
-        ws = torch.empty(L.sr_rasterize_pyramid_workspace_bytes(b, len(sizes), csz) // 8 + 1, dtype=torch.int64, device=dev)
+        ws = torch.empty(L.sr_rasterize_pyramid_workspace_bytes(b, nv, nf, len(sizes), csz) // 8 + 1, dtype=torch.int64, device=dev)
         arr = _levels(sizes, inds, coeffs, outs)
         with torch.cuda.device(dev):
             rc = L.sr_rasterize_pyramid_forward_f32(b, nv, nf, len(sizes), arr, int(shared_v), int(shared_f),
@@ -248,7 +248,7 @@ def rasterize_pyramid_maps(v, tex, tri, sizes, perspective=False, eps=1e-6, plan
         outs.append(torch.empty(shape, dtype=vc.dtype, device=dev))
     L = _lib.lib()
     csz = (ctypes.c_int64 * len(sizes))(*[int(s) for s in sizes])
-    ws = torch.empty(L.sr_rasterize_pyramid_workspace_bytes(b, len(sizes), csz) // 8 + 1, dtype=torch.int64, device=dev)
+    ws = torch.empty(L.sr_rasterize_pyramid_workspace_bytes(b, nv, nf, len(sizes), csz) // 8 + 1, dtype=torch.int64, device=dev)
     arr = (RasterLevel * len(sizes))()
     for i, sz in enumerate(sizes):
         arr[i].size, arr[i].out = int(sz), _lib.ptr(outs[i])

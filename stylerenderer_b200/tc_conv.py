@@ -51,11 +51,15 @@ def supported(cin, cout):
 #          columns [hi | hi | lo]), the weight-gradient kernel as three accumulating launches.  Products then carry
 #          ~2^-21 relative error instead of 2^-11, so no leaky-ReLU mask flips and every gradient can be checked at the
 #          1e-3 bar with generic inputs.  3x the tensor-core work plus unfused glue passes: a checking mode, not a fast one.
+# "bf16"   (train-step mode, BASELINE.json configs[3]): the GEMM operands -- modulated activations, re-laid-out weights,
+#          the gradient operand of dgrad / wgrad -- are bfloat16 tensors (tcgen05 kind::f16: twice the tensor-core rate,
+#          half the operand bytes); accumulation, saved activations, epilogue vectors, reductions and every parameter
+#          gradient stay fp32.  8-bit significands: outputs agree with the fp32 oracle to ~1e-2, not 1e-3.
 _PRECISION = {"mode": "tf32"}
 
 
 def set_precision(mode):
-    assert mode in ("tf32", "tf32x3")
+    assert mode in ("tf32", "tf32x3", "bf16")
     _PRECISION["mode"] = mode
 
 
@@ -79,6 +83,20 @@ class precision:
 
 def _exact():
     return _PRECISION["mode"] == "tf32x3"
+
+
+def _bf16():
+    return _PRECISION["mode"] == "bf16"
+
+
+def operand_dtype():
+    """dtype of the GEMM operand tensors in the current mode."""
+    return torch.bfloat16 if _bf16() else torch.float32
+
+
+def operand_like(t):
+    """An empty GEMM-operand tensor shaped like the fp32 NHWC tensor t."""
+    return torch.empty(t.shape, dtype=operand_dtype(), device=t.device)
 
 
 def split_tf32(x):
@@ -106,9 +124,11 @@ def _styled_tail(pre, noise, noise_weight, bias, stylemap, alpha, gain):
     return _lrelu(t, alpha, gain)
 
 
-def _check_nhwc(t, name):
-    if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.is_contiguous()):
-        raise RuntimeError(f"{name}: expected a contiguous float32 CUDA tensor [batch, h, w, channels]")
+def _check_nhwc(t, name, operand=False):
+    ok_dtype = t.dtype == torch.float32 or (operand and t.dtype == torch.bfloat16)
+    if not (t.is_cuda and ok_dtype and t.dim() == 4 and t.is_contiguous()):
+        raise RuntimeError(f"{name}: expected a contiguous float32{' / bfloat16' if operand else ''} CUDA tensor "
+                           "[batch, h, w, channels]")
 
 
 def weight_prep(w, scale, mode):
@@ -116,13 +136,13 @@ def weight_prep(w, scale, mode):
     mode 0: rows=cout, cols=cin (forward);  1: rows=cin, cols=cout, taps flipped (dgrad of the plain conv);
     mode 2: rows=cin, cols=cout, taps as is (dgrad of the stride-2 transposed conv)."""
     cout, cin, kh, kw = w.shape
-    if _exact():                                             # same layouts, unrounded (split by the GEMM wrappers)
+    if _exact() or _bf16():                                  # same layouts: unrounded (split by the GEMM wrappers) / bfloat16
         ws = w.detach() * scale
         if mode in (0, 3):
-            return ws.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin).contiguous()
-        if mode == 1:
-            ws = ws.flip(2, 3)
-        return ws.permute(1, 2, 3, 0).reshape(cin, kh * kw, cout).contiguous()
+            ws = ws.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+        else:
+            ws = (ws.flip(2, 3) if mode == 1 else ws).permute(1, 2, 3, 0).reshape(cin, kh * kw, cout)
+        return ws.to(operand_dtype()).contiguous()
     rows, cols = (cout, cin) if mode in (0, 3) else (cin, cout)
     dst = torch.empty(rows, kh * kw, cols, dtype=torch.float32, device=w.device)
     wc = w.contiguous()
@@ -142,13 +162,14 @@ def weight_prep_dual(w, scale, flip_transposed, want_wsq=True):
         return (weight_prep(w, scale, 0), weight_prep(w, scale, 1 if flip_transposed else 2),
                 ws.pow(2).sum((2, 3)) if want_wsq else None)
     wc = w.contiguous()
-    fwd = torch.empty(cout, kh * kw, cin, dtype=torch.float32, device=w.device)
-    tr = torch.empty(cin, kh * kw, cout, dtype=torch.float32, device=w.device)
+    fwd = torch.empty(cout, kh * kw, cin, dtype=operand_dtype(), device=w.device)
+    tr = torch.empty(cin, kh * kw, cout, dtype=operand_dtype(), device=w.device)
     wsq = torch.empty(cout, cin, dtype=torch.float32, device=w.device) if want_wsq else None
+    fn = _lib.lib().sr_conv_weight_prep_dual_bf16 if _bf16() else _lib.lib().sr_conv_weight_prep_dual_tf32
     with torch.cuda.device(w.device):
-        rc = _lib.lib().sr_conv_weight_prep_dual_tf32(_lib.ptr(fwd), _lib.ptr(tr), _lib.ptr(wsq), _lib.ptr(wc), float(scale), cout,
-                                                      cin, kh * kw, 1 if flip_transposed else 0, _lib.stream_of(w))
-    _lib.check(rc, "sr_conv_weight_prep_dual_tf32")
+        rc = fn(_lib.ptr(fwd), _lib.ptr(tr), _lib.ptr(wsq), _lib.ptr(wc), float(scale), cout, cin, kh * kw,
+                1 if flip_transposed else 0, _lib.stream_of(w))
+    _lib.check(rc, "sr_conv_weight_prep_dual")
     return fwd, tr, wsq
 
 
@@ -158,11 +179,12 @@ def modulate(x, style=None):
     b, h, w, c = x.shape
     if _exact():
         return x * style.reshape(b, 1, 1, c) if style is not None else x.clone()
-    xs = torch.empty_like(x)
+    xs = operand_like(x)
     s = style.contiguous() if style is not None else None
+    fn = _lib.lib().sr_modulate_bf16 if _bf16() else _lib.lib().sr_modulate_tf32
     with torch.cuda.device(x.device):
-        rc = _lib.lib().sr_modulate_tf32(_lib.ptr(xs), _lib.ptr(x), _lib.ptr(s), b, h * w, c, _lib.stream_of(x))
-    _lib.check(rc, "sr_modulate_tf32")
+        rc = fn(_lib.ptr(xs), _lib.ptr(x), _lib.ptr(s), b, h * w, c, _lib.stream_of(x))
+    _lib.check(rc, "sr_modulate")
     return xs
 
 
@@ -202,9 +224,12 @@ def conv_igemm_multi(x, wmat, phases, out, *, in_stride=1, out_stride=1, epilogu
                      scale2=None, bias=None, noise=None, noise_weight=None, stylemap=None, alpha=0.2, gain=2 ** 0.5,
                      rgb_weight=None, rgb_out=None):
     """One persistent launch over up to 4 phases [(taps, grid, out_origin)] sharing all tensors (see conv_igemm)."""
-    _check_nhwc(x, "conv input")
+    _check_nhwc(x, "conv input", operand=True)
     _check_nhwc(out, "conv output")
     assert wmat.is_contiguous() and wmat.shape[2] == x.shape[3] and out.shape[3] == wmat.shape[0] and out.shape[0] == x.shape[0]
+    op16 = x.dtype == torch.bfloat16
+    if wmat.dtype != x.dtype or (out2 is not None and out2.dtype != x.dtype):
+        raise RuntimeError("conv: the activation operand, the weights and the second output must share the operand dtype")
     if _exact():                     # split operands: K = [hi | lo | hi] x [hi | hi | lo] through the same kernels
         xh, xl = split_tf32(x)
         wh, wl = split_tf32(wmat)
@@ -215,8 +240,9 @@ def conv_igemm_multi(x, wmat, phases, out, *, in_stride=1, out_stride=1, epilogu
         _fill_args(a, x, wmat, taps, out, in_stride, grid, out_stride, origin, epilogue, rowscale, out2, scale2, bias, noise,
                    noise_weight, stylemap, alpha, gain, rgb_weight, rgb_out)
     with torch.cuda.device(x.device):
-        rc = _lib.lib().sr_conv_igemm_multi_tf32(arr, len(phases), _lib.stream_of(x))
-    _lib.check(rc, "sr_conv_igemm_multi_tf32")
+        fn = _lib.lib().sr_conv_igemm_multi_bf16 if op16 else _lib.lib().sr_conv_igemm_multi_tf32
+        rc = fn(arr, len(phases), _lib.stream_of(x))
+    _lib.check(rc, "sr_conv_igemm_multi")
     if _exact() and out2 is not None:   # the next layer's operand, unrounded (the kernel wrote its tf32 rounding)
         y = out if epilogue != 2 else _styled_tail(out, noise, noise_weight, bias, stylemap, alpha, gain)
         out2.copy_(y * scale2.reshape(out.shape[0], 1, 1, -1))
@@ -267,8 +293,11 @@ def conv3x3_s2_gather(g, wmat, out_hw, out=None, rowscale=None):
 def wgrad(g, x, taps, grid, *, g_stride=1, x_stride=1, taps_total=9, dw=None):
     """dw[co, t_out, ci] = sum_{n,gy,gx} g[n, gy*gs + gdy, gx*gs + gdx, co] * x[n, gy*xs + xdy, gx*xs + xdx, ci];
     taps: list of (g_dy, g_dx, x_dy, x_dx, t_out) -> [cout, taps_total, cin]."""
-    _check_nhwc(g, "wgrad g")
-    _check_nhwc(x, "wgrad x")
+    _check_nhwc(g, "wgrad g", operand=True)
+    _check_nhwc(x, "wgrad x", operand=True)
+    if g.dtype != x.dtype:
+        raise RuntimeError("wgrad: both operands must share the operand dtype")
+    wg_fn = _lib.lib().sr_conv_wgrad_bf16 if g.dtype == torch.bfloat16 else _lib.lib().sr_conv_wgrad_tf32
     a = WgradArgs()
     a.g, a.x = _lib.ptr(g), _lib.ptr(x)
     a.batch, a.g_h, a.g_w, a.cout = g.shape
@@ -290,8 +319,8 @@ def wgrad(g, x, taps, grid, *, g_stride=1, x_stride=1, taps_total=9, dw=None):
     with torch.cuda.device(g.device):
         for i, (gt, xt) in enumerate(terms):
             a.g, a.x, a.zero_init = _lib.ptr(gt), _lib.ptr(xt), 1 if i == 0 else 0
-            rc = _lib.lib().sr_conv_wgrad_tf32(ctypes.byref(a), _lib.stream_of(g))
-            _lib.check(rc, "sr_conv_wgrad_tf32")
+            rc = wg_fn(ctypes.byref(a), _lib.stream_of(g))
+            _lib.check(rc, "sr_conv_wgrad")
     return dw
 
 
@@ -332,14 +361,14 @@ def blur_styled(t, taps, pad, noise, noise_weight, bias, alpha, gain, scale2=Non
     b, ih, iw, c = t.shape
     oh, ow = ih + pad[0] + pad[1] - 3, iw + pad[0] + pad[1] - 3
     out = torch.empty(b, oh, ow, c, dtype=torch.float32, device=t.device)
-    out2 = torch.empty_like(out) if scale2 is not None else None
+    out2 = operand_like(out) if scale2 is not None else None
     nz, nbs = _noise_args(noise, oh, ow, b)
     sm, sms = _map_args(stylemap, oh, ow)
+    fn = _lib.lib().sr_blur_nhwc_styled3_bf16 if _bf16() else _lib.lib().sr_blur_nhwc_styled3_f32
     with torch.cuda.device(t.device):
-        rc = _lib.lib().sr_blur_nhwc_styled3_f32(_lib.ptr(out), _lib.ptr(out2), _lib.ptr(scale2), _lib.ptr(t),
-                                                 _lib.ptr(taps.contiguous()), b, ih, iw, c, pad[0], pad[1], _lib.ptr(nz), nbs,
-                                                 _lib.ptr(noise_weight), _lib.ptr(bias), float(alpha), float(gain),
-                                                 _lib.ptr(sm), sms, _lib.stream_of(t))
+        rc = fn(_lib.ptr(out), _lib.ptr(out2), _lib.ptr(scale2), _lib.ptr(t), _lib.ptr(taps.contiguous()), b, ih, iw, c,
+                pad[0], pad[1], _lib.ptr(nz), nbs, _lib.ptr(noise_weight), _lib.ptr(bias), float(alpha), float(gain),
+                _lib.ptr(sm), sms, _lib.stream_of(t))
     _lib.check(rc, "sr_blur_nhwc_styled3_f32")
     if _exact() and scale2 is not None:
         y = out if stylemap is None else _styled_tail(out, noise, noise_weight, bias, stylemap, alpha, gain)
@@ -353,17 +382,18 @@ def bwd_prologue(gy, y, noise, noise_weight, bias, d, alpha, gain, want_e):
     _check_nhwc(y, "bwd_prologue y")
     b, h, w, c = y.shape
     dev = y.device
-    ga = torch.empty_like(y)
+    d_k = None if _exact() else d                       # tf32x3: the kernel leaves g_pre unrounded, * d below
+    ga = operand_like(y) if d_k is not None else torch.empty_like(y)      # the GEMM operand only when d is applied here
     g_bias = torch.empty(c, dtype=torch.float32, device=dev)
     g_nw = torch.empty(1, dtype=torch.float32, device=dev)
     e = torch.empty(b, c, dtype=torch.float32, device=dev) if want_e else None
     nz, nbs = _noise_args(noise, h, w, b)
-    d_k = None if _exact() else d                       # tf32x3: the kernel leaves g_pre unrounded, * d below
+    fn = _lib.lib().sr_styled_bwd_prologue3_bf16 if _bf16() else _lib.lib().sr_styled_bwd_prologue3_f32
     with torch.cuda.device(dev):
-        rc = _lib.lib().sr_styled_bwd_prologue_f32(_lib.ptr(ga), _lib.ptr(g_bias), _lib.ptr(g_nw), _lib.ptr(e), _lib.ptr(gy),
-                                                   _lib.ptr(y), _lib.ptr(nz), nbs, _lib.ptr(noise_weight), _lib.ptr(bias),
-                                                   _lib.ptr(d_k), b, h * w, c, float(alpha), float(gain), _lib.stream_of(y))
-    _lib.check(rc, "sr_styled_bwd_prologue_f32")
+        rc = fn(_lib.ptr(ga), _lib.ptr(g_bias), _lib.ptr(g_nw), _lib.ptr(e), None, None, _lib.ptr(gy), None, None, None, None,
+                _lib.ptr(y), _lib.ptr(nz), nbs, _lib.ptr(noise_weight), _lib.ptr(bias), _lib.ptr(d_k), b, h * w, c,
+                float(alpha), float(gain), None, 0, None, _lib.stream_of(y))
+    _lib.check(rc, "sr_styled_bwd_prologue3")
     if d is not None and d_k is None:
         ga = ga * d.reshape(b, 1, 1, c)
     return ga, g_bias, g_nw, e
@@ -382,6 +412,8 @@ def scale_dot(a, other, scale, round_out, want_out=True):
                                               _lib.ptr(scale.contiguous() if scale is not None else None), b, h * w, c,
                                               int(bool(round_out)), _lib.stream_of(a))
     _lib.check(rc, "sr_scale_dot_nhwc_f32")
+    if round_out and _bf16() and out is not None:        # this (unchained) path gets its bf16 operand from a torch cast
+        out = out.to(torch.bfloat16)
     return out, dot
 
 
@@ -392,7 +424,8 @@ def bwd_prologue2(y, noise, noise_weight, bias, d, alpha, gain, want_e, gy=None,
     _check_nhwc(y, "bwd_prologue2 y")
     b, h, w, c = y.shape
     dev = y.device
-    ga = torch.empty_like(y)
+    d_k = None if _exact() else d                       # tf32x3: the kernel leaves g_pre unrounded, * d below
+    ga = operand_like(y) if d_k is not None else torch.empty_like(y)      # the GEMM operand only when d is applied here
     g_bias = torch.empty(c, dtype=torch.float32, device=dev)
     g_nw = torch.empty(1, dtype=torch.float32, device=dev)
     e = torch.empty(b, c, dtype=torch.float32, device=dev) if want_e else None
@@ -406,9 +439,9 @@ def bwd_prologue2(y, noise, noise_weight, bias, d, alpha, gain, want_e, gy=None,
         assert g_rgb.is_contiguous() and g_rgb.shape == (b, h, w, 3) and rgb_weight.is_contiguous()
     sm, sms = _map_args(stylemap, h, w)
     g_map = torch.empty(b, 2, h, w, dtype=torch.float32, device=dev) if sm is not None else None
-    d_k = None if _exact() else d                       # tf32x3: the kernel leaves g_pre unrounded, * d below
+    fn = _lib.lib().sr_styled_bwd_prologue3_bf16 if _bf16() else _lib.lib().sr_styled_bwd_prologue3_f32
     with torch.cuda.device(dev):
-        rc = _lib.lib().sr_styled_bwd_prologue3_f32(
+        rc = fn(
             _lib.ptr(ga), _lib.ptr(g_bias), _lib.ptr(g_nw), _lib.ptr(e), _lib.ptr(ds_next), _lib.ptr(dwb), _lib.ptr(gy),
             _lib.ptr(gxs), _lib.ptr(s_next), _lib.ptr(g_rgb), _lib.ptr(rgb_weight), _lib.ptr(y), _lib.ptr(nz), nbs,
             _lib.ptr(noise_weight), _lib.ptr(bias), _lib.ptr(d_k), b, h * w, c, float(alpha), float(gain), _lib.ptr(sm), sms,
@@ -432,11 +465,11 @@ def blur_scaledot(x, taps, pad, scale, other=None):
         from .op.upfirdn2d import upfirdn2d_raw
         f = upfirdn2d_raw(x, taps, 1, 1, 1, 1, pad[0], pad[1], pad[0], pad[1])
         return f * scale.reshape(b, 1, 1, c), ((f * other).sum((1, 2)) if other is not None else None)
-    out = torch.empty(b, oh, ow, c, dtype=torch.float32, device=x.device)
+    out = torch.empty(b, oh, ow, c, dtype=operand_dtype(), device=x.device)
     dot = torch.empty(b, c, dtype=torch.float32, device=x.device) if other is not None else None
+    fn = _lib.lib().sr_blur_nhwc_scaledot_bf16 if _bf16() else _lib.lib().sr_blur_nhwc_scaledot_f32
     with torch.cuda.device(x.device):
-        rc = _lib.lib().sr_blur_nhwc_scaledot_f32(_lib.ptr(out), _lib.ptr(dot), _lib.ptr(x), _lib.ptr(taps.contiguous()),
-                                                  _lib.ptr(scale.contiguous()), _lib.ptr(other), b, ih, iw, c, pad[0], pad[1],
-                                                  _lib.stream_of(x))
-    _lib.check(rc, "sr_blur_nhwc_scaledot_f32")
+        rc = fn(_lib.ptr(out), _lib.ptr(dot), _lib.ptr(x), _lib.ptr(taps.contiguous()), _lib.ptr(scale.contiguous()),
+                _lib.ptr(other), b, ih, iw, c, pad[0], pad[1], _lib.stream_of(x))
+    _lib.check(rc, "sr_blur_nhwc_scaledot")
     return out, dot

@@ -94,20 +94,40 @@ def param_errors(key, got, want):
     return errs
 
 
-# network-level gradient envelopes (see the module docstring): (median, fraction within 1e-3, max)
-ENVELOPE = {"tf32x3": (1e-3, 0.75, 5e-2), "mixed": (1e-3, 0.70, 5e-2), "tf32": (1e-2, 0.0, 3e-1)}
+def count_flips(got_y, want_y):
+    """Elements whose leaky-ReLU mask differs between two evaluations of an activated output (sign of y = sign of the
+    pre-activation since gain, alpha > 0).  One such element changes its gradient by the factor (1 - alpha) and, through
+    the backward convolution, a whole neighbourhood of dx by ~2 % of its max-norm at the test sizes."""
+    return int(((got_y.detach().cpu() > 0) != (want_y.detach().cpu() > 0)).sum())
+
+
+# Network-level gradient envelopes with the REAL leaky-ReLU (see the docstring of test_gpu_parity_tc.py and
+# profiles/r2_gradient_sensitivity.md): (median, max) over all gradient tensors, max-norm relative.  Measured on B200
+# (round 2): Generator(256): tf32x3 / mixed median 5.4e-3, max 7.6e-2; tf32 median 1.7e-2, max 1.7e-1 -- the oracle's own
+# fp32-vs-fp64 deviation is median 4.4e-4, max 1.0e-2 with a forward that agrees to 1.5e-6 (ours: 1.6e-4 / 5e-4).  The
+# kernels themselves are held to 1e-3 by the block tests and by the smooth-activation network test.
+ENVELOPE = {"tf32x3": (1.5e-2, 2e-1), "mixed": (1.5e-2, 2e-1), "tf32": (5e-2, 5e-1)}
 
 
 def hold_envelope(key, errs, mode):
     """errs: [(error, name)] over every gradient tensor of a network."""
     import statistics
     assert errs and all(e == e and e != float("inf") for e, _ in errs), f"{key}: non-finite gradient error"
-    med_tol, frac_tol, max_tol = ENVELOPE[mode]
+    med_tol, max_tol = ENVELOPE[mode]
     vals = sorted(e for e, _ in errs)
     med, worst = statistics.median(vals), max(errs)
     frac = sum(1 for v in vals if v <= REL) / len(vals)
     REPORT[key + "/gradients"] = {"tensors": len(vals), "median": med, "within_1e-3": frac, "max": worst[0], "argmax": worst[1]}
     print(f"{key}: {len(vals)} gradient tensors, median {med:.2e}, {100 * frac:.0f}% within 1e-3, max {worst[0]:.2e} ({worst[1]})")
     assert med <= med_tol, f"{key}: median gradient error {med:.2e} > {med_tol:.0e}"
-    assert frac >= frac_tol, f"{key}: only {100 * frac:.0f}% of the gradient tensors within 1e-3"
     assert worst[0] <= max_tol, f"{key}: {worst[1]} error {worst[0]:.2e} > {max_tol:.0e}"
+
+
+def hold_all(key, errs, tol):
+    """errs: [(error, name)]: EVERY gradient tensor within tol (used where no leaky-ReLU mask can flip)."""
+    import statistics
+    vals = sorted(e for e, _ in errs)
+    worst = max(errs)
+    REPORT[key + "/gradients"] = {"tensors": len(vals), "median": statistics.median(vals), "max": worst[0], "argmax": worst[1]}
+    print(f"{key}: {len(vals)} gradient tensors, median {statistics.median(vals):.2e}, max {worst[0]:.2e} ({worst[1]})")
+    assert worst[0] <= tol, f"{key}: {worst[1]} error {worst[0]:.2e} > {tol:.0e}"

@@ -66,7 +66,8 @@ def test_no_cpu_fallback_and_argument_errors():
     assert b"level size" in L.sr_last_error()
     import ctypes
     sizes = (ctypes.c_int64 * 3)(4, 8, 16)
-    assert L.sr_rasterize_pyramid_workspace_bytes(2, 3, sizes) == 2 * (16 + 64 + 256) * 8 + 16
+    # keys (8 B per pixel of every level) + pre-pass products (projected vertices per level, int32 triangles) + slack
+    assert L.sr_rasterize_pyramid_workspace_bytes(2, 5, 7, 3, sizes) == 2 * (16 + 64 + 256) * 8 + 2 * 5 * 12 * 3 + 8 + 2 * 7 * 12 + 8 + 16
 
 
 def test_product_does_not_import_the_oracle():

@@ -148,29 +148,32 @@ def test_styled_conv_tcgen05_vs_oracle(up, shape):
     finally:
         L.set_conv_backend("cudnn")
     close(got_y, want_y, "y")
-    # Gradients in the shipped tf32 mode: a tf32 forward moves pre-activations by ~3e-4, which flips the leaky-ReLU mask of
-    # the few elements that sit that close to zero; at these tiny spatial sizes one flip is a percent-level change of a
-    # max-norm, so the bound here is on the relative L2 error ...
-    def l2(a, b_):
-        a, b_ = a.detach().cpu().double().flatten(), b_.detach().cpu().double().flatten()
-        return float((a - b_).norm() / b_.norm())
-    assert l2(got_g[0], want_g[0]) < 3e-2 and l2(got_g[1], want_g[1]) < 3e-2
-    for k in want_p:
-        assert l2(got_p[k], want_p[k]) < 6e-2, k
-    # ... and the SAME backward kernels in tf32 on the fp32-faithful forward's activations (no flips) meet 1e-3 on every
-    # gradient with these generic inputs, as does the fp32-faithful mode end to end
-    from parity_util import tcgen05
-    for mode in ("mixed", "tf32x3"):
-        with tcgen05(mode) as t:
-            xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
-            sc = style.cuda().requires_grad_(True)
-            y_ = mod(xc, sc, noise.cuda())
-            t.backward_mode()
-            names = [n for n, _ in sorted(mod.named_parameters())]
-            gr = torch.autograd.grad(y_, [xc, sc] + [p for _, p in sorted(mod.named_parameters())], gy.cuda(), allow_unused=True)
-        close(y_, want_y, f"y [{mode}]")
-        close(gr[0], want_g[0], f"gx [{mode}]"); close(gr[1], want_g[1], f"gs [{mode}]")
-        check_param_grads(dict(zip(names, gr[2:])), {k_: v_.detach() if v_ is not None else None for k_, v_ in want_p.items()})
+    # Gradients in the shipped tf32 mode.  A tf32 forward moves pre-activations by ~3e-4, which flips the leaky-ReLU mask of
+    # the few elements that sit that close to zero, and one flip is a percent-level change of a max-norm at these sizes.
+    # The oracle is therefore evaluated once more with the KERNEL'S OWN mask in its leaky-ReLU backward (the forward is
+    # untouched): what remains is the arithmetic of the tf32 backward kernels on generic inputs, held to 1e-3.
+    mask = (got_y.detach().cpu() > 0)
+    flips = int((mask != (want_y > 0)).sum())
+
+    class MaskedLReLU(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, t):
+            return torch.nn.functional.leaky_relu(t, 0.2) * 2 ** 0.5
+
+        @staticmethod
+        def backward(ctx, g):
+            return torch.where(mask, g, g * 0.2) * 2 ** 0.5
+
+    old = T.fused_leaky_relu
+    T.fused_leaky_relu = lambda t, bias, negative_slope=0.2, scale=2 ** 0.5: MaskedLReLU.apply(t + bias.view(1, -1, 1, 1))
+    try:
+        xr, sr = x.clone().requires_grad_(True), style.clone().requires_grad_(True)
+        _, want_g, want_p = grads(ref, (xr, sr, noise), [xr, sr], gy)
+    finally:
+        T.fused_leaky_relu = old
+    print(f"StyledConv {shape} up={up}: {flips} of {mask.numel()} mask elements differ between the tf32 forward and the oracle")
+    close(got_g[0], want_g[0], "gx"); close(got_g[1], want_g[1], "gs")
+    check_param_grads(got_p, {k_: (v_.detach() if v_ is not None else None) for k_, v_ in want_p.items()})
 
 
 def _exact_inputs(b, cin, cout, r, up):
@@ -268,7 +271,7 @@ def test_styled_layer_chain_exact_forward(up, shape, with_map):
     smc = None
     if with_map:
         smc = wide.cuda()[:, 2:].requires_grad_(True)   # non-contiguous batch stride (4 planes per image)
-    got_main, got_rgb = fused.StyledLayerTC.apply(xc, cu[1], cu[2], noise.cuda(), cu[3], cu[4], cu[5],
+    got_main, got_rgb, _ = fused.StyledLayerTC.apply(xc, cu[1], cu[2], noise.cuda(), cu[3], cu[4], cu[5],
                                                   cu[6] if wb is not None else None, scale, up, taps.cuda(), alpha, gain,
                                                   None, None, smc)
     close(got_main, main.detach().float(), "main (tf32-rounded)")

@@ -54,7 +54,8 @@ def fp32_math():
         pass
 
 
-from parity_util import REL, REPORT, hold, hold_envelope, hold_param_grads, param_errors, rel_err, tcgen05  # noqa: E402
+from parity_util import (REL, REPORT, count_flips, hold, hold_all, hold_envelope, hold_param_grads, param_errors,  # noqa: E402
+                         rel_err, tcgen05)
 
 
 def grads_of(mod, args, wrt, gy, ctx=None):
@@ -70,11 +71,15 @@ def grads_of(mod, args, wrt, gy, ctx=None):
 MODES = ["tf32", "tf32x3", "mixed"]
 
 
-def block_grad_tol(mode, has_activation):
-    """Single block, same inputs as the reference: 1e-3 on every gradient -- except the pure tf32 mode through a
-    leaky-ReLU at these tiny sizes (8 x 8 ... 16 x 16 pixels), where a single mask flip is a percent-level change of a
-    max-norm (module docstring); there the bound is 1e-1 and the "mixed" mode carries the 1e-3 claim for the kernels."""
-    return 1e-1 if (mode == "tf32" and has_activation) else REL
+def block_grad_tol(key, got_y, want_y):
+    """Gradient bound of a single block with a leaky-ReLU: 1e-3 on every gradient whenever the block's mask equals the
+    reference's (always, so far, in the fp32-faithful modes at these sizes); if elements flipped -- the pure tf32 forward
+    moves pre-activations by ~3e-4 -- each flip is a ~2 % change of a max-norm (parity_util.count_flips) and the bound is
+    2e-1.  The flip-free 1e-3 claim for the tf32 BACKWARD kernels is carried by the "mixed" mode and by
+    test_gpu_modules.py::test_styled_conv_tcgen05_vs_oracle (oracle evaluated with the kernel's own mask)."""
+    flips = count_flips(got_y, want_y)
+    REPORT[key + "/mask_flips"] = flips
+    return REL if flips == 0 else 2e-1
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -111,7 +116,7 @@ def test_styled_conv_tcgen05_vs_reference_fixture(golden_tc, name, mode):
         y, (gx, gs), gp = grads_of(m, (x, s, g["noise"].cuda()), [x, s], g["gy"], t)
     assert t.calls >= 3
     k = f"{name}[{mode}]"
-    gtol = block_grad_tol(mode, True)
+    gtol = block_grad_tol(k, y, g["y"])
     hold(k + "/y", y, g["y"], REL)
     hold(k + "/gx", gx, g["gx"], gtol)
     hold(k + "/gs", gs, g["gs"], gtol)
@@ -135,10 +140,10 @@ def test_styled_map_layer_chain_vs_reference_fixture(golden_tc, name, mode):
     with tcgen05(mode) as t:
         conv = m.conv
         (s, d), = S.style_scales_all(s_in.unsqueeze(1), [conv], [0])
-        xs = fused.ModulateTC.apply(x, s)
+        xs, _ = fused.ModulateTC.apply(x, s)
         one = torch.ones(b, 128, device="cuda")
         taps = conv.blur.kernel if conv.upsample else m.noise.weight
-        main, _ = fused.StyledLayerTC.apply(xs, conv.weight, d, noise, m.noise.weight, m.activate.bias, one, None, conv.scale,
+        main, _, _ = fused.StyledLayerTC.apply(xs, conv.weight, d, noise, m.noise.weight, m.activate.bias, one, None, conv.scale,
                                             conv.upsample, taps, m.activate.negative_slope, m.activate.scale, None, None, smap)
         t.backward_mode()
         names = [n for n, _ in sorted(m.named_parameters())]
@@ -147,7 +152,7 @@ def test_styled_map_layer_chain_vs_reference_fixture(golden_tc, name, mode):
     assert t.calls >= 3
     k = f"{name}[{mode}]"
     assert all(bool(torch.isfinite(t_).all()) for t_ in gr if t_ is not None), "non-finite gradient (map0 == 0 pixels)"
-    gtol = block_grad_tol(mode, True)
+    gtol = block_grad_tol(k, main, g["y"])
     hold(k + "/y", main, g["y"], REL)                   # main = tf32(y * 1) in tf32 mode: one more rounding of 2^-11
     hold(k + "/gx", gr[0], g["gx"], gtol)
     hold(k + "/gs", gr[1], g["gs"], gtol)
@@ -277,6 +282,61 @@ def test_headline_generator256_vs_oracle(headline, mode):
             continue
         errs.append((rel_err(g_, w), n))
     hold_envelope(k, errs, mode)
+
+
+@pytest.fixture(scope="module")
+def headline_smooth():
+    """The same Generator(256, 512, 8) with the leaky-ReLU slope of every StyledConv set to 1 (activation = bias + gain):
+    the network is then a smooth function of its inputs, no mask can flip, and EVERY gradient of the chained tensor-core
+    blocks can be held to the oracle at 1e-3 -- the network-level proof of the backward kernels / chain plumbing."""
+    from oracle import torch_ref as T
+    ref, G = _headline_generator()
+    for net in (ref, G):
+        for blk in [net.conv1] + list(net.convs):
+            blk.activate.negative_slope = 1.0
+    old = T.fused_leaky_relu
+
+    def lrelu_honouring_slope(x, bias, negative_slope=0.2, scale=2 ** 0.5):     # the CPU branch hard-codes 0.2 (quirk #3)
+        shape = [1, -1] + [1] * (x.dim() - 2)
+        return torch.nn.functional.leaky_relu(x + bias.view(*shape), negative_slope=negative_slope) * scale
+    T.fused_leaky_relu = lrelu_honouring_slope
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+        z = seeded((2, 512), 1750)
+        cot = seeded((2, 3, 256, 256), 1751)
+        zr = z.clone().requires_grad_(True)
+        img, _ = ref([zr], randomize_noise=False)
+        named = [(n, p) for n, p in sorted(ref.named_parameters())]
+        gr = torch.autograd.grad(img, [zr] + [p for _, p in named], cot, allow_unused=True)
+    finally:
+        T.fused_leaky_relu = old
+    return dict(G=G, z=z, cot=cot, img=img.detach(), gz=gr[0], gp={n: g_ for (n, _), g_ in zip(named, gr[1:])})
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_headline_generator256_smooth_activation_every_gradient(headline_smooth, mode):
+    """Generator(256, 512, 8), batch 2, slope-1 activations: image and EVERY gradient (dz + 110 parameter tensors) against
+    the oracle -- 1e-3 in the fp32-faithful and mixed modes; the pure tf32 mode, whose 13 chained layers each add ~3e-4 of
+    operand rounding, is held to 5e-3."""
+    h = headline_smooth
+    G = h["G"]
+    named = [(n, p) for n, p in sorted(G.named_parameters())]
+    z = h["z"].cuda().requires_grad_(True)
+    with tcgen05(mode) as t:
+        img, _ = G([z], randomize_noise=False)
+        t.backward_mode()
+        gr = torch.autograd.grad(img, [z] + [p for _, p in named], h["cot"].cuda(), allow_unused=True)
+    assert t.calls >= 39
+    k = f"generator256_smooth[{mode}]"
+    hold(k + "/img", img, h["img"], REL)
+    errs = [(rel_err(gr[0], h["gz"]), "z")]
+    for (n, _), g_ in zip(named, gr[1:]):
+        w = h["gp"][n]
+        if w is None or float(w.abs().max()) == 0:
+            assert g_ is None or float(g_.abs().max()) == 0, n
+            continue
+        errs.append((rel_err(g_, w), n))
+    hold_all(k, errs, 5e-3 if mode == "tf32" else REL)
 
 
 # ------------------------------------------------------------------------------------- config 3 at full size
