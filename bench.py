@@ -185,20 +185,22 @@ def algorithmic_bytes(name, a):
     if name == "sr_blur_nhwc_styled_f32":
         b, ih, iw, c, p0, p1 = a[3], a[4], a[5], a[6], a[7], a[8]
         return 4 * b * c * (ih * iw + (ih + p0 + p1 - 3) * (iw + p0 + p1 - 3))
-    if name == "sr_blur_nhwc_styled3_f32":              # x -> y (+ the next layer's tf32 operand)
+    op = 2 if name.endswith("_bf16") else 4             # bytes per element of a GEMM-operand tensor in this call
+    if name in ("sr_blur_nhwc_styled3_f32", "sr_blur_nhwc_styled3_bf16"):      # x -> y (+ the next layer's operand)
         b, ih, iw, c, p0, p1 = a[5:11]
-        return 4 * b * c * (ih * iw + (ih + p0 + p1 - 3) * (iw + p0 + p1 - 3) * (2 if a[1] else 1))
-    if name == "sr_blur_nhwc_scaledot_f32":             # g -> tf32 operand (+ one more read when the dot product is asked for)
+        return b * c * (4 * ih * iw + (ih + p0 + p1 - 3) * (iw + p0 + p1 - 3) * (4 + (op if a[1] else 0)))
+    if name in ("sr_blur_nhwc_scaledot_f32", "sr_blur_nhwc_scaledot_bf16"):    # g -> operand (+ one more read for the dot product)
         b, ih, iw, c, p0, p1 = a[6:12]
-        return 4 * b * c * (ih * iw + (ih + p0 + p1 - 3) * (iw + p0 + p1 - 3) * (2 if a[5] else 1))
-    if name in ("sr_styled_bwd_prologue2_f32", "sr_styled_bwd_prologue3_f32"):
-        return 12 * a[17] * a[18] * a[19]               # read the gradient source and y, write the GEMM operand
-    if name == "sr_conv_weight_prep_dual_tf32":
-        return 4 * a[5] * a[6] * a[7] * (1 + (1 if a[0] else 0) + (1 if a[1] else 0))
+        return b * c * (4 * ih * iw + (ih + p0 + p1 - 3) * (iw + p0 + p1 - 3) * (op + (4 if a[5] else 0)))
+    if name in ("sr_styled_bwd_prologue2_f32", "sr_styled_bwd_prologue3_f32", "sr_styled_bwd_prologue3_bf16"):
+        # read the gradient source and y, write the GEMM operand (fp32 g_pre when d == NULL)
+        return (8 + (op if a[16] else 4)) * a[17] * a[18] * a[19]
+    if name in ("sr_conv_weight_prep_dual_tf32", "sr_conv_weight_prep_dual_bf16"):
+        return a[5] * a[6] * a[7] * (4 + (op if a[0] else 0) + (op if a[1] else 0))
     if name == "sr_weight_grad_layout_f32":
         return 8 * a[3] * a[4] * a[5]
-    if name == "sr_modulate_tf32":
-        return 8 * a[3] * a[4] * a[5]
+    if name in ("sr_modulate_tf32", "sr_modulate_bf16"):
+        return (4 + op) * a[3] * a[4] * a[5]
     if name == "sr_styled_bwd_prologue_f32":
         return 12 * a[11] * a[12] * a[13]
     if name == "sr_scale_dot_nhwc_f32":
@@ -209,9 +211,9 @@ def algorithmic_bytes(name, a):
 
 def algorithmic_flops(name, a):
     """2 * M * N * K of the implicit GEMM (tensor-bound kernels)."""
-    if name == "sr_conv_igemm_multi_tf32":
+    if name in ("sr_conv_igemm_multi_tf32", "sr_conv_igemm_multi_bf16"):
         return sum(2 * s.batch * s.grid_h * s.grid_w * s.num_taps * s.cin * s.cout for s in list(a[0])[:a[1]])
-    if name in ("sr_conv_igemm_tf32", "sr_conv_wgrad_tf32"):
+    if name in ("sr_conv_igemm_tf32", "sr_conv_wgrad_tf32", "sr_conv_wgrad_bf16"):
         s = a[0]._obj
         return 2 * s.batch * s.grid_h * s.grid_w * s.num_taps * s.cin * s.cout
     return 0
@@ -220,11 +222,11 @@ def algorithmic_flops(name, a):
 def launch_signature(name, a):
     """Shape key of one C-ABI call (launches of the same kernel on different layer shapes are different work)."""
     try:
-        if name == "sr_conv_igemm_multi_tf32":
+        if name in ("sr_conv_igemm_multi_tf32", "sr_conv_igemm_multi_bf16"):
             s = list(a[0])[0]
             kind = "up" if s.out_stride == 2 else ("gather" if s.in_stride == 2 else "plain")
             return f"conv:{kind}:{s.cin}:{s.cout}:{s.in_h}"
-        if name == "sr_conv_wgrad_tf32":
+        if name in ("sr_conv_wgrad_tf32", "sr_conv_wgrad_bf16"):
             s = a[0]._obj
             return f"wgrad:{s.cin}:{s.cout}:{s.grid_h}:{s.g_stride}"
     except Exception:                                   # noqa: BLE001
@@ -274,14 +276,17 @@ def dominant_kernel_roofline(stats, peaks, total_ms, steps):
         # denominator: the dense TF32 rate cuBLAS sustains on this GPU in this run (measure_tf32_peak), because these
         # launches are timed inside a long step; the burst figure and the nominal 1100 TF/s are given beside it
         peak = peaks.get("tf32_tflops_sustained") or 1100.0
+        if name.endswith("_bf16"):                      # bf16 operands: the driver-measured dense bf16 rate (sustained)
+            peak = peaks.get("bf16_tflops_sustained") or 2250.0
         ach = fl_all / (ms_all * 1e-3) / 1e12
         fl = sum(algorithmic_flops(name, a) for a, _ in calls)
         ach1 = fl / (ms * 1e-3) / 1e12
         common.update({"bound": "tensor", "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
-                       "peak_source": peaks.get("tf32_how", "nominal dense TF32 (B200_PROFILING.md)"),
-                       "peak_burst": peaks.get("tf32_tflops"), "peak_nominal": 1100.0,
-                       "frac_of_burst": round(ach / peaks["tf32_tflops"], 4) if peaks.get("tf32_tflops") else None,
-                       "frac_of_nominal": round(ach / 1100.0, 4),
+                       "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if name.endswith("_bf16")
+                                       else peaks.get("tf32_how", "nominal dense TF32 (B200_PROFILING.md)")),
+                       "peak_burst": peaks.get("bf16_tflops" if name.endswith("_bf16") else "tf32_tflops"),
+                       "peak_nominal": 2250.0 if name.endswith("_bf16") else 1100.0,
+                       "frac_of_nominal": round(ach / (2250.0 if name.endswith("_bf16") else 1100.0), 4),
                        "algorithmic_flops_per_step": fl_all // steps,
                        "heaviest_launch": {"launch": sig, "launches_per_step": len(calls) / steps,
                                            "avg_launch_ms": round(ms / len(calls), 5), "achieved": round(ach1, 1),
@@ -573,7 +578,7 @@ def run_train_step(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
     steps = args.steps if args.steps_given else 16
     cfg = ts.default_args(batch=16 if not args.batch_given else args.batch, iters=steps, warmup=max(args.warmup, 3),
-                          conv_backend=args.conv_backend or "tcgen05")
+                          conv_backend=args.conv_backend or "tcgen05", precision=args.precision or "bf16")
     peaks = measured_peaks()
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -614,8 +619,8 @@ def run_train_step(args):
     if rank == 0:
         line = {"metric": res["metric"], "value": res["value"], "unit": "images/s", "n_gpus": world, "steps": steps,
                 "warmup": cfg.warmup, "ms_per_step": res["ms_per_iter"], "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
-                "config": dict(res["config"], global_batch=world * cfg.batch, conv_backend=res["conv_backend"],
+                "vs_baseline": None, "dtype": cfg.precision, "data": "synthetic",
+                "config": dict(res["config"], global_batch=world * cfg.batch, conv_backend=res["conv_backend"], precision=res["dtype"],
                                execution="eager", l2="activations per iteration exceed the 126 MB L2; no explicit flush"),
                 "clocks": clocks.summary(), "e2e": res.get("e2e"), "gpu_launches": int(res["gpu_launches_per_iter"]),
                 "roofline": roof, "cpu_baseline": cpu_base, "collective": res["collective"], "losses": res["losses"]}
@@ -638,6 +643,8 @@ def main():
     ap.add_argument("--workload", default="generator", choices=["generator", "rasterize", "train_step"],
                     help="generator = BASELINE.json configs[1] (headline); rasterize = configs[2]; train_step = configs[3] "
                          "(DDP gradient all-reduce)")
+    ap.add_argument("--precision", default=None, choices=[None, "tf32", "bf16"],
+                    help="train_step only: operand mode of the tensor-core convs (default bf16, as BASELINE.json configs[3] asks)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches only (default: also replay the step as a CUDA graph)")
     args = ap.parse_args()
     args.steps_given = any(a == "--steps" or a.startswith("--steps=") for a in sys.argv[1:])

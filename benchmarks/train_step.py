@@ -173,6 +173,8 @@ def run(args):
     from stylerenderer_b200.model import Discriminator, GeneratorWithMap
 
     layers.set_conv_backend(args.conv_backend)
+    from stylerenderer_b200 import tc_conv
+    tc_conv.set_precision(getattr(args, "precision", "tf32"))       # operand mode of the tensor-core convolutions
     # the Discriminator's 3-channel stem / 513-channel final conv are cuDNN's: let it pick its algorithms by measurement
     # and keep D in channels_last so that no NCHW<->NHWC conversion kernels run around them
     torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
@@ -351,7 +353,10 @@ def run(args):
     res = {
         "metric": "GAR train step (G+D+rasterize+R1/16+path/4) images/sec", "value": round(world * B * args.iters / (ms * 1e-3), 2),
         "unit": "images/s", "n_gpus": world, "iters": args.iters, "ms_per_iter": round(ms / args.iters, 2),
-        "scaling": "weak", "dtype": "f32 storage, tf32 tensor-core convs",
+        "scaling": "weak",
+        "dtype": ("bf16 conv operands (tcgen05 kind::f16), fp32 accumulation / storage / parameter gradients"
+                  if getattr(args, "precision", "tf32") == "bf16" else "f32 storage, tf32 tensor-core convs"),
+        "precision": getattr(args, "precision", "tf32"),
         "conv_backend": {"generator": args.conv_backend, "discriminator": args.conv_backend + " (ResBlock convs; 3-channel stem, final conv on cuDNN)"},
         "config": {"workload": "GeneratorWithMap + Discriminator 256x256 (BASELINE.json configs[3])", "per_gpu_batch": B,
                    "parallelism": f"ddp{world} (NCCL gradient all-reduce, broadcast_buffers=False, dead ToRGB copies frozen)",
@@ -368,7 +373,7 @@ def run(args):
 
 def default_args(**over):
     ns = argparse.Namespace(batch=16, size=256, iters=16, warmup=3, mesh_n=189, conv_backend="tcgen05",
-                            no_cudnn_benchmark=False, d_nchw=False, profile=False, e2e=True)
+                            no_cudnn_benchmark=False, d_nchw=False, profile=False, e2e=True, precision="bf16")
     for k, v in over.items():
         setattr(ns, k, v)
     return ns
@@ -387,6 +392,8 @@ def main():
     ap.add_argument("--d-nchw", action="store_true", help="keep the Discriminator in NCHW (default: channels_last, no layout conversions)")
     ap.add_argument("--profile", action="store_true", help="print the top CUDA kernels of the timed iterations (torch.profiler)")
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"],
+                    help="operand mode of the tensor-core convolutions (BASELINE.json configs[3] asks for bf16)")
     args = ap.parse_args()
     res, _ = run(args)
     if res is not None:

@@ -17,10 +17,10 @@ class tcgen05:
         self.L, self.tc, self.lib = L, tc, _lib.lib()
         self.prev_backend, self.prev_mode = L.get_conv_backend(), tc.get_precision()
         L.set_conv_backend("tcgen05")
-        tc.set_precision("tf32x3" if self.mode == "mixed" else self.mode)
+        tc.set_precision("tf32x3" if self.mode == "mixed" else self.mode)      # modes: tf32, tf32x3, mixed, bf16
         self.calls = 0
         self._orig = {}
-        for n in ("sr_conv_igemm_multi_tf32", "sr_conv_wgrad_tf32"):
+        for n in ("sr_conv_igemm_multi_tf32", "sr_conv_wgrad_tf32", "sr_conv_igemm_multi_bf16", "sr_conv_wgrad_bf16"):
             fn = getattr(self.lib, n)
             self._orig[n] = fn
 
@@ -123,11 +123,12 @@ def hold_envelope(key, errs, mode):
     assert worst[0] <= max_tol, f"{key}: {worst[1]} error {worst[0]:.2e} > {max_tol:.0e}"
 
 
-def hold_all(key, errs, tol):
+def hold_all(key, errs, tol, median_tol=None):
     """errs: [(error, name)]: EVERY gradient tensor within tol (used where no leaky-ReLU mask can flip)."""
     import statistics
     vals = sorted(e for e, _ in errs)
-    worst = max(errs)
-    REPORT[key + "/gradients"] = {"tensors": len(vals), "median": statistics.median(vals), "max": worst[0], "argmax": worst[1]}
-    print(f"{key}: {len(vals)} gradient tensors, median {statistics.median(vals):.2e}, max {worst[0]:.2e} ({worst[1]})")
+    worst, med = max(errs), statistics.median(vals)
+    REPORT[key + "/gradients"] = {"tensors": len(vals), "median": med, "max": worst[0], "argmax": worst[1]}
+    print(f"{key}: {len(vals)} gradient tensors, median {med:.2e}, max {worst[0]:.2e} ({worst[1]})")
     assert worst[0] <= tol, f"{key}: {worst[1]} error {worst[0]:.2e} > {tol:.0e}"
+    assert median_tol is None or med <= median_tol, f"{key}: median {med:.2e} > {median_tol:.0e}"

@@ -209,7 +209,7 @@ def test_plain_conv_layer_tc(kind, shape, operand_mode):
     want = F.leaky_relu(t + b64.view(1, -1, 1, 1), 0.2) * 2 ** 0.5 if bias is not None else t
     assert relerr(y.detach(), want.detach()) < 3e-5, (kind, shape)
     # gradients: the backward operand (activation backward of gy) is rounded to the operand type inside the block
-    gtol = 2e-3 if operand_mode == "tf32" else 1.5e-2
+    gtol = 2e-3 if operand_mode == "tf32" else 2.5e-2
     wg = torch.autograd.grad(want, [x64, w_r] + ([b64] if bias is not None else []), gy.double())
     assert relerr(grads[0], wg[0]) < gtol, (kind, "dx")
     assert relerr(grads[1], wg[1] * scale) < gtol, (kind, "dw")       # d/dw = scale * d/d(scale*w)
@@ -243,7 +243,7 @@ def test_conv_tc_double_backward(kind, shape, operand_mode):
         yr = F.conv_transpose2d(xn, w64.transpose(0, 1), stride=2)
     else:
         yr = F.conv2d(xn, w64, stride=2)
-    tol = 2e-3 if operand_mode == "tf32" else 1.5e-2       # generic (unrounded) inputs: operand rounding 2^-11 / 2^-8
+    tol = 2e-3 if operand_mode == "tf32" else 2.5e-2       # generic (unrounded) inputs: operand rounding 2^-11 / 2^-8
     assert relerr(y.detach().permute(0, 3, 1, 2), yr.detach()) < tol
     gxr, gwr = torch.autograd.grad(yr, (x64, w64), g64.permute(0, 3, 1, 2), create_graph=True)
     assert relerr(gx.detach(), gxr.detach()) < tol and relerr(gw.detach(), gwr.detach()) < tol
