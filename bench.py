@@ -640,9 +640,9 @@ def main():
     ap.add_argument("--conv-backend", default=None, choices=[None, "cudnn", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's GPU formulation (gpu_reference)")
-    ap.add_argument("--workload", default="generator", choices=["generator", "rasterize", "train_step"],
+    ap.add_argument("--workload", default="generator", choices=["generator", "rasterize", "train_step", "inversion"],
                     help="generator = BASELINE.json configs[1] (headline); rasterize = configs[2]; train_step = configs[3] "
-                         "(DDP gradient all-reduce)")
+                         "(DDP gradient all-reduce); inversion = configs[4] (face-sharded, no collective)")
     ap.add_argument("--precision", default=None, choices=[None, "tf32", "bf16"],
                     help="train_step only: operand mode of the tensor-core convs (default bf16, as BASELINE.json configs[3] asks)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches only (default: also replay the step as a CUDA graph)")
@@ -655,6 +655,15 @@ def main():
         return run_rasterize(args)
     if args.workload == "train_step":
         return run_train_step(args)
+    if args.workload == "inversion":                    # BASELINE.json configs[4]: benchmarks/inversion.py prints the line
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("sr_inversion", os.path.join(ROOT, "benchmarks", "inversion.py"))
+        inv = importlib.util.module_from_spec(spec)
+        sys.modules["bench"] = sys.modules[__name__]     # inversion.py imports this module as `bench`
+        spec.loader.exec_module(inv)
+        sys.argv = [sys.argv[0], "--steps", str(args.steps if args.steps_given else 100), "--warmup", str(args.warmup)] + \
+                   (["--no-graph"] if args.no_graph else [])
+        return inv.main()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

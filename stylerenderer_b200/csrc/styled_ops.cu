@@ -298,7 +298,10 @@ static int styled_bwd_prologue_any(float *ga, float *g_bias, float *g_noise_w, f
     SR_REQUIRE(!noise || (noise_weight && g_noise_w), "styled_bwd_prologue: noise needs its weight and gradient slot");
     SR_REQUIRE(!gxs || (s_next && ds_next), "styled_bwd_prologue: gxs needs s_next and ds_next");
     SR_REQUIRE(!g_rgb || (rgb_weight && d_rgb_weight), "styled_bwd_prologue: g_rgb needs rgb_weight and d_rgb_weight");
-    SR_REQUIRE(alpha > 0 && gain > 0, "styled_bwd_prologue: alpha, gain must be positive");
+    // alpha == 0 (plain ReLU, e.g. the VGG-shaped perceptual stack of the inversion loop) is fine as long as nothing has to
+    // recover the pre-activation from y (e) or rebuild y from the pre-map value (stylemap)
+    SR_REQUIRE(gain > 0 && (alpha > 0 || (alpha == 0 && !e && !stylemap)),
+               "styled_bwd_prologue: gain must be positive and alpha positive (alpha == 0 only without e / stylemap)");
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t er = cudaMemsetAsync(g_bias, 0, sizeof(float) * (size_t)channels, st);
     if (er == cudaSuccess && g_noise_w) er = cudaMemsetAsync(g_noise_w, 0, sizeof(float), st);
