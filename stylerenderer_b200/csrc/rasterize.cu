@@ -193,6 +193,10 @@ struct RasterGeom {
     int64_t b, nv, nf;
     int h, w;
     int shared_v, shared_f, perspective;
+    // exact division by h*w and by w through host-prepared magic numbers: the pixel index arithmetic of the resolve /
+    // backward passes was ~85 % of their instructions as 64-bit divisions and address chains (ncu, round 2); every pixel
+    // count is < 2^31 (checked by the entry points)
+    FastDiv div_hw, div_w;
 };
 
 template <typename T>
@@ -261,12 +265,14 @@ template <typename T, int PASS>
 __device__ __forceinline__ void emit(const Tri<T> &t, int x, int y, uint32_t f, const RasterGeom &g, T eps,
                                      uint64_t *__restrict__ zkeys, uint32_t *__restrict__ idkeys, int64_t img)
 {
+    // zkeys / idkeys already point at this image's planes (cover_warp's callers add img * h * w once)
+    (void)img;
     T w[3], z;
     if (!tri_sample<T>(t, (T)x, (T)y, g.perspective != 0, eps, w, z)) return;
     if (!(z > RN<T>::lowest())) return;            // the buffer starts at -MAX and the test is strict; drops NaN
     z = z + (T)0;                                  // -0 -> +0: they compare equal on the host
     // reference pixel index is x + y*w (op/rasterize.cpp:42) with x spanning h and y spanning w (quirk 6)
-    const int64_t pix = (img * g.h * (int64_t)g.w) + (int64_t)y * g.w + x;
+    const uint32_t pix = (uint32_t)y * (uint32_t)g.w + (uint32_t)x;
     if (PASS == 0) {
         const uint64_t key = ((uint64_t)order_bits((float)z) << 32) | (uint64_t)(0xffffffffu - f);
         atomicMax(reinterpret_cast<unsigned long long *>(zkeys + pix), (unsigned long long)key);
@@ -340,7 +346,8 @@ raster_tri_kernel(const RasterGeom g, const T *__restrict__ verts, const int64_t
                 if (live) live = tri_setup<T>(t, g.h, g.w, g.perspective != 0, eps);
             }
         }
-        cover_warp<T, PASS>(t, live, f, lane, g, eps, zkeys, idkeys, img);
+        cover_warp<T, PASS>(t, live, f, lane, g, eps, zkeys + img * g.h * (int64_t)g.w,
+                            idkeys ? idkeys + img * g.h * (int64_t)g.w : nullptr, img);
     }
 }
 
@@ -363,6 +370,7 @@ struct Pyramid {
     T *out[kMaxLevels];
     const T *gout[kMaxLevels];
     int planar;                           // forward: interpolated maps are written as [b, c, size, size] planes (NCHW)
+    FastDiv div_hw[kMaxLevels], div_w[kMaxLevels];
 };
 
 template <typename T>
@@ -402,7 +410,7 @@ raster_tri_pyramid_kernel(const RasterGeom g0, const Pyramid<T> L, const T *__re
                 }
                 live = tri_setup<T, true>(t, g.h, g.w, g.perspective != 0, eps);
             }
-            cover_warp<T, 0>(t, live, f, lane, g, eps, zkeys + L.key_off[l], nullptr, img);
+            cover_warp<T, 0>(t, live, f, lane, g, eps, zkeys + L.key_off[l] + img * g.h * (int64_t)g.w, nullptr, img);
         }
     }
 }
@@ -428,6 +436,17 @@ __device__ __forceinline__ void stream_out(void *gdst, const void *ssrc, int byt
     }
 }
 
+// full 256-pixel block, 16-byte aligned destination: N16 int4 per CTA as straight-line code (no loop, no remainder)
+template <int N16>
+__device__ __forceinline__ void stream_out_full(void *gdst, const void *ssrc)
+{
+#pragma unroll
+    for (int r = 0; r < (N16 + kThreads - 1) / kThreads; ++r) {
+        const int i = r * kThreads + (int)threadIdx.x;
+        if (N16 % kThreads == 0 || i < N16) reinterpret_cast<int4 *>(gdst)[i] = reinterpret_cast<const int4 *>(ssrc)[i];
+    }
+}
+
 template <typename T>
 struct ResolveStage {
     int64_t ids[kThreads * 3];
@@ -435,68 +454,97 @@ struct ResolveStage {
     T out[kThreads * kMaxStageC];
 };
 
-// 256 consecutive pixels (block `blk`) of one raster geometry; called by the whole CTA.
+// 256 consecutive pixels (block `blk`) of one raster geometry; called by the whole CTA.  All pixel indices are 32-bit
+// (npix < 2^31) and the (image, row, column) split uses the host-prepared exact divisions of RasterGeom.
 template <typename T, bool PACKED>
 __device__ __forceinline__ void resolve_block(const RasterGeom &g, const T *__restrict__ verts, const int64_t *__restrict__ tris,
                                               const uint64_t *__restrict__ zkeys, const uint32_t *__restrict__ idkeys, T eps,
                                               int64_t *__restrict__ ids_out, T *__restrict__ bary_out,
                                               const T *__restrict__ tex, int c, T *__restrict__ out, int vec_ok,
-                                              int64_t blk, int64_t npix, ResolveStage<T> &st, bool planar = false,
+                                              uint32_t blk, uint32_t npix, ResolveStage<T> &st, bool planar = false,
                                               const T *__restrict__ P = nullptr, const int32_t *__restrict__ F32 = nullptr)
 {
     // planar: the map leaves as [b, c, h, w] planes -- consecutive threads are consecutive pixels of one plane, so the
     // per-thread 4-byte stores coalesce by themselves; ids_out / bary_out may then be NULL (forward-only callers: the mesh
     // is sampled under no_grad in the training loop, reference train.py:249-251, so nothing reads those buffers back)
     const bool stage_out = tex != nullptr && c <= kMaxStageC && !planar;
-    const int64_t pix0 = blk * kThreads, pix = pix0 + threadIdx.x;
-    const int count = (int)((npix - pix0 < kThreads) ? (npix - pix0) : kThreads);
+    const uint32_t pix0 = blk * kThreads, pix = pix0 + threadIdx.x;
+    const int count = (int)((npix - pix0 < (uint32_t)kThreads) ? (npix - pix0) : (uint32_t)kThreads);
     int64_t ids[3] = {0, 0, 0};
     T w[3] = {0, 0, 0};
     bool hit = false;
-    int64_t img = 0;
-    int rem = 0;
+    uint32_t img = 0, rem = 0;
     if (pix < npix) {
         const uint64_t key = zkeys[pix];
         hit = key != 0;
-        img = pix / (g.h * (int64_t)g.w);
-        rem = (int)(pix - img * g.h * (int64_t)g.w);
+        g.div_hw.divmod(pix, img, rem);
         if (hit) {
             const uint32_t f = PACKED ? (0xffffffffu - (uint32_t)key) : idkeys[pix];
-            const int y = rem / g.w, x = rem - y * g.w;
-            const T *V = verts + (g.shared_v ? 0 : img * g.nv * 3);
-            const int64_t *F = tris + (g.shared_f ? 0 : img * g.nf * 3);
+            uint32_t y, x;
+            g.div_w.divmod(rem, y, x);
+            const int64_t voff = g.shared_v ? 0 : (int64_t)img * g.nv * 3, foff = g.shared_f ? 0 : (int64_t)img * g.nf * 3;
             Tri<T> t;
             T z;
             if (P) {             // pre-projected corners, no pixel box needed: the edge matrix and the sample only
                 int32_t i32[3];
-                hit = load_tri_pre<T>(t, P + (g.shared_v ? 0 : img * g.nv * 3), F32 + (g.shared_f ? 0 : img * g.nf * 3), f, i32) &&
+                hit = load_tri_pre<T>(t, P + voff, F32 + foff, f, i32) &&
                       tri_setup<T, true, false>(t, g.h, g.w, g.perspective != 0, eps) &&
-                      tri_sample<T>(t, (T)x, (T)y, g.perspective != 0, eps, w, z);
+                      tri_sample<T>(t, (T)(int)x, (T)(int)y, g.perspective != 0, eps, w, z);
                 ids[0] = i32[0]; ids[1] = i32[1]; ids[2] = i32[2];
             } else {
-                hit = load_tri<T>(t, V, F, f, g.nv, ids) && tri_setup<T>(t, g.h, g.w, g.perspective != 0, eps) &&
-                      tri_sample<T>(t, (T)x, (T)y, g.perspective != 0, eps, w, z);
+                hit = load_tri<T>(t, verts + voff, tris + foff, f, g.nv, ids) && tri_setup<T>(t, g.h, g.w, g.perspective != 0, eps) &&
+                      tri_sample<T>(t, (T)(int)x, (T)(int)y, g.perspective != 0, eps, w, z);
             }
-            if (hit && !g.shared_v) { ids[0] += g.nv * img; ids[1] += g.nv * img; ids[2] += g.nv * img; }
+            if (hit && !g.shared_v) { const int64_t o = g.nv * (int64_t)img; ids[0] += o; ids[1] += o; ids[2] += o; }
             if (!hit) { ids[0] = ids[1] = ids[2] = 0; w[0] = w[1] = w[2] = 0; }
         }
     }
+    if (ids_out) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { st.ids[3 * threadIdx.x + k] = ids[k]; st.w[3 * threadIdx.x + k] = w[k]; }
+        for (int k = 0; k < 3; ++k) st.ids[3 * threadIdx.x + k] = ids[k];
+    }
+    if (bary_out) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) st.w[3 * threadIdx.x + k] = w[k];
+    }
     if (tex && pix < npix) {
         // op/rasterize.py:29-37: sum_k tex[ids_k] * bary_k  (background: row 0 times 0 = 0)
-        for (int ch = 0; ch < c; ++ch) {
-            T v = 0;
-            if (hit) v = tex[ids[0] * c + ch] * w[0] + tex[ids[1] * c + ch] * w[1] + tex[ids[2] * c + ch] * w[2];
-            if (stage_out) st.out[threadIdx.x * c + ch] = v;
-            else if (planar) out[((img * c + ch) * g.h * (int64_t)g.w) + rem] = v;
-            else out[pix * c + ch] = v;
+        if (c == 3) {                                    // normals / colours: the case every caller of the model has
+            T v[3] = {0, 0, 0};
+            if (hit) {
+                const T *t0 = tex + ids[0] * 3, *t1 = tex + ids[1] * 3, *t2 = tex + ids[2] * 3;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) v[ch] = __ldg(t0 + ch) * w[0] + __ldg(t1 + ch) * w[1] + __ldg(t2 + ch) * w[2];
+            }
+            if (stage_out) { st.out[threadIdx.x * 3] = v[0]; st.out[threadIdx.x * 3 + 1] = v[1]; st.out[threadIdx.x * 3 + 2] = v[2]; }
+            else if (planar) {
+                T *o = out + ((size_t)img * 3 * g.h) * g.w + rem;
+                const size_t plane = (size_t)g.h * g.w;
+                o[0] = v[0]; o[plane] = v[1]; o[2 * plane] = v[2];
+            } else { T *o = out + (size_t)pix * 3; o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; }
+        } else {
+            for (int ch = 0; ch < c; ++ch) {
+                T v = 0;
+                if (hit) v = tex[ids[0] * c + ch] * w[0] + tex[ids[1] * c + ch] * w[1] + tex[ids[2] * c + ch] * w[2];
+                if (stage_out) st.out[threadIdx.x * c + ch] = v;
+                else if (planar) out[(((size_t)img * c + ch) * g.h) * g.w + rem] = v;
+                else out[(size_t)pix * c + ch] = v;
+            }
         }
     }
+    if (!ids_out && !bary_out && !stage_out) return;         // maps-only planar output: nothing staged
     __syncthreads();
-    if (ids_out) stream_out<int4>(ids_out + pix0 * 3, st.ids, count * 3 * (int)sizeof(int64_t), vec_ok);
-    if (bary_out) stream_out<int4>(bary_out + pix0 * 3, st.w, count * 3 * (int)sizeof(T), vec_ok);
-    if (stage_out) stream_out<int4>(out + pix0 * c, st.out, count * c * (int)sizeof(T), vec_ok && ((pix0 * c * (int64_t)sizeof(T)) % 16 == 0));
+    if (count == kThreads && vec_ok && sizeof(T) == 4) {     // common case: straight-line 16-byte copies
+        if (ids_out) stream_out_full<kThreads * 24 / 16>(ids_out + (size_t)pix0 * 3, st.ids);
+        if (bary_out) stream_out_full<kThreads * 12 / 16>(bary_out + (size_t)pix0 * 3, st.w);
+        if (stage_out && c == 3) stream_out_full<kThreads * 12 / 16>(out + (size_t)pix0 * 3, st.out);
+        else if (stage_out) stream_out<int4>(out + (size_t)pix0 * c, st.out, count * c * (int)sizeof(T), ((size_t)pix0 * c * sizeof(T)) % 16 == 0);
+    } else {
+        if (ids_out) stream_out<int4>(ids_out + (size_t)pix0 * 3, st.ids, count * 3 * (int)sizeof(int64_t), vec_ok);
+        if (bary_out) stream_out<int4>(bary_out + (size_t)pix0 * 3, st.w, count * 3 * (int)sizeof(T), vec_ok);
+        if (stage_out) stream_out<int4>(out + (size_t)pix0 * c, st.out, count * c * (int)sizeof(T),
+                                        vec_ok && (((size_t)pix0 * c * sizeof(T)) % 16 == 0));
+    }
     __syncthreads();
 }
 
@@ -509,9 +557,9 @@ raster_resolve_kernel(const RasterGeom g, const T *__restrict__ verts, const int
                       const T *__restrict__ P = nullptr, const int32_t *__restrict__ F32 = nullptr)
 {
     __shared__ __align__(16) ResolveStage<T> st;
-    const int64_t npix = g.b * g.h * (int64_t)g.w;
-    const int64_t nblk = (npix + kThreads - 1) / kThreads;
-    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x)
+    const uint32_t npix = (uint32_t)(g.b * g.h * (int64_t)g.w);
+    const uint32_t nblk = (npix + kThreads - 1) / kThreads;
+    for (uint32_t blk = blockIdx.x; blk < nblk; blk += gridDim.x)
         resolve_block<T, PACKED>(g, verts, tris, zkeys, idkeys, eps, ids_out, bary_out, tex, c, out, vec_ok, blk, npix, st,
                                  false, P, F32);
 }
@@ -531,9 +579,10 @@ raster_resolve_pyramid_kernel(const RasterGeom g0, const Pyramid<T> L, const T *
         while (blk >= L.blk_off[l + 1]) ++l;                 // CTA-uniform
         RasterGeom g = g0;
         g.h = g.w = L.size[l];
-        const int64_t npix = g.b * g.h * (int64_t)g.w;
+        g.div_hw = L.div_hw[l]; g.div_w = L.div_w[l];
+        const uint32_t npix = (uint32_t)(g.b * g.h * (int64_t)g.w);
         resolve_block<T, true>(g, verts, tris, zkeys + L.key_off[l], nullptr, eps, L.ids[l], L.bary[l], tex, c, L.out[l],
-                               vec_ok, blk - L.blk_off[l], npix, st, L.planar != 0, P + l * level_stride, F32);
+                               vec_ok, (uint32_t)(blk - L.blk_off[l]), npix, st, L.planar != 0, P + l * level_stride, F32);
     }
 }
 
@@ -633,7 +682,7 @@ __device__ __forceinline__ void backward_pixel(int64_t b, int64_t n, int h, int 
                                                const T *__restrict__ verts, const T *__restrict__ tex,
                                                const int64_t *__restrict__ ids, const T *__restrict__ bary,
                                                const T *__restrict__ gout, T *__restrict__ grad_v, T *__restrict__ grad_tex,
-                                               T eps, int64_t pix)
+                                               T eps, uint32_t pix, const FastDiv &div_hw, const FastDiv &div_w)
 {
     const T w0 = bary[3 * pix], w1 = bary[3 * pix + 1], w2 = bary[3 * pix + 2];
     if (w0 == (T)0 && w1 == (T)0 && w2 == (T)0) return;                 // background
@@ -651,8 +700,10 @@ __device__ __forceinline__ void backward_pixel(int64_t b, int64_t n, int h, int 
     if (!grad_v) return;
     T q[9], d[27];
     if (!gather_pixel_tri<T>(verts, I, n * b, q)) return;
-    const int rem = (int)(pix % (h * (int64_t)w));
-    if (!bary_grad<T>(q, (T)(rem % w), (T)(rem / w), (T)h, (T)w, perspective != 0, eps, d)) return;
+    uint32_t img_, rem, py, px;
+    div_hw.divmod(pix, img_, rem);
+    div_w.divmod(rem, py, px);
+    if (!bary_grad<T>(q, (T)(int)px, (T)(int)py, (T)h, (T)w, perspective != 0, eps, d)) return;
 #pragma unroll
     for (int k = 0; k < 3; ++k)
 #pragma unroll
@@ -667,12 +718,13 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 raster_backward_kernel(int64_t b, int64_t n, int h, int w, int c, int perspective, const T *__restrict__ verts,
                        const T *__restrict__ tex, const int64_t *__restrict__ ids, const T *__restrict__ bary,
-                       const T *__restrict__ gout, T *__restrict__ grad_v, T *__restrict__ grad_tex, T eps)
+                       const T *__restrict__ gout, T *__restrict__ grad_v, T *__restrict__ grad_tex, T eps,
+                       const FastDiv div_hw, const FastDiv div_w)
 {
-    const int64_t npix = b * h * (int64_t)w;
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
-    for (int64_t pix = (int64_t)blockIdx.x * kThreads + threadIdx.x; pix < npix; pix += stride)
-        backward_pixel<T>(b, n, h, w, c, perspective, verts, tex, ids, bary, gout, grad_v, grad_tex, eps, pix);
+    const uint32_t npix = (uint32_t)(b * h * (int64_t)w);
+    const uint32_t stride = gridDim.x * kThreads;
+    for (uint32_t pix = blockIdx.x * kThreads + threadIdx.x; pix < npix; pix += stride)
+        backward_pixel<T>(b, n, h, w, c, perspective, verts, tex, ids, bary, gout, grad_v, grad_tex, eps, pix, div_hw, div_w);
 }
 
 // every level of a pyramid scatters into the SAME grad_v / grad_tex (the sum autograd would form from per-level calls)
@@ -687,10 +739,10 @@ raster_backward_pyramid_kernel(int64_t b, int64_t n, const Pyramid<T> L, int c, 
         int l = 0;
         while (blk >= L.blk_off[l + 1]) ++l;
         const int size = L.size[l];
-        const int64_t pix = (blk - L.blk_off[l]) * kThreads + threadIdx.x;
-        if (pix < b * size * (int64_t)size)
+        const uint32_t pix = (uint32_t)(blk - L.blk_off[l]) * kThreads + threadIdx.x;
+        if (pix < (uint32_t)(b * size * (int64_t)size))
             backward_pixel<T>(b, n, size, size, c, perspective, verts, tex, L.ids[l], L.bary[l], L.gout[l], grad_v, grad_tex,
-                              eps, pix);
+                              eps, pix, L.div_hw[l], L.div_w[l]);
     }
 }
 
@@ -727,6 +779,8 @@ int rasterize_forward(int64_t b, int64_t nv, int64_t nf, int64_t h, int64_t w, i
     RasterGeom g;
     g.b = b; g.nv = nv; g.nf = nf; g.h = (int)h; g.w = (int)w;
     g.shared_v = shared_v; g.shared_f = shared_f; g.perspective = perspective;
+    SR_REQUIRE(npix < 0x7fffffffll, "rasterize: more than 2^31 pixels");
+    g.div_hw = FastDiv((uint32_t)(h * w)); g.div_w = FastDiv((uint32_t)w);
     if (eps < 0) eps = -eps;
     uint32_t *idkeys = reinterpret_cast<uint32_t *>(keys + npix);
     // float path: per-vertex / per-triangle pre-pass products behind the keys (see raster_prepass_kernel)
@@ -789,8 +843,10 @@ int rasterize_backward(int64_t b, int64_t n, int64_t h, int64_t w, int64_t c, in
     if (b == 0 || (!grad_v && !grad_tex)) return SR_OK;
     SR_REQUIRE(verts && tex && ids && bary && gout, "rasterize_backward: null pointer");
     if (eps < 0) eps = -eps;
+    SR_REQUIRE(b * h * w < 0x7fffffffll, "rasterize_backward: more than 2^31 pixels");
     raster_backward_kernel<T><<<grid_for(b * h * w, 16), kThreads, 0, (cudaStream_t)stream>>>(
-        b, n, (int)h, (int)w, (int)c, perspective, verts, tex, ids, bary, gout, grad_v, grad_tex, eps);
+        b, n, (int)h, (int)w, (int)c, perspective, verts, tex, ids, bary, gout, grad_v, grad_tex, eps,
+        FastDiv((uint32_t)(h * w)), FastDiv((uint32_t)w));
     count_launch();
     return check_launch("sr_rasterize_backward");
 }
@@ -813,7 +869,9 @@ int build_pyramid(Pyramid<T> &L, int64_t b, int n_levels, const sr_raster_level 
         if (backward && !lv.gout) continue;
         SR_REQUIRE(maps_only || (lv.ids && lv.bary), "rasterize_pyramid: null ids / bary");
         const int l = L.n++;
+        SR_REQUIRE(npix < 0x7fffffffll, "rasterize_pyramid: more than 2^31 pixels in a level");
         L.size[l] = (int)lv.size;
+        L.div_hw[l] = FastDiv((uint32_t)(lv.size * lv.size)); L.div_w[l] = FastDiv((uint32_t)lv.size);
         L.key_off[l] = keys;
         L.blk_off[l + 1] = L.blk_off[l] + (npix + kThreads - 1) / kThreads;
         L.ids[l] = lv.ids;

@@ -72,7 +72,7 @@ struct PrologueParams {
 // MINB), the ToRGB ones 80 (profiles/r1_prologue_specialisation_ptxas.md).  SR_PROLOGUE_SPEC=0 forces the run-time kernel.
 constexpr int kSpecGy = 1, kSpecGxs = 2, kSpecRgb = 4, kSpecE = 8, kSpecNoise = 16, kSpecD = 32;
 
-template <bool MAP, int SPEC, int MINB>
+template <bool MAP, int SPEC, int MINB, int U = 2>      // U = pixels per loop iteration (the ToRGB variants take 1: fewer temporaries)
 __global__ void __launch_bounds__(kThreads, MINB)
 styled_bwd_prologue_kernel(const PrologueParams p)
 {
@@ -109,14 +109,14 @@ styled_bwd_prologue_kernel(const PrologueParams p)
     const float ipos = 1.0f / p.gain, ineg = 1.0f / (p.gain * p.alpha);
     float4 a_bias = zero4, a_e = zero4;
     float a_nw = 0.0f;
-    // two pixels per iteration: twice the loads in flight per thread (the pass is pure streaming)
-    for (int px0 = p0 + pl; px0 < p1; px0 += 2 * lanes_p) {
+    // U pixels per iteration: U times the loads in flight per thread (the pass is pure streaming)
+    for (int px0 = p0 + pl; px0 < p1; px0 += U * lanes_p) {
         const int pxs[2] = {px0, px0 + lanes_p};
-        float4 yy2[2], g2[2], gx2[2];
-        float gk2[2][3], n2[2], m02[2], m12[2];
-        bool ok[2];
+        float4 yy2[U], g2[U], gx2[U];
+        float gk2[U][3], n2[U], m02[U], m12[U];
+        bool ok[U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
             ok[u] = pxs[u] < p1;
             const long long off = (long long)(ok[u] ? pxs[u] : px0) * C4;
             yy2[u] = __ldg(y + off);
@@ -130,7 +130,7 @@ styled_bwd_prologue_kernel(const PrologueParams p)
             m12[u] = MAP ? __ldg(p.stylemap + (long long)b * p.map_bstride + p.pixels + pp) : 0.0f;
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
             if (!ok[u]) continue;
             const int px = pxs[u];
             const float n = n2[u];
@@ -327,9 +327,11 @@ static int styled_bwd_prologue_any(float *ga, float *g_bias, float *g_noise_w, f
                      (noise ? kSpecNoise : 0) | (d ? kSpecD : 0);
     bool launched = false;
     // measured (B200, B = 32 generator step, profiles/r2_prologue_spec.md): specialising the combinations WITHOUT the ToRGB
-    // gradient (64 registers, no spill) takes the pass from 2.59 to 2.46 ms; the ToRGB combinations at 80 registers spill
-    // and lose the gain (2.55 ms), so they stay on the run-time kernel unless SR_PROLOGUE_SPEC=1
-    const bool spec_rgb = spec_env && spec_env[0] == '1';
+    // gradient (64 registers, no spill) takes the pass from 2.59 to 2.46 ms; the ToRGB combinations spilled at 80 registers
+    // with two pixels per iteration and lost the gain (2.55 ms) -- they now take one pixel per iteration (no spill, 3 CTAs
+    // per SM; ncu: the run-time kernel they replace sits at 45 % of DRAM, the spill-free specialised ones at 79 %).
+    // SR_PROLOGUE_SPEC=2 keeps them on the run-time kernel (A/B).
+    const bool spec_rgb = !(spec_env && spec_env[0] == '2');
     if (!(spec_env && spec_env[0] == '0') && !stylemap && (spec_rgb || !g_rgb)) {
         launched = true;
         switch (spec) {                                   // the combinations the chained generator produces
@@ -338,9 +340,9 @@ static int styled_bwd_prologue_any(float *ga, float *g_bias, float *g_noise_w, f
         case kSpecGxs | kSpecE | kSpecNoise | kSpecD:                            // plain block without ToRGB
             styled_bwd_prologue_kernel<false, kSpecGxs | kSpecE | kSpecNoise | kSpecD, 4><<<nb, kThreads, 0, st>>>(p); break;
         case kSpecGxs | kSpecRgb | kSpecE | kSpecNoise | kSpecD:                 // plain block with ToRGB
-            styled_bwd_prologue_kernel<false, kSpecGxs | kSpecRgb | kSpecE | kSpecNoise | kSpecD, 3><<<nb, kThreads, 0, st>>>(p); break;
+            styled_bwd_prologue_kernel<false, kSpecGxs | kSpecRgb | kSpecE | kSpecNoise | kSpecD, 3, 1><<<nb, kThreads, 0, st>>>(p); break;
         case kSpecGy | kSpecRgb | kSpecE | kSpecNoise | kSpecD:                  // last block (image gradient + ToRGB)
-            styled_bwd_prologue_kernel<false, kSpecGy | kSpecRgb | kSpecE | kSpecNoise | kSpecD, 3><<<nb, kThreads, 0, st>>>(p); break;
+            styled_bwd_prologue_kernel<false, kSpecGy | kSpecRgb | kSpecE | kSpecNoise | kSpecD, 3, 1><<<nb, kThreads, 0, st>>>(p); break;
         default: launched = false;
         }
     }

@@ -847,6 +847,217 @@ fir_nhwc_ring_kernel(float *__restrict__ out, const float *__restrict__ x, const
     }
 }
 
+// ---- channels-last FIR, low-instruction-count form (default since round 2) ---------------------------------------------
+// ncu on the 256^2 layer of the generator step (profiles/r2_ncu_hbm_passes.md): upfirdn2d_nhwc_kernel issues 566 M warp
+// instructions for 67 M float4 outputs (270 per output: 64 FFMA for the 16 taps, 30 MOV to slide its 4 x 5 register window,
+// the rest addressing / predicates / tail) and is ISSUE bound (issue active 67 % at 24 % occupancy, DRAM 55 %).  Here:
+//   * rank-1 taps (every FIR the model builds, reference layers.py:7-12) take the separable form: a 4-tap row filter of the
+//     incoming input row, then one FMA per open output row -- 32 instead of 64 FFMA per float4 output (general taps keep
+//     the 2-D form: same loop, 16 FMAs);
+//   * the four open output rows live in a register ring whose slot index is a compile-time constant inside a 4x unrolled
+//     row loop -- no register moves;
+//   * the next input row is fetched while the current one is consumed; column predicates and row pointers are hoisted.
+// Thread decomposition and tails as upfirdn2d_nhwc_kernel (4 channels x 2 columns x a strip of rows).
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 2)
+fir_nhwc_sep_kernel(float *__restrict__ out, const float *__restrict__ x, const float *__restrict__ taps, const NhwcGeom g)
+{
+    constexpr int K = 4;
+    constexpr bool STYLED = (MODE == 1);
+    constexpr bool PREFETCH = (MODE != 2);                 // the scale(+dot) tail needs the registers of the second row buffer
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (tid >= g.total_threads) return;
+    uint32_t t = (uint32_t)tid, c, xp, ys, n;
+    g.div_c4.divmod(t, t, c);
+    g.div_pairs.divmod(t, t, xp);
+    g.div_strips.divmod(t, n, ys);
+
+    // flipped taps tk[a][b] = taps[K-1-a][K-1-b]; rank-1 factorisation tk[a][b] = kv[a] * kh[b] through the largest tap
+    float kv[K], kh[K];
+    bool sep;
+    {
+        float tk[K][K];
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+#pragma unroll
+            for (int b = 0; b < K; ++b) tk[a][b] = __ldg(taps + (K - 1 - a) * K + (K - 1 - b));
+        int pa = 0, pb = 0;
+        float best = 0.0f;
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+#pragma unroll
+            for (int b = 0; b < K; ++b)
+                if (fabsf(tk[a][b]) > best) { best = fabsf(tk[a][b]); pa = a; pb = b; }
+        float pivot = 1.0f;
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+#pragma unroll
+            for (int b = 0; b < K; ++b)
+                if (a == pa && b == pb) pivot = tk[a][b];
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+            kv[a] = 0.0f; kh[a] = 0.0f;
+#pragma unroll
+            for (int b = 0; b < K; ++b) {
+                if (b == pb) kv[a] = tk[a][b];
+                if (b == pa) kh[a] = tk[b][a] / pivot;
+            }
+        }
+        sep = best > 0.0f;
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+#pragma unroll
+            for (int b = 0; b < K; ++b) sep = sep && fabsf(kv[a] * kh[b] - tk[a][b]) <= 1e-6f * best;
+    }
+
+    const int ox0 = xp * 2;
+    const int ix0 = ox0 - g.pad_x0;
+    const int oy0 = ys * g.rows_per_strip;
+    const int oy1 = min(g.out_h, oy0 + g.rows_per_strip);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool col1 = ox0 + 1 < g.out_w;
+    bool cok[K + 1];
+#pragma unroll
+    for (int b = 0; b < K + 1; ++b) cok[b] = ix0 + b >= 0 && ix0 + b < g.in_w;
+    const int64_t row_stride = (int64_t)g.in_w * g.c4;                  // float4 units
+    // first input pixel of this thread's window: image n, row (oy0 - pad), column ix0, channel quad c
+    const float4 *src = reinterpret_cast<const float4 *>(x) + (int64_t)n * g.in_h * row_stride + (int64_t)(oy0 - g.pad_y0) * row_stride +
+                        (int64_t)ix0 * g.c4 + c;
+    int iy = oy0 - g.pad_y0;
+
+    float nw = 0.0f;
+    float4 bias4 = zero;
+    const float *nz = nullptr;
+    if (STYLED) {
+        if (g.noise) { nw = __ldg(g.noise_weight); nz = g.noise + (int64_t)n * g.noise_bstride; }
+        if (g.bias) bias4 = __ldg(reinterpret_cast<const float4 *>(g.bias) + c);
+    }
+    float4 sc2 = zero;
+    if ((STYLED && g.out2) || MODE == 2) sc2 = __ldg(reinterpret_cast<const float4 *>(g.scale2) + (int64_t)n * g.c4 + c);
+    float4 dot = zero;
+    const int64_t img_quads = (int64_t)n * g.out_h * g.out_w * g.c4 + c;    // this image / channel quad in an output-shaped tensor
+    const float4 *oth = (MODE == 2 && g.other) ? reinterpret_cast<const float4 *>(g.other) + img_quads : nullptr;
+    const float *smap = (STYLED && g.stylemap) ? g.stylemap + (int64_t)n * g.map_bstride : nullptr;
+    const int64_t map_plane = (int64_t)g.out_h * g.out_w;
+
+    auto load_row = [&](float4 (&row)[K + 1], const float4 *p, int y) {
+        const bool row_ok = y >= 0 && y < g.in_h;
+#pragma unroll
+        for (int b = 0; b < K + 1; ++b) row[b] = (row_ok && cok[b]) ? __ldg(p + (int64_t)b * g.c4) : zero;
+    };
+
+    float4 acc[K][2];                                      // ring of open output rows: slot of output row o is (o & 3)
+#pragma unroll
+    for (int s_ = 0; s_ < K; ++s_) { acc[s_][0] = zero; acc[s_][1] = zero; }
+    const int nsteps = oy1 - oy0 + K - 1;
+    float4 cur[K + 1], nxt[K + 1];
+    load_row(cur, src, iy);
+    for (int r0 = 0; r0 < nsteps; r0 += K) {
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+            const int r = r0 + u;
+            if (r < nsteps) {
+                if (PREFETCH && r + 1 < nsteps) load_row(nxt, src + row_stride, iy + 1);   // in flight while row r is consumed
+                if (sep) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        float4 h = zero;
+#pragma unroll
+                        for (int b = 0; b < K; ++b) {
+                            h.x = fmaf(cur[j + b].x, kh[b], h.x); h.y = fmaf(cur[j + b].y, kh[b], h.y);
+                            h.z = fmaf(cur[j + b].z, kh[b], h.z); h.w = fmaf(cur[j + b].w, kh[b], h.w);
+                        }
+#pragma unroll
+                        for (int a = 0; a < K; ++a) {          // input row r is tap row a of output row r - a
+                            float4 &d = acc[(u - a) & 3][j];
+                            d.x = fmaf(h.x, kv[a], d.x); d.y = fmaf(h.y, kv[a], d.y);
+                            d.z = fmaf(h.z, kv[a], d.z); d.w = fmaf(h.w, kv[a], d.w);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int a = 0; a < K; ++a)
+#pragma unroll
+                        for (int b = 0; b < K; ++b)
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                float4 &d = acc[(u - a) & 3][j];
+                                const float k = __ldg(taps + (K - 1 - a) * K + (K - 1 - b));    // (kept out of the register file)
+                                d.x = fmaf(cur[j + b].x, k, d.x); d.y = fmaf(cur[j + b].y, k, d.y);
+                                d.z = fmaf(cur[j + b].z, k, d.z); d.w = fmaf(cur[j + b].w, k, d.w);
+                            }
+                }
+                const int oy = oy0 + r - (K - 1);              // the output row this step completes: ring slot (u + 1) & 3
+                if (r >= K - 1) {
+                    float4 o[2] = {acc[(u + 1) & 3][0], acc[(u + 1) & 3][1]};
+                    const float4 pre[2] = {o[0], o[1]};
+                    const int64_t opix = (int64_t)oy * g.out_w + ox0;
+                    if (STYLED) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const bool in = (j == 0) || col1;
+                            float add = (nz && in) ? nw * __ldg(nz + opix + j) : 0.0f;
+                            float m0 = 1.0f;
+                            if (smap && in) { m0 = __ldg(smap + opix + j); add += __ldg(smap + map_plane + opix + j); }
+                            float v;
+                            v = fmaf(o[j].x, m0, add + bias4.x); o[j].x = ((v > 0.f) ? v : v * g.alpha) * g.gain;
+                            v = fmaf(o[j].y, m0, add + bias4.y); o[j].y = ((v > 0.f) ? v : v * g.alpha) * g.gain;
+                            v = fmaf(o[j].z, m0, add + bias4.z); o[j].z = ((v > 0.f) ? v : v * g.alpha) * g.gain;
+                            v = fmaf(o[j].w, m0, add + bias4.w); o[j].w = ((v > 0.f) ? v : v * g.alpha) * g.gain;
+                        }
+                    }
+                    const int64_t q = img_quads + opix * g.c4;      // channel-quad index of (n, oy, ox0, c)
+                    if (MODE == 2) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            if (j == 1 && !col1) break;
+                            if (oth) {
+                                const float4 tt = __ldg(oth + (opix + j) * g.c4);
+                                dot.x = fmaf(o[j].x, tt.x, dot.x); dot.y = fmaf(o[j].y, tt.y, dot.y);
+                                dot.z = fmaf(o[j].z, tt.z, dot.z); dot.w = fmaf(o[j].w, tt.w, dot.w);
+                            }
+                            o[j].x *= sc2.x; o[j].y *= sc2.y; o[j].z *= sc2.z; o[j].w *= sc2.w;
+                            if (g.op16) {
+                                reinterpret_cast<uint2 *>(out)[q + (int64_t)j * g.c4] = pack4_bf16(o[j].x, o[j].y, o[j].z, o[j].w);
+                            } else {
+                                reinterpret_cast<float4 *>(out)[q + (int64_t)j * g.c4] =
+                                    make_float4(round_tf32_(o[j].x), round_tf32_(o[j].y), round_tf32_(o[j].z), round_tf32_(o[j].w));
+                            }
+                        }
+                    } else {
+                        const bool keep_pre = STYLED && smap;
+                        reinterpret_cast<float4 *>(out)[q] = keep_pre ? pre[0] : o[0];
+                        if (col1) reinterpret_cast<float4 *>(out)[q + g.c4] = keep_pre ? pre[1] : o[1];
+                        if (STYLED && g.out2) {
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                if (j == 1 && !col1) break;
+                                const float a0 = o[j].x * sc2.x, a1 = o[j].y * sc2.y, a2 = o[j].z * sc2.z, a3 = o[j].w * sc2.w;
+                                if (g.op16) reinterpret_cast<uint2 *>(g.out2)[q + (int64_t)j * g.c4] = pack4_bf16(a0, a1, a2, a3);
+                                else reinterpret_cast<float4 *>(g.out2)[q + (int64_t)j * g.c4] =
+                                         make_float4(round_tf32_(a0), round_tf32_(a1), round_tf32_(a2), round_tf32_(a3));
+                            }
+                        }
+                    }
+                }
+                acc[(u + 1) & 3][0] = zero; acc[(u + 1) & 3][1] = zero;      // the slot now belongs to output row r + 1
+                src += row_stride;
+                ++iy;
+                if (PREFETCH) {
+#pragma unroll
+                    for (int b = 0; b < K + 1; ++b) cur[b] = nxt[b];
+                } else if (r + 1 < nsteps) {
+                    load_row(cur, src, iy);
+                }
+            }
+        }
+    }
+    if (MODE == 2 && g.dot) {   // one 128-bit reduction per thread into dot[n, 4c .. 4c+3]
+        float *dp = g.dot + ((int64_t)n * g.c4 + c) * 4;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dp), "f"(dot.x), "f"(dot.y), "f"(dot.z), "f"(dot.w) : "memory");
+    }
+}
+
 // ---- channels-last FIR through TMA-staged tiles (up = down = 1, 4x4 taps, C % 32 == 0, planes >= 32 x 32) --------------
 // Persistent CTAs walk the tile list; a tile is 16 x 32 output pixels x 32 channels.  A producer warp fetches the
 // {32 ch, 19, 35} input box of the next tile with ONE TMA instruction into a 2-stage shared-memory ring (zero fill
@@ -1217,7 +1428,14 @@ int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, in
         else if (mode == 1) fir_nhwc_ring_kernel<1, D, NT, MINB><<<nb, NT, 0, st>>>(out, x, taps, g);                   \
         else fir_nhwc_ring_kernel<0, D, NT, MINB><<<nb, NT, 0, st>>>(out, x, taps, g);                                  \
     } while (0)
-    if (ring == 1) SR_RING(2, 256, 2);
+    // default: the low-instruction-count separable kernel (fir_nhwc_sep_kernel); SR_FIR_SEP=0 = the 4x5 input-window kernel
+    static const char *sep_env = getenv("SR_FIR_SEP");
+    const bool use_sep = ring == 0 && !(sep_env && sep_env[0] == '0');
+    if (use_sep) {
+        if (mode == 2) fir_nhwc_sep_kernel<2><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
+        else if (mode == 1) fir_nhwc_sep_kernel<1><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
+        else fir_nhwc_sep_kernel<0><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
+    } else if (ring == 1) SR_RING(2, 256, 2);
     else if (ring == 2) SR_RING(3, 128, 3);
     else if (ring == 3) SR_RING(3, 256, 1);
     else if (ring == 4) SR_RING(4, 128, 2);
