@@ -12,9 +12,9 @@ weight frozen, so the weight-gradient GEMMs are skipped (fused.StyledLayerTC).  
 and its LPIPS backbone needs ImageNet VGG16 weights that are not available offline; the perceptual term here is the
 LPIPS formula (reference lpips/networks_basic.py:64-92: unit-normalised features of 5 VGG16 stages, squared difference,
 1x1 heads, spatial mean) over a VGG16-shaped stack with SEEDED RANDOM weights -- the same flops and memory traffic as
-LPIPS-VGG (reference lpips/pretrained_networks.py:97-137), not its metric values.  Its 3x3 conv + bias + ReLU layers with
-at least 64 input and 128 output channels (11 of the 13) run on this repository's tensor-core kernels too
-(fused.PlainConvTC with alpha = 0: forward + dgrad, no weight gradient); conv1_1 / conv1_2 (3 -> 64 -> 64) stay on cuDNN.
+LPIPS-VGG (reference lpips/pretrained_networks.py:97-137), not its metric values.  Its 3x3 conv + bias + ReLU layers whose
+channel counts are multiples of 128 (10 of the 13) run on this repository's tensor-core kernels too (fused.PlainConvTC with
+alpha = 0: forward + dgrad, no weight gradient); conv1_1 / conv1_2 / conv2_1 (3 -> 64 -> 64 -> 128) stay on cuDNN.
 The whole Adam step -- G forward, perceptual stack, backward to the latents, fused Adam -- is captured ONCE as a CUDA graph
 and replayed (`--no-graph` times the eager step).  Default: 64 faces per GPU, 100 timed Adam steps (a bounded sample of
 config 5's 1000; `--steps 1000` runs them all).
@@ -133,7 +133,7 @@ def main():
     latents = [w_mean.view(1, 1, 512).repeat(B, G.n_latent, 1).clone().requires_grad_(True) for _ in range(n_faces // B)]
     opts = [torch.optim.Adam([w], lr=args.lr, fused=True, capturable=True) for w in latents]
     loss_host = torch.empty(n_faces // B, B).pin_memory()
-    tc_convs = sum(1 for m in P.modules() if isinstance(m, ConvReLU) and m.weight.shape[1] >= 64 and m.weight.shape[0] >= 128)
+    tc_convs = sum(1 for m in P.modules() if isinstance(m, ConvReLU) and m.weight.shape[1] % 128 == 0 and m.weight.shape[0] % 128 == 0)
 
     def adam_step():
         """One Adam step for every face of this rank (chunks of B faces)."""
@@ -211,7 +211,7 @@ def main():
                        "global_faces": world * n_faces, "parallelism": f"dp{world} (face-sharded, no collective)",
                        "perceptual": f"LPIPS formula over a VGG16-shaped stack with seeded random weights (ImageNet weights "
                                      f"unavailable offline); {tc_convs} of its 13 conv layers on the tensor-core kernels, "
-                                     "conv1_1 / conv1_2 on cuDNN",
+                                     "conv1_1 / conv1_2 / conv2_1 on cuDNN",
                        "execution": execution,
                        "frozen_weights": "generator / perceptual weight-gradient GEMMs skipped"},
             "clocks": clocks.summary(), "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": None,

@@ -200,6 +200,7 @@ def run(args):
         G = DDP(G, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True)
         D = DDP(D, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True)
     B, tri = args.batch, face.tri
+    ema_params, g_all_params = list(g_ema.parameters()), list(g_mod.parameters())
     mean_path = torch.zeros((), device=dev)
     real_host = torch.randn(B, 3, args.size, args.size).pin_memory()
     loss_host = torch.zeros(4).pin_memory()
@@ -274,9 +275,9 @@ def run(args):
                     off += g.numel()
             g_optim.step()
             losses["path"] = path_loss.detach()
-        with torch.no_grad():                                           # EMA (train.py:100-104,358)
-            for pe, p in zip(g_ema.parameters(), g_mod.parameters()):
-                pe.mul_(0.999).add_(p.detach(), alpha=0.001)
+        with torch.no_grad():                                           # EMA (train.py:100-104,358), 2 launches instead of ~500
+            torch._foreach_mul_(ema_params, 0.999)
+            torch._foreach_add_(ema_params, g_all_params, alpha=0.001)
         if e2e:                                                         # the loop reads its scalars every iteration (train.py:360-372)
             loss_host[0].copy_(losses["d"], non_blocking=True)
             loss_host[1].copy_(losses["g"], non_blocking=True)

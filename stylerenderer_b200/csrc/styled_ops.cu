@@ -330,8 +330,9 @@ static int styled_bwd_prologue_any(float *ga, float *g_bias, float *g_noise_w, f
     // gradient (64 registers, no spill) takes the pass from 2.59 to 2.46 ms; the ToRGB combinations spilled at 80 registers
     // with two pixels per iteration and lost the gain (2.55 ms) -- they now take one pixel per iteration (no spill, 3 CTAs
     // per SM; ncu: the run-time kernel they replace sits at 45 % of DRAM, the spill-free specialised ones at 79 %).
-    // SR_PROLOGUE_SPEC=2 keeps them on the run-time kernel (A/B).
-    const bool spec_rgb = !(spec_env && spec_env[0] == '2');
+    // Measured again: 2.48 ms with them, 2.44 ms without (profiles/r2_prologue_spec.md) -- the specialised ToRGB kernels still
+    // spill 16-36 B at 80 registers, so they stay opt-in (SR_PROLOGUE_SPEC=1).
+    const bool spec_rgb = spec_env && spec_env[0] == '1';
     if (!(spec_env && spec_env[0] == '0') && !stylemap && (spec_rgb || !g_rgb)) {
         launched = true;
         switch (spec) {                                   // the combinations the chained generator produces

@@ -366,13 +366,12 @@ class PlainConvTC(Function):
 
 
 def plain_conv_supported(conv, x):
-    """EqualConv2d shapes the tensor-core path takes: 3x3 s1 p1, 3x3 s2 p0, 1x1 s2 p0 with channels in multiples of 128
-    (a frozen weight needs no weight-gradient GEMM: then cin % 64 is enough)."""
+    """EqualConv2d shapes the tensor-core path takes: 3x3 s1 p1, 3x3 s2 p0, 1x1 s2 p0 with channels in multiples of 128."""
     k = conv.weight.shape[2]
     cout, cin = conv.weight.shape[:2]
     kind = {(3, 1, 1): "s1", (3, 2, 0): "s2", (1, 2, 0): "p2"}.get((k, conv.stride, conv.padding))
-    need_w = conv.weight.requires_grad and torch.is_grad_enabled()
-    ok = tc.supported(cin, cout) and cin % 64 == 0 and (tc.wgrad_supported(cin, cout) or not need_w)
+    # forward GEMM: N = cout, dgrad GEMM: N = cin -> both multiples of 128 (which is also what the wgrad kernels need)
+    ok = tc.supported(cin, cout) and tc.supported(cout, cin)
     if kind is None or not (x.is_cuda and x.dtype == torch.float32 and ok):
         return None
     if kind == "s2" and (x.shape[2] % 2 == 0 or x.shape[3] % 2 == 0):      # dgrad = transposed conv: needs odd (2m+1) inputs
