@@ -271,6 +271,17 @@ def dominant_kernel_roofline(stats, peaks, total_ms, steps):
             gbs = by_n / (ms_n * 1e-3) / 1e9
             hbm[n] = {"ms_per_step": round(ms_n / steps, 4), "GBps": round(gbs, 1), "frac": round(gbs / peaks["hbm_gbs"], 4)}
     common["hbm_kernels"] = hbm
+    # every layer shape of the tensor-core kernels: ms per step and achieved TFLOP/s (which shapes lag, not only the mean)
+    shapes = {}
+    for n, kcalls in stats.items():
+        if not any(algorithmic_flops(n, a) for a, _ in kcalls[:1]):
+            continue
+        for a, m in kcalls:
+            g = shapes.setdefault(launch_signature(n, a), [0, 0.0, 0])
+            g[0] += 1; g[1] += m; g[2] += algorithmic_flops(n, a)
+    common["tensor_shapes"] = {k: {"n": round(v[0] / steps, 2), "ms_per_step": round(v[1] / steps, 4),
+                                   "TFLOPs": round(v[2] / (v[1] * 1e-3) / 1e12, 1) if v[1] > 0 else None}
+                               for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1])}
     fl_all = sum(algorithmic_flops(name, a) for a, _ in all_calls)
     if fl_all:
         # denominator: the dense TF32 rate cuBLAS sustains on this GPU in this run (measure_tf32_peak), because these

@@ -192,7 +192,10 @@ class GeneratorWithMap(Generator):                    # reference model.py:188-2
         """The rasterised normal map at every resolution 4, 8, ..., size as [B,3,r,r] views (reference model.py:260-270
         calls rasterize once per resolution; here all of them come from one pyramid launch set, same values)."""
         sizes = [2 ** i for i in range(2, self.log_size + 1)]
-        if isinstance(mesh, NormalMaps):                 # already rendered by the fused front-end (mesh.normal_pyramid)
+        # already rendered by the fused front-end (mesh.normal_pyramid).  DistributedDataParallel rebuilds its inputs as
+        # plain lists, so a list of [b,3,r,r] tensors is recognised by structure, not only by type
+        if isinstance(mesh, NormalMaps) or (isinstance(mesh, (list, tuple)) and len(mesh) == len(sizes)
+                                            and all(torch.is_tensor(m) and m.dim() == 4 for m in mesh)):
             assert [m.shape[-1] for m in mesh] == sizes, "NormalMaps must hold one map per resolution 4 .. size"
             return list(mesh)
         pyramid_ok = mesh[0].dtype == torch.float32 and len(sizes) <= MAX_LEVELS
