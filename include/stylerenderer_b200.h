@@ -396,6 +396,27 @@ int sr_mesh_normal_pyramid_f32(int64_t batch, int64_t nv, int64_t nf, const floa
                                const float *pose, const int64_t *tris, float *verts_out, float *normals, int n_levels,
                                const sr_raster_level *levels, uint64_t *keys, float eps, void *stream);
 
+/* The style-map network of GeneratorWithMap -- ResBlock(3 -> cout, downsample = False), cout = 2 or 4 (reference
+ * model.py:194-216 builds them, model.py:262,271-275 runs them on the rasterised normal map of every resolution; the block
+ * is reference layers.py:379-391 over the ConvLayers of layers.py:341-378) -- as ONE pass over [batch, 3, h, w] planes:
+ *   y1  = lrelu(conv3x3(x,  w1 / sqrt(27)) + b1_conv + b1_act) * gain
+ *   y2  = lrelu(conv3x3(y1, w2 / sqrt(27)) + b2_conv + b2_act) * gain
+ *   out = (y2 + conv1x1(x, w_skip / sqrt(3))) / sqrt(2)                       out: [batch, cout, h, w] planes
+ * Weights are the raw parameters (w1 [3,3,3,3], w2 [cout,3,3,3], w_skip [cout,3,1,1]); bias pointers may be NULL.
+ * Replaces three cuDNN convolutions and five elementwise passes per block (and their autograd graph). */
+int sr_stylemap_resblock_forward_f32(float *out, const float *x, const float *w1, const float *b1_conv, const float *b1_act,
+                                     const float *w2, const float *b2_conv, const float *b2_act, const float *w_skip,
+                                     int64_t batch, int cin, int cout, int64_t h, int64_t w, float alpha, float gain,
+                                     void *stream);
+/* Parameter gradients of the block above from grad_out [batch, cout, h, w] and x (y1 and both activation masks are
+ * recomputed): grads = [d w1 (81) | d b1 (3) | d w2 (27 cout) | d b2 (cout) | d w_skip (3 cout)] floats, overwritten.
+ * d b1 / d b2 are the gradient of BOTH biases of the layer (conv bias and activation bias enter as a sum).
+ * The gradient with respect to x is not produced. */
+int sr_stylemap_resblock_backward_f32(float *grads, const float *grad_out, const float *x, const float *w1,
+                                      const float *b1_conv, const float *b1_act, const float *w2, const float *b2_conv,
+                                      const float *b2_act, const float *w_skip, int64_t batch, int cin, int cout,
+                                      int64_t h, int64_t w, float alpha, float gain, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

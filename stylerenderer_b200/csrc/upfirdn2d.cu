@@ -1238,6 +1238,285 @@ fir_nhwc_tma_kernel(float *__restrict__ out, const __grid_constant__ CUtensorMap
     }
 }
 
+// Flipped taps tk[a][b] = taps[3-a][3-b] of a 4 x 4 FIR and, when the matrix is rank 1 (every FIR the model builds,
+// reference layers.py:7-12), its factorisation tk[a][b] = kv[a] * kh[b] through the largest tap.  Returns whether it is.
+__device__ __forceinline__ bool fir_rank1_taps(const float *__restrict__ taps, float (&kv)[4], float (&kh)[4])
+{
+    constexpr int K = 4;
+    float tk[K][K];
+#pragma unroll
+    for (int a = 0; a < K; ++a)
+#pragma unroll
+        for (int b = 0; b < K; ++b) tk[a][b] = __ldg(taps + (K - 1 - a) * K + (K - 1 - b));
+    int pa = 0, pb = 0;
+    float best = 0.0f;
+#pragma unroll
+    for (int a = 0; a < K; ++a)
+#pragma unroll
+        for (int b = 0; b < K; ++b)
+            if (fabsf(tk[a][b]) > best) { best = fabsf(tk[a][b]); pa = a; pb = b; }
+    float pivot = 1.0f;
+#pragma unroll
+    for (int a = 0; a < K; ++a)
+#pragma unroll
+        for (int b = 0; b < K; ++b)
+            if (a == pa && b == pb) pivot = tk[a][b];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        kv[a] = 0.0f; kh[a] = 0.0f;
+#pragma unroll
+        for (int b = 0; b < K; ++b) {
+            if (b == pb) kv[a] = tk[a][b];
+            if (b == pa) kh[a] = tk[b][a] / pivot;
+        }
+    }
+    bool sep = best > 0.0f;
+#pragma unroll
+    for (int a = 0; a < K; ++a)
+#pragma unroll
+        for (int b = 0; b < K; ++b) sep = sep && fabsf(kv[a] * kh[b] - tk[a][b]) <= 1e-6f * best;
+    return sep;
+}
+
+// ---- channels-last FIR, row-streaming through a deep TMA ring (default for planes >= 32 x 32, C % 32 == 0) -------------
+// ncu on the generator step (profiles/r2_ncu_hbm_passes.md): the register-window kernels above issue ~270 thread
+// instructions per float4 output and saturate the ISSUE slots at 0.5-0.6 of the copy bandwidth; the tile-at-a-time TMA
+// kernel waits for a whole 85 KB tile behind a 2-deep ring.  This form streams DOWN a column strip instead:
+//   * work item = (image, block of 32 channels, strip of 32 output columns, segment of ~64 output rows); persistent CTAs
+//     (2 per SM) walk the item list; the producer lane runs ahead across item boundaries;
+//   * the producer fetches 4 input rows x 35 pixels x 128 B per stage with ONE TMA box (zero fill outside the plane = the
+//     FIR padding: no bounds test on the load side) into a 6-deep ring -> ~105 KB in flight per CTA, 210 KB per SM;
+//   * consumer thread = (output column, channel quad): per input row 4 conflict-free LDS.128, a 4-tap row filter, then ONE
+//     FMA per open output row -- the four open rows live in a register ring whose slot index is a compile-time constant of
+//     the 4-row stage loop; every step retires one output row: ~75 instructions per float4 output (32 FFMA);
+//   * each warp stores 4 pixels x 128 contiguous bytes (whole lines); HBM sees each input byte 1.09x (3 halo columns per
+//     32) + 3 halo rows per segment.
+constexpr int FS_W = 32, FS_C = 32, FS_ROWS = 4, FS_MAX_STAGES = 6;
+constexpr int FS_IW = FS_W + 3;
+constexpr int FS_X_BYTES = FS_ROWS * FS_IW * FS_C * 4;              // 17920: the input box of a stage
+constexpr int FS_NOISE_BYTES = FS_ROWS * FS_W * 4;                  // 512: noise[n, 4 output rows, 32 columns] (styled tail)
+constexpr int FS_MAP_BYTES = 2 * FS_NOISE_BYTES;                    // 1024: the two style-map planes of the same pixels
+constexpr int FS_CONSUMERS = 256;
+
+struct FirStreamGeom {
+    int in_h, in_w, out_h, out_w, c, cblocks, xtiles, nseg, seg_rows, total_items, pad_x0, pad_y0;
+    FastDiv div_cb, div_xt, div_seg;
+    const float *noise, *noise_weight, *bias;
+    long long noise_bstride;
+    float alpha, gain;
+    float *out2;
+    const float *scale2, *other;
+    float *dot;
+    const float *stylemap;
+    long long map_bstride;
+    int op16;
+    int stages, stage_bytes;      // ring depth (6, or 5 with a style map) and bytes per stage (input box + side boxes)
+    int side_tma;                 // bit 0: noise rows arrive through the ring (tmap_nz), bit 1: style-map rows (tmap_map)
+};
+
+// The per-pixel side inputs of the styled tail (noise, style map) ride the same ring as the input rows: fetched with
+// per-thread loads they sat between the filter and the stores of every row (ncu: half of all stall samples on the
+// `noise_weight * noise` multiply, 0.55 of the copy bandwidth against 0.89 for the tail without side inputs).
+template <int MODE>     // MODE 0 plain, 1 styled forward tail (+ optional out2 / style map), 2 scale(+dot) backward tail
+__global__ void __launch_bounds__(FS_CONSUMERS + 32, 2)
+fir_nhwc_stream_kernel(float *__restrict__ out, const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_nz,
+                       const __grid_constant__ CUtensorMap tmap_map, const float *__restrict__ taps, const FirStreamGeom g)
+{
+    extern __shared__ uint8_t fs_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(fs_raw) + 127) & ~(uintptr_t)127);
+    const int FS_STAGES = g.stages, FS_STAGE_BYTES = g.stage_bytes;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + FS_STAGES * FS_STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + FS_MAX_STAGES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool nz_tma = MODE == 1 && (g.side_tma & 1), map_tma = MODE == 1 && (g.side_tma & 2);
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_x) : "memory");
+        for (int s = 0; s < FS_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&full_bar[s])), "r"(1u) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&empty_bar[s])), "r"((uint32_t)(FS_CONSUMERS / 32)) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == FS_CONSUMERS / 32) {                   // ===== producer warp (one lane)
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            for (uint32_t T = blockIdx.x; T < (uint32_t)g.total_items; T += gridDim.x) {
+                uint32_t t = T, cb, xt, seg, n;
+                g.div_cb.divmod(t, t, cb);
+                g.div_xt.divmod(t, t, xt);
+                g.div_seg.divmod(t, n, seg);
+                const int oy_start = seg * g.seg_rows;
+                const int oy_end = min(g.out_h, oy_start + g.seg_rows);
+                const int nstages = (oy_end - oy_start + 3 + FS_ROWS - 1) / FS_ROWS;
+                const int cx = (int)(xt * FS_W) - g.pad_x0;
+                int cy = oy_start - g.pad_y0;
+                const uint32_t tx_bytes = FS_X_BYTES + (nz_tma ? FS_NOISE_BYTES : 0) + (map_tma ? FS_MAP_BYTES : 0);
+                for (int k = 0; k < nstages; ++k, cy += FS_ROWS) {
+                    ft_mbar_wait(&empty_bar[s], ph ^ 1);
+                    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&full_bar[s]);
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem + s * FS_STAGE_BYTES);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(tx_bytes) : "memory");
+                    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                                 :: "r"(dst), "l"(&tmap_x), "r"(bar), "r"((int)(cb * FS_C)), "r"(cx), "r"(cy), "r"((int)n) : "memory");
+                    const int oy0 = oy_start + k * FS_ROWS - 3;          // first output row this stage retires (rows < 0: zero fill, unused)
+                    if (nz_tma)
+                        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                                     :: "r"(dst + FS_X_BYTES), "l"(&tmap_nz), "r"(bar), "r"((int)(xt * FS_W)), "r"(oy0),
+                                        "r"(g.noise_bstride ? (int)n : 0) : "memory");
+                    if (map_tma)
+                        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                                     :: "r"(dst + FS_X_BYTES + FS_NOISE_BYTES), "l"(&tmap_map), "r"(bar), "r"((int)(xt * FS_W)), "r"(oy0),
+                                        "r"(0), "r"((int)n) : "memory");
+                    if (++s == FS_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers: thread = (output column of the strip, channel quad)
+    constexpr int K = 4;
+    float kv[K], kh[K];
+    const bool sep = fir_rank1_taps(taps, kv, kh);
+    const int quad = threadIdx.x & 7, col = threadIdx.x >> 3;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    float nw = 0.0f;
+    if (MODE == 1 && g.noise) nw = __ldg(g.noise_weight);
+    const long long map_plane = (long long)g.out_h * g.out_w;
+
+    uint32_t s = 0, ph = 0;
+    for (uint32_t T = blockIdx.x; T < (uint32_t)g.total_items; T += gridDim.x) {
+        uint32_t t = T, cb, xt, seg, n;
+        g.div_cb.divmod(t, t, cb);
+        g.div_xt.divmod(t, t, xt);
+        g.div_seg.divmod(t, n, seg);
+        const int ox = xt * FS_W + col;
+        const bool col_ok = ox < g.out_w;
+        const int oy_start = seg * g.seg_rows;
+        const int oy_end = min(g.out_h, oy_start + g.seg_rows);
+        const int nstages = (oy_end - oy_start + 3 + FS_ROWS - 1) / FS_ROWS;
+        const int ch = cb * FS_C + 4 * quad;
+        float4 bias4 = zero, sc2 = zero;
+        if (MODE == 1 && g.bias) bias4 = __ldg(reinterpret_cast<const float4 *>(g.bias + ch));
+        if (MODE == 2) sc2 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if ((MODE == 1 && g.out2) || (MODE == 2 && g.scale2)) sc2 = __ldg(reinterpret_cast<const float4 *>(g.scale2 + (long long)n * g.c + ch));
+        const long long pix0 = (long long)n * g.out_h * g.out_w;          // first output pixel of the image
+        const float *nz = (MODE == 1 && g.noise) ? g.noise + (long long)n * g.noise_bstride : nullptr;
+        const float *smap = (MODE == 1 && g.stylemap) ? g.stylemap + (long long)n * g.map_bstride : nullptr;
+        float4 dot = zero;
+        float4 acc[K];
+#pragma unroll
+        for (int a = 0; a < K; ++a) acc[a] = zero;
+
+        for (int k = 0; k < nstages; ++k) {
+            // side inputs of the four output rows this stage retires, fetched BEFORE the wait for the stage: their latency
+            // overlaps the barrier wait instead of sitting between the filter and the stores of every row
+            float add_[FS_ROWS], m0_[FS_ROWS];
+            float4 tt_[FS_ROWS];
+#pragma unroll
+            for (int u = 0; u < FS_ROWS; ++u) {
+                const int oy = oy_start + k * FS_ROWS + u - (K - 1);
+                const bool emit = (k > 0 || u == K - 1) && oy < oy_end && col_ok;
+                const int opix = oy * g.out_w + ox;
+                add_[u] = 0.0f; m0_[u] = 1.0f; tt_[u] = zero;
+                if (MODE == 1 && emit) {                       // (per-thread loads only when the side boxes could not be built)
+                    if (nz && !nz_tma) add_[u] = nw * __ldg(nz + opix);
+                    if (smap && !map_tma) { m0_[u] = __ldg(smap + opix); add_[u] += __ldg(smap + map_plane + opix); }
+                }
+                if (MODE == 2 && emit && g.other) tt_[u] = __ldg(reinterpret_cast<const float4 *>(g.other + (pix0 + opix) * g.c + ch));
+            }
+            ft_mbar_wait(&full_bar[s], ph);
+            const float4 *stg = reinterpret_cast<const float4 *>(smem + s * FS_STAGE_BYTES) + col * (FS_C / 4) + quad;
+#pragma unroll
+            for (int u = 0; u < FS_ROWS; ++u) {
+                const int oy = oy_start + k * FS_ROWS + u - (K - 1);        // the output row this step completes
+                const bool emit = (k > 0 || u == K - 1) && oy < oy_end && col_ok;
+                const int opix = oy * g.out_w + ox;
+                float add = add_[u], m0 = m0_[u];
+                const float4 tt = tt_[u];
+                if (MODE == 1) {
+                    const float *side = reinterpret_cast<const float *>(smem + s * FS_STAGE_BYTES + FS_X_BYTES) + u * FS_W + col;
+                    if (nz_tma) add = nw * side[0];
+                    if (map_tma) { m0 = side[FS_NOISE_BYTES / 4]; add += side[FS_NOISE_BYTES / 4 + FS_ROWS * FS_W]; }
+                }
+                float4 cur[K];
+#pragma unroll
+                for (int b = 0; b < K; ++b) cur[b] = stg[(u * FS_IW + b) * (FS_C / 4)];
+                if (sep) {
+                    float4 h = zero;
+#pragma unroll
+                    for (int b = 0; b < K; ++b) {
+                        h.x = fmaf(cur[b].x, kh[b], h.x); h.y = fmaf(cur[b].y, kh[b], h.y);
+                        h.z = fmaf(cur[b].z, kh[b], h.z); h.w = fmaf(cur[b].w, kh[b], h.w);
+                    }
+#pragma unroll
+                    for (int a = 0; a < K; ++a) {              // input row r is tap row a of output row r - a
+                        float4 &d = acc[(u - a) & 3];
+                        d.x = fmaf(h.x, kv[a], d.x); d.y = fmaf(h.y, kv[a], d.y);
+                        d.z = fmaf(h.z, kv[a], d.z); d.w = fmaf(h.w, kv[a], d.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int a = 0; a < K; ++a)
+#pragma unroll
+                        for (int b = 0; b < K; ++b) {
+                            float4 &d = acc[(u - a) & 3];
+                            const float kk = __ldg(taps + (K - 1 - a) * K + (K - 1 - b));
+                            d.x = fmaf(cur[b].x, kk, d.x); d.y = fmaf(cur[b].y, kk, d.y);
+                            d.z = fmaf(cur[b].z, kk, d.z); d.w = fmaf(cur[b].w, kk, d.w);
+                        }
+                }
+                if (emit) {
+                    float4 o = acc[(u + 1) & 3];
+                    const float4 pre = o;
+                    float *op = out + (pix0 + opix) * g.c + ch;
+                    if (MODE == 1) {
+                        float v;
+                        v = fmaf(o.x, m0, add + bias4.x); o.x = ((v > 0.f) ? v : v * g.alpha) * g.gain;
+                        v = fmaf(o.y, m0, add + bias4.y); o.y = ((v > 0.f) ? v : v * g.alpha) * g.gain;
+                        v = fmaf(o.z, m0, add + bias4.z); o.z = ((v > 0.f) ? v : v * g.alpha) * g.gain;
+                        v = fmaf(o.w, m0, add + bias4.w); o.w = ((v > 0.f) ? v : v * g.alpha) * g.gain;
+                        *reinterpret_cast<float4 *>(op) = smap ? pre : o;
+                        if (g.out2) {
+                            const float a0 = o.x * sc2.x, a1 = o.y * sc2.y, a2 = o.z * sc2.z, a3 = o.w * sc2.w;
+                            if (g.op16) reinterpret_cast<uint2 *>(g.out2)[((pix0 + opix) * g.c + ch) >> 2] = pack4_bf16(a0, a1, a2, a3);
+                            else *reinterpret_cast<float4 *>(g.out2 + (pix0 + opix) * g.c + ch) =
+                                     make_float4(round_tf32_(a0), round_tf32_(a1), round_tf32_(a2), round_tf32_(a3));
+                        }
+                    } else if (MODE == 2) {
+                        dot.x = fmaf(o.x, tt.x, dot.x); dot.y = fmaf(o.y, tt.y, dot.y);
+                        dot.z = fmaf(o.z, tt.z, dot.z); dot.w = fmaf(o.w, tt.w, dot.w);
+                        o.x *= sc2.x; o.y *= sc2.y; o.z *= sc2.z; o.w *= sc2.w;
+                        if (g.op16) reinterpret_cast<uint2 *>(out)[((pix0 + opix) * g.c + ch) >> 2] = pack4_bf16(o.x, o.y, o.z, o.w);
+                        else *reinterpret_cast<float4 *>(op) =
+                                 make_float4(round_tf32_(o.x), round_tf32_(o.y), round_tf32_(o.z), round_tf32_(o.w));
+                    } else {
+                        *reinterpret_cast<float4 *>(op) = o;
+                    }
+                }
+                acc[(u + 1) & 3] = zero;                       // the slot now belongs to the output row three steps ahead
+            }
+            __syncwarp();                                      // this warp no longer reads the stage
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"((uint32_t)__cvta_generic_to_shared(&empty_bar[s])) : "memory");
+            if (++s == FS_STAGES) { s = 0; ph ^= 1; }
+        }
+        if (MODE == 2 && g.dot) {   // lanes with equal channel quad (l, l^8, l^16, l^24) -> one 128-bit reduction per quad and warp
+#pragma unroll
+            for (int o = 8; o < 32; o <<= 1) {
+                dot.x += __shfl_xor_sync(0xffffffffu, dot.x, o); dot.y += __shfl_xor_sync(0xffffffffu, dot.y, o);
+                dot.z += __shfl_xor_sync(0xffffffffu, dot.z, o); dot.w += __shfl_xor_sync(0xffffffffu, dot.w, o);
+            }
+            if (lane < 8) {
+                float *dp = g.dot + (long long)n * g.c + ch;
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dp), "f"(dot.x), "f"(dot.y), "f"(dot.z), "f"(dot.w) : "memory");
+            }
+        }
+    }
+}
+
 // ---- generic: one thread per output element, any geometry ---------------------------------------
 struct GenericGeom {
     int64_t major, minor, total;
@@ -1389,12 +1668,94 @@ int launch_nhwc_tma(float *out, const float *x, const float *taps, int64_t major
     return launch(fir_nhwc_tma_kernel<0, 32, 4>, 0);
 }
 
+// Streaming path of launch_nhwc (fir_nhwc_stream_kernel): returns SR_ERR_UNSUPPORTED when the shape does not qualify.
+int launch_nhwc_stream(float *out, const float *x, const float *taps, int64_t major, int in_h, int in_w, int oh, int ow,
+                       int64_t minor, int pad_x0, int pad_y0, int mode, const float *noise, long long noise_bstride,
+                       const float *noise_weight, const float *bias, float alpha, float gain, cudaStream_t st, float *out2,
+                       const float *scale2, const float *other, float *dot, const float *stylemap, long long map_bstride, int op16)
+{
+    const char *off = getenv("SR_FIR_STREAM");                 // A/B switch, read per call: 0 = the register-window kernels
+    if (off && off[0] == '0') return SR_ERR_UNSUPPORTED;
+    if (minor % FS_C != 0 || oh < 32 || ow < 32 || (reinterpret_cast<uintptr_t>(x) & 15u)) return SR_ERR_UNSUPPORTED;
+    if ((int64_t)major * oh * ow * minor >= (1ll << 40)) return SR_ERR_UNSUPPORTED;
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return SR_ERR_UNSUPPORTED;
+    CUtensorMap tm;
+    cuuint64_t dims[4] = {(cuuint64_t)minor, (cuuint64_t)in_w, (cuuint64_t)in_h, (cuuint64_t)major};
+    cuuint64_t strides[3] = {(cuuint64_t)minor * 4, (cuuint64_t)in_w * minor * 4, (cuuint64_t)in_h * in_w * minor * 4};
+    cuuint32_t box[4] = {FS_C, FS_IW, FS_ROWS, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return SR_ERR_UNSUPPORTED;
+    FirStreamGeom g;
+    g.in_h = in_h; g.in_w = in_w; g.out_h = oh; g.out_w = ow; g.c = (int)minor; g.cblocks = (int)(minor / FS_C);
+    g.xtiles = (ow + FS_W - 1) / FS_W;
+    g.nseg = (oh + 32) / 64 > 0 ? (oh + 32) / 64 : 1;           // segments of ~64 output rows (3 halo rows each)
+    g.seg_rows = (oh + g.nseg - 1) / g.nseg;
+    const int64_t total = (int64_t)major * g.nseg * g.xtiles * g.cblocks;
+    if (total >= 0x7fffffffll) return SR_ERR_UNSUPPORTED;
+    g.total_items = (int)total; g.pad_x0 = pad_x0; g.pad_y0 = pad_y0;
+    g.div_cb = FastDiv((uint32_t)g.cblocks); g.div_xt = FastDiv((uint32_t)g.xtiles); g.div_seg = FastDiv((uint32_t)g.nseg);
+    g.noise = noise; g.noise_weight = noise_weight; g.bias = bias; g.noise_bstride = noise_bstride;
+    g.alpha = alpha; g.gain = gain; g.out2 = out2; g.scale2 = scale2; g.other = other; g.dot = dot;
+    g.stylemap = stylemap; g.map_bstride = map_bstride; g.op16 = op16;
+    // side inputs of the styled tail through the ring: [b, oh, ow] noise rows and [b, 2, oh, ow] style-map rows as TMA boxes
+    // of 4 rows x 32 columns (rows must be 16-byte multiples; otherwise the consumers load them per thread)
+    CUtensorMap tm_nz = tm, tm_map = tm;
+    g.side_tma = 0;
+    if (mode == 1 && noise && ow % 4 == 0 && (reinterpret_cast<uintptr_t>(noise) & 15u) == 0 && noise_bstride % 4 == 0) {
+        const cuuint64_t nb = noise_bstride ? (cuuint64_t)major : 1;
+        cuuint64_t d3[3] = {(cuuint64_t)ow, (cuuint64_t)oh, nb};
+        cuuint64_t s3[2] = {(cuuint64_t)ow * 4, (cuuint64_t)(noise_bstride ? noise_bstride : (long long)oh * ow) * 4};
+        cuuint32_t b3[3] = {FS_W, FS_ROWS, 1}, e3[3] = {1, 1, 1};
+        if (enc(&tm_nz, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(noise), d3, s3, b3, e3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            g.side_tma |= 1;
+    }
+    if (mode == 1 && stylemap && ow % 4 == 0 && (reinterpret_cast<uintptr_t>(stylemap) & 15u) == 0 && map_bstride % 4 == 0 &&
+        map_bstride >= 2ll * oh * ow) {
+        cuuint64_t d4[4] = {(cuuint64_t)ow, (cuuint64_t)oh, 2, (cuuint64_t)major};
+        cuuint64_t s4[3] = {(cuuint64_t)ow * 4, (cuuint64_t)oh * ow * 4, (cuuint64_t)map_bstride * 4};
+        cuuint32_t b4[4] = {FS_W, FS_ROWS, 2, 1}, e4[4] = {1, 1, 1, 1};
+        if (enc(&tm_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(stylemap), d4, s4, b4, e4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            g.side_tma |= 2;
+    }
+    g.stage_bytes = FS_X_BYTES + ((g.side_tma & 1) ? FS_NOISE_BYTES : 0) + ((g.side_tma & 2) ? FS_MAP_BYTES : 0);
+    if ((g.side_tma & 2) && !(g.side_tma & 1)) g.stage_bytes += FS_NOISE_BYTES;      // fixed offsets inside a stage
+    g.stages = (g.side_tma & 2) ? 5 : FS_MAX_STAGES;                                 // two CTAs per SM must fit 227 KB
+    const size_t smem = 128 + (size_t)g.stages * g.stage_bytes + 2 * FS_MAX_STAGES * sizeof(uint64_t);
+    const size_t smem_max = 128 + (size_t)FS_MAX_STAGES * (FS_X_BYTES + FS_NOISE_BYTES) + 2 * FS_MAX_STAGES * sizeof(uint64_t);
+    static_assert(5 * (FS_X_BYTES + FS_NOISE_BYTES + FS_MAP_BYTES) <= FS_MAX_STAGES * (FS_X_BYTES + FS_NOISE_BYTES), "ring sizes");
+    const int slots = 2 * kNumSMs;
+    const int grid = total < slots ? (int)total : slots;
+    static bool configured[3] = {};
+    auto launch = [&](auto kern, int idx) -> int {
+        if (!configured[idx]) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess) return SR_ERR_UNSUPPORTED;
+            configured[idx] = true;
+        }
+        kern<<<grid, FS_CONSUMERS + 32, smem, st>>>(out, tm, tm_nz, tm_map, taps, g);
+        return SR_OK;
+    };
+    if (mode == 2) return launch(fir_nhwc_stream_kernel<2>, 2);
+    if (mode == 1) return launch(fir_nhwc_stream_kernel<1>, 1);
+    return launch(fir_nhwc_stream_kernel<0>, 0);
+}
+
 int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, int in_h, int in_w, int oh, int ow,
                 int64_t minor, int pad_x0, int pad_y0, bool styled, const float *noise, long long noise_bstride,
                 const float *noise_weight, const float *bias, float alpha, float gain, cudaStream_t st,
                 float *out2 = nullptr, const float *scale2 = nullptr, const float *other = nullptr, float *dot = nullptr,
                 const float *stylemap = nullptr, long long map_bstride = 0, int op16 = 0)
 {
+    {
+        const int mode = (dot || (!styled && scale2)) ? 2 : (styled ? 1 : 0);
+        if (launch_nhwc_stream(out, x, taps, major, in_h, in_w, oh, ow, minor, pad_x0, pad_y0, mode, noise, noise_bstride, noise_weight,
+                               bias, alpha, gain, st, out2, scale2, other, dot, stylemap, map_bstride, op16) == SR_OK)
+            return SR_OK;
+    }
     if (pad_x0 == pad_y0 && !stylemap && !op16) {
         const int rc = (!dot && !styled && scale2) ? SR_ERR_UNSUPPORTED :
                        launch_nhwc_tma(out, x, taps, major, in_h, in_w, oh, ow, minor, pad_x0, dot ? 2 : (styled ? 1 : 0), noise,

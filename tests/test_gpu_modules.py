@@ -325,21 +325,28 @@ def test_fused_pass_kernels():
         torch.testing.assert_close(dt, (f * other).sum((1, 2)), rtol=1e-4, atol=1e-2)
 
 
-@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4", "5"])
+@pytest.mark.parametrize("variant", ["stream", "0", "1", "2", "3", "4", "5"])
 @pytest.mark.parametrize("rank1", [True, False])
 def test_fir_nhwc_kernel_variants_vs_oracle(variant, rank1, monkeypatch):
-    """Every channels-last FIR kernel (SR_FIR_RING: 0 = input-window kernel, the default; 1-5 = row-streaming ring kernels
-    with 1-4 input rows in flight per thread) in its three modes -- plain, styled tail, scale(+dot) tail -- against the oracle's upfirdn2d
+    """Every channels-last FIR kernel ("stream" = the default: TMA row-streaming kernel for planes >= 32 x 32 with C % 32 == 0,
+    register-window kernel below that; SR_FIR_STREAM=0 + SR_FIR_RING: 0 = register-window kernels everywhere, 1-5 = per-thread
+    row-streaming ring kernels) in its three modes -- plain, styled tail, scale(+dot) tail -- against the oracle's upfirdn2d
     (oracle/sr_oracle.c, reference op/upfirdn2d.py:159-200), with the model's rank-1 taps (separable form inside the
-    ring kernels, reference layers.py:7-12) and with general, asymmetric taps (2-D form)."""
+    kernels, reference layers.py:7-12) and with general, asymmetric taps (2-D form).  Shapes cover several column strips
+    with a ragged last strip (65, 35 wide), several row segments (129 rows) and the sub-32 fall-back."""
     from oracle import cpu as O
     from stylerenderer_b200 import tc_conv as tc
     from stylerenderer_b200.op import upfirdn2d_raw
     from make_golden import seeded
-    monkeypatch.setenv("SR_FIR_RING", variant)
+    if variant != "stream":
+        monkeypatch.setenv("SR_FIR_STREAM", "0")
+        monkeypatch.setenv("SR_FIR_RING", variant)
     k1 = torch.tensor([1., 3., 3., 1.])
     k = (torch.outer(k1, k1) / 64 * 4) if rank1 else seeded((4, 4), 16)
-    for (b, h, w, c) in [(2, 8, 8, 128), (3, 5, 7, 256), (1, 33, 35, 512), (2, 64, 64, 128), (1, 3, 2, 4)]:
+    shapes = [(2, 8, 8, 128), (3, 5, 7, 256), (1, 33, 35, 512), (2, 64, 64, 128), (1, 3, 2, 4)]
+    if variant == "stream":
+        shapes += [(1, 70, 65, 64), (2, 129, 40, 32), (1, 32, 32, 96)]
+    for (b, h, w, c) in shapes:
         t = seeded((b, h + 1, w + 1, c), 17)
         noise, nw = seeded((b, 1, h, w), 18), torch.tensor([0.4])
         bias, d = seeded((c,), 19), seeded((b, c), 20).abs() + 0.5
@@ -362,6 +369,26 @@ def test_fir_nhwc_kernel_variants_vs_oracle(variant, rank1, monkeypatch):
         torch.testing.assert_close(dt.cpu(), (f2 * other).sum((1, 2)), rtol=1e-4, atol=1e-2)
         o2, none = tc.blur_scaledot(t.cuda(), k.cuda(), (2, 2), d.cuda())
         assert none is None and torch.equal(o2, o)
+        gbc = tc.blur_styled(t.cuda(), k.cuda(), (1, 1), noise[:1].cuda(), nw.cuda(), bias.cuda(), 0.2, 2 ** 0.5)   # broadcast noise
+        refb = f1 + nw * noise[:1].view(1, h, w, 1) + bias
+        torch.testing.assert_close(gbc.cpu(), torch.where(refb > 0, refb, refb * 0.2) * 2 ** 0.5, **tol)
+        # StyledMapConv tail: y = lrelu(fir * map0 + map1 + noise + bias) * gain; `out` keeps the FIR output, out2 sees y
+        smap = seeded((b, 2, h, w), 22)
+        refm = f1 * smap[:, 0].view(b, h, w, 1) + smap[:, 1].view(b, h, w, 1) + nw * noise.view(b, h, w, 1) + bias
+        refm = torch.where(refm > 0, refm, refm * 0.2) * 2 ** 0.5
+        gm1, gm2 = tc.blur_styled(t.cuda(), k.cuda(), (1, 1), noise.cuda(), nw.cuda(), bias.cuda(), 0.2, 2 ** 0.5,
+                                  scale2=d.cuda(), stylemap=smap.cuda())
+        torch.testing.assert_close(gm1.cpu(), f1, **tol)
+        torch.testing.assert_close(gm2.cpu(), refm * d.view(b, 1, 1, c), rtol=6e-4, atol=2e-5)
+        # bfloat16 GEMM operands (tcgen05 kind::f16): the fp32 output is unchanged, the operand is rounded to bf16
+        with tc.precision("bf16"):
+            gb1, gb2 = tc.blur_styled(t.cuda(), k.cuda(), (1, 1), noise.cuda(), nw.cuda(), bias.cuda(), 0.2, 2 ** 0.5,
+                                      scale2=d.cuda())
+            ob, _ = tc.blur_scaledot(t.cuda(), k.cuda(), (2, 2), d.cuda())
+        assert gb2.dtype == torch.bfloat16 and ob.dtype == torch.bfloat16
+        torch.testing.assert_close(gb1.cpu(), ref, **tol)
+        torch.testing.assert_close(gb2.float().cpu(), ref * d.view(b, 1, 1, c), rtol=5e-3, atol=1e-4)
+        torch.testing.assert_close(ob.float().cpu(), f2 * d.view(b, 1, 1, c), rtol=5e-3, atol=1e-4)
 
 
 @pytest.mark.parametrize("up", [False, True])
