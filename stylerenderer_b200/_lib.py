@@ -65,6 +65,8 @@ _SIGNATURES = {
     "sr_rasterize_pyramid_maps_f32": (_I, [_L, _L, _L, _I, _P, _I, _I, _I, _P, _P, _P, _F, _P, _L, _I, _P]),
     "sr_blur_nhwc_styled3_f32": (_I, [_P, _P, _P, _P, _P, _L, _L, _L, _L, _I, _I, _P, _L, _P, _P, _F, _F, _P, _L, _P]),
     "sr_styled_bwd_prologue3_f32": (_I, [_P] * 13 + [_L, _P, _P, _P, _L, _L, _L, _F, _F, _P, _L, _P, _P]),
+    "sr_stylemap_resblock_forward_f32": (_I, [_P] * 9 + [_L, _I, _I, _L, _L, _F, _F, _P]),
+    "sr_stylemap_resblock_backward_f32": (_I, [_P] * 10 + [_L, _I, _I, _L, _L, _F, _F, _P]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

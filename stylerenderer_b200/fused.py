@@ -13,6 +13,7 @@ import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
+from . import _lib
 from . import style
 from . import tc_conv as tc
 from .op.upfirdn2d import upfirdn2d_raw
@@ -585,3 +586,75 @@ def generator_chain_forward(gen, latent, noise, maps_fn=None):
             out = rgb.permute(0, 3, 1, 2) + to_rgb.bias
             skip = out if skip is None else out + to_rgb.upsample(skip)
     return skip
+
+
+# ------------------------------------------------------------------------------------------------- style-map networks
+class StyleMapResBlockFn(Function):
+    """ResBlock(3 -> 2 / 4, downsample=False) of GeneratorWithMap's style-map networks (reference model.py:194-216,
+    layers.py:379-391) as ONE kernel per direction over [B,3,H,W] planes (csrc/stylemap_net.cu): forward writes only the
+    block output, backward recomputes the intermediate activations from x and reduces every parameter gradient.
+    The input gets no gradient (callers that need one take the composed path, see stylemap_resblock_supported)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1c, b1a, w2, b2c, b2a, ws, alpha, gain):
+        b, ci, h, w = x.shape
+        co = w2.shape[0]
+        out = torch.empty(b, co, h, w, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().sr_stylemap_resblock_forward_f32(
+                _lib.ptr(out), _lib.ptr(x), _lib.ptr(w1), _lib.ptr(b1c), _lib.ptr(b1a), _lib.ptr(w2), _lib.ptr(b2c),
+                _lib.ptr(b2a), _lib.ptr(ws), b, ci, co, h, w, float(alpha), float(gain), _lib.stream_of(x))
+        _lib.check(rc, "sr_stylemap_resblock_forward_f32")
+        ctx.save_for_backward(x, w1, b1c, b1a, w2, b2c, b2a, ws)
+        ctx.alpha, ctx.gain = alpha, gain
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, w1, b1c, b1a, w2, b2c, b2a, ws = ctx.saved_tensors
+        b, ci, h, w = x.shape
+        co = w2.shape[0]
+        n1, n2 = ci * ci * 9, co * ci * 9
+        grads = torch.empty(n1 + ci + n2 + co + co * ci, dtype=torch.float32, device=x.device)
+        g = g.contiguous()
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().sr_stylemap_resblock_backward_f32(
+                _lib.ptr(grads), _lib.ptr(g), _lib.ptr(x), _lib.ptr(w1), _lib.ptr(b1c), _lib.ptr(b1a), _lib.ptr(w2),
+                _lib.ptr(b2c), _lib.ptr(b2a), _lib.ptr(ws), b, ci, co, h, w, float(ctx.alpha), float(ctx.gain),
+                _lib.stream_of(x))
+        _lib.check(rc, "sr_stylemap_resblock_backward_f32")
+        dw1, db1 = grads[:n1].view_as(w1), grads[n1:n1 + ci]
+        dw2, db2 = grads[n1 + ci:n1 + ci + n2].view_as(w2), grads[n1 + ci + n2:n1 + ci + n2 + co]
+        dws = grads[n1 + ci + n2 + co:].view_as(ws)
+        return (None, dw1, db1 if b1c is not None else None, db1 if b1a is not None else None, dw2,
+                db2 if b2c is not None else None, db2 if b2a is not None else None, dws, None, None)
+
+
+def stylemap_resblock_supported(block, x):
+    """The fused kernel covers the blocks GeneratorWithMap builds by default: 3 -> 2 / 4 channels, stride 1, fp32 NCHW CUDA
+    input without gradient, first-order differentiation only."""
+    from .layers import EqualConv2d, double_backward_requested
+    from .op.fused_act import FusedLeakyReLU
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3):
+        return False
+    if (x.requires_grad and torch.is_grad_enabled()) or (torch.is_grad_enabled() and double_backward_requested()):
+        return False
+    c1, c2, sk = list(block.conv1), list(block.conv2), list(block.skip)
+    if not (len(c1) == 2 and len(c2) == 2 and len(sk) == 1):
+        return False
+    if not (isinstance(c1[0], EqualConv2d) and isinstance(c2[0], EqualConv2d) and isinstance(sk[0], EqualConv2d)
+            and isinstance(c1[1], FusedLeakyReLU) and isinstance(c2[1], FusedLeakyReLU)):
+        return False
+    if c1[1].negative_slope != c2[1].negative_slope or c1[1].scale != c2[1].scale:
+        return False
+    ok = lambda c, k: c.weight.shape[2:] == (k, k) and c.stride == 1 and c.padding == k // 2    # noqa: E731
+    return (ok(c1[0], 3) and ok(c2[0], 3) and ok(sk[0], 1) and sk[0].bias is None and c1[0].weight.shape[:2] == (3, 3)
+            and c2[0].weight.shape[0] in (2, 4) and c2[0].weight.shape[1] == 3 and sk[0].weight.shape[:2] == c2[0].weight.shape[:2])
+
+
+def stylemap_resblock(block, x):
+    c1, a1 = block.conv1[0], block.conv1[1]
+    c2, a2 = block.conv2[0], block.conv2[1]
+    return StyleMapResBlockFn.apply(x.contiguous(), c1.weight, c1.bias, a1.bias, c2.weight, c2.bias, a2.bias,
+                                    block.skip[0].weight, a1.negative_slope, a1.scale)

@@ -323,5 +323,10 @@ class ResBlock(nn.Module):                            # reference layers.py:379-
         self.skip = ConvLayer(in_channel, out_channel, 1, downsample=downsample, activate=False, bias=False)
 
     def forward(self, input):
+        if _CONFIG["conv_backend"] == "tcgen05" and input.is_cuda and input.dim() == 4 and input.shape[1] == 3:
+            # the style-map networks of GeneratorWithMap (reference model.py:194-216): the whole block in one kernel
+            from . import fused
+            if fused.stylemap_resblock_supported(self, input):
+                return fused.stylemap_resblock(self, input)
         out = self.conv2(self.conv1(input))
         return (out + self.skip(input)) / math.sqrt(2)

@@ -627,3 +627,44 @@ def test_discriminator_tcgen05_backend_matches_cudnn_backend():
     from parity_util import hold_envelope, rel_err
     errs = [(rel_err(bb, a), n) for n, a, bb in zip(names, g_a, g_b) if float(a.abs().max()) > 0]
     hold_envelope("discriminator64_tcgen05_vs_composed[tf32]", errs, "tf32")
+
+
+@pytest.mark.parametrize("co", [2, 4])
+@pytest.mark.parametrize("shape", [(2, 4, 4), (3, 37, 70), (1, 16, 32), (2, 256, 256)])
+def test_stylemap_resblock_kernel_vs_composed_fp64(co, shape):
+    """sr_stylemap_resblock_forward/backward_f32 (GeneratorWithMap's style-map nets, reference model.py:194-216: one kernel
+    per direction) against the composed ResBlock of reference layers.py:379-391 evaluated in float64 on the CPU -- output
+    and every parameter gradient (both biases of each layer, the 1x1 skip), ragged tiles included."""
+    from stylerenderer_b200 import _lib, fused, layers as L
+    from make_golden import seeded
+    b, h, w = shape
+    torch.manual_seed(co * 100 + h)
+    blk = L.ResBlock(3, co, downsample=False)
+    with torch.no_grad():
+        for p in blk.parameters():
+            if p.dim() == 1:
+                p.normal_(0, 0.3)                                     # zero biases would hide the bias paths
+    x = seeded((b, 3, h, w), 5)
+    x[:, :, : h // 2, : w // 3] = 0                                   # background pixels of a rasterised map are exactly 0
+    gy = seeded((b, co, h, w), 6)
+    ref = L.ResBlock(3, co, downsample=False).double()
+    ref.load_state_dict({k: v.double() for k, v in blk.state_dict().items()})
+    want = ref(x.double())
+    want.backward(gy.double())
+    blk = blk.cuda()
+    old = L.get_conv_backend()
+    L.set_conv_backend("tcgen05")
+    try:
+        assert fused.stylemap_resblock_supported(blk, x.cuda())
+        n0 = _lib.launch_count()
+        got = blk(x.cuda())
+        got.backward(gy.cuda())
+        assert _lib.launch_count() - n0 == 2, "one kernel forward, one backward"
+    finally:
+        L.set_conv_backend(old)
+    scale = want.abs().max().item()
+    assert (got.detach().cpu().double() - want.detach()).abs().max().item() <= 2e-6 * scale + 1e-6
+    for (n, p), (_, q) in zip(blk.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None, n
+        err = (p.grad.cpu().double() - q.grad).abs().max().item()
+        assert err <= 2e-5 * q.grad.abs().max().item() + 1e-5, (n, err, q.grad.abs().max().item())
