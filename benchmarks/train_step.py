@@ -191,8 +191,8 @@ def run(args):
     dead_ids = {id(p) for p in dead}
     g_params = [p for p in G.parameters() if id(p) not in dead_ids]
     d_params = list(D.parameters())
-    g_optim = torch.optim.Adam(g_params, lr=0.002 * g_ratio, betas=(0.0, 0.99 ** g_ratio))
-    d_optim = torch.optim.Adam(d_params, lr=0.002 * d_ratio, betas=(0.0, 0.99 ** d_ratio))
+    g_optim = torch.optim.Adam(g_params, lr=0.002 * g_ratio, betas=(0.0, 0.99 ** g_ratio), fused=True)   # same update (train.py:548-557), one multi-tensor kernel
+    d_optim = torch.optim.Adam(d_params, lr=0.002 * d_ratio, betas=(0.0, 0.99 ** d_ratio), fused=True)
     g_mod, d_mod = G, D
     buckets = None
     if world > 1:
@@ -307,9 +307,12 @@ def run(args):
     n0 = _lib.launch_count()
     if args.profile and rank == 0:
         from torch.profiler import ProfilerActivity, profile
-        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof:
             ms = timed(args.iters)
-        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90), file=sys.stderr)
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90), file=sys.stderr)
+        # which torch ops (with their input shapes) still own device time: the library / elementwise leftovers
+        print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=60, max_name_column_width=50,
+                                                                  max_shapes_column_width=110), file=sys.stderr)
     else:
         ms = timed(args.iters)
     launches = (_lib.launch_count() - n0) // args.iters

@@ -417,6 +417,29 @@ int sr_stylemap_resblock_backward_f32(float *grads, const float *grad_out, const
                                       const float *b2_act, const float *w_skip, int64_t batch, int cin, int cout,
                                       int64_t h, int64_t w, float alpha, float gain, void *stream);
 
+/* Small-channel convolution pair (1..8 channels, 1x1 or 3x3 with zero padding k/2, stride 1, [batch, c, h, w] planes):
+ * y = conv(x, w), w [cout, cin, k, k] (cross-correlation like F.conv2d, no bias), and its weight gradient
+ * dw[o,i,ky,kx] = sum gy[n,o,p] x[n,i,p + (ky,kx) - k/2] (cin * cout * k * k <= 256).  The two maps are each other's
+ * derivatives, so they carry the style-map nets through the regulariser iterations that differentiate twice (reference
+ * train.py:335-354 with the normal maps among the inputs), where torch's double backward of the cuDNN convolutions computes
+ * weight gradients as convolutions with image-sized kernels. */
+int sr_small_conv_f32(float *y, const float *x, const float *w, int64_t batch, int cin, int cout, int ksize, int64_t h,
+                      int64_t wd, void *stream);
+int sr_small_conv_wgrad_f32(float *dw, const float *gy, const float *x, int64_t batch, int cin, int cout, int ksize,
+                            int64_t h, int64_t wd, void *stream);
+/* The Discriminator's stem, ConvLayer(3, cout, 1) = EqualConv2d 1x1 + bias + FusedLeakyReLU (reference model.py:303,
+ * layers.py:341-378), as one bandwidth pass per direction.  x: [batch, 3, h, w] planes or (x_channels_last) [batch, h, w, 3];
+ * y / gy: channels-last [batch, h, w, cout]; w [cout, 3] raw (scaled by 1/sqrt(3) inside); biases may be NULL.
+ *   forward : y = lrelu(conv1x1(x, w / sqrt(3)) + b_conv + b_act) * gain
+ *   backward: grads = [d w (3 cout) | d b (cout)] (d b is the gradient of both biases), dx (layout of x) optional;
+ *             the activation mask is recomputed from x, so nothing but gy is read at full size. */
+int sr_stem_conv_forward_f32(float *y, const float *x, const float *w, const float *b_conv, const float *b_act,
+                             int64_t batch, int cin, int64_t cout, int64_t h, int64_t wd, int x_channels_last, float alpha,
+                             float gain, void *stream);
+int sr_stem_conv_backward_f32(float *grads, float *dx, const float *gy, const float *x, const float *w, const float *b_conv,
+                              const float *b_act, int64_t batch, int cin, int64_t cout, int64_t h, int64_t wd,
+                              int x_channels_last, float alpha, float gain, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,10 @@ _SIGNATURES = {
     "sr_styled_bwd_prologue3_f32": (_I, [_P] * 13 + [_L, _P, _P, _P, _L, _L, _L, _F, _F, _P, _L, _P, _P]),
     "sr_stylemap_resblock_forward_f32": (_I, [_P] * 9 + [_L, _I, _I, _L, _L, _F, _F, _P]),
     "sr_stylemap_resblock_backward_f32": (_I, [_P] * 10 + [_L, _I, _I, _L, _L, _F, _F, _P]),
+    "sr_small_conv_f32": (_I, [_P, _P, _P, _L, _I, _I, _I, _L, _L, _P]),
+    "sr_small_conv_wgrad_f32": (_I, [_P, _P, _P, _L, _I, _I, _I, _L, _L, _P]),
+    "sr_stem_conv_forward_f32": (_I, [_P] * 5 + [_L, _I, _L, _L, _L, _I, _F, _F, _P]),
+    "sr_stem_conv_backward_f32": (_I, [_P] * 7 + [_L, _I, _L, _L, _L, _I, _F, _F, _P]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

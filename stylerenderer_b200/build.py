@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libstylerenderer_b200.so")
-SOURCES = ["lib.cu", "fused_bias_act.cu", "upfirdn2d.cu", "rasterize.cu", "modconv.cu", "styled_ops.cu", "style_ops.cu", "mesh_ops.cu", "stylemap_net.cu"]
+SOURCES = ["lib.cu", "fused_bias_act.cu", "upfirdn2d.cu", "rasterize.cu", "modconv.cu", "styled_ops.cu", "style_ops.cu", "mesh_ops.cu", "stylemap_net.cu", "stem_conv.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--compiler-options", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 

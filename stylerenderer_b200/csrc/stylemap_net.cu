@@ -278,10 +278,127 @@ int check_args(const void *a, const void *b, const float *w1, const float *w2, c
     return SR_OK;
 }
 
+// ---- small-channel convolution pair (<= 8 channels): any-order differentiable building blocks ---------------------------
+// The regulariser iterations (path length: reference train.py:335-354 differentiates the image with respect to the latents AND
+// the normal maps with create_graph=True) need the style-map nets twice differentiable.  torch's double backward of a
+// cuDNN conv computes weight gradients as convolutions with 256 x 256 "kernels" (12.5 ms per call at [8,3,256,256]).  A
+// stride-1 convolution and its weight gradient are bilinear maps whose derivatives are each other:
+//   y  = conv(x, w)            dx = conv(gy, flipT(w))        dw = wgrad(gy, x)
+//   dw = wgrad(g, x)           dg = conv(x, gdw)              dx = conv(g, flipT(gdw))
+// so two kernels cover every order (fused.SmallConvFn / SmallWgradFn).
+constexpr int SC_MAX = 8;
+
+struct SmallConvGeom {
+    int batch, ci, co, k, h, w;                 // k = 1 or 3 (zero padding k / 2), stride 1
+    int64_t total;                              // batch * h * w
+};
+
+__global__ void __launch_bounds__(NT)
+small_conv_kernel(float *__restrict__ y, const float *__restrict__ x, const float *__restrict__ wgt, const SmallConvGeom g)
+{
+    __shared__ float ws[SC_MAX * SC_MAX * 9];
+    for (int e = threadIdx.x; e < g.co * g.ci * g.k * g.k; e += NT) ws[e] = __ldg(wgt + e);
+    __syncthreads();
+    const int pad = g.k / 2, kk = g.k * g.k;
+    const int64_t plane = (int64_t)g.h * g.w;
+    for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < g.total; idx += (int64_t)gridDim.x * NT) {
+        const int px = (int)(idx % g.w), py = (int)((idx / g.w) % g.h);
+        const int64_t n = idx / plane;
+        float acc[SC_MAX];
+#pragma unroll
+        for (int o = 0; o < SC_MAX; ++o) acc[o] = 0.0f;
+        for (int i = 0; i < g.ci; ++i) {
+            const float *xp = x + (n * g.ci + i) * plane;
+            for (int ky = 0; ky < g.k; ++ky) {
+                const int yy = py + ky - pad;
+                if (yy < 0 || yy >= g.h) continue;
+                for (int kx = 0; kx < g.k; ++kx) {
+                    const int xx = px + kx - pad;
+                    if (xx < 0 || xx >= g.w) continue;
+                    const float v = __ldg(xp + (int64_t)yy * g.w + xx);
+                    const float *wp = ws + i * kk + ky * g.k + kx;
+#pragma unroll
+                    for (int o = 0; o < SC_MAX; ++o)
+                        if (o < g.co) acc[o] = fmaf(wp[o * g.ci * kk], v, acc[o]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < SC_MAX; ++o)
+            if (o < g.co) y[(n * g.co + o) * plane + (int64_t)py * g.w + px] = acc[o];
+    }
+}
+
+// dw[o,i,ky,kx] = sum_{n,p} gy[n,o,p] * x[n,i,p + (ky,kx) - pad]; one thread per element (co*ci*k*k <= 256), tiles of
+// TH x TW pixels staged in shared memory, register accumulation across the tiles of a persistent CTA, one atomic per CTA
+__global__ void __launch_bounds__(NT)
+small_wgrad_kernel(float *__restrict__ dw, const float *__restrict__ gy, const float *__restrict__ x, const SmallConvGeom g,
+                   const NetGeom tg)
+{
+    constexpr int XR = TH + 2, XC = TW + 2, XPS = plane_stride(XR, XC), GPS = plane_stride(TH, TW);
+    __shared__ float xs[SC_MAX * XPS], gs[SC_MAX * GPS];
+    const int pad = g.k / 2, kk = g.k * g.k, nacc = g.co * g.ci * kk;
+    const int t = threadIdx.x;
+    const float *pa = nullptr, *pb = nullptr;
+    if (t < nacc) {
+        const int o = t / (g.ci * kk), i = (t / kk) % g.ci, ky = (t % kk) / g.k, kx = t % g.k;
+        pa = gs + o * GPS;
+        pb = xs + i * XPS + (1 + ky - pad) * XC + 1 + kx - pad;
+    }
+    float acc = 0.0f;
+    for (uint32_t T = blockIdx.x; T < (uint32_t)tg.total_tiles; T += gridDim.x) {
+        uint32_t tt = T, tx, ty, n;
+        tg.div_tx.divmod(tt, tt, tx);
+        tg.div_ty.divmod(tt, n, ty);
+        const int oy0 = ty * TH, ox0 = tx * TW;
+        __syncthreads();
+        load_planes<1>(xs, x + (int64_t)n * g.ci * g.h * g.w, g.ci, oy0, ox0, g.h, g.w);
+        load_planes<0>(gs, gy + (int64_t)n * g.co * g.h * g.w, g.co, oy0, ox0, g.h, g.w);
+        __syncthreads();
+        if (pa)
+            for (int r = 0; r < TH; ++r)
+#pragma unroll 8
+                for (int q = 0; q < TW; ++q) acc = fmaf(pa[r * TW + q], pb[r * XC + q], acc);
+    }
+    if (pa) atomicAdd(dw + t, acc);
+}
+
 }  // namespace
 }  // namespace sr
 
 using namespace sr;
+
+extern "C" int sr_small_conv_f32(float *y, const float *x, const float *w, int64_t batch, int cin, int cout, int ksize,
+                                 int64_t h, int64_t wd, void *stream)
+{
+    SR_REQUIRE(y && x && w, "small_conv: null pointer");
+    SR_REQUIRE(cin >= 1 && cin <= SC_MAX && cout >= 1 && cout <= SC_MAX && (ksize == 1 || ksize == 3),
+               "small_conv: 1..8 channels, 1x1 or 3x3 (got %d -> %d, k = %d)", cin, cout, ksize);
+    SR_REQUIRE(batch >= 1 && h >= 1 && wd >= 1 && h < (1 << 20) && wd < (1 << 20), "small_conv: bad sizes");
+    SmallConvGeom g = {(int)batch, cin, cout, ksize, (int)h, (int)wd, batch * h * wd};
+    int64_t blocks = (g.total + NT - 1) / NT;
+    if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+    small_conv_kernel<<<(unsigned)blocks, NT, 0, (cudaStream_t)stream>>>(y, x, w, g);
+    count_launch();
+    return check_launch("small_conv");
+}
+
+extern "C" int sr_small_conv_wgrad_f32(float *dw, const float *gy, const float *x, int64_t batch, int cin, int cout, int ksize,
+                                       int64_t h, int64_t wd, void *stream)
+{
+    SR_REQUIRE(dw && gy && x, "small_conv_wgrad: null pointer");
+    SR_REQUIRE(cin >= 1 && cin <= SC_MAX && cout >= 1 && cout <= SC_MAX && (ksize == 1 || ksize == 3) &&
+               cin * cout * ksize * ksize <= NT, "small_conv_wgrad: cin * cout * k * k must be <= 256 (got %d -> %d, k = %d)", cin, cout, ksize);
+    SR_REQUIRE(batch >= 1 && h >= 1 && wd >= 1 && batch * ((h + TH - 1) / TH) * ((wd + TW - 1) / TW) < 0x7fffffffll, "small_conv_wgrad: bad sizes");
+    SmallConvGeom g = {(int)batch, cin, cout, ksize, (int)h, (int)wd, batch * h * wd};
+    const NetGeom tg = make_geom(batch, h, wd, cin, cout, 0.f, 1.f);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(dw, 0, sizeof(float) * cin * cout * ksize * ksize, st) != cudaSuccess) return check_launch("small_conv_wgrad (memset)");
+    const int grid = tg.total_tiles < 2 * kNumSMs ? tg.total_tiles : 2 * kNumSMs;
+    small_wgrad_kernel<<<grid, NT, 0, st>>>(dw, gy, x, g, tg);
+    count_launch();
+    return check_launch("small_conv_wgrad");
+}
 
 extern "C" int sr_stylemap_resblock_forward_f32(float *out, const float *x, const float *w1, const float *b1_conv, const float *b1_act,
                                                 const float *w2, const float *b2_conv, const float *b2_act, const float *w_skip,

@@ -658,3 +658,132 @@ def stylemap_resblock(block, x):
     c2, a2 = block.conv2[0], block.conv2[1]
     return StyleMapResBlockFn.apply(x.contiguous(), c1.weight, c1.bias, a1.bias, c2.weight, c2.bias, a2.bias,
                                     block.skip[0].weight, a1.negative_slope, a1.scale)
+
+
+# ------------------------------------------------------------------------------------------------- small-channel convs
+def _small_conv_call(x, w):
+    b, ci, h, wd = x.shape
+    co, k = w.shape[0], w.shape[2]
+    y = torch.empty(b, co, h, wd, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().sr_small_conv_f32(_lib.ptr(y), _lib.ptr(x), _lib.ptr(w), b, ci, co, k, h, wd, _lib.stream_of(x))
+    _lib.check(rc, "sr_small_conv_f32")
+    return y
+
+
+def _flip_t(w):
+    """Weights of the data gradient of a stride-1 'same' convolution: spatially flipped, channel axes swapped."""
+    return w.flip(2, 3).transpose(0, 1)
+
+
+class SmallConvFn(Function):
+    """y = conv(x, w): 1..8 channels, 1x1 or 3x3, stride 1, zero padding k // 2 (csrc/stylemap_net.cu).  With SmallWgradFn
+    it is differentiable to any order on the same two kernels: the style-map nets of GeneratorWithMap inside the
+    regulariser iterations (reference train.py:335-354), where torch's double backward of a cuDNN convolution computes
+    weight gradients as convolutions with image-sized kernels (12.5 ms per call at [8,3,256,256])."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x, w = x.contiguous(), w.contiguous()
+        ctx.save_for_backward(x, w)
+        return _small_conv_call(x, w)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gx = SmallConvFn.apply(gy, _flip_t(w)) if ctx.needs_input_grad[0] else None
+        gw = SmallWgradFn.apply(gy, x, w.shape[2]) if ctx.needs_input_grad[1] else None
+        return gx, gw
+
+
+class SmallWgradFn(Function):
+    """dw[o,i,ky,kx] = sum gy[n,o,p] x[n,i,p + (ky,kx) - k/2]: bilinear in (gy, x); its derivatives are convolutions."""
+
+    @staticmethod
+    def forward(ctx, gy, x, k):
+        gy, x = gy.contiguous(), x.contiguous()
+        ctx.save_for_backward(gy, x)
+        b, ci, h, wd = x.shape
+        co = gy.shape[1]
+        dw = torch.empty(co, ci, k, k, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().sr_small_conv_wgrad_f32(_lib.ptr(dw), _lib.ptr(gy), _lib.ptr(x), b, ci, co, k, h, wd,
+                                                    _lib.stream_of(x))
+        _lib.check(rc, "sr_small_conv_wgrad_f32")
+        return dw
+
+    @staticmethod
+    def backward(ctx, gdw):
+        gy, x = ctx.saved_tensors
+        ggy = SmallConvFn.apply(x, gdw) if ctx.needs_input_grad[0] else None
+        gx = SmallConvFn.apply(gy, _flip_t(gdw)) if ctx.needs_input_grad[1] else None
+        return ggy, gx, None
+
+
+def small_conv_supported(conv, x):
+    w = conv.weight
+    k = w.shape[2]
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and w.shape[2] == w.shape[3] and k in (1, 3)
+            and conv.stride == 1 and conv.padding == k // 2 and w.shape[0] <= 8 and w.shape[1] <= 8
+            and w.shape[0] * w.shape[1] * k * k <= 256)
+
+
+def small_conv(conv, x):
+    out = SmallConvFn.apply(x, conv.weight * conv.scale)
+    return out if conv.bias is None else out + conv.bias.view(1, -1, 1, 1)
+
+
+# ------------------------------------------------------------------------------------------------- Discriminator stem
+class StemConvFn(Function):
+    """ConvLayer(3, C, 1) of the Discriminator (reference model.py:303): 1x1 EqualConv2d + bias + FusedLeakyReLU in one
+    bandwidth pass per direction (csrc/stem_conv.cu).  Output is channels_last (logical [N,C,H,W]) for the tensor-core
+    ResBlocks that follow.  First-order gradients (x, weight, both biases); the backward recomputes the activation mask
+    from x, so nothing is saved but x itself."""
+
+    @staticmethod
+    def forward(ctx, x, w, b_conv, b_act, alpha, gain):
+        n, ci, h, wd = x.shape
+        co = w.shape[0]
+        nhwc = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
+        if not nhwc:
+            x = x.contiguous()
+        y = torch.empty(n, h, wd, co, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().sr_stem_conv_forward_f32(_lib.ptr(y), _lib.ptr(x), _lib.ptr(w), _lib.ptr(b_conv), _lib.ptr(b_act),
+                                                     n, ci, co, h, wd, int(nhwc), float(alpha), float(gain), _lib.stream_of(x))
+        _lib.check(rc, "sr_stem_conv_forward_f32")
+        ctx.save_for_backward(x, w, b_conv, b_act)
+        ctx.cfg = (nhwc, alpha, gain)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, w, b_conv, b_act = ctx.saved_tensors
+        nhwc, alpha, gain = ctx.cfg
+        n, ci, h, wd = x.shape
+        co = w.shape[0]
+        g = gy.permute(0, 2, 3, 1).contiguous()                              # a free view for channels_last gradients
+        grads = torch.empty(co * 4, dtype=torch.float32, device=x.device)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None      # same layout as x
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().sr_stem_conv_backward_f32(_lib.ptr(grads), _lib.ptr(dx), _lib.ptr(g), _lib.ptr(x), _lib.ptr(w),
+                                                      _lib.ptr(b_conv), _lib.ptr(b_act), n, ci, co, h, wd, int(nhwc),
+                                                      float(alpha), float(gain), _lib.stream_of(x))
+        _lib.check(rc, "sr_stem_conv_backward_f32")
+        dw = grads[:co * ci].view_as(w) if ctx.needs_input_grad[1] else None
+        db = grads[co * ci:]
+        return (dx, dw, db if (b_conv is not None and ctx.needs_input_grad[2]) else None,
+                db if (b_act is not None and ctx.needs_input_grad[3]) else None, None, None)
+
+
+def stem_conv_supported(conv, act, x):
+    from .layers import double_backward_requested
+    w = conv.weight
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and act is not None and w.shape[1] == 3 and x.shape[1] == 3
+            and w.shape[2] == 1 and w.shape[3] == 1 and conv.stride == 1 and conv.padding == 0 and w.shape[0] % 4 == 0
+            and 4 <= w.shape[0] <= 1024 and not (torch.is_grad_enabled() and double_backward_requested()))
+
+
+def stem_conv(conv, act, x):
+    return StemConvFn.apply(x, conv.weight, conv.bias, act.bias, act.negative_slope, act.scale)

@@ -118,6 +118,12 @@ class EqualConv2d(nn.Module):                         # reference layers.py:204-
         self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
 
     def forward(self, input):
+        if _CONFIG["conv_backend"] == "tcgen05" and input.is_cuda and self.weight.shape[0] <= 8 and self.weight.shape[1] <= 8:
+            # convolutions with a handful of channels (the style-map nets of GeneratorWithMap): two small kernels that are
+            # each other's derivatives, differentiable to any order (fused.SmallConvFn)
+            from . import fused
+            if fused.small_conv_supported(self, input):
+                return fused.small_conv(self, input)
         w = self.weight * self.scale
         if (w.shape[2] == 1 and w.shape[3] == 1 and self.stride == 1 and self.padding == 0 and w.shape[1] <= 8 and input.is_cuda
                 and input.dim() == 4):
@@ -304,6 +310,8 @@ class ConvLayer(nn.Sequential):                       # reference layers.py:341-
             act = rest[1] if len(rest) > 1 else None
             if isinstance(conv, EqualConv2d) and (isinstance(act, FusedLeakyReLU) or (act is None and conv.bias is None)):
                 from . import fused
+                if blur is None and isinstance(act, FusedLeakyReLU) and fused.stem_conv_supported(conv, act, input):
+                    return fused.stem_conv(conv, act, input)          # 3 -> C pointwise stem: one bandwidth pass
                 x = blur(input) if blur is not None else input
                 kind = fused.plain_conv_supported(conv, x)
                 if kind is not None:

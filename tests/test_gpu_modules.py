@@ -668,3 +668,76 @@ def test_stylemap_resblock_kernel_vs_composed_fp64(co, shape):
         assert p.grad is not None, n
         err = (p.grad.cpu().double() - q.grad).abs().max().item()
         assert err <= 2e-5 * q.grad.abs().max().item() + 1e-5, (n, err, q.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("cfg", [(3, 3, 3), (3, 4, 3), (4, 3, 3), (3, 2, 1), (8, 3, 3), (1, 8, 1)])
+def test_small_conv_pair_any_order(cfg):
+    """fused.SmallConvFn / SmallWgradFn (sr_small_conv_f32, sr_small_conv_wgrad_f32) against F.conv2d in float64 on the CPU:
+    output, first-order gradients, and the gradients of a gradient-norm penalty (the shape of the path-length regulariser,
+    reference train.py:118-134, which differentiates through the backward pass of the style-map nets)."""
+    import torch.nn.functional as F
+    from stylerenderer_b200 import fused
+    from make_golden import seeded
+    ci, co, k = cfg
+    b, h, w = 2, 37, 45
+    x0, w0, gy = seeded((b, ci, h, w), 1), seeded((co, ci, k, k), 2) * 0.3, seeded((b, co, h, w), 3)
+
+    def penalty(conv, x, wt):
+        y = conv(x, wt)
+        loss1 = (torch.tanh(y) * gy.to(y)).sum()
+        gx, = torch.autograd.grad(loss1, x, create_graph=True)
+        return y, (gx.pow(2).sum() + loss1)
+
+    xr, wr = x0.double().requires_grad_(True), w0.double().requires_grad_(True)
+    yr, pr = penalty(lambda a, c: F.conv2d(a, c, padding=k // 2), xr, wr)
+    gxr, gwr = torch.autograd.grad(pr, [xr, wr])
+    xg, wg = x0.cuda().requires_grad_(True), w0.cuda().requires_grad_(True)
+    yg, pg = penalty(fused.SmallConvFn.apply, xg, wg)
+    gxg, gwg = torch.autograd.grad(pg, [xg, wg])
+    for name, got, want in (("y", yg, yr), ("dx", gxg, gxr), ("dw", gwg, gwr)):
+        err = (got.detach().cpu().double() - want.detach()).abs().max().item()
+        assert err <= 3e-5 * want.abs().max().item() + 1e-6, (name, err, want.abs().max().item())
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("shape", [(2, 128, 19, 23), (1, 256, 8, 8), (3, 64, 32, 32)])
+def test_stem_conv_kernel_vs_composed_fp64(shape, channels_last):
+    """sr_stem_conv_forward/backward_f32 (the Discriminator's ConvLayer(3, C, 1), reference model.py:303) against the composed
+    layer in float64: output, weight / both bias gradients, input gradient; planar and channels_last images."""
+    from stylerenderer_b200 import _lib, fused, layers as L
+    from make_golden import seeded
+    b, c, h, w = shape
+    torch.manual_seed(c + h)
+    layer = L.ConvLayer(3, c, 1)
+    with torch.no_grad():
+        layer[0].bias.normal_(0, 0.3)
+        layer[1].bias.normal_(0, 0.3)
+    x0, gy = seeded((b, 3, h, w), 7), seeded((b, c, h, w), 8)
+    ref = L.ConvLayer(3, c, 1).double()
+    ref.load_state_dict({k: v.double() for k, v in layer.state_dict().items()})
+    xr = x0.double().requires_grad_(True)
+    want = ref(xr)
+    want.backward(gy.double())
+    layer = layer.cuda()
+    xg = x0.cuda()
+    if channels_last:
+        xg = xg.contiguous(memory_format=torch.channels_last)
+    xg.requires_grad_(True)
+    old = L.get_conv_backend()
+    L.set_conv_backend("tcgen05")
+    try:
+        n0 = _lib.launch_count()
+        got = layer(xg)
+        got.backward(gy.cuda().contiguous(memory_format=torch.channels_last))
+        assert _lib.launch_count() - n0 == 2, "one kernel forward, one backward"
+    finally:
+        L.set_conv_backend(old)
+    assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+
+    def close(name, a, bb, rel):
+        err = (a.detach().cpu().double() - bb.detach()).abs().max().item()
+        assert err <= rel * bb.abs().max().item() + 1e-6, (name, err, bb.abs().max().item())
+    close("y", got, want, 2e-6)
+    close("dx", xg.grad, xr.grad, 2e-5)
+    for (n, p), (_, q) in zip(layer.named_parameters(), ref.named_parameters()):
+        close(n, p.grad, q.grad, 3e-5)
