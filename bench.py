@@ -575,8 +575,9 @@ def run_rasterize(args):
 
 def run_train_step(args):
     """BASELINE.json configs[3]: the full GAR train step (GeneratorWithMap + Discriminator + rasterise + R1/16 + path/4,
-    reference train.py:239-358) under DistributedDataParallel -- the one workload of the path with a data-plane collective
-    (NCCL gradient all-reduce).  A "step" is one training iteration; --steps should be a multiple of 16 (one regulariser
+    reference train.py:239-358), data-parallel -- the one workload of the path with a data-plane collective (NCCL gradient
+    all-reduce; --no-graph: torch DistributedDataParallel with eager launches, default: CUDA-graph replay of the phases with
+    one flat-buffer all-reduce per backward pass).  A "step" is one training iteration; --steps should be a multiple of 16 (one regulariser
     cycle).  Same JSON contract as the headline workload."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("sr_train_step", os.path.join(ROOT, "benchmarks", "train_step.py"))
@@ -589,7 +590,8 @@ def run_train_step(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
     steps = args.steps if args.steps_given else 16
     cfg = ts.default_args(batch=16 if not args.batch_given else args.batch, iters=steps, warmup=max(args.warmup, 3),
-                          conv_backend=args.conv_backend or "tcgen05", precision=args.precision or "bf16")
+                          conv_backend=args.conv_backend or "tcgen05", precision=args.precision or "bf16",
+                          execution="eager" if args.no_graph else "graph")
     peaks = measured_peaks()
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -632,7 +634,7 @@ def run_train_step(args):
                 "warmup": cfg.warmup, "ms_per_step": res["ms_per_iter"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": cfg.precision, "data": "synthetic",
                 "config": dict(res["config"], global_batch=world * cfg.batch, conv_backend=res["conv_backend"], precision=res["dtype"],
-                               execution="eager", l2="activations per iteration exceed the 126 MB L2; no explicit flush"),
+                               l2="activations per iteration exceed the 126 MB L2; no explicit flush"),
                 "clocks": clocks.summary(), "e2e": res.get("e2e"), "gpu_launches": int(res["gpu_launches_per_iter"]),
                 "roofline": roof, "cpu_baseline": cpu_base, "collective": res["collective"], "losses": res["losses"]}
         print(json.dumps(line), flush=True)

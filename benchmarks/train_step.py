@@ -191,11 +191,13 @@ def run(args):
     dead_ids = {id(p) for p in dead}
     g_params = [p for p in G.parameters() if id(p) not in dead_ids]
     d_params = list(D.parameters())
-    g_optim = torch.optim.Adam(g_params, lr=0.002 * g_ratio, betas=(0.0, 0.99 ** g_ratio), fused=True)   # same update (train.py:548-557), one multi-tensor kernel
-    d_optim = torch.optim.Adam(d_params, lr=0.002 * d_ratio, betas=(0.0, 0.99 ** d_ratio), fused=True)
+    use_graph = getattr(args, "execution", "graph") == "graph"
+    # same update as train.py:548-557, one multi-tensor kernel; capturable = the step counter lives on the device
+    g_optim = torch.optim.Adam(g_params, lr=0.002 * g_ratio, betas=(0.0, 0.99 ** g_ratio), fused=True, capturable=use_graph)
+    d_optim = torch.optim.Adam(d_params, lr=0.002 * d_ratio, betas=(0.0, 0.99 ** d_ratio), fused=True, capturable=use_graph)
     g_mod, d_mod = G, D
     buckets = None
-    if world > 1:
+    if world > 1 and not use_graph:
         from torch.nn.parallel import DistributedDataParallel as DDP
         G = DDP(G, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True)
         D = DDP(D, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True)
@@ -283,6 +285,121 @@ def run(args):
             loss_host[1].copy_(losses["g"], non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
+    # ---- execution = "graph": every phase of the iteration (D step, R1, G step, path length: forward + backward into flat
+    # gradient buffers) and the two optimiser steps are captured ONCE as CUDA graphs and replayed; the data-parallel exchange is
+    # one NCCL all-reduce (AVG) of the flat gradient buffer between the backward graph and the optimiser graph -- the same
+    # gradients DDP's reducer would average (reference distributed.py:98-105), without its per-parameter hooks, bucket
+    # copies and the ~3000 eager launches per iteration whose host cost is what limits the eager step when 8 ranks share
+    # the box's host cores (profiles/r2_train_step_scaling.md).
+    graphs, graph_launches = {}, {}
+    if use_graph:
+        def flat_grads(params):
+            flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+            off = 0
+            for p in params:
+                # same layout as the parameter (channels_last Discriminator weights are dense permutations)
+                p.grad = flat[off:off + p.numel()].as_strided(p.size(), p.stride())
+                off += p.numel()
+            return flat
+        flat_g, flat_d = flat_grads(g_params), flat_grads(d_params)
+        real_static = torch.randn(B, 3, args.size, args.size, device=dev)
+        if not args.d_nchw:
+            real_static = real_static.contiguous(memory_format=torch.channels_last)
+        loss_buf = torch.zeros(4, device=dev)
+        pb = max(1, B // 2)
+        vert_buf = torch.zeros(pb, args.mesh_n ** 2, 3, device=dev)
+        norm_buf = torch.zeros(pb, args.mesh_n ** 2, 3, device=dev)
+
+        def d_phase():
+            requires_grad(g_params, False); requires_grad(d_params, True)
+            _, _, maps = sample_mesh(B)
+            fake, _, _ = g_mod([torch.randn(B, 512, device=dev)], maps)
+            d_loss = d_logistic_loss(d_mod(real_static), d_mod(fake))
+            flat_d.zero_()
+            d_loss.backward()
+            loss_buf[0].copy_(d_loss.detach())
+
+        def r1_phase():
+            requires_grad(g_params, False); requires_grad(d_params, True)
+            real = real_static.detach().requires_grad_(True)
+            with layers.double_backward():
+                real_pred = d_mod(real)
+                r1 = d_r1_loss(real_pred, real)
+                flat_d.zero_()
+                (10 / 2 * r1 * d_reg + 0 * real_pred[0]).backward()
+            loss_buf[1].copy_(r1.detach())
+
+        def g_phase():
+            requires_grad(g_params, True); requires_grad(d_params, False)
+            vert, norm, maps = sample_mesh(B)
+            vert_buf.copy_(vert[:pb]); norm_buf.copy_(norm[:pb])
+            fake, _, _ = g_mod([torch.randn(B, 512, device=dev)], maps)
+            g_loss = F.softplus(-d_mod(fake)).mean()
+            flat_g.zero_()
+            g_loss.backward()
+            loss_buf[2].copy_(g_loss.detach())
+
+        def path_phase():
+            requires_grad(g_params, True); requires_grad(d_params, False)
+            v = vert_buf.clone().requires_grad_(True)
+            n = norm_buf.clone().requires_grad_(True)
+            with layers.double_backward():
+                fake, latents, normals = g_mod([torch.randn(pb, 512, device=dev)], (v, n, tri), return_latents=True,
+                                               return_normals=True)
+                path_loss, new_mean = g_path_regularize(fake, [latents] + normals, mean_path)
+                flat_g.zero_()
+                (2 * g_reg * path_loss + 0 * fake[0, 0, 0, 0]).backward()
+            mean_path.copy_(new_mean)
+            loss_buf[3].copy_(path_loss.detach())
+
+        def d_opt():
+            d_optim.step()
+
+        def g_opt():
+            g_optim.step()
+            with torch.no_grad():
+                torch._foreach_mul_(ema_params, 0.999)
+                torch._foreach_add_(ema_params, g_all_params, alpha=0.001)
+
+        phases = {"d": d_phase, "r1": r1_phase, "g": g_phase, "path": path_phase, "d_opt": d_opt, "g_opt": g_opt}
+        order = ["d", "d_opt", "r1", "d_opt", "g", "g_opt", "path", "g_opt"]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                                   # warm-up: optimiser state, cuDNN choices, lazy inits
+            for _ in range(3):
+                for name in order:
+                    phases[name]()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        pool = None
+        for name, fn in phases.items():
+            gr = torch.cuda.CUDAGraph()
+            n_before = _lib.launch_count()
+            with torch.cuda.graph(gr, pool=pool):
+                fn()
+            pool = pool or gr.pool()
+            graphs[name], graph_launches[name] = gr, _lib.launch_count() - n_before
+
+        def reduce_(flat):
+            if world > 1:
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+
+        def iteration_graph(i, e2e=False):
+            if e2e:
+                real_static.copy_(real_host, non_blocking=True)
+            else:
+                real_static.normal_()
+            graphs["d"].replay(); reduce_(flat_d); graphs["d_opt"].replay()
+            if i % d_reg == 0:
+                graphs["r1"].replay(); reduce_(flat_d); graphs["d_opt"].replay()
+            graphs["g"].replay(); reduce_(flat_g); graphs["g_opt"].replay()
+            if i % g_reg == 0:
+                graphs["path"].replay(); reduce_(flat_g); graphs["g_opt"].replay()
+            if e2e:
+                loss_host.copy_(loss_buf, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+        eager_iteration, iteration = iteration, iteration_graph
+
     def timed(n_iters, e2e=False):
         if world > 1:
             dist.barrier()
@@ -316,6 +433,11 @@ def run(args):
     else:
         ms = timed(args.iters)
     launches = (_lib.launch_count() - n0) // args.iters
+    if use_graph:                                                       # replays do not pass through the C ABI: count the captures
+        gl = graph_launches
+        launches = int(gl["d"] + gl["g"] + gl["r1"] / d_reg + gl["path"] / g_reg)
+        lb = loss_buf.tolist()
+        losses.update({"d": torch.tensor(lb[0]), "r1": torch.tensor(lb[1]), "g": torch.tensor(lb[2]), "path": torch.tensor(lb[3])})
     ms_e2e = timed(args.iters, e2e=True) if getattr(args, "e2e", True) else None
 
     # ---- the collective: DDP's gradient all-reduce (bucket layout from the reducer) and its stand-alone cost
@@ -340,8 +462,12 @@ def run(args):
         e.record()
         torch.cuda.synchronize()
         ar_ms = s.elapsed_time(e) / 10
-        comm = {"collective": "NCCL all-reduce of the G and D gradients (DDP buckets, overlapped with the backward)",
-                "gradient_bytes_per_iteration": 4 * (n_g + n_d), "generator": bucket_info(G), "discriminator": bucket_info(D),
+        comm = {"collective": ("NCCL all-reduce (AVG) of the flat G / D gradient buffers, one call per backward pass, between the "
+                               "backward graph and the optimiser graph" if use_graph else
+                               "NCCL all-reduce of the G and D gradients (DDP buckets, overlapped with the backward)"),
+                "gradient_bytes_per_iteration": 4 * (n_g + n_d),
+                "generator": {"buckets": 1, "bytes": 4 * n_g} if use_graph else bucket_info(G),
+                "discriminator": {"buckets": 1, "bytes": 4 * n_d} if use_graph else bucket_info(D),
                 "allreduce_ms_standalone": round(ar_ms, 3),
                 "allreduce_busbw_GBps": round(2 * (world - 1) / world * 4 * (n_g + n_d) / (ar_ms * 1e-3) / 1e9, 1)}
 
@@ -351,7 +477,8 @@ def run(args):
     if not finite:
         raise RuntimeError(f"train step diverged: losses {dict((k, float(v)) for k, v in losses.items())}")
 
-    state = dict(iteration=iteration, lib=_lib, dev=dev, world=world, rank=rank, local=local, B=B, tri=tri)
+    state = dict(iteration=(eager_iteration if use_graph else iteration), lib=_lib, dev=dev, world=world, rank=rank, local=local,
+                 B=B, tri=tri, execution="cuda_graph_replay" if use_graph else "eager")
     if rank != 0:
         return None, state
     res = {
@@ -363,7 +490,10 @@ def run(args):
         "precision": getattr(args, "precision", "tf32"),
         "conv_backend": {"generator": args.conv_backend, "discriminator": args.conv_backend + " (ResBlock convs; 3-channel stem, final conv on cuDNN)"},
         "config": {"workload": "GeneratorWithMap + Discriminator 256x256 (BASELINE.json configs[3])", "per_gpu_batch": B,
-                   "parallelism": f"ddp{world} (NCCL gradient all-reduce, broadcast_buffers=False, dead ToRGB copies frozen)",
+                   "parallelism": (f"dp{world} (flat-buffer NCCL gradient all-reduce between graph replays, dead ToRGB copies frozen)"
+                                   if use_graph else
+                                   f"ddp{world} (NCCL gradient all-reduce, broadcast_buffers=False, dead ToRGB copies frozen)"),
+                   "execution": "cuda_graph_replay (4 phase graphs + 2 optimiser graphs)" if use_graph else "eager",
                    "mesh": f"{args.mesh_n ** 2} verts / {tri.shape[0]} tris"},
         "gpu_launches_per_iter": launches, "losses": {k: round(float(v), 5) for k, v in losses.items()},
         "collective": comm}
@@ -377,7 +507,8 @@ def run(args):
 
 def default_args(**over):
     ns = argparse.Namespace(batch=16, size=256, iters=16, warmup=3, mesh_n=189, conv_backend="tcgen05",
-                            no_cudnn_benchmark=False, d_nchw=False, profile=False, e2e=True, precision="bf16")
+                            no_cudnn_benchmark=False, d_nchw=False, profile=False, e2e=True, precision="bf16",
+                            execution="graph")
     for k, v in over.items():
         setattr(ns, k, v)
     return ns
@@ -396,6 +527,8 @@ def main():
     ap.add_argument("--d-nchw", action="store_true", help="keep the Discriminator in NCHW (default: channels_last, no layout conversions)")
     ap.add_argument("--profile", action="store_true", help="print the top CUDA kernels of the timed iterations (torch.profiler)")
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
+    ap.add_argument("--execution", default="graph", choices=["graph", "eager"],
+                    help="graph: CUDA-graph replay of the phases + flat-buffer all-reduce (default); eager: torch DDP, eager launches")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"],
                     help="operand mode of the tensor-core convolutions (BASELINE.json configs[3] asks for bf16)")
     args = ap.parse_args()
