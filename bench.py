@@ -277,10 +277,12 @@ def dominant_kernel_roofline(stats, peaks, total_ms, steps):
         if not any(algorithmic_flops(n, a) for a, _ in kcalls[:1]):
             continue
         for a, m in kcalls:
-            g = shapes.setdefault(launch_signature(n, a), [0, 0.0, 0])
+            g = shapes.setdefault(launch_signature(n, a), [0, 0.0, 0, []])
             g[0] += 1; g[1] += m; g[2] += algorithmic_flops(n, a)
+            if len(g[3]) < 4:
+                g[3].append(round(m, 4))
     common["tensor_shapes"] = {k: {"n": round(v[0] / steps, 2), "ms_per_step": round(v[1] / steps, 4),
-                                   "TFLOPs": round(v[2] / (v[1] * 1e-3) / 1e12, 1) if v[1] > 0 else None}
+                                   "TFLOPs": round(v[2] / (v[1] * 1e-3) / 1e12, 1) if v[1] > 0 else None, "first_calls_ms": v[3]}
                                for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1])}
     fl_all = sum(algorithmic_flops(name, a) for a, _ in all_calls)
     if fl_all:

@@ -108,6 +108,28 @@ def dead_parameters(gen):
     return [p for m in list(gen.to_rgbs)[len(gen.to_rgbs) // 2:] for p in m.parameters()]
 
 
+def flat_grad_views(params, device):
+    """One flat fp32 buffer holding the gradients of `params`; every p.grad becomes a view of it with the parameter's own
+    layout (channels_last Discriminator weights are dense permutations), so backward passes accumulate straight into the
+    buffer the collective reduces -- DDP's gradient_as_bucket_view with a single bucket (reference distributed.py:98-105)."""
+    flat = torch.zeros(sum(p.numel() for p in params), device=device)
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].as_strided(p.size(), p.stride())
+        off += p.numel()
+    return flat
+
+
+def average_gradients(flat, world, dist):
+    """The data-parallel exchange of the train step: ONE all-reduce of the flat gradient buffer, averaged over ranks."""
+    if world > 1:
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        else:                                                           # gloo (CPU tests) has no AVG
+            dist.all_reduce(flat)
+            flat.div_(world)
+
+
 def requires_grad(params, flag):
     for p in params:
         p.requires_grad = flag
@@ -293,15 +315,7 @@ def run(args):
     # the box's host cores (profiles/r2_train_step_scaling.md).
     graphs, graph_launches = {}, {}
     if use_graph:
-        def flat_grads(params):
-            flat = torch.zeros(sum(p.numel() for p in params), device=dev)
-            off = 0
-            for p in params:
-                # same layout as the parameter (channels_last Discriminator weights are dense permutations)
-                p.grad = flat[off:off + p.numel()].as_strided(p.size(), p.stride())
-                off += p.numel()
-            return flat
-        flat_g, flat_d = flat_grads(g_params), flat_grads(d_params)
+        flat_g, flat_d = flat_grad_views(g_params, dev), flat_grad_views(d_params, dev)
         real_static = torch.randn(B, 3, args.size, args.size, device=dev)
         if not args.d_nchw:
             real_static = real_static.contiguous(memory_format=torch.channels_last)
@@ -381,8 +395,7 @@ def run(args):
             graphs[name], graph_launches[name] = gr, _lib.launch_count() - n_before
 
         def reduce_(flat):
-            if world > 1:
-                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            average_gradients(flat, world, dist)
 
         def iteration_graph(i, e2e=False):
             if e2e:

@@ -45,3 +45,46 @@ def test_single_rank_is_identity():
     import bench
     assert bench.max_over_ranks_ms(3.5) == 3.5
     assert bench.whole_job_rate(32, 10, 200.0, 1) == 32 * 10 / 0.2
+
+
+def _grad_worker(rank, world, port, out):
+    """The train step's data-parallel exchange (benchmarks/train_step.py: flat gradient buffer viewed by every p.grad + one
+    averaged all-reduce) against torch's DistributedDataParallel on the same two-rank problem."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sr_train_step", os.path.join(ROOT, "benchmarks", "train_step.py"))
+    ts = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ts)
+
+    def net():
+        torch.manual_seed(7)                               # identical replicas
+        m = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.LeakyReLU(0.2), torch.nn.Conv2d(8, 4, 1))
+        return m.to(memory_format=torch.channels_last)     # strided parameters, like the Discriminator's
+    torch.manual_seed(100 + rank)
+    x = torch.randn(5, 3, 9, 9)                            # this rank's shard
+    ref = torch.nn.parallel.DistributedDataParallel(net())
+    ref(x).square().mean().backward()
+    mine = net()
+    params = list(mine.parameters())
+    flat = ts.flat_grad_views(params, torch.device("cpu"))
+    for _ in range(2):                                     # a second pass must start from zeroed buffers, as the phase graphs do
+        flat.zero_()
+        mine(x).square().mean().backward()
+        assert all(p.grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr() for p in params)
+        ts.average_gradients(flat, world, dist)
+    err = max((p.grad - q.grad).abs().max().item() for p, q in zip(params, ref.module.parameters()))
+    if rank == 0:
+        torch.save({"err": err, "numel": flat.numel(), "want": sum(p.numel() for p in params)}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_matches_ddp(tmp_path):
+    out = str(tmp_path / "grads.pt")
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_grad_worker, args=(2, port, out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["numel"] == r["want"]
+    assert r["err"] < 1e-6, r
