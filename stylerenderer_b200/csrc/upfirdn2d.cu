@@ -1517,6 +1517,210 @@ fir_nhwc_stream_kernel(float *__restrict__ out, const __grid_constant__ CUtensor
     }
 }
 
+// ---- planes (NCHW, minor = 1) 4x4 FIR, row-streaming through a bulk-copy ring (round 2) ---------------------------------
+// The reference layout [major = N*C, H, W] of `op.upfirdn2d`.  Rows of a (2H+1)-wide plane are not 16-byte aligned, so
+// TMA tiles (16-byte strides) and vector loads do not apply; but FULL rows of a plane are contiguous in memory.  A stage
+// of the ring is therefore a 1-D bulk copy (cp.async.bulk) of 4 consecutive input rows: the source is aligned down to 16
+// bytes and the size rounded up (the over-fetch stays inside the tensor: base 16-byte aligned, element count % 4 == 0),
+// consumers address the stage with the 0..3-float lead of that chunk.  Work item = (plane, ~128-row segment), persistent
+// CTAs; consumer lane l of warp w owns output columns 128 w + l + 32 j (j = 0..3): every LDS / STG of a warp touches 32
+// consecutive floats (conflict free, whole 128-byte lines); 4-tap row filter, then one FMA per open output row (register
+// ring, compile-time slots).  Rows outside the plane are skipped (zero), edge columns take predicated loads.
+constexpr int FP_ROWS = 4;
+
+struct FirPlaneGeom {
+    int in_h, in_w, out_h, out_w, pad_x0, pad_y0, nseg, seg_rows, total_items, stages, stage_bytes;
+    FastDiv div_seg;
+};
+
+// J = output columns per consumer lane (32 apart).  Measured: the consumers are LATENCY bound (a serial row loop with short
+// dependent chains), so what counts is consumer warps per SM: J = 1 gives a warp per 32 columns (9 warps for a 257-wide plane).
+template <int J>
+__global__ void __launch_bounds__(32 * (16 / J + 1))
+fir_planes_stream_kernel(float *__restrict__ out, const float *__restrict__ x, const float *__restrict__ taps, const FirPlaneGeom g)
+{
+    extern __shared__ uint8_t fp_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(fp_raw) + 127) & ~(uintptr_t)127);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + g.stages * g.stage_bytes);
+    uint64_t *empty_bar = full_bar + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int consumer_warps = (blockDim.x >> 5) - 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&full_bar[s])), "r"(1u) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&empty_bar[s])), "r"((uint32_t)consumer_warps) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t plane_in = (int64_t)g.in_h * g.in_w;
+
+    if (warp == consumer_warps) {                        // ===== producer warp (one lane)
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            for (uint32_t T = blockIdx.x; T < (uint32_t)g.total_items; T += gridDim.x) {
+                uint32_t m, seg;
+                g.div_seg.divmod(T, m, seg);
+                const int oy_start = seg * g.seg_rows;
+                const int oy_end = min(g.out_h, oy_start + g.seg_rows);
+                const int nstages = (oy_end - oy_start + 3 + FP_ROWS - 1) / FP_ROWS;
+                int iy0 = oy_start - g.pad_y0;
+                for (int k = 0; k < nstages; ++k, iy0 += FP_ROWS) {
+                    ft_mbar_wait(&empty_bar[s], ph ^ 1);
+                    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&full_bar[s]);
+                    const int r0 = max(iy0, 0), r1 = min(iy0 + FP_ROWS, g.in_h);
+                    if (r1 > r0) {
+                        const int64_t idx = (int64_t)m * plane_in + (int64_t)r0 * g.in_w;
+                        const int lead = (int)(idx & 3);
+                        const uint32_t bytes = (uint32_t)(((lead + (r1 - r0) * g.in_w) * 4 + 15) & ~15);
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     :: "r"((uint32_t)__cvta_generic_to_shared(smem + s * g.stage_bytes)), "l"(x + (idx - lead)), "r"(bytes), "r"(bar) : "memory");
+                    } else {
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+                    }
+                    if (++s == (uint32_t)g.stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers
+    constexpr int K = 4;
+    float kv[K], kh[K];
+    const bool sep = fir_rank1_taps(taps, kv, kh);
+    const int col0 = warp * (32 * J) + lane;              // output columns col0 + 32 j
+    bool live[J], edge[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int ox = col0 + 32 * j, ix = ox - g.pad_x0;
+        live[j] = ox < g.out_w;
+        edge[j] = ix < 0 || ix + K - 1 >= g.in_w;
+    }
+    uint32_t s = 0, ph = 0;
+    for (uint32_t T = blockIdx.x; T < (uint32_t)g.total_items; T += gridDim.x) {
+        uint32_t m, seg;
+        g.div_seg.divmod(T, m, seg);
+        const int oy_start = seg * g.seg_rows;
+        const int oy_end = min(g.out_h, oy_start + g.seg_rows);
+        const int nstages = (oy_end - oy_start + 3 + FP_ROWS - 1) / FP_ROWS;
+        const int lead_plane = (int)(((int64_t)m * plane_in) & 3);
+        float *orow = out + ((int64_t)m * g.out_h + oy_start - (K - 1)) * g.out_w + col0;    // row of the output the next step retires
+        float acc[K][J];
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+#pragma unroll
+            for (int j = 0; j < J; ++j) acc[a][j] = 0.0f;
+        int iy0 = oy_start - g.pad_y0;
+        for (int k = 0; k < nstages; ++k, iy0 += FP_ROWS) {
+            ft_mbar_wait(&full_bar[s], ph);
+            const int r0 = max(iy0, 0);
+            const int lead = (lead_plane + r0 * g.in_w) & 3;
+            const float *stg = reinterpret_cast<const float *>(smem + s * g.stage_bytes) + lead + col0 - g.pad_x0;
+#pragma unroll
+            for (int u = 0; u < FP_ROWS; ++u) {
+                const int iy = iy0 + u;
+                if (iy >= 0 && iy < g.in_h) {             // rows outside the plane contribute nothing
+                    const float *row = stg + (iy - r0) * g.in_w;
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        float c[K];
+                        if (!edge[j]) {
+#pragma unroll
+                            for (int b = 0; b < K; ++b) c[b] = row[32 * j + b];
+                        } else {
+                            const int ix = col0 + 32 * j - g.pad_x0;
+#pragma unroll
+                            for (int b = 0; b < K; ++b) c[b] = (live[j] && ix + b >= 0 && ix + b < g.in_w) ? row[32 * j + b] : 0.0f;
+                        }
+                        if (sep) {
+                            float h = 0.0f;
+#pragma unroll
+                            for (int b = 0; b < K; ++b) h = fmaf(c[b], kh[b], h);
+#pragma unroll
+                            for (int a = 0; a < K; ++a) acc[(u - a) & 3][j] = fmaf(h, kv[a], acc[(u - a) & 3][j]);
+                        } else {
+#pragma unroll
+                            for (int a = 0; a < K; ++a)
+#pragma unroll
+                                for (int b = 0; b < K; ++b)
+                                    acc[(u - a) & 3][j] = fmaf(c[b], __ldg(taps + (K - 1 - a) * K + (K - 1 - b)), acc[(u - a) & 3][j]);
+                        }
+                    }
+                }
+                const int oy = oy_start + k * FP_ROWS + u - (K - 1);
+                if ((k > 0 || u == K - 1) && oy < oy_end) {
+#pragma unroll
+                    for (int j = 0; j < J; ++j)
+                        if (live[j]) orow[32 * j] = acc[(u + 1) & 3][j];
+                }
+#pragma unroll
+                for (int j = 0; j < J; ++j) acc[(u + 1) & 3][j] = 0.0f;
+                orow += g.out_w;
+            }
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"((uint32_t)__cvta_generic_to_shared(&empty_bar[s])) : "memory");
+            if (++s == (uint32_t)g.stages) { s = 0; ph ^= 1; }
+        }
+    }
+}
+
+// Streaming path of the planes blur: SR_ERR_UNSUPPORTED when the shape does not qualify (the tile kernels take over).
+int launch_planes_stream(float *out, const float *x, const float *taps, int64_t major, int in_h, int in_w, int oh, int ow,
+                         int pad_x0, int pad_y0, cudaStream_t st)
+{
+    const char *off = getenv("SR_FIR_PLANES_STREAM");           // A/B switch, read per call: 0 = the tile / strip kernels
+    if (off && off[0] == '0') return SR_ERR_UNSUPPORTED;
+    if (ow < 64 || ow > 512 || oh < 16 || in_w < 8 || in_w > 1024) return SR_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) & 15u) || (major * (int64_t)in_h * in_w) % 4 != 0) return SR_ERR_UNSUPPORTED;
+    FirPlaneGeom g;
+    g.in_h = in_h; g.in_w = in_w; g.out_h = oh; g.out_w = ow; g.pad_x0 = pad_x0; g.pad_y0 = pad_y0;
+    g.nseg = (oh + 64) / 128 > 0 ? (oh + 64) / 128 : 1;
+    g.seg_rows = (oh + g.nseg - 1) / g.nseg;
+    const int64_t total = major * g.nseg;
+    if (total >= 0x7fffffffll) return SR_ERR_UNSUPPORTED;
+    g.total_items = (int)total;
+    g.div_seg = FastDiv((uint32_t)g.nseg);
+    g.stage_bytes = ((FP_ROWS * in_w * 4 + 16 + 127) / 128) * 128;
+    const char *st_env = getenv("SR_FIR_PLANES_STAGES");          // experiment switches, read per call
+    const char *j_env = getenv("SR_FIR_PLANES_J");
+    g.stages = st_env ? atoi(st_env) : 8;
+    if (g.stages > 16) g.stages = 16;
+    if (g.stages < 2) g.stages = 2;
+    // measured (scratch/planes_sweep.py, B200; fraction of the copy bandwidth, tile kernels -> this kernel):
+    //   257^2 -> 256^2: 0.41 -> 0.54 (J = 2 or 4)   256^2 -> 257^2: 0.32 -> 0.45 (J = 4)   129^2 -> 128^2: 0.40 -> 0.46 (J = 2)
+    //   128^2 -> 129^2: 0.26 -> 0.31 (J = 2)        64^2 -> 65^2: 0.14 -> 0.22 (J = 2)     65^2 -> 64^2: 0.36 (tile kernel) vs 0.23
+    // The kernel is ISSUE bound (4-byte LDS / STG per lane: ~25 instructions per output); J = 1 (more warps) is slowest.
+    if (!j_env && ow < 100 && in_w % 4 != 0) return SR_ERR_UNSUPPORTED;
+    const int J = j_env ? atoi(j_env) : (ow >= 200 ? 4 : 2);
+    if (J != 1 && J != 2 && J != 4) return SR_ERR_UNSUPPORTED;
+    const int consumer_warps = (ow + 32 * J - 1) / (32 * J);
+    if (consumer_warps > 16 / J) return SR_ERR_UNSUPPORTED;
+    const int threads = 32 * (consumer_warps + 1);
+    const size_t smem = 128 + (size_t)g.stages * g.stage_bytes + 32 * sizeof(uint64_t);
+    if (smem > 100 * 1024) return SR_ERR_UNSUPPORTED;
+    int per_sm = (int)(220 * 1024 / (smem + 1024));
+    if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+    if (per_sm > 16) per_sm = 16;
+    if (per_sm < 1) return SR_ERR_UNSUPPORTED;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(fir_planes_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(fir_planes_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(fir_planes_stream_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+            return SR_ERR_UNSUPPORTED;
+        configured = true;
+    }
+    const int64_t slots = (int64_t)per_sm * kNumSMs;
+    const int grid = (int)(total < slots ? total : slots);
+    if (J == 1) fir_planes_stream_kernel<1><<<grid, threads, smem, st>>>(out, x, taps, g);
+    else if (J == 2) fir_planes_stream_kernel<2><<<grid, threads, smem, st>>>(out, x, taps, g);
+    else fir_planes_stream_kernel<4><<<grid, threads, smem, st>>>(out, x, taps, g);
+    return SR_OK;
+}
+
 // ---- generic: one thread per output element, any geometry ---------------------------------------
 struct GenericGeom {
     int64_t major, minor, total;
@@ -1938,7 +2142,10 @@ extern "C" int sr_upfirdn2d_f32(float *out, const float *x, const float *taps,
 #define SR_TILE(UP, DOWN, PHX, PHY, VY) \
     rc = launch_tile<UP, DOWN, 4, 4, PHX, PHY, VY>(out, x, taps, major, (int)in_h, (int)in_w, (int)oh, (int)ow, \
                                                    pad_x0, pad_y0, st)
-        if (up_x == 1 && down_x == 1 && pad_x0 == pad_y0 &&
+        if (up_x == 1 && down_x == 1 &&
+            launch_planes_stream(out, x, taps, major, (int)in_h, (int)in_w, (int)oh, (int)ow, pad_x0, pad_y0, st) == SR_OK) {
+            rc = SR_OK;
+        } else if (up_x == 1 && down_x == 1 && pad_x0 == pad_y0 &&
             launch_blur_rows(out, x, taps, major, (int)in_h, (int)in_w, (int)oh, (int)ow, pad_x0, pad_y0, st) == SR_OK) {
             rc = SR_OK;
         } else if (up_x == 1 && down_x == 1) {

@@ -156,6 +156,30 @@ def test_upfirdn2d_separable_taps(op, shape, pad):
         torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("rank1", [True, False])
+@pytest.mark.parametrize("shape,pad", [((4, 1, 257, 257), (1, 1)), ((2, 2, 256, 256), (2, 2)), ((1, 4, 100, 513), (1, 1)),
+                                       ((2, 2, 130, 70), (2, 1)), ((1, 4, 64, 96), (-1, 2)), ((4, 1, 300, 64), (0, 3)),
+                                       ((1, 8, 17, 385), (3, 3)), ((2, 2, 16, 66), (1, 1))])
+def test_upfirdn2d_planes_stream_kernel(op, shape, pad, rank1, monkeypatch):
+    """The row-streaming bulk-copy blur of the reference layout ([N*C, H, W] planes, reference op/upfirdn2d.py:99;
+    fir_planes_stream_kernel: planes >= 16 rows x 64..512 columns) against the oracle: unaligned 257-wide rows (every
+    chunk lead 0..3), several row segments, ragged last warp, asymmetric and negative pads, separable and general taps;
+    and bit-equal shapes / near-equal values against the tile kernels it replaces (SR_FIR_PLANES_STREAM=0)."""
+    x = seeded(shape, 40)
+    if rank1:
+        k = torch.outer(torch.tensor([1., 3., 3., 1.]), seeded((4,), 41))
+        k = k / k.abs().sum()
+    else:
+        k = seeded((4, 4), 42)
+    want = O.upfirdn2d(x, k, 1, 1, pad)
+    got = op.upfirdn2d(cuda(x), cuda(k), pad=pad)
+    assert got.shape == want.shape
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-5, atol=1e-5)
+    monkeypatch.setenv("SR_FIR_PLANES_STREAM", "0")
+    old = op.upfirdn2d(cuda(x), cuda(k), pad=pad)
+    torch.testing.assert_close(got, old, rtol=1e-5, atol=1e-5)
+
+
 @pytest.mark.parametrize("shape,pad", [((2, 8, 9, 9), (1, 1)), ((1, 128, 33, 33), (1, 1)), ((3, 12, 16, 16), (2, 2)),
                                        ((2, 64, 5, 7), (2, 1)), ((1, 4, 64, 64), (2, 2)),
                                        # TMA-staged tile kernel (C % 32 == 0, output >= 32 x 32), ragged edges and pads
