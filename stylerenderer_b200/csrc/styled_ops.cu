@@ -322,7 +322,7 @@ static int styled_bwd_prologue_any(float *ga, float *g_bias, float *g_noise_w, f
     p.ga_bf16 = (ga_bf16 && d) ? 1 : 0;
     const unsigned nb = (unsigned)(batch * p.chunks_per_image);
     // kernels specialised on the inputs present (see styled_bwd_prologue_kernel); SR_PROLOGUE_SPEC=0: run-time checks only
-    static const char *spec_env = getenv("SR_PROLOGUE_SPEC");
+    const char *spec_env = getenv("SR_PROLOGUE_SPEC");          // read per call (A/B runs in one process)
     const int spec = (gy ? kSpecGy : 0) | (gxs ? kSpecGxs : 0) | (g_rgb ? kSpecRgb : 0) | (e ? kSpecE : 0) |
                      (noise ? kSpecNoise : 0) | (d ? kSpecD : 0);
     bool launched = false;
@@ -333,7 +333,18 @@ static int styled_bwd_prologue_any(float *ga, float *g_bias, float *g_noise_w, f
     // Measured again: 2.48 ms with them, 2.44 ms without (profiles/r2_prologue_spec.md) -- the specialised ToRGB kernels still
     // spill 16-36 B at 80 registers, so they stay opt-in (SR_PROLOGUE_SPEC=1).
     const bool spec_rgb = spec_env && spec_env[0] == '1';
-    if (!(spec_env && spec_env[0] == '0') && !stylemap && (spec_rgb || !g_rgb)) {
+    const bool spec_rgb2 = spec_env && spec_env[0] == '2';          // experiment: ToRGB combinations at 128 registers, 2 pixels / iteration
+    if (spec_rgb2 && !stylemap && g_rgb) {
+        launched = true;
+        switch (spec) {
+        case kSpecGxs | kSpecRgb | kSpecE | kSpecNoise | kSpecD:
+            styled_bwd_prologue_kernel<false, kSpecGxs | kSpecRgb | kSpecE | kSpecNoise | kSpecD, 2, 2><<<nb, kThreads, 0, st>>>(p); break;
+        case kSpecGy | kSpecRgb | kSpecE | kSpecNoise | kSpecD:
+            styled_bwd_prologue_kernel<false, kSpecGy | kSpecRgb | kSpecE | kSpecNoise | kSpecD, 2, 2><<<nb, kThreads, 0, st>>>(p); break;
+        default: launched = false;
+        }
+    }
+    if (!launched && !(spec_env && spec_env[0] == '0') && !stylemap && (spec_rgb || !g_rgb)) {
         launched = true;
         switch (spec) {                                   // the combinations the chained generator produces
         case kSpecGxs | kSpecE | kSpecNoise:                                     // up-sampling block

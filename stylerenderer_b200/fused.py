@@ -315,55 +315,122 @@ class PlainConvTC(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, scale, kind, alpha, gain):
         x_nhwc = to_nhwc(x)
-        b, h, w, cin = x_nhwc.shape
-        cout, _, k, _ = weight.shape
-        xr = tc.modulate(x_nhwc)
-        wk_f, wk_t, _ = tc.weight_prep_dual(weight, scale, kind == "s1", want_wsq=False)
-        act = bias is not None
-        kw = dict(epilogue=1, bias=bias, alpha=alpha, gain=gain) if act else dict(epilogue=0)
-        if kind == "s1":
-            y = tc.conv3x3(xr, wk_f, **kw)
-        else:
-            oh, ow = (h - k) // 2 + 1, (w - k) // 2 + 1
-            y = torch.empty(b, oh, ow, cout, dtype=torch.float32, device=x.device)
-            taps = TAPS_S2 if k == 3 else [(0, 0, 0)]
-            tc.conv_igemm(xr, wk_f, taps, y, in_stride=2, **kw)
-        ctx.save_for_backward(xr, y if act else None, wk_t, bias)
-        ctx.cfg = (scale, kind, alpha, gain, k, cin, cout, (h, w))
-        ctx.exact_fwd = tc._exact()
-        return from_nhwc(y)
+        return from_nhwc(_plain_conv_forward(ctx, tc.modulate(x_nhwc), weight, bias, scale, kind, alpha, gain))
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
-        xr, y, wk_t, bias = ctx.saved_tensors
-        xr, wk_t = _mode_operand(ctx, xr), _mode_operand(ctx, wk_t)
-        scale, kind, alpha, gain, k, cin, cout, (h, w) = ctx.cfg
-        gy = to_nhwc(gy)
-        b, oh, ow, _ = gy.shape
-        g_bias = None
-        if y is not None:       # activation backward + bias gradient + tf32 operand in one pass (d = 1)
-            ga, g_bias, _, _ = tc.bwd_prologue(gy, y, None, None, bias, _ones(b, cout, gy.device), alpha, gain, False)
-        else:
-            ga = tc.modulate(gy)
-        need_w = ctx.needs_input_grad[1]          # False in the generator's step of the GAN loop (reference train.py:292-293)
-        dwk = None
-        if kind == "s1":
-            dx = tc.conv3x3(ga, wk_t)
-            if need_w:
-                dwk = tc.wgrad3x3(ga, xr)
-        elif kind == "s2":
-            dx = tc.conv_transpose3x3_s2(ga, wk_t)
-            if need_w:
-                dwk = tc.wgrad(ga, xr, [(0, 0, ky, kx, ky * 3 + kx) for ky in range(3) for kx in range(3)], (oh, ow),
-                               x_stride=2)
-        else:
-            dx = torch.zeros(b, h, w, cin, dtype=torch.float32, device=gy.device)
-            tc.conv_igemm_multi(ga, wk_t, [([(0, 0, 0)], (oh, ow), (0, 0))], dx, out_stride=2)
-            if need_w:
-                dwk = tc.wgrad(ga, xr, [(0, 0, 0, 0, 0)], (oh, ow), x_stride=2, taps_total=1)
-        g_w = style.weight_grad_layout(dwk, scale, cout, cin, k)[0] if need_w else None
+        dx, g_w, g_bias = _plain_conv_backward(ctx, gy)
         return from_nhwc(dx), g_w, g_bias, None, None, None, None
+
+
+def _plain_conv_forward(ctx, xr, weight, bias, scale, kind, alpha, gain):
+    """Shared forward of PlainConvTC / BlurConvTC from the GEMM operand xr [B,H,W,Cin] (tf32-rounded fp32 or bf16)."""
+    b, h, w, cin = xr.shape
+    cout, _, k, _ = weight.shape
+    wk_f, wk_t, _ = tc.weight_prep_dual(weight, scale, kind == "s1", want_wsq=False)
+    act = bias is not None
+    kw = dict(epilogue=1, bias=bias, alpha=alpha, gain=gain) if act else dict(epilogue=0)
+    if kind == "s1":
+        y = tc.conv3x3(xr, wk_f, **kw)
+    else:
+        oh, ow = (h - k) // 2 + 1, (w - k) // 2 + 1
+        y = torch.empty(b, oh, ow, cout, dtype=torch.float32, device=xr.device)
+        taps = TAPS_S2 if k == 3 else [(0, 0, 0)]
+        tc.conv_igemm(xr, wk_f, taps, y, in_stride=2, **kw)
+    ctx.save_for_backward(xr, y if act else None, wk_t, bias)
+    ctx.cfg = (scale, kind, alpha, gain, k, cin, cout, (h, w))
+    ctx.exact_fwd = tc._exact()
+    return y
+
+
+def _plain_conv_backward(ctx, gy):
+    """-> (dx [B,H,W,Cin] fp32 w.r.t. the conv's input, g_weight or None, g_bias or None)."""
+    xr, y, wk_t, bias = ctx.saved_tensors
+    xr, wk_t = _mode_operand(ctx, xr), _mode_operand(ctx, wk_t)
+    scale, kind, alpha, gain, k, cin, cout, (h, w) = ctx.cfg
+    gy = to_nhwc(gy)
+    b, oh, ow, _ = gy.shape
+    g_bias = None
+    if y is not None:       # activation backward + bias gradient + tf32 operand in one pass (d = 1)
+        ga, g_bias, _, _ = tc.bwd_prologue(gy, y, None, None, bias, _ones(b, cout, gy.device), alpha, gain, False)
+    else:
+        ga = tc.modulate(gy)
+    need_w = ctx.needs_input_grad[1]          # False in the generator's step of the GAN loop (reference train.py:292-293)
+    dwk = None
+    if kind == "s1":
+        dx = tc.conv3x3(ga, wk_t)
+        if need_w:
+            dwk = tc.wgrad3x3(ga, xr)
+    elif kind == "s2":
+        dx = tc.conv_transpose3x3_s2(ga, wk_t)
+        if need_w:
+            dwk = tc.wgrad(ga, xr, [(0, 0, ky, kx, ky * 3 + kx) for ky in range(3) for kx in range(3)], (oh, ow),
+                           x_stride=2)
+    else:
+        dx = torch.zeros(b, h, w, cin, dtype=torch.float32, device=gy.device)
+        tc.conv_igemm_multi(ga, wk_t, [([(0, 0, 0)], (oh, ow), (0, 0))], dx, out_stride=2)
+        if need_w:
+            dwk = tc.wgrad(ga, xr, [(0, 0, 0, 0, 0)], (oh, ow), x_stride=2, taps_total=1)
+    g_w = style.weight_grad_layout(dwk, scale, cout, cin, k)[0] if need_w else None
+    return dx, g_w, g_bias
+
+
+class BlurConvTC(Function):
+    """Blur -> EqualConv2d (+ FusedLeakyReLU): the down-sampling ConvLayers of the Discriminator's ResBlocks (reference
+    layers.py:346-351, 379-391).  The 4x4 FIR writes the GEMM OPERAND (tf32-rounded / bf16) directly -- no fp32 blurred tensor,
+    no separate operand pass (6 instead of 14 bytes per element around the blur) -- and the backward runs the FIR's adjoint
+    (flipped taps, pads 3 - p) on the dgrad output inside the same Function."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, scale, kind, alpha, gain, taps, pad):
+        x_nhwc = to_nhwc(x)
+        b, _, _, cin = x_nhwc.shape
+        xr, _ = tc.blur_scaledot(x_nhwc, taps, pad, _ones(b, cin, x.device))
+        ctx.blur = (taps, pad)
+        return from_nhwc(_plain_conv_forward(ctx, xr, weight, bias, scale, kind, alpha, gain))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        dxb, g_w, g_bias = _plain_conv_backward(ctx, gy)
+        taps, (p0, p1) = ctx.blur
+        dx = None
+        if ctx.needs_input_grad[0]:
+            kh = taps.shape[0]
+            dx = upfirdn2d_raw(dxb, torch.flip(taps, [0, 1]), 1, 1, 1, 1, kh - 1 - p0, kh - 1 - p1, kh - 1 - p0, kh - 1 - p1)
+        return (from_nhwc(dx) if dx is not None else None), g_w, g_bias, None, None, None, None, None, None
+
+
+def env_blur_conv():
+    """A/B switch: SR_BLUR_CONV=0 keeps Blur and the convolution as two autograd nodes (round-1 form)."""
+    import os
+    return os.environ.get("SR_BLUR_CONV", "1") != "0"
+
+
+def blur_conv_supported(conv, blur, x):
+    """Shapes BlurConvTC takes: a 4x4 FIR in front of a tensor-core-supported stride-2 EqualConv2d."""
+    if blur.kernel.shape != (4, 4) or not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
+        return None
+    p0, p1 = blur.pad
+    bh, bw = x.shape[2] + p0 + p1 - 3, x.shape[3] + p0 + p1 - 3
+    if bh < 1 or bw < 1:
+        return None
+    k = conv.weight.shape[2]
+    cout, cin = conv.weight.shape[:2]
+    kind = {(3, 2, 0): "s2", (1, 2, 0): "p2"}.get((k, conv.stride, conv.padding))
+    if kind is None or not (tc.supported(cin, cout) and tc.supported(cout, cin)):
+        return None
+    if kind == "s2" and (bh % 2 == 0 or bw % 2 == 0):
+        return None
+    return kind
+
+
+def blur_conv(conv, act, blur, x, kind):
+    if act is not None:
+        bias = act.bias if conv.bias is None else act.bias + conv.bias
+        return BlurConvTC.apply(x, conv.weight, bias, conv.scale, kind, act.negative_slope, act.scale, blur.kernel, tuple(blur.pad))
+    return BlurConvTC.apply(x, conv.weight, None, conv.scale, kind, 0.2, 1.0, blur.kernel, tuple(blur.pad))
 
 
 def plain_conv_supported(conv, x):

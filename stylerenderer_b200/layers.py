@@ -312,6 +312,10 @@ class ConvLayer(nn.Sequential):                       # reference layers.py:341-
                 from . import fused
                 if blur is None and isinstance(act, FusedLeakyReLU) and fused.stem_conv_supported(conv, act, input):
                     return fused.stem_conv(conv, act, input)          # 3 -> C pointwise stem: one bandwidth pass
+                if blur is not None and not dd and fused.env_blur_conv():
+                    kind = fused.blur_conv_supported(conv, blur, input)
+                    if kind is not None:                              # FIR writes the GEMM operand directly (fused.BlurConvTC)
+                        return fused.blur_conv(conv, act, blur, input, kind)
                 x = blur(input) if blur is not None else input
                 kind = fused.plain_conv_supported(conv, x)
                 if kind is not None:
