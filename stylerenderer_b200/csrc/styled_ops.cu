@@ -333,7 +333,9 @@ static int styled_bwd_prologue_any(float *ga, float *g_bias, float *g_noise_w, f
     // Measured again: 2.48 ms with them, 2.44 ms without (profiles/r2_prologue_spec.md) -- the specialised ToRGB kernels still
     // spill 16-36 B at 80 registers, so they stay opt-in (SR_PROLOGUE_SPEC=1).
     const bool spec_rgb = spec_env && spec_env[0] == '1';
-    const bool spec_rgb2 = spec_env && spec_env[0] == '2';          // experiment: ToRGB combinations at 128 registers, 2 pixels / iteration
+    // ToRGB combinations at up to 128 registers (106 used, no spill), 2 pixels per iteration: 2.475 -> 2.438 ms per step (default;
+    // SR_PROLOGUE_SPEC=3 = the run-time kernel for them, as before)
+    const bool spec_rgb2 = !spec_env || spec_env[0] == '2';
     if (spec_rgb2 && !stylemap && g_rgb) {
         launched = true;
         switch (spec) {

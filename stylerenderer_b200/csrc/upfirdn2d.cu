@@ -1086,6 +1086,21 @@ __device__ __forceinline__ void ft_mbar_wait(uint64_t *bar, uint32_t parity) {
         :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
+// Shared-memory loads by 32-bit shared address.  The ring kernels carve their stages out of the dynamic shared array with
+// integer pointer arithmetic (128-byte alignment), after which the compiler no longer knows the address space and emits
+// GENERIC loads (LD.E: long-scoreboard latency) for every stage read; these keep them LDS.  volatile: never moved across the
+// mbarrier waits (also volatile asm).
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds_f1(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
 template <int MODE, int FT_H, int TR>     // MODE 0 plain, 1 styled forward tail (+ optional out2), 2 scale-dot backward tail
 __global__ void __launch_bounds__(FT_CONSUMERS + 32, FT_H == 32 ? 1 : 2)   // FT_H = 32: one CTA per SM, 16: two; TR < 4: timing experiment only
 fir_nhwc_tma_kernel(float *__restrict__ out, const __grid_constant__ CUtensorMap tmap_x, const float *__restrict__ taps,
@@ -1429,7 +1444,7 @@ fir_nhwc_stream_kernel(float *__restrict__ out, const __grid_constant__ CUtensor
                 if (MODE == 2 && emit && g.other) tt_[u] = __ldg(reinterpret_cast<const float4 *>(g.other + (pix0 + opix) * g.c + ch));
             }
             ft_mbar_wait(&full_bar[s], ph);
-            const float4 *stg = reinterpret_cast<const float4 *>(smem + s * FS_STAGE_BYTES) + col * (FS_C / 4) + quad;
+            const uint32_t stg = (uint32_t)__cvta_generic_to_shared(smem + s * FS_STAGE_BYTES) + (col * (FS_C / 4) + quad) * 16;
 #pragma unroll
             for (int u = 0; u < FS_ROWS; ++u) {
                 const int oy = oy_start + k * FS_ROWS + u - (K - 1);        // the output row this step completes
@@ -1438,13 +1453,13 @@ fir_nhwc_stream_kernel(float *__restrict__ out, const __grid_constant__ CUtensor
                 float add = add_[u], m0 = m0_[u];
                 const float4 tt = tt_[u];
                 if (MODE == 1) {
-                    const float *side = reinterpret_cast<const float *>(smem + s * FS_STAGE_BYTES + FS_X_BYTES) + u * FS_W + col;
-                    if (nz_tma) add = nw * side[0];
-                    if (map_tma) { m0 = side[FS_NOISE_BYTES / 4]; add += side[FS_NOISE_BYTES / 4 + FS_ROWS * FS_W]; }
+                    const uint32_t side = (uint32_t)__cvta_generic_to_shared(smem + s * FS_STAGE_BYTES + FS_X_BYTES) + (u * FS_W + col) * 4;
+                    if (nz_tma) add = nw * lds_f1(side);
+                    if (map_tma) { m0 = lds_f1(side + FS_NOISE_BYTES); add += lds_f1(side + FS_NOISE_BYTES + FS_ROWS * FS_W * 4); }
                 }
                 float4 cur[K];
 #pragma unroll
-                for (int b = 0; b < K; ++b) cur[b] = stg[(u * FS_IW + b) * (FS_C / 4)];
+                for (int b = 0; b < K; ++b) cur[b] = lds_f4(stg + (u * FS_IW + b) * (FS_C / 4) * 16);
                 if (sep) {
                     float4 h = zero;
 #pragma unroll
@@ -1530,6 +1545,7 @@ constexpr int FP_ROWS = 4;
 
 struct FirPlaneGeom {
     int in_h, in_w, out_h, out_w, pad_x0, pad_y0, nseg, seg_rows, total_items, stages, stage_bytes;
+    int debug;                    // profiling only (SR_FIR_PLANES_DEBUG): bit 0 = no stores, bit 1 = no filter arithmetic
     FastDiv div_seg;
 };
 
@@ -1667,6 +1683,195 @@ fir_planes_stream_kernel(float *__restrict__ out, const float *__restrict__ x, c
     }
 }
 
+// ---- planes FIR, vectorised consumers (round 2, second form) -------------------------------------------------------------
+// fir_planes_stream_kernel above is ISSUE bound: 4-byte LDS / STG per lane, ~25 instructions per output.  Same ring, but a
+// consumer thread owns FOUR ADJACENT output columns: the 7 inputs of a row come from three ALIGNED LDS.128 (12 floats) and a
+// compile-time selection by the row's misalignment a = (chunk lead + row offset - pad) mod 4, which is uniform over the CTA
+// (a 4-way switch around the row body); aligned output rows leave as STG.128, unaligned ones (odd widths) as four scalar
+// stores.  The <= 3 columns beyond the last full quad are a scalar side job of warp 0.  ~12 instructions per output.
+// rank-1 taps (every FIR the model builds): 4-tap row filter, then one FMA per open output row
+template <int A, int U>
+__device__ __forceinline__ void fpv_row(uint32_t q4, const float (&kh)[4], const float (&kv)[4], float (&acc)[4][4])
+{
+    const float4 v0 = lds_f4(q4), v1 = lds_f4(q4 + 16), v2 = lds_f4(q4 + 32);
+    const float f[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float h = 0.0f;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) h = fmaf(f[A + j + b], kh[b], h);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) acc[(U - a) & 3][j] = fmaf(h, kv[a], acc[(U - a) & 3][j]);
+    }
+}
+
+// general (rank > 1) taps: rare; a compact rolled loop over the tap column with scalar shared-memory reads, so that the hot
+// loop stays small (ncu: the first version of this kernel, both forms inlined 16 times, stalled on instruction fetch)
+template <int U>
+__device__ __forceinline__ void fpv_row_general(uint32_t srow, const float *__restrict__ taps, float (&acc)[4][4])
+{
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {
+        const float c0 = lds_f1(srow + 4 * b), c1 = lds_f1(srow + 4 * b + 4), c2 = lds_f1(srow + 4 * b + 8), c3 = lds_f1(srow + 4 * b + 12);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const float kk = __ldg(taps + (3 - a) * 4 + (3 - b));
+            acc[(U - a) & 3][0] = fmaf(c0, kk, acc[(U - a) & 3][0]); acc[(U - a) & 3][1] = fmaf(c1, kk, acc[(U - a) & 3][1]);
+            acc[(U - a) & 3][2] = fmaf(c2, kk, acc[(U - a) & 3][2]); acc[(U - a) & 3][3] = fmaf(c3, kk, acc[(U - a) & 3][3]);
+        }
+    }
+}
+
+// Interior quads [e0, e1) -- all 7 inputs of every row inside the plane -- run the vector path with no masking at all; the
+// columns of the edge quads and the <= 3 columns past the last full quad (at most 32 in total) are a scalar side job of the
+// lanes of warp 0 with predicated loads.
+__global__ void __launch_bounds__(32 * 5)
+fir_planes_vec_kernel(float *__restrict__ out, const float *__restrict__ x, const float *__restrict__ taps, const FirPlaneGeom g,
+                      const int e0, const int e1)
+{
+    extern __shared__ uint8_t fp_raw[];
+    // 128 bytes of slack in front of stage 0: an aligned quad may start up to 12 bytes before a chunk
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(fp_raw) + 127) & ~(uintptr_t)127) + 128;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + g.stages * g.stage_bytes);
+    uint64_t *empty_bar = full_bar + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int consumer_warps = (blockDim.x >> 5) - 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&full_bar[s])), "r"(1u) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&empty_bar[s])), "r"((uint32_t)consumer_warps) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t plane_in = (int64_t)g.in_h * g.in_w;
+
+    if (warp == consumer_warps) {                        // ===== producer warp (one lane): as fir_planes_stream_kernel
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            for (uint32_t T = blockIdx.x; T < (uint32_t)g.total_items; T += gridDim.x) {
+                uint32_t m, seg;
+                g.div_seg.divmod(T, m, seg);
+                const int oy_start = seg * g.seg_rows;
+                const int oy_end = min(g.out_h, oy_start + g.seg_rows);
+                const int nstages = (oy_end - oy_start + 3 + FP_ROWS - 1) / FP_ROWS;
+                int iy0 = oy_start - g.pad_y0;
+                for (int k = 0; k < nstages; ++k, iy0 += FP_ROWS) {
+                    ft_mbar_wait(&empty_bar[s], ph ^ 1);
+                    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&full_bar[s]);
+                    const int r0 = max(iy0, 0), r1 = min(iy0 + FP_ROWS, g.in_h);
+                    if (r1 > r0) {
+                        const int64_t idx = (int64_t)m * plane_in + (int64_t)r0 * g.in_w;
+                        const int lead = (int)(idx & 3);
+                        const uint32_t bytes = (uint32_t)(((lead + (r1 - r0) * g.in_w) * 4 + 15) & ~15);
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     :: "r"((uint32_t)__cvta_generic_to_shared(smem + s * g.stage_bytes)), "l"(x + (idx - lead)), "r"(bytes), "r"(bar) : "memory");
+                    } else {
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+                    }
+                    if (++s == (uint32_t)g.stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers: thread t owns the interior quad t (output columns 4t .. 4t+3, e0 <= t < e1); lane l of warp 0 also owns
+    // side column l (l < 4 e0) or 4 e1 + l - 4 e0
+    float kv[4], kh[4];
+    const bool sep = fir_rank1_taps(taps, kv, kh);
+    const int t = threadIdx.x;
+    const bool quad_live = t >= e0 && t < e1;
+    const int sx = lane < 4 * e0 ? lane : 4 * e1 + lane - 4 * e0;              // side column of this lane
+    const bool side_live = warp == 0 && sx < g.out_w;
+    const int six = sx - g.pad_x0;                                             // its first input column
+    const bool out_vec = (g.out_w & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+    uint32_t s = 0, ph = 0;
+    for (uint32_t T = blockIdx.x; T < (uint32_t)g.total_items; T += gridDim.x) {
+        uint32_t m, seg;
+        g.div_seg.divmod(T, m, seg);
+        const int oy_start = seg * g.seg_rows;
+        const int oy_end = min(g.out_h, oy_start + g.seg_rows);
+        const int nstages = (oy_end - oy_start + 3 + FP_ROWS - 1) / FP_ROWS;
+        const int lead_plane = (int)(((int64_t)m * plane_in) & 3);
+        float *orow = out + ((int64_t)m * g.out_h + oy_start - 3) * g.out_w;       // output row the next step retires
+        float acc[4][4], tacc[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            tacc[a] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[a][j] = 0.0f;
+        }
+        int iy0 = oy_start - g.pad_y0;
+        for (int k = 0; k < nstages; ++k, iy0 += FP_ROWS) {
+            ft_mbar_wait(&full_bar[s], ph);
+            const int r0 = max(iy0, 0);
+            const uint32_t stage = (uint32_t)__cvta_generic_to_shared(smem + s * g.stage_bytes);
+            // stage float index of the first tap of output column 0 in input row iy0 (rows advance by in_w)
+            int base = ((lead_plane + r0 * g.in_w) & 3) + (iy0 - r0) * g.in_w - g.pad_x0;
+            // one step per input row; U = ring phase (compile time): the row is tap a of the output row in slot (U - a) & 3,
+            // the output row in slot (U + 1) & 3 is complete after it
+#define FPV_STEP(U)                                                                                                      \
+            {                                                                                                            \
+                const int iy = iy0 + U;                                                                                  \
+                if (iy >= 0 && iy < g.in_h && !(g.debug & 2)) {                                                          \
+                    const int a = base & 3;                                  /* two's complement: right for base < 0 too */ \
+                    if (quad_live) {                                                                                     \
+                        if (sep) {                                                                                       \
+                            const uint32_t q4 = stage + (base - a) * 4 + t * 16;                                         \
+                            switch (a) {                                                                                 \
+                            case 0: fpv_row<0, U>(q4, kh, kv, acc); break;                                               \
+                            case 1: fpv_row<1, U>(q4, kh, kv, acc); break;                                               \
+                            case 2: fpv_row<2, U>(q4, kh, kv, acc); break;                                               \
+                            default: fpv_row<3, U>(q4, kh, kv, acc); break;                                              \
+                            }                                                                                            \
+                        } else {                                                                                         \
+                            fpv_row_general<U>(stage + (base + 4 * t) * 4, taps, acc);                                   \
+                        }                                                                                                \
+                    }                                                                                                    \
+                    if (side_live) {                                                                                     \
+                        const uint32_t row = stage + (base + sx) * 4;                                                    \
+                        float c[4];                                                                                      \
+                        _Pragma("unroll") for (int b = 0; b < 4; ++b) c[b] = (six + b >= 0 && six + b < g.in_w) ? lds_f1(row + 4 * b) : 0.0f; \
+                        if (sep) {                                                                                       \
+                            float h = 0.0f;                                                                              \
+                            _Pragma("unroll") for (int b = 0; b < 4; ++b) h = fmaf(c[b], kh[b], h);                      \
+                            _Pragma("unroll") for (int a2 = 0; a2 < 4; ++a2) tacc[(U - a2) & 3] = fmaf(h, kv[a2], tacc[(U - a2) & 3]); \
+                        } else {                                                                                         \
+                            _Pragma("unroll") for (int a2 = 0; a2 < 4; ++a2)                                             \
+                                _Pragma("unroll") for (int b = 0; b < 4; ++b)                                            \
+                                    tacc[(U - a2) & 3] = fmaf(c[b], __ldg(taps + (3 - a2) * 4 + (3 - b)), tacc[(U - a2) & 3]); \
+                        }                                                                                                \
+                    }                                                                                                    \
+                }                                                                                                        \
+                base += g.in_w;                                                                                          \
+                const int oy = oy_start + k * FP_ROWS + U - 3;                                                           \
+                if ((k > 0 || U == 3) && oy < oy_end && !(g.debug & 1)) {                                                \
+                    constexpr int D = (U + 1) & 3;                                                                       \
+                    if (quad_live) {                                                                                     \
+                        float *o = orow + 4 * t;                                                                         \
+                        if (out_vec) *reinterpret_cast<float4 *>(o) = make_float4(acc[D][0], acc[D][1], acc[D][2], acc[D][3]); \
+                        else { o[0] = acc[D][0]; o[1] = acc[D][1]; o[2] = acc[D][2]; o[3] = acc[D][3]; }                 \
+                    }                                                                                                    \
+                    if (side_live) orow[sx] = tacc[D];                                                                   \
+                }                                                                                                        \
+                _Pragma("unroll") for (int j = 0; j < 4; ++j) acc[(U + 1) & 3][j] = 0.0f;                                \
+                tacc[(U + 1) & 3] = 0.0f;                                                                                \
+                orow += g.out_w;                                                                                         \
+            }
+            FPV_STEP(0) FPV_STEP(1) FPV_STEP(2) FPV_STEP(3)
+#undef FPV_STEP
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"((uint32_t)__cvta_generic_to_shared(&empty_bar[s])) : "memory");
+            if (++s == (uint32_t)g.stages) { s = 0; ph ^= 1; }
+        }
+    }
+}
+
+inline bool vec_env_early() { const char *v = getenv("SR_FIR_PLANES_VEC"); return v && v[0] == '1'; }   // 1 = force the vector kernel
+
 // Streaming path of the planes blur: SR_ERR_UNSUPPORTED when the shape does not qualify (the tile kernels take over).
 int launch_planes_stream(float *out, const float *x, const float *taps, int64_t major, int in_h, int in_w, int oh, int ow,
                          int pad_x0, int pad_y0, cudaStream_t st)
@@ -1684,6 +1889,7 @@ int launch_planes_stream(float *out, const float *x, const float *taps, int64_t 
     g.total_items = (int)total;
     g.div_seg = FastDiv((uint32_t)g.nseg);
     g.stage_bytes = ((FP_ROWS * in_w * 4 + 16 + 127) / 128) * 128;
+    { const char *d = getenv("SR_FIR_PLANES_DEBUG"); g.debug = d ? atoi(d) : 0; }
     const char *st_env = getenv("SR_FIR_PLANES_STAGES");          // experiment switches, read per call
     const char *j_env = getenv("SR_FIR_PLANES_J");
     g.stages = st_env ? atoi(st_env) : 8;
@@ -1693,7 +1899,7 @@ int launch_planes_stream(float *out, const float *x, const float *taps, int64_t 
     //   257^2 -> 256^2: 0.41 -> 0.54 (J = 2 or 4)   256^2 -> 257^2: 0.32 -> 0.45 (J = 4)   129^2 -> 128^2: 0.40 -> 0.46 (J = 2)
     //   128^2 -> 129^2: 0.26 -> 0.31 (J = 2)        64^2 -> 65^2: 0.14 -> 0.22 (J = 2)     65^2 -> 64^2: 0.36 (tile kernel) vs 0.23
     // The kernel is ISSUE bound (4-byte LDS / STG per lane: ~25 instructions per output); J = 1 (more warps) is slowest.
-    if (!j_env && ow < 100 && in_w % 4 != 0) return SR_ERR_UNSUPPORTED;
+    if (!j_env && !vec_env_early() && ow < 100 && in_w % 4 != 0) return SR_ERR_UNSUPPORTED;     // the tile kernel is faster there
     const int J = j_env ? atoi(j_env) : (ow >= 200 ? 4 : 2);
     if (J != 1 && J != 2 && J != 4) return SR_ERR_UNSUPPORTED;
     const int consumer_warps = (ow + 32 * J - 1) / (32 * J);
@@ -1715,6 +1921,35 @@ int launch_planes_stream(float *out, const float *x, const float *taps, int64_t 
     }
     const int64_t slots = (int64_t)per_sm * kNumSMs;
     const int grid = (int)(total < slots ? total : slots);
+    const char *vec_env = getenv("SR_FIR_PLANES_VEC");            // A/B switch: 0 = the scalar-lane kernel above
+    // measured (scratch/planes_sweep.py, fraction of the copy bandwidth; tile kernels -> scalar-lane ring -> this kernel):
+    //   257^2 -> 256^2: 0.41 -> 0.52 -> 0.65    256^2 -> 257^2: 0.32 -> 0.45 -> 0.63    513^2 -> 512^2: 0.43 -> 0.56 -> 0.66
+    //   129^2 -> 128^2: 0.40 -> 0.46 -> 0.39    128^2 -> 129^2: 0.26 -> 0.31 -> 0.38     64^2 -> 65^2: 0.14 -> 0.22 -> 0.19
+    // 4 stages beat 8 / 12 everywhere (more CTAs per SM); the bare ring without consumer work streams reads at 5.1 TB/s.
+    const bool vec_shape = ow >= 200 || (in_w % 4 == 0 && ow >= 100);
+    if (!(vec_env && vec_env[0] == '0') && !j_env && (vec_shape || (vec_env && vec_env[0] == '1'))) {
+        if (!st_env) g.stages = 4;
+        const int nq = ow / 4, cw = nq > 0 ? (nq + 31) / 32 : 1;
+        // interior quads [e0, e1): 4t - pad >= 0 and 4t + 6 - pad < in_w; everything else (<= 32 columns) is the side job
+        int e0 = pad_x0 > 0 ? (pad_x0 + 3) / 4 : 0, e1 = (in_w + pad_x0 - 7 >= 0) ? (in_w + pad_x0 - 7) / 4 + 1 : 0;
+        if (e1 > nq) e1 = nq;
+        if (e0 > e1) e0 = e1;
+        if (cw <= 4 && 4 * e0 + (ow - 4 * e1) <= 32) {
+            const int vthreads = 32 * (cw + 1);
+            const size_t vsmem = 256 + (size_t)g.stages * g.stage_bytes + 32 * sizeof(uint64_t);
+            int vper_sm = (int)(220 * 1024 / (vsmem + 1024));
+            if (vper_sm > 2048 / vthreads) vper_sm = 2048 / vthreads;
+            if (vper_sm > 16) vper_sm = 16;
+            static bool vconf = false;
+            if (!vconf) {
+                if (cudaFuncSetAttribute(fir_planes_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) return SR_ERR_UNSUPPORTED;
+                vconf = true;
+            }
+            const int64_t vslots = (int64_t)vper_sm * kNumSMs;
+            fir_planes_vec_kernel<<<(int)(total < vslots ? total : vslots), vthreads, vsmem, st>>>(out, x, taps, g, e0, e1);
+            return SR_OK;
+        }
+    }
     if (J == 1) fir_planes_stream_kernel<1><<<grid, threads, smem, st>>>(out, x, taps, g);
     else if (J == 2) fir_planes_stream_kernel<2><<<grid, threads, smem, st>>>(out, x, taps, g);
     else fir_planes_stream_kernel<4><<<grid, threads, smem, st>>>(out, x, taps, g);

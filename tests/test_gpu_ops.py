@@ -156,15 +156,23 @@ def test_upfirdn2d_separable_taps(op, shape, pad):
         torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("kernel", ["default", "vec", "scalar"])
 @pytest.mark.parametrize("rank1", [True, False])
 @pytest.mark.parametrize("shape,pad", [((4, 1, 257, 257), (1, 1)), ((2, 2, 256, 256), (2, 2)), ((1, 4, 100, 513), (1, 1)),
                                        ((2, 2, 130, 70), (2, 1)), ((1, 4, 64, 96), (-1, 2)), ((4, 1, 300, 64), (0, 3)),
                                        ((1, 8, 17, 385), (3, 3)), ((2, 2, 16, 66), (1, 1))])
-def test_upfirdn2d_planes_stream_kernel(op, shape, pad, rank1, monkeypatch):
-    """The row-streaming bulk-copy blur of the reference layout ([N*C, H, W] planes, reference op/upfirdn2d.py:99;
-    fir_planes_stream_kernel: planes >= 16 rows x 64..512 columns) against the oracle: unaligned 257-wide rows (every
-    chunk lead 0..3), several row segments, ragged last warp, asymmetric and negative pads, separable and general taps;
-    and bit-equal shapes / near-equal values against the tile kernels it replaces (SR_FIR_PLANES_STREAM=0)."""
+def test_upfirdn2d_planes_stream_kernel(op, shape, pad, rank1, kernel, monkeypatch):
+    """The row-streaming bulk-copy blurs of the reference layout ([N*C, H, W] planes, reference op/upfirdn2d.py:99; planes
+    >= 16 rows x 64..512 columns: fir_planes_vec_kernel = a thread owns 4 adjacent columns, aligned LDS.128 + selection by
+    the row's misalignment, scalar side job for the edge columns; fir_planes_stream_kernel = a lane owns columns 32 apart)
+    against the oracle: unaligned 257-wide rows (every chunk lead and row shift 0..3), several row segments, ragged
+    widths, asymmetric and negative pads, separable and general taps; "default" = the measured per-shape choice; and
+    near-equal values against the tile kernels they replace (SR_FIR_PLANES_STREAM=0)."""
+    if kernel == "vec":
+        monkeypatch.setenv("SR_FIR_PLANES_VEC", "1")
+    elif kernel == "scalar":
+        monkeypatch.setenv("SR_FIR_PLANES_VEC", "0")
+        monkeypatch.setenv("SR_FIR_PLANES_J", "2")
     x = seeded(shape, 40)
     if rank1:
         k = torch.outer(torch.tensor([1., 3., 3., 1.]), seeded((4,), 41))
