@@ -263,7 +263,7 @@ __device__ __forceinline__ void stage_tile_vectors(const ConvKParams &p, const T
     }
 }
 
-template <int BLOCK_N, bool STAGED = false>
+template <int BLOCK_N, bool STAGED = false, bool OP16 = false>
 __device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvOutMaps &om, const ConvPhase &ph,
                                               const TileCoord &tc, int q, int lane, int tx, int ty, int tn, uint32_t tmem_acc,
                                               uint64_t *tmem_full, uint32_t acc_par, uint8_t *stage, uint32_t &stage_sel,
@@ -293,7 +293,7 @@ __device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvOu
     // one pixel) instead of TMA stores: nothing in the chunk loop waits for the TMA unit, which is busy with the loads.
     // rowoff[i] = element offset of row (lane / 8 + 4 i) of this warp's 32 rows, or -1 outside the lattice.
     long long rowoff[8];
-    const bool direct = STAGED && (p.debug & 8) && !p.op16;
+    const bool direct = STAGED && (p.debug & 8) && !OP16;
     if (direct) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -376,7 +376,7 @@ __device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvOu
                 if (lane == 0) tma_store_wait_read<1>();
                 __syncwarp();
             }
-            if (p.op16) {
+            if (OP16) {
                 // bf16 operand for the next layer: 32 channels = 64 bytes per row, 64-byte swizzle (16-byte chunk q of row r
                 // lives at chunk q ^ ((r >> 1) & 3): conflict free for the 8 lanes of a store wavefront)
 #pragma unroll
@@ -423,7 +423,7 @@ __device__ __forceinline__ bool epilogue_tile(const ConvKParams &p, const ConvOu
 
 // Persistent: gridDim.x CTAs (one per SM) walk the tile list round-robin.  The TMEM holds TWO accumulators, so the
 // epilogue of tile i (TMEM -> registers -> fused tail -> global) overlaps the TMA/MMA main loop of tile i+1.
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool OP16>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const __grid_constant__ ConvOutMaps out_maps,
@@ -474,8 +474,8 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     mbar_wait(&empty_bar[s], par ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
-                        tma_load_4d(sA + s * A_BYTES, &tmap_a, &full_bar[s], kc * p.kelems, cx, cy, tc.n0);
-                        tma_load_2d(sB + s * B_BYTES, &tmap_b, &full_bar[s], ph.tap_k0[t] + kc * p.kelems, tc.n_tile * BLOCK_N);
+                        tma_load_4d(sA + s * A_BYTES, &tmap_a, &full_bar[s], kc * (OP16 ? 64 : 32), cx, cy, tc.n0);
+                        tma_load_2d(sB + s * B_BYTES, &tmap_b, &full_bar[s], ph.tap_k0[t] + kc * (OP16 ? 64 : 32), tc.n_tile * BLOCK_N);
                     }
                     __syncwarp();
                     if (++s == STAGES) { s = 0; par ^= 1; }
@@ -502,7 +502,7 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 8; ++k) {    // one instruction = 32 bytes along the swizzled row (8 tf32 / 16 bf16)
                         if (p.debug & 2) continue;
-                        if (p.op16) umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_bf16(kIdesc), (kb | k) != 0);
+                        if (OP16) umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_bf16(kIdesc), (kb | k) != 0);
                         else umma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
                     }
                     tcgen05_commit(&empty_bar[s]);             // frees the ring slot once these MMAs have read it
@@ -530,7 +530,7 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             ++lt;
             float rgb[3];
             long long rgb_index;
-            const bool valid = epilogue_tile<BLOCK_N>(p, out_maps, ph, tc, q, lane, tx, ty, tn, tmem_base + acc * BLOCK_N,
+            const bool valid = epilogue_tile<BLOCK_N, false, OP16>(p, out_maps, ph, tc, q, lane, tx, ty, tn, tmem_base + acc * BLOCK_N,
                                                       &tmem_full_bar[acc], acc_par, my_stage, stage_sel, rgb, rgb_index);
             tcgen05_fence_before();
             __syncwarp();
@@ -623,7 +623,7 @@ __device__ __forceinline__ TileCoord decode_tile_pair(const ConvKParams &p, int 
     return c;
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool OP16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const __grid_constant__ ConvOutMaps out_maps,
@@ -678,8 +678,8 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                     mbar_wait(&empty_bar[s], par ^ 1);
                     if (elect_one()) {
                         if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * (A_BYTES + BH_BYTES));   // bytes of BOTH CTAs
-                        tma_load_4d_2sm(sA + s * A_BYTES, &tmap_a, &full_bar[s], kc * p.kelems, cx, cy, tc.n0);
-                        tma_load_2d_2sm(sB + s * BH_BYTES, &tmap_b, &full_bar[s], ph.tap_k0[t] + kc * p.kelems,
+                        tma_load_4d_2sm(sA + s * A_BYTES, &tmap_a, &full_bar[s], kc * (OP16 ? 64 : 32), cx, cy, tc.n0);
+                        tma_load_2d_2sm(sB + s * BH_BYTES, &tmap_b, &full_bar[s], ph.tap_k0[t] + kc * (OP16 ? 64 : 32),
                                         tc.n_tile * BLOCK_N + rank * (BLOCK_N / 2));
                     }
                     __syncwarp();
@@ -708,7 +708,7 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / 8; ++k) {
                             if (p.debug & 2) continue;
-                            if (p.op16) umma_f16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_bf16(kIdesc), (kb | k) != 0);
+                            if (OP16) umma_f16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_bf16(kIdesc), (kb | k) != 0);
                             else umma_tf32_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
                         }
                         tcgen05_commit_2sm(&empty_bar[s]);
@@ -742,10 +742,10 @@ conv_igemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                 float *vb = vec_stage + (acc & 1) * (kVecKinds * BLOCK_N);     // (ncu: the rowscale loads were the epilogue's stall)
                 stage_tile_vectors<BLOCK_N, 128>(p, tc, vb, (int)threadIdx.x - 64);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                valid = epilogue_tile<BLOCK_N, true>(p, out_maps, ph, tc, q, lane, tx, ty, tn, tmem_base + acc * BLOCK_N,
+                valid = epilogue_tile<BLOCK_N, true, OP16>(p, out_maps, ph, tc, q, lane, tx, ty, tn, tmem_base + acc * BLOCK_N,
                                                      &tmem_full_bar[acc], acc_par, my_stage, stage_sel, rgb, rgb_index, vb);
             } else {
-                valid = epilogue_tile<BLOCK_N>(p, out_maps, ph, tc, q, lane, tx, ty, tn, tmem_base + acc * BLOCK_N,
+                valid = epilogue_tile<BLOCK_N, false, OP16>(p, out_maps, ph, tc, q, lane, tx, ty, tn, tmem_base + acc * BLOCK_N,
                                                &tmem_full_bar[acc], acc_par, my_stage, stage_sel, rgb, rgb_index);
             }
             tcgen05_fence_before();
@@ -806,7 +806,7 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc_sbo(uint32_t smem_add
 
 // EPI_WARPS = 4 or 8 epilogue warps: with 8, two warps share each 32-lane TMEM quadrant and split the columns, which
 // doubles the number of independent tcgen05.ld -> math -> TMA-store chains that drain an accumulator.
-template <int BLOCK_N, int SA, int SB, int TPS, int EPI_WARPS>   // TPS = taps per weight stage (one barrier round trip per TPS taps)
+template <int BLOCK_N, int SA, int SB, int TPS, int EPI_WARPS, bool OP16>   // TPS = taps per weight stage (one barrier round trip per TPS taps)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 conv_halo_tf32_2cta_kernel(const __grid_constant__ HaloMaps amaps, const __grid_constant__ CUtensorMap tmap_b,
                            const __grid_constant__ ConvOutMaps out_maps, const ConvKParams p, const HaloParams hp)
@@ -864,7 +864,7 @@ conv_halo_tf32_2cta_kernel(const __grid_constant__ HaloMaps amaps, const __grid_
                     mbar_wait_warp(&a_empty[sa], pa ^ 1, p.debug & 4);
                     if (elect_one()) {
                         if (rank == 0) mbar_expect_tx(&a_full[sa], 2 * (uint32_t)h.g_bytes[g]);
-                        tma_load_4d_2sm(sA + sa * kHaloStageBytes, &amaps.a[h.g_map[g]], &a_full[sa], kc * p.kelems,
+                        tma_load_4d_2sm(sA + sa * kHaloStageBytes, &amaps.a[h.g_map[g]], &a_full[sa], kc * (OP16 ? 64 : 32),
                                         tc.gx0 + h.g_xoff[g], tc.gy0 + h.g_yoff[g], tc.n0);
                     }
                     __syncwarp();
@@ -879,7 +879,7 @@ conv_halo_tf32_2cta_kernel(const __grid_constant__ HaloMaps amaps, const __grid_
                             for (int j = 0; j < TPS; ++j)
                                 if (j < n)
                                     tma_load_2d_2sm(sB + sb * B_STAGE + j * BH_BYTES, &tmap_b, &b_full[sb],
-                                                    h.tap_k0[t + j] + kc * p.kelems, brow);
+                                                    h.tap_k0[t + j] + kc * (OP16 ? 64 : 32), brow);
                         }
                         __syncwarp();
                         if (++sb == SB) { sb = 0; pb ^= 1; }
@@ -920,7 +920,7 @@ conv_halo_tf32_2cta_kernel(const __grid_constant__ HaloMaps amaps, const __grid_
 #pragma unroll
                                         for (int k = 0; k < BLOCK_K / 8; ++k) {
                                             if (!(p.debug & 2)) {
-                                                if (p.op16) umma_f16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_bf16(kIdesc), accumulate);
+                                                if (OP16) umma_f16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_bf16(kIdesc), accumulate);
                                                 else umma_tf32_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, accumulate);
                                             }
                                             accumulate = 1;
@@ -963,7 +963,7 @@ conv_halo_tf32_2cta_kernel(const __grid_constant__ HaloMaps amaps, const __grid_
             float *vb = vec_stage + (lt & 1) * (kVecKinds * BLOCK_N);
             stage_tile_vectors<BLOCK_N, 32 * EPI_WARPS>(p, tc, vb, (int)threadIdx.x - 64);
             asm volatile("bar.sync 1, %0;" :: "n"(32 * EPI_WARPS) : "memory");
-            const bool valid = epilogue_tile<BLOCK_N, true>(p, out_maps, ph, tc, q, lane, tx, ty, tn, tmem_base + acc * BLOCK_N,
+            const bool valid = epilogue_tile<BLOCK_N, true, OP16>(p, out_maps, ph, tc, q, lane, tx, ty, tn, tmem_base + acc * BLOCK_N,
                                                             &tmem_full_bar[acc], acc_par, my_stage, stage_sel, rgb, rgb_index, vb,
                                                             half * CHUNKS, (half + 1) * CHUNKS);
             tcgen05_fence_before();
@@ -1493,12 +1493,15 @@ weight_prep_dual_kernel(float *__restrict__ fwd, float *__restrict__ tr, float *
 // ------------------------------------------------------------------------------------ host side
 int ilog2_exact(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
-template <int BLOCK_N, int STAGES>
+// OP16 (bf16 operands, tcgen05 kind::f16) is a COMPILE-TIME parameter of the conv kernels: as a run-time branch around every
+// MMA it cost the tf32 path a quarter of its speed (ncu, round 2: 128 -> 128 @ 256^2 at 56 % tensor pipe instead of 87 %,
+// 512 -> 512 @ 64^2 at 72 % instead of 98 % -- the issuing thread bounds these loops).
+template <int BLOCK_N, int STAGES, bool OP16>
 int launch_conv(const CUtensorMap &ta, const CUtensorMap &tb, const ConvOutMaps &om, const ConvKParams &p, cudaStream_t st)
 {
     constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
     const size_t smem = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 1024 + kEpiSmemBytes;
-    auto kern = conv_igemm_tf32_kernel<BLOCK_N, STAGES>;
+    auto kern = conv_igemm_tf32_kernel<BLOCK_N, STAGES, OP16>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1510,14 +1513,14 @@ int launch_conv(const CUtensorMap &ta, const CUtensorMap &tb, const ConvOutMaps 
     return SR_OK;
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool OP16>
 int launch_conv_2cta(const CUtensorMap &ta, const CUtensorMap &tb, const ConvOutMaps &om, const ConvKParams &p, cudaStream_t st)
 {
     constexpr int BH_BYTES = (BLOCK_N / 2) * BLOCK_K * 4;
     const size_t smem = 1024 + (size_t)STAGES * (A_BYTES + BH_BYTES) + 1024 + kEpiSmemBytes + 2 * kVecKinds * BLOCK_N * sizeof(float);
     static_assert(1024 + STAGES * (A_BYTES + BH_BYTES) + 1024 + kEpiSmemBytes + 2 * kVecKinds * BLOCK_N * 4 <= 232448,
                   "CTA-pair conv kernel: shared memory budget");
-    auto kern = conv_igemm_tf32_2cta_kernel<BLOCK_N, STAGES>;
+    auto kern = conv_igemm_tf32_2cta_kernel<BLOCK_N, STAGES, OP16>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1529,7 +1532,7 @@ int launch_conv_2cta(const CUtensorMap &ta, const CUtensorMap &tb, const ConvOut
     return SR_OK;
 }
 
-template <int BLOCK_N, int SA, int SB, int TPS, int EPI_WARPS>
+template <int BLOCK_N, int SA, int SB, int TPS, int EPI_WARPS, bool OP16>
 int launch_conv_halo(const HaloMaps &am, const CUtensorMap &tb, const ConvOutMaps &om, const ConvKParams &p, const HaloParams &hp,
                      cudaStream_t st)
 {
@@ -1538,7 +1541,7 @@ int launch_conv_halo(const HaloMaps &am, const CUtensorMap &tb, const ConvOutMap
                         (size_t)EPI_WARPS * 2 * kStageBufBytes + 2 * kVecKinds * BLOCK_N * sizeof(float);
     static_assert(1024 + SA * kHaloStageBytes + SB * TPS * BH_BYTES + 1024 + EPI_WARPS * 2 * kStageBufBytes +
                   2 * kVecKinds * BLOCK_N * 4 <= 232448, "halo kernel: shared memory budget");
-    auto kern = conv_halo_tf32_2cta_kernel<BLOCK_N, SA, SB, TPS, EPI_WARPS>;
+    auto kern = conv_halo_tf32_2cta_kernel<BLOCK_N, SA, SB, TPS, EPI_WARPS, OP16>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1835,15 +1838,16 @@ static int conv_igemm_multi(const sr_conv_args *args, int count, void *stream, i
         static const char *epi_env = getenv("SR_CONV_EPI_WARPS");          // A/B: force 4 or 8 epilogue warps
         bool epi8 = a->out2 != nullptr && block_n == 128;
         if (epi_env) epi8 = epi_env[0] == '8';
-        if (block_n == 256) rc = epi8 ? launch_conv_halo<256, 2, 6, 1, 8>(am, tb, om, p, hp, st)
-                                      : launch_conv_halo<256, 2, 7, 1, 4>(am, tb, om, p, hp, st);
-        else rc = epi8 ? launch_conv_halo<128, 2, 4, 3, 8>(am, tb, om, p, hp, st)
-                       : launch_conv_halo<128, 3, 4, 3, 4>(am, tb, om, p, hp, st);
+#define SR_HALO(N, A, B, T, E) (p.op16 ? launch_conv_halo<N, A, B, T, E, true>(am, tb, om, p, hp, st) \
+                                       : launch_conv_halo<N, A, B, T, E, false>(am, tb, om, p, hp, st))
+        if (block_n == 256) rc = epi8 ? SR_HALO(256, 2, 6, 1, 8) : SR_HALO(256, 2, 7, 1, 4);
+        else rc = epi8 ? SR_HALO(128, 2, 4, 3, 8) : SR_HALO(128, 3, 4, 3, 4);
+#undef SR_HALO
     } else if (use_2cta) {
-        if (block_n == 256) rc = launch_conv_2cta<256, 5>(ta, tb, om, p, st);
-        else rc = launch_conv_2cta<128, 7>(ta, tb, om, p, st);
-    } else if (block_n == 256) rc = launch_conv<256, 4>(ta, tb, om, p, st);
-    else rc = launch_conv<128, 6>(ta, tb, om, p, st);
+        if (block_n == 256) rc = p.op16 ? launch_conv_2cta<256, 5, true>(ta, tb, om, p, st) : launch_conv_2cta<256, 5, false>(ta, tb, om, p, st);
+        else rc = p.op16 ? launch_conv_2cta<128, 7, true>(ta, tb, om, p, st) : launch_conv_2cta<128, 7, false>(ta, tb, om, p, st);
+    } else if (block_n == 256) rc = p.op16 ? launch_conv<256, 4, true>(ta, tb, om, p, st) : launch_conv<256, 4, false>(ta, tb, om, p, st);
+    else rc = p.op16 ? launch_conv<128, 6, true>(ta, tb, om, p, st) : launch_conv<128, 6, false>(ta, tb, om, p, st);
     if (rc != SR_OK) return rc;
     count_launch();
     return check_launch("sr_conv_igemm_tf32");
