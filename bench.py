@@ -235,8 +235,8 @@ def launch_signature(name, a):
 
 
 def ncu_traffic(sig):
-    """DRAM bytes (read + write) of one launch from the committed `ncu --set full` captures (profiles/r1_ncu_traffic.json)."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    """DRAM bytes (read + write) of one launch from the committed `ncu --set full` captures (profiles/r2_ncu_traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
     if not os.path.exists(path):
         return None
     return json.load(open(path)).get(sig)
@@ -260,7 +260,7 @@ def dominant_kernel_roofline(stats, peaks, total_ms, steps):
     common = {"kernel": name, "launches_per_step": len(all_calls) / steps, "avg_launch_ms": round(ms_all / len(all_calls), 5),
               "share_of_step": round(ms_all / total_ms, 4) if total_ms else None,
               "traffic": ncu_traffic(sig),
-              "traffic_source": f"profiles/r1_ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one '{sig}' launch)",
+              "traffic_source": f"profiles/r2_ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one '{sig}' launch)",
               "all_kernels_ms_per_step": {n: round(v / steps, 4) for n, v in tot.items()}}
     # the bandwidth-bound passes of the step against the measured copy bandwidth (BASELINE metric: "HBM GB/s vs roofline")
     hbm = {}
