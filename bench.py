@@ -765,6 +765,7 @@ def main():
 
     # ---- the same step captured once as a CUDA graph and replayed (removes ~1300 host launches per step)
     ms, ms_e2e, graphed = ms_eager, ms_e2e_eager, False
+    e2e_how, ms_e2e_sync = "eager step, synchronous read-back", ms_e2e_eager
     if not args.no_graph:
         try:
             z_static = torch.randn(B, 512, device=dev)
@@ -793,11 +794,56 @@ def main():
                 img_host.copy_(img_static, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
 
+            # e2e with the read-back of the images overlapped INSIDE the step: forward and backward captured as two graphs
+            # (one memory pool); the 25 MB of images leave on a copy stream while the backward graph runs; the caller still
+            # waits for every result of the step before the next one starts.
+            e2e_step, e2e_how = step_graph_e2e, "synchronous read-back after the step"
+            try:
+                graph_f, graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph_f):
+                    for prm in G.parameters():
+                        prm.grad = None
+                    z_req = z_static.detach().requires_grad_(True)
+                    img2, _ = G([z_req])
+                    loss2 = (img2 * cot).sum()
+                    img2_static, loss2_static = img2.detach(), loss2.detach()
+                with torch.cuda.graph(graph_b, pool=graph_f.pool()):
+                    loss2.backward()
+                    gz2_static = z_req.grad
+                copy_stream, fwd_done = torch.cuda.Stream(), torch.cuda.Event()
+
+                def step_graph_e2e_overlap():
+                    z_static.copy_(z_host, non_blocking=True)
+                    graph_f.replay()
+                    fwd_done.record()
+                    copy_stream.wait_event(fwd_done)
+                    with torch.cuda.stream(copy_stream):
+                        img_host.copy_(img2_static, non_blocking=True)
+                        loss_host.copy_(loss2_static, non_blocking=True)
+                    graph_b.replay()
+                    gz_host.copy_(gz2_static, non_blocking=True)
+                    copy_stream.synchronize()
+                    torch.cuda.current_stream().synchronize()
+
+                step_graph_e2e_overlap()
+                # (every replay draws fresh noise, so the two-graph step cannot be compared value by value with the single
+                # graph; what is checked: the host copies are the step's own results and the gradient is finite and alive)
+                ok = (torch.isfinite(gz_host).all() and gz_host.abs().max() > 0 and torch.equal(img_host, img2_static.cpu())
+                      and abs(float(loss_host) - float((img2_static * cot).sum())) <= 1e-3 * abs(float(loss_host)) + 1e-3)
+                if not ok:
+                    raise RuntimeError("split forward / backward graphs: inconsistent results")
+                e2e_step, e2e_how = step_graph_e2e_overlap, ("forward and backward replayed as two CUDA graphs; the images and the loss "
+                                                             "leave on a copy stream during the backward graph")
+            except Exception as ex:                     # noqa: BLE001
+                print(f"[bench] overlapped e2e step unavailable, using the synchronous one: {ex!r}", file=sys.stderr)
             for _ in range(3):
                 step_graph()
             with ClockSampler(local) as clocks:             # sampled over both timed regions (device-resident and e2e)
                 ms = timed(step_graph, args.steps)
-                ms_e2e = timed(step_graph_e2e, args.steps)
+                ms_e2e_sync = timed(step_graph_e2e, args.steps)
+                ms_e2e = timed(e2e_step, args.steps) if e2e_step is not step_graph_e2e else ms_e2e_sync
+                if ms_e2e > ms_e2e_sync:                    # keep whichever public-API step is faster on this box
+                    ms_e2e, e2e_how = ms_e2e_sync, "synchronous read-back after the step"
             graphed = True
         except Exception as ex:                         # report, never hide: fall back to the eager numbers
             print(f"[bench] CUDA graph capture failed, reporting eager timings: {ex!r}", file=sys.stderr)
@@ -855,7 +901,9 @@ def main():
                 "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": z_host.numel() * 4,
                         "d2h_bytes_per_step": 4 + gz_host.numel() * 4 + img_host.numel() * 4,
                         "d2h": "loss + dz + the generated images [B,3,256,256] fp32",
-                        "ms_per_step": round(ms_e2e / args.steps, 3)},
+                        "ms_per_step": round(ms_e2e / args.steps, 3),
+                        "how": e2e_how if graphed else "eager step, synchronous read-back",
+                        "ms_per_step_synchronous": round(ms_e2e_sync / args.steps, 3) if graphed else None},
                 "gpu_launches": int(launches),
                 "roofline": roof, "cpu_baseline": cpu_base, "gpu_reference": gpu_ref,
                 "measured_peaks": {k: v for k, v in peaks.items() if k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained",
