@@ -197,6 +197,18 @@ def algorithmic_bytes(name, a):
         return (8 + (op if a[16] else 4)) * a[17] * a[18] * a[19]
     if name in ("sr_conv_weight_prep_dual_tf32", "sr_conv_weight_prep_dual_bf16"):
         return a[5] * a[6] * a[7] * (4 + (op if a[0] else 0) + (op if a[1] else 0))
+    if name in ("sr_conv_weight_prep_multi_tf32", "sr_conv_weight_prep_multi_bf16", "sr_weight_sq_backward_multi_f32"):
+        try:                                            # a[0] = ctypes array of sr_weight_prep_item, a[1] = n
+            tot = 0
+            for it in list(a[0])[:a[1]]:
+                n = it.cout * it.cin * it.taps
+                if name.startswith("sr_weight_sq"):
+                    tot += 8 * n + 4 * it.cout * it.cin
+                else:
+                    tot += n * (4 + (op if it.fwd else 0) + (op if it.tr else 0)) + (4 * it.cout * it.cin if it.wsq else 0)
+            return tot
+        except Exception:                               # noqa: BLE001
+            return 0
     if name == "sr_weight_grad_layout_f32":
         return 8 * a[3] * a[4] * a[5]
     if name in ("sr_modulate_tf32", "sr_modulate_bf16"):

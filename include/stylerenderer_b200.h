@@ -396,6 +396,22 @@ int sr_mesh_normal_pyramid_f32(int64_t batch, int64_t nv, int64_t nf, const floa
                                const float *pose, const int64_t *tris, float *verts_out, float *normals, int n_levels,
                                const sr_raster_level *levels, uint64_t *keys, float eps, void *stream);
 
+/* sr_conv_weight_prep_dual_* / sr_weight_sq_backward_f32 for up to SR_WEIGHT_PREP_MAX conv weights in ONE launch each (every
+ * ModulatedConv2d of a generator, reference layers.py:296-299): fwd / tr are tf32-rounded fp32 (bfloat16 for _bf16) GEMM
+ * operands or NULL, wsq fp32 or NULL; the backward reads w and g_wsq [cout, cin] and writes gw [cout, cin, taps]. */
+#define SR_WEIGHT_PREP_MAX 16
+typedef struct sr_weight_prep_item {
+    void *fwd, *tr;
+    float *wsq;
+    const float *w;
+    float *gw;
+    const float *g_wsq;
+    float scale;
+    int32_t cout, cin, taps, flip_transposed, reserved;
+} sr_weight_prep_item;
+int sr_conv_weight_prep_multi_tf32(const sr_weight_prep_item *items, int n, void *stream);
+int sr_conv_weight_prep_multi_bf16(const sr_weight_prep_item *items, int n, void *stream);
+int sr_weight_sq_backward_multi_f32(const sr_weight_prep_item *items, int n, void *stream);
 /* The style-map network of GeneratorWithMap -- ResBlock(3 -> cout, downsample = False), cout = 2 or 4 (reference
  * model.py:194-216 builds them, model.py:262,271-275 runs them on the rasterised normal map of every resolution; the block
  * is reference layers.py:379-391 over the ConvLayers of layers.py:341-378) -- as ONE pass over [batch, 3, h, w] planes:

@@ -67,6 +67,9 @@ _SIGNATURES = {
     "sr_styled_bwd_prologue3_f32": (_I, [_P] * 13 + [_L, _P, _P, _P, _L, _L, _L, _F, _F, _P, _L, _P, _P]),
     "sr_stylemap_resblock_forward_f32": (_I, [_P] * 9 + [_L, _I, _I, _L, _L, _F, _F, _P]),
     "sr_stylemap_resblock_backward_f32": (_I, [_P] * 10 + [_L, _I, _I, _L, _L, _F, _F, _P]),
+    "sr_conv_weight_prep_multi_tf32": (_I, [_P, _I, _P]),
+    "sr_conv_weight_prep_multi_bf16": (_I, [_P, _I, _P]),
+    "sr_weight_sq_backward_multi_f32": (_I, [_P, _I, _P]),
     "sr_small_conv_f32": (_I, [_P, _P, _P, _L, _I, _I, _I, _L, _L, _P]),
     "sr_small_conv_wgrad_f32": (_I, [_P, _P, _P, _L, _I, _I, _I, _L, _L, _P]),
     "sr_stem_conv_forward_f32": (_I, [_P] * 5 + [_L, _I, _L, _L, _L, _I, _F, _F, _P]),
@@ -80,7 +83,8 @@ CONV_EXPORTS = ("sr_blur_nhwc_scaledot_f32", "sr_blur_nhwc_styled_f32", "sr_blur
                 "sr_weight_grad_layout_f32", "sr_conv_weight_prep_dual_tf32", "sr_blur_nhwc_styled3_f32",
                 "sr_styled_bwd_prologue3_f32", "sr_conv_igemm_multi_bf16", "sr_conv_wgrad_bf16", "sr_modulate_bf16",
                 "sr_conv_weight_prep_dual_bf16", "sr_blur_nhwc_styled3_bf16", "sr_blur_nhwc_scaledot_bf16",
-                "sr_styled_bwd_prologue3_bf16")
+                "sr_styled_bwd_prologue3_bf16", "sr_conv_weight_prep_multi_tf32", "sr_conv_weight_prep_multi_bf16",
+                "sr_weight_sq_backward_multi_f32")
 
 
 class NativeLibraryError(RuntimeError):

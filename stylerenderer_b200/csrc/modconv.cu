@@ -23,6 +23,7 @@
 // fp32 storage, TF32 multiplicands (both operands are rounded to tf32 with cvt.rna by the kernels that
 // produce them), fp32 accumulation: the same arithmetic class as the reference's cuDNN path under
 // torch's default cudnn.allow_tf32 = True.
+#include <algorithm>
 #include "common.cuh"
 #include "tma_host.cuh"
 #include <stdlib.h>
@@ -1451,13 +1452,12 @@ __device__ __forceinline__ void store_operand(float *base, int64_t idx, float v,
     }
 }
 
-__global__ void __launch_bounds__(256)
-weight_prep_dual_kernel(float *__restrict__ fwd, float *__restrict__ tr, float *__restrict__ wsq, const float *__restrict__ w,
-                        float scale, int cout, int cin, int taps, int flip, int bf16)
+__device__ __forceinline__ void weight_prep_dual_body(float *__restrict__ fwd, float *__restrict__ tr, float *__restrict__ wsq,
+                                                      const float *__restrict__ w, float scale, int cout, int cin, int taps,
+                                                      int flip, int bf16, int bx, int by, float *wt)
 {
-    extern __shared__ float wt[];                         // [32 co][32 ci * taps + 1]
     const int row = kWP * taps + 1;
-    const int co0 = blockIdx.y * kWP, ci0 = blockIdx.x * kWP;
+    const int co0 = by * kWP, ci0 = bx * kWP;
     for (int idx = threadIdx.x; idx < kWP * kWP * taps; idx += 256) {
         const int r = idx / (kWP * taps), c = idx - r * (kWP * taps);          // c = ci_local * taps + t
         const int co = co0 + r, ci = ci0 + c / taps;
@@ -1488,6 +1488,38 @@ weight_prep_dual_kernel(float *__restrict__ fwd, float *__restrict__ tr, float *
             if (co0 + r < cout && ci0 + c < cin) wsq[(int64_t)(co0 + r) * cin + ci0 + c] = acc;
         }
     }
+}
+
+__global__ void __launch_bounds__(256)
+weight_prep_dual_kernel(float *__restrict__ fwd, float *__restrict__ tr, float *__restrict__ wsq, const float *__restrict__ w,
+                        float scale, int cout, int cin, int taps, int flip, int bf16)
+{
+    extern __shared__ float wt[];                         // [32 co][32 ci * taps + 1]
+    weight_prep_dual_body(fwd, tr, wsq, w, scale, cout, cin, taps, flip, bf16, blockIdx.x, blockIdx.y, wt);
+}
+
+// every conv weight of a network in ONE launch (blockIdx.z = layer): 13 launches of 256 CTAs each were latency bound
+// (28 us for 28 MB); together they fill the machine
+struct WeightPrepTable { int n; sr_weight_prep_item item[SR_WEIGHT_PREP_MAX]; };
+
+__global__ void __launch_bounds__(256)
+weight_prep_multi_kernel(const __grid_constant__ WeightPrepTable tab, int bf16)
+{
+    extern __shared__ float wt[];
+    const sr_weight_prep_item &it = tab.item[blockIdx.z];
+    if ((int)blockIdx.x * kWP >= it.cin || (int)blockIdx.y * kWP >= it.cout) return;
+    weight_prep_dual_body(reinterpret_cast<float *>(it.fwd), reinterpret_cast<float *>(it.tr), it.wsq, it.w, it.scale, it.cout, it.cin,
+                          it.taps, it.flip_transposed, bf16, blockIdx.x, blockIdx.y, wt);
+}
+
+__global__ void __launch_bounds__(256)
+weight_sq_backward_multi_kernel(const __grid_constant__ WeightPrepTable tab)
+{
+    const sr_weight_prep_item &it = tab.item[blockIdx.y];
+    const uint32_t total = (uint32_t)it.cout * it.cin * it.taps;
+    const float s2 = 2.0f * it.scale * it.scale;
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u)
+        it.gw[i] = s2 * __ldg(it.w + i) * __ldg(it.g_wsq + i / (uint32_t)it.taps);
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -2089,4 +2121,52 @@ extern "C" int sr_conv_weight_prep_dual_bf16(void *fwd, void *tr, float *wsq, co
 {
     return weight_prep_dual_any(reinterpret_cast<float *>(fwd), reinterpret_cast<float *>(tr), wsq, w, scale, cout, cin, taps,
                                 flip_transposed, stream, 1);
+}
+
+static int weight_prep_multi_any(const sr_weight_prep_item *items, int n, void *stream, int bf16)
+{
+    SR_REQUIRE(items && n >= 1 && n <= SR_WEIGHT_PREP_MAX, "weight_prep_multi: 1..%d layers", SR_WEIGHT_PREP_MAX);
+    WeightPrepTable tab;
+    tab.n = n;
+    int gx = 0, gy = 0, taps_max = 0;
+    for (int i = 0; i < n; ++i) {
+        const sr_weight_prep_item &it = items[i];
+        SR_REQUIRE(it.w && it.cout > 0 && it.cin > 0 && it.taps > 0 && it.taps <= 25 && (it.fwd || it.tr || it.wsq),
+                   "weight_prep_multi: bad layer %d", i);
+        tab.item[i] = it;
+        gx = std::max(gx, (it.cin + kWP - 1) / kWP); gy = std::max(gy, (it.cout + kWP - 1) / kWP); taps_max = std::max(taps_max, it.taps);
+    }
+    const size_t smem = sizeof(float) * kWP * (kWP * taps_max + 1);
+    static bool configured = false;
+    if (!configured && smem > 48 * 1024) {
+        cudaFuncSetAttribute(weight_prep_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kWP * (kWP * 25 + 1)));
+        configured = true;
+    }
+    weight_prep_multi_kernel<<<dim3(gx, gy, n), 256, smem, (cudaStream_t)stream>>>(tab, bf16);
+    count_launch();
+    return check_launch("sr_conv_weight_prep_multi");
+}
+
+extern "C" int sr_conv_weight_prep_multi_tf32(const sr_weight_prep_item *items, int n, void *stream)
+{
+    return weight_prep_multi_any(items, n, stream, 0);
+}
+extern "C" int sr_conv_weight_prep_multi_bf16(const sr_weight_prep_item *items, int n, void *stream)
+{
+    return weight_prep_multi_any(items, n, stream, 1);
+}
+extern "C" int sr_weight_sq_backward_multi_f32(const sr_weight_prep_item *items, int n, void *stream)
+{
+    SR_REQUIRE(items && n >= 1 && n <= SR_WEIGHT_PREP_MAX, "weight_sq_backward_multi: 1..%d layers", SR_WEIGHT_PREP_MAX);
+    WeightPrepTable tab;
+    tab.n = n;
+    for (int i = 0; i < n; ++i) {
+        const sr_weight_prep_item &it = items[i];
+        SR_REQUIRE(it.w && it.gw && it.g_wsq && it.cout > 0 && it.cin > 0 && it.taps > 0 &&
+                   (int64_t)it.cout * it.cin * it.taps < (1ll << 31), "weight_sq_backward_multi: bad layer %d", i);
+        tab.item[i] = it;
+    }
+    weight_sq_backward_multi_kernel<<<dim3(kNumSMs * 2, n), 256, 0, (cudaStream_t)stream>>>(tab);
+    count_launch();
+    return check_launch("sr_weight_sq_backward_multi_f32");
 }

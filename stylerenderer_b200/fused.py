@@ -628,7 +628,7 @@ def generator_chain_forward(gen, latent, noise, maps_fn=None):
     mods = [blk.conv for blk in blocks] + [rgbs[k][0].conv for k in sorted(rgbs)]
     lat_idx = list(range(len(blocks))) + [rgbs[k][1] for k in sorted(rgbs)]
     # one pass per conv weight: demodulation statistic + forward / dgrad GEMM operands (style.WeightPrepAll)
-    prep = [style.WeightPrepAll.apply(blk.conv.weight, blk.conv.scale, not blk.conv.upsample) for blk in blocks]
+    prep = style.weight_prep_all_layers([(blk.conv.weight, blk.conv.scale, not blk.conv.upsample) for blk in blocks])
     sd = style.style_scales_all(latent, mods, lat_idx, [pr[0] for pr in prep] + [None] * len(rgbs))
     scales = sd[:len(blocks)]
     rgb_style = {k: sd[len(blocks) + j][0] for j, k in enumerate(sorted(rgbs))}

@@ -6,6 +6,7 @@ Reference per layer (layers.py:232-239, 295-299): `s = modulation(style)` (Equal
 computed for ALL layers by `style_scales_all` (2 launches forward, 4 backward) instead of ~35 torch launches per layer.
 """
 import ctypes
+import os
 
 import torch
 from torch.autograd import Function
@@ -81,6 +82,77 @@ class WeightPrepAll(Function):
                                                       _lib.stream_of(w))
         _lib.check(rc, "sr_weight_sq_backward_f32")
         return gw, None, None
+
+
+class WeightPrepItem(ctypes.Structure):      # mirrors `sr_weight_prep_item` in include/stylerenderer_b200.h
+    _fields_ = [("fwd", _P), ("tr", _P), ("wsq", _P), ("w", _P), ("gw", _P), ("g_wsq", _P), ("scale", ctypes.c_float),
+                ("cout", _I32), ("cin", _I32), ("taps", _I32), ("flip_transposed", _I32), ("reserved", _I32)]
+
+
+WEIGHT_PREP_MAX = 16
+
+
+class WeightPrepAllLayers(Function):
+    """WeightPrepAll for every conv weight of a network in ONE launch (sr_conv_weight_prep_multi_*), and one launch for all
+    the demodulation-statistic gradients in the backward (sr_weight_sq_backward_multi_f32).
+    forward(cfgs, *weights) with cfgs = ((scale, flip_transposed), ...) -> (wsq_0, wk_f_0, wk_t_0, wsq_1, ...)."""
+
+    @staticmethod
+    def forward(ctx, cfgs, *weights):
+        from . import tc_conv as tc
+        n = len(weights)
+        assert 1 <= n <= WEIGHT_PREP_MAX and len(cfgs) == n
+        ws = [w.contiguous() for w in weights]
+        arr = (WeightPrepItem * n)()
+        outs = []
+        for a, w, (scale, flip) in zip(arr, ws, cfgs):
+            _, cout, cin, kh, kw = w.shape
+            wk_f = torch.empty(cout, kh * kw, cin, dtype=tc.operand_dtype(), device=w.device)
+            wk_t = torch.empty(cin, kh * kw, cout, dtype=tc.operand_dtype(), device=w.device)
+            wsq = torch.empty(cout, cin, dtype=torch.float32, device=w.device)
+            a.fwd, a.tr, a.wsq, a.w = _lib.ptr(wk_f), _lib.ptr(wk_t), _lib.ptr(wsq), _lib.ptr(w)
+            a.scale, a.cout, a.cin, a.taps, a.flip_transposed = float(scale), cout, cin, kh * kw, int(bool(flip))
+            outs += [wsq, wk_f, wk_t]
+        fn = _lib.lib().sr_conv_weight_prep_multi_bf16 if tc._bf16() else _lib.lib().sr_conv_weight_prep_multi_tf32
+        with torch.cuda.device(ws[0].device):
+            rc = fn(arr, n, _lib.stream_of(ws[0]))
+        _lib.check(rc, "sr_conv_weight_prep_multi")
+        ctx.save_for_backward(*ws)
+        ctx.cfgs = cfgs
+        ctx.mark_non_differentiable(*[o for i, o in enumerate(outs) if i % 3])
+        ctx.set_materialize_grads(False)
+        return tuple(outs)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *grads):
+        ws = ctx.saved_tensors
+        live = [(i, w, grads[3 * i]) for i, w in enumerate(ws) if grads[3 * i] is not None and ctx.needs_input_grad[1 + i]]
+        out = [None] * len(ws)
+        if live:
+            arr = (WeightPrepItem * len(live))()
+            keep = []
+            for a, (i, w, g) in zip(arr, live):
+                _, cout, cin, kh, kw = w.shape
+                gw, g = torch.empty_like(w), g.contiguous()
+                a.w, a.gw, a.g_wsq = _lib.ptr(w), _lib.ptr(gw), _lib.ptr(g)
+                a.scale, a.cout, a.cin, a.taps = float(ctx.cfgs[i][0]), cout, cin, kh * kw
+                out[i] = gw
+                keep.append(g)
+            with torch.cuda.device(ws[0].device):
+                rc = _lib.lib().sr_weight_sq_backward_multi_f32(arr, len(live), _lib.stream_of(ws[0]))
+            _lib.check(rc, "sr_weight_sq_backward_multi_f32")
+        return (None, *out)
+
+
+def weight_prep_all_layers(mods_cfg):
+    """[(weight [1,cout,cin,k,k], scale, flip_transposed), ...] -> [(wsq, wk_fwd, wk_tr), ...]: one launch when the operand mode
+    allows it (tf32 / bf16), per-layer WeightPrepAll in the fp32-faithful parity mode or beyond WEIGHT_PREP_MAX layers."""
+    from . import tc_conv as tc
+    if tc._exact() or not 1 <= len(mods_cfg) <= WEIGHT_PREP_MAX or os.environ.get("SR_WEIGHT_PREP_MULTI", "1") == "0":
+        return [WeightPrepAll.apply(w, sc, fl) for w, sc, fl in mods_cfg]
+    flat = WeightPrepAllLayers.apply(tuple((float(sc), bool(fl)) for _, sc, fl in mods_cfg), *[w for w, _, _ in mods_cfg])
+    return [tuple(flat[3 * i:3 * i + 3]) for i in range(len(mods_cfg))]
 
 
 def weight_grad_layout(dwk, scale, cout, cin, k):
