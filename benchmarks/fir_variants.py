@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""A/B timing of the channels-last FIR kernels (SR_FIR_RING = 0..5, see csrc/upfirdn2d.cu) on the generator's two largest
+"""A/B timing of the channels-last FIR kernels (stream = TMA row-streaming ring, the default; sep / window = the per-thread
+kernels behind SR_FIR_STREAM=0 [+ SR_FIR_SEP=0], see csrc/upfirdn2d.cu) on the generator's two largest
 up-sampling blocks: forward tail (fir + noise + bias + lrelu + tf32 second output) and backward tail (fir^T * d -> tf32).
 CUDA events, inputs larger than L2; prints one JSON line per (variant, shape)."""
 import json
@@ -39,11 +40,15 @@ def main():
         bias, d = torch.randn(c, device=dev), torch.rand(B, c, device=dev) + 0.5
         by_f = 4 * B * c * ((r + 1) ** 2 + 2 * r * r)
         by_b = 4 * B * c * (r * r + (r + 1) ** 2)
-        for variant in ("0", "1", "2", "3", "4", "5"):
-            os.environ["SR_FIR_RING"] = variant
+        for variant in ("stream", "sep", "window"):
+            os.environ.pop("SR_FIR_STREAM", None); os.environ.pop("SR_FIR_SEP", None)
+            if variant != "stream":
+                os.environ["SR_FIR_STREAM"] = "0"
+            if variant == "window":
+                os.environ["SR_FIR_SEP"] = "0"
             ms_f = timed(lambda: tc.blur_styled(t, taps, (1, 1), noise, nw, bias, 0.2, 2 ** 0.5, scale2=d))
             ms_b = timed(lambda: tc.blur_scaledot(g, taps, (2, 2), d))
-            print(json.dumps({"SR_FIR_RING": variant, "res": r, "channels": c, "fwd_tail_ms": round(ms_f, 4),
+            print(json.dumps({"kernel": variant, "res": r, "channels": c, "fwd_tail_ms": round(ms_f, 4),
                               "fwd_GBps": round(by_f / ms_f / 1e6, 1), "fwd_frac": round(by_f / ms_f / 1e6 / peak, 3),
                               "bwd_tail_ms": round(ms_b, 4), "bwd_GBps": round(by_b / ms_b / 1e6, 1),
                               "bwd_frac": round(by_b / ms_b / 1e6 / peak, 3)}), flush=True)

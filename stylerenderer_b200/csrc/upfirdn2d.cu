@@ -639,214 +639,6 @@ upfirdn2d_nhwc_kernel(float *__restrict__ out, const float *__restrict__ x, cons
     }
 }
 
-// ---- channels-last FIR, row-streaming form (default) ------------------------------------------------------------------
-// Same thread decomposition and tails as upfirdn2d_nhwc_kernel (4 channels x 2 columns x a strip of rows), but the
-// input rows flow through a ring of the KH open output rows instead of a KH x (KW+1) input window: a thread keeps
-// 4 x 2 accumulators + the 5 pixels of the current row (52 instead of 100 vector registers' worth of state), so more
-// CTAs fit and more loads are in flight -- the kernel was latency bound (ncu: sm 54 %, DRAM 50 %, occupancy 24 %).
-// Rank-1 taps (every FIR the model builds is an outer product, reference layers.py:7-12) take the separable form: 4
-// FMAs for the row filter + 4 to scatter it over the open rows = 8 instead of 16 per output (checked on the device,
-// like upfirdn2d_tile_kernel); general taps accumulate in the same (a, b) order as the 2-D kernel (bit-identical).
-// D = input rows in flight per thread: a row buffer is re-loaded (row r + D) right after step r consumed it, so D row
-// loads overlap every step -- the kernel is bound by the latency of its sequential row loop (time ~ waves x rows x
-// latency, A/B record in profiles/r1_fir_ring_experiment.md), not by arithmetic.  NT = threads per CTA, MINB = CTAs per
-// SM the register allocation is bounded for.
-template <int MODE, int D, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB)
-fir_nhwc_ring_kernel(float *__restrict__ out, const float *__restrict__ x, const float *__restrict__ taps, const NhwcGeom g)
-{
-    constexpr int K = 4;
-    constexpr bool STYLED = (MODE == 1);
-    const int64_t tid = (int64_t)blockIdx.x * NT + threadIdx.x;
-    if (tid >= g.total_threads) return;
-    uint32_t t = (uint32_t)tid, c, xp, ys, n;
-    g.div_c4.divmod(t, t, c);
-    g.div_pairs.divmod(t, t, xp);
-    g.div_strips.divmod(t, n, ys);
-
-    // flipped taps tk[a][b] = taps[K-1-a][K-1-b]; rank-1 factorisation tk[a][b] = kv[a] * kh[b] through the largest tap
-    float kv[K], kh[K];
-    bool sep;
-    {
-        float tk[K][K];
-#pragma unroll
-        for (int a = 0; a < K; ++a)
-#pragma unroll
-            for (int b = 0; b < K; ++b) tk[a][b] = __ldg(taps + (K - 1 - a) * K + (K - 1 - b));
-        int pa = 0, pb = 0;
-        float best = 0.0f;
-#pragma unroll
-        for (int a = 0; a < K; ++a)
-#pragma unroll
-            for (int b = 0; b < K; ++b)
-                if (fabsf(tk[a][b]) > best) { best = fabsf(tk[a][b]); pa = a; pb = b; }
-        float pivot = 1.0f;
-#pragma unroll
-        for (int a = 0; a < K; ++a)
-#pragma unroll
-            for (int b = 0; b < K; ++b)
-                if (a == pa && b == pb) pivot = tk[a][b];
-#pragma unroll
-        for (int a = 0; a < K; ++a) {
-            kv[a] = 0.0f; kh[a] = 0.0f;
-#pragma unroll
-            for (int b = 0; b < K; ++b) {
-                if (b == pb) kv[a] = tk[a][b];
-                if (b == pa) kh[a] = tk[b][a] / pivot;
-            }
-        }
-        sep = best > 0.0f;
-#pragma unroll
-        for (int a = 0; a < K; ++a)
-#pragma unroll
-            for (int b = 0; b < K; ++b) sep = sep && fabsf(kv[a] * kh[b] - tk[a][b]) <= 1e-6f * best;
-    }
-
-    const int ox0 = xp * 2;
-    const int ix0 = ox0 - g.pad_x0;
-    const int oy0 = ys * g.rows_per_strip;
-    const int oy1 = min(g.out_h, oy0 + g.rows_per_strip);
-    const float4 *xin = reinterpret_cast<const float4 *>(x) + (int64_t)n * g.in_h * g.in_w * g.c4 + c;
-    float4 *yout = reinterpret_cast<float4 *>(out) + (int64_t)n * g.out_h * g.out_w * g.c4 + c;
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool col1 = ox0 + 1 < g.out_w;
-
-    float nw = 0.0f;
-    float4 bias4 = zero;
-    const float *nz = nullptr;
-    if (STYLED) {
-        if (g.noise) { nw = __ldg(g.noise_weight); nz = g.noise + (int64_t)n * g.noise_bstride; }
-        if (g.bias) bias4 = __ldg(reinterpret_cast<const float4 *>(g.bias) + c);
-    }
-    float4 sc2 = zero;
-    if ((STYLED && g.out2) || MODE == 2) sc2 = __ldg(reinterpret_cast<const float4 *>(g.scale2) + (int64_t)n * g.c4 + c);
-    float4 dot = zero;
-    const float4 *oth = (MODE == 2 && g.other) ? reinterpret_cast<const float4 *>(g.other) + (int64_t)n * g.out_h * g.out_w * g.c4 + c : nullptr;
-
-    float4 acc[K][2];                                      // acc[s]: output row (current - (K-1) + s), still open
-#pragma unroll
-    for (int s = 0; s < K; ++s) { acc[s][0] = zero; acc[s][1] = zero; }
-    const int nsteps = oy1 - oy0 + K - 1;
-    auto load_row = [&](float4 (&row)[K + 1], int iy) {
-        const bool row_ok = iy >= 0 && iy < g.in_h;
-        const float4 *src = xin + (int64_t)iy * g.in_w * g.c4;
-#pragma unroll
-        for (int b = 0; b < K + 1; ++b) {
-            const int ix = ix0 + b;
-            row[b] = (row_ok && ix >= 0 && ix < g.in_w) ? __ldg(src + (int64_t)ix * g.c4) : zero;
-        }
-    };
-    float4 buf[D][K + 1];
-#pragma unroll
-    for (int u = 0; u < D; ++u)
-        if (u < nsteps) load_row(buf[u], oy0 - g.pad_y0 + u);
-    auto step = [&](const float4 (&v)[K + 1], int r) {
-        const int oy = oy0 + r - (K - 1);                  // output row this step completes (a strip's first K-1 steps: none)
-        float4 tt[2] = {zero, zero};
-        if (MODE == 2 && oth && oy >= oy0) {               // issue the loads of the dot operand before the FMA block
-            tt[0] = __ldg(oth + ((int64_t)oy * g.out_w + ox0) * g.c4);
-            if (col1) tt[1] = __ldg(oth + ((int64_t)oy * g.out_w + ox0 + 1) * g.c4);
-        }
-        {                                                  // (rows outside the plane arrive as zeros)
-            if (sep) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    float4 h = zero;
-#pragma unroll
-                    for (int b = 0; b < K; ++b) {
-                        h.x = fmaf(v[j + b].x, kh[b], h.x); h.y = fmaf(v[j + b].y, kh[b], h.y);
-                        h.z = fmaf(v[j + b].z, kh[b], h.z); h.w = fmaf(v[j + b].w, kh[b], h.w);
-                    }
-#pragma unroll
-                    for (int a = 0; a < K; ++a) {          // input row iy is tap row a of output row iy + pad - a
-                        float4 &d = acc[K - 1 - a][j];
-                        d.x = fmaf(h.x, kv[a], d.x); d.y = fmaf(h.y, kv[a], d.y);
-                        d.z = fmaf(h.z, kv[a], d.z); d.w = fmaf(h.w, kv[a], d.w);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int a = 0; a < K; ++a)
-#pragma unroll
-                    for (int b = 0; b < K; ++b) {
-                        const float k = __ldg(taps + (K - 1 - a) * K + (K - 1 - b));
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            float4 &d = acc[K - 1 - a][j];
-                            d.x = fmaf(v[j + b].x, k, d.x); d.y = fmaf(v[j + b].y, k, d.y);
-                            d.z = fmaf(v[j + b].z, k, d.z); d.w = fmaf(v[j + b].w, k, d.w);
-                        }
-                    }
-            }
-        }
-        if (oy >= oy0) {
-            float4 o[2] = {acc[0][0], acc[0][1]};
-            const float4 pre[2] = {acc[0][0], acc[0][1]};      // stored instead of y with a stylemap
-            if (STYLED) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const bool in = (j == 0) || col1;
-                    float add = (nz && in) ? nw * __ldg(nz + (int64_t)oy * g.out_w + ox0 + j) : 0.0f;
-                    float m0 = 1.0f;
-                    if (g.stylemap && in) {
-                        const float *mp = g.stylemap + (int64_t)n * g.map_bstride + (int64_t)oy * g.out_w + ox0 + j;
-                        m0 = __ldg(mp);
-                        add += __ldg(mp + (int64_t)g.out_h * g.out_w);
-                    }
-                    float u;
-                    u = fmaf(o[j].x, m0, add + bias4.x); o[j].x = ((u > 0.f) ? u : u * g.alpha) * g.gain;
-                    u = fmaf(o[j].y, m0, add + bias4.y); o[j].y = ((u > 0.f) ? u : u * g.alpha) * g.gain;
-                    u = fmaf(o[j].z, m0, add + bias4.z); o[j].z = ((u > 0.f) ? u : u * g.alpha) * g.gain;
-                    u = fmaf(o[j].w, m0, add + bias4.w); o[j].w = ((u > 0.f) ? u : u * g.alpha) * g.gain;
-                }
-            }
-            if (MODE == 2) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (j == 1 && !col1) break;
-                    dot.x = fmaf(o[j].x, tt[j].x, dot.x); dot.y = fmaf(o[j].y, tt[j].y, dot.y);
-                    dot.z = fmaf(o[j].z, tt[j].z, dot.z); dot.w = fmaf(o[j].w, tt[j].w, dot.w);
-                    o[j].x = round_tf32_(o[j].x * sc2.x); o[j].y = round_tf32_(o[j].y * sc2.y);
-                    o[j].z = round_tf32_(o[j].z * sc2.z); o[j].w = round_tf32_(o[j].w * sc2.w);
-                }
-            }
-            float4 *dst = yout + ((int64_t)oy * g.out_w + ox0) * g.c4;
-            const bool keep_pre = STYLED && g.stylemap;
-            dst[0] = keep_pre ? pre[0] : o[0];
-            if (col1) dst[g.c4] = keep_pre ? pre[1] : o[1];
-            if (STYLED && g.out2) {
-                float4 *dst2 = reinterpret_cast<float4 *>(g.out2) + (int64_t)n * g.out_h * g.out_w * g.c4 + c +
-                               ((int64_t)oy * g.out_w + ox0) * g.c4;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (j == 1 && !col1) break;
-                    float4 q;
-                    q.x = round_tf32_(o[j].x * sc2.x); q.y = round_tf32_(o[j].y * sc2.y);
-                    q.z = round_tf32_(o[j].z * sc2.z); q.w = round_tf32_(o[j].w * sc2.w);
-                    dst2[(int64_t)j * g.c4] = q;
-                }
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < K - 1; ++s) { acc[s][0] = acc[s + 1][0]; acc[s][1] = acc[s + 1][1]; }
-        acc[K - 1][0] = zero; acc[K - 1][1] = zero;
-    };
-    for (int r0 = 0; r0 < nsteps; r0 += D) {
-#pragma unroll
-        for (int u = 0; u < D; ++u) {
-            const int r = r0 + u;
-            if (r < nsteps) {
-                step(buf[u], r);
-                if (r + D < nsteps) load_row(buf[u], oy0 - g.pad_y0 + r + D);
-            }
-        }
-    }
-    if (MODE == 2 && g.dot) {   // one 128-bit reduction per thread into dot[n, 4c .. 4c+3]
-        float *dp = g.dot + ((int64_t)n * g.c4 + c) * 4;
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dp), "f"(dot.x), "f"(dot.y), "f"(dot.z), "f"(dot.w) : "memory");
-    }
-}
-
 // ---- channels-last FIR, low-instruction-count form (default since round 2) ---------------------------------------------
 // ncu on the 256^2 layer of the generator step (profiles/r2_ncu_hbm_passes.md): upfirdn2d_nhwc_kernel issues 566 M warp
 // instructions for 67 M float4 outputs (270 per output: 64 FFMA for the 16 taps, 30 MOV to slide its 4 x 5 register window,
@@ -1058,28 +850,7 @@ fir_nhwc_sep_kernel(float *__restrict__ out, const float *__restrict__ x, const 
     }
 }
 
-// ---- channels-last FIR through TMA-staged tiles (up = down = 1, 4x4 taps, C % 32 == 0, planes >= 32 x 32) --------------
-// Persistent CTAs walk the tile list; a tile is 16 x 32 output pixels x 32 channels.  A producer warp fetches the
-// {32 ch, 19, 35} input box of the next tile with ONE TMA instruction into a 2-stage shared-memory ring (zero fill
-// outside the plane = the FIR padding, so there is not a single bounds test on the load side) while 8 consumer warps
-// run the FIR out of shared memory: thread = 4 channels x 2 columns x 8 rows, sliding 4 x 5 register window fed by
-// LDS.128 (lanes 0-7 read the 128 contiguous bytes of one pixel -> conflict free), results leave as 16-byte stores
-// whose 8-lane groups cover whole 128-byte lines.  HBM sees each input byte once (tile halos overlap in L2).
-constexpr int FT_W = 16, FT_C = 32, FT_STAGES = 2;
-constexpr int FT_IW = FT_W + 3;
-constexpr int FT_CONSUMERS = 256;
-
-struct FirTmaGeom {
-    int out_h, out_w, c, cblocks, tiles_x, tiles_y, total_tiles, pad0;
-    FastDiv div_cb, div_tx, div_ty;
-    const float *noise, *noise_weight, *bias;
-    long long noise_bstride;
-    float alpha, gain;
-    float *out2;
-    const float *scale2, *other;
-    float *dot;
-};
-
+// ---- helpers of the ring kernels below (mbarrier wait, shared-space loads) ---------------------------------------------
 __device__ __forceinline__ void ft_mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n.reg .pred p;\nFTW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra FTD_%=;\nbra FTW_%=;\nFTD_%=:\n}\n"
@@ -1099,158 +870,6 @@ __device__ __forceinline__ float lds_f1(uint32_t addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
-}
-
-template <int MODE, int FT_H, int TR>     // MODE 0 plain, 1 styled forward tail (+ optional out2), 2 scale-dot backward tail
-__global__ void __launch_bounds__(FT_CONSUMERS + 32, FT_H == 32 ? 1 : 2)   // FT_H = 32: one CTA per SM, 16: two; TR < 4: timing experiment only
-fir_nhwc_tma_kernel(float *__restrict__ out, const __grid_constant__ CUtensorMap tmap_x, const float *__restrict__ taps,
-                    const FirTmaGeom g)
-{
-    constexpr int FT_IH = FT_H + 3, FT_STAGE_BYTES = FT_IW * FT_IH * FT_C * 4, RPS = FT_H / 4;   // rows per strip
-    extern __shared__ uint8_t ft_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(ft_raw) + 127) & ~(uintptr_t)127);
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + FT_STAGES * FT_STAGE_BYTES);
-    uint64_t *empty_bar = full_bar + FT_STAGES;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    if (threadIdx.x == 0) {
-        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_x) : "memory");
-        for (int s = 0; s < FT_STAGES; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&full_bar[s])), "r"(1u) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&empty_bar[s])), "r"(8u) : "memory");
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (warp == FT_CONSUMERS / 32) {                   // ===== producer warp
-        if (lane == 0) {
-            uint32_t s = 0, ph = 0;
-            for (uint32_t T = blockIdx.x; T < (uint32_t)g.total_tiles; T += gridDim.x) {
-                uint32_t t = T, cb, tx, ty, n;
-                g.div_cb.divmod(t, t, cb);
-                g.div_tx.divmod(t, t, tx);
-                g.div_ty.divmod(t, n, ty);
-                ft_mbar_wait(&empty_bar[s], ph ^ 1);
-                const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&full_bar[s]);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t)FT_STAGE_BYTES) : "memory");
-                asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                             :: "r"((uint32_t)__cvta_generic_to_shared(smem + s * FT_STAGE_BYTES)), "l"(&tmap_x), "r"(bar),
-                                "r"((int)(cb * FT_C)), "r"((int)(tx * FT_W) - g.pad0), "r"((int)(ty * FT_H) - g.pad0), "r"((int)n) : "memory");
-                if (++s == FT_STAGES) { s = 0; ph ^= 1; }
-            }
-        }
-        return;
-    }
-
-    // ===== consumers
-    float tk[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) tk[a][b] = __ldg(taps + (3 - a) * 4 + (3 - b));
-    const int q4 = threadIdx.x & 7, cp = (threadIdx.x >> 3) & 7, strip = threadIdx.x >> 6;
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    float nw = 0.0f;
-    if (MODE == 1 && g.noise) nw = __ldg(g.noise_weight);
-
-    uint32_t s = 0, ph = 0;
-    for (uint32_t T = blockIdx.x; T < (uint32_t)g.total_tiles; T += gridDim.x) {
-        uint32_t t = T, cb, tx, ty, n;
-        g.div_cb.divmod(t, t, cb);
-        g.div_tx.divmod(t, t, tx);
-        g.div_ty.divmod(t, n, ty);
-        const int ox0 = tx * FT_W + 2 * cp, oy0 = ty * FT_H + RPS * strip;
-        const int ch = cb * FT_C + 4 * q4;
-        float4 bias4 = zero, sc2 = zero;
-        if (MODE == 1 && g.bias) bias4 = __ldg(reinterpret_cast<const float4 *>(g.bias + ch));
-        if ((MODE == 1 && g.out2) || MODE == 2) sc2 = __ldg(reinterpret_cast<const float4 *>(g.scale2 + (long long)n * g.c + ch));
-        const long long pix0 = ((long long)n * g.out_h) * g.out_w;       // first output pixel of the image
-        float4 dot = zero;
-
-        ft_mbar_wait(&full_bar[s], ph);
-        const float4 *tile = reinterpret_cast<const float4 *>(smem + s * FT_STAGE_BYTES) + q4;
-        // window rows: input row (8*strip + r) of the box, columns 2cp .. 2cp+4
-        float4 win[4][5];
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int b = 0; b < 5; ++b) win[a][b] = tile[((RPS * strip + a) * FT_IW + 2 * cp + b) * (FT_C / 4)];
-#pragma unroll
-        for (int r = 0; r < RPS; ++r) {
-#pragma unroll
-            for (int b = 0; b < 5; ++b) win[3][b] = tile[((RPS * strip + r + 3) * FT_IW + 2 * cp + b) * (FT_C / 4)];
-            const int oy = oy0 + r;
-            const bool row_ok = oy < g.out_h;
-            float4 tt[2] = {zero, zero};
-            if (MODE == 2 && row_ok) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-                    if (ox0 + j < g.out_w)
-                        tt[j] = __ldg(reinterpret_cast<const float4 *>(g.other + (pix0 + (long long)oy * g.out_w + ox0 + j) * g.c + ch));
-            }
-            float4 acc[2] = {zero, zero};
-#pragma unroll
-            for (int a = 0; a < TR; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const float4 v = win[a][j + b];
-                        const float k = tk[a][b];
-                        acc[j].x = fmaf(v.x, k, acc[j].x); acc[j].y = fmaf(v.y, k, acc[j].y);
-                        acc[j].z = fmaf(v.z, k, acc[j].z); acc[j].w = fmaf(v.w, k, acc[j].w);
-                    }
-            if (row_ok) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (ox0 + j >= g.out_w) break;
-                    const long long pix = pix0 + (long long)oy * g.out_w + ox0 + j;
-                    float4 y = acc[j];
-                    if (MODE == 1) {
-                        const float add = g.noise ? nw * __ldg(g.noise + (long long)n * g.noise_bstride + (long long)oy * g.out_w + ox0 + j) : 0.0f;
-                        float u;
-                        u = y.x + add + bias4.x; y.x = ((u > 0.f) ? u : u * g.alpha) * g.gain;
-                        u = y.y + add + bias4.y; y.y = ((u > 0.f) ? u : u * g.alpha) * g.gain;
-                        u = y.z + add + bias4.z; y.z = ((u > 0.f) ? u : u * g.alpha) * g.gain;
-                        u = y.w + add + bias4.w; y.w = ((u > 0.f) ? u : u * g.alpha) * g.gain;
-                    }
-                    if (MODE == 2) {
-                        dot.x = fmaf(y.x, tt[j].x, dot.x); dot.y = fmaf(y.y, tt[j].y, dot.y);
-                        dot.z = fmaf(y.z, tt[j].z, dot.z); dot.w = fmaf(y.w, tt[j].w, dot.w);
-                        y.x = round_tf32_(y.x * sc2.x); y.y = round_tf32_(y.y * sc2.y);
-                        y.z = round_tf32_(y.z * sc2.z); y.w = round_tf32_(y.w * sc2.w);
-                    }
-                    *reinterpret_cast<float4 *>(out + pix * g.c + ch) = y;
-                    if (MODE == 1 && g.out2) {
-                        float4 o;
-                        o.x = round_tf32_(y.x * sc2.x); o.y = round_tf32_(y.y * sc2.y);
-                        o.z = round_tf32_(y.z * sc2.z); o.w = round_tf32_(y.w * sc2.w);
-                        *reinterpret_cast<float4 *>(g.out2 + pix * g.c + ch) = o;
-                    }
-                }
-            }
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int b = 0; b < 5; ++b) win[a][b] = win[a + 1][b];
-        }
-        // this warp no longer reads the stage
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"((uint32_t)__cvta_generic_to_shared(&empty_bar[s])) : "memory");
-        if (MODE == 2) {        // lanes with equal channel quad (l, l^8, l^16, l^24) -> one 128-bit reduction per quad and warp
-#pragma unroll
-            for (int o = 8; o < 32; o <<= 1) {
-                dot.x += __shfl_xor_sync(0xffffffffu, dot.x, o); dot.y += __shfl_xor_sync(0xffffffffu, dot.y, o);
-                dot.z += __shfl_xor_sync(0xffffffffu, dot.z, o); dot.w += __shfl_xor_sync(0xffffffffu, dot.w, o);
-            }
-            if (lane < 8) {
-                float *dp = g.dot + (long long)n * g.c + ch;
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dp), "f"(dot.x), "f"(dot.y), "f"(dot.z), "f"(dot.w) : "memory");
-            }
-        }
-        if (++s == FT_STAGES) { s = 0; ph ^= 1; }
-    }
 }
 
 // Flipped taps tk[a][b] = taps[3-a][3-b] of a 4 x 4 FIR and, when the matrix is rank 1 (every FIR the model builds,
@@ -2039,74 +1658,6 @@ int launch_tile(float *out, const float *x, const float *taps, int64_t major, in
     return SR_OK;
 }
 
-// TMA path of launch_nhwc: returns SR_ERR_UNSUPPORTED when the shape does not qualify.
-int launch_nhwc_tma(float *out, const float *x, const float *taps, int64_t major, int in_h, int in_w, int oh, int ow,
-                    int64_t minor, int pad0, int mode, const float *noise, long long noise_bstride, const float *noise_weight,
-                    const float *bias, float alpha, float gain, cudaStream_t st, float *out2, const float *scale2,
-                    const float *other, float *dot)
-{
-    // Opt-in (SR_FIR_TMA=1).  Measured on the B=32 generator step (profiles/r1_fir_tma_experiment.md): 1.48 / 1.93 ms for
-    // the forward / backward tails against 1.44 / 1.53 ms of the register-window kernel above; halving the FMAs moves it
-    // by 5 %, so neither variant is arithmetic bound -- the L1-cached direct loads with 16 resident warps hide latency
-    // better than 8 consumer warps behind a 2-stage TMA ring.
-    static const char *on = getenv("SR_FIR_TMA");
-    if (!(on && on[0] == '1')) return SR_ERR_UNSUPPORTED;
-    if (minor % FT_C != 0 || oh < 32 || ow < 32 || (reinterpret_cast<uintptr_t>(x) & 15u)) return SR_ERR_UNSUPPORTED;
-    EncodeTiledFn enc = encode_tiled();
-    if (!enc) return SR_ERR_UNSUPPORTED;
-    CUtensorMap tm;
-    cuuint64_t dims[4] = {(cuuint64_t)minor, (cuuint64_t)in_w, (cuuint64_t)in_h, (cuuint64_t)major};
-    cuuint64_t strides[3] = {(cuuint64_t)minor * 4, (cuuint64_t)in_w * minor * 4, (cuuint64_t)in_h * in_w * minor * 4};
-    static const char *dbg = getenv("SR_FIR_DEBUG");            // 1: half the taps (timing experiment), 2: 16-row tiles, 2 CTAs/SM
-    const int variant = dbg ? atoi(dbg) : 0;
-    const int FT_H = (variant & 2) ? 16 : 32, FT_IH = FT_H + 3, FT_STAGE_BYTES = FT_IW * FT_IH * FT_C * 4;
-    cuuint32_t box[4] = {FT_C, FT_IW, (cuuint32_t)FT_IH, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return SR_ERR_UNSUPPORTED;
-    FirTmaGeom g;
-    g.out_h = oh; g.out_w = ow; g.c = (int)minor; g.cblocks = (int)(minor / FT_C);
-    g.tiles_x = (ow + FT_W - 1) / FT_W; g.tiles_y = (oh + FT_H - 1) / FT_H;
-    const int64_t total = (int64_t)major * g.tiles_x * g.tiles_y * g.cblocks;
-    if (total >= 0x7fffffffll) return SR_ERR_UNSUPPORTED;
-    g.total_tiles = (int)total; g.pad0 = pad0;
-    g.div_cb = FastDiv((uint32_t)g.cblocks); g.div_tx = FastDiv((uint32_t)g.tiles_x); g.div_ty = FastDiv((uint32_t)g.tiles_y);
-    g.noise = noise; g.noise_weight = noise_weight; g.bias = bias; g.noise_bstride = noise_bstride;
-    g.alpha = alpha; g.gain = gain; g.out2 = out2; g.scale2 = scale2; g.other = other; g.dot = dot;
-    const size_t smem = 128 + (size_t)FT_STAGES * FT_STAGE_BYTES + 64;
-    const int slots = (variant & 2) ? 2 * kNumSMs : kNumSMs;
-    const int grid = total < slots ? (int)total : slots;
-    static bool configured[12] = {};
-    auto launch = [&](auto kern, int idx) -> int {
-        if (!configured[idx]) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return SR_ERR_UNSUPPORTED;
-            configured[idx] = true;
-        }
-        kern<<<grid, FT_CONSUMERS + 32, smem, st>>>(out, tm, taps, g);
-        return SR_OK;
-    };
-    if (variant == 1) {
-        if (mode == 2) return launch(fir_nhwc_tma_kernel<2, 32, 2>, 3);
-        if (mode == 1) return launch(fir_nhwc_tma_kernel<1, 32, 2>, 4);
-        return launch(fir_nhwc_tma_kernel<0, 32, 2>, 5);
-    }
-    if (variant == 2) {
-        if (mode == 2) return launch(fir_nhwc_tma_kernel<2, 16, 4>, 6);
-        if (mode == 1) return launch(fir_nhwc_tma_kernel<1, 16, 4>, 7);
-        return launch(fir_nhwc_tma_kernel<0, 16, 4>, 8);
-    }
-    if (variant == 3) {
-        if (mode == 2) return launch(fir_nhwc_tma_kernel<2, 16, 2>, 9);
-        if (mode == 1) return launch(fir_nhwc_tma_kernel<1, 16, 2>, 10);
-        return launch(fir_nhwc_tma_kernel<0, 16, 2>, 11);
-    }
-    if (mode == 2) return launch(fir_nhwc_tma_kernel<2, 32, 4>, 2);
-    if (mode == 1) return launch(fir_nhwc_tma_kernel<1, 32, 4>, 1);
-    return launch(fir_nhwc_tma_kernel<0, 32, 4>, 0);
-}
-
 // Streaming path of launch_nhwc (fir_nhwc_stream_kernel): returns SR_ERR_UNSUPPORTED when the shape does not qualify.
 int launch_nhwc_stream(float *out, const float *x, const float *taps, int64_t major, int in_h, int in_w, int oh, int ow,
                        int64_t minor, int pad_x0, int pad_y0, int mode, const float *noise, long long noise_bstride,
@@ -2195,12 +1746,6 @@ int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, in
                                bias, alpha, gain, st, out2, scale2, other, dot, stylemap, map_bstride, op16) == SR_OK)
             return SR_OK;
     }
-    if (pad_x0 == pad_y0 && !stylemap && !op16) {
-        const int rc = (!dot && !styled && scale2) ? SR_ERR_UNSUPPORTED :
-                       launch_nhwc_tma(out, x, taps, major, in_h, in_w, oh, ow, minor, pad_x0, dot ? 2 : (styled ? 1 : 0), noise,
-                                       noise_bstride, noise_weight, bias, alpha, gain, st, out2, scale2, other, dot);
-        if (rc == SR_OK) return rc;
-    }
     NhwcGeom g;
     g.out2 = out2; g.scale2 = scale2; g.other = other; g.dot = dot;
     g.stylemap = stylemap; g.map_bstride = map_bstride; g.op16 = op16;
@@ -2215,37 +1760,18 @@ int launch_nhwc(float *out, const float *x, const float *taps, int64_t major, in
     g.alpha = alpha; g.gain = gain;
     if (g.total_threads >= 0x7fffffffll) return SR_ERR_UNSUPPORTED;
     const int64_t blocks = (g.total_threads + kThreads - 1) / kThreads;
-    // A/B switch, read per call: 0 = the 4x5 input-window kernel (default: measured best, profiles/r1_fir_ring_experiment.md),
-    // 1-5 = row-streaming ring kernels with (rows in flight, threads per CTA, CTAs per SM) = (2,256,2) (3,128,3) (3,256,1)
-    // (4,128,2) (1,256,2)
-    const char *ring_env = getenv("SR_FIR_RING");
-    const int ring = (ring_env && ring_env[0] >= '0' && ring_env[0] <= '5' && !op16) ? ring_env[0] - '0' : 0;
     const int mode = (dot || (!styled && scale2)) ? 2 : (styled ? 1 : 0);
-#define SR_RING(D, NT, MINB)                                                                                           \
-    do {                                                                                                               \
-        const unsigned nb = (unsigned)((g.total_threads + NT - 1) / NT);                                               \
-        if (mode == 2) fir_nhwc_ring_kernel<2, D, NT, MINB><<<nb, NT, 0, st>>>(out, x, taps, g);                        \
-        else if (mode == 1) fir_nhwc_ring_kernel<1, D, NT, MINB><<<nb, NT, 0, st>>>(out, x, taps, g);                   \
-        else fir_nhwc_ring_kernel<0, D, NT, MINB><<<nb, NT, 0, st>>>(out, x, taps, g);                                  \
-    } while (0)
     // default: the low-instruction-count separable kernel (fir_nhwc_sep_kernel); SR_FIR_SEP=0 = the 4x5 input-window kernel
-    static const char *sep_env = getenv("SR_FIR_SEP");
-    const bool use_sep = ring == 0 && !(sep_env && sep_env[0] == '0');
-    if (use_sep) {
+    const char *sep_env = getenv("SR_FIR_SEP");
+    if (!(sep_env && sep_env[0] == '0')) {
         if (mode == 2) fir_nhwc_sep_kernel<2><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
         else if (mode == 1) fir_nhwc_sep_kernel<1><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
         else fir_nhwc_sep_kernel<0><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
-    } else if (ring == 1) SR_RING(2, 256, 2);
-    else if (ring == 2) SR_RING(3, 128, 3);
-    else if (ring == 3) SR_RING(3, 256, 1);
-    else if (ring == 4) SR_RING(4, 128, 2);
-    else if (ring == 5) SR_RING(1, 256, 2);
-    else {
+    } else {
         if (mode == 2) upfirdn2d_nhwc_kernel<4, 4, 2><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
         else if (mode == 1) upfirdn2d_nhwc_kernel<4, 4, 1><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
         else upfirdn2d_nhwc_kernel<4, 4, 0><<<(unsigned)blocks, kThreads, 0, st>>>(out, x, taps, g);
     }
-#undef SR_RING
     return SR_OK;
 }
 
