@@ -650,7 +650,8 @@ def run_train_step(args):
                 "config": dict(res["config"], global_batch=world * cfg.batch, conv_backend=res["conv_backend"], precision=res["dtype"],
                                l2="activations per iteration exceed the 126 MB L2; no explicit flush"),
                 "clocks": clocks.summary(), "e2e": res.get("e2e"), "gpu_launches": int(res["gpu_launches_per_iter"]),
-                "roofline": roof, "cpu_baseline": cpu_base, "collective": res["collective"], "losses": res["losses"]}
+                "roofline": roof, "cpu_baseline": cpu_base, "collective": res["collective"], "losses": res["losses"],
+                "phase_ms": res.get("phase_ms")}
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist

@@ -441,11 +441,25 @@ def run(args):
             ms = timed(args.iters)
         print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90), file=sys.stderr)
         # which torch ops (with their input shapes) still own device time: the library / elementwise leftovers
-        print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=60, max_name_column_width=50,
+        print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=250, max_name_column_width=50,
                                                                   max_shapes_column_width=110), file=sys.stderr)
     else:
         ms = timed(args.iters)
     launches = (_lib.launch_count() - n0) // args.iters
+    phase_ms = None
+    if use_graph:                                                       # device time of every phase graph (3 replays each)
+        phase_ms = {}
+        for name, gr in graphs.items():
+            torch.cuda.synchronize()
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record()
+            for _ in range(3):
+                gr.replay()
+            e_.record()
+            torch.cuda.synchronize()
+            phase_ms[name] = round(s_.elapsed_time(e_) / 3, 3)
+        phase_ms["per_iteration"] = round(phase_ms["d"] + phase_ms["g"] + phase_ms["d_opt"] + phase_ms["g_opt"]
+                                          + (phase_ms["r1"] + phase_ms["d_opt"]) / d_reg + (phase_ms["path"] + phase_ms["g_opt"]) / g_reg, 3)
     if use_graph:                                                       # replays do not pass through the C ABI: count the captures
         gl = graph_launches
         launches = int(gl["d"] + gl["g"] + gl["r1"] / d_reg + gl["path"] / g_reg)
@@ -509,6 +523,7 @@ def run(args):
                    "execution": "cuda_graph_replay (4 phase graphs + 2 optimiser graphs)" if use_graph else "eager",
                    "mesh": f"{args.mesh_n ** 2} verts / {tri.shape[0]} tris"},
         "gpu_launches_per_iter": launches, "losses": {k: round(float(v), 5) for k, v in losses.items()},
+        "phase_ms": phase_ms,
         "collective": comm}
     if ms_e2e is not None:
         res["e2e"] = {"value": round(world * B * args.iters / (ms_e2e * 1e-3), 2), "unit": "images/s",

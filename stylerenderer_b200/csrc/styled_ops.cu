@@ -360,6 +360,22 @@ static int styled_bwd_prologue_any(float *ga, float *g_bias, float *g_noise_w, f
         default: launched = false;
         }
     }
+    // StyledMapConv blocks (GeneratorWithMap): the same four combinations with the style-map arithmetic compiled in (they ran
+    // the 117-register run-time kernel at 45 % of DRAM: ncu, profiles/r2_ncu_full_summary.md); SR_PROLOGUE_SPEC=0/3 keeps it
+    if (!launched && stylemap && !(spec_env && (spec_env[0] == '0' || spec_env[0] == '3'))) {
+        launched = true;
+        switch (spec) {
+        case kSpecGxs | kSpecE | kSpecNoise:
+            styled_bwd_prologue_kernel<true, kSpecGxs | kSpecE | kSpecNoise, 2, 2><<<nb, kThreads, 0, st>>>(p); break;
+        case kSpecGxs | kSpecE | kSpecNoise | kSpecD:
+            styled_bwd_prologue_kernel<true, kSpecGxs | kSpecE | kSpecNoise | kSpecD, 2, 2><<<nb, kThreads, 0, st>>>(p); break;
+        case kSpecGxs | kSpecRgb | kSpecE | kSpecNoise | kSpecD:
+            styled_bwd_prologue_kernel<true, kSpecGxs | kSpecRgb | kSpecE | kSpecNoise | kSpecD, 2, 2><<<nb, kThreads, 0, st>>>(p); break;
+        case kSpecGy | kSpecRgb | kSpecE | kSpecNoise | kSpecD:
+            styled_bwd_prologue_kernel<true, kSpecGy | kSpecRgb | kSpecE | kSpecNoise | kSpecD, 2, 2><<<nb, kThreads, 0, st>>>(p); break;
+        default: launched = false;
+        }
+    }
     if (!launched) {
         if (stylemap) styled_bwd_prologue_kernel<true, -1, 1><<<nb, kThreads, 0, st>>>(p);
         else styled_bwd_prologue_kernel<false, -1, 1><<<nb, kThreads, 0, st>>>(p);

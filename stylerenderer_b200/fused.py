@@ -281,16 +281,80 @@ def plain_conv_dd(conv, act, x, kind):
     return fused_leaky_relu(y, bias, act.negative_slope, act.scale)
 
 
+class ScaleBC(Function):
+    """y[b,h,w,c] = a[b,h,w,c] * s[b,c] on channels-last tensors (sr_scale_dot_nhwc_f32).  With DotP (r[b,c] = sum over pixels
+    of a * o) and ScaleDot (both in one pass) it is closed under differentiation -- the modulation / demodulation multiplies
+    of ModulatedConv2d (reference layers.py:296-299, here in activation form) for the regulariser iterations that
+    differentiate twice: torch's `x * s.view(b,c,1,1)` costs a multiply, and per differentiation two more multiplies with a
+    full-size temporary plus a reduction pass."""
+
+    @staticmethod
+    def forward(ctx, a, s):
+        a, s = a.contiguous(), s.contiguous()
+        ctx.save_for_backward(a, s)
+        return tc.scale_dot(a, None, s, False)[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        a, s = ctx.saved_tensors
+        need_a, need_s = ctx.needs_input_grad
+        if need_a and need_s:
+            return ScaleDot.apply(g, a, s)
+        if need_a:
+            return ScaleBC.apply(g, s), None
+        return None, (DotP.apply(g, a) if need_s else None)
+
+
+class DotP(Function):
+    """r[b,c] = sum_{h,w} a[b,h,w,c] * o[b,h,w,c] (one read of both, no full-size temporary)."""
+
+    @staticmethod
+    def forward(ctx, a, o):
+        a, o = a.contiguous(), o.contiguous()
+        ctx.save_for_backward(a, o)
+        return tc.scale_dot(a, o, None, False, want_out=False)[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        a, o = ctx.saved_tensors
+        return (ScaleBC.apply(o, g) if ctx.needs_input_grad[0] else None,
+                ScaleBC.apply(a, g) if ctx.needs_input_grad[1] else None)
+
+
+class ScaleDot(Function):
+    """(g * s[b,c], sum_{h,w} g * a) in ONE pass over g and a: the two gradients of ScaleBC."""
+
+    @staticmethod
+    def forward(ctx, g, a, s):
+        g, a, s = g.contiguous(), a.contiguous(), s.contiguous()
+        ctx.save_for_backward(g, a, s)
+        ctx.set_materialize_grads(False)
+        return tc.scale_dot(g, a, s, False)
+
+    @staticmethod
+    def backward(ctx, go, gd):
+        g, a, s = ctx.saved_tensors
+        gg = ga = gs = None
+        if go is not None:                               # out = g * s
+            gg, gs = ScaleBC.apply(go, s), DotP.apply(go, g)
+        if gd is not None:                               # dot = sum g * a
+            t = ScaleBC.apply(a, gd)
+            gg = t if gg is None else gg + t
+            ga = ScaleBC.apply(g, gd)
+        return gg, ga, gs
+
+
 def mod_conv_dd(mod, x, style):
-    """ModulatedConv2d.forward for iterations that need double backward: the modulation / demodulation are plain torch
-    ops (differentiable to any order), the contraction is ConvTC on the tensor cores."""
+    """ModulatedConv2d.forward for iterations that need double backward: modulation / demodulation through the ScaleBC /
+    DotP pair (closed under differentiation), the contraction through ConvTC on the tensor cores."""
     s, d = mod.style_scales(style)
-    b, cin = x.shape[:2]
-    xs = (x * s.view(b, cin, 1, 1)).permute(0, 2, 3, 1).contiguous()
-    y = ConvTC.apply(xs, mod.weight[0] * mod.scale, "up" if mod.upsample else "plain").permute(0, 3, 1, 2)
+    xs = ScaleBC.apply(to_nhwc(x), s)
+    y = ConvTC.apply(xs, mod.weight[0] * mod.scale, "up" if mod.upsample else "plain")
     if mod.upsample:
-        y = mod.blur(y)
-    return y * d.view(b, -1, 1, 1)
+        y = to_nhwc(mod.blur(from_nhwc(y)))
+    if d is not None:
+        y = ScaleBC.apply(y, d)
+    return from_nhwc(y)
 
 
 _ONES = {}

@@ -113,3 +113,37 @@ def test_raster_pyramid_block_table(b, sizes):
             assert count >= 1
             seen[key_off[lv] + pix0: key_off[lv] + pix0 + count] += 1
     assert (seen == 1).all(), "every pixel of every level belongs to exactly one block"
+
+
+def test_scale_bc_family_is_closed_under_differentiation(monkeypatch):
+    """fused.ScaleBC / DotP / ScaleDot (the modulation / demodulation multiplies of ModulatedConv2d in the regulariser
+    iterations) express each other's derivatives: first and second derivatives against finite differences, with the CUDA
+    primitive (sr_scale_dot_nhwc_f32) replaced by its torch definition so that the autograd logic runs on the CPU."""
+    import torch
+    from torch.autograd import gradcheck, gradgradcheck
+    from stylerenderer_b200 import fused
+
+    def scale_dot(a, other, scale, round_out, want_out=True):
+        b, _, _, c = a.shape
+        out = (a * scale.view(b, 1, 1, c) if scale is not None else a.clone()) if want_out else None
+        dot = (a * other).sum((1, 2)) if other is not None else None
+        return out, dot
+    monkeypatch.setattr(fused.tc, "scale_dot", scale_dot)
+    torch.manual_seed(3)
+    a = torch.randn(2, 3, 2, 4, dtype=torch.float64, requires_grad=True)
+    o = torch.randn(2, 3, 2, 4, dtype=torch.float64, requires_grad=True)
+    s = torch.randn(2, 4, dtype=torch.float64, requires_grad=True)
+    assert gradcheck(fused.ScaleBC.apply, (a, s)) and gradgradcheck(fused.ScaleBC.apply, (a, s))
+    assert gradcheck(fused.DotP.apply, (a, o)) and gradgradcheck(fused.DotP.apply, (a, o))
+    assert gradcheck(fused.ScaleDot.apply, (a, o, s)) and gradgradcheck(fused.ScaleDot.apply, (a, o, s))
+    # the shape of the path-length regulariser: a gradient-norm penalty through x -> ScaleBC -> nonlinearity
+    x = torch.randn(2, 3, 2, 4, dtype=torch.float64, requires_grad=True)
+
+    def penalty(fn):
+        y = torch.tanh(fn(x, s)).sum()
+        gx, = torch.autograd.grad(y, x, create_graph=True)
+        return torch.autograd.grad(gx.pow(2).sum(), [x, s])
+    got = penalty(fused.ScaleBC.apply)
+    want = penalty(lambda xx, ss: xx * ss.view(2, 1, 1, 4))
+    for g, w in zip(got, want):
+        torch.testing.assert_close(g, w)
