@@ -742,3 +742,53 @@ def test_stem_conv_kernel_vs_composed_fp64(shape, channels_last):
     close("dx", xg.grad, xr.grad, 2e-5)
     for (n, p), (_, q) in zip(layer.named_parameters(), ref.named_parameters()):
         close(n, p.grad, q.grad, 3e-5)
+
+
+@pytest.mark.parametrize("mode", ["tf32x3", "tf32"])
+@pytest.mark.parametrize("up", [False, True])
+def test_modulated_conv_double_backward_mode_matches_composed(up, mode):
+    """ModulatedConv2d under layers.double_backward() on the tensor-core backend (fused.mod_conv_dd: ScaleBC / DotP
+    modulation pair + ConvTC contraction, every piece differentiable to any order) against the composed torch ops in
+    float64 on the CPU: output, first-order gradients, and the gradients of a path-length-style penalty (reference
+    train.py:118-134: norm of the gradient w.r.t. the style, differentiated again w.r.t. the parameters)."""
+    from stylerenderer_b200 import layers as L
+    from make_golden import seeded
+    torch.manual_seed(11)
+    b, cin, cout, h = 2, 128, 128, 8
+    mod = L.ModulatedConv2d(cin, cout, 3, 64, upsample=up)
+    x0, w0 = seeded((b, cin, h, h), 50), seeded((b, 64), 51)
+    oh = 2 * h if up else h
+    noise = seeded((b, cout, oh, oh), 52) / oh
+
+    def run(m, x, w):
+        y = m(x, w)
+        g, = torch.autograd.grad((torch.tanh(y) * noise.to(y)).sum(), w, create_graph=True)
+        pen = g.pow(2).sum(1).sqrt().sum() + y.square().mean()
+        params = [p for p in m.parameters()]
+        grads = torch.autograd.grad(pen, params + [x], allow_unused=True)
+        return y, pen, grads
+
+    ref = L.ModulatedConv2d(cin, cout, 3, 64, upsample=up).double()
+    ref.load_state_dict({k: v.double() for k, v in mod.state_dict().items()})
+    yr, pr, gr = run(ref, x0.double().requires_grad_(True), w0.double().requires_grad_(True))
+    mod = mod.cuda()
+    noise = noise.cuda()
+    old = L.get_conv_backend()
+    L.set_conv_backend("tcgen05")
+    from stylerenderer_b200 import tc_conv as tc
+    try:
+        with L.double_backward(), tc.precision(mode):
+            xg = x0.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+            yg, pg, gg = run(mod, xg, w0.cuda().requires_grad_(True))
+    finally:
+        L.set_conv_backend(old)
+    tol = 1e-3 if mode == "tf32x3" else 3e-2                          # tf32: second-order quantities through tf32 contractions
+
+    def rel(a, b_):
+        return (a.detach().cpu().double() - b_.detach()).abs().max().item() / (b_.detach().abs().max().item() + 1e-12)
+    assert rel(yg, yr) < min(tol, 2e-3)
+    assert abs(float(pg.detach()) - float(pr.detach())) < tol * abs(float(pr.detach()))
+    for a, b_ in zip(gg, gr):
+        assert (a is None) == (b_ is None)
+        if a is not None:
+            assert rel(a, b_) < tol, (mode, rel(a, b_))
