@@ -51,6 +51,13 @@ class StyledMapConv(nn.Module):                       # reference model.py:33-55
 
     def forward(self, input, style, stylemap, noise=None):
         out = self.conv(input, style)
+        if out.is_cuda and double_backward_requested():
+            # regulariser iterations (composed, twice differentiable): the map affine and the noise injection as ONE
+            # full-size pass -- out * map0 + (map1 + weight * noise), the per-pixel term is a [B,1,H,W] tensor
+            if noise is None:
+                noise = out.new_empty(out.shape[0], 1, out.shape[2], out.shape[3]).normal_()
+            out = torch.addcmul(stylemap[:, 1:2] + self.noise.weight * noise, out, stylemap[:, :1])
+            return self.activate(out)
         out = out * stylemap[:, :1] + stylemap[:, 1:2]                    # reference model.py:50
         out = self.noise(out, noise=noise)
         return self.activate(out)
