@@ -51,7 +51,7 @@ class StyledMapConv(nn.Module):                       # reference model.py:33-55
 
     def forward(self, input, style, stylemap, noise=None):
         out = self.conv(input, style)
-        if out.is_cuda and double_backward_requested():
+        if out.is_cuda and layers.double_backward_requested():
             # regulariser iterations (composed, twice differentiable): the map affine and the noise injection as ONE
             # full-size pass -- out * map0 + (map1 + weight * noise), the per-pixel term is a [B,1,H,W] tensor
             if noise is None:
