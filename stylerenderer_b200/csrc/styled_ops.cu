@@ -349,6 +349,8 @@ static int styled_bwd_prologue_any(float *ga, float *g_bias, float *g_noise_w, f
     if (!launched && !(spec_env && spec_env[0] == '0') && !stylemap && (spec_rgb || !g_rgb)) {
         launched = true;
         switch (spec) {                                   // the combinations the chained generator produces
+        case kSpecGy | kSpecD:                                                   // plain ConvLayer (Discriminator, perceptual stack)
+            styled_bwd_prologue_kernel<false, kSpecGy | kSpecD, 4><<<nb, kThreads, 0, st>>>(p); break;
         case kSpecGxs | kSpecE | kSpecNoise:                                     // up-sampling block
             styled_bwd_prologue_kernel<false, kSpecGxs | kSpecE | kSpecNoise, 4><<<nb, kThreads, 0, st>>>(p); break;
         case kSpecGxs | kSpecE | kSpecNoise | kSpecD:                            // plain block without ToRGB
