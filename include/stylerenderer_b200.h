@@ -412,6 +412,11 @@ typedef struct sr_weight_prep_item {
 int sr_conv_weight_prep_multi_tf32(const sr_weight_prep_item *items, int n, void *stream);
 int sr_conv_weight_prep_multi_bf16(const sr_weight_prep_item *items, int n, void *stream);
 int sr_weight_sq_backward_multi_f32(const sr_weight_prep_item *items, int n, void *stream);
+/* out = (a + b) * scale over n fp32 elements (n % 4 == 0) and, when `operand` is not NULL, the GEMM-operand copy of out
+ * (tf32-rounded fp32 / bfloat16) in the same pass: the residual sum `(out + skip) / sqrt(2)` of a Discriminator ResBlock
+ * (reference layers.py:386-391) together with the operand conversion of the next block's first convolution. */
+int sr_residual_combine_tf32(float *out, float *operand, const float *a, const float *b, float scale, int64_t n, void *stream);
+int sr_residual_combine_bf16(float *out, void *operand, const float *a, const float *b, float scale, int64_t n, void *stream);
 /* The style-map network of GeneratorWithMap -- ResBlock(3 -> cout, downsample = False), cout = 2 or 4 (reference
  * model.py:194-216 builds them, model.py:262,271-275 runs them on the rasterised normal map of every resolution; the block
  * is reference layers.py:379-391 over the ConvLayers of layers.py:341-378) -- as ONE pass over [batch, 3, h, w] planes:

@@ -70,6 +70,8 @@ _SIGNATURES = {
     "sr_conv_weight_prep_multi_tf32": (_I, [_P, _I, _P]),
     "sr_conv_weight_prep_multi_bf16": (_I, [_P, _I, _P]),
     "sr_weight_sq_backward_multi_f32": (_I, [_P, _I, _P]),
+    "sr_residual_combine_tf32": (_I, [_P, _P, _P, _P, _F, _L, _P]),
+    "sr_residual_combine_bf16": (_I, [_P, _P, _P, _P, _F, _L, _P]),
     "sr_small_conv_f32": (_I, [_P, _P, _P, _L, _I, _I, _I, _L, _L, _P]),
     "sr_small_conv_wgrad_f32": (_I, [_P, _P, _P, _L, _I, _I, _I, _L, _L, _P]),
     "sr_stem_conv_forward_f32": (_I, [_P] * 5 + [_L, _I, _L, _L, _L, _I, _F, _F, _P]),

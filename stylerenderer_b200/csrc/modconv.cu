@@ -1409,6 +1409,25 @@ modulate_tf32_kernel(float *__restrict__ xs, const float *__restrict__ x, const 
     }
 }
 
+// out = (a + b) * scale (fp32) and, optionally, its GEMM-operand copy (tf32-rounded fp32 or bfloat16) in one pass: the
+// residual sum of a Discriminator ResBlock (reference layers.py:390) feeding the next block's first conv
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+residual_combine_kernel(float *__restrict__ out, float *__restrict__ op, const float *__restrict__ a, const float *__restrict__ b,
+                        float scale, uint32_t n4)
+{
+    const uint32_t stride = gridDim.x * 256;
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n4; i += stride) {
+        const float4 u = ld_stream4(a + 4ull * i), v = ld_stream4(b + 4ull * i);
+        const float4 o = make_float4((u.x + v.x) * scale, (u.y + v.y) * scale, (u.z + v.z) * scale, (u.w + v.w) * scale);
+        *reinterpret_cast<float4 *>(out + 4ull * i) = o;
+        if (op) {
+            if (BF16) reinterpret_cast<uint2 *>(op)[i] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+            else *reinterpret_cast<float4 *>(op + 4ull * i) = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
+        }
+    }
+}
+
 // Weight re-layout: reference [cout, cin, kh, kw] -> GEMM B operand [rows][taps][cols], scaled and rounded to tf32.
 //   transpose = 0: rows = cout, cols = cin, tap t = ky*kw + kx                         (forward)
 //   transpose = 1: rows = cin, cols = cout, tap t = (kh-1-ky)*kw + (kw-1-kx)           (dgrad of the plain conv)
@@ -2169,4 +2188,31 @@ extern "C" int sr_weight_sq_backward_multi_f32(const sr_weight_prep_item *items,
     weight_sq_backward_multi_kernel<<<dim3(kNumSMs * 2, n), 256, 0, (cudaStream_t)stream>>>(tab);
     count_launch();
     return check_launch("sr_weight_sq_backward_multi_f32");
+}
+
+static int residual_combine_any(float *out, float *op, const float *a, const float *b, float scale, int64_t n, void *stream, bool bf16)
+{
+    SR_REQUIRE(out && a && b && n >= 0 && n % 4 == 0, "residual_combine: bad arguments (element count must be a multiple of 4)");
+    SR_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(op) | reinterpret_cast<uintptr_t>(a) |
+                 reinterpret_cast<uintptr_t>(b)) & 15) == 0, "residual_combine: 16-byte alignment required");
+    const int64_t n4 = n / 4;
+    if (n4 == 0) return SR_OK;
+    SR_REQUIRE(n4 < 0x7fffffffll, "residual_combine: tensor too large");
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    if (bf16) residual_combine_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(out, op, a, b, scale, (uint32_t)n4);
+    else residual_combine_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(out, op, a, b, scale, (uint32_t)n4);
+    count_launch();
+    return check_launch("sr_residual_combine");
+}
+
+extern "C" int sr_residual_combine_tf32(float *out, float *operand, const float *a, const float *b, float scale, int64_t n,
+                                        void *stream)
+{
+    return residual_combine_any(out, operand, a, b, scale, n, stream, false);
+}
+extern "C" int sr_residual_combine_bf16(float *out, void *operand, const float *a, const float *b, float scale, int64_t n,
+                                        void *stream)
+{
+    return residual_combine_any(out, reinterpret_cast<float *>(operand), a, b, scale, n, stream, true);
 }

@@ -370,6 +370,54 @@ def _ones(b, c, device):
 TAPS_S2 = [(ky, kx, ky * 3 + kx) for ky in range(3) for kx in range(3)]
 
 
+def _operand_of(x, x_nhwc):
+    """The GEMM operand of an activation: the copy its producer already wrote (ResidualCombine tags its output with it), or
+    one operand pass (sr_modulate_*)."""
+    tag = getattr(x, "_sr_operand", None)
+    if tag is not None and tag[0] == tc.get_precision() and tag[1].shape == x_nhwc.shape and tag[1].device == x_nhwc.device:
+        return tag[1]
+    return tc.modulate(x_nhwc)
+
+
+class ResidualCombine(Function):
+    """(a + b) * scale on channels-last activations in one pass, with the GEMM-operand copy of the result for the next
+    convolution (sr_residual_combine_*): the tail of the Discriminator's ResBlock (reference layers.py:386-391)."""
+
+    @staticmethod
+    def forward(ctx, a, b, scale):
+        a_n, b_n = to_nhwc(a), to_nhwc(b)
+        out = torch.empty_like(a_n)
+        op = tc.operand_like(a_n)
+        fn = _lib.lib().sr_residual_combine_bf16 if tc._bf16() else _lib.lib().sr_residual_combine_tf32
+        with torch.cuda.device(a.device):
+            rc = fn(_lib.ptr(out), _lib.ptr(op), _lib.ptr(a_n), _lib.ptr(b_n), float(scale), a_n.numel(), _lib.stream_of(a_n))
+        _lib.check(rc, "sr_residual_combine")
+        ctx.scale = float(scale)
+        y = from_nhwc(out)
+        ctx.mark_non_differentiable(op)
+        return y, op
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g, _gop):
+        gs = g * ctx.scale
+        return gs, gs, None
+
+
+def residual_combine_supported(a, b):
+    import os
+    from .layers import double_backward_requested
+    return (os.environ.get("SR_RES_COMBINE", "1") != "0" and a.is_cuda and a.dtype == torch.float32 and a.shape == b.shape
+            and a.dim() == 4 and a.shape[1] % 4 == 0 and not tc._exact()
+            and not (torch.is_grad_enabled() and double_backward_requested()))
+
+
+def residual_combine(a, b, scale):
+    y, op = ResidualCombine.apply(a, b, scale)
+    y._sr_operand = (tc.get_precision(), op)          # read by _operand_of in the next block's first convolution
+    return y
+
+
 class PlainConvTC(Function):
     """EqualConv2d (+ FusedLeakyReLU) of the Discriminator / ConvLayer stack (reference layers.py:204-221, 341-378) on the
     tensor-core kernels: kind 's1' = 3x3 stride 1 pad 1, 's2' = 3x3 stride 2 pad 0 (after the Blur), 'p2' = 1x1 stride 2.
@@ -379,7 +427,7 @@ class PlainConvTC(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, scale, kind, alpha, gain):
         x_nhwc = to_nhwc(x)
-        return from_nhwc(_plain_conv_forward(ctx, tc.modulate(x_nhwc), weight, bias, scale, kind, alpha, gain))
+        return from_nhwc(_plain_conv_forward(ctx, _operand_of(x, x_nhwc), weight, bias, scale, kind, alpha, gain))
 
     @staticmethod
     @once_differentiable

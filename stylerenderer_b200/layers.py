@@ -349,5 +349,9 @@ class ResBlock(nn.Module):                            # reference layers.py:379-
             from . import fused
             if fused.stylemap_resblock_supported(self, input):
                 return fused.stylemap_resblock(self, input)
-        out = self.conv2(self.conv1(input))
-        return (out + self.skip(input)) / math.sqrt(2)
+        out, skip = self.conv2(self.conv1(input)), self.skip(input)
+        if _CONFIG["conv_backend"] == "tcgen05" and out.is_cuda and out.shape[1] % 128 == 0:
+            from . import fused
+            if fused.residual_combine_supported(out, skip):       # one pass: residual sum + the next conv's GEMM operand
+                return fused.residual_combine(out, skip, 1 / math.sqrt(2))
+        return (out + skip) / math.sqrt(2)
