@@ -225,15 +225,17 @@ extern "C" int sr_stem_conv_backward_f32(float *grads, float *dx, const float *g
     if (cudaMemsetAsync(grads, 0, sizeof(float) * cout * 4, st) != cudaSuccess) return check_launch("stem_conv_backward (memset)");
     const size_t smem = sizeof(float) * (NT / 32) * cout * 4;
     const int grid = (int)(g.pixels < 4ll * kNumSMs * 8 ? (g.pixels + 7) / 8 : 4ll * kNumSMs);
-    if (dx) {
-        static bool conf = false;
-        if (!conf && smem > 48 * 1024) { cudaFuncSetAttribute(stem_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); conf = true; }
-        stem_bwd_kernel<true><<<grid, NT, smem, st>>>(grads, dx, gy, x, w, b_conv, b_act, g);
-    } else {
-        static bool conf = false;
-        if (!conf && smem > 48 * 1024) { cudaFuncSetAttribute(stem_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); conf = true; }
-        stem_bwd_kernel<false><<<grid, NT, smem, st>>>(grads, dx, gy, x, w, b_conv, b_act, g);
+    // dynamic shared memory: 8 warps x [C x 4] partials = 16 KB at C = 128, 128 KB at the largest supported C = 1024
+    constexpr int kMaxSmem = (NT / 32) * 1024 * 4 * (int)sizeof(float);
+    static bool conf = false;
+    if (!conf) {
+        if (cudaFuncSetAttribute(stem_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess ||
+            cudaFuncSetAttribute(stem_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess)
+            return check_launch("stem_conv_backward (shared memory)");
+        conf = true;
     }
+    if (dx) stem_bwd_kernel<true><<<grid, NT, smem, st>>>(grads, dx, gy, x, w, b_conv, b_act, g);
+    else stem_bwd_kernel<false><<<grid, NT, smem, st>>>(grads, dx, gy, x, w, b_conv, b_act, g);
     count_launch();
     return check_launch("stem_conv_backward");
 }
