@@ -51,3 +51,30 @@ def test_fused_leaky_relu_cpu_slope_quirk_and_module():
     y = m(x.requires_grad_(True))
     y.sum().backward()
     assert m.bias.grad is not None and x.grad is not None
+
+
+def test_tensor_core_backend_leaves_cpu_tensors_on_the_composed_path():
+    """With conv_backend = "tcgen05" selected (as a GPU job would), modules fed CPU tensors must take the composed torch ops:
+    every fused dispatcher of the package (style-map ResBlock kernel, small-channel conv pair, Discriminator stem, blur ->
+    operand, residual combine, tensor-core ConvLayers) gates on `is_cuda`.  Same outputs and gradients as the "cudnn" backend."""
+    from stylerenderer_b200 import model as M
+    torch.manual_seed(5)
+    nets = [L.ResBlock(3, 4, downsample=False), L.ConvLayer(3, 128, 1), L.ResBlock(128, 128), M.Discriminator(16)]
+    xs = [torch.randn(2, 3, 9, 9), torch.randn(2, 3, 8, 8), torch.randn(1, 128, 8, 8), torch.randn(2, 3, 16, 16)]
+    old = L.get_conv_backend()
+    try:
+        for net, x in zip(nets, xs):
+            res = {}
+            for backend in ("cudnn", "tcgen05"):
+                L.set_conv_backend(backend)
+                net.zero_grad()
+                xx = x.clone().requires_grad_(True)
+                y = net(xx)
+                y.square().mean().backward()
+                res[backend] = (y.detach(), xx.grad, [p.grad.clone() for p in net.parameters()])
+            torch.testing.assert_close(res["tcgen05"][0], res["cudnn"][0], rtol=0, atol=0)
+            torch.testing.assert_close(res["tcgen05"][1], res["cudnn"][1], rtol=0, atol=0)
+            for a, b in zip(res["tcgen05"][2], res["cudnn"][2]):
+                torch.testing.assert_close(a, b, rtol=0, atol=0)
+    finally:
+        L.set_conv_backend(old)
